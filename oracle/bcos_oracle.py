@@ -1,0 +1,369 @@
+"""CPU oracle for the B-cos forward + dynamic-linear explanation path.
+
+TEST INFRASTRUCTURE.  This file restates, in plain fp32 PyTorch on the CPU, the arithmetic of the
+reference's hot path (shrebox/B-cosification).  Only `tests/`, `__graft_entry__.smoke()` and the
+`cpu_baseline` / `--impl reference` legs of `bench.py` may import it - it is the checker, never
+the product: nothing under `b-cosification_b200/` imports this module and the product path raises
+when its CUDA library is missing.
+
+Parity status: the reference ships NO tests or golden vectors for this path, so
+the oracle is pinned against the reference *itself*: `oracle/make_golden.py` imports the reference
+modules read-only in the build container (oracle/refload.py), feeds both the same synthetic
+state-dict and images, asserts agreement and writes `tests/golden/*.npz`.  `tests/test_oracle_*.py`
+re-check the oracle against those committed vectors everywhere and against the live reference
+where /root/reference exists.
+
+Every function cites the reference lines it follows (paths relative to the reference root).
+The arithmetic lives in ATen (torch==2.2.1 pinned by the reference, requirements.txt:83); the
+container's torch 2.11 runs the same calls.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+IMAGENET_MEAN_ADDINVERSE = (0.485, 0.456, 0.406, 0.515, 0.544, 0.594)  # bcosify.py:14
+IMAGENET_STD_ADDINVERSE = (0.229, 0.224, 0.225, 0.229, 0.224, 0.225)  # bcosify.py:15
+CLIP_MEAN_ADDINVERSE = (0.48145466, 0.4578275, 0.40821073, 0.51854534, 0.5421725, 0.59178927)  # bcosify.py:17
+CLIP_STD_ADDINVERSE = (0.26862954, 0.26130258, 0.27577711, 0.26862954, 0.26130258, 0.27577711)  # bcosify.py:19
+LOGIT_BIAS_1000 = -math.log(1000 - 1)  # bcosify.py:31
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+# ----------------------------------------------------------------------------------------------
+# B-cos conv / linear  (bcos/modules/bcosconv2d.py, bcosifyconv2d.py, bcoslinear.py, bcosifylinear.py)
+# ----------------------------------------------------------------------------------------------
+def patch_norms(x: Tensor, kernel_size, stride, padding, groups: int = 1, out_channels: Optional[int] = None) -> Tensor:
+    """bcosconv2d.py:196-231 `calc_patch_norms`: sqrt(sumpool_k,s,p(sum_c x^2) + 1e-6)."""
+    sq = x * x
+    if groups == 1:
+        sq = sq.sum(1, keepdim=True)
+    else:
+        sq = sq.unflatten(1, (groups, x.shape[1] // groups)).sum(2)
+    n = (F.avg_pool2d(sq, _pair(kernel_size), padding=_pair(padding), stride=_pair(stride), divisor_override=1) + 1e-6).sqrt()
+    if groups > 1:
+        n = torch.repeat_interleave(n, repeats=out_channels // groups, dim=1)
+    return n
+
+
+def patch_norms_slow(x: Tensor, weight: Tensor, stride, padding, dilation, groups) -> Tensor:
+    """bcosconv2d.py:233-250 `_calc_patch_norms_slow` (ones-kernel conv; the in-code cross-check)."""
+    return (F.conv2d(x * x, torch.ones_like(weight), None, stride, padding, dilation, groups) + 1e-6).sqrt()
+
+
+def normed_weight(weight: Tensor) -> Tensor:
+    """bcosconv2d.py:26-35 `NormedConv2d` / bcoslinear.py:20-27 `NormedLinear`: unit L2 norm per output unit."""
+    dims = tuple(range(1, weight.dim()))
+    return weight / torch.linalg.vector_norm(weight, dim=dims, keepdim=True)
+
+
+def _maxout(out: Tensor, max_out: int, dim: int) -> Tensor:
+    """bcosconv2d.py:166-170: channel c = o*M + m, max over m."""
+    if max_out > 1:
+        out = out.unflatten(dim, (out.shape[dim] // max_out, max_out)).max(dim=dim + 1 if dim >= 0 else dim).values
+    return out
+
+
+def _bcos_scale(lin: Tensor, norm: Tensor, b: float, detach: bool) -> Tensor:
+    """bcosconv2d.py:181-193: b==2 -> |lin|/norm ; else (|lin/norm| + 1e-6)^(b-1); detached in explanation mode."""
+    l, n = (lin.detach(), norm.detach()) if detach else (lin, norm)
+    if b == 2:
+        return l.abs() / n
+    return ((l / n).abs() + 1e-6).pow(b - 1)
+
+
+def bcos_conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, stride=1, padding=0, dilation=1,
+                groups: int = 1, b: float = 2, max_out: int = 1, detach: bool = False,
+                normalize_weight: bool = False) -> Tensor:
+    """`BcosConv2d.forward_impl` bcosconv2d.py:153-194 (normalize_weight=True, NormedConv2d) and
+    `BcosifyConv2d.forward_impl` bcosifyconv2d.py:50-102 (normalize_weight=False, plain nn.Conv2d)."""
+    w = normed_weight(weight) if normalize_weight else weight
+    lin = F.conv2d(x, w, bias, _pair(stride), _pair(padding), _pair(dilation), groups)
+    lin = _maxout(lin, max_out, 1)
+    if b == 1:
+        return lin
+    if _pair(dilation) != (1, 1):
+        assert max_out == 1
+        norm = patch_norms_slow(x, weight, stride, padding, dilation, groups)
+    else:
+        norm = patch_norms(x, weight.shape[2:], stride, padding, groups, lin.shape[1])
+    return _bcos_scale(lin, norm, b, detach) * lin
+
+
+def bcos_linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, b: float = 2, max_out: int = 1,
+                detach: bool = False, normalize_weight: bool = False) -> Tensor:
+    """`BcosLinear.forward` bcoslinear.py:88-130 / `BcosifyLinear.forward` bcosifylinear.py:42-95.
+    NB the eps sits OUTSIDE the sqrt here: norm = ||x||_2 + 1e-12 (bcoslinear.py:113)."""
+    w = normed_weight(weight) if normalize_weight else weight
+    lin = F.linear(x, w, bias)
+    lin = _maxout(lin, max_out, -1) if max_out > 1 else lin
+    if b == 1:
+        return lin
+    norm = torch.linalg.vector_norm(x, dim=-1, keepdim=True) + 1e-12
+    return _bcos_scale(lin, norm, b, detach) * lin
+
+
+# ----------------------------------------------------------------------------------------------
+# norms / small layers
+# ----------------------------------------------------------------------------------------------
+def batch_norm_uncentered_2d(x: Tensor, running_var: Optional[Tensor], weight: Optional[Tensor] = None,
+                             bias: Optional[Tensor] = None, training: bool = False, momentum: float = 0.1,
+                             eps: float = 1e-5, detach: bool = False) -> Tensor:
+    """bcos/modules/norms/uncentered_norms/batchnorm_uncentered.py:21-60."""
+    if training:
+        xs = x.detach() if detach else x
+        var = xs.var(dim=(0, 2, 3), unbiased=False)  # centred, biased variance of an uncentred signal (:39)
+        if running_var is not None:
+            running_var.copy_((1 - momentum) * running_var + momentum * var.detach())  # (:43)
+    else:
+        var = running_var
+    y = x / (var + eps).sqrt()[None, :, None, None]
+    if weight is not None:
+        y = weight[None, :, None, None] * y
+    if bias is not None:
+        y = y + bias[None, :, None, None]
+    return y.type(x.dtype)
+
+
+def bn_uncentered_from_standard(weight, bias, running_mean, running_var, eps) -> Tuple[Tensor, Optional[Tensor]]:
+    """`BatchNormUncentered2d.from_standard_module` batchnorm_uncentered.py:118-141 ("BnUncV2" fold)."""
+    if bias is None:
+        return weight, None
+    std = (running_var + eps).sqrt()
+    return weight, bias - (running_mean / std) * weight
+
+
+def layer_norm_detachable(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], eps: float = 1e-5,
+                          detach: bool = False) -> Tensor:
+    """`DetachableLayerNorm.forward` bcos/modules/norms/centered_norms.py:187-224: mean stays in-graph,
+    only the variance is detached in explanation mode; otherwise stock F.layer_norm."""
+    if not detach:
+        return F.layer_norm(x, x.shape[-1:], weight, bias, eps)
+    var, mean = torch.var_mean(x, dim=-1, unbiased=False, keepdim=True)
+    std = (var + eps).sqrt().detach()
+    y = (x - mean) / std
+    if weight is not None:
+        y = weight * y
+    if bias is not None:
+        y = y + bias
+    return y
+
+
+def gelu_detachable(x: Tensor, detach: bool = False) -> Tensor:
+    """`MyGELU` bcosify_vit.py:27-32: gate = 0.5*(1+erf(x/sqrt2)) (detached in explanation mode) * x."""
+    gate = 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+    if detach:
+        gate = gate.detach()
+    return gate * x
+
+
+def logit_layer(x: Tensor, logit_temperature: Optional[float] = None, logit_bias: Optional[float] = None) -> Tensor:
+    """bcos/modules/logitlayer.py:22-27."""
+    if logit_temperature is not None:
+        x = x / logit_temperature
+    if logit_bias is not None:
+        x = x + logit_bias
+    return x
+
+
+def normalize6(x: Tensor, mean: Sequence[float] = IMAGENET_MEAN_ADDINVERSE,
+               std: Sequence[float] = IMAGENET_STD_ADDINVERSE) -> Tensor:
+    """`BcosifyNetwork.forward` bcosify.py:50-53 -> torchvision Normalize on the 6-channel [x, 1-x] input."""
+    m = torch.tensor(mean, dtype=x.dtype).view(1, -1, 1, 1)
+    s = torch.tensor(std, dtype=x.dtype).view(1, -1, 1, 1)
+    return (x - m) / s
+
+
+def add_channels_conv(weight3: Tensor) -> Tensor:
+    """`BcosifyNetwork.add_channels` bcosify.py:55-72: stem weight cat(W, -W)/2 along C_in."""
+    return torch.cat((weight3, -weight3), dim=1) / 2
+
+
+# ----------------------------------------------------------------------------------------------
+# B-cosified ResNet (torchvision skeleton; bcos/models/standard_models.py:36-54 ResNetBcos:
+# classifier applied per position BEFORE global average pooling; maxpool -> AvgPool2d(3,2,1),
+# bcos/experiments/ImageNet/bcosification/model.py:47-49; all biases None :53-55)
+# ----------------------------------------------------------------------------------------------
+RESNET_ARCH = {
+    "resnet18": ("basic", [2, 2, 2, 2]),
+    "resnet34": ("basic", [3, 4, 6, 3]),
+    "resnet50": ("bottleneck", [3, 4, 6, 3]),
+    "resnet101": ("bottleneck", [3, 4, 23, 3]),
+}
+
+
+def resnet_state_shapes(arch: str, num_classes: int = 1000) -> Dict[str, Tuple[int, ...]]:
+    """State-dict keys/shapes of `BcosifyNetwork(ResNetBcos(...))` after biases are stripped (probe: SURVEY.md section 5)."""
+    kind, layers = RESNET_ARCH[arch]
+    exp = 1 if kind == "basic" else 4
+    shapes: Dict[str, Tuple[int, ...]] = {}
+
+    def bn(prefix, c):
+        shapes[prefix + ".weight"] = (c,)
+        shapes[prefix + ".running_mean"] = (c,)
+        shapes[prefix + ".running_var"] = (c,)
+        shapes[prefix + ".num_batches_tracked"] = ()
+
+    shapes["model.conv1.linear.weight"] = (64, 6, 7, 7)
+    bn("model.bn1", 64)
+    inplanes = 64
+    for li, (planes, nblocks) in enumerate(zip([64, 128, 256, 512], layers), start=1):
+        for bi in range(nblocks):
+            stride = 2 if (li > 1 and bi == 0) else 1
+            p = f"model.layer{li}.{bi}"
+            if kind == "basic":
+                shapes[p + ".conv1.linear.weight"] = (planes, inplanes, 3, 3)
+                bn(p + ".bn1", planes)
+                shapes[p + ".conv2.linear.weight"] = (planes, planes, 3, 3)
+                bn(p + ".bn2", planes)
+            else:
+                shapes[p + ".conv1.linear.weight"] = (planes, inplanes, 1, 1)
+                bn(p + ".bn1", planes)
+                shapes[p + ".conv2.linear.weight"] = (planes, planes, 3, 3)
+                bn(p + ".bn2", planes)
+                shapes[p + ".conv3.linear.weight"] = (planes * 4, planes, 1, 1)
+                bn(p + ".bn3", planes * 4)
+            if stride != 1 or inplanes != planes * exp:
+                shapes[p + ".downsample.0.linear.weight"] = (planes * exp, inplanes, 1, 1)
+                bn(p + ".downsample.1", planes * exp)
+            inplanes = planes * exp
+    shapes["model.fc.linear.weight"] = (num_classes, 512 * exp, 1, 1)
+    return shapes
+
+
+class OracleResNet:
+    """Functional B-cosified ResNet over a reference-keyed state dict."""
+
+    def __init__(self, arch: str, sd: Dict[str, Tensor], b: float = 2, eps: float = 1e-5,
+                 mean=IMAGENET_MEAN_ADDINVERSE, std=IMAGENET_STD_ADDINVERSE, logit_bias: Optional[float] = LOGIT_BIAS_1000):
+        self.arch, self.sd, self.b, self.eps = arch, sd, b, eps
+        self.kind, self.layers = RESNET_ARCH[arch]
+        self.mean, self.std, self.logit_bias = mean, std, logit_bias
+        self.training = False  # True => BN uses batch statistics and updates running_var
+        self.momentum = 0.1
+        self.taps: Optional[Dict[str, Tensor]] = None  # set to {} to record intermediate activations
+
+    # --- building blocks -------------------------------------------------------------------
+    def _conv(self, name, x, stride, padding, detach):
+        return bcos_conv2d(x, self.sd[name + ".linear.weight"], self.sd.get(name + ".linear.bias"), stride, padding,
+                           b=self.b, detach=detach)
+
+    def _bn(self, name, x, detach):
+        return batch_norm_uncentered_2d(x, self.sd[name + ".running_var"], self.sd.get(name + ".weight"),
+                                        self.sd.get(name + ".bias"), self.training, self.momentum, self.eps, detach)
+
+    def _tap(self, name, t):
+        if self.taps is not None:
+            self.taps[name] = t.detach()
+
+    def _block(self, p, x, stride, detach):
+        identity = x
+        if self.kind == "basic":  # torchvision BasicBlock: stride on conv1
+            out = F.relu(self._bn(p + ".bn1", self._conv(p + ".conv1", x, stride, 1, detach), detach))
+            out = self._bn(p + ".bn2", self._conv(p + ".conv2", out, 1, 1, detach), detach)
+        else:  # torchvision Bottleneck v1.5: stride on the 3x3
+            out = F.relu(self._bn(p + ".bn1", self._conv(p + ".conv1", x, 1, 0, detach), detach))
+            out = F.relu(self._bn(p + ".bn2", self._conv(p + ".conv2", out, stride, 1, detach), detach))
+            out = self._bn(p + ".bn3", self._conv(p + ".conv3", out, 1, 0, detach), detach)
+        if (p + ".downsample.0.linear.weight") in self.sd:
+            identity = self._bn(p + ".downsample.1", self._conv(p + ".downsample.0", x, stride, 0, detach), detach)
+        out = F.relu(out + identity)
+        self._tap(p, out)
+        return out
+
+    def forward(self, x6: Tensor, detach: bool = False) -> Tensor:
+        """x6: [B,6,H,W] un-normalised `[x, 1-x]`.  Returns logits [B, classes]."""
+        x = normalize6(x6, self.mean, self.std)
+        x = F.relu(self._bn("model.bn1", self._conv("model.conv1", x, 2, 3, detach), detach))
+        self._tap("stem", x)
+        x = F.avg_pool2d(x, 3, 2, 1)
+        for li, nblocks in enumerate(self.layers, start=1):
+            for bi in range(nblocks):
+                x = self._block(f"model.layer{li}.{bi}", x, 2 if (li > 1 and bi == 0) else 1, detach)
+        x = self._conv("model.fc", x, 1, 0, detach)  # classifier before GAP (standard_models.py:50-52)
+        self._tap("fc", x)
+        x = F.adaptive_avg_pool2d(x, 1).flatten(1)
+        return logit_layer(x, None, self.logit_bias)
+
+    __call__ = forward
+
+    def calibrate_bn(self, x6: Tensor) -> None:
+        """one train-mode forward with momentum=1.0 so running_var := batch variance."""
+        self.training, self.momentum = True, 1.0
+        with torch.no_grad():
+            self.forward(x6)
+        self.training, self.momentum = False, 0.1
+
+
+# ----------------------------------------------------------------------------------------------
+# explanation  (bcos/common.py:92-188 `BcosUtilMixin.explain`, batched form SURVEY.md A.4)
+# ----------------------------------------------------------------------------------------------
+def explain_batched(forward: Callable[..., Tensor], x6: Tensor, idx: Optional[Tensor] = None,
+                    seed_grad: Optional[Tensor] = None) -> Dict[str, Tensor]:
+    """fwd under explanation mode (detach=True) -> out.max(1) (or `idx`, or an arbitrary output
+    gradient `seed_grad`) -> backward(inputs=[x]) -> dynamic linear weights = x.grad,
+    contribution_map = (x * x.grad).sum(1)   (bcos/common.py:163-181).
+    Images are independent in eval mode, so one batched backward of the summed logits equals the
+    per-sample `model.explain` loop."""
+    xb = x6.clone().requires_grad_(True)
+    with torch.enable_grad():
+        out = forward(xb, detach=True)
+        if seed_grad is not None:
+            target = (out * seed_grad).sum()
+            pred = out.argmax(1)
+        else:
+            pred = out.argmax(1)
+            sel = pred if idx is None else idx
+            target = out.gather(1, sel.view(-1, 1)).sum()
+        (grad,) = torch.autograd.grad(target, [xb])
+    return {
+        "logits": out.detach(),
+        "prediction": pred,
+        "dynamic_linear_weights": grad,
+        "contribution_map": (x6 * grad).sum(1),
+    }
+
+
+def gradient_to_image(image: Tensor, linear_mapping: Tensor, smooth: int = 15, alpha_percentile: float = 99.5) -> Tensor:
+    """`gradient_to_image` bcos/common.py:387-436 -> RGBA [H,W,4] (torch, no numpy/matplotlib)."""
+    contribs = (image * linear_mapping).sum(0, keepdim=True)[0]
+    rgb_grad = linear_mapping / (linear_mapping.abs().max(0, keepdim=True).values + 1e-12)
+    rgb_grad = rgb_grad.clamp(min=0)
+    rgb_grad = rgb_grad[:3] / (rgb_grad[:3] + rgb_grad[3:] + 1e-12)
+    alpha = linear_mapping.norm(p=2, dim=0, keepdim=True)
+    alpha = torch.where(contribs[None] < 0, torch.zeros_like(alpha) + 1e-12, alpha)
+    if smooth:
+        alpha = F.avg_pool2d(alpha, smooth, stride=1, padding=(smooth - 1) // 2)
+    alpha = alpha / torch.quantile(alpha.flatten(), q=alpha_percentile / 100)
+    alpha = alpha.clamp(0, 1)
+    rgb_grad = torch.cat([rgb_grad, alpha], dim=0)
+    return rgb_grad.permute(1, 2, 0)
+
+
+# ----------------------------------------------------------------------------------------------
+# parity metrics (BASELINE.json north_star tolerances)
+# ----------------------------------------------------------------------------------------------
+def parity_metrics(logits: Tensor, maps: Tensor, ref_logits: Tensor, ref_maps: Tensor,
+                   logit_bias: float = LOGIT_BIAS_1000) -> Dict[str, float]:
+    """argmax equality, logit relative error, per-image map cosine and max-abs / range."""
+    logits, maps, ref_logits, ref_maps = (t.detach().double().cpu() for t in (logits, maps, ref_logits, ref_maps))
+    rel = ((logits - ref_logits).abs().max() / ref_logits.abs().max()).item()
+    rel_nb = ((logits - ref_logits).abs().max() / (ref_logits - logit_bias).abs().max()).item()
+    a, r = maps.flatten(1), ref_maps.flatten(1)
+    cos = F.cosine_similarity(a, r, dim=1)
+    rng = (r.max(1).values - r.min(1).values)
+    mar = ((a - r).abs().max(1).values / rng)
+    return {
+        "argmax_equal": bool((logits.argmax(1) == ref_logits.argmax(1)).all()),
+        "logit_rel_err": rel,
+        "logit_rel_err_vs_unbiased": rel_nb,
+        "map_cos_min": cos.min().item(),
+        "map_maxabs_over_range": mar.max().item(),
+    }

@@ -1,0 +1,269 @@
+"""Generate tests/golden/*.npz from the REFERENCE ITSELF (build container only).
+
+TEST INFRASTRUCTURE.  Imports shrebox/B-cosification read-only through oracle/refload.py, builds the
+reference models offline (weights=None; mirrors bcos/experiments/ImageNet/bcosification/model.py:15-57
+and experiment_parameters.py:82-129), loads the synthetic state dict from
+`bcos_b200.utils.synth`, calibrates BN, runs forward + batched explanation
+ and stores inputs / calibrated BN variances / logits / contribution maps.
+While doing so it asserts that oracle/bcos_oracle.py reproduces the reference, i.e. it PINS the oracle.
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py [--only resnet18,resnet50,modules]
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import refload  # noqa: E402
+import bcos_oracle as O  # noqa: E402
+from bcos_b200.utils import synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def build_reference_resnet(arch: str):
+    refload.load()
+    import bcosify
+    from bcos.models.standard_models import ResNetBcos
+    from torchvision.models.resnet import BasicBlock, Bottleneck
+
+    kind, layers = O.RESNET_ARCH[arch]
+    cfg = dict(is_bcos=True, name=arch, last_layer_name="fc", weights=None, bcos_args=dict(b=2, max_out=1),
+               bcosify_args=dict(fix_b=True, use_bias=False, norm_layer="BnUncV2", manual_optim=False, gap=True,
+                                 act_layer=True))
+    tv = ResNetBcos(BasicBlock if kind == "basic" else Bottleneck, layers)
+    m = bcosify.BcosifyNetwork(tv, cfg, add_channels=True, logit_layer=True)
+    m.model.maxpool = nn.AvgPool2d(3, 2, 1)
+    for mod in m.modules():
+        if hasattr(mod, "bias") and mod.bias is not None:
+            mod.bias = None
+    return m
+
+
+def reference_calibrate(m, x6):
+    m.train()
+    for b in m.modules():
+        if isinstance(b, nn.BatchNorm2d):
+            b.momentum = 1.0
+    with torch.no_grad():
+        m(x6)
+    for b in m.modules():
+        if isinstance(b, nn.BatchNorm2d):
+            b.momentum = 0.1
+    m.eval()
+
+
+def reference_explain_batched(m, x6):
+    xb = x6.clone().requires_grad_(True)
+    with torch.enable_grad(), m.explanation_mode():
+        out = m(xb)
+        out.max(1).values.sum().backward(inputs=[xb])
+    return out.detach(), xb.grad.detach(), (xb * xb.grad).sum(1).detach()
+
+
+def golden_resnet(arch: str, batch: int, seed: int = 0):
+    t0 = time.time()
+    torch.manual_seed(0)
+    m = build_reference_resnet(arch)
+    ref_shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert ref_shapes == O.resnet_state_shapes(arch), "oracle key/shape table differs from the reference state dict"
+    sd = synth.synth_state_dict(ref_shapes, seed)
+    m.load_state_dict(sd, strict=True)
+    u8 = synth.synth_images_u8(batch, 224, seed)
+    x6 = synth.to_bcos_input(u8)
+    reference_calibrate(m, x6)
+
+    # plain eval forward + the official per-sample explain on image 0
+    with torch.inference_mode():
+        logits_fwd = m(x6)
+    logits, grad, cmap = reference_explain_batched(m, x6)
+    assert torch.equal(logits, logits_fwd)
+    e0 = m.explain(x6[:1].clone().requires_grad_(True))
+    assert torch.allclose(e0["contribution_map"], cmap[:1], rtol=1e-4, atol=1e-9), "batched explain != model.explain"
+
+    # ---- pin the oracle against the reference ----
+    osd = {k: v.clone() for k, v in sd.items()}
+    om = O.OracleResNet(arch, osd)
+    om.calibrate_bn(x6)
+    cal = {k: v for k, v in m.state_dict().items() if k.endswith("running_var")}
+    for k, v in cal.items():
+        assert torch.allclose(osd[k], v, rtol=1e-5, atol=0), k
+        osd[k] = v.clone()  # continue from the reference's exact calibration
+    oe = O.explain_batched(om.forward, x6)
+    pm = O.parity_metrics(oe["logits"], oe["contribution_map"], logits, cmap)
+    print(f"[{arch}] oracle vs reference: {pm}")
+    assert pm["argmax_equal"] and pm["logit_rel_err"] < 1e-5 and pm["map_cos_min"] > 0.99999
+
+    keys = sorted(cal)
+    out = dict(
+        images_u8=u8,
+        bn_keys=np.array(keys),
+        bn_sizes=np.array([cal[k].numel() for k in keys], dtype=np.int64),
+        bn_var=torch.cat([cal[k].flatten() for k in keys]).numpy(),
+        logits=logits.numpy(),
+        contribution_map=cmap.numpy(),
+        grad_absmax=grad.abs().amax(dim=(1, 2, 3)).numpy(),
+        seed=np.int64(seed),
+    )
+    path = os.path.join(GOLD, f"{arch}_b{batch}.npz")
+    np.savez_compressed(path, **out)
+    print(f"[{arch}] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB) in {time.time()-t0:.1f}s; "
+          f"logit std {logits.std():.4f}, pred {logits.argmax(1).tolist()}")
+
+
+def golden_modules(seed: int = 0):
+    """Known-answer vectors for single modules, produced by the reference classes themselves."""
+    refload.load()
+    from bcos.modules.bcosconv2d import BcosConv2d
+    from bcos.modules.bcosifyconv2d import BcosifyConv2d
+    from bcos.modules.bcoslinear import BcosLinear
+    from bcos.modules.bcosifylinear import BcosifyLinear
+    from bcos.modules.norms.uncentered_norms import BatchNormUncentered2d
+    from bcos.modules.norms.centered_norms import DetachableLayerNorm
+    from bcos.modules.logitlayer import LogitLayer
+    import bcosify_vit
+
+    g = torch.Generator().manual_seed(1234 + seed)
+    out = {}
+    conv_cases = [
+        # name, cls, cin, cout, k, s, p, b, max_out, H
+        ("conv_bcosify_3x3", BcosifyConv2d, 16, 32, 3, 1, 1, 2, 1, 12),
+        ("conv_bcosify_3x3_s2", BcosifyConv2d, 16, 32, 3, 2, 1, 2, 1, 13),
+        ("conv_bcosify_1x1", BcosifyConv2d, 64, 24, 1, 1, 0, 2, 1, 7),
+        ("conv_bcosify_1x1_s2", BcosifyConv2d, 32, 16, 1, 2, 0, 2, 1, 8),
+        ("conv_bcosify_7x7_s2", BcosifyConv2d, 6, 16, 7, 2, 3, 2, 1, 20),
+        ("conv_bcos_3x3_normed", BcosConv2d, 8, 16, 3, 1, 1, 2, 1, 9),
+        ("conv_bcos_b1p5", BcosConv2d, 8, 16, 3, 1, 1, 1.5, 1, 9),
+        ("conv_bcos_b2p5_mo2", BcosConv2d, 8, 16, 5, 2, 2, 2.5, 2, 11),
+        ("conv_bcos_b2_mo3", BcosConv2d, 8, 8, 1, 1, 0, 2, 3, 6),
+        ("conv_bcos_b1", BcosConv2d, 8, 8, 3, 1, 1, 1, 1, 6),
+    ]
+    for name, cls, cin, cout, k, s, p, b, mo, H in conv_cases:
+        mod = cls(cin, cout, kernel_size=k, stride=s, padding=p, b=b, max_out=mo)
+        w = torch.randn(mod.linear.weight.shape, generator=g) * 0.2
+        mod.linear.weight.data = w.clone()
+        x = torch.randn(2, cin, H, H, generator=g)
+        y = mod(x)
+        # explanation mode: detached scale, gradient of a fixed random seed
+        seedg = torch.randn(y.shape, generator=g)
+        mod.set_explanation_mode(True)
+        xg = x.clone().requires_grad_(True)
+        ye = mod(xg)
+        (gx,) = torch.autograd.grad((ye * seedg).sum(), [xg])
+        norm = mod.calc_patch_norms(x) if b != 1 else torch.zeros(1)
+        normed = cls is BcosConv2d
+        yo = O.bcos_conv2d(x, w, None, s, p, b=b, max_out=mo, normalize_weight=normed)
+        assert torch.equal(yo, y.detach()), name
+        out.update({f"{name}.w": w, f"{name}.x": x, f"{name}.y": y.detach(), f"{name}.seed": seedg, f"{name}.gx": gx,
+                    f"{name}.norm": norm.detach(),
+                    f"{name}.meta": torch.tensor([cin, cout, k, s, p, b, mo, float(normed)], dtype=torch.float64)})
+
+    lin_cases = [
+        ("lin_bcosify", BcosifyLinear, 48, 40, 2, 1),
+        ("lin_bcos_normed", BcosLinear, 48, 40, 2, 1),
+        ("lin_bcos_b1p5_mo2", BcosLinear, 32, 24, 1.5, 2),
+    ]
+    for name, cls, fin, fout, b, mo in lin_cases:
+        mod = cls(fin, fout, b=b, max_out=mo)
+        w = torch.randn(mod.linear.weight.shape, generator=g) * 0.2
+        mod.linear.weight.data = w.clone()
+        if getattr(mod.linear, "bias", None) is not None:
+            mod.linear.bias = None
+        mod.bias = None
+        x = torch.randn(3, 5, fin, generator=g)
+        y = mod(x)
+        seedg = torch.randn(y.shape, generator=g)
+        mod.set_explanation_mode(True)
+        xg = x.clone().requires_grad_(True)
+        (gx,) = torch.autograd.grad((mod(xg) * seedg).sum(), [xg])
+        normed = cls is BcosLinear
+        yo = O.bcos_linear(x, w, None, b=b, max_out=mo, normalize_weight=normed)
+        assert torch.allclose(yo, y.detach(), rtol=1e-6, atol=1e-7), name
+        out.update({f"{name}.w": w, f"{name}.x": x, f"{name}.y": y.detach(), f"{name}.seed": seedg, f"{name}.gx": gx,
+                    f"{name}.meta": torch.tensor([fin, fout, b, mo, float(normed)], dtype=torch.float64)})
+
+    # BatchNormUncentered2d eval + train + BnUncV2 fold
+    bnu = BatchNormUncentered2d(12)
+    bnu.weight.data = torch.rand(12, generator=g) + 0.5
+    bnu.bias.data = torch.randn(12, generator=g) * 0.1
+    bnu.running_var.data = torch.rand(12, generator=g) + 0.2
+    x = torch.randn(4, 12, 5, 5, generator=g) + 0.3
+    bnu.eval()
+    y_eval = bnu(x)
+    assert torch.equal(O.batch_norm_uncentered_2d(x, bnu.running_var, bnu.weight, bnu.bias), y_eval.detach())
+    rv0 = bnu.running_var.detach().clone()
+    bnu.train()
+    y_train = bnu(x)
+    out.update({"bnu.w": bnu.weight.detach(), "bnu.b": bnu.bias.detach(), "bnu.rv0": rv0, "bnu.x": x,
+                "bnu.y_eval": y_eval.detach(), "bnu.y_train": y_train.detach(), "bnu.rv1": bnu.running_var.detach().clone()})
+    std_bn = nn.BatchNorm2d(12)
+    std_bn.weight.data = torch.rand(12, generator=g) + 0.5
+    std_bn.bias.data = torch.randn(12, generator=g)
+    std_bn.running_mean.data = torch.randn(12, generator=g)
+    std_bn.running_var.data = torch.rand(12, generator=g) + 0.2
+    std_bn.eval()
+    folded = BatchNormUncentered2d.from_standard_module(std_bn, dict(bcosify_args=dict(norm_layer="BnUncV2"))).eval()
+    assert torch.allclose(folded(x), std_bn(x), rtol=1e-5, atol=1e-6)
+    fw, fb = O.bn_uncentered_from_standard(std_bn.weight.data, std_bn.bias.data, std_bn.running_mean, std_bn.running_var, std_bn.eps)
+    assert torch.allclose(fb, folded.bias.data)
+    out.update({"bnfold.w": std_bn.weight.detach(), "bnfold.b": std_bn.bias.detach(), "bnfold.rm": std_bn.running_mean.clone(),
+                "bnfold.rv": std_bn.running_var.clone(), "bnfold.y": std_bn(x).detach(), "bnfold.bias_folded": folded.bias.detach()})
+
+    # DetachableLayerNorm / MyGELU / LogitLayer
+    ln = DetachableLayerNorm(24)
+    ln.weight.data = torch.rand(24, generator=g) + 0.5
+    ln.bias = None
+    x = torch.randn(2, 7, 24, generator=g)
+    y = ln(x)
+    seedg = torch.randn(y.shape, generator=g)
+    ln.set_explanation_mode(True)
+    xg = x.clone().requires_grad_(True)
+    ye = ln(xg)
+    (gx,) = torch.autograd.grad((ye * seedg).sum(), [xg])
+    assert torch.allclose(O.layer_norm_detachable(x, ln.weight, None, ln.eps, True), ye.detach(), rtol=1e-6, atol=1e-6)
+    out.update({"ln.w": ln.weight.detach(), "ln.x": x, "ln.y": y.detach(), "ln.y_explain": ye.detach(), "ln.seed": seedg, "ln.gx": gx})
+
+    gelu = bcosify_vit.MyGELU()
+    x = torch.randn(3, 11, 16, generator=g) * 2
+    y = gelu(x)
+    seedg = torch.randn(y.shape, generator=g)
+    gelu.set_explanation_mode(True)
+    xg = x.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad((gelu(xg) * seedg).sum(), [xg])
+    assert torch.allclose(O.gelu_detachable(x), y, rtol=1e-6, atol=1e-7)
+    out.update({"gelu.x": x, "gelu.y": y.detach(), "gelu.seed": seedg, "gelu.gx": gx})
+
+    ll = LogitLayer(logit_temperature=2.0, logit_bias=-1.5)
+    x = torch.randn(4, 10, generator=g)
+    assert torch.equal(O.logit_layer(x, 2.0, -1.5), ll(x))
+    out.update({"logit.x": x, "logit.y": ll(x)})
+
+    path = os.path.join(GOLD, "modules_kat.npz")
+    np.savez_compressed(path, **{k: v.detach().numpy() for k, v in out.items()})
+    print(f"[modules] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB), {len(out)} arrays")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="modules,resnet18,resnet50")
+    args = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_grad_enabled(True)
+    which = args.only.split(",")
+    if "modules" in which:
+        golden_modules()
+    if "resnet18" in which:
+        golden_resnet("resnet18", 8)
+    if "resnet50" in which:
+        golden_resnet("resnet50", 4)
