@@ -1,0 +1,200 @@
+"""ctypes binding of the C ABI in include/bcosk.h (libbcosk.so).
+
+The header is the single source of truth: `bcosk_igemm_params` is parsed from it, and the result is
+checked against `bcosk_sizeof_igemm_params()` of the loaded library.  There is NO fallback: if the
+library is missing, cannot be loaded, or the device is not sm_100, the callers raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import Dict, List, Tuple
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+HEADER = os.path.join(ROOT, "include", "bcosk.h")
+LIB_PATH = os.path.join(PKG, "libbcosk.so")
+
+_CT = {
+    "int32_t": C.c_int32, "uint32_t": C.c_uint32, "int64_t": C.c_int64, "uint16_t": C.c_uint16,
+    "float": C.c_float, "int": C.c_int,
+}
+
+
+def _parse_header() -> Tuple[Dict[str, int], List[Tuple[str, object]], List[str]]:
+    with open(HEADER) as fh:
+        src = fh.read()
+    defines = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(BCOSK_\w+)\s+\(?(-?\d+)\)?", src)}
+    body = re.search(r"typedef struct bcosk_igemm_params \{(.*?)\} bcosk_igemm_params;", src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields: List[Tuple[str, object]] = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        m = re.match(r"(const\s+)?(\w+)\s*(\*?)\s*(.*)", decl)
+        base, ptr, names = m.group(2), m.group(3), m.group(4)
+        for nm in names.split(","):
+            nm = nm.strip()
+            is_ptr = bool(ptr) or nm.startswith("*")
+            nm = nm.lstrip("* ")
+            arr = re.match(r"(\w+)\[(\w+)\]", nm)
+            if is_ptr:
+                fields.append((nm, C.c_void_p))
+            elif arr:
+                n = defines.get(arr.group(2)) or int(arr.group(2))
+                fields.append((arr.group(1), _CT[base] * n))
+            else:
+                fields.append((nm, _CT[base]))
+    protos = re.findall(r"^(?:int|const char\*)\s+(bcosk_\w+)\(", src, re.M)
+    return defines, fields, protos
+
+
+DEFINES, _FIELDS, EXPORTS = _parse_header()
+globals().update(DEFINES)  # BCOSK_OK, BCOSK_MODE_FWD, ...
+
+
+class IgemmParams(C.Structure):
+    _fields_ = _FIELDS
+
+    def set_ptr(self, name: str, tensor) -> None:
+        setattr(self, name, None if tensor is None else tensor.data_ptr())
+
+
+class BcoskError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libbcosk.so (building is the job of `bcos_b200.build` / `__graft_entry__.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BcoskError(f"{LIB_PATH} not found - run `python -m bcos_b200.build` (there is no CPU/PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.bcosk_last_error.restype = C.c_char_p
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise BcoskError(f"libbcosk.so does not export {name}")
+    if lib.bcosk_sizeof_igemm_params() != C.sizeof(IgemmParams):
+        raise BcoskError(f"bcosk_igemm_params layout mismatch: lib {lib.bcosk_sizeof_igemm_params()} vs "
+                         f"binding {C.sizeof(IgemmParams)}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().bcosk_last_error().decode(errors="replace")
+        raise BcoskError(f"{what} failed (rc={rc}): {msg}")
+
+
+def require_device() -> None:
+    """Raise unless the current CUDA device can run the sm_100a kernels."""
+    import torch
+    if not torch.cuda.is_available():
+        raise BcoskError("bcos_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    if not load().bcosk_device_supported():
+        raise BcoskError("bcos_b200 kernels are built for sm_100a (B200) only")
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+DTYPE_CODE = {"bf16": 1, "fp16": 0}
+
+
+def torch_dtype(code: int):
+    import torch
+    return torch.bfloat16 if code == 1 else torch.float16
+
+
+# ------------------------------------------------------------------------------------------------
+# thin wrappers (device tensors in, nothing allocated here)
+# ------------------------------------------------------------------------------------------------
+def igemm(p: IgemmParams) -> None:
+    check(load().bcosk_igemm(C.byref(p), _stream()), "bcosk_igemm")
+
+
+def debug_a_tile(p: IgemmParams, tile_m: int, chunk: int, out) -> None:
+    check(load().bcosk_debug_a_tile(C.byref(p), tile_m, chunk, _p(out), _stream()), "bcosk_debug_a_tile")
+
+
+def _f6(vals):
+    return (C.c_float * 6)(*[float(v) for v in vals])
+
+
+def _is_u8(x) -> bool:
+    import torch
+    nb, c, h, w = x.shape
+    assert x.is_contiguous()
+    if x.dtype == torch.uint8:
+        assert c == 3, "uint8 input must be RGB [nb, 3, h, w]"
+        return True
+    assert x.dtype == torch.float32 and c == 6, "float input must be fp32 [nb, 6, h, w] = [x, 1-x]"
+    return False
+
+
+def input_prep_s2d(x, mean6, inv_std6, out, cp, planes, dtype, sq) -> None:
+    nb, _, h, w = x.shape
+    fn = load().bcosk_input_prep_s2d_u8 if _is_u8(x) else load().bcosk_input_prep_s2d
+    check(fn(_p(x), nb, h, w, _f6(mean6), _f6(inv_std6), _p(out), cp, planes, dtype, _p(sq), _stream()),
+          "bcosk_input_prep_s2d")
+
+
+def patch_inv_norm(sq, parts, nb, h, w, kh, kw, stride, pad, eps_in, eps_out, inv_norm, op, oq) -> None:
+    check(load().bcosk_patch_inv_norm(_p(sq), parts, nb, h, w, kh, kw, stride, pad, C.c_float(eps_in), C.c_float(eps_out),
+                                      _p(inv_norm), op, oq, _stream()), "bcosk_patch_inv_norm")
+
+
+def pixel_sqsum(x, rows, c, planes, plane_stride, ld, dtype, sq) -> None:
+    check(load().bcosk_pixel_sqsum(_p(x), C.c_int64(rows), c, planes, plane_stride, ld, dtype, _p(sq), _stream()),
+          "bcosk_pixel_sqsum")
+
+
+def avgpool_fwd(x, nb, h, w, c, planes, k, stride, pad, y, op, oq, dtype, sq) -> None:
+    check(load().bcosk_avgpool_fwd(_p(x), nb, h, w, c, planes, k, stride, pad, _p(y), op, oq, dtype, _p(sq), _stream()),
+          "bcosk_avgpool_fwd")
+
+
+def avgpool_bwd_mul(gy, nb, h, w, c, planes, k, stride, pad, op, oq, gain, gain_f32, gx, dtype) -> None:
+    check(load().bcosk_avgpool_bwd_mul(_p(gy), nb, h, w, c, planes, k, stride, pad, op, oq, _p(gain), int(gain_f32), _p(gx),
+                                       dtype, _stream()), "bcosk_avgpool_bwd_mul")
+
+
+def gap_logits(fc, nb, npix, ncls, inv_temp, bias, logits, pred) -> None:
+    check(load().bcosk_gap_logits(_p(fc), nb, npix, ncls, C.c_float(inv_temp), C.c_float(bias), _p(logits), _p(pred),
+                                  _stream()), "bcosk_gap_logits")
+
+
+def fc_seed_dgrad(target, gain_fc, gain_f32, w_fc, nb, npix, ncls, c, inv_temp, seed_scale, mul1, mul1_f32, out1, mask2,
+                  out2, planes, dtype) -> None:
+    check(load().bcosk_fc_seed_dgrad(_p(target), _p(gain_fc), int(gain_f32), _p(w_fc), nb, npix, ncls, c,
+                                     C.c_float(inv_temp), C.c_float(seed_scale), _p(mul1), int(mul1_f32), _p(out1),
+                                     _p(mask2), _p(out2), planes, dtype, _stream()), "bcosk_fc_seed_dgrad")
+
+
+def contrib_map_s2d(g, x, nb, h, w, cp, inv_std6, out_scale, cmap, grad6) -> None:
+    fn = load().bcosk_contrib_map_s2d_u8 if _is_u8(x) else load().bcosk_contrib_map_s2d
+    check(fn(_p(g), _p(x), nb, h, w, cp, _f6(inv_std6), C.c_float(out_scale), _p(cmap), _p(grad6), _stream()),
+          "bcosk_contrib_map_s2d")
+
+
+def channel_affine(x, rows, c, alpha, beta, relu, y, dtype) -> None:
+    check(load().bcosk_channel_affine(_p(x), C.c_int64(rows), c, _p(alpha), _p(beta), int(relu), _p(y), dtype, _stream()),
+          "bcosk_channel_affine")
+
+
+def mul(a, b, n, out, dtype) -> None:
+    check(load().bcosk_mul(_p(a), _p(b), C.c_int64(n), _p(out), dtype, _stream()), "bcosk_mul")

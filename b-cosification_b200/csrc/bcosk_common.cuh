@@ -12,7 +12,7 @@
 
 #ifndef BCOSK_SPIN_LIMIT
 // A wedged pipeline traps (-> cudaErrorLaunchFailure) instead of hanging the GPU forever.
-#define BCOSK_SPIN_LIMIT (1u << 28)
+#define BCOSK_SPIN_LIMIT (1u << 24)
 #endif
 
 namespace bcosk {

@@ -1,0 +1,596 @@
+// bcosk_elementwise.cu -- bandwidth kernels around the implicit GEMM (sm_100a).
+//
+// All tensors are NHWC; 16-bit tensors are moved with 16-byte vector accesses (8 channels per thread),
+// reductions use warp shuffles, and every kernel is sized so that consecutive lanes touch consecutive
+// addresses.  Each entry point is documented in include/bcosk.h with the reference code it replaces.
+#include "../../include/bcosk.h"
+#include "bcosk_common.cuh"
+#include "bcosk_host.h"
+
+namespace bcosk {
+
+static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 a;
+  a = Cvt<T>::unpack2(u.x); f[0] = a.x; f[1] = a.y;
+  a = Cvt<T>::unpack2(u.y); f[2] = a.x; f[3] = a.y;
+  a = Cvt<T>::unpack2(u.z); f[4] = a.x; f[5] = a.y;
+  a = Cvt<T>::unpack2(u.w); f[6] = a.x; f[7] = a.y;
+}
+template <typename T>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(Cvt<T>::pack2(f[0], f[1]), Cvt<T>::pack2(f[2], f[3]), Cvt<T>::pack2(f[4], f[5]),
+                    Cvt<T>::pack2(f[6], f[7]));
+}
+// 8 channels summed over precision planes
+template <typename T>
+__device__ __forceinline__ void load8_planes(const T* ptr, int planes, int plane_stride, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = 0.f;
+  for (int pl = 0; pl < planes; ++pl) {
+    float g[8];
+    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(ptr + (size_t)pl * plane_stride)), g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] += g[i];
+  }
+}
+// split-store 8 channels into planes; f returns the stored (representable) value
+template <typename T>
+__device__ __forceinline__ void store8_planes(T* ptr, int planes, int plane_stride, float (&f)[8]) {
+  float r[8], acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { r[i] = f[i]; acc[i] = 0.f; }
+  for (int pl = 0; pl < planes; ++pl) {
+    uint4 u = pack8<T>(r);
+    float g[8];
+    unpack8<T>(u, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r[i] -= g[i]; acc[i] += g[i]; }
+    *reinterpret_cast<uint4*>(ptr + (size_t)pl * plane_stride) = u;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = acc[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// input normalise + NCHW fp32 -> NHWC 16-bit + 2x2 space-to-depth (+ per-pixel sum of squares)
+// ------------------------------------------------------------------------------------------------
+struct Norm6 { float mean[6]; float inv_std[6]; };
+
+// 2x2 patch of the 6-channel [x, 1-x] input at (img, 2r.., 2s..): either fp32 NCHW with 6 channels, or uint8 NCHW RGB
+// (x = u8/255, the inverse channels are formed on the fly: AddInverse, reference bcos/data/transforms.py:42-55)
+template <typename SRC>
+__device__ __forceinline__ void load_patch6(const SRC* __restrict__ x, int img, int r, int s, int h, int w, float (&raw)[24]);
+template <>
+__device__ __forceinline__ void load_patch6<float>(const float* __restrict__ x, int img, int r, int s, int h, int w,
+                                                   float (&raw)[24]) {
+  const size_t plane = (size_t)h * w;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    const float* src = x + ((size_t)img * 6 + c) * plane + (size_t)(2 * r) * w + 2 * s;
+    const float2 top = __ldg(reinterpret_cast<const float2*>(src));
+    const float2 bot = __ldg(reinterpret_cast<const float2*>(src + w));
+    raw[0 * 6 + c] = top.x; raw[1 * 6 + c] = top.y; raw[2 * 6 + c] = bot.x; raw[3 * 6 + c] = bot.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load_patch6<uint8_t>(const uint8_t* __restrict__ x, int img, int r, int s, int h, int w,
+                                                     float (&raw)[24]) {
+  const size_t plane = (size_t)h * w;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const uint8_t* src = x + ((size_t)img * 3 + c) * plane + (size_t)(2 * r) * w + 2 * s;
+    const uchar2 top = __ldg(reinterpret_cast<const uchar2*>(src));
+    const uchar2 bot = __ldg(reinterpret_cast<const uchar2*>(src + w));
+    const float v0 = (float)top.x / 255.0f, v1 = (float)top.y / 255.0f, v2 = (float)bot.x / 255.0f, v3 = (float)bot.y / 255.0f;
+    raw[0 * 6 + c] = v0; raw[1 * 6 + c] = v1; raw[2 * 6 + c] = v2; raw[3 * 6 + c] = v3;
+    raw[0 * 6 + c + 3] = 1.0f - v0; raw[1 * 6 + c + 3] = 1.0f - v1; raw[2 * 6 + c + 3] = 1.0f - v2; raw[3 * 6 + c + 3] = 1.0f - v3;
+  }
+}
+
+template <typename T, typename SRC>
+__global__ void input_prep_s2d_kernel(const SRC* __restrict__ x, int nb, int h, int w, Norm6 nm, T* __restrict__ out,
+                                      int cp, int planes, float* __restrict__ sq) {
+  const int h2 = h >> 1, w2 = w >> 1;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nb * h2 * w2) return;
+  const int s = (int)(idx % w2);
+  const int r = (int)((idx / w2) % h2);
+  const int img = (int)(idx / ((long long)w2 * h2));
+  float v[24];  // channel (dy*2+dx)*6 + c
+  load_patch6<SRC>(x, img, r, s, h, w, v);
+  const size_t plane = (size_t)h * w;
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) v[d * 6 + c] = (v[d * 6 + c] - nm.mean[c]) * nm.inv_std[c];
+  T* dst = out + (size_t)idx * ((size_t)planes * cp);
+  float st[24];
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = v[g * 8 + i];
+    store8_planes<T>(dst + g * 8, planes, cp, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st[g * 8 + i] = f[i];
+  }
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int pl = 0; pl < planes; ++pl)
+    for (int g = 3; g < cp / 8; ++g) *reinterpret_cast<uint4*>(dst + (size_t)pl * cp + g * 8) = z;
+  if (sq != nullptr) {
+    float q[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      float a = 0.f;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) a = fmaf(st[d * 6 + c], st[d * 6 + c], a);
+      q[d] = a;
+    }
+    float* sp = sq + (size_t)img * plane + (size_t)(2 * r) * w + 2 * s;
+    *reinterpret_cast<float2*>(sp) = make_float2(q[0], q[1]);
+    *reinterpret_cast<float2*>(sp + w) = make_float2(q[2], q[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// patch norm from per-pixel sums of squares
+// ------------------------------------------------------------------------------------------------
+__global__ void patch_inv_norm_kernel(const float* __restrict__ sq, int parts, int nb, int h, int w, int kh, int kw,
+                                      int stride, int pad, float eps_in, float eps_out, float* __restrict__ inv_norm,
+                                      int op, int oq) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)nb * op * oq;
+  if (idx >= total) return;
+  const int q = (int)(idx % oq);
+  const int p = (int)((idx / oq) % op);
+  const int img = (int)(idx / ((long long)oq * op));
+  const size_t part_stride = (size_t)nb * h * w;
+  float acc = 0.f;
+  for (int dy = 0; dy < kh; ++dy) {
+    const int y = p * stride - pad + dy;
+    if (y < 0 || y >= h) continue;
+    for (int dx = 0; dx < kw; ++dx) {
+      const int xx = q * stride - pad + dx;
+      if (xx < 0 || xx >= w) continue;
+      const size_t o = ((size_t)img * h + y) * w + xx;
+      for (int t = 0; t < parts; ++t) acc += __ldg(sq + t * part_stride + o);
+    }
+  }
+  inv_norm[idx] = 1.0f / (sqrtf(acc + eps_in) + eps_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sum_c x^2 per pixel (one warp per row)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pixel_sqsum_kernel(const T* __restrict__ x, long long rows, int c, int planes, int plane_stride, int ld,
+                                   float* __restrict__ sq) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const T* src = x + (size_t)row * ld;
+  float acc = 0.f;
+  for (int g = lane; g < c / 8; g += 32) {
+    float f[8];
+    load8_planes<T>(src + g * 8, planes, plane_stride, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc = fmaf(f[i], f[i], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) sq[row] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// average pooling (count_include_pad=True) forward / explain-backward
+// ------------------------------------------------------------------------------------------------
+// lanes_per_pix = min(32, c/8) (a power of two); a warp covers 32/lanes_per_pix output pixels.
+template <typename T>
+__global__ void avgpool_fwd_kernel(const T* __restrict__ x, int nb, int h, int w, int c, int planes, int k, int stride,
+                                   int pad, T* __restrict__ y, int op, int oq, float* __restrict__ sq, int lpp) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int ppw = 32 / lpp;  // pixels per warp
+  const long long pix = warp_id * ppw + lane / lpp;
+  const long long total = (long long)nb * op * oq;
+  const bool valid = pix < total;
+  const int sub = lane % lpp;
+  float sqacc = 0.f;
+  if (valid) {
+    const int q = (int)(pix % oq);
+    const int p = (int)((pix / oq) % op);
+    const int img = (int)(pix / ((long long)oq * op));
+    const float inv = 1.0f / (float)(k * k);
+    const int ld = planes * c;
+    for (int g = sub; g < c / 8; g += lpp) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int dy = 0; dy < k; ++dy) {
+        const int yy = p * stride - pad + dy;
+        if (yy < 0 || yy >= h) continue;
+        for (int dx = 0; dx < k; ++dx) {
+          const int xx = q * stride - pad + dx;
+          if (xx < 0 || xx >= w) continue;
+          float f[8];
+          load8_planes<T>(x + (((size_t)img * h + yy) * w + xx) * ld + g * 8, planes, c, f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] *= inv;
+      store8_planes<T>(y + (size_t)pix * ld + g * 8, planes, c, acc);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sqacc = fmaf(acc[i], acc[i], sqacc);
+    }
+  }
+  if (sq != nullptr) {
+    for (int o = lpp >> 1; o > 0; o >>= 1) sqacc += __shfl_xor_sync(0xffffffffu, sqacc, o);
+    if (valid && sub == 0) sq[pix] = sqacc;
+  }
+}
+
+template <typename T>
+__global__ void avgpool_bwd_mul_kernel(const T* __restrict__ gy, int nb, int h, int w, int c, int planes, int k,
+                                       int stride, int pad, int op, int oq, const void* __restrict__ gain, int gain_f32,
+                                       T* __restrict__ gx) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = c / 8;
+  const long long total = (long long)nb * h * w * cg;
+  if (idx >= total) return;
+  const int g = (int)(idx % cg);
+  const long long pix = idx / cg;
+  const int xx = (int)(pix % w);
+  const int yy = (int)((pix / w) % h);
+  const int img = (int)(pix / ((long long)w * h));
+  const int ld = planes * c;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  // output rows p with p*stride - pad <= yy <= p*stride - pad + k - 1
+  const int p_lo = max(0, (yy + pad - k + 1 + stride - 1) / stride);
+  const int p_hi = min(op - 1, (yy + pad) / stride);
+  const int q_lo = max(0, (xx + pad - k + 1 + stride - 1) / stride);
+  const int q_hi = min(oq - 1, (xx + pad) / stride);
+  for (int p = p_lo; p <= p_hi; ++p)
+    for (int q = q_lo; q <= q_hi; ++q) {
+      float f[8];
+      load8_planes<T>(gy + (((size_t)img * op + p) * oq + q) * ld + g * 8, planes, c, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+  const float inv = 1.0f / (float)(k * k);
+  float gn[8];
+  if (gain == nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gn[i] = 1.f;
+  } else if (gain_f32) {
+    const float4* gp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(gain) + (size_t)pix * c + g * 8);
+    const float4 a = __ldg(gp), b = __ldg(gp + 1);
+    gn[0] = a.x; gn[1] = a.y; gn[2] = a.z; gn[3] = a.w; gn[4] = b.x; gn[5] = b.y; gn[6] = b.z; gn[7] = b.w;
+  } else {
+    unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(gain) + (size_t)pix * c + g * 8)), gn);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] *= inv * gn[i];
+  store8_planes<T>(gx + (size_t)pix * ld + g * 8, planes, c, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// classifier tail: GAP + logit layer + argmax (one block per image)
+// ------------------------------------------------------------------------------------------------
+__global__ void gap_logits_kernel(const float* __restrict__ fc, int npix, int ncls, float inv_temp, float bias,
+                                  float* __restrict__ logits, int* __restrict__ pred) {
+  const int img = blockIdx.x;
+  const float* src = fc + (size_t)img * npix * ncls;
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  const float invn = 1.0f / (float)npix;
+  for (int cls = threadIdx.x; cls < ncls; cls += blockDim.x) {
+    float acc = 0.f;
+    for (int px = 0; px < npix; ++px) acc += __ldg(src + (size_t)px * ncls + cls);
+    const float l = acc * invn * inv_temp + bias;
+    logits[(size_t)img * ncls + cls] = l;
+    if (l > best) { best = l; best_i = cls; }
+  }
+  // block arg-max, smallest index on ties
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_v[warp] = best; s_i[warp] = best_i; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    best = lane < nw ? s_v[lane] : -INFINITY;
+    best_i = lane < nw ? s_i[lane] : 0x7fffffff;
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    if (lane == 0 && pred != nullptr) pred[img] = best_i;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// explain seed through GAP + classifier for a one-hot logit gradient
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void fc_seed_dgrad_kernel(const int* __restrict__ target, const void* __restrict__ gain_fc, int gain_f32,
+                                     const float* __restrict__ w_fc, int nb, int npix, int ncls, int c, float coef,
+                                     const void* __restrict__ mul1, int mul1_f32, T* __restrict__ out1,
+                                     const uint32_t* __restrict__ mask2, T* __restrict__ out2, int planes) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = c / 8;
+  const long long total = (long long)nb * npix * cg;
+  if (idx >= total) return;
+  const int g = (int)(idx % cg);
+  const long long row = idx / cg;  // img * npix + pix
+  const int img = (int)(row / npix);
+  const int cls = __ldg(target + img);
+  float gf;
+  if (gain_f32) gf = __ldg(reinterpret_cast<const float*>(gain_fc) + (size_t)row * ncls + cls);
+  else gf = Cvt<T>::unpack2((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(gain_fc) + (size_t)row * ncls + cls)).x;
+  const float s = coef * gf;
+  const float4* wp = reinterpret_cast<const float4*>(w_fc + (size_t)cls * c + g * 8);
+  const float4 wa = __ldg(wp), wb = __ldg(wp + 1);
+  float v[8] = {s * wa.x, s * wa.y, s * wa.z, s * wa.w, s * wb.x, s * wb.y, s * wb.z, s * wb.w};
+  const int ld = planes * c;
+  if (out2 != nullptr) {
+    float o[8];
+    const uint32_t mb = mask2 ? __ldg(mask2 + (size_t)row * ((c + 31) / 32) + (g >> 2)) : 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = ((mb >> ((g & 3) * 8 + i)) & 1u) ? v[i] : 0.f;
+    store8_planes<T>(out2 + (size_t)row * ld + g * 8, planes, c, o);
+  }
+  if (mul1 != nullptr) {
+    float gn[8];
+    if (mul1_f32) {
+      const float4* gp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(mul1) + (size_t)row * c + g * 8);
+      const float4 a = __ldg(gp), b = __ldg(gp + 1);
+      gn[0] = a.x; gn[1] = a.y; gn[2] = a.z; gn[3] = a.w; gn[4] = b.x; gn[5] = b.y; gn[6] = b.z; gn[7] = b.w;
+    } else {
+      unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(mul1) + (size_t)row * c + g * 8)), gn);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= gn[i];
+  }
+  store8_planes<T>(out1 + (size_t)row * ld + g * 8, planes, c, v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// contribution map from the stem dgrad (space-to-depth layout)
+// ------------------------------------------------------------------------------------------------
+struct InvStd6 { float v[6]; };
+
+template <typename SRC>
+__global__ void contrib_map_s2d_kernel(const float* __restrict__ g, const SRC* __restrict__ x, int nb, int h, int w,
+                                       int cp, InvStd6 is, float out_scale, float* __restrict__ cmap,
+                                       float* __restrict__ grad6) {
+  const int h2 = h >> 1, w2 = w >> 1;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nb * h2 * w2) return;
+  const int s = (int)(idx % w2);
+  const int r = (int)((idx / w2) % h2);
+  const int img = (int)(idx / ((long long)w2 * h2));
+  const float4* gp = reinterpret_cast<const float4*>(g + (size_t)idx * cp);
+  float gv[24];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float4 a = __ldg(gp + i);
+    gv[4 * i] = a.x; gv[4 * i + 1] = a.y; gv[4 * i + 2] = a.z; gv[4 * i + 3] = a.w;
+  }
+  float xv[24];
+  load_patch6<SRC>(x, img, r, s, h, w, xv);
+  const size_t plane = (size_t)h * w;
+  float cm[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    const size_t off = ((size_t)img * 6 + c) * plane + (size_t)(2 * r) * w + 2 * s;
+    const float k = is.v[c] * out_scale;
+    const float g0 = gv[0 * 6 + c] * k, g1 = gv[1 * 6 + c] * k, g2 = gv[2 * 6 + c] * k, g3 = gv[3 * 6 + c] * k;
+    cm[0] = fmaf(xv[0 * 6 + c], g0, cm[0]);
+    cm[1] = fmaf(xv[1 * 6 + c], g1, cm[1]);
+    cm[2] = fmaf(xv[2 * 6 + c], g2, cm[2]);
+    cm[3] = fmaf(xv[3 * 6 + c], g3, cm[3]);
+    if (grad6 != nullptr) {
+      *reinterpret_cast<float2*>(grad6 + off) = make_float2(g0, g1);
+      *reinterpret_cast<float2*>(grad6 + off + w) = make_float2(g2, g3);
+    }
+  }
+  float* cp_out = cmap + (size_t)img * plane + (size_t)(2 * r) * w + 2 * s;
+  *reinterpret_cast<float2*>(cp_out) = make_float2(cm[0], cm[1]);
+  *reinterpret_cast<float2*>(cp_out + w) = make_float2(cm[2], cm[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic element-wise helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void channel_affine_kernel(const T* __restrict__ x, long long rows, int c, const float* __restrict__ alpha,
+                                      const float* __restrict__ beta, int relu, T* __restrict__ y) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = c / 8;
+  if (idx >= rows * cg) return;
+  const int g = (int)(idx % cg);
+  float f[8];
+  unpack8<T>(__ldg(reinterpret_cast<const uint4*>(x) + idx), f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float a = alpha ? __ldg(alpha + g * 8 + i) : 1.f;
+    const float b = beta ? __ldg(beta + g * 8 + i) : 0.f;
+    float v = fmaf(f[i], a, b);
+    f[i] = (relu && v < 0.f) ? 0.f : v;
+  }
+  reinterpret_cast<uint4*>(y)[idx] = pack8<T>(f);
+}
+
+template <typename T>
+__global__ void mul_kernel(const T* __restrict__ a, const T* __restrict__ b, long long n8, T* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n8) return;
+  float fa[8], fb[8];
+  unpack8<T>(__ldg(reinterpret_cast<const uint4*>(a) + idx), fa);
+  unpack8<T>(__ldg(reinterpret_cast<const uint4*>(b) + idx), fb);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) fa[i] *= fb[i];
+  reinterpret_cast<uint4*>(out)[idx] = pack8<T>(fa);
+}
+
+}  // namespace bcosk
+
+using namespace bcosk;
+
+#define BCOSK_DTYPE_SWITCH(dtype, ...)                                              \
+  if ((dtype) == BCOSK_DTYPE_BF16) { using T = __nv_bfloat16; __VA_ARGS__ }         \
+  else if ((dtype) == BCOSK_DTYPE_F16) { using T = __half; __VA_ARGS__ }            \
+  else return set_error(BCOSK_EINVAL, "bad dtype %d", (int)(dtype));
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename SRC>
+static int input_prep_impl(const SRC* x, int32_t nb, int32_t h, int32_t w, const float* mean6, const float* inv_std6,
+                           void* out, int32_t cp, int32_t planes, int32_t dtype, float* sq, void* stream) {
+  if (!x || !out || !mean6 || !inv_std6) return set_error(BCOSK_EINVAL, "input_prep: null pointer");
+  if (h % 2 || w % 2 || cp < 24 || cp % 8) return set_error(BCOSK_EINVAL, "input_prep: need even h,w and cp>=24, cp%%8==0");
+  Norm6 nm;
+  for (int i = 0; i < 6; ++i) { nm.mean[i] = mean6[i]; nm.inv_std[i] = inv_std6[i]; }  // host pointers
+  const long long n = (long long)nb * (h / 2) * (w / 2);
+  BCOSK_DTYPE_SWITCH(dtype, input_prep_s2d_kernel<T, SRC><<<blocks_for(n, 256), 256, 0, S(stream)>>>(
+      x, nb, h, w, nm, reinterpret_cast<T*>(out), cp, planes, sq);)
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_input_prep_s2d(const float* x, int32_t nb, int32_t h, int32_t w, const float* mean6,
+                                    const float* inv_std6, void* out, int32_t cp, int32_t planes, int32_t dtype, float* sq,
+                                    void* stream) {
+  return input_prep_impl<float>(x, nb, h, w, mean6, inv_std6, out, cp, planes, dtype, sq, stream);
+}
+
+extern "C" int bcosk_input_prep_s2d_u8(const uint8_t* x, int32_t nb, int32_t h, int32_t w, const float* mean6,
+                                       const float* inv_std6, void* out, int32_t cp, int32_t planes, int32_t dtype,
+                                       float* sq, void* stream) {
+  return input_prep_impl<uint8_t>(x, nb, h, w, mean6, inv_std6, out, cp, planes, dtype, sq, stream);
+}
+
+extern "C" int bcosk_patch_inv_norm(const float* sq, int32_t parts, int32_t nb, int32_t h, int32_t w, int32_t kh,
+                                    int32_t kw, int32_t stride, int32_t pad, float eps_in, float eps_out, float* inv_norm,
+                                    int32_t op, int32_t oq, void* stream) {
+  if (!sq || !inv_norm || parts < 1) return set_error(BCOSK_EINVAL, "patch_inv_norm: bad argument");
+  const long long n = (long long)nb * op * oq;
+  patch_inv_norm_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(sq, parts, nb, h, w, kh, kw, stride, pad, eps_in,
+                                                                     eps_out, inv_norm, op, oq);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_pixel_sqsum(const void* x, int64_t rows, int32_t c, int32_t planes, int32_t plane_stride, int32_t ld,
+                                 int32_t dtype, float* sq, void* stream) {
+  if (!x || !sq || c % 8) return set_error(BCOSK_EINVAL, "pixel_sqsum: bad argument");
+  BCOSK_DTYPE_SWITCH(dtype, pixel_sqsum_kernel<T><<<blocks_for(rows, 8), 256, 0, S(stream)>>>(
+      reinterpret_cast<const T*>(x), rows, c, planes, plane_stride, ld, sq);)
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+static int lanes_per_pixel(int c) {
+  const int g = c / 8;
+  if (c % 8) return 0;
+  if (g >= 32) return (g % 32 == 0) ? 32 : 0;
+  return (g & (g - 1)) == 0 ? g : 0;
+}
+
+extern "C" int bcosk_avgpool_fwd(const void* x, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t k,
+                                 int32_t stride, int32_t pad, void* y, int32_t op, int32_t oq, int32_t dtype, float* sq,
+                                 void* stream) {
+  const int lpp = lanes_per_pixel(c);
+  if (!x || !y || lpp == 0) return set_error(BCOSK_EUNSUPPORTED, "avgpool_fwd: c/8 must be a power of two or a multiple of 32");
+  const long long pix = (long long)nb * op * oq;
+  const long long warps = (pix + (32 / lpp) - 1) / (32 / lpp);
+  BCOSK_DTYPE_SWITCH(dtype, avgpool_fwd_kernel<T><<<blocks_for(warps, 8), 256, 0, S(stream)>>>(
+      reinterpret_cast<const T*>(x), nb, h, w, c, planes, k, stride, pad, reinterpret_cast<T*>(y), op, oq, sq, lpp);)
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_avgpool_bwd_mul(const void* gy, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t k,
+                                     int32_t stride, int32_t pad, int32_t op, int32_t oq, const void* gain, int32_t gain_f32,
+                                     void* gx, int32_t dtype, void* stream) {
+  if (!gy || !gx || c % 8) return set_error(BCOSK_EINVAL, "avgpool_bwd_mul: bad argument");
+  const long long n = (long long)nb * h * w * (c / 8);
+  BCOSK_DTYPE_SWITCH(dtype, avgpool_bwd_mul_kernel<T><<<blocks_for(n, 256), 256, 0, S(stream)>>>(
+      reinterpret_cast<const T*>(gy), nb, h, w, c, planes, k, stride, pad, op, oq, gain, gain_f32, reinterpret_cast<T*>(gx));)
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_gap_logits(const float* fc, int32_t nb, int32_t npix, int32_t ncls, float inv_temp, float bias,
+                                float* logits, int32_t* pred, void* stream) {
+  if (!fc || !logits) return set_error(BCOSK_EINVAL, "gap_logits: null pointer");
+  gap_logits_kernel<<<nb, 256, 0, S(stream)>>>(fc, npix, ncls, inv_temp, bias, logits, pred);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_fc_seed_dgrad(const int32_t* target, const void* gain_fc, int32_t gain_f32, const float* w_fc,
+                                   int32_t nb, int32_t npix, int32_t ncls, int32_t c, float inv_temp, float seed_scale,
+                                   const void* mul1, int32_t mul1_f32, void* out1, const uint32_t* mask2, void* out2,
+                                   int32_t planes, int32_t dtype, void* stream) {
+  if (!target || !gain_fc || !w_fc || !out1 || c % 8) return set_error(BCOSK_EINVAL, "fc_seed_dgrad: bad argument");
+  const long long n = (long long)nb * npix * (c / 8);
+  const float coef = inv_temp * seed_scale / (float)npix;
+  BCOSK_DTYPE_SWITCH(dtype, fc_seed_dgrad_kernel<T><<<blocks_for(n, 256), 256, 0, S(stream)>>>(
+      target, gain_fc, gain_f32, w_fc, nb, npix, ncls, c, coef, mul1, mul1_f32, reinterpret_cast<T*>(out1), mask2,
+      reinterpret_cast<T*>(out2), planes);)
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+template <typename SRC>
+static int contrib_map_impl(const float* g, const SRC* x, int32_t nb, int32_t h, int32_t w, int32_t cp,
+                            const float* inv_std6, float out_scale, float* cmap, float* grad6, void* stream) {
+  if (!g || !x || !cmap || !inv_std6 || cp < 24 || cp % 4) return set_error(BCOSK_EINVAL, "contrib_map: bad argument");
+  InvStd6 is;
+  for (int i = 0; i < 6; ++i) is.v[i] = inv_std6[i];
+  const long long n = (long long)nb * (h / 2) * (w / 2);
+  contrib_map_s2d_kernel<SRC><<<blocks_for(n, 256), 256, 0, S(stream)>>>(g, x, nb, h, w, cp, is, out_scale, cmap, grad6);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_contrib_map_s2d(const float* g, const float* x, int32_t nb, int32_t h, int32_t w, int32_t cp,
+                                     const float* inv_std6, float out_scale, float* cmap, float* grad6, void* stream) {
+  return contrib_map_impl<float>(g, x, nb, h, w, cp, inv_std6, out_scale, cmap, grad6, stream);
+}
+
+extern "C" int bcosk_contrib_map_s2d_u8(const float* g, const uint8_t* x, int32_t nb, int32_t h, int32_t w, int32_t cp,
+                                        const float* inv_std6, float out_scale, float* cmap, float* grad6, void* stream) {
+  return contrib_map_impl<uint8_t>(g, x, nb, h, w, cp, inv_std6, out_scale, cmap, grad6, stream);
+}
+
+extern "C" int bcosk_channel_affine(const void* x, int64_t rows, int32_t c, const float* alpha, const float* beta,
+                                    int32_t relu, void* y, int32_t dtype, void* stream) {
+  if (!x || !y || c % 8) return set_error(BCOSK_EINVAL, "channel_affine: bad argument");
+  const long long n = rows * (c / 8);
+  BCOSK_DTYPE_SWITCH(dtype, channel_affine_kernel<T><<<blocks_for(n, 256), 256, 0, S(stream)>>>(
+      reinterpret_cast<const T*>(x), rows, c, alpha, beta, relu, reinterpret_cast<T*>(y));)
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_mul(const void* a, const void* b, int64_t n, void* out, int32_t dtype, void* stream) {
+  if (!a || !b || !out || n % 8) return set_error(BCOSK_EINVAL, "mul: bad argument");
+  BCOSK_DTYPE_SWITCH(dtype, mul_kernel<T><<<blocks_for(n / 8, 256), 256, 0, S(stream)>>>(
+      reinterpret_cast<const T*>(a), reinterpret_cast<const T*>(b), n / 8, reinterpret_cast<T*>(out));)
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}

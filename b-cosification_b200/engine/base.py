@@ -1,0 +1,243 @@
+"""Shared machinery of the fused execution plans: buffers, forward conv emission, explain-dgrad emission.
+
+A plan owns its device buffers (NHWC 16-bit activations with optional precision planes, fp32 side
+tensors) and two flat launch lists, `fwd_ops` and `bwd_ops` (engine/ops.py).  Concrete networks
+(engine/resnet.py, ...) only decide which launches to emit.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from .. import _lib as L
+from . import ops as O
+from . import pack as P
+
+@dataclass
+class Act:
+    """An activation tensor in HBM: [nb, h, w, planes*c] + partial per-pixel sums of squares."""
+    t: Tensor
+    c: int
+    sq: Optional[Tensor] = None      # [parts, nb*h*w] fp32
+    parts: int = 0
+
+    @property
+    def hw(self) -> Tuple[int, int]:
+        return self.t.shape[1], self.t.shape[2]
+
+
+@dataclass
+class ConvRec:
+    """What the explanation pass needs to remember about one fused conv launch."""
+    name: str
+    w: Tensor                 # [o, c, kh, kw] fp32 as seen by the GEMM (stem: space-to-depth form)
+    stride: int
+    pad_lo: int
+    pad_hi: int
+    in_hw: Tuple[int, int]
+    out_hw: Tuple[int, int]
+    cin_phys: int             # channels per plane of the input tensor
+    gain: Optional[Tensor] = None
+    mask: Optional[Tensor] = None
+    ghat: Optional[Tensor] = None          # gradient wrt the pre-scale linear output (x gain), maybe zero-inserted
+    ghat_map: Optional[Tuple[int, int, int, int]] = None
+    algo_flops: float = 0.0
+
+    @property
+    def k(self) -> int:
+        return self.w.shape[2]
+
+    @property
+    def cout(self) -> int:
+        return self.w.shape[0]
+
+
+@dataclass
+class BlockRec:
+    name: str
+    convs: List[ConvRec]
+    ds: Optional[ConvRec]
+    x: Act
+    y: Act
+    mask: Tensor
+    side: Optional[Tensor] = None   # gradient entering the identity / downsample branch
+
+
+
+class PlanBase:
+    """Buffers + launch emission shared by all network plans."""
+
+    def __init__(self, batch: int, *, planes: int = 1, dtype: str = "bf16", device="cuda", explain: bool = True,
+                 b: float = 2.0, bn_eps: float = 1e-5, state_dict: Optional[Dict[str, Tensor]] = None):
+        self.nb, self.planes, self.device = batch, planes, torch.device(device)
+        self.dt_code = L.DTYPE_CODE[dtype]
+        self.dt = torch.bfloat16 if dtype == "bf16" else torch.float16
+        self.gain_dt = self.dt if planes == 1 else torch.float32
+        self.b, self.bn_eps = float(b), bn_eps
+        self.scale_mode = L.BCOSK_SCALE_NONE if b == 1 else (L.BCOSK_SCALE_B2 if b == 2 else L.BCOSK_SCALE_POW)
+        self.sd = {k: v.detach().to(torch.float32) for k, v in (state_dict or {}).items() if v.is_floating_point()}
+        self.with_explain = explain
+        self.fwd_ops: List = []
+        self.bwd_ops: List = []
+        self._graph_fwd = None
+        self._graph_all = None
+
+    # ------------------------------------------------------------------ allocation helpers
+    def _zeros(self, *shape, dtype=None) -> Tensor:
+        return torch.zeros(*shape, dtype=dtype or self.dt, device=self.device)
+
+    def _empty(self, *shape, dtype=None) -> Tensor:
+        # zeros (not empty): tails that the kernels never write must stay finite
+        return torch.zeros(*shape, dtype=dtype or self.dt, device=self.device)
+
+    def _dev(self, t: Tensor, dtype=torch.float32) -> Tensor:
+        return t.to(device=self.device, dtype=dtype).contiguous()
+
+    def _bn_alpha(self, prefix: str) -> Tuple[Tensor, Optional[Tensor]]:
+        """eval-mode batch_norm_uncentered_2d: y = x / sqrt(running_var + eps) * weight (+ bias)."""
+        var = self.sd[prefix + ".running_var"]
+        w = self.sd.get(prefix + ".weight")
+        alpha = 1.0 / torch.sqrt(var + self.bn_eps)
+        if w is not None:
+            alpha = alpha * w
+        beta = self.sd.get(prefix + ".bias")
+        return self._dev(alpha), (None if beta is None else self._dev(beta))
+
+    # ------------------------------------------------------------------ forward emission
+    def _conv_fwd(self, name: str, x: Act, w: Tensor, stride: int, pad_lo: int, pad_hi: int, *, bn: Optional[str],
+                  relu: bool, res: Optional[Act] = None, want_mask: bool = False, y_f32: bool = False,
+                  inv_norm: Optional[Tensor] = None, kch: int = 64, want_sq: bool = True) -> Tuple[Act, ConvRec]:
+        nb = self.nb
+        h, wd = x.hw
+        o, c, kh, kw = w.shape
+        oh = (h + pad_lo + pad_hi - kh) // stride + 1
+        ow = (wd + pad_lo + pad_hi - kw) // stride + 1
+        M = nb * oh * ow
+        cin_phys = x.t.shape[-1] // self.planes
+        assert c <= cin_phys
+        if inv_norm is None and self.scale_mode != L.BCOSK_SCALE_NONE:
+            inv_norm = self._empty(M, dtype=torch.float32)
+            self.fwd_ops.append(O.PatchNormOp(name + ".norm", x.sq, x.parts, nb, h, wd, kh, stride, pad_lo, 1e-6, 0.0,
+                                              inv_norm, oh, ow))
+        bmat, cpt = P.pack_b(P.fwd_weight_taps(w), self.planes, kch, self.dt)
+        alpha, beta = self._bn_alpha(bn) if bn else (None, None)
+        block_n = 32 if o <= 32 else (64 if o <= 64 else 128)
+        parts = (o + block_n - 1) // block_n
+        yp = 1 if y_f32 else self.planes
+        y = self._empty(nb, oh, ow, yp * o, dtype=torch.float32 if y_f32 else self.dt)
+        rec = ConvRec(name, w, stride, pad_lo, pad_hi, (h, wd), (oh, ow), cin_phys)
+        if self.with_explain:
+            rec.gain = self._empty(M, o, dtype=self.gain_dt)
+            if want_mask:
+                rec.mask = self._zeros(M, (o + 31) // 32, dtype=torch.int32)
+        sq = self._empty(parts, M, dtype=torch.float32) if want_sq else None
+        self.fwd_ops.append(O.IgemmOp(
+            name=name, a=x.t, b=self._dev(bmat, self.dt), n=o, lo=(-pad_lo, -pad_lo),
+            up=(pad_hi - (kw - 1), pad_hi - (kh - 1)), stride=(stride, stride), op=oh, oq=ow, kch=kch, chunks_per_tap=cpt,
+            taps=P.conv_taps(kh, kw), seg_a_choff=P.seg_a_offsets(self.planes, cin_phys), dtype=self.dt_code,
+            mode=L.BCOSK_MODE_FWD, block_n=block_n, scale_mode=self.scale_mode, b_exp=self.b, relu=relu,
+            inv_norm=inv_norm, alpha=alpha, beta=beta, res=None if res is None else res.t, res_planes=self.planes,
+            gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32,
+            algo_flops=2.0 * M * o * float((w != 0).sum().item()) / o))
+        rec.algo_flops = self.fwd_ops[-1].algo_flops
+        return Act(y, o, sq, parts), rec
+
+    # ------------------------------------------------------------------ explanation emission
+    def _alloc_ghat(self, rec: ConvRec) -> None:
+        """Buffer for g_out * gain of `rec`.  A strided k>1 conv reads it zero-inserted at input resolution so
+        that its data gradient is a stride-1 gather."""
+        nb, pl = self.nb, self.planes
+        if rec.stride > 1 and rec.k > 1:
+            h, w = rec.in_hw
+            assert rec.stride * (rec.out_hw[0] - 1) <= h - 1 and rec.stride * (rec.out_hw[1] - 1) <= w - 1
+            rec.ghat = self._zeros(nb, h, w, pl * rec.cout)
+            rec.ghat_map = (0, h * w, rec.stride * w, rec.stride)
+        else:
+            rec.ghat = self._zeros(nb, rec.out_hw[0], rec.out_hw[1], pl * rec.cout)
+            rec.ghat_map = None
+
+    def _dgrad(self, rec: ConvRec, *, y: Tensor, y_map=None, mul1: Optional[Tensor] = None, add: Optional[Tensor] = None,
+               add_stride: int = 1, out2: Optional[Tensor] = None, mul2: Optional[Tensor] = None,
+               mask2: Optional[Tensor] = None, y_f32: bool = False, kch: int = 64) -> None:
+        """Data gradient of `rec` as a stride-1 gather over rec.ghat (tcgen05 implicit GEMM, explain epilogue)."""
+        g = rec.ghat
+        k = rec.k
+        if rec.stride > 1 and k == 1:
+            oh, ow = rec.out_hw      # dense GEMM at output resolution; consumer adds it sub-sampled
+        else:
+            oh, ow = rec.in_hw
+        lo = rec.pad_lo - (k - 1)
+        up_h = oh - g.shape[1] + lo
+        up_w = ow - g.shape[2] + lo
+        n = rec.cin_phys
+        wt = P.dgrad_weight_taps(rec.w)                      # [c, taps, o]
+        if wt.shape[0] < n:                                  # physical input channels beyond the logical ones
+            wt = torch.cat([wt, wt.new_zeros(n - wt.shape[0], *wt.shape[1:])], 0)
+        bmat, cpt = P.pack_b(wt, self.planes, kch, self.dt)
+        self.bwd_ops.append(O.IgemmOp(
+            name=rec.name + ".dgrad", a=g, b=self._dev(bmat, self.dt), n=n, lo=(lo, lo), up=(up_w, up_h), stride=(1, 1),
+            op=oh, oq=ow, kch=kch, chunks_per_tap=cpt, taps=P.conv_taps(k, k),
+            seg_a_choff=P.seg_a_offsets(self.planes, rec.cout), dtype=self.dt_code, mode=L.BCOSK_MODE_EXPLAIN,
+            block_n=32 if n <= 32 else (64 if n <= 64 else 128), y=y, y_planes=1 if y_f32 else self.planes, y_f32=y_f32,
+            out_map=y_map, add=add, add_planes=self.planes, add_stride=add_stride, mul1=mul1, out2=out2,
+            out2_planes=self.planes, mul2=mul2, mask2=mask2, algo_flops=rec.algo_flops,
+            a_dense_frac=1.0 / (rec.stride * rec.stride) if rec.ghat_map is not None else 1.0))
+
+    # ------------------------------------------------------------------ execution
+    def _require_gpu(self) -> None:
+        if self.device.type != "cuda":
+            raise L.BcoskError("plans execute only on a CUDA device (sm_100a); no CPU fallback exists")
+        L.require_device()
+
+    def run_forward(self) -> None:
+        self._require_gpu()
+        O.run_ops(self.fwd_ops)
+
+    def run_explain(self) -> None:
+        self._require_gpu()
+        O.run_ops(self.bwd_ops)
+
+    def capture(self) -> None:
+        """Capture forward and forward+explain as CUDA graphs (kernel parameters incl. TMA descriptors are baked in)."""
+        self._require_gpu()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.run_forward()
+            if self.with_explain:
+                self.run_explain()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._graph_fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_fwd):
+            O.run_ops(self.fwd_ops)
+        if self.with_explain:
+            self._graph_all = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_all):
+                O.run_ops(self.fwd_ops)
+                O.run_ops(self.bwd_ops)
+
+    def replay_forward(self) -> None:
+        if self._graph_fwd is not None:
+            self._graph_fwd.replay()
+        else:
+            self.run_forward()
+
+    def replay_all(self) -> None:
+        if self._graph_all is not None:
+            self._graph_all.replay()
+        else:
+            self.run_forward()
+            self.run_explain()
+
+    # ------------------------------------------------------------------ accounting
+    def num_launches(self, explain: bool = True) -> int:
+        return len(self.fwd_ops) + (len(self.bwd_ops) if explain else 0)
+
+    def gemm_flops(self, explain: bool = True) -> float:
+        ops = self.fwd_ops + (self.bwd_ops if explain else [])
+        return sum(o.flops() for o in ops if isinstance(o, O.IgemmOp))

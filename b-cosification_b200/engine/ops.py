@@ -1,0 +1,312 @@
+"""Launch records of the fused execution plans.
+
+A plan is a flat list of these records; each one names the device tensors it reads/writes and maps
+1:1 onto one entry point of the C ABI (include/bcosk.h).  `run()` enqueues the kernel on the current
+CUDA stream through ctypes - there is no other execution path in the product (tests/emulator.py holds
+a torch restatement of each record's semantics that is used ONLY to check plans on CPU).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from .. import _lib as L
+
+
+@dataclass
+class IgemmOp:
+    """One `bcosk_igemm` launch (forward B-cos epilogue or explain-dgrad epilogue)."""
+    name: str
+    a: Tensor                      # [nb, h, w, a_c] 16-bit NHWC (a_c = planes * channels)
+    b: Tensor                      # [n, ktot] packed weights
+    n: int
+    lo: Tuple[int, int]            # (w, h) lower corner
+    up: Tuple[int, int]
+    stride: Tuple[int, int]
+    op: int
+    oq: int
+    kch: int
+    chunks_per_tap: int
+    taps: List[Tuple[int, int]]    # (off_w, off_h)
+    seg_a_choff: List[int]
+    dtype: int
+    mode: int = 0
+    block_n: int = 0
+    # forward epilogue
+    scale_mode: int = 0
+    b_exp: float = 2.0
+    relu: bool = False
+    inv_norm: Optional[Tensor] = None
+    alpha: Optional[Tensor] = None
+    beta: Optional[Tensor] = None
+    res: Optional[Tensor] = None
+    res_planes: int = 1
+    gain: Optional[Tensor] = None
+    maskbits: Optional[Tensor] = None
+    sq_out: Optional[Tensor] = None
+    # primary output
+    y: Optional[Tensor] = None
+    y_planes: int = 1
+    y_f32: bool = False
+    out_map: Optional[Tuple[int, int, int, int]] = None   # (os_0, os_n, os_p, os_q); None = dense
+    # explain epilogue
+    add: Optional[Tensor] = None
+    add_planes: int = 1
+    add_stride: int = 1
+    mul1: Optional[Tensor] = None
+    out2: Optional[Tensor] = None
+    out2_planes: int = 1
+    mul2: Optional[Tensor] = None
+    mask2: Optional[Tensor] = None
+    # accounting (set by the plan): 2*MAC of the logical convolution, fraction of `a` that is not structural zeros
+    algo_flops: float = 0.0
+    a_dense_frac: float = 1.0
+
+    # ---- derived ----
+    @property
+    def M(self) -> int:
+        return self.a.shape[0] * self.op * self.oq
+
+    @property
+    def ktot(self) -> int:
+        return len(self.seg_a_choff) * len(self.taps) * self.chunks_per_tap * self.kch
+
+    def flops(self) -> float:
+        return 2.0 * self.M * self.n * self.ktot
+
+    def algo_bytes(self) -> float:
+        """Algorithmic HBM bytes of this launch: every operand / result tensor moved exactly once
+        (x, W, y, gain, mask, sq, residual | g_out, W, g_in, gains, masks, extra gradient)."""
+        def nbytes(t):
+            return 0.0 if t is None else float(t.numel() * t.element_size())
+        nb, h, w, ac = self.a.shape
+        strided_1x1 = len(self.taps) == 1 and self.stride[0] > 1
+        a_pix = self.M if strided_1x1 else nb * h * w
+        total = a_pix * ac * self.a.element_size() * self.a_dense_frac
+        total += nbytes(self.b)
+        ydense = self.M * (self.y.shape[-1]) * self.y.element_size()      # rows actually written
+        total += ydense
+        for t in (self.inv_norm, self.alpha, self.beta, self.res, self.gain, self.maskbits, self.sq_out, self.add,
+                  self.mul1, self.out2, self.mul2, self.mask2):
+            total += nbytes(t)
+        return total
+
+    def resolved_block_n(self) -> int:
+        if self.block_n:
+            return self.block_n
+        return 32 if self.n <= 32 else (64 if self.n <= 64 else 128)
+
+    def params(self) -> L.IgemmParams:
+        p = L.IgemmParams()
+        nb, h, w, ac = self.a.shape
+        p.a = self.a.data_ptr()
+        p.a_nb, p.a_h, p.a_w, p.a_c = nb, h, w, ac
+        p.lo_w, p.lo_h = self.lo
+        p.up_w, p.up_h = self.up
+        p.stride_w, p.stride_h = self.stride
+        p.op, p.oq = self.op, self.oq
+        p.kch, p.chunks_per_tap = self.kch, self.chunks_per_tap
+        p.num_taps, p.num_segs = len(self.taps), len(self.seg_a_choff)
+        for i, o in enumerate(self.seg_a_choff):
+            p.seg_a_choff[i] = o
+        for i, (ow, oh) in enumerate(self.taps):
+            p.tap_off_w[i], p.tap_off_h[i] = ow, oh
+        assert self.b.shape == (self.n, self.ktot), (self.name, self.b.shape, self.n, self.ktot)
+        p.b = self.b.data_ptr()
+        p.n, p.dtype, p.block_n, p.mode = self.n, self.dtype, self.resolved_block_n(), self.mode
+        p.scale_mode, p.b_exp, p.relu = self.scale_mode, self.b_exp, int(self.relu)
+        p.set_ptr("inv_norm", self.inv_norm)
+        p.set_ptr("alpha", self.alpha)
+        p.set_ptr("beta", self.beta)
+        if self.res is not None:
+            p.res = self.res.data_ptr()
+            p.res_ld = self.res.shape[-1]
+            p.res_planes = self.res_planes
+            p.res_plane_stride = self.res.shape[-1] // self.res_planes
+        if self.gain is not None:
+            p.gain = self.gain.data_ptr()
+            p.gain_ld = self.gain.shape[-1]
+            p.gain_f32 = int(self.gain.dtype == torch.float32)
+        if self.maskbits is not None:
+            p.maskbits = self.maskbits.data_ptr()
+            p.mask_ld = self.maskbits.shape[-1]
+        p.set_ptr("sq_out", self.sq_out)
+        p.y = self.y.data_ptr()
+        p.y_ld = self.y.shape[-1]
+        p.y_planes = self.y_planes
+        p.y_plane_stride = self.y.shape[-1] // self.y_planes
+        p.y_f32 = int(self.y_f32)
+        if self.out_map is None:
+            p.os_0, p.os_n, p.os_p, p.os_q = 0, self.op * self.oq, self.oq, 1
+        else:
+            p.os_0, p.os_n, p.os_p, p.os_q = self.out_map
+        if self.add is not None:
+            p.add = self.add.data_ptr()
+            p.add_ld = self.add.shape[-1]
+            p.add_planes = self.add_planes
+            p.add_plane_stride = self.add.shape[-1] // self.add_planes
+            p.add_stride = self.add_stride
+            p.add_p, p.add_q = self.add.shape[1], self.add.shape[2]
+        if self.mul1 is not None:
+            p.mul1 = self.mul1.data_ptr()
+            p.mul1_ld = self.mul1.shape[-1]
+            p.mul1_f32 = int(self.mul1.dtype == torch.float32)
+        if self.out2 is not None:
+            p.out2 = self.out2.data_ptr()
+            p.out2_ld = self.out2.shape[-1]
+            p.out2_planes = self.out2_planes
+            p.out2_plane_stride = self.out2.shape[-1] // self.out2_planes
+        if self.mul2 is not None:
+            p.mul2 = self.mul2.data_ptr()
+            p.mul2_ld = self.mul2.shape[-1]
+            p.mul2_f32 = int(self.mul2.dtype == torch.float32)
+        if self.mask2 is not None:
+            p.mask2 = self.mask2.data_ptr()
+            p.mask2_ld = self.mask2.shape[-1]
+        return p
+
+    def run(self) -> None:
+        L.igemm(self.params())
+
+
+@dataclass
+class InputPrepOp:
+    name: str
+    x: Tensor            # [nb, 6, h, w] fp32
+    mean6: Tuple[float, ...]
+    inv_std6: Tuple[float, ...]
+    out: Tensor          # [nb, h/2, w/2, planes*cp]
+    cp: int
+    planes: int
+    dtype: int
+    sq: Optional[Tensor]  # [nb*h*w] fp32
+
+    def run(self) -> None:
+        L.input_prep_s2d(self.x, self.mean6, self.inv_std6, self.out, self.cp, self.planes, self.dtype, self.sq)
+
+
+@dataclass
+class PatchNormOp:
+    name: str
+    sq: Tensor           # [parts, nb*h*w] fp32
+    parts: int
+    nb: int
+    h: int
+    w: int
+    k: int
+    stride: int
+    pad: int
+    eps_in: float
+    eps_out: float
+    inv_norm: Tensor     # [nb*op*oq]
+    op: int
+    oq: int
+
+    def run(self) -> None:
+        L.patch_inv_norm(self.sq, self.parts, self.nb, self.h, self.w, self.k, self.k, self.stride, self.pad, self.eps_in,
+                         self.eps_out, self.inv_norm, self.op, self.oq)
+
+
+@dataclass
+class AvgPoolFwdOp:
+    name: str
+    x: Tensor            # [nb, h, w, planes*c]
+    c: int
+    planes: int
+    k: int
+    stride: int
+    pad: int
+    y: Tensor            # [nb, op, oq, planes*c]
+    dtype: int
+    sq: Optional[Tensor]
+
+    def run(self) -> None:
+        nb, h, w, _ = self.x.shape
+        L.avgpool_fwd(self.x, nb, h, w, self.c, self.planes, self.k, self.stride, self.pad, self.y, self.y.shape[1],
+                      self.y.shape[2], self.dtype, self.sq)
+
+
+@dataclass
+class AvgPoolBwdMulOp:
+    name: str
+    gy: Tensor           # [nb, op, oq, planes*c]
+    c: int
+    planes: int
+    k: int
+    stride: int
+    pad: int
+    gain: Optional[Tensor]  # [nb*h*w, c]
+    gx: Tensor           # [nb, h, w, planes*c]
+    dtype: int
+
+    def run(self) -> None:
+        nb, h, w, _ = self.gx.shape
+        L.avgpool_bwd_mul(self.gy, nb, h, w, self.c, self.planes, self.k, self.stride, self.pad, self.gy.shape[1],
+                          self.gy.shape[2], self.gain, self.gain is not None and self.gain.dtype == torch.float32,
+                          self.gx, self.dtype)
+
+
+@dataclass
+class GapLogitsOp:
+    name: str
+    fc: Tensor           # [nb*npix, ncls] fp32
+    nb: int
+    npix: int
+    ncls: int
+    inv_temp: float
+    bias: float
+    logits: Tensor       # [nb, ncls] fp32
+    pred: Tensor         # [nb] int32
+
+    def run(self) -> None:
+        L.gap_logits(self.fc, self.nb, self.npix, self.ncls, self.inv_temp, self.bias, self.logits, self.pred)
+
+
+@dataclass
+class FcSeedOp:
+    name: str
+    target: Tensor       # [nb] int32
+    gain_fc: Tensor      # [nb*npix, ncls]
+    w_fc: Tensor         # [ncls, c] fp32
+    nb: int
+    npix: int
+    ncls: int
+    c: int
+    inv_temp: float
+    seed_scale: float
+    mul1: Optional[Tensor]
+    out1: Tensor         # [nb*npix, planes*c]
+    mask2: Optional[Tensor]
+    out2: Optional[Tensor]
+    planes: int
+    dtype: int
+
+    def run(self) -> None:
+        L.fc_seed_dgrad(self.target, self.gain_fc, self.gain_fc.dtype == torch.float32, self.w_fc, self.nb, self.npix,
+                        self.ncls, self.c, self.inv_temp, self.seed_scale, self.mul1,
+                        self.mul1 is not None and self.mul1.dtype == torch.float32, self.out1, self.mask2, self.out2,
+                        self.planes, self.dtype)
+
+
+@dataclass
+class ContribMapOp:
+    name: str
+    g: Tensor            # [nb, h/2, w/2, cp] fp32 (space-to-depth stem gradient)
+    x: Tensor            # [nb, 6, h, w] fp32
+    cp: int
+    inv_std6: Tuple[float, ...]
+    out_scale: float
+    cmap: Tensor         # [nb, h, w] fp32
+    grad6: Optional[Tensor]  # [nb, 6, h, w] fp32
+
+    def run(self) -> None:
+        nb, _, h, w = self.x.shape
+        L.contrib_map_s2d(self.g, self.x, nb, h, w, self.cp, self.inv_std6, self.out_scale, self.cmap, self.grad6)
+
+
+def run_ops(ops) -> None:
+    for o in ops:
+        o.run()

@@ -1,0 +1,96 @@
+"""Weight packing for the implicit GEMM (`bcosk_igemm`): K-major [n][segment][tap][channel chunk].
+
+Precision planes.  A tensor with P planes stores value = sum_p plane_p (each plane 16-bit).  A GEMM on
+split operands is evaluated as a sum of plane products, dropping the terms below ~2^-(8P) relative:
+    P=1: a0*b0          P=2: a0*b0 + a0*b1 + a1*b0          P=3: + a0*b2 + a2*b0 + a1*b1
+Each product is one K "segment": the kernel walks (segment, tap, channel-chunk) and only needs the A
+plane's channel offset per segment; the B planes are laid out here in the same order.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+SEGMENTS = {
+    1: [(0, 0)],
+    2: [(0, 0), (0, 1), (1, 0)],
+    3: [(0, 0), (0, 1), (1, 0), (0, 2), (2, 0), (1, 1)],
+}
+
+
+def split_planes(x: Tensor, planes: int, dtype: torch.dtype) -> List[Tensor]:
+    """fp32 -> `planes` 16-bit tensors whose (fp32) sum approximates x to ~8*planes mantissa bits (bf16)."""
+    r = x.to(torch.float32)
+    out = []
+    for _ in range(planes):
+        h = r.to(dtype)
+        out.append(h)
+        r = r - h.to(torch.float32)
+    return out
+
+
+def join_planes(t: Tensor, planes: int) -> Tensor:
+    """[..., planes*C] 16-bit -> [..., C] fp32 (sum of planes)."""
+    c = t.shape[-1] // planes
+    acc = t[..., :c].to(torch.float32)
+    for p in range(1, planes):
+        acc = acc + t[..., p * c:(p + 1) * c].to(torch.float32)
+    return acc
+
+
+def pack_b(wt: Tensor, planes: int, kch: int, dtype: torch.dtype) -> Tuple[Tensor, int]:
+    """wt [n, taps, c] fp32 (one [n, c] matrix per tap) -> (B [n, segs*taps*cpt*kch], chunks_per_tap)."""
+    n, taps, c = wt.shape
+    cpt = (c + kch - 1) // kch
+    pl = split_planes(wt, planes, dtype)
+    segs = SEGMENTS[planes]
+    out = torch.zeros(n, len(segs), taps, cpt * kch, dtype=dtype, device=wt.device)
+    for s, (_, bp) in enumerate(segs):
+        out[:, s, :, :c] = pl[bp]
+    return out.reshape(n, len(segs) * taps * cpt * kch).contiguous(), cpt
+
+
+def seg_a_offsets(planes: int, a_plane_channels: int) -> List[int]:
+    return [ap * a_plane_channels for ap, _ in SEGMENTS[planes]]
+
+
+def conv_taps(kh: int, kw: int, dil: int = 1) -> List[Tuple[int, int]]:
+    """Tap order (kh-major) as (off_w, off_h)."""
+    return [(j * dil, i * dil) for i in range(kh) for j in range(kw)]
+
+
+def fwd_weight_taps(w: Tensor) -> Tensor:
+    """W [o, c, kh, kw] -> [o, kh*kw, c] in conv_taps order (forward / fprop)."""
+    o, c, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(o, kh * kw, c)
+
+
+def dgrad_weight_taps(w: Tensor) -> Tensor:
+    """W [o, c, kh, kw] -> [c, kh*kw, o]: tap (off_h, off_w) of the stride-1 data-gradient gather uses
+    W[:, :, kh-1-off_h, kw-1-off_w]  (d[h] = sum_off g[h + pad-(k-1) + off] * W[k-1-off])."""
+    o, c, kh, kw = w.shape
+    wf = torch.flip(w, dims=(2, 3))
+    return wf.permute(1, 2, 3, 0).reshape(c, kh * kw, o)
+
+
+def stem_s2d_weight(w7: Tensor, cp: int) -> Tensor:
+    """7x7/2 pad-3 stem on [x,1-x] (6 ch) == 4x4/1 conv (pad 2 low, 1 high) on the 2x2 space-to-depth input:
+    W4[o, (dy*2+dx)*6 + c, tr, ts] = W7[o, c, 2*tr+dy-1, 2*ts+dx-1] (zero outside the 7x7 support)."""
+    o, c, kh, kw = w7.shape
+    assert (c, kh, kw) == (6, 7, 7)
+    w4 = torch.zeros(o, cp, 4, 4, dtype=w7.dtype, device=w7.device)
+    for dy in range(2):
+        for dx in range(2):
+            for tr in range(4):
+                i = 2 * tr + dy - 1
+                if not 0 <= i < 7:
+                    continue
+                for ts in range(4):
+                    j = 2 * ts + dx - 1
+                    if not 0 <= j < 7:
+                        continue
+                    base = (dy * 2 + dx) * 6
+                    w4[:, base:base + 6, tr, ts] = w7[:, :, i, j]
+    return w4

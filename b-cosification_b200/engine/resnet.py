@@ -1,0 +1,196 @@
+"""Fused execution plan for B-cosified ResNets: forward + dynamic-linear explanation.
+
+Network (reference): `BcosifyNetwork(ResNetBcos(...))` bcosify.py:22-53 on the torchvision skeleton with
+FC-before-GAP (bcos/models/standard_models.py:36-54), maxpool -> AvgPool2d(3,2,1) and all biases removed
+(bcos/experiments/ImageNet/bcosification/model.py:47-55).  Explanation: `BcosUtilMixin.explain`
+bcos/common.py:92-188 evaluated for the whole batch at once (images are independent in eval mode).
+
+Every conv+BN(+residual)+ReLU group is ONE `bcosk_igemm` launch (tcgen05 implicit GEMM, fused epilogue);
+the explanation pass is the chain of explain-dgrad launches whose epilogues multiply by the producer
+layer's saved gain, so no stand-alone element-wise pass touches an activation-sized tensor except the two
+poolings.  Data layout in HBM: NHWC, 16-bit, optional precision planes (see engine/pack.py).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from .. import _lib as L
+from . import ops as O
+from . import pack as P
+from .base import Act, BlockRec, ConvRec, PlanBase
+
+IMAGENET_MEAN_ADDINVERSE = (0.485, 0.456, 0.406, 0.515, 0.544, 0.594)  # reference bcosify.py:14
+IMAGENET_STD_ADDINVERSE = (0.229, 0.224, 0.225, 0.229, 0.224, 0.225)   # reference bcosify.py:15
+
+RESNET_ARCH = {
+    "resnet18": ("basic", [2, 2, 2, 2]),
+    "resnet34": ("basic", [3, 4, 6, 3]),
+    "resnet50": ("bottleneck", [3, 4, 6, 3]),
+    "resnet101": ("bottleneck", [3, 4, 23, 3]),
+}
+
+
+class ResNetPlan(PlanBase):
+    def __init__(self, arch: str, state_dict: Dict[str, Tensor], batch: int, *, planes: int = 1, dtype: str = "bf16",
+                 device="cuda", image_size: int = 224, explain: bool = True, want_grad6: bool = False, b: float = 2.0,
+                 bn_eps: float = 1e-5, mean=IMAGENET_MEAN_ADDINVERSE, std=IMAGENET_STD_ADDINVERSE,
+                 logit_bias: Optional[float] = -math.log(1000 - 1), logit_temperature: Optional[float] = None,
+                 seed_scale: float = 1.0, stem_kch: int = 32, input_u8: bool = False):
+        super().__init__(batch, planes=planes, dtype=dtype, device=device, explain=explain, b=b, bn_eps=bn_eps,
+                         state_dict=state_dict)
+        self.arch = arch
+        self.kind, self.layers = RESNET_ARCH[arch]
+        self.mean, self.std = tuple(mean), tuple(std)
+        self.inv_std = tuple(1.0 / s for s in std)
+        self.logit_bias = 0.0 if logit_bias is None else float(logit_bias)
+        self.inv_temp = 1.0 if logit_temperature is None else 1.0 / float(logit_temperature)
+        self.seed_scale = float(seed_scale)
+        self.stem_kch = stem_kch
+        self.stem_cp = 32 if stem_kch == 32 else 64
+        self.size = image_size
+        self.input_u8 = input_u8
+        self.blocks: List[BlockRec] = []
+        self._build_forward()
+        if explain:
+            self._build_explain(want_grad6)
+
+    def _build_forward(self) -> None:
+        nb, S, pl = self.nb, self.size, self.planes
+        sd = self.sd
+        # network input: fp32 [nb,6,S,S] = [x, 1-x], or uint8 RGB [nb,3,S,S] (inverse channels formed on the fly)
+        self.x_in = self._empty(nb, 3, S, S, dtype=torch.uint8) if self.input_u8 else self._empty(nb, 6, S, S, dtype=torch.float32)
+        # ---- stem: normalise + space-to-depth, 7x7/2 conv as a 4x4/1 conv, BN, ReLU
+        h2 = S // 2
+        a0 = self._empty(nb, h2, h2, pl * self.stem_cp)
+        sq0 = self._empty(1, nb * S * S, dtype=torch.float32)
+        self.fwd_ops.append(O.InputPrepOp("input_prep", self.x_in, self.mean, self.inv_std, a0, self.stem_cp, pl,
+                                          self.dt_code, sq0))
+        inv0 = self._empty(nb * h2 * h2, dtype=torch.float32)
+        if self.scale_mode != L.BCOSK_SCALE_NONE:
+            self.fwd_ops.append(O.PatchNormOp("stem.norm", sq0, 1, nb, S, S, 7, 2, 3, 1e-6, 0.0, inv0, h2, h2))
+        w4 = P.stem_s2d_weight(sd["model.conv1.linear.weight"], self.stem_cp)
+        y1, self.stem = self._conv_fwd("stem", Act(a0, self.stem_cp), w4, 1, 2, 1, bn="model.bn1", relu=True,
+                                       inv_norm=inv0, kch=self.stem_kch, want_sq=False)
+        # ---- AvgPool2d(3, 2, 1) (replaces maxpool)
+        hp = (h2 + 2 - 3) // 2 + 1
+        p1 = self._empty(nb, hp, hp, pl * 64)
+        sqp = self._empty(1, nb * hp * hp, dtype=torch.float32)
+        self.fwd_ops.append(O.AvgPoolFwdOp("pool", y1.t, 64, pl, 3, 2, 1, p1, self.dt_code, sqp))
+        self.stem_out, self.pool_out = y1, Act(p1, 64, sqp, 1)
+        x = self.pool_out
+        # ---- residual stages
+        exp = 1 if self.kind == "basic" else 4
+        inplanes = 64
+        for li, (planes_, nblocks) in enumerate(zip([64, 128, 256, 512], self.layers), start=1):
+            for bi in range(nblocks):
+                stride = 2 if (li > 1 and bi == 0) else 1
+                pfx = f"model.layer{li}.{bi}"
+                has_ds = (pfx + ".downsample.0.linear.weight") in sd
+                idn, ds_rec = x, None
+                if has_ds:
+                    idn, ds_rec = self._conv_fwd(pfx + ".downsample", x, sd[pfx + ".downsample.0.linear.weight"], stride,
+                                                 0, 0, bn=pfx + ".downsample.1", relu=False, want_sq=False)
+                if self.kind == "basic":
+                    t1, r1 = self._conv_fwd(pfx + ".conv1", x, sd[pfx + ".conv1.linear.weight"], stride, 1, 1,
+                                            bn=pfx + ".bn1", relu=True)
+                    y, r2 = self._conv_fwd(pfx + ".conv2", t1, sd[pfx + ".conv2.linear.weight"], 1, 1, 1,
+                                           bn=pfx + ".bn2", relu=True, res=idn, want_mask=True)
+                    recs = [r1, r2]
+                else:
+                    t1, r1 = self._conv_fwd(pfx + ".conv1", x, sd[pfx + ".conv1.linear.weight"], 1, 0, 0,
+                                            bn=pfx + ".bn1", relu=True)
+                    t2, r2 = self._conv_fwd(pfx + ".conv2", t1, sd[pfx + ".conv2.linear.weight"], stride, 1, 1,
+                                            bn=pfx + ".bn2", relu=True)
+                    y, r3 = self._conv_fwd(pfx + ".conv3", t2, sd[pfx + ".conv3.linear.weight"], 1, 0, 0,
+                                           bn=pfx + ".bn3", relu=True, res=idn, want_mask=True)
+                    recs = [r1, r2, r3]
+                self.blocks.append(BlockRec(pfx, recs, ds_rec, x, y, recs[-1].mask))
+                x = y
+                inplanes = planes_ * exp
+        # ---- classifier (1x1 B-cos conv per position) -> GAP -> LogitLayer
+        wfc = sd["model.fc.linear.weight"]
+        self.ncls = wfc.shape[0]
+        fc, self.fc = self._conv_fwd("fc", x, wfc, 1, 0, 0, bn=None, relu=False, y_f32=True, want_sq=False)
+        self.npix = x.hw[0] * x.hw[1]
+        self.fc_out = fc.t.view(nb * self.npix, self.ncls)
+        self.logits = self._empty(nb, self.ncls, dtype=torch.float32)
+        self.pred = self._zeros(nb, dtype=torch.int32)
+        self.fwd_ops.append(O.GapLogitsOp("gap_logits", self.fc_out, nb, self.npix, self.ncls, self.inv_temp,
+                                          self.logit_bias, self.logits, self.pred))
+
+    def _build_explain(self, want_grad6: bool) -> None:
+        nb, pl = self.nb, self.planes
+        for blk in self.blocks:
+            for r in blk.convs:
+                self._alloc_ghat(r)
+            if blk.ds is not None:
+                self._alloc_ghat(blk.ds)
+                blk.side = blk.ds.ghat
+            else:
+                blk.side = self._zeros(*blk.y.t.shape)
+        self._alloc_ghat(self.stem)
+        last = self.blocks[-1]
+        assert last.ds is None, "classifier seed kernel expects an identity shortcut in the last block"
+        # ---- seed: d logit[target] / d fc-input, straight through GAP and the classifier's detached scale
+        c_last = last.y.c
+        self.w_fc32 = self._dev(self.sd["model.fc.linear.weight"].reshape(self.ncls, c_last))
+        self.bwd_ops.append(O.FcSeedOp("fc.seed", self.pred, self.fc.gain, self.w_fc32, nb, self.npix, self.ncls, c_last,
+                                       self.inv_temp, self.seed_scale, last.convs[-1].gain,
+                                       last.convs[-1].ghat.view(nb * self.npix, pl * c_last), last.mask,
+                                       last.side.view(nb * self.npix, pl * c_last), pl, self.dt_code))
+        # ---- blocks in reverse
+        self.g_pool = self._zeros(*self.pool_out.t.shape)
+        for bi in range(len(self.blocks) - 1, -1, -1):
+            blk = self.blocks[bi]
+            convs = blk.convs
+            for j in range(len(convs) - 1, 0, -1):       # conv_j's data gradient feeds conv_{j-1}'s ghat
+                self._dgrad(convs[j], y=convs[j - 1].ghat, y_map=convs[j - 1].ghat_map, mul1=convs[j - 1].gain)
+            add, add_stride = blk.side, 1
+            if blk.ds is not None:
+                dds = self._zeros(nb, blk.ds.out_hw[0], blk.ds.out_hw[1], pl * blk.ds.cin_phys) if blk.ds.stride > 1 \
+                    else self._zeros(*blk.x.t.shape)
+                self._dgrad(blk.ds, y=dds)
+                add, add_stride = dds, blk.ds.stride
+            if bi > 0:
+                prev = self.blocks[bi - 1]
+                self._dgrad(convs[0], y=prev.convs[-1].ghat, mul1=prev.convs[-1].gain, add=add, add_stride=add_stride,
+                            out2=prev.side, mul2=None if prev.ds is None else prev.ds.gain, mask2=prev.mask)
+            else:
+                self._dgrad(convs[0], y=self.g_pool, add=add, add_stride=add_stride)
+        # ---- pool backward x stem gain, stem data gradient (space-to-depth), contribution map
+        self.bwd_ops.append(O.AvgPoolBwdMulOp("pool.bwd", self.g_pool, 64, pl, 3, 2, 1, self.stem.gain, self.stem.ghat,
+                                              self.dt_code))
+        h2 = self.size // 2
+        self.g0 = self._zeros(nb, h2, h2, self.stem_cp, dtype=torch.float32)
+        self._dgrad(self.stem, y=self.g0, y_f32=True, kch=64)
+        self.cmap = self._zeros(nb, self.size, self.size, dtype=torch.float32)
+        self.grad6 = self._zeros(nb, 6, self.size, self.size, dtype=torch.float32) if want_grad6 else None
+        self.bwd_ops.append(O.ContribMapOp("contrib_map", self.g0, self.x_in, self.stem_cp, self.inv_std,
+                                           1.0 / self.seed_scale, self.cmap, self.grad6))
+
+    def load_input(self, x6: Tensor) -> None:
+        """x6: [nb, 6, H, W] float32 `[x, 1-x]`, or uint8 RGB [nb, 3, H, W] for an `input_u8` plan (host or device)."""
+        assert tuple(x6.shape) == tuple(self.x_in.shape), (x6.shape, self.x_in.shape)
+        self.x_in.copy_(x6, non_blocking=True)
+
+    def forward(self, x6: Optional[Tensor] = None) -> Tensor:
+        if x6 is not None:
+            self.load_input(x6)
+        self.replay_forward()
+        return self.logits
+
+    def explain(self, x6: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        """Forward + explanation of each image's predicted class (argmax logit)."""
+        if not self.with_explain:
+            raise RuntimeError("plan was built with explain=False")
+        if x6 is not None:
+            self.load_input(x6)
+        self.replay_all()
+        out = {"logits": self.logits, "prediction": self.pred, "contribution_map": self.cmap}
+        if self.grad6 is not None:
+            out["dynamic_linear_weights"] = self.grad6
+        return out

@@ -1,0 +1,58 @@
+"""Offline descriptions of the B-cosified networks (reference state-dict key names).
+
+The reference's factories download weights (bcos/experiments/ImageNet/bcosification/model.py:15-57); here the
+networks are described by their state-dict layout so that released checkpoints (`*.linear.weight`, BN buffers;
+reference scripts/strip_checkpoints.py:52-61) or the synthetic checkpoint load directly into the fused plans.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+from .engine.resnet import RESNET_ARCH, ResNetPlan
+from .utils import synth
+
+
+def resnet_state_shapes(arch: str, num_classes: int = 1000) -> Dict[str, Tuple[int, ...]]:
+    """Keys/shapes of `BcosifyNetwork(ResNetBcos(...))` (bcosify.py:22-53 over the torchvision ResNet skeleton,
+    bcos/models/standard_models.py:36-54) after the factories removed every bias."""
+    kind, layers = RESNET_ARCH[arch]
+    exp = 1 if kind == "basic" else 4
+    shapes: Dict[str, Tuple[int, ...]] = {}
+
+    def bn(prefix, c):
+        shapes[prefix + ".weight"] = (c,)
+        shapes[prefix + ".running_mean"] = (c,)
+        shapes[prefix + ".running_var"] = (c,)
+        shapes[prefix + ".num_batches_tracked"] = ()
+
+    shapes["model.conv1.linear.weight"] = (64, 6, 7, 7)
+    bn("model.bn1", 64)
+    inplanes = 64
+    for li, (planes, nblocks) in enumerate(zip([64, 128, 256, 512], layers), start=1):
+        for bi in range(nblocks):
+            stride = 2 if (li > 1 and bi == 0) else 1
+            p = f"model.layer{li}.{bi}"
+            if kind == "basic":
+                shapes[p + ".conv1.linear.weight"] = (planes, inplanes, 3, 3)
+                bn(p + ".bn1", planes)
+                shapes[p + ".conv2.linear.weight"] = (planes, planes, 3, 3)
+                bn(p + ".bn2", planes)
+            else:
+                shapes[p + ".conv1.linear.weight"] = (planes, inplanes, 1, 1)
+                bn(p + ".bn1", planes)
+                shapes[p + ".conv2.linear.weight"] = (planes, planes, 3, 3)
+                bn(p + ".bn2", planes)
+                shapes[p + ".conv3.linear.weight"] = (planes * 4, planes, 1, 1)
+                bn(p + ".bn3", planes * 4)
+            if stride != 1 or inplanes != planes * exp:
+                shapes[p + ".downsample.0.linear.weight"] = (planes * exp, inplanes, 1, 1)
+                bn(p + ".downsample.1", planes * exp)
+            inplanes = planes * exp
+    shapes["model.fc.linear.weight"] = (num_classes, 512 * exp, 1, 1)
+    return shapes
+
+
+def synthetic_resnet_plan(arch: str, batch: int, **plan_kwargs) -> ResNetPlan:
+    """Fused plan over the synthetic (random-init, BN-calibrated) checkpoint - the benchmark workload."""
+    sd = synth.synthetic_checkpoint(arch, resnet_state_shapes(arch))
+    return ResNetPlan(arch, sd, batch, **plan_kwargs)

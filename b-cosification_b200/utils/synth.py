@@ -73,3 +73,18 @@ def synth_state_dict(shapes: Dict[str, Tuple[int, ...]] | Iterable, seed: int = 
     if not isinstance(shapes, dict):
         shapes = dict(shapes)
     return {k: synth_tensor(k, tuple(s), seed) for k, s in shapes.items()}
+
+
+def synthetic_checkpoint(arch: str, shapes: Dict[str, Tuple[int, ...]], seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Synthetic weights (seed 0) + the shipped BN calibration (utils/calib/<arch>_bnvar.npz, written by
+    oracle/make_golden.py --only calib) -> a state dict with the reference's key names."""
+    import os
+    sd = synth_state_dict(shapes, seed)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "calib", f"{arch}_bnvar.npz")
+    z = np.load(path)
+    assert int(z["weights_seed"]) == seed, "calibration file belongs to another weight seed"
+    off = 0
+    for k, n in zip(z["bn_keys"].tolist(), z["bn_sizes"].tolist()):
+        sd[k] = torch.from_numpy(z["bn_var"][off:off + n].copy())
+        off += n
+    return sd

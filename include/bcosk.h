@@ -1,0 +1,195 @@
+/* bcosk.h -- C ABI of libbcosk.so: hand-written sm_100a kernels for the B-cos forward pass and its
+ * dynamic-linear explanation (explain-dgrad) pass.
+ *
+ * The reference (shrebox/B-cosification) is pure Python on ATen: it has no FFI of its own.  The
+ * boundary a maintainer binds is therefore the arithmetic behind its torch modules; each entry
+ * point below names the reference code it replaces (paths relative to the reference root).
+ * INTEGRATION.md shows the ctypes stub that binds these symbols inside `bcos.modules`.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; the caller owns all buffers; nothing here
+ *     allocates or synchronises; all work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - activations are NHWC ("channels_last"), 16-bit (bf16 or fp16).  A tensor may carry P precision
+ *     planes concatenated along the channel axis ([hi | lo | lo2], value = sum of planes); P=1 is
+ *     the plain 16-bit throughput mode, P=2/3 is the parity mode (~16/24 mantissa bits).
+ *   - return value: 0 ok, -1 bad argument, -2 unsupported shape / device, -3 CUDA error
+ *     (text via bcosk_last_error()).
+ */
+#ifndef BCOSK_H_
+#define BCOSK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCOSK_OK 0
+#define BCOSK_EINVAL (-1)
+#define BCOSK_EUNSUPPORTED (-2)
+#define BCOSK_ECUDA (-3)
+
+#define BCOSK_DTYPE_F16 0
+#define BCOSK_DTYPE_BF16 1
+
+#define BCOSK_MAX_TAPS 64
+#define BCOSK_MAX_SEGS 6
+
+/* epilogue modes of the implicit GEMM */
+#define BCOSK_MODE_FWD 0     /* B-cos forward epilogue */
+#define BCOSK_MODE_EXPLAIN 1 /* explanation-dgrad epilogue */
+
+/* scale modes (forward) */
+#define BCOSK_SCALE_NONE 0 /* plain linear map (B = 1, or nn.Linear / nn.Conv2d) */
+#define BCOSK_SCALE_B2 1   /* |lin| / ||patch||                       (bcosconv2d.py:186-187) */
+#define BCOSK_SCALE_POW 2  /* (|lin / ||patch||| + 1e-6)^(B-1)         (bcosconv2d.py:189-190) */
+
+/* One implicit-GEMM launch:   D[m, n] = sum_k A[m, k] * B[n, k]
+ *   m = output pixel (image, p, q) of an NHWC tensor gathered by TMA im2col, k = (segment, tap, channel).
+ * Forward  (replaces BcosConv2d.forward_impl bcos/modules/bcosconv2d.py:153-194, BcosifyConv2d.forward_impl
+ *           bcosifyconv2d.py:50-102, BcosLinear.forward bcoslinear.py:88-130, BcosifyLinear.forward
+ *           bcosifylinear.py:42-95 and, fused into the epilogue, batch_norm_uncentered_2d (eval)
+ *           batchnorm_uncentered.py:49-58, the block's residual add and nn.ReLU):
+ *     s    = scale(D, inv_norm[m]);  t = s * alpha[n];  v = D * t + beta[n] + res[m, n]
+ *     y    = relu ? max(v, 0) : v;   gain = (relu && v <= 0) ? 0 : t;   mask bit = (v > 0)
+ *     sq_out[tile_n][m] = sum_n y^2   (feeds the next layer's patch norm)
+ * Explain  (replaces autograd's MulBackward * detached scale -> ConvolutionBackward(dgrad) reached from
+ *           BcosUtilMixin.explain bcos/common.py:163-181):
+ *     tot  = D + add[m', n];   y = tot * mul1[m, n];   out2 = tot * mul2[m, n] * mask2 bit
+ */
+typedef struct bcosk_igemm_params {
+  /* ---- A operand: activations / output-gradients, NHWC 16-bit, total channels a_c per pixel */
+  const void* a;
+  int32_t a_nb, a_h, a_w, a_c;
+  int32_t lo_w, lo_h;         /* im2col lower corner: -pad (fprop) or pad-(k-1) (dgrad) */
+  int32_t up_w, up_h;         /* im2col upper corner: pad-(k-1)*dil (fprop) */
+  int32_t stride_w, stride_h; /* traversal stride */
+  int32_t op, oq;             /* output spatial extent; M = a_nb * op * oq */
+  /* ---- K loop: chunk i = ((seg * num_taps) + tap) * chunks_per_tap + kc, B column = i * kch */
+  int32_t kch;                /* channels per chunk: 64 (128B swizzle) or 32 (64B swizzle) */
+  int32_t chunks_per_tap;
+  int32_t num_taps;
+  int32_t num_segs;
+  int32_t seg_a_choff[BCOSK_MAX_SEGS]; /* first channel of the A plane used by segment s */
+  uint16_t tap_off_w[BCOSK_MAX_TAPS];
+  uint16_t tap_off_h[BCOSK_MAX_TAPS];
+  /* ---- B operand: packed weights [n][num_segs*num_taps*chunks_per_tap*kch], 16-bit, K-major */
+  const void* b;
+  int32_t n;
+  int32_t dtype;   /* BCOSK_DTYPE_* of a, b, and all 16-bit epilogue tensors */
+  int32_t block_n; /* CTA tile N: 32, 64, 128, 256; 0 = choose */
+  int32_t mode;    /* BCOSK_MODE_* */
+  /* ---- forward epilogue */
+  int32_t scale_mode; /* BCOSK_SCALE_* */
+  float b_exp;        /* B (used by BCOSK_SCALE_POW) */
+  int32_t relu;
+  const float* inv_norm; /* [M] 1/||patch||, NULL iff scale_mode == NONE */
+  const float* alpha;    /* [n] per-channel multiplier (BN weight/sqrt(var+eps)), NULL = 1 */
+  const float* beta;     /* [n] per-channel bias, NULL = 0 */
+  const void* res;       /* [M, res_ld] residual (16-bit planes), NULL = none */
+  int32_t res_ld, res_planes, res_plane_stride;
+  void* gain;            /* [M, gain_ld] d y / d lin under the detached scale; NULL = not saved */
+  int32_t gain_ld, gain_f32;
+  uint32_t* maskbits;    /* [M, mask_ld] ReLU mask, bit (n % 32) of word n / 32; NULL = not saved */
+  int32_t mask_ld;
+  float* sq_out;         /* [ceil(n / block_n)][M] partial sum_n y^2; NULL = not produced */
+  /* ---- primary output (forward: y, explain: y = tot * mul1); row m=(img,p,q) is written at
+   *      row  os_0 + img*os_n + p*os_p + q*os_q  (dense: os_n = op*oq, os_p = oq, os_q = 1) */
+  void* y;
+  int32_t y_ld, y_planes, y_plane_stride, y_f32;
+  int64_t os_0, os_n, os_p, os_q;
+  /* ---- explain epilogue */
+  const void* add;       /* extra gradient contribution (16-bit planes), spatially sub-sampled by add_stride */
+  int32_t add_ld, add_planes, add_plane_stride, add_stride, add_p, add_q;
+  const void* mul1;      /* [M, mul1_ld] gain of the producer layer, NULL = 1 */
+  int32_t mul1_ld, mul1_f32;
+  void* out2;            /* second output [M, out2_ld] = tot * mul2 * mask2 bit (each optional), NULL = none */
+  int32_t out2_ld, out2_planes, out2_plane_stride;
+  const void* mul2;
+  int32_t mul2_ld, mul2_f32;
+  const uint32_t* mask2;
+  int32_t mask2_ld;
+} bcosk_igemm_params;
+
+int bcosk_igemm(const bcosk_igemm_params* p, void* stream);
+
+/* Debug aid: raw bytes of the first A chunk (tile_m, chunk) as TMA im2col lands it in shared memory
+ * (128 rows x kch 16-bit values, de-swizzled) -> out[128*kch]. */
+int bcosk_debug_a_tile(const bcosk_igemm_params* p, int32_t tile_m, int32_t chunk, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Bandwidth kernels (coalesced, 16-byte vectorised, warp-shuffle reductions)
+ * ------------------------------------------------------------------------------------------- */
+
+/* BcosifyNetwork.forward bcosify.py:50-53 (Normalize(mean6, std6)) fused with the NCHW fp32 -> NHWC
+ * 16-bit layout change and the 2x2 space-to-depth that turns the 7x7/2 stem into a 4x4/1 conv:
+ *   x    [nb, 6, h, w] fp32 (un-normalised [x, 1-x])
+ *   out  [nb, h/2, w/2, planes * cp]   channel (dy*2+dx)*6 + c, zero padded to cp
+ *   sq   [nb, h, w] fp32  sum_c xn^2 per ORIGINAL pixel (for the stem patch norm); may be NULL */
+int bcosk_input_prep_s2d(const float* x, int32_t nb, int32_t h, int32_t w, const float* mean6, const float* inv_std6,
+                         void* out, int32_t cp, int32_t planes, int32_t dtype, float* sq, void* stream);
+/* Same, from uint8 RGB images x [nb, 3, h, w]: x/255 and the inverse channels 1 - x/255 (AddInverse,
+ * bcos/data/transforms.py:42-55) are formed on the fly (8x fewer host->device bytes than fp32 6-channel input). */
+int bcosk_input_prep_s2d_u8(const uint8_t* x, int32_t nb, int32_t h, int32_t w, const float* mean6,
+                            const float* inv_std6, void* out, int32_t cp, int32_t planes, int32_t dtype, float* sq,
+                            void* stream);
+
+/* BcosConv2d.calc_patch_norms bcosconv2d.py:196-231: inv_norm[img,p,q] = 1/sqrt(sumpool_k,s,p(sq) + eps_in) (conv)
+ * or 1/(sqrt(sq) + eps_out) (linear, bcoslinear.py:113).  sq holds `parts` partial maps [parts][nb*h*w]. */
+int bcosk_patch_inv_norm(const float* sq, int32_t parts, int32_t nb, int32_t h, int32_t w, int32_t kh, int32_t kw,
+                         int32_t stride, int32_t pad, float eps_in, float eps_out, float* inv_norm, int32_t op,
+                         int32_t oq, void* stream);
+
+/* sum_c x^2 per pixel of an NHWC 16-bit tensor with planes -> sq [rows] (module-level path). */
+int bcosk_pixel_sqsum(const void* x, int64_t rows, int32_t c, int32_t planes, int32_t plane_stride, int32_t ld,
+                      int32_t dtype, float* sq, void* stream);
+
+/* nn.AvgPool2d(k, s, pad) forward on NHWC 16-bit planes (count_include_pad=True), + optional sq map. */
+int bcosk_avgpool_fwd(const void* x, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t k,
+                      int32_t stride, int32_t pad, void* y, int32_t op, int32_t oq, int32_t dtype, float* sq,
+                      void* stream);
+
+/* Explain backward of AvgPool2d fused with the producer's gain: gx = avgpool_bwd(gy) * gain. */
+int bcosk_avgpool_bwd_mul(const void* gy, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t k,
+                          int32_t stride, int32_t pad, int32_t op, int32_t oq, const void* gain, int32_t gain_f32,
+                          void* gx, int32_t dtype, void* stream);
+
+/* ResNetBcos._forward_impl standard_models.py:50-52 tail + LogitLayer logitlayer.py:22-27:
+ * logits[img, cls] = mean_pix fc[img, pix, cls] * inv_temp + bias; pred[img] = argmax (first max). */
+int bcosk_gap_logits(const float* fc, int32_t nb, int32_t npix, int32_t ncls, float inv_temp, float bias,
+                     float* logits, int32_t* pred, void* stream);
+
+/* Explain seed through GAP + classifier (one-hot logit gradient; bcos/common.py:166-177):
+ *   g[img,pix,c] = inv_temp/npix * gain_fc[img,pix,cls] * W_fc[cls, c],  cls = target[img]
+ *   out1 = g * mul1 (gain of the producing conv), out2 = g * mask2 bit   (both 16-bit planes) */
+int bcosk_fc_seed_dgrad(const int32_t* target, const void* gain_fc, int32_t gain_f32, const float* w_fc, int32_t nb,
+                        int32_t npix, int32_t ncls, int32_t c, float inv_temp, float seed_scale, const void* mul1,
+                        int32_t mul1_f32, void* out1, const uint32_t* mask2, void* out2, int32_t planes, int32_t dtype,
+                        void* stream);
+
+/* (in_tensor * in_tensor.grad).sum(1) bcos/common.py:181, reading the stem dgrad in its space-to-depth
+ * layout g [nb, h/2, w/2, cp] fp32 and the raw input x [nb,6,h,w] fp32:
+ *   grad6[img,c,y,x] = g * inv_std6[c] * out_scale (optional output), cmap[img,y,x] = sum_c x * grad6 */
+int bcosk_contrib_map_s2d(const float* g, const float* x, int32_t nb, int32_t h, int32_t w, int32_t cp,
+                          const float* inv_std6, float out_scale, float* cmap, float* grad6, void* stream);
+int bcosk_contrib_map_s2d_u8(const float* g, const uint8_t* x, int32_t nb, int32_t h, int32_t w, int32_t cp,
+                             const float* inv_std6, float out_scale, float* cmap, float* grad6, void* stream);
+
+/* Generic element-wise helpers for the module-level (un-fused) path. */
+/* batch_norm_uncentered_2d eval (batchnorm_uncentered.py:49-58) / ReLU on NHWC 16-bit: y = relu?(x*alpha[c]+beta[c]) */
+int bcosk_channel_affine(const void* x, int64_t rows, int32_t c, const float* alpha, const float* beta, int32_t relu,
+                         void* y, int32_t dtype, void* stream);
+/* out = a * b element-wise (16-bit), used for g_out * detached scale */
+int bcosk_mul(const void* a, const void* b, int64_t n, void* out, int32_t dtype, void* stream);
+
+const char* bcosk_last_error(void);
+int bcosk_version(void);
+/* sizeof(bcosk_igemm_params) as compiled into the library (binding self-check). */
+int bcosk_sizeof_igemm_params(void);
+/* 1 when the current device is compute capability 10.x (sm_100a kernels can run). */
+int bcosk_device_supported(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCOSK_H_ */

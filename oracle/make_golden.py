@@ -254,6 +254,24 @@ def golden_modules(seed: int = 0):
     print(f"[modules] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB), {len(out)} arrays")
 
 
+def calibration_file(arch: str, batch: int = 16, seed: int = 100):
+    """BN running variances for the synthetic benchmark checkpoint (weights seed 0), calibrated on `batch` synthetic
+    images by the oracle (== the reference, see golden_resnet).  Shipped with the package so that bench.py needs no
+    oracle/reference at run time: random-init B-cos nets collapse to ~1e-13 activations without it."""
+    sd = synth.synth_state_dict(O.resnet_state_shapes(arch), 0)
+    x6 = synth.to_bcos_input(synth.synth_images_u8(batch, 224, seed))
+    om = O.OracleResNet(arch, sd)
+    om.calibrate_bn(x6)
+    keys = sorted(k for k in sd if k.endswith("running_var"))
+    d = os.path.join(ROOT, "b-cosification_b200", "utils", "calib")
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, f"{arch}_bnvar.npz")
+    np.savez_compressed(path, bn_keys=np.array(keys), bn_sizes=np.array([sd[k].numel() for k in keys], dtype=np.int64),
+                        bn_var=torch.cat([sd[k].flatten() for k in keys]).numpy(), weights_seed=np.int64(0),
+                        images_seed=np.int64(seed), batch=np.int64(batch))
+    print(f"[calib] wrote {path} ({os.path.getsize(path)/1e3:.0f} kB)")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="modules,resnet18,resnet50")
@@ -267,3 +285,6 @@ if __name__ == "__main__":
         golden_resnet("resnet18", 8)
     if "resnet50" in which:
         golden_resnet("resnet50", 4)
+    if "calib" in which:
+        calibration_file("resnet18")
+        calibration_file("resnet50")

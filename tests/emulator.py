@@ -1,0 +1,258 @@
+"""CPU restatement of every launch record in bcos_b200.engine.ops -- TEST INFRASTRUCTURE ONLY.
+
+It executes a plan's op list with plain torch on the CPU, following the kernels' documented semantics
+(include/bcosk.h) including the TMA im2col traversal, the packed (segment, tap, chunk) K order, precision
+planes and 16-bit storage rounding.  Used to (a) check the host-side plan logic (weight packing, tap
+tables, zero-insertion, residual/gradient routing) against the oracle without a GPU, and (b) as the
+per-kernel expected value in the `-m gpu` tests.  The product never imports this file.
+"""
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+from bcos_b200 import _lib as L
+from bcos_b200.engine import ops as O
+
+
+def _split_store(dst: Tensor, val: Tensor, planes: int) -> Tensor:
+    """val [..., C] fp32 -> dst [..., planes*C] 16-bit; returns the stored (representable) value."""
+    c = val.shape[-1]
+    r = val.clone()
+    acc = torch.zeros_like(val)
+    for p in range(planes):
+        h = r.to(dst.dtype)
+        dst[..., p * c:(p + 1) * c] = h
+        r = r - h.float()
+        acc = acc + h.float()
+    return acc
+
+
+def _join(t: Tensor, planes: int) -> Tensor:
+    c = t.shape[-1] // planes
+    acc = t[..., :c].float()
+    for p in range(1, planes):
+        acc = acc + t[..., p * c:(p + 1) * c].float()
+    return acc
+
+
+def gather_a(op: O.IgemmOp) -> Tensor:
+    """[M, ktot] fp32: what the TMA im2col loads deliver, chunk by chunk."""
+    a = op.a.float()
+    nb, h, w, ac = a.shape
+    # the TMA unit derives the number of base pixels per row/column from the bounding box; the plan must agree
+    assert op.oq == (w + op.up[0] - op.lo[0] - 1) // op.stride[0] + 1, (op.name, "oq vs im2col box")
+    assert op.op == (h + op.up[1] - op.lo[1] - 1) // op.stride[1] + 1, (op.name, "op vs im2col box")
+    assert -128 <= op.lo[0] <= 127 and -128 <= op.up[0] <= 127
+    p = torch.arange(op.op)
+    q = torch.arange(op.oq)
+    cols = []
+    for choff in op.seg_a_choff:
+        for (off_w, off_h) in op.taps:
+            hh = op.lo[1] + p * op.stride[1] + off_h
+            ww = op.lo[0] + q * op.stride[0] + off_w
+            vh = (hh >= 0) & (hh < h)
+            vw = (ww >= 0) & (ww < w)
+            t = a[:, hh.clamp(0, h - 1)][:, :, ww.clamp(0, w - 1)]           # [nb, op, oq, ac]
+            t = t * (vh[:, None] & vw[None, :])[None, :, :, None]
+            for kc in range(op.chunks_per_tap):
+                c0 = choff + kc * op.kch
+                chunk = torch.zeros(nb, op.op, op.oq, op.kch)
+                c1 = min(c0 + op.kch, ac)
+                if c1 > c0:
+                    chunk[..., :c1 - c0] = t[..., c0:c1]
+                cols.append(chunk.reshape(-1, op.kch))
+    return torch.cat(cols, dim=1)
+
+
+def _out_rows(op: O.IgemmOp) -> Tensor:
+    nb = op.a.shape[0]
+    img = torch.arange(nb).view(-1, 1, 1)
+    p = torch.arange(op.op).view(1, -1, 1)
+    q = torch.arange(op.oq).view(1, 1, -1)
+    if op.out_map is None:
+        os0, osn, osp, osq = 0, op.op * op.oq, op.oq, 1
+    else:
+        os0, osn, osp, osq = op.out_map
+    return (os0 + img * osn + p * osp + q * osq).reshape(-1)
+
+
+def _mask_bits(mask_words: Tensor, n: int) -> Tensor:
+    """[M, words] int32 -> [M, n] bool"""
+    w = mask_words.to(torch.int64) & 0xFFFFFFFF
+    bits = (w.unsqueeze(-1) >> torch.arange(32)) & 1
+    return bits.reshape(w.shape[0], -1)[:, :n].bool()
+
+
+def _pack_mask(pos: Tensor) -> Tensor:
+    """[M, n] bool -> [M, ceil(n/32)] int32"""
+    M, n = pos.shape
+    words = (n + 31) // 32
+    padded = torch.zeros(M, words * 32, dtype=torch.int64)
+    padded[:, :n] = pos.to(torch.int64)
+    v = (padded.view(M, words, 32) << torch.arange(32)).sum(-1)
+    v = torch.where(v >= 2**31, v - 2**32, v)
+    return v.to(torch.int32)
+
+
+def run_igemm(op: O.IgemmOp) -> None:
+    M, n = op.M, op.n
+    assert op.ktot % 64 == 0, "chunk count must fill whole pipeline stages"
+    A = gather_a(op)
+    D = A @ op.b.float().t()                      # [M, n]
+    rows = _out_rows(op)
+    if op.mode == L.BCOSK_MODE_FWD:
+        alpha = op.alpha.float() if op.alpha is not None else torch.ones(n)
+        beta = op.beta.float() if op.beta is not None else torch.zeros(n)
+        if op.scale_mode == L.BCOSK_SCALE_B2:
+            t = D.abs() * op.inv_norm.float()[:, None] * alpha
+        elif op.scale_mode == L.BCOSK_SCALE_POW:
+            t = (D.abs() * op.inv_norm.float()[:, None] + 1e-6).pow(op.b_exp - 1.0) * alpha
+        else:
+            t = alpha.expand(M, n).clone()
+        v = D * t + beta
+        if op.res is not None:
+            v = v + _join(op.res.reshape(M, -1), op.res_planes)
+        pos = v > 0
+        if op.relu:
+            v = torch.where(pos, v, torch.zeros_like(v))
+            t = torch.where(pos, t, torch.zeros_like(t))
+        if op.maskbits is not None:
+            op.maskbits.copy_(_pack_mask(pos if op.relu else torch.ones_like(pos)))
+        if op.gain is not None:
+            op.gain.copy_(t.to(op.gain.dtype))
+        y2 = op.y.view(-1, op.y.shape[-1])
+        if op.y_f32:
+            y2[rows] = v
+            stored = v
+        else:
+            tmp = torch.zeros(M, op.y.shape[-1], dtype=op.y.dtype)
+            stored = _split_store(tmp, v, op.y_planes)
+            y2[rows] = tmp
+        if op.sq_out is not None:
+            bn = op.resolved_block_n()
+            for ti in range(op.sq_out.shape[0]):
+                op.sq_out[ti] = (stored[:, ti * bn:(ti + 1) * bn] ** 2).sum(1)
+    else:
+        tot = D
+        if op.add is not None:
+            nb = op.a.shape[0]
+            addv = _join(op.add, op.add_planes)                      # [nb, ap, aq, n]
+            s = op.add_stride
+            full = torch.zeros(nb, op.op, op.oq, n)
+            ap, aq = op.add.shape[1], op.add.shape[2]
+            hh = min(op.op, (ap - 1) * s + 1)
+            ww = min(op.oq, (aq - 1) * s + 1)
+            full[:, 0:hh:s, 0:ww:s] = addv[:, :(hh + s - 1) // s, :(ww + s - 1) // s]
+            tot = tot + full.reshape(M, n)
+        if op.out2 is not None:
+            o = tot.clone()
+            if op.mul2 is not None:
+                o = o * op.mul2.float()
+            if op.mask2 is not None:
+                o = o * _mask_bits(op.mask2, n)
+            _split_store(op.out2.view(M, -1), o, op.out2_planes)
+        v = tot * op.mul1.float() if op.mul1 is not None else tot
+        y2 = op.y.view(-1, op.y.shape[-1])
+        if op.y_f32:
+            y2[rows] = v
+        else:
+            tmp = torch.zeros(M, op.y.shape[-1], dtype=op.y.dtype)
+            _split_store(tmp, v, op.y_planes)
+            y2[rows] = tmp
+
+
+def _x6(x: Tensor) -> Tensor:
+    if x.dtype == torch.uint8:          # RGB uint8 -> [x, 1-x] (AddInverse)
+        v = x.float() / 255.0
+        return torch.cat([v, 1.0 - v], 1)
+    return x.float()
+
+
+def run_input_prep(op: O.InputPrepOp) -> None:
+    x = _x6(op.x)
+    nb, _, h, w = x.shape
+    mean = torch.tensor(op.mean6).view(1, 6, 1, 1)
+    istd = torch.tensor(op.inv_std6).view(1, 6, 1, 1)
+    xn = (x - mean) * istd                                          # [nb,6,h,w]
+    # channel (dy*2+dx)*6 + c
+    s2d = xn.view(nb, 6, h // 2, 2, w // 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(nb, h // 2, w // 2, 24)
+    val = torch.zeros(nb, h // 2, w // 2, op.cp)
+    val[..., :24] = s2d
+    stored = _split_store(op.out, val, op.planes)
+    if op.sq is not None:
+        st = stored[..., :24].view(nb, h // 2, w // 2, 2, 2, 6).permute(0, 5, 1, 3, 2, 4).reshape(nb, 6, h, w)
+        op.sq.view(-1)[:] = (st ** 2).sum(1).reshape(-1)
+
+
+def run_patch_norm(op: O.PatchNormOp) -> None:
+    sq = op.sq.view(op.parts, op.nb, 1, op.h, op.w).sum(0)
+    s = torch.nn.functional.avg_pool2d(sq, op.k, stride=op.stride, padding=op.pad, divisor_override=1)
+    assert s.shape[-2:] == (op.op, op.oq), (op.name, s.shape, op.op, op.oq)
+    op.inv_norm[:] = (1.0 / ((s + op.eps_in).sqrt() + op.eps_out)).reshape(-1)
+
+
+def run_avgpool_fwd(op: O.AvgPoolFwdOp) -> None:
+    x = _join(op.x, op.planes).permute(0, 3, 1, 2)
+    y = torch.nn.functional.avg_pool2d(x, op.k, stride=op.stride, padding=op.pad).permute(0, 2, 3, 1)
+    stored = _split_store(op.y, y.contiguous(), op.planes)
+    if op.sq is not None:
+        op.sq.view(-1)[:] = (stored ** 2).sum(-1).reshape(-1)
+
+
+def run_avgpool_bwd_mul(op: O.AvgPoolBwdMulOp) -> None:
+    gy = _join(op.gy, op.planes).permute(0, 3, 1, 2).contiguous()
+    nb, h, w, _ = op.gx.shape
+    x = torch.zeros(nb, op.c, h, w, requires_grad=True)
+    y = torch.nn.functional.avg_pool2d(x, op.k, stride=op.stride, padding=op.pad)
+    (gx,) = torch.autograd.grad(y, x, gy)
+    gx = gx.permute(0, 2, 3, 1)
+    if op.gain is not None:
+        gx = gx * op.gain.float().view(nb, h, w, op.c)
+    _split_store(op.gx, gx.contiguous(), op.planes)
+
+
+def run_gap_logits(op: O.GapLogitsOp) -> None:
+    fc = op.fc.view(op.nb, op.npix, op.ncls)
+    lg = fc.mean(1) * op.inv_temp + op.bias
+    op.logits.copy_(lg)
+    op.pred.copy_(lg.argmax(1).to(torch.int32))
+
+
+def run_fc_seed(op: O.FcSeedOp) -> None:
+    rows = op.nb * op.npix
+    tgt = op.target.long().repeat_interleave(op.npix)
+    gf = op.gain_fc.float()[torch.arange(rows), tgt]
+    g = (op.inv_temp * op.seed_scale / op.npix) * gf[:, None] * op.w_fc[tgt]
+    if op.out2 is not None:
+        o = g * _mask_bits(op.mask2, op.c) if op.mask2 is not None else g
+        _split_store(op.out2, o, op.planes)
+    v = g * op.mul1.float() if op.mul1 is not None else g
+    _split_store(op.out1, v, op.planes)
+
+
+def run_contrib_map(op: O.ContribMapOp) -> None:
+    nb, _, h, w = op.x.shape
+    g = op.g[..., :24].view(nb, h // 2, w // 2, 2, 2, 6).permute(0, 5, 1, 3, 2, 4).reshape(nb, 6, h, w)
+    g6 = g * torch.tensor(op.inv_std6).view(1, 6, 1, 1) * op.out_scale
+    op.cmap.copy_((_x6(op.x) * g6).sum(1))
+    if op.grad6 is not None:
+        op.grad6.copy_(g6)
+
+
+_DISPATCH = {
+    O.IgemmOp: run_igemm, O.InputPrepOp: run_input_prep, O.PatchNormOp: run_patch_norm, O.AvgPoolFwdOp: run_avgpool_fwd,
+    O.AvgPoolBwdMulOp: run_avgpool_bwd_mul, O.GapLogitsOp: run_gap_logits, O.FcSeedOp: run_fc_seed,
+    O.ContribMapOp: run_contrib_map,
+}
+
+
+def run(ops) -> None:
+    with torch.no_grad():
+        for o in ops:
+            fn = _DISPATCH[type(o)]
+            if fn is run_avgpool_bwd_mul:
+                with torch.enable_grad():
+                    fn(o)
+            else:
+                fn(o)

@@ -1,0 +1,237 @@
+"""-m gpu: every CUDA kernel (called through the C ABI) against its torch restatement (tests/emulator.py),
+on seeded inputs.  Tolerances: 16-bit outputs agree to 1 ulp-ish of bf16 (relative 2^-7 of the tensor max is far
+too loose, we use 1.6e-2 only for single-plane bf16 tensors whose last bit may round differently because the
+GPU accumulates the fp32 dot products in a different order); fp32 outputs to 2e-5.
+"""
+import math
+
+import pytest
+import torch
+
+import emulator as E
+import opsutil as U
+from bcos_b200 import _lib as L
+from bcos_b200.engine import ops as O
+from bcos_b200.engine import pack as P
+from bcos_b200.engine.base import Act, PlanBase
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 1.0e-2
+F32_TOL = 3e-5
+
+
+def _mini_plan(nb, planes, explain=True, b=2.0):
+    return PlanBase(nb, planes=planes, dtype="bf16", device="cpu", explain=explain, b=b)
+
+
+def _rand_act(g, nb, h, w, c, planes, dt=torch.bfloat16, scale=1.0):
+    v = torch.randn(nb, h, w, c, generator=g) * scale
+    t = torch.zeros(nb, h, w, planes * c, dtype=dt)
+    stored = E._split_store(t, v, planes)
+    sq = (stored ** 2).sum(-1).reshape(1, -1).contiguous()
+    return Act(t, c, sq, 1)
+
+
+def _run_and_compare(ops, tol16=BF16_TOL, tol32=None):
+    # fp32 side outputs computed FROM single-plane bf16 data (sums of squares, logits of rounded inputs) inherit the
+    # 1-ulp bf16 differences caused by the different fp32 accumulation order on the GPU
+    tol32 = tol32 if tol32 is not None else (5e-3 if tol16 >= 1e-3 else F32_TOL)
+    memo = {}
+    dev_ops = [U.to_device(o, "cuda", memo) for o in ops]
+    E.run(ops)
+    for o in dev_ops:
+        o.run()
+    torch.cuda.synchronize()
+    out = {}
+    for r, d in zip(ops, dev_ops):
+        for name in U.OUTPUT_FIELDS[type(r)]:
+            t = getattr(r, name)
+            if t is None:
+                continue
+            tol = tol32 if t.dtype == torch.float32 else tol16
+            out[(r.name, name)] = U.compare(r, d, tol, [name])[name]
+    return out
+
+
+CONV_CASES = [
+    # name, nb, h, cin, cout, k, stride, pad_lo, pad_hi, planes, relu, res, kch
+    ("1x1_c64", 2, 16, 64, 64, 1, 1, 0, 0, 1, True, False, 64),
+    ("1x1_c128_n256_res", 2, 12, 128, 256, 1, 1, 0, 0, 1, True, True, 64),
+    ("3x3_c64", 2, 14, 64, 64, 3, 1, 1, 1, 1, True, False, 64),
+    ("3x3_s2_c64_n128", 2, 14, 64, 128, 3, 2, 1, 1, 1, True, False, 64),
+    ("3x3_odd_hw", 3, 7, 128, 128, 3, 1, 1, 1, 1, False, False, 64),
+    ("1x1_s2", 2, 14, 128, 256, 1, 2, 0, 0, 1, False, False, 64),
+    ("4x4_asym_kch32", 2, 20, 32, 64, 4, 1, 2, 1, 1, True, False, 32),
+    ("3x3_planes2", 2, 10, 64, 64, 3, 1, 1, 1, 2, True, True, 64),
+    ("3x3_planes3", 1, 10, 64, 128, 3, 1, 1, 1, 3, True, False, 64),
+    ("1x1_cin96_tail", 2, 9, 96, 72, 1, 1, 0, 0, 1, True, False, 64),
+    ("4x4_asym_kch32_planes3", 1, 12, 32, 64, 4, 1, 2, 1, 3, True, False, 32),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_igemm_forward(bcosk_lib, case):
+    name, nb, h, cin, cout, k, stride, plo, phi, planes, relu, use_res, kch = case
+    g = torch.Generator().manual_seed(hash(name) % 2**31)
+    plan = _mini_plan(nb, planes)
+    x = _rand_act(g, nb, h, h, cin, planes)
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    plan.sd = {"bn.running_var": torch.rand(cout, generator=g) + 0.5, "bn.weight": torch.rand(cout, generator=g) + 0.5}
+    oh = (h + plo + phi - k) // stride + 1
+    res = _rand_act(g, nb, oh, oh, cout, planes) if use_res else None
+    inv_norm = (torch.rand(nb * oh * oh, generator=g) + 0.5) if plo != phi else None   # asymmetric pad: norm given
+    y, rec = plan._conv_fwd(name, x, w, stride, plo, phi, bn="bn", relu=relu, res=res, want_mask=True, kch=kch,
+                            inv_norm=inv_norm)
+    errs = _run_and_compare(plan.fwd_ops, tol16=BF16_TOL if planes == 1 else 2e-4)
+    print(name, errs)
+
+
+def test_igemm_forward_fc_f32_tail(bcosk_lib):
+    """classifier-like: n = 1000 (partial last tile), fp32 output, no BN/ReLU"""
+    g = torch.Generator().manual_seed(7)
+    plan = _mini_plan(3, 1)
+    x = _rand_act(g, 3, 7, 7, 256, 1)
+    w = torch.randn(1000, 256, 1, 1, generator=g) / 16
+    plan._conv_fwd("fc", x, w, 1, 0, 0, bn=None, relu=False, y_f32=True, want_sq=False)
+    print(_run_and_compare(plan.fwd_ops))
+
+
+def test_igemm_forward_general_b(bcosk_lib):
+    g = torch.Generator().manual_seed(8)
+    plan = _mini_plan(2, 1, b=2.5)
+    x = _rand_act(g, 2, 8, 8, 64, 1)
+    w = torch.randn(64, 64, 3, 3, generator=g) / 24
+    plan._conv_fwd("b2p5", x, w, 1, 1, 1, bn=None, relu=False)
+    print(_run_and_compare(plan.fwd_ops, tol32=2e-4))
+
+
+DGRAD_CASES = [
+    # name, nb, h_in, cin, cout, k, stride, pad, planes
+    ("d_1x1", 2, 12, 64, 128, 1, 1, 0, 1),
+    ("d_3x3", 2, 12, 64, 64, 3, 1, 1, 1),
+    ("d_3x3_s2_zero_insert", 2, 12, 64, 128, 3, 2, 1, 1),
+    ("d_1x1_s2", 2, 12, 128, 256, 1, 2, 0, 1),
+    ("d_3x3_planes2", 1, 8, 64, 64, 3, 1, 1, 2),
+    ("d_4x4_asym_n32_f32", 2, 16, 32, 64, 4, 1, 2, 1),
+]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES, ids=[c[0] for c in DGRAD_CASES])
+def test_igemm_explain_dgrad(bcosk_lib, case):
+    name, nb, h, cin, cout, k, stride, pad, planes = case
+    g = torch.Generator().manual_seed(hash(name) % 2**31)
+    plan = _mini_plan(nb, planes)
+    pad_hi = pad if k != 4 else 1
+    x = _rand_act(g, nb, h, h, cin, planes)
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    inv_norm = (torch.rand(nb * ((h + pad + pad_hi - k) // stride + 1) ** 2, generator=g) + 0.5) if pad != pad_hi else None
+    y, rec = plan._conv_fwd(name, x, w, stride, pad, pad_hi, bn=None, relu=True, want_mask=True, inv_norm=inv_norm,
+                            kch=32 if cin == 32 else 64)
+    plan._alloc_ghat(rec)
+    # fill ghat (dense positions only when zero-inserted)
+    oh, ow = rec.out_hw
+    gv = torch.randn(nb, oh, ow, cout, generator=g)
+    tmp = torch.zeros(nb, oh, ow, planes * cout, dtype=plan.dt)
+    E._split_store(tmp, gv, planes)
+    if rec.ghat_map is not None:
+        rec.ghat[:, ::stride, ::stride][:, :oh, :ow] = tmp
+    else:
+        rec.ghat.copy_(tmp)
+    f32 = name.endswith("f32")
+    dense = stride > 1 and k == 1
+    oh2, ow2 = (rec.out_hw if dense else rec.in_hw)
+    M = nb * oh2 * ow2
+    yb = torch.zeros(nb, oh2, ow2, (1 if f32 else planes) * cin, dtype=torch.float32 if f32 else plan.dt)
+    mul1 = None if f32 else (torch.rand(M, cin, generator=g) + 0.5).to(plan.gain_dt)
+    add = None if f32 else _rand_act(g, nb, oh2, ow2, cin, planes).t
+    out2 = None if f32 else torch.zeros(nb, oh2, ow2, planes * cin, dtype=plan.dt)
+    mul2 = None if f32 else (torch.rand(M, cin, generator=g) + 0.5).to(plan.gain_dt)
+    mask2 = None if f32 else torch.randint(-2**31, 2**31 - 1, (M, (cin + 31) // 32), generator=g, dtype=torch.int64).to(torch.int32)
+    plan._dgrad(rec, y=yb, mul1=mul1, add=add, out2=out2, mul2=mul2, mask2=mask2, y_f32=f32)
+    errs = _run_and_compare(plan.bwd_ops, tol16=BF16_TOL if planes == 1 else 2e-4)
+    print(name, errs)
+
+
+def test_igemm_dgrad_strided_add_and_outmap(bcosk_lib):
+    """conv1x1 data gradient that adds a half-resolution tensor and writes zero-inserted rows"""
+    g = torch.Generator().manual_seed(11)
+    nb, h, cin, cout = 2, 12, 64, 64
+    plan = _mini_plan(nb, 1)
+    x = _rand_act(g, nb, h, h, cin, 1)
+    w = torch.randn(cout, cin, 1, 1, generator=g) / 8
+    _, rec = plan._conv_fwd("c", x, w, 1, 0, 0, bn=None, relu=False)
+    plan._alloc_ghat(rec)
+    rec.ghat.copy_(torch.randn(nb, h, h, cout, generator=g).to(plan.dt))
+    add = _rand_act(g, nb, h // 2, h // 2, cin, 1).t
+    big = torch.zeros(nb, 2 * h, 2 * h, cin, dtype=plan.dt)
+    plan._dgrad(rec, y=big, y_map=(0, 4 * h * h, 2 * 2 * h, 2), add=add, add_stride=2)
+    print(_run_and_compare(plan.bwd_ops))
+    assert float(big.abs().sum()) > 0
+
+
+def test_a_tile_im2col(bcosk_lib):
+    """what TMA im2col lands in shared memory == the emulator's gather (bit exact)"""
+    g = torch.Generator().manual_seed(3)
+    for (h, cin, k, stride, plo, phi, kch) in [(9, 64, 3, 1, 1, 1, 64), (9, 64, 3, 2, 1, 1, 64), (10, 32, 4, 1, 2, 1, 32),
+                                                 (8, 128, 1, 2, 0, 0, 64)]:
+        nb = 3
+        plan = _mini_plan(nb, 1)
+        x = _rand_act(g, nb, h, h, cin, 1)
+        w = torch.randn(64, cin, k, k, generator=g)
+        plan._conv_fwd("t", x, w, stride, plo, phi, bn=None, relu=False, kch=kch)
+        op = [o for o in plan.fwd_ops if isinstance(o, O.IgemmOp)][0]
+        A = E.gather_a(op)                                   # [M, ktot]
+        dop = U.to_device(op, "cuda")
+        nchunks = op.ktot // kch
+        m_tiles = (op.M + 127) // 128
+        for tile_m in range(m_tiles):
+            for chunk in sorted({0, 1 % nchunks, nchunks - 1}):
+                out = torch.zeros(128, kch, dtype=torch.bfloat16, device="cuda")
+                L.debug_a_tile(dop.params(), tile_m, chunk, out)
+                torch.cuda.synchronize()
+                exp = torch.zeros(128, kch)
+                rows = min(128, op.M - tile_m * 128)
+                exp[:rows] = A[tile_m * 128: tile_m * 128 + rows, chunk * kch:(chunk + 1) * kch]
+                assert torch.equal(out.float().cpu(), exp), (h, cin, k, stride, kch, tile_m, chunk)
+
+
+def test_elementwise_kernels(bcosk_lib):
+    g = torch.Generator().manual_seed(5)
+    nb, S = 3, 32
+    for planes in (1, 2, 3):
+        dt = torch.bfloat16
+        x = torch.rand(nb, 3, S, S, generator=g)
+        x6 = torch.cat([x, 1 - x], 1).contiguous()
+        mean = (0.485, 0.456, 0.406, 0.515, 0.544, 0.594)
+        istd = tuple(1 / s for s in (0.229, 0.224, 0.225, 0.229, 0.224, 0.225))
+        out = torch.zeros(nb, S // 2, S // 2, planes * 32, dtype=dt)
+        sq = torch.zeros(1, nb * S * S)
+        ops = [O.InputPrepOp("prep", x6, mean, istd, out, 32, planes, 1, sq)]
+        inv = torch.zeros(nb * 16 * 16)
+        ops.append(O.PatchNormOp("norm7", sq, 1, nb, S, S, 7, 2, 3, 1e-6, 0.0, inv, 16, 16))
+        a = _rand_act(g, nb, 16, 16, 64, planes)
+        py = torch.zeros(nb, 8, 8, planes * 64, dtype=dt)
+        psq = torch.zeros(1, nb * 64)
+        ops.append(O.AvgPoolFwdOp("pool", a.t, 64, planes, 3, 2, 1, py, 1, psq))
+        gy = _rand_act(g, nb, 8, 8, 64, planes).t
+        gain = (torch.rand(nb * 256, 64, generator=g)).to(dt if planes == 1 else torch.float32)
+        gx = torch.zeros(nb, 16, 16, planes * 64, dtype=dt)
+        ops.append(O.AvgPoolBwdMulOp("poolbwd", gy, 64, planes, 3, 2, 1, gain, gx, 1))
+        fc = torch.randn(nb * 49, 1000, generator=g)
+        logits = torch.zeros(nb, 1000)
+        pred = torch.zeros(nb, dtype=torch.int32)
+        ops.append(O.GapLogitsOp("gap", fc, nb, 49, 1000, 1.0, -6.9, logits, pred))
+        gfc = torch.rand(nb * 49, 1000, generator=g).to(dt if planes == 1 else torch.float32)
+        wfc = torch.randn(1000, 128, generator=g)
+        mul1 = torch.rand(nb * 49, 128, generator=g).to(dt if planes == 1 else torch.float32)
+        mask2 = torch.randint(-2**31, 2**31 - 1, (nb * 49, 4), generator=g, dtype=torch.int64).to(torch.int32)
+        o1 = torch.zeros(nb * 49, planes * 128, dtype=dt)
+        o2 = torch.zeros(nb * 49, planes * 128, dtype=dt)
+        tgt = torch.tensor([3, 999, 500], dtype=torch.int32)
+        ops.append(O.FcSeedOp("seed", tgt, gfc, wfc, nb, 49, 1000, 128, 1.0, 4.0, mul1, o1, mask2, o2, planes, 1))
+        g0 = torch.randn(nb, S // 2, S // 2, 32, generator=g)
+        cmap = torch.zeros(nb, S, S)
+        grad6 = torch.zeros(nb, 6, S, S)
+        ops.append(O.ContribMapOp("cmap", g0, x6, 32, istd, 0.25, cmap, grad6))
+        print(planes, _run_and_compare(ops, tol16=BF16_TOL if planes == 1 else 2e-4))
