@@ -121,9 +121,8 @@ def cpu_reference_arm(args, steps, warmup):
 
 def main():
     args = parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from bcos_b200.utils import dist as D
+    rank, local_rank, world = D.env_rank()
 
     if args.impl == "reference":
         if rank != 0:
@@ -140,15 +139,13 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
     from bcos_b200 import build as bbuild
     from bcos_b200.engine import ops as O
     from bcos_b200.models import synthetic_resnet_plan
     from bcos_b200.utils import synth
 
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    D.init("nccl")
     bbuild.build()
 
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
@@ -161,17 +158,7 @@ def main():
     plan.load_input(h_in)
     plan.capture()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    barrier, max_over_ranks = D.barrier, D.max_over_ranks
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -232,8 +219,7 @@ def main():
     step_ms_eager = sum(per_op)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        D.shutdown()
         return
 
     pk = peaks()
@@ -279,8 +265,7 @@ def main():
         c = cpu_reference_arm(args, 3, 1)
         res["cpu_baseline"] = {"value": c["value"], "unit": "img/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]}
     print(json.dumps(res))
-    if world > 1:
-        dist.destroy_process_group()
+    D.shutdown()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,146 @@
+"""CPU: the oracle (oracle/bcos_oracle.py) against the committed golden vectors that the REFERENCE produced
+(oracle/make_golden.py), and - where /root/reference exists - against the live reference modules."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import bcos_oracle as OR
+import refload
+from bcos_b200.utils import synth
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    return np.load(os.path.join(golden_dir, "modules_kat.npz"))
+
+
+CONV = ["conv_bcosify_3x3", "conv_bcosify_3x3_s2", "conv_bcosify_1x1", "conv_bcosify_1x1_s2", "conv_bcosify_7x7_s2",
+        "conv_bcos_3x3_normed", "conv_bcos_b1p5", "conv_bcos_b2p5_mo2", "conv_bcos_b2_mo3", "conv_bcos_b1"]
+
+
+@pytest.mark.parametrize("name", CONV)
+def test_conv_known_answers(kat, name):
+    cin, cout, k, s, p, b, mo, normed = kat[name + ".meta"].tolist()
+    x, w = _t(kat[name + ".x"]), _t(kat[name + ".w"])
+    y = OR.bcos_conv2d(x, w, None, int(s), int(p), b=b, max_out=int(mo), normalize_weight=bool(normed))
+    assert torch.equal(y, _t(kat[name + ".y"]))                     # bit exact: same ATen calls in the same order
+    xg = x.clone().requires_grad_(True)
+    ye = OR.bcos_conv2d(xg, w, None, int(s), int(p), b=b, max_out=int(mo), detach=True, normalize_weight=bool(normed))
+    (gx,) = torch.autograd.grad((ye * _t(kat[name + ".seed"])).sum(), [xg])
+    assert torch.allclose(gx, _t(kat[name + ".gx"]), rtol=1e-6, atol=1e-7)
+    if b != 1:
+        n = OR.patch_norms(x, int(k), int(s), int(p))
+        assert torch.equal(n, _t(kat[name + ".norm"]))
+        # reference's own in-code cross-check (bcosconv2d.py:233-250): slow == fast to 6e-6
+        slow = OR.patch_norms_slow(x, w[:1, :, :, :] if False else w, int(s), int(p), 1, 1)[:, :1]
+        assert torch.allclose(slow, n, rtol=0, atol=6e-6)
+
+
+@pytest.mark.parametrize("name", ["lin_bcosify", "lin_bcos_normed", "lin_bcos_b1p5_mo2"])
+def test_linear_known_answers(kat, name):
+    fin, fout, b, mo, normed = kat[name + ".meta"].tolist()
+    x, w = _t(kat[name + ".x"]), _t(kat[name + ".w"])
+    y = OR.bcos_linear(x, w, None, b=b, max_out=int(mo), normalize_weight=bool(normed))
+    assert torch.allclose(y, _t(kat[name + ".y"]), rtol=1e-6, atol=1e-7)
+    xg = x.clone().requires_grad_(True)
+    ye = OR.bcos_linear(xg, w, None, b=b, max_out=int(mo), detach=True, normalize_weight=bool(normed))
+    (gx,) = torch.autograd.grad((ye * _t(kat[name + ".seed"])).sum(), [xg])
+    assert torch.allclose(gx, _t(kat[name + ".gx"]), rtol=1e-5, atol=1e-7)
+
+
+def test_norms_and_small_layers(kat):
+    x = _t(kat["bnu.x"])
+    y = OR.batch_norm_uncentered_2d(x, _t(kat["bnu.rv0"]), _t(kat["bnu.w"]), _t(kat["bnu.b"]))
+    assert torch.equal(y, _t(kat["bnu.y_eval"]))
+    rv = _t(kat["bnu.rv0"]).clone()
+    yt = OR.batch_norm_uncentered_2d(x, rv, _t(kat["bnu.w"]), _t(kat["bnu.b"]), training=True, momentum=0.1)
+    assert torch.equal(yt, _t(kat["bnu.y_train"])) and torch.equal(rv, _t(kat["bnu.rv1"]))
+    w, b2 = OR.bn_uncentered_from_standard(_t(kat["bnfold.w"]), _t(kat["bnfold.b"]), _t(kat["bnfold.rm"]), _t(kat["bnfold.rv"]), 1e-5)
+    assert torch.allclose(b2, _t(kat["bnfold.bias_folded"]))
+    assert torch.allclose(OR.batch_norm_uncentered_2d(x, _t(kat["bnfold.rv"]), w, b2), _t(kat["bnfold.y"]), rtol=1e-5, atol=1e-6)
+    # DetachableLayerNorm: plain and explanation mode
+    lx = _t(kat["ln.x"])
+    assert torch.allclose(OR.layer_norm_detachable(lx, _t(kat["ln.w"]), None, 1e-5, False), _t(kat["ln.y"]), rtol=1e-6, atol=1e-6)
+    xg = lx.clone().requires_grad_(True)
+    ye = OR.layer_norm_detachable(xg, _t(kat["ln.w"]), None, 1e-5, True)
+    assert torch.allclose(ye, _t(kat["ln.y_explain"]), rtol=1e-6, atol=1e-6)
+    (gx,) = torch.autograd.grad((ye * _t(kat["ln.seed"])).sum(), [xg])
+    assert torch.allclose(gx, _t(kat["ln.gx"]), rtol=1e-5, atol=1e-6)
+    gx_ = _t(kat["gelu.x"]).clone().requires_grad_(True)
+    ge = OR.gelu_detachable(gx_, True)
+    assert torch.allclose(ge, _t(kat["gelu.y"]), rtol=1e-6, atol=1e-7)
+    (gg,) = torch.autograd.grad((ge * _t(kat["gelu.seed"])).sum(), [gx_])
+    assert torch.allclose(gg, _t(kat["gelu.gx"]), rtol=1e-6, atol=1e-7)
+    assert torch.equal(OR.logit_layer(_t(kat["logit.x"]), 2.0, -1.5), _t(kat["logit.y"]))
+
+
+def _golden_state(arch, gold):
+    sd = synth.synth_state_dict(OR.resnet_state_shapes(arch), int(gold["seed"]))
+    off = 0
+    for k, n in zip(gold["bn_keys"].tolist(), gold["bn_sizes"].tolist()):
+        sd[k] = torch.from_numpy(gold["bn_var"][off:off + n].copy())
+        off += n
+    return sd
+
+
+@pytest.mark.parametrize("arch,batch", [("resnet18", 8), ("resnet50", 4)])
+def test_resnet_golden(golden_dir, arch, batch):
+    gold = np.load(os.path.join(golden_dir, f"{arch}_b{batch}.npz"))
+    assert np.array_equal(gold["images_u8"], synth.synth_images_u8(batch, 224, int(gold["seed"])))  # workload is reproducible
+    sd = _golden_state(arch, gold)
+    nb = 2                                                   # images are independent in eval mode
+    x6 = synth.to_bcos_input(gold["images_u8"][:nb])
+    e = OR.explain_batched(OR.OracleResNet(arch, sd).forward, x6)
+    m = OR.parity_metrics(e["logits"], e["contribution_map"], _t(gold["logits"][:nb]), _t(gold["contribution_map"][:nb]))
+    # oneDNN picks batch-size dependent kernels, so sub-batches agree to fp32 noise (amplified by the random deep net)
+    assert m["argmax_equal"] and m["logit_rel_err"] < 1e-5 and m["map_cos_min"] > 0.99999, m
+    # completeness of the dynamic-linear decomposition (bias-free net): sum(contributions) ~ logit - logit_bias, up to the
+    # input-normalisation offset (SURVEY.md section 8c invariant 4)
+    tot = e["contribution_map"].flatten(1).sum(1)
+    top = e["logits"].max(1).values - OR.LOGIT_BIAS_1000
+    assert torch.all((tot - top).abs() < 0.5 * top.abs() + 1e-3)
+
+
+def test_batched_explain_equals_per_sample(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "resnet18_b8.npz"))
+    sd = _golden_state("resnet18", gold)
+    x6 = synth.to_bcos_input(gold["images_u8"][:3])
+    om = OR.OracleResNet("resnet18", sd)
+    eb = OR.explain_batched(om.forward, x6)
+    for i in range(3):
+        ei = OR.explain_batched(om.forward, x6[i:i + 1])
+        assert torch.allclose(ei["contribution_map"][0], eb["contribution_map"][i], rtol=1e-3, atol=1e-9)
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference checkout not present (GPU box)")
+def test_oracle_pinned_to_live_reference():
+    refload.load()
+    from bcos.modules.bcosifyconv2d import BcosifyConv2d
+    from bcos.modules.bcoslinear import BcosLinear
+    from bcos.modules.norms.uncentered_norms import BatchNormUncentered2d
+    g = torch.Generator().manual_seed(99)
+    for (cin, cout, k, s, p, b, mo) in [(8, 12, 3, 1, 1, 2, 1), (6, 8, 7, 2, 3, 2, 1), (8, 6, 1, 2, 0, 1.7, 2)]:
+        mod = BcosifyConv2d(cin, cout, kernel_size=k, stride=s, padding=p, b=b, max_out=mo)
+        x = torch.randn(2, cin, 11, 11, generator=g)
+        for detach in (False, True):
+            mod.set_explanation_mode(detach)
+            xr = x.clone().requires_grad_(True)
+            yr = mod(xr)
+            xo = x.clone().requires_grad_(True)
+            yo = OR.bcos_conv2d(xo, mod.linear.weight.detach(), None, s, p, b=b, max_out=mo, detach=detach)
+            assert torch.equal(yr.detach(), yo.detach())
+            sg = torch.randn(yr.shape, generator=g)
+            assert torch.allclose(torch.autograd.grad((yr * sg).sum(), [xr])[0], torch.autograd.grad((yo * sg).sum(), [xo])[0],
+                                  rtol=1e-6, atol=1e-7)
+    lin = BcosLinear(20, 10, b=2)
+    x = torch.randn(4, 20, generator=g)
+    assert torch.allclose(lin(x), OR.bcos_linear(x, lin.linear.weight.detach(), None, normalize_weight=True), rtol=1e-6, atol=1e-7)
+    bn = BatchNormUncentered2d(6).eval()
+    x = torch.randn(2, 6, 4, 4, generator=g)
+    assert torch.equal(bn(x), OR.batch_norm_uncentered_2d(x, bn.running_var, bn.weight, bn.bias))
