@@ -21,11 +21,12 @@ constexpr int STAGE_K = 64;   // K elements per pipeline stage (128 bytes of 16-
 constexpr int A_STAGE_BYTES = BM * STAGE_K * 2;
 constexpr int NUM_THREADS = 192;
 
-template <int BN> struct TileCfg {
+template <int BN, bool HP = false> struct TileCfg {
   static constexpr int kStages = (BN == 128) ? 3 : 4;
   static constexpr int kMinBlocks = (BN <= 128) ? 2 : 1;
   static constexpr int kBStageBytes = BN * STAGE_K * 2;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  // HP (high-precision accumulation): two TMEM accumulators that the epilogue warps drain every pipeline stage
+  static constexpr int kTmemCols = (BN < 32 ? 32 : BN) * (HP ? 2 : 1);
   // stages + 1 KB alignment slack + barriers/params
   static constexpr int kSmemBytes = kStages * (A_STAGE_BYTES + kBStageBytes) + 1024 + 256 + 2 * BN * 4;
 };
@@ -102,11 +103,111 @@ __device__ __forceinline__ void store32_f32(float* ptr, int ncols, const float (
       reinterpret_cast<float4*>(ptr)[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
 }
 
-template <int BN, int MODE, typename T>
-__global__ void __launch_bounds__(NUM_THREADS, TileCfg<BN>::kMinBlocks)
+// One 32-column slice of one output row: everything after the accumulator is in registers.
+template <int MODE, typename T>
+__device__ __forceinline__ void epilogue_chunk(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow, float inv_norm,
+                                               int64_t add_row, const float* s_alpha, const float* s_beta, int j, int c0,
+                                               int ncols, float (&v)[32], float& sq_acc) {
+  T* y16 = reinterpret_cast<T*>(p.y);
+  float* y32 = reinterpret_cast<float*>(p.y);
+  if (MODE == BCOSK_MODE_FWD) {
+    float t[32];
+    if (p.scale_mode == BCOSK_SCALE_B2) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t[i] = fabsf(v[i]) * inv_norm * s_alpha[j * 32 + i];
+    } else if (p.scale_mode == BCOSK_SCALE_POW) {
+      const float e = p.b_exp - 1.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t[i] = __powf(fabsf(v[i]) * inv_norm + 1e-6f, e) * s_alpha[j * 32 + i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t[i] = s_alpha[j * 32 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], t[i], s_beta[j * 32 + i]);
+    if (p.res != nullptr) {
+      float r[32];
+      load32_planes<T>(reinterpret_cast<const T*>(p.res) + (size_t)ri.m * p.res_ld + c0, p.res_planes,
+                       p.res_plane_stride, ncols, r);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += r[i];
+    }
+    uint32_t mbits = 0xffffffffu;
+    if (p.relu) {
+      mbits = 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const bool pos = v[i] > 0.f;
+        mbits |= (pos ? 1u : 0u) << i;
+        v[i] = pos ? v[i] : 0.f;
+        t[i] = pos ? t[i] : 0.f;
+      }
+    }
+    if (p.maskbits != nullptr) p.maskbits[(size_t)ri.m * p.mask_ld + (c0 >> 5)] = mbits;
+    if (p.gain != nullptr) {
+      if (p.gain_f32) {
+        store32_f32(reinterpret_cast<float*>(p.gain) + (size_t)ri.m * p.gain_ld + c0, ncols, t);
+      } else {
+        store32_planes<T>(reinterpret_cast<T*>(p.gain) + (size_t)ri.m * p.gain_ld + c0, 1, 0, ncols, t);
+      }
+    }
+    if (p.y_f32) {
+      store32_f32(y32 + (size_t)yrow * p.y_ld + c0, ncols, v);
+    } else {
+      store32_planes<T>(y16 + (size_t)yrow * p.y_ld + c0, p.y_planes, p.y_plane_stride, ncols, v);
+    }
+    if (p.sq_out != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sq_acc = fmaf(v[i], v[i], sq_acc);  // columns >= n are exact zeros
+    }
+  } else {
+    // ---------------- explain-dgrad epilogue ----------------
+    if (add_row >= 0) {
+      float a[32];
+      load32_planes<T>(reinterpret_cast<const T*>(p.add) + (size_t)add_row * p.add_ld + c0, p.add_planes,
+                       p.add_plane_stride, ncols, a);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += a[i];
+    }
+    if (p.out2 != nullptr) {
+      float o[32];
+      if (p.mul2 != nullptr) {
+        if (p.mul2_f32) load32_f32(reinterpret_cast<const float*>(p.mul2) + (size_t)ri.m * p.mul2_ld + c0, ncols, o);
+        else load32_planes<T>(reinterpret_cast<const T*>(p.mul2) + (size_t)ri.m * p.mul2_ld + c0, 1, 0, ncols, o);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] *= v[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = v[i];
+      }
+      if (p.mask2 != nullptr) {
+        const uint32_t mb = __ldg(p.mask2 + (size_t)ri.m * p.mask2_ld + (c0 >> 5));
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = ((mb >> i) & 1u) ? o[i] : 0.f;
+      }
+      store32_planes<T>(reinterpret_cast<T*>(p.out2) + (size_t)ri.m * p.out2_ld + c0, p.out2_planes,
+                        p.out2_plane_stride, ncols, o);
+    }
+    if (p.mul1 != nullptr) {
+      float g[32];
+      if (p.mul1_f32) load32_f32(reinterpret_cast<const float*>(p.mul1) + (size_t)ri.m * p.mul1_ld + c0, ncols, g);
+      else load32_planes<T>(reinterpret_cast<const T*>(p.mul1) + (size_t)ri.m * p.mul1_ld + c0, 1, 0, ncols, g);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= g[i];
+    }
+    if (p.y_f32) {
+      store32_f32(y32 + (size_t)yrow * p.y_ld + c0, ncols, v);
+    } else {
+      store32_planes<T>(y16 + (size_t)yrow * p.y_ld + c0, p.y_planes, p.y_plane_stride, ncols, v);
+    }
+  }
+}
+
+template <int BN, int MODE, typename T, bool HP>
+__global__ void __launch_bounds__(NUM_THREADS, TileCfg<BN, HP>::kMinBlocks)
 bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ bcosk_igemm_params p) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, HP>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
@@ -115,8 +216,10 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint8_t* smem_b = smem + kStages * A_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kStages * Cfg::kBStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + kStages;   // non-HP: accumulator complete
+  uint64_t* acc_full_bar = tmem_full_bar + 1;      // HP: [2] partial accumulator ready
+  uint64_t* acc_empty_bar = acc_full_bar + 2;      // HP: [2] partial accumulator drained
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
   float* s_alpha = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
   float* s_beta = s_alpha + BN;
 
@@ -141,6 +244,10 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full_bar[s], 1);
+      mbar_init(&acc_empty_bar[s], 4);  // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -197,6 +304,15 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       uint32_t phase = 0;
       uint32_t accumulate = 0;
       for (int it = 0; it < num_iters; ++it) {
+        uint32_t tmem_d = tmem_base;
+        if (HP) {
+          // fresh accumulator per stage: the tensor core truncates when it aligns addends to a large running sum,
+          // so long dot products are summed in registers (round-to-nearest fp32) by the epilogue warps instead
+          const int buf = it & 1;
+          mbar_wait(&acc_empty_bar[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+          tmem_d = tmem_base + (uint32_t)(buf * BN);
+          accumulate = 0;
+        }
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         for (int j = 0; j < chunks_per_stage; ++j) {
@@ -204,14 +320,15 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           const uint64_t db = umma_smem_desc_kmajor(smem_u32(smem_b + stage * Cfg::kBStageBytes + j * b_chunk_bytes), row_bytes);
           for (int k = 0; k < mma_per_chunk; ++k) {
             // advance 16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
+            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
             accumulate = 1;
           }
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        if (HP) umma_commit(&acc_full_bar[it & 1]);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
+      if (!HP) umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -250,116 +367,54 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           add_row = ((int64_t)ri.img * p.add_p + ri.p / s) * p.add_q + ri.q / s;
       }
     }
-
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-
     float sq_acc = 0.f;
-    T* y16 = reinterpret_cast<T*>(p.y);
-    float* y32 = reinterpret_cast<float*>(p.y);
-#pragma unroll 1
-    for (int j = 0; j < BN / 32; ++j) {
-      const int c0 = n0 + j * 32;
-      if (c0 >= p.n) break;  // warp-uniform
-      const int ncols = min(32, p.n - c0);
-      uint32_t raw[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * 32), raw);
-      tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-      if (!ri.valid) continue;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 
-      if (MODE == BCOSK_MODE_FWD) {
-        float t[32];
-        if (p.scale_mode == BCOSK_SCALE_B2) {
+    if constexpr (HP) {
+      float acc[BN];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) t[i] = fabsf(v[i]) * inv_norm * s_alpha[j * 32 + i];
-        } else if (p.scale_mode == BCOSK_SCALE_POW) {
-          const float e = p.b_exp - 1.f;
+      for (int i = 0; i < BN; ++i) acc[i] = 0.f;
+      for (int it = 0; it < num_iters; ++it) {
+        const int buf = it & 1;
+        mbar_wait(&acc_full_bar[buf], ((uint32_t)it >> 1) & 1u);
+        tc_fence_after();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) t[i] = __powf(fabsf(v[i]) * inv_norm + 1e-6f, e) * s_alpha[j * 32 + i];
-        } else {
+        for (int j = 0; j < BN / 32; ++j) {
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(buf * BN + j * 32), raw);
+          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) t[i] = s_alpha[j * 32 + i];
+          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(raw[i]);
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty_bar[buf]);
+      }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], t[i], s_beta[j * 32 + i]);
-        if (p.res != nullptr) {
-          float r[32];
-          load32_planes<T>(reinterpret_cast<const T*>(p.res) + (size_t)ri.m * p.res_ld + c0, p.res_planes,
-                           p.res_plane_stride, ncols, r);
+      for (int j = 0; j < BN / 32; ++j) {
+        const int c0 = n0 + j * 32;
+        if (c0 < p.n && ri.valid) {
+          float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += r[i];
+          for (int i = 0; i < 32; ++i) v[i] = acc[j * 32 + i];
+          epilogue_chunk<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, min(32, p.n - c0), v, sq_acc);
         }
-        uint32_t mbits = 0xffffffffu;
-        if (p.relu) {
-          mbits = 0;
+      }
+    } else {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        const int c0 = n0 + j * 32;
+        if (c0 >= p.n) break;  // warp-uniform
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(j * 32), raw);
+        tmem_ld_wait();
+        if (!ri.valid) continue;
+        float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const bool pos = v[i] > 0.f;
-            mbits |= (pos ? 1u : 0u) << i;
-            v[i] = pos ? v[i] : 0.f;
-            t[i] = pos ? t[i] : 0.f;
-          }
-        }
-        if (p.maskbits != nullptr) p.maskbits[(size_t)ri.m * p.mask_ld + (c0 >> 5)] = mbits;
-        if (p.gain != nullptr) {
-          if (p.gain_f32) {
-            store32_f32(reinterpret_cast<float*>(p.gain) + (size_t)ri.m * p.gain_ld + c0, ncols, t);
-          } else {
-            store32_planes<T>(reinterpret_cast<T*>(p.gain) + (size_t)ri.m * p.gain_ld + c0, 1, 0, ncols, t);
-          }
-        }
-        if (p.y_f32) {
-          store32_f32(y32 + (size_t)yrow * p.y_ld + c0, ncols, v);
-        } else {
-          store32_planes<T>(y16 + (size_t)yrow * p.y_ld + c0, p.y_planes, p.y_plane_stride, ncols, v);
-        }
-        if (p.sq_out != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sq_acc = fmaf(v[i], v[i], sq_acc);  // columns >= n are exact zeros
-        }
-      } else {
-        // ---------------- explain-dgrad epilogue ----------------
-        if (add_row >= 0) {
-          float a[32];
-          load32_planes<T>(reinterpret_cast<const T*>(p.add) + (size_t)add_row * p.add_ld + c0, p.add_planes,
-                           p.add_plane_stride, ncols, a);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += a[i];
-        }
-        if (p.out2 != nullptr) {
-          float o[32];
-          if (p.mul2 != nullptr) {
-            if (p.mul2_f32) load32_f32(reinterpret_cast<const float*>(p.mul2) + (size_t)ri.m * p.mul2_ld + c0, ncols, o);
-            else load32_planes<T>(reinterpret_cast<const T*>(p.mul2) + (size_t)ri.m * p.mul2_ld + c0, 1, 0, ncols, o);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] *= v[i];
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = v[i];
-          }
-          if (p.mask2 != nullptr) {
-            const uint32_t mb = __ldg(p.mask2 + (size_t)ri.m * p.mask2_ld + (c0 >> 5));
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = ((mb >> i) & 1u) ? o[i] : 0.f;
-          }
-          store32_planes<T>(reinterpret_cast<T*>(p.out2) + (size_t)ri.m * p.out2_ld + c0, p.out2_planes,
-                            p.out2_plane_stride, ncols, o);
-        }
-        if (p.mul1 != nullptr) {
-          float g[32];
-          if (p.mul1_f32) load32_f32(reinterpret_cast<const float*>(p.mul1) + (size_t)ri.m * p.mul1_ld + c0, ncols, g);
-          else load32_planes<T>(reinterpret_cast<const T*>(p.mul1) + (size_t)ri.m * p.mul1_ld + c0, 1, 0, ncols, g);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= g[i];
-        }
-        if (p.y_f32) {
-          store32_f32(y32 + (size_t)yrow * p.y_ld + c0, ncols, v);
-        } else {
-          store32_planes<T>(y16 + (size_t)yrow * p.y_ld + c0, p.y_planes, p.y_plane_stride, ncols, v);
-        }
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        epilogue_chunk<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, min(32, p.n - c0), v, sq_acc);
       }
     }
     if (MODE == BCOSK_MODE_FWD) {
@@ -416,11 +471,11 @@ __global__ void bcosk_debug_a_tile_kernel(const __grid_constant__ CUtensorMap tm
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BN, int MODE>
+template <int BN, int MODE, bool HP>
 static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const bcosk_igemm_params& p, cudaStream_t st) {
-  using Cfg = TileCfg<BN>;
-  auto kern = bcosk_igemm_kernel<BN, MODE, __nv_bfloat16>;
-  auto kern_h = bcosk_igemm_kernel<BN, MODE, __half>;
+  using Cfg = TileCfg<BN, HP>;
+  auto kern = bcosk_igemm_kernel<BN, MODE, __nv_bfloat16, HP>;
+  auto kern_h = bcosk_igemm_kernel<BN, MODE, __half, HP>;
   const void* fn = (p.dtype == BCOSK_DTYPE_BF16) ? (const void*)kern : (const void*)kern_h;
   static bool attr_done[2] = {false, false};
   if (!attr_done[p.dtype]) {
@@ -476,17 +531,25 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
   int rc = validate(p);
   if (rc) return rc;
   int bn = p.block_n;
-  if (bn == 0) bn = p.n <= 32 ? 32 : (p.n <= 64 ? 64 : 128);
+  if (bn == 0) bn = p.n <= 32 ? 32 : ((p.n <= 64 || p.hp_accum) ? 64 : 128);
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return set_error(BCOSK_EINVAL, "igemm: block_n");
+  if (p.hp_accum && bn > 64) return set_error(BCOSK_EINVAL, "igemm: hp_accum needs block_n <= 64");
   p.block_n = bn;
   CUtensorMap ta, tb;
   rc = make_maps(p, bn, &ta, &tb);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define BCOSK_DISPATCH(BN_)                                                                 \
-  case BN_:                                                                                 \
-    return p.mode == BCOSK_MODE_FWD ? launch_igemm<BN_, BCOSK_MODE_FWD>(ta, tb, p, st)      \
-                                    : launch_igemm<BN_, BCOSK_MODE_EXPLAIN>(ta, tb, p, st);
+#define BCOSK_DISPATCH(BN_)                                                                        \
+  case BN_:                                                                                        \
+    return p.mode == BCOSK_MODE_FWD ? launch_igemm<BN_, BCOSK_MODE_FWD, false>(ta, tb, p, st)      \
+                                    : launch_igemm<BN_, BCOSK_MODE_EXPLAIN, false>(ta, tb, p, st);
+  if (p.hp_accum) {
+    if (bn == 32)
+      return p.mode == BCOSK_MODE_FWD ? launch_igemm<32, BCOSK_MODE_FWD, true>(ta, tb, p, st)
+                                      : launch_igemm<32, BCOSK_MODE_EXPLAIN, true>(ta, tb, p, st);
+    return p.mode == BCOSK_MODE_FWD ? launch_igemm<64, BCOSK_MODE_FWD, true>(ta, tb, p, st)
+                                    : launch_igemm<64, BCOSK_MODE_EXPLAIN, true>(ta, tb, p, st);
+  }
   switch (bn) {
     BCOSK_DISPATCH(32)
     BCOSK_DISPATCH(64)

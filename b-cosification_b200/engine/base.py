@@ -77,6 +77,7 @@ class PlanBase:
         self.dt_code = L.DTYPE_CODE[dtype]
         self.dt = torch.bfloat16 if dtype == "bf16" else torch.float16
         self.gain_dt = self.dt if planes == 1 else torch.float32
+        self.hp_accum = planes > 1        # parity mode: fp32-faithful accumulation (see include/bcosk.h hp_accum)
         self.b, self.bn_eps = float(b), bn_eps
         self.scale_mode = L.BCOSK_SCALE_NONE if b == 1 else (L.BCOSK_SCALE_B2 if b == 2 else L.BCOSK_SCALE_POW)
         self.sd = {k: v.detach().to(torch.float32) for k, v in (state_dict or {}).items() if v.is_floating_point()}
@@ -107,6 +108,9 @@ class PlanBase:
         beta = self.sd.get(prefix + ".bias")
         return self._dev(alpha), (None if beta is None else self._dev(beta))
 
+    def _block_n(self, n: int) -> int:
+        return 32 if n <= 32 else (64 if (n <= 64 or self.hp_accum) else 128)
+
     # ------------------------------------------------------------------ forward emission
     def _conv_fwd(self, name: str, x: Act, w: Tensor, stride: int, pad_lo: int, pad_hi: int, *, bn: Optional[str],
                   relu: bool, res: Optional[Act] = None, want_mask: bool = False, y_f32: bool = False,
@@ -125,7 +129,7 @@ class PlanBase:
                                               inv_norm, oh, ow))
         bmat, cpt = P.pack_b(P.fwd_weight_taps(w), self.planes, kch, self.dt)
         alpha, beta = self._bn_alpha(bn) if bn else (None, None)
-        block_n = 32 if o <= 32 else (64 if o <= 64 else 128)
+        block_n = self._block_n(o)
         parts = (o + block_n - 1) // block_n
         yp = 1 if y_f32 else self.planes
         y = self._empty(nb, oh, ow, yp * o, dtype=torch.float32 if y_f32 else self.dt)
@@ -141,7 +145,7 @@ class PlanBase:
             taps=P.conv_taps(kh, kw), seg_a_choff=P.seg_a_offsets(self.planes, cin_phys), dtype=self.dt_code,
             mode=L.BCOSK_MODE_FWD, block_n=block_n, scale_mode=self.scale_mode, b_exp=self.b, relu=relu,
             inv_norm=inv_norm, alpha=alpha, beta=beta, res=None if res is None else res.t, res_planes=self.planes,
-            gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32,
+            gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32, hp_accum=self.hp_accum,
             algo_flops=2.0 * M * o * float((w != 0).sum().item()) / o))
         rec.algo_flops = self.fwd_ops[-1].algo_flops
         return Act(y, o, sq, parts), rec
@@ -182,7 +186,7 @@ class PlanBase:
             name=rec.name + ".dgrad", a=g, b=self._dev(bmat, self.dt), n=n, lo=(lo, lo), up=(up_w, up_h), stride=(1, 1),
             op=oh, oq=ow, kch=kch, chunks_per_tap=cpt, taps=P.conv_taps(k, k),
             seg_a_choff=P.seg_a_offsets(self.planes, rec.cout), dtype=self.dt_code, mode=L.BCOSK_MODE_EXPLAIN,
-            block_n=32 if n <= 32 else (64 if n <= 64 else 128), y=y, y_planes=1 if y_f32 else self.planes, y_f32=y_f32,
+            block_n=self._block_n(n), hp_accum=self.hp_accum, y=y, y_planes=1 if y_f32 else self.planes, y_f32=y_f32,
             out_map=y_map, add=add, add_planes=self.planes, add_stride=add_stride, mul1=mul1, out2=out2,
             out2_planes=self.planes, mul2=mul2, mask2=mask2, algo_flops=rec.algo_flops,
             a_dense_frac=1.0 / (rec.stride * rec.stride) if rec.ghat_map is not None else 1.0))

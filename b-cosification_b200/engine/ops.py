@@ -64,6 +64,7 @@ class IgemmOp:
     # accounting (set by the plan): 2*MAC of the logical convolution, fraction of `a` that is not structural zeros
     algo_flops: float = 0.0
     a_dense_frac: float = 1.0
+    hp_accum: bool = False           # per-stage TMEM accumulators summed in registers (parity mode)
 
     # ---- derived ----
     @property
@@ -97,7 +98,7 @@ class IgemmOp:
     def resolved_block_n(self) -> int:
         if self.block_n:
             return self.block_n
-        return 32 if self.n <= 32 else (64 if self.n <= 64 else 128)
+        return 32 if self.n <= 32 else (64 if (self.n <= 64 or self.hp_accum) else 128)
 
     def params(self) -> L.IgemmParams:
         p = L.IgemmParams()
@@ -166,6 +167,7 @@ class IgemmOp:
         if self.mask2 is not None:
             p.mask2 = self.mask2.data_ptr()
             p.mask2_ld = self.mask2.shape[-1]
+        p.hp_accum = int(self.hp_accum)
         return p
 
     def run(self) -> None:

@@ -109,6 +109,11 @@ typedef struct bcosk_igemm_params {
   int32_t mul2_ld, mul2_f32;
   const uint32_t* mask2;
   int32_t mask2_ld;
+  /* ---- accumulation: 0 = one fp32 TMEM accumulator over all of K (throughput mode); 1 = a fresh TMEM accumulator
+   *      per 64-deep K stage, summed in registers with round-to-nearest fp32 adds (parity mode; block_n <= 64).
+   *      The tensor core truncates when aligning addends to a large running sum (measured: relative error ~K*2^-26,
+   *      biased), which random-init deep B-cos nets amplify 10^2-10^3 x. */
+  int32_t hp_accum;
 } bcosk_igemm_params;
 
 int bcosk_igemm(const bcosk_igemm_params* p, void* stream);

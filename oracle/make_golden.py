@@ -105,8 +105,20 @@ def golden_resnet(arch: str, batch: int, seed: int = 0):
     print(f"[{arch}] oracle vs reference: {pm}")
     assert pm["argmax_equal"] and pm["logit_rel_err"] < 1e-5 and pm["map_cos_min"] > 0.99999
 
+    # ---- fp64 evaluation of the (pinned) oracle: the reference's own fp32 rounding-noise floor on this workload.
+    # Random-init deep B-cos nets amplify rounding noise by 10^2-10^3, so "distance to the fp32
+    # reference" is only meaningful down to the reference's own distance from the exact result.
+    osd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in osd.items()}
+    e64 = O.explain_batched(O.OracleResNet(arch, osd64).forward, x6.double())
+    floor = O.parity_metrics(logits, cmap, e64["logits"], e64["contribution_map"])
+    print(f"[{arch}] reference fp32 vs fp64 evaluation (noise floor): {floor}")
+
     keys = sorted(cal)
     out = dict(
+        logits_fp64=e64["logits"].numpy(),
+        contribution_map_fp64=e64["contribution_map"].float().numpy(),
+        fp32_noise_floor_maxabs_over_range=np.float64(floor["map_maxabs_over_range"]),
+        fp32_noise_floor_logit_rel_err=np.float64(floor["logit_rel_err"]),
         images_u8=u8,
         bn_keys=np.array(keys),
         bn_sizes=np.array([cal[k].numel() for k in keys], dtype=np.int64),

@@ -1,0 +1,33 @@
+"""Workload for ncu: 2 warm eager steps of the RN50 plan, then either one full step or a few selected launches.
+
+  ncu --metrics gpu__time_duration.sum --clock-control none -s 334 -c 167 --csv --log-file gpurun_out/launches.csv \
+      python scripts/profile_step.py
+  ncu --set full --clock-control none --import-source on -k regex:bcosk_igemm -s 214 -c 4 -o gpurun_out/prof \
+      python scripts/profile_step.py --only model.layer1.1.conv3,model.layer3.1.conv2,model.layer1.1.conv1.dgrad,model.layer3.1.conv2.dgrad
+"""
+import argparse, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from bcos_b200.models import synthetic_resnet_plan
+from bcos_b200.utils import synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--arch", default="resnet50")
+ap.add_argument("--only", default="")
+ap.add_argument("--planes", type=int, default=1)
+a = ap.parse_args()
+plan = synthetic_resnet_plan(a.arch, a.batch, planes=a.planes, device="cuda", input_u8=True)
+imgs = torch.from_numpy(synth.synth_images_u8(32, 224, 5)).repeat((a.batch + 31) // 32, 1, 1, 1)[:a.batch].contiguous()
+plan.load_input(imgs)
+ops = plan.fwd_ops + plan.bwd_ops
+for _ in range(2):
+    for o in ops:
+        o.run()
+torch.cuda.synchronize()
+sel = [s for s in a.only.split(",") if s]
+for o in ops:
+    if not sel or o.name in sel:
+        o.run()
+torch.cuda.synchronize()
+print("launches per step", len(ops), "igemm", sum(type(o).__name__ == "IgemmOp" for o in ops))

@@ -69,8 +69,16 @@ def test_golden_parity_mode(bcosk_lib, golden_dir, arch, batch):
     assert m["argmax_equal"]
     assert m["logit_rel_err"] <= 2e-3
     assert m["map_cos_min"] >= 0.999
-    floor = float(gold["fp32_noise_floor_maxabs_over_range"]) if "fp32_noise_floor_maxabs_over_range" in gold.files else 0.0
-    assert m["map_maxabs_over_range"] <= max(1e-3, 3 * floor)
+    # max-abs <= 1e-3 of the map range.  The fp32 reference is itself `floor` away from the exact (fp64) evaluation of
+    # the same network (ResNet-50: 1.09e-3 > 1e-3), so the bound against the reference is max(1e-3, 1.5 * floor), and the
+    # strict 1e-3 is asserted against the fp64 evaluation.
+    floor = float(gold["fp32_noise_floor_maxabs_over_range"])
+    assert m["map_maxabs_over_range"] <= max(1e-3, 1.5 * floor), (m, floor)
+    m64 = OR.parity_metrics(out["logits"], out["contribution_map"], torch.from_numpy(gold["logits_fp64"]),
+                            torch.from_numpy(gold["contribution_map_fp64"]))
+    print(arch, "parity mode vs fp64 evaluation:", m64, "| reference's own floor:", floor)
+    assert m64["argmax_equal"] and m64["logit_rel_err"] <= 2e-3 and m64["map_cos_min"] >= 0.999
+    assert m64["map_maxabs_over_range"] <= 1e-3
     # graph replay gives the same answer
     plan.capture()
     out2 = plan.explain(x6)
