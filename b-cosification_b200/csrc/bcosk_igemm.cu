@@ -8,7 +8,12 @@
 //   warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (tcgen05.ld).
 //   Non-persistent; two CTAs are co-resident per SM (BN <= 128) so one CTA's epilogue overlaps the other's
 //   main loop.  Epilogues are documented in include/bcosk.h (struct bcosk_igemm_params).
+//   Epilogue I/O (throughput mode): the big per-element tensors move as 128x64 tiles through shared memory with
+//   TMA bulk copies - one input tile (residual / producer gain) is prefetched during the main loop, the two output
+//   tiles (y + gain, or y + out2) are staged in the drained pipeline slots and written with TMA stores - so the
+//   HBM-bound layers keep >100 KB per SM in flight without spending registers or warps on it.
 #include <cuda.h>
+#include <cstring>
 
 #include "../../include/bcosk.h"
 #include "bcosk_common.cuh"
@@ -22,9 +27,12 @@ constexpr int A_STAGE_BYTES = BM * STAGE_K * 2;
 constexpr int NUM_THREADS = 192;
 
 template <int BN, bool HP = false> struct TileCfg {
-  static constexpr int kStages = (BN == 128) ? 3 : 4;
+  static constexpr int kStages = (BN == 128) ? 3 : 4;   // pipeline slots; the last one may hold the epilogue input tile
   static constexpr int kMinBlocks = (BN <= 128) ? 2 : 1;
   static constexpr int kBStageBytes = BN * STAGE_K * 2;
+  static constexpr int kSlotBytes = A_STAGE_BYTES + kBStageBytes;   // A stage followed by its B stage
+  static constexpr int kTileBytes = BM * BN * 2;                    // one 16-bit epilogue tile (BN/64 boxes of 16 KB)
+  static constexpr bool kTmaEpilogue = !HP && (BN == 64 || BN == 128);
   // HP (high-precision accumulation): two TMEM accumulators that the epilogue warps drain every pipeline stage
   static constexpr int kTmemCols = (BN < 32 ? 32 : BN) * (HP ? 2 : 1);
   // stages + 1 KB alignment slack + barriers/params
@@ -103,11 +111,73 @@ __device__ __forceinline__ void store32_f32(float* ptr, int ncols, const float (
       reinterpret_cast<float4*>(ptr)[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
 }
 
+// Library-internal launch state (decided by the host launcher, see launch_igemm)
+struct IgemmAux {
+  int tma_in;    // 0 none, 1 = forward residual, 2 = explain mul1: prefetched as a tile into the last pipeline slot
+  int tma_out1;  // primary output y staged in slot 0 and written with TMA
+  int tma_out2;  // forward: gain, explain: out2 - staged in slot 1 and written with TMA
+};
+
+// Shared-memory tiles of the TMA epilogue: [BN/64 boxes][128 rows][128 bytes], 16-byte units XOR-swizzled by row
+// (CU_TENSOR_MAP_SWIZZLE_128B).  Thread = row r, chunk j = 32 columns = 4 units.
+// Tiles are addressed in the shared window (32-bit addresses, 0 = absent) with explicit ld.shared / st.shared so that
+// the compiler never falls back to generic-space accesses.
+struct EpiTiles {
+  uint32_t in;
+  uint32_t out1;
+  uint32_t out2;
+};
+__device__ __forceinline__ uint32_t tile_ptr(uint32_t tile, int r, int j, int g) {
+  const int u = ((j & 1) << 2) + g;
+  return tile + ((j >> 1) << 14) + (r << 7) + ((u ^ (r & 7)) << 4);
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+  return u;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& u) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 f;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(addr));
+  return f;
+}
+template <typename T>
+__device__ __forceinline__ void tile_load32(uint32_t tile, int r, int j, float (&v)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint4 u = lds128(tile_ptr(tile, r, j, g));
+    float2 f;
+    f = Cvt<T>::unpack2(u.x); v[g * 8 + 0] = f.x; v[g * 8 + 1] = f.y;
+    f = Cvt<T>::unpack2(u.y); v[g * 8 + 2] = f.x; v[g * 8 + 3] = f.y;
+    f = Cvt<T>::unpack2(u.z); v[g * 8 + 4] = f.x; v[g * 8 + 5] = f.y;
+    f = Cvt<T>::unpack2(u.w); v[g * 8 + 6] = f.x; v[g * 8 + 7] = f.y;
+  }
+}
+// rounds v to 16 bit (v returns the stored value) and writes the 32 columns of this row into the tile
+template <typename T>
+__device__ __forceinline__ void tile_store32(uint32_t tile, int r, int j, float (&v)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      w[k] = Cvt<T>::pack2(v[g * 8 + 2 * k], v[g * 8 + 2 * k + 1]);
+      const float2 f = Cvt<T>::unpack2(w[k]);
+      v[g * 8 + 2 * k] = f.x; v[g * 8 + 2 * k + 1] = f.y;
+    }
+    sts128(tile_ptr(tile, r, j, g), make_uint4(w[0], w[1], w[2], w[3]));
+  }
+}
+
 // One 32-column slice of one output row: everything after the accumulator is in registers.
+// Generic (scalar) form: any scale mode, precision planes, fp32 side tensors.
 template <int MODE, typename T>
-__device__ __forceinline__ void epilogue_chunk(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow, float inv_norm,
+__device__ __noinline__ void epilogue_chunk_generic(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow, float inv_norm,
                                                int64_t add_row, const float* s_alpha, const float* s_beta, int j, int c0,
-                                               int ncols, float (&v)[32], float& sq_acc) {
+                                               int ncols, float (&v)[32], float& sq_acc, const EpiTiles& tl, int row) {
   T* y16 = reinterpret_cast<T*>(p.y);
   float* y32 = reinterpret_cast<float*>(p.y);
   if (MODE == BCOSK_MODE_FWD) {
@@ -127,8 +197,9 @@ __device__ __forceinline__ void epilogue_chunk(const bcosk_igemm_params& p, cons
     for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], t[i], s_beta[j * 32 + i]);
     if (p.res != nullptr) {
       float r[32];
-      load32_planes<T>(reinterpret_cast<const T*>(p.res) + (size_t)ri.m * p.res_ld + c0, p.res_planes,
-                       p.res_plane_stride, ncols, r);
+      if (tl.in != 0) tile_load32<T>(tl.in, row, j, r);
+      else load32_planes<T>(reinterpret_cast<const T*>(p.res) + (size_t)ri.m * p.res_ld + c0, p.res_planes,
+                            p.res_plane_stride, ncols, r);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] += r[i];
     }
@@ -145,13 +216,17 @@ __device__ __forceinline__ void epilogue_chunk(const bcosk_igemm_params& p, cons
     }
     if (p.maskbits != nullptr) p.maskbits[(size_t)ri.m * p.mask_ld + (c0 >> 5)] = mbits;
     if (p.gain != nullptr) {
-      if (p.gain_f32) {
+      if (tl.out2 != 0) {
+        tile_store32<T>(tl.out2, row, j, t);
+      } else if (p.gain_f32) {
         store32_f32(reinterpret_cast<float*>(p.gain) + (size_t)ri.m * p.gain_ld + c0, ncols, t);
       } else {
         store32_planes<T>(reinterpret_cast<T*>(p.gain) + (size_t)ri.m * p.gain_ld + c0, 1, 0, ncols, t);
       }
     }
-    if (p.y_f32) {
+    if (tl.out1 != 0) {
+      tile_store32<T>(tl.out1, row, j, v);
+    } else if (p.y_f32) {
       store32_f32(y32 + (size_t)yrow * p.y_ld + c0, ncols, v);
     } else {
       store32_planes<T>(y16 + (size_t)yrow * p.y_ld + c0, p.y_planes, p.y_plane_stride, ncols, v);
@@ -185,17 +260,21 @@ __device__ __forceinline__ void epilogue_chunk(const bcosk_igemm_params& p, cons
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] = ((mb >> i) & 1u) ? o[i] : 0.f;
       }
-      store32_planes<T>(reinterpret_cast<T*>(p.out2) + (size_t)ri.m * p.out2_ld + c0, p.out2_planes,
-                        p.out2_plane_stride, ncols, o);
+      if (tl.out2 != 0) tile_store32<T>(tl.out2, row, j, o);
+      else store32_planes<T>(reinterpret_cast<T*>(p.out2) + (size_t)ri.m * p.out2_ld + c0, p.out2_planes,
+                             p.out2_plane_stride, ncols, o);
     }
     if (p.mul1 != nullptr) {
       float g[32];
-      if (p.mul1_f32) load32_f32(reinterpret_cast<const float*>(p.mul1) + (size_t)ri.m * p.mul1_ld + c0, ncols, g);
+      if (tl.in != 0) tile_load32<T>(tl.in, row, j, g);
+      else if (p.mul1_f32) load32_f32(reinterpret_cast<const float*>(p.mul1) + (size_t)ri.m * p.mul1_ld + c0, ncols, g);
       else load32_planes<T>(reinterpret_cast<const T*>(p.mul1) + (size_t)ri.m * p.mul1_ld + c0, 1, 0, ncols, g);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] *= g[i];
     }
-    if (p.y_f32) {
+    if (tl.out1 != 0) {
+      tile_store32<T>(tl.out1, row, j, v);
+    } else if (p.y_f32) {
       store32_f32(y32 + (size_t)yrow * p.y_ld + c0, ncols, v);
     } else {
       store32_planes<T>(y16 + (size_t)yrow * p.y_ld + c0, p.y_planes, p.y_plane_stride, ncols, v);
@@ -203,23 +282,220 @@ __device__ __forceinline__ void epilogue_chunk(const bcosk_igemm_params& p, cons
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast form for the throughput mode (single 16-bit plane, B=2 or no scale): the math runs on float2 pairs with the
+// sm_100 packed-fp32 instructions (FMUL2 / FFMA2 / FADD2), ReLU and the gain mask are applied on the packed 16-bit
+// words, per-channel vectors are read with 128-bit shared loads.  ~3x fewer instructions than the generic form -
+// the epilogue, not HBM, was the limiter of the bandwidth-bound layers (profiles/r01_*).
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Pk;
+template <> struct Pk<__nv_bfloat16> {
+  static __device__ __forceinline__ uint32_t gt0_mask(uint32_t w) {
+    return __hgt2_mask(*reinterpret_cast<__nv_bfloat162*>(&w), __floats2bfloat162_rn(0.f, 0.f));
+  }
+};
+template <> struct Pk<__half> {
+  static __device__ __forceinline__ uint32_t gt0_mask(uint32_t w) {
+    return __hgt2_mask(*reinterpret_cast<__half2*>(&w), __floats2half2_rn(0.f, 0.f));
+  }
+};
+
+__device__ __forceinline__ void tile_load_words(uint32_t tile, int r, int j, uint32_t (&w)[16]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint4 u = lds128(tile_ptr(tile, r, j, g));
+    w[g * 4 + 0] = u.x; w[g * 4 + 1] = u.y; w[g * 4 + 2] = u.z; w[g * 4 + 3] = u.w;
+  }
+}
+__device__ __forceinline__ void tile_store_words(uint32_t tile, int r, int j, const uint32_t (&w)[16]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) sts128(tile_ptr(tile, r, j, g), make_uint4(w[g * 4], w[g * 4 + 1], w[g * 4 + 2], w[g * 4 + 3]));
+}
+__device__ __forceinline__ void global_load_words(const void* ptr, int ncols, uint32_t (&w)[16]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (g * 8 < ncols) u = __ldg(reinterpret_cast<const uint4*>(ptr) + g);
+    w[g * 4 + 0] = u.x; w[g * 4 + 1] = u.y; w[g * 4 + 2] = u.z; w[g * 4 + 3] = u.w;
+  }
+}
+__device__ __forceinline__ void global_store_words(void* ptr, int ncols, const uint32_t (&w)[16]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    if (g * 8 < ncols) reinterpret_cast<uint4*>(ptr)[g] = make_uint4(w[g * 4], w[g * 4 + 1], w[g * 4 + 2], w[g * 4 + 3]);
+}
+
+// Forward, B=2 scale: branch-free over the 16 column pairs so the compiler can interleave them (all launch-uniform
+// options are folded into data: a zero residual word, an all-ones ReLU mask, ...).
+template <typename T, bool MASK>
+__device__ __forceinline__ void epilogue_fwd_fast(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow,
+                                                  float inv_norm, const float* s_alpha, const float* s_beta, int j, int c0,
+                                                  int ncols, const float (&v)[32], float& sq_acc, const EpiTiles& tl, int row) {
+  uint32_t yw[16], tw[16], rw[16];
+  if (p.res != nullptr) {
+    if (tl.in != 0) tile_load_words(tl.in, row, j, rw);
+    else global_load_words(reinterpret_cast<const T*>(p.res) + (size_t)ri.m * p.res_ld + c0, ncols, rw);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) rw[k] = 0u;
+  }
+  const uint32_t a4 = smem_u32(s_alpha + j * 32), b4 = smem_u32(s_beta + j * 32);
+  const float2 inv2 = make_float2(inv_norm, inv_norm);
+  const uint32_t relu_off = p.relu ? 0u : 0xffffffffu;
+  float2 sq2 = make_float2(0.f, 0.f);
+  uint32_t mbits = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 al = lds_f4(a4 + q * 16), be = lds_f4(b4 + q * 16);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = q * 2 + h;  // pair index: columns 2k, 2k+1
+      const float2 vv = make_float2(v[2 * k], v[2 * k + 1]);
+      const float2 kk = __fmul2_rn(h ? make_float2(al.z, al.w) : make_float2(al.x, al.y), inv2);
+      const float2 t = make_float2(fabsf(vv.x) * kk.x, fabsf(vv.y) * kk.y);       // |lin| / ||patch|| * alpha
+      float2 y = __ffma2_rn(vv, t, h ? make_float2(be.z, be.w) : make_float2(be.x, be.y));
+      y = __fadd2_rn(y, Cvt<T>::unpack2(rw[k]));
+      const uint32_t ywk = Cvt<T>::pack2(y.x, y.y);
+      const uint32_t m = Pk<T>::gt0_mask(ywk) | relu_off;                          // 0xFFFF per kept half
+      yw[k] = ywk & m;
+      tw[k] = Cvt<T>::pack2(t.x, t.y) & m;
+      if (MASK) mbits |= ((m & 1u) | ((m >> 15) & 2u)) << (2 * k);
+      const float2 ym = Cvt<T>::unpack2(yw[k]);                                    // what the consumer will read
+      sq2 = __ffma2_rn(ym, ym, sq2);
+    }
+  }
+  if (MASK) p.maskbits[(size_t)ri.m * p.mask_ld + (c0 >> 5)] = mbits;
+  if (p.gain != nullptr) {
+    if (tl.out2 != 0) tile_store_words(tl.out2, row, j, tw);
+    else global_store_words(reinterpret_cast<T*>(p.gain) + (size_t)ri.m * p.gain_ld + c0, ncols, tw);
+  }
+  if (tl.out1 != 0) tile_store_words(tl.out1, row, j, yw);
+  else global_store_words(reinterpret_cast<T*>(p.y) + (size_t)yrow * p.y_ld + c0, ncols, yw);
+  sq_acc += sq2.x + sq2.y;
+}
+
+template <typename T>
+__device__ __forceinline__ void epilogue_explain_fast(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow,
+                                                      int64_t add_row, int j, int c0, int ncols, float (&v)[32],
+                                                      const EpiTiles& tl, int row) {
+  uint32_t w[16];
+  if (add_row >= 0) {
+    global_load_words(reinterpret_cast<const T*>(p.add) + (size_t)add_row * p.add_ld + c0, ncols, w);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float2 a = __fadd2_rn(make_float2(v[2 * k], v[2 * k + 1]), Cvt<T>::unpack2(w[k]));
+      v[2 * k] = a.x;
+      v[2 * k + 1] = a.y;
+    }
+  }
+  if (p.out2 != nullptr) {
+    uint32_t ow[16];
+    if (p.mul2 != nullptr) {
+      global_load_words(reinterpret_cast<const T*>(p.mul2) + (size_t)ri.m * p.mul2_ld + c0, ncols, w);
+    } else {
+      const uint32_t one2 = Cvt<T>::pack2(1.f, 1.f);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) w[k] = one2;
+    }
+    const uint32_t mb = (p.mask2 != nullptr) ? __ldg(p.mask2 + (size_t)ri.m * p.mask2_ld + (c0 >> 5)) : 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float2 o = __fmul2_rn(make_float2(v[2 * k], v[2 * k + 1]), Cvt<T>::unpack2(w[k]));
+      // bit 2k -> low half, bit 2k+1 -> high half of an AND mask for the packed word
+      const uint32_t sel = ((mb >> (2 * k)) & 1u) * 0xffffu + ((mb >> (2 * k + 1)) & 1u) * 0xffff0000u;
+      ow[k] = Cvt<T>::pack2(o.x, o.y) & sel;
+    }
+    if (tl.out2 != 0) tile_store_words(tl.out2, row, j, ow);
+    else global_store_words(reinterpret_cast<T*>(p.out2) + (size_t)ri.m * p.out2_ld + c0, ncols, ow);
+  }
+  if (p.mul1 != nullptr) {
+    if (tl.in != 0) tile_load_words(tl.in, row, j, w);
+    else global_load_words(reinterpret_cast<const T*>(p.mul1) + (size_t)ri.m * p.mul1_ld + c0, ncols, w);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float2 g = __fmul2_rn(make_float2(v[2 * k], v[2 * k + 1]), Cvt<T>::unpack2(w[k]));
+      v[2 * k] = g.x;
+      v[2 * k + 1] = g.y;
+    }
+  }
+  if (p.y_f32) {
+    store32_f32(reinterpret_cast<float*>(p.y) + (size_t)yrow * p.y_ld + c0, ncols, v);
+  } else {
+    uint32_t yw[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) yw[k] = Cvt<T>::pack2(v[2 * k], v[2 * k + 1]);
+    if (tl.out1 != 0) tile_store_words(tl.out1, row, j, yw);
+    else global_store_words(reinterpret_cast<T*>(p.y) + (size_t)yrow * p.y_ld + c0, ncols, yw);
+  }
+}
+
+template <int MODE, typename T>
+__device__ __forceinline__ void epilogue_chunk_fast(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow,
+                                                    float inv_norm, int64_t add_row, const float* s_alpha,
+                                                    const float* s_beta, int j, int c0, int ncols, float (&v)[32],
+                                                    float& sq_acc, const EpiTiles& tl, int row) {
+  if (MODE == BCOSK_MODE_FWD) {
+    if (p.maskbits != nullptr)
+      epilogue_fwd_fast<T, true>(p, ri, yrow, inv_norm, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
+    else
+      epilogue_fwd_fast<T, false>(p, ri, yrow, inv_norm, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
+  } else {
+    epilogue_explain_fast<T>(p, ri, yrow, add_row, j, c0, ncols, v, tl, row);
+  }
+}
+
+// eligibility of the fast form (uniform over the launch)
+template <int MODE>
+__device__ __forceinline__ bool epilogue_fast_ok(const bcosk_igemm_params& p) {
+  if (MODE == BCOSK_MODE_FWD)
+    return !p.y_f32 && p.y_planes == 1 && (p.gain == nullptr || !p.gain_f32) && (p.res == nullptr || p.res_planes == 1) &&
+           p.scale_mode == BCOSK_SCALE_B2;
+  return (p.y_f32 || p.y_planes == 1) && (p.add == nullptr || p.add_planes == 1) && (p.mul1 == nullptr || !p.mul1_f32) &&
+         (p.out2 == nullptr || p.out2_planes == 1) && (p.mul2 == nullptr || !p.mul2_f32);
+}
+
+template <int MODE, typename T>
+__device__ __forceinline__ void epilogue_chunk(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow, float inv_norm,
+                                               int64_t add_row, const float* s_alpha, const float* s_beta, int j, int c0,
+                                               int ncols, float (&v)[32], float& sq_acc, const EpiTiles& tl, int row,
+                                               bool fast) {
+  if (fast) {
+    epilogue_chunk_fast<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
+  } else {
+    // the generic form is an out-of-line call: give it its own copies so that `v` stays in registers on the fast path
+    float vv[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) vv[i] = v[i];
+    float sq_local = sq_acc;
+    const RowInfo ri_copy = ri;
+    const EpiTiles tl_copy = tl;
+    epilogue_chunk_generic<MODE, T>(p, ri_copy, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, ncols, vv, sq_local, tl_copy,
+                                    row);
+    sq_acc = sq_local;
+  }
+}
+
 template <int BN, int MODE, typename T, bool HP>
 __global__ void __launch_bounds__(NUM_THREADS, TileCfg<BN, HP>::kMinBlocks)
 bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   const __grid_constant__ bcosk_igemm_params p) {
+                   const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out1,
+                   const __grid_constant__ CUtensorMap tmap_out2, const __grid_constant__ bcosk_igemm_params p,
+                   const IgemmAux aux) {
   using Cfg = TileCfg<BN, HP>;
-  constexpr int kStages = Cfg::kStages;
+  constexpr int kSlots = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kStages * Cfg::kBStageBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;   // non-HP: accumulator complete
+  // slot s = [A stage 16 KB | B stage BN*128 B]; after the main loop slots 0/1 hold the output tiles, and when an
+  // epilogue input tile is prefetched it owns the last slot (the ring then has kSlots-1 stages)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSlots * Cfg::kSlotBytes);
+  uint64_t* empty_bar = full_bar + kSlots;
+  uint64_t* tmem_full_bar = empty_bar + kSlots;    // non-HP: accumulator complete
   uint64_t* acc_full_bar = tmem_full_bar + 1;      // HP: [2] partial accumulator ready
   uint64_t* acc_empty_bar = acc_full_bar + 2;      // HP: [2] partial accumulator drained
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
+  uint64_t* in_bar = acc_empty_bar + 2;            // epilogue input tile landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(in_bar + 1);
   float* s_alpha = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
   float* s_beta = s_alpha + BN;
 
@@ -235,11 +511,13 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int chunks_per_stage = STAGE_K / p.kch;  // 1 (kch = 64) or 2 (kch = 32)
   const int total_chunks = p.num_segs * p.num_taps * p.chunks_per_tap;
   const int num_iters = total_chunks / chunks_per_stage;  // host guarantees divisibility
+  const bool use_in_tile = Cfg::kTmaEpilogue && aux.tma_in != 0;
+  const int num_stages = use_in_tile ? kSlots - 1 : kSlots;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kSlots; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -248,6 +526,7 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_init(&acc_full_bar[s], 1);
       mbar_init(&acc_empty_bar[s], 4);  // one arrival per epilogue warp
     }
+    mbar_init(in_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -262,6 +541,12 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (use_in_tile) {
+        // residual (forward) / producer gain (explain): whole 128 x BN tile, lands while the main loop runs
+        uint8_t* dst = smem + (kSlots - 1) * Cfg::kSlotBytes;
+        mbar_arrive_expect_tx(in_bar, Cfg::kTileBytes);
+        for (int b = 0; b < BN / 64; ++b) tma_load_2d(dst + b * 16384, &tmap_in, in_bar, n0 + b * 64, m0);
+      }
       // first output pixel of this tile -> im2col base coordinates
       const int opq = p.op * p.oq;
       const int img = m0 / opq;
@@ -272,24 +557,24 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int base_h = p.lo_h + pp * p.stride_h;
       const uint32_t a_chunk_bytes = BM * p.kch * 2;
       const uint32_t b_chunk_bytes = BN * p.kch * 2;
-      const uint32_t stage_bytes = A_STAGE_BYTES + Cfg::kBStageBytes;
       int stage = 0;
       uint32_t phase = 0;
       int seg = 0, tap = 0, kc = 0;
       for (int it = 0; it < num_iters; ++it) {
+        uint8_t* slot = smem + stage * Cfg::kSlotBytes;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kSlotBytes);
         for (int j = 0; j < chunks_per_stage; ++j) {
           const int ci = it * chunks_per_stage + j;
-          tma_load_im2col_4d(smem_a + stage * A_STAGE_BYTES + j * a_chunk_bytes, &tmap_a, &full_bar[stage],
-                             p.seg_a_choff[seg] + kc * p.kch, base_w, base_h, img, p.tap_off_w[tap], p.tap_off_h[tap]);
-          tma_load_2d(smem_b + stage * Cfg::kBStageBytes + j * b_chunk_bytes, &tmap_b, &full_bar[stage], ci * p.kch, n0);
+          tma_load_im2col_4d(slot + j * a_chunk_bytes, &tmap_a, &full_bar[stage], p.seg_a_choff[seg] + kc * p.kch, base_w,
+                             base_h, img, p.tap_off_w[tap], p.tap_off_h[tap]);
+          tma_load_2d(slot + A_STAGE_BYTES + j * b_chunk_bytes, &tmap_b, &full_bar[stage], ci * p.kch, n0);
           if (++kc == p.chunks_per_tap) {
             kc = 0;
             if (++tap == p.num_taps) { tap = 0; ++seg; }
           }
         }
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -313,11 +598,12 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           tmem_d = tmem_base + (uint32_t)(buf * BN);
           accumulate = 0;
         }
+        uint8_t* slot = smem + stage * Cfg::kSlotBytes;
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         for (int j = 0; j < chunks_per_stage; ++j) {
-          const uint64_t da = umma_smem_desc_kmajor(smem_u32(smem_a + stage * A_STAGE_BYTES + j * a_chunk_bytes), row_bytes);
-          const uint64_t db = umma_smem_desc_kmajor(smem_u32(smem_b + stage * Cfg::kBStageBytes + j * b_chunk_bytes), row_bytes);
+          const uint64_t da = umma_smem_desc_kmajor(smem_u32(slot + j * a_chunk_bytes), row_bytes);
+          const uint64_t db = umma_smem_desc_kmajor(smem_u32(slot + A_STAGE_BYTES + j * b_chunk_bytes), row_bytes);
           for (int k = 0; k < mma_per_chunk; ++k) {
             // advance 16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
             umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
@@ -326,7 +612,7 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         if (HP) umma_commit(&acc_full_bar[it & 1]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
       if (!HP) umma_commit(tmem_full_bar);  // accumulator complete
     }
@@ -359,7 +645,26 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     float inv_norm = 1.f;
     int64_t add_row = -1;
     if (MODE == BCOSK_MODE_FWD) {
-      if (p.scale_mode != BCOSK_SCALE_NONE && ri.valid) inv_norm = __ldg(p.inv_norm + ri.m);
+      if (p.scale_mode != BCOSK_SCALE_NONE && ri.valid) {
+        if (p.inv_norm != nullptr) {
+          inv_norm = __ldg(p.inv_norm + ri.m);
+        } else {
+          // patch norm from the producer's per-pixel sums of squares (reference calc_patch_norms, bcosconv2d.py:196-231)
+          const size_t part_stride = (size_t)p.a_nb * p.sq_h * p.sq_w;
+          float acc = 0.f;
+          for (int dy = 0; dy < p.sq_k; ++dy) {
+            const int yy = ri.p * p.sq_stride - p.sq_pad + dy;
+            if (yy < 0 || yy >= p.sq_h) continue;
+            for (int dx = 0; dx < p.sq_k; ++dx) {
+              const int xx = ri.q * p.sq_stride - p.sq_pad + dx;
+              if (xx < 0 || xx >= p.sq_w) continue;
+              const size_t o = ((size_t)ri.img * p.sq_h + yy) * p.sq_w + xx;
+              for (int t = 0; t < p.sq_parts; ++t) acc += __ldg(p.sq_in + t * part_stride + o);
+            }
+          }
+          inv_norm = 1.0f / (sqrtf(acc + p.sq_eps_in) + p.sq_eps_out);
+        }
+      }
     } else {
       if (p.add != nullptr && ri.valid) {
         const int s = p.add_stride;
@@ -369,6 +674,10 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     float sq_acc = 0.f;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    EpiTiles tl;
+    tl.in = use_in_tile ? smem_u32(smem + (kSlots - 1) * Cfg::kSlotBytes) : 0u;
+    tl.out1 = (Cfg::kTmaEpilogue && aux.tma_out1) ? smem_u32(smem) : 0u;
+    tl.out2 = (Cfg::kTmaEpilogue && aux.tma_out2) ? smem_u32(smem + Cfg::kSlotBytes) : 0u;
 
     if constexpr (HP) {
       float acc[BN];
@@ -397,11 +706,14 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = acc[j * 32 + i];
-          epilogue_chunk<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, min(32, p.n - c0), v, sq_acc);
+          epilogue_chunk_generic<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, min(32, p.n - c0), v,
+                                          sq_acc, tl, row);
         }
       }
     } else {
-      mbar_wait(tmem_full_bar, 0);
+      const bool fast = epilogue_fast_ok<MODE>(p);
+      if (use_in_tile) mbar_wait(in_bar, 0);
+      mbar_wait(tmem_full_bar, 0);  // all MMAs done: accumulator complete AND every pipeline slot is drained
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < BN / 32; ++j) {
@@ -414,12 +726,326 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        epilogue_chunk<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, min(32, p.n - c0), v, sq_acc);
+        epilogue_chunk<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, min(32, p.n - c0), v, sq_acc, tl,
+                                row, fast);
+      }
+      if (tl.out1 != 0 || tl.out2 != 0) {
+        // generic-proxy smem writes -> visible to the async proxy, then one thread issues the bulk tensor stores
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          for (int b = 0; b < BN / 64; ++b) {
+            const int c = n0 + b * 64;
+            if (c >= p.n) break;
+            if (tl.out1 != 0) tma_store_2d_addr(&tmap_out1, tl.out1 + b * 16384, c, m0);
+            if (tl.out2 != 0) tma_store_2d_addr(&tmap_out2, tl.out2 + b * 16384, c, m0);
+          }
+          tma_store_commit_and_wait_read();
+        }
       }
     }
     if (MODE == BCOSK_MODE_FWD) {
       if (p.sq_out != nullptr && ri.valid) p.sq_out[(size_t)tile_n * M + ri.m] = sq_acc;
     }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// =================================================================================================
+// Persistent variant (throughput mode): one CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ...
+//   warp 0  A/B TMA producer (3-4 slot ring, runs ahead across tiles)
+//   warp 1  TMEM allocator + MMA issuer, two accumulator buffers (tile i -> buffer i&1)
+//   warp 2  epilogue-input producer: residual / producer-gain tile of the NEXT tile, double buffered
+//   warp 3  idle
+//   warps 4..11  epilogue: warp w reads TMEM lane quadrant w%4 and column half (w-4)/4, stages the output tiles in
+//                shared memory; one thread issues the TMA stores, whose shared-memory reads overlap the next tile
+// so a tile's epilogue overlaps the next tile's loads and MMAs inside one CTA.
+// =================================================================================================
+constexpr int P_THREADS = 384;
+constexpr int P_EPI_THREADS = 256;
+
+template <int BN> struct PersistCfg {
+  static constexpr int kSlots = (BN == 128) ? 3 : 4;
+  static constexpr int kBStageBytes = BN * STAGE_K * 2;
+  static constexpr int kSlotBytes = A_STAGE_BYTES + kBStageBytes;
+  static constexpr int kTileBytes = BM * BN * 2;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kRingBytes = kSlots * kSlotBytes;
+  // ring | in[2] | out1 | out2 | barriers (256 B) | per-channel vectors | sq scratch      (BN=128: 231,680 B of 232,448)
+  static constexpr int kSmemBytes = kRingBytes + 4 * kTileBytes + 256 + 2 * BN * 4 + 2 * BM * 4;
+};
+
+template <int BN, int MODE, typename T>
+__global__ void __launch_bounds__(P_THREADS, 1)
+bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                              const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out1,
+                              const __grid_constant__ CUtensorMap tmap_out2, const __grid_constant__ bcosk_igemm_params p,
+                              const IgemmAux aux) {
+  using Cfg = PersistCfg<BN>;
+  constexpr int kSlots = Cfg::kSlots;
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  uint8_t* smem = smem_dyn;   // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* in_tile = smem + Cfg::kRingBytes;                 // [2][kTileBytes]
+  uint8_t* out1_tile = in_tile + 2 * Cfg::kTileBytes;
+  uint8_t* out2_tile = out1_tile + Cfg::kTileBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out2_tile + Cfg::kTileBytes);
+  uint64_t* empty_bar = full_bar + kSlots;
+  uint64_t* acc_full_bar = empty_bar + kSlots;               // [2]
+  uint64_t* acc_empty_bar = acc_full_bar + 2;                // [2]
+  uint64_t* in_full_bar = acc_empty_bar + 2;                 // [2]
+  uint64_t* in_empty_bar = in_full_bar + 2;                  // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(in_empty_bar + 2);
+  float* s_alpha = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+  float* s_beta = s_alpha + BN;
+  float* s_sq = s_beta + BN;                                 // [2][BM] per-half partial sums of squares
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = (p.n + BN - 1) / BN;
+  const int M = p.a_nb * p.op * p.oq;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int total_tiles = m_tiles * n_tiles;
+  const int chunks_per_stage = STAGE_K / p.kch;
+  const int num_iters = (p.num_segs * p.num_taps * p.chunks_per_tap) / chunks_per_stage;
+  const bool use_in_tile = aux.tma_in != 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full_bar[s], 1);
+      mbar_init(&acc_empty_bar[s], 8);   // one arrival per epilogue warp
+      mbar_init(&in_full_bar[s], 1);
+      mbar_init(&in_empty_bar[s], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== A/B producer =====================
+    if (lane == 0) {
+      const int opq = p.op * p.oq;
+      const uint32_t a_chunk_bytes = BM * p.kch * 2;
+      const uint32_t b_chunk_bytes = BN * p.kch * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+        const int img = m0 / opq;
+        const int rem = m0 - img * opq;
+        const int pp = rem / p.oq;
+        const int qq = rem - pp * p.oq;
+        const int base_w = p.lo_w + qq * p.stride_w;
+        const int base_h = p.lo_h + pp * p.stride_h;
+        int seg = 0, tap = 0, kc = 0;
+        for (int it = 0; it < num_iters; ++it) {
+          uint8_t* slot = smem + stage * Cfg::kSlotBytes;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kSlotBytes);
+          for (int j = 0; j < chunks_per_stage; ++j) {
+            const int ci = it * chunks_per_stage + j;
+            tma_load_im2col_4d(slot + j * a_chunk_bytes, &tmap_a, &full_bar[stage], p.seg_a_choff[seg] + kc * p.kch, base_w,
+                               base_h, img, p.tap_off_w[tap], p.tap_off_h[tap]);
+            tma_load_2d(slot + A_STAGE_BYTES + j * b_chunk_bytes, &tmap_b, &full_bar[stage], ci * p.kch, n0);
+            if (++kc == p.chunks_per_tap) {
+              kc = 0;
+              if (++tap == p.num_taps) { tap = 0; ++seg; }
+            }
+          }
+          if (++stage == kSlots) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16((uint32_t)p.dtype, BM, BN);
+      const uint32_t row_bytes = p.kch * 2;
+      const uint32_t a_chunk_bytes = BM * p.kch * 2;
+      const uint32_t b_chunk_bytes = BN * p.kch * 2;
+      const int mma_per_chunk = p.kch / 16;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t i = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        const uint32_t buf = i & 1u;
+        mbar_wait(&acc_empty_bar[buf], ((i >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        uint32_t accumulate = 0;
+        for (int it = 0; it < num_iters; ++it) {
+          uint8_t* slot = smem + stage * Cfg::kSlotBytes;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          for (int j = 0; j < chunks_per_stage; ++j) {
+            const uint64_t da = umma_smem_desc_kmajor(smem_u32(slot + j * a_chunk_bytes), row_bytes);
+            const uint64_t db = umma_smem_desc_kmajor(smem_u32(slot + A_STAGE_BYTES + j * b_chunk_bytes), row_bytes);
+            for (int k = 0; k < mma_per_chunk; ++k) {
+              umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kSlots) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full_bar[buf]);
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== epilogue-input producer =====================
+    if (lane == 0 && use_in_tile) {
+      uint32_t i = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        const uint32_t buf = i & 1u;
+        const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+        mbar_wait(&in_empty_bar[buf], ((i >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&in_full_bar[buf], Cfg::kTileBytes);
+        for (int b = 0; b < BN / 64; ++b)
+          tma_load_2d(in_tile + buf * Cfg::kTileBytes + b * 16384, &tmap_in, &in_full_bar[buf], n0 + b * 64, m0);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (warps 4..11) =====================
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;                  // column half of the tile handled by this warp
+    constexpr int kChunksPerHalf = BN / 64;            // 32-column chunks per half: 2 (BN=128) or 1 (BN=64)
+    const int row = quad * 32 + lane;
+    const int et = threadIdx.x - 128;                  // 0..255
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const bool any_out_tile = aux.tma_out1 || aux.tma_out2;
+    const bool fast = epilogue_fast_ok<MODE>(p);
+    uint32_t i = 0;
+    int staged_n0 = -1;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      const uint32_t buf = i & 1u;
+      const int tile_n = t % n_tiles;
+      const int m0 = (t / n_tiles) * BM, n0 = tile_n * BN;
+      if (MODE == BCOSK_MODE_FWD && n0 != staged_n0) {
+        // (re)stage the per-channel vectors of this column tile
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int c = et; c < BN; c += P_EPI_THREADS) {
+          const int cc = n0 + c;
+          s_alpha[c] = (p.alpha != nullptr && cc < p.n) ? __ldg(p.alpha + cc) : 1.f;
+          s_beta[c] = (p.beta != nullptr && cc < p.n) ? __ldg(p.beta + cc) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        staged_n0 = n0;
+      }
+      RowInfo ri;
+      ri.m = m0 + row;
+      ri.valid = ri.m < M;
+      {
+        const int opq = p.op * p.oq;
+        const int mm = ri.valid ? ri.m : 0;
+        ri.img = mm / opq;
+        const int rem = mm - ri.img * opq;
+        ri.p = rem / p.oq;
+        ri.q = rem - ri.p * p.oq;
+      }
+      const int64_t yrow = p.os_0 + (int64_t)ri.img * p.os_n + (int64_t)ri.p * p.os_p + (int64_t)ri.q * p.os_q;
+      float inv_norm = 1.f;
+      int64_t add_row = -1;
+      if (MODE == BCOSK_MODE_FWD) {
+        if (p.scale_mode != BCOSK_SCALE_NONE && ri.valid) {
+          if (p.inv_norm != nullptr) {
+            inv_norm = __ldg(p.inv_norm + ri.m);
+          } else {
+            const size_t part_stride = (size_t)p.a_nb * p.sq_h * p.sq_w;
+            float acc = 0.f;
+            for (int dy = 0; dy < p.sq_k; ++dy) {
+              const int yy = ri.p * p.sq_stride - p.sq_pad + dy;
+              if (yy < 0 || yy >= p.sq_h) continue;
+              for (int dx = 0; dx < p.sq_k; ++dx) {
+                const int xx = ri.q * p.sq_stride - p.sq_pad + dx;
+                if (xx < 0 || xx >= p.sq_w) continue;
+                const size_t o = ((size_t)ri.img * p.sq_h + yy) * p.sq_w + xx;
+                for (int tt = 0; tt < p.sq_parts; ++tt) acc += __ldg(p.sq_in + tt * part_stride + o);
+              }
+            }
+            inv_norm = 1.0f / (sqrtf(acc + p.sq_eps_in) + p.sq_eps_out);
+          }
+        }
+      } else {
+        if (p.add != nullptr && ri.valid) {
+          const int s = p.add_stride;
+          if (ri.p % s == 0 && ri.q % s == 0 && ri.p / s < p.add_p && ri.q / s < p.add_q)
+            add_row = ((int64_t)ri.img * p.add_p + ri.p / s) * p.add_q + ri.q / s;
+        }
+      }
+      EpiTiles tl;
+      tl.in = use_in_tile ? smem_u32(in_tile + buf * Cfg::kTileBytes) : 0u;
+      tl.out1 = aux.tma_out1 ? smem_u32(out1_tile) : 0u;
+      tl.out2 = aux.tma_out2 ? smem_u32(out2_tile) : 0u;
+
+      mbar_wait(&acc_full_bar[buf], (i >> 1) & 1u);
+      tc_fence_after();
+      if (use_in_tile) mbar_wait(&in_full_bar[buf], (i >> 1) & 1u);
+      if (any_out_tile && i > 0) {
+        // the previous tile's TMA stores must have finished reading the staging tiles before they are overwritten
+        if (et == 0) tma_store_wait_read();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      float sq_acc = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < kChunksPerHalf; ++jj) {
+        const int j = half * kChunksPerHalf + jj;
+        const int c0 = n0 + j * 32;
+        if (c0 < p.n) {   // warp-uniform
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(buf * BN + j * 32), raw);
+          tmem_ld_wait();
+          if (ri.valid) {
+            float v[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+            epilogue_chunk<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, min(32, p.n - c0), v, sq_acc, tl,
+                                    row, fast);
+          }
+        }
+      }
+      // accumulator and input tile are consumed: hand them back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&acc_empty_bar[buf]);
+        if (use_in_tile) mbar_arrive(&in_empty_bar[buf]);
+      }
+      const bool want_sq = MODE == BCOSK_MODE_FWD && p.sq_out != nullptr;
+      if (want_sq) s_sq[half * BM + row] = sq_acc;
+      if (any_out_tile) fence_proxy_async_smem();
+      if (any_out_tile || want_sq) asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (any_out_tile && et == 0) {
+        for (int b = 0; b < BN / 64; ++b) {
+          const int c = n0 + b * 64;
+          if (c >= p.n) break;
+          if (tl.out1 != 0) tma_store_2d_addr(&tmap_out1, tl.out1 + b * 16384, c, m0);
+          if (tl.out2 != 0) tma_store_2d_addr(&tmap_out2, tl.out2 + b * 16384, c, m0);
+        }
+        tma_store_commit();
+      }
+      if (want_sq && half == 0 && ri.valid) p.sq_out[(size_t)tile_n * M + ri.m] = s_sq[row] + s_sq[BM + row];
+      if (want_sq) asm volatile("bar.sync 1, 256;" ::: "memory");   // s_sq is rewritten by the next tile
+    }
+    if (any_out_tile && et == 0) tma_store_wait_read();
     tc_fence_before();
   }
 
@@ -471,8 +1097,12 @@ __global__ void bcosk_debug_a_tile_kernel(const __grid_constant__ CUtensorMap tm
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+struct LaunchMaps {
+  CUtensorMap a, b, in, out1, out2;
+};
+
 template <int BN, int MODE, bool HP>
-static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const bcosk_igemm_params& p, cudaStream_t st) {
+static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const IgemmAux& aux, cudaStream_t st) {
   using Cfg = TileCfg<BN, HP>;
   auto kern = bcosk_igemm_kernel<BN, MODE, __nv_bfloat16, HP>;
   auto kern_h = bcosk_igemm_kernel<BN, MODE, __half, HP>;
@@ -488,9 +1118,40 @@ static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const bcos
   if (m_tiles * n_tiles > 0x7fffffffLL) return set_error(BCOSK_EUNSUPPORTED, "igemm: grid too large");
   dim3 grid((unsigned)(m_tiles * n_tiles));
   if (p.dtype == BCOSK_DTYPE_BF16)
-    kern<<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, p);
+    kern<<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.out1, mp.out2, p, aux);
   else
-    kern_h<<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, p);
+    kern_h<<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.out1, mp.out2, p, aux);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+static int g_num_sms = 0;
+static bool g_persistent_enabled = true;
+
+template <int BN, int MODE>
+static int launch_persistent(const LaunchMaps& mp, const bcosk_igemm_params& p, const IgemmAux& aux, cudaStream_t st) {
+  using Cfg = PersistCfg<BN>;
+  auto kern = bcosk_igemm_persistent_kernel<BN, MODE, __nv_bfloat16>;
+  auto kern_h = bcosk_igemm_persistent_kernel<BN, MODE, __half>;
+  const void* fn = (p.dtype == BCOSK_DTYPE_BF16) ? (const void*)kern : (const void*)kern_h;
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[p.dtype]) {
+    BCOSK_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done[p.dtype] = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    BCOSK_CUDA_CHECK(cudaGetDevice(&dev));
+    BCOSK_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long M = (long long)p.a_nb * p.op * p.oq;
+  const long long tiles = ((M + BM - 1) / BM) * ((p.n + BN - 1) / BN);
+  if (tiles > 0x7fffffffLL) return set_error(BCOSK_EUNSUPPORTED, "igemm: too many tiles");
+  dim3 grid((unsigned)(tiles < g_num_sms ? tiles : g_num_sms));
+  if (p.dtype == BCOSK_DTYPE_BF16)
+    kern<<<grid, P_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.out1, mp.out2, p, aux);
+  else
+    kern_h<<<grid, P_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.out1, mp.out2, p, aux);
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }
@@ -506,19 +1167,43 @@ static int validate(const bcosk_igemm_params& p) {
   if (p.a_c % 8 != 0) return set_error(BCOSK_EINVAL, "igemm: a_c must be a multiple of 8 (16-byte pixels)");
   if (p.n < 8 || p.n % 8 != 0) return set_error(BCOSK_EINVAL, "igemm: n must be a positive multiple of 8");
   if (p.dtype != BCOSK_DTYPE_BF16 && p.dtype != BCOSK_DTYPE_F16) return set_error(BCOSK_EINVAL, "igemm: dtype");
-  if (p.mode == BCOSK_MODE_FWD && p.scale_mode != BCOSK_SCALE_NONE && !p.inv_norm)
-    return set_error(BCOSK_EINVAL, "igemm: inv_norm required for a B-cos scale");
+  if (p.mode == BCOSK_MODE_FWD && p.scale_mode != BCOSK_SCALE_NONE && !p.inv_norm && !p.sq_in)
+    return set_error(BCOSK_EINVAL, "igemm: inv_norm or sq_in required for a B-cos scale");
+  if (!p.inv_norm && p.sq_in && (p.sq_parts < 1 || p.sq_k < 1 || p.sq_stride < 1 || p.sq_h < 1 || p.sq_w < 1))
+    return set_error(BCOSK_EINVAL, "igemm: bad sq_in geometry");
   if (p.y_ld % (p.y_f32 ? 4 : 8) != 0) return set_error(BCOSK_EINVAL, "igemm: y_ld alignment");
   if (p.a_nb < 1 || p.op < 1 || p.oq < 1) return set_error(BCOSK_EINVAL, "igemm: empty problem");
   return BCOSK_OK;
 }
 
-static int make_maps(const bcosk_igemm_params& p, int bn, CUtensorMap* ta, CUtensorMap* tb) {
-  int rc = make_im2col_map_nhwc(ta, p.a, p.a_nb, p.a_h, p.a_w, p.a_c, p.lo_w, p.lo_h, p.up_w, p.up_h, p.stride_w,
+static int make_maps(const bcosk_igemm_params& p, int bn, LaunchMaps* mp, IgemmAux* aux) {
+  memset(mp, 0, sizeof(*mp));
+  memset(aux, 0, sizeof(*aux));
+  int rc = make_im2col_map_nhwc(&mp->a, p.a, p.a_nb, p.a_h, p.a_w, p.a_c, p.lo_w, p.lo_h, p.up_w, p.up_h, p.stride_w,
                                 p.stride_h, p.kch, BM, p.kch == 64 ? 128 : 64);
   if (rc) return rc;
   const long long ktot = (long long)p.num_segs * p.num_taps * p.chunks_per_tap * p.kch;
-  return make_tiled_map_2d(tb, p.b, ktot, p.n, p.kch, bn, p.kch == 64 ? 128 : 64);
+  rc = make_tiled_map_2d(&mp->b, p.b, ktot, p.n, p.kch, bn, p.kch == 64 ? 128 : 64);
+  if (rc) return rc;
+  // ---- TMA epilogue (throughput mode): 16-bit single-plane tensors addressed densely by output row
+  const long long M = (long long)p.a_nb * p.op * p.oq;
+  const bool tile_ok = !p.hp_accum && (bn == 64 || bn == 128);
+  const bool dense_out = p.os_0 == 0 && p.os_q == 1 && p.os_p == p.oq && p.os_n == (long long)p.op * p.oq;
+  auto map16 = [&](CUtensorMap* m, const void* base, int ld) -> bool {
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ld % 8 != 0) return false;
+    return make_tiled_map_2d(m, base, ld, M, 64, BM, 128) == BCOSK_OK;
+  };
+  if (tile_ok) {
+    if (p.y && !p.y_f32 && p.y_planes == 1 && dense_out) aux->tma_out1 = map16(&mp->out1, p.y, p.y_ld) ? 1 : 0;
+    if (p.mode == BCOSK_MODE_FWD) {
+      if (p.gain && !p.gain_f32) aux->tma_out2 = map16(&mp->out2, p.gain, p.gain_ld) ? 1 : 0;
+      if (p.res && p.res_planes == 1) aux->tma_in = map16(&mp->in, p.res, p.res_ld) ? 1 : 0;
+    } else {
+      if (p.out2 && p.out2_planes == 1) aux->tma_out2 = map16(&mp->out2, p.out2, p.out2_ld) ? 1 : 0;
+      if (p.mul1 && !p.mul1_f32) aux->tma_in = map16(&mp->in, p.mul1, p.mul1_ld) ? 2 : 0;
+    }
+  }
+  return BCOSK_OK;
 }
 
 }  // namespace bcosk
@@ -535,20 +1220,28 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return set_error(BCOSK_EINVAL, "igemm: block_n");
   if (p.hp_accum && bn > 64) return set_error(BCOSK_EINVAL, "igemm: hp_accum needs block_n <= 64");
   p.block_n = bn;
-  CUtensorMap ta, tb;
-  rc = make_maps(p, bn, &ta, &tb);
+  LaunchMaps mp;
+  IgemmAux aux;
+  rc = make_maps(p, bn, &mp, &aux);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define BCOSK_DISPATCH(BN_)                                                                        \
-  case BN_:                                                                                        \
-    return p.mode == BCOSK_MODE_FWD ? launch_igemm<BN_, BCOSK_MODE_FWD, false>(ta, tb, p, st)      \
-                                    : launch_igemm<BN_, BCOSK_MODE_EXPLAIN, false>(ta, tb, p, st);
+#define BCOSK_DISPATCH(BN_)                                                                         \
+  case BN_:                                                                                         \
+    return p.mode == BCOSK_MODE_FWD ? launch_igemm<BN_, BCOSK_MODE_FWD, false>(mp, p, aux, st)      \
+                                    : launch_igemm<BN_, BCOSK_MODE_EXPLAIN, false>(mp, p, aux, st);
+  if (!p.hp_accum && g_persistent_enabled && (bn == 64 || bn == 128)) {
+    if (bn == 64)
+      return p.mode == BCOSK_MODE_FWD ? launch_persistent<64, BCOSK_MODE_FWD>(mp, p, aux, st)
+                                      : launch_persistent<64, BCOSK_MODE_EXPLAIN>(mp, p, aux, st);
+    return p.mode == BCOSK_MODE_FWD ? launch_persistent<128, BCOSK_MODE_FWD>(mp, p, aux, st)
+                                    : launch_persistent<128, BCOSK_MODE_EXPLAIN>(mp, p, aux, st);
+  }
   if (p.hp_accum) {
     if (bn == 32)
-      return p.mode == BCOSK_MODE_FWD ? launch_igemm<32, BCOSK_MODE_FWD, true>(ta, tb, p, st)
-                                      : launch_igemm<32, BCOSK_MODE_EXPLAIN, true>(ta, tb, p, st);
-    return p.mode == BCOSK_MODE_FWD ? launch_igemm<64, BCOSK_MODE_FWD, true>(ta, tb, p, st)
-                                    : launch_igemm<64, BCOSK_MODE_EXPLAIN, true>(ta, tb, p, st);
+      return p.mode == BCOSK_MODE_FWD ? launch_igemm<32, BCOSK_MODE_FWD, true>(mp, p, aux, st)
+                                      : launch_igemm<32, BCOSK_MODE_EXPLAIN, true>(mp, p, aux, st);
+    return p.mode == BCOSK_MODE_FWD ? launch_igemm<64, BCOSK_MODE_FWD, true>(mp, p, aux, st)
+                                    : launch_igemm<64, BCOSK_MODE_EXPLAIN, true>(mp, p, aux, st);
   }
   switch (bn) {
     BCOSK_DISPATCH(32)
@@ -558,6 +1251,12 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
   }
 #undef BCOSK_DISPATCH
   return set_error(BCOSK_EINVAL, "igemm: unreachable");
+}
+
+extern "C" int bcosk_set_persistent(int32_t enabled) {
+  const int prev = g_persistent_enabled ? 1 : 0;
+  g_persistent_enabled = enabled != 0;
+  return prev;
 }
 
 extern "C" int bcosk_debug_a_tile(const bcosk_igemm_params* pp, int32_t tile_m, int32_t chunk, void* out, void* stream) {

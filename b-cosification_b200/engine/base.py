@@ -114,7 +114,11 @@ class PlanBase:
     # ------------------------------------------------------------------ forward emission
     def _conv_fwd(self, name: str, x: Act, w: Tensor, stride: int, pad_lo: int, pad_hi: int, *, bn: Optional[str],
                   relu: bool, res: Optional[Act] = None, want_mask: bool = False, y_f32: bool = False,
-                  inv_norm: Optional[Tensor] = None, kch: int = 64, want_sq: bool = True) -> Tuple[Act, ConvRec]:
+                  inv_norm: Optional[Tensor] = None, kch: int = 64, want_sq: bool = True,
+                  sq_geom: Optional[Tuple[int, int, int, int, int]] = None) -> Tuple[Act, ConvRec]:
+        """One fused launch: B-cos conv (+BN multiplier, +residual, +ReLU).  The patch norm comes from `x.sq`
+        (per-pixel sums of squares written by x's producer) and is evaluated inside the kernel; `sq_geom`
+        overrides its (h, w, k, stride, pad) when the GEMM geometry is not the convolution's (space-to-depth stem)."""
         nb = self.nb
         h, wd = x.hw
         o, c, kh, kw = w.shape
@@ -123,10 +127,12 @@ class PlanBase:
         M = nb * oh * ow
         cin_phys = x.t.shape[-1] // self.planes
         assert c <= cin_phys
+        sq_in = None
         if inv_norm is None and self.scale_mode != L.BCOSK_SCALE_NONE:
-            inv_norm = self._empty(M, dtype=torch.float32)
-            self.fwd_ops.append(O.PatchNormOp(name + ".norm", x.sq, x.parts, nb, h, wd, kh, stride, pad_lo, 1e-6, 0.0,
-                                              inv_norm, oh, ow))
+            sq_in = x.sq
+            if sq_geom is None:
+                assert pad_lo == pad_hi and kh == kw, "asymmetric convs must pass inv_norm or sq_geom"
+                sq_geom = (h, wd, kh, stride, pad_lo)
         bmat, cpt = P.pack_b(P.fwd_weight_taps(w), self.planes, kch, self.dt)
         alpha, beta = self._bn_alpha(bn) if bn else (None, None)
         block_n = self._block_n(o)
@@ -144,7 +150,8 @@ class PlanBase:
             up=(pad_hi - (kw - 1), pad_hi - (kh - 1)), stride=(stride, stride), op=oh, oq=ow, kch=kch, chunks_per_tap=cpt,
             taps=P.conv_taps(kh, kw), seg_a_choff=P.seg_a_offsets(self.planes, cin_phys), dtype=self.dt_code,
             mode=L.BCOSK_MODE_FWD, block_n=block_n, scale_mode=self.scale_mode, b_exp=self.b, relu=relu,
-            inv_norm=inv_norm, alpha=alpha, beta=beta, res=None if res is None else res.t, res_planes=self.planes,
+            inv_norm=inv_norm, sq_in=sq_in, sq_geom=sq_geom, alpha=alpha, beta=beta,
+            res=None if res is None else res.t, res_planes=self.planes,
             gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32, hp_accum=self.hp_accum,
             algo_flops=2.0 * M * o * float((w != 0).sum().item()) / o))
         rec.algo_flops = self.fwd_ops[-1].algo_flops

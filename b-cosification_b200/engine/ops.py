@@ -39,7 +39,10 @@ class IgemmOp:
     scale_mode: int = 0
     b_exp: float = 2.0
     relu: bool = False
-    inv_norm: Optional[Tensor] = None
+    inv_norm: Optional[Tensor] = None      # [M] precomputed 1/||patch||, or None -> computed in-kernel from sq_in
+    sq_in: Optional[Tensor] = None         # [parts, nb*sq_h*sq_w] per-pixel sums of squares of the input tensor
+    sq_geom: Optional[Tuple[int, int, int, int, int]] = None   # (sq_h, sq_w, k, stride, pad)
+    sq_eps: Tuple[float, float] = (1e-6, 0.0)                   # (inside sqrt, outside sqrt)
     alpha: Optional[Tensor] = None
     beta: Optional[Tensor] = None
     res: Optional[Tensor] = None
@@ -90,6 +93,8 @@ class IgemmOp:
         total += nbytes(self.b)
         ydense = self.M * (self.y.shape[-1]) * self.y.element_size()      # rows actually written
         total += ydense
+        if self.inv_norm is None and self.sq_in is not None:
+            total += nbytes(self.sq_in)
         for t in (self.inv_norm, self.alpha, self.beta, self.res, self.gain, self.maskbits, self.sq_out, self.add,
                   self.mul1, self.out2, self.mul2, self.mask2):
             total += nbytes(t)
@@ -120,6 +125,11 @@ class IgemmOp:
         p.n, p.dtype, p.block_n, p.mode = self.n, self.dtype, self.resolved_block_n(), self.mode
         p.scale_mode, p.b_exp, p.relu = self.scale_mode, self.b_exp, int(self.relu)
         p.set_ptr("inv_norm", self.inv_norm)
+        if self.inv_norm is None and self.sq_in is not None:
+            p.sq_in = self.sq_in.data_ptr()
+            p.sq_parts = self.sq_in.shape[0]
+            p.sq_h, p.sq_w, p.sq_k, p.sq_stride, p.sq_pad = self.sq_geom
+            p.sq_eps_in, p.sq_eps_out = self.sq_eps
         p.set_ptr("alpha", self.alpha)
         p.set_ptr("beta", self.beta)
         if self.res is not None:

@@ -69,12 +69,10 @@ class ResNetPlan(PlanBase):
         sq0 = self._empty(1, nb * S * S, dtype=torch.float32)
         self.fwd_ops.append(O.InputPrepOp("input_prep", self.x_in, self.mean, self.inv_std, a0, self.stem_cp, pl,
                                           self.dt_code, sq0))
-        inv0 = self._empty(nb * h2 * h2, dtype=torch.float32)
-        if self.scale_mode != L.BCOSK_SCALE_NONE:
-            self.fwd_ops.append(O.PatchNormOp("stem.norm", sq0, 1, nb, S, S, 7, 2, 3, 1e-6, 0.0, inv0, h2, h2))
         w4 = P.stem_s2d_weight(sd["model.conv1.linear.weight"], self.stem_cp)
-        y1, self.stem = self._conv_fwd("stem", Act(a0, self.stem_cp), w4, 1, 2, 1, bn="model.bn1", relu=True,
-                                       inv_norm=inv0, kch=self.stem_kch, want_sq=False)
+        # the patch norm is the ORIGINAL 7x7/2 pad-3 window over the full-resolution sums of squares
+        y1, self.stem = self._conv_fwd("stem", Act(a0, self.stem_cp, sq0, 1), w4, 1, 2, 1, bn="model.bn1", relu=True,
+                                       kch=self.stem_kch, want_sq=False, sq_geom=(S, S, 7, 2, 3))
         # ---- AvgPool2d(3, 2, 1) (replaces maxpool)
         hp = (h2 + 2 - 3) // 2 + 1
         p1 = self._empty(nb, hp, hp, pl * 64)

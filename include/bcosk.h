@@ -83,7 +83,12 @@ typedef struct bcosk_igemm_params {
   int32_t scale_mode; /* BCOSK_SCALE_* */
   float b_exp;        /* B (used by BCOSK_SCALE_POW) */
   int32_t relu;
-  const float* inv_norm; /* [M] 1/||patch||, NULL iff scale_mode == NONE */
+  const float* inv_norm; /* [M] 1/||patch||; NULL = compute from sq_in (or scale_mode == NONE) */
+  /* patch norm from the producer's per-pixel sums of squares (calc_patch_norms bcosconv2d.py:196-231):
+   * 1/(sqrt(sumpool_{sq_k,sq_stride,sq_pad} sum_parts sq_in + sq_eps_in) + sq_eps_out), sq_in = [sq_parts][a_nb*sq_h*sq_w] */
+  const float* sq_in;
+  int32_t sq_parts, sq_h, sq_w, sq_k, sq_stride, sq_pad;
+  float sq_eps_in, sq_eps_out;
   const float* alpha;    /* [n] per-channel multiplier (BN weight/sqrt(var+eps)), NULL = 1 */
   const float* beta;     /* [n] per-channel bias, NULL = 0 */
   const void* res;       /* [M, res_ld] residual (16-bit planes), NULL = none */
@@ -117,6 +122,10 @@ typedef struct bcosk_igemm_params {
 } bcosk_igemm_params;
 
 int bcosk_igemm(const bcosk_igemm_params* p, void* stream);
+
+/* Scheduling switch for A/B measurements: 1 (default) = persistent one-CTA-per-SM kernel with TMEM double buffering for
+ * the throughput mode, 0 = one CTA per tile.  Returns the previous setting.  Results are identical. */
+int bcosk_set_persistent(int32_t enabled);
 
 /* Debug aid: raw bytes of the first A chunk (tile_m, chunk) as TMA im2col lands it in shared memory
  * (128 rows x kch 16-bit values, de-swizzled) -> out[128*kch]. */

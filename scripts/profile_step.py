@@ -16,7 +16,10 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--arch", default="resnet50")
 ap.add_argument("--only", default="")
 ap.add_argument("--planes", type=int, default=1)
+ap.add_argument("--persistent", type=int, default=1)
 a = ap.parse_args()
+from bcos_b200 import _lib
+_lib.load().bcosk_set_persistent(a.persistent)
 plan = synthetic_resnet_plan(a.arch, a.batch, planes=a.planes, device="cuda", input_u8=True)
 imgs = torch.from_numpy(synth.synth_images_u8(32, 224, 5)).repeat((a.batch + 31) // 32, 1, 1, 1)[:a.batch].contiguous()
 plan.load_input(imgs)

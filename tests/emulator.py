@@ -102,18 +102,30 @@ def run_igemm(op: O.IgemmOp) -> None:
     D = A @ op.b.float().t()                      # [M, n]
     rows = _out_rows(op)
     if op.mode == L.BCOSK_MODE_FWD:
+        inv_norm = op.inv_norm
+        if inv_norm is None and op.sq_in is not None:      # in-kernel patch norm from the producer's sums of squares
+            sh, sw, k, st, pd = op.sq_geom
+            nb = op.a.shape[0]
+            sq = op.sq_in.view(op.sq_in.shape[0], nb, 1, sh, sw).sum(0)
+            sp = torch.nn.functional.avg_pool2d(sq, k, stride=st, padding=pd, divisor_override=1)
+            assert sp.shape[-2:] == (op.op, op.oq), (op.name, sp.shape, op.op, op.oq)
+            inv_norm = (1.0 / ((sp + op.sq_eps[0]).sqrt() + op.sq_eps[1])).reshape(-1)
         alpha = op.alpha.float() if op.alpha is not None else torch.ones(n)
         beta = op.beta.float() if op.beta is not None else torch.zeros(n)
         if op.scale_mode == L.BCOSK_SCALE_B2:
-            t = D.abs() * op.inv_norm.float()[:, None] * alpha
+            t = D.abs() * inv_norm.float()[:, None] * alpha
         elif op.scale_mode == L.BCOSK_SCALE_POW:
-            t = (D.abs() * op.inv_norm.float()[:, None] + 1e-6).pow(op.b_exp - 1.0) * alpha
+            t = (D.abs() * inv_norm.float()[:, None] + 1e-6).pow(op.b_exp - 1.0) * alpha
         else:
             t = alpha.expand(M, n).clone()
         v = D * t + beta
         if op.res is not None:
             v = v + _join(op.res.reshape(M, -1), op.res_planes)
-        pos = v > 0
+        # throughput path (single 16-bit plane): ReLU / mask are decided on the ROUNDED value (packed 16-bit compare) and
+        # the sums of squares use the un-rounded fp32 value; the generic path decides on fp32 and squares what it stored
+        fast = (not op.y_f32) and op.y_planes == 1 and (op.gain is None or op.gain.dtype != torch.float32) \
+            and op.res_planes == 1 and op.scale_mode == L.BCOSK_SCALE_B2
+        pos = (v.to(op.y.dtype).float() > 0) if fast else (v > 0)
         if op.relu:
             v = torch.where(pos, v, torch.zeros_like(v))
             t = torch.where(pos, t, torch.zeros_like(t))
@@ -128,6 +140,7 @@ def run_igemm(op: O.IgemmOp) -> None:
         else:
             tmp = torch.zeros(M, op.y.shape[-1], dtype=op.y.dtype)
             stored = _split_store(tmp, v, op.y_planes)
+            # (fast path: sums of squares of the stored, i.e. rounded, values - same as the generic path)
             y2[rows] = tmp
         if op.sq_out is not None:
             bn = op.resolved_block_n()

@@ -179,7 +179,8 @@ def test_a_tile_im2col(bcosk_lib):
         plan = _mini_plan(nb, 1)
         x = _rand_act(g, nb, h, h, cin, 1)
         w = torch.randn(64, cin, k, k, generator=g)
-        plan._conv_fwd("t", x, w, stride, plo, phi, bn=None, relu=False, kch=kch)
+        oh = (h + plo + phi - k) // stride + 1
+        plan._conv_fwd("t", x, w, stride, plo, phi, bn=None, relu=False, kch=kch, inv_norm=torch.ones(nb * oh * oh))
         op = [o for o in plan.fwd_ops if isinstance(o, O.IgemmOp)][0]
         A = E.gather_a(op)                                   # [M, ktot]
         dop = U.to_device(op, "cuda")
@@ -194,6 +195,36 @@ def test_a_tile_im2col(bcosk_lib):
                 rows = min(128, op.M - tile_m * 128)
                 exp[:rows] = A[tile_m * 128: tile_m * 128 + rows, chunk * kch:(chunk + 1) * kch]
                 assert torch.equal(out.float().cpu(), exp), (h, cin, k, stride, kch, tile_m, chunk)
+
+
+def test_persistent_and_per_tile_schedules_agree(bcosk_lib):
+    """same launches through the persistent (TMEM double-buffered) and the one-CTA-per-tile kernels"""
+    g = torch.Generator().manual_seed(21)
+    nb, h, cin, cout = 4, 28, 128, 256
+    outs = []
+    for persistent in (1, 0):
+        prev = bcosk_lib.bcosk_set_persistent(persistent)
+        try:
+            gg = torch.Generator().manual_seed(21)
+            plan = _mini_plan(nb, 1)
+            x = _rand_act(gg, nb, h, h, cin, 1)
+            w = torch.randn(cout, cin, 3, 3, generator=gg) / math.sqrt(cin * 9)
+            plan.sd = {"bn.running_var": torch.rand(cout, generator=gg) + 0.5, "bn.weight": torch.rand(cout, generator=gg) + 0.5}
+            res = _rand_act(gg, nb, h, h, cout, 1)
+            y, rec = plan._conv_fwd("p", x, w, 1, 1, 1, bn="bn", relu=True, res=res, want_mask=True)
+            memo = {}
+            dops = [U.to_device(o, "cuda", memo) for o in plan.fwd_ops]
+            for o in dops:
+                o.run()
+            torch.cuda.synchronize()
+            outs.append([t.cpu() for t in (dops[-1].y, dops[-1].gain, dops[-1].maskbits, dops[-1].sq_out)])
+        finally:
+            bcosk_lib.bcosk_set_persistent(prev)
+    for k, (a, b) in enumerate(zip(*outs)):
+        if k == 3:      # sums of squares: the persistent kernel adds two half-row partials (different rounding order)
+            assert torch.allclose(a, b, rtol=1e-5, atol=0)
+        else:
+            assert torch.equal(a, b)
 
 
 def test_elementwise_kernels(bcosk_lib):
