@@ -48,13 +48,15 @@ def _digest() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile libbcosk.so if sources changed; returns the library path."""
-    dig = _digest()
+    """Compile libbcosk.so if sources changed; returns the library path.
+    $BCOSK_EXTRA_NVCC_FLAGS (e.g. -DBCOSK_TIMING, experiments only) is appended to the nvcc command line."""
+    extra = os.environ.get("BCOSK_EXTRA_NVCC_FLAGS", "").split()
+    dig = _digest() + "|" + " ".join(extra)
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
             if fh.read().strip() == dig:
                 return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-o", LIB]
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-o", LIB]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]

@@ -26,9 +26,11 @@ constexpr int STAGE_K = 64;   // K elements per pipeline stage (128 bytes of 16-
 constexpr int A_STAGE_BYTES = BM * STAGE_K * 2;
 constexpr int NUM_THREADS = 192;
 
-template <int BN, bool HP = false> struct TileCfg {
-  static constexpr int kStages = (BN == 128) ? 3 : 4;   // pipeline slots; the last one may hold the epilogue input tile
-  static constexpr int kMinBlocks = (BN <= 128) ? 2 : 1;
+// LIGHT: 3 small slots and 3 CTAs per SM - for the bandwidth-bound launches with a short K loop, where what matters is
+// how many tiles (i.e. how many bytes) are in flight per SM, not the depth of the MMA pipeline.
+template <int BN, bool HP = false, bool LIGHT = false> struct TileCfg {
+  static constexpr int kStages = LIGHT ? 3 : ((BN == 128) ? 3 : 4);   // pipeline slots; the last may hold the input tile
+  static constexpr int kMinBlocks = LIGHT ? 3 : ((BN <= 128) ? 2 : 1);
   static constexpr int kBStageBytes = BN * STAGE_K * 2;
   static constexpr int kSlotBytes = A_STAGE_BYTES + kBStageBytes;   // A stage followed by its B stage
   static constexpr int kTileBytes = BM * BN * 2;                    // one 16-bit epilogue tile (BN/64 boxes of 16 KB)
@@ -38,6 +40,18 @@ template <int BN, bool HP = false> struct TileCfg {
   // stages + 1 KB alignment slack + barriers/params
   static constexpr int kSmemBytes = kStages * (A_STAGE_BYTES + kBStageBytes) + 1024 + 256 + 2 * BN * 4;
 };
+
+#ifdef BCOSK_TIMING
+// Experiment-only instrumentation (never in the shipped library): per-CTA clock64 stamps of the per-tile kernel.
+__device__ unsigned long long* g_timing_buf = nullptr;
+__device__ int g_timing_cap = 0;
+#define BCOSK_STAMP(slot)                                                                                  \
+  do {                                                                                                     \
+    if (g_timing_buf != nullptr && (int)blockIdx.x < g_timing_cap) g_timing_buf[blockIdx.x * 8 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define BCOSK_STAMP(slot) do { } while (0)
+#endif
 
 struct RowInfo {
   int m, img, p, q;
@@ -114,6 +128,7 @@ __device__ __forceinline__ void store32_f32(float* ptr, int ncols, const float (
 // Library-internal launch state (decided by the host launcher, see launch_igemm)
 struct IgemmAux {
   int tma_in;    // 0 none, 1 = forward residual, 2 = explain mul1: prefetched as a tile into the last pipeline slot
+  int tma_in2;   // explain: the extra gradient `add` (dense, same rows as y) prefetched into the slot before it
   int tma_out1;  // primary output y staged in slot 0 and written with TMA
   int tma_out2;  // forward: gain, explain: out2 - staged in slot 1 and written with TMA
 };
@@ -124,6 +139,7 @@ struct IgemmAux {
 // the compiler never falls back to generic-space accesses.
 struct EpiTiles {
   uint32_t in;
+  uint32_t in2;
   uint32_t out1;
   uint32_t out2;
 };
@@ -328,7 +344,7 @@ __device__ __forceinline__ void global_store_words(void* ptr, int ncols, const u
 
 // Forward, B=2 scale: branch-free over the 16 column pairs so the compiler can interleave them (all launch-uniform
 // options are folded into data: a zero residual word, an all-ones ReLU mask, ...).
-template <typename T, bool MASK>
+template <typename T, bool MASK, bool AFFINE>
 __device__ __forceinline__ void epilogue_fwd_fast(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow,
                                                   float inv_norm, const float* s_alpha, const float* s_beta, int j, int c0,
                                                   int ncols, const float (&v)[32], float& sq_acc, const EpiTiles& tl, int row) {
@@ -347,15 +363,26 @@ __device__ __forceinline__ void epilogue_fwd_fast(const bcosk_igemm_params& p, c
   uint32_t mbits = 0;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float4 al = lds_f4(a4 + q * 16), be = lds_f4(b4 + q * 16);
+    float4 al = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (AFFINE) {
+      al = lds_f4(a4 + q * 16);
+      be = lds_f4(b4 + q * 16);
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int k = q * 2 + h;  // pair index: columns 2k, 2k+1
       const float2 vv = make_float2(v[2 * k], v[2 * k + 1]);
-      const float2 kk = __fmul2_rn(h ? make_float2(al.z, al.w) : make_float2(al.x, al.y), inv2);
-      const float2 t = make_float2(fabsf(vv.x) * kk.x, fabsf(vv.y) * kk.y);       // |lin| / ||patch|| * alpha
-      float2 y = __ffma2_rn(vv, t, h ? make_float2(be.z, be.w) : make_float2(be.x, be.y));
-      y = __fadd2_rn(y, Cvt<T>::unpack2(rw[k]));
+      float2 t, y;
+      if (AFFINE) {
+        const float2 kk = __fmul2_rn(h ? make_float2(al.z, al.w) : make_float2(al.x, al.y), inv2);
+        t = make_float2(fabsf(vv.x) * kk.x, fabsf(vv.y) * kk.y);                   // |lin| / ||patch|| * alpha
+        y = __ffma2_rn(vv, t, h ? make_float2(be.z, be.w) : make_float2(be.x, be.y));
+        y = __fadd2_rn(y, Cvt<T>::unpack2(rw[k]));
+      } else {
+        // the plan folded sqrt(BN multiplier) into the weights: nothing per channel is left
+        t = make_float2(fabsf(vv.x) * inv_norm, fabsf(vv.y) * inv_norm);
+        y = __ffma2_rn(vv, t, Cvt<T>::unpack2(rw[k]));
+      }
       const uint32_t ywk = Cvt<T>::pack2(y.x, y.y);
       const uint32_t m = Pk<T>::gt0_mask(ywk) | relu_off;                          // 0xFFFF per kept half
       yw[k] = ywk & m;
@@ -378,10 +405,11 @@ __device__ __forceinline__ void epilogue_fwd_fast(const bcosk_igemm_params& p, c
 template <typename T>
 __device__ __forceinline__ void epilogue_explain_fast(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow,
                                                       int64_t add_row, int j, int c0, int ncols, float (&v)[32],
-                                                      const EpiTiles& tl, int row) {
+                                                      const EpiTiles& tl, int row, uint32_t mb) {
   uint32_t w[16];
   if (add_row >= 0) {
-    global_load_words(reinterpret_cast<const T*>(p.add) + (size_t)add_row * p.add_ld + c0, ncols, w);
+    if (tl.in2 != 0) tile_load_words(tl.in2, row, j, w);
+    else global_load_words(reinterpret_cast<const T*>(p.add) + (size_t)add_row * p.add_ld + c0, ncols, w);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const float2 a = __fadd2_rn(make_float2(v[2 * k], v[2 * k + 1]), Cvt<T>::unpack2(w[k]));
@@ -398,7 +426,6 @@ __device__ __forceinline__ void epilogue_explain_fast(const bcosk_igemm_params& 
 #pragma unroll
       for (int k = 0; k < 16; ++k) w[k] = one2;
     }
-    const uint32_t mb = (p.mask2 != nullptr) ? __ldg(p.mask2 + (size_t)ri.m * p.mask2_ld + (c0 >> 5)) : 0xffffffffu;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const float2 o = __fmul2_rn(make_float2(v[2 * k], v[2 * k + 1]), Cvt<T>::unpack2(w[k]));
@@ -434,15 +461,28 @@ template <int MODE, typename T>
 __device__ __forceinline__ void epilogue_chunk_fast(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow,
                                                     float inv_norm, int64_t add_row, const float* s_alpha,
                                                     const float* s_beta, int j, int c0, int ncols, float (&v)[32],
-                                                    float& sq_acc, const EpiTiles& tl, int row) {
+                                                    float& sq_acc, const EpiTiles& tl, int row, uint32_t mb) {
   if (MODE == BCOSK_MODE_FWD) {
-    if (p.maskbits != nullptr)
-      epilogue_fwd_fast<T, true>(p, ri, yrow, inv_norm, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
-    else
-      epilogue_fwd_fast<T, false>(p, ri, yrow, inv_norm, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
+    const bool affine = p.alpha != nullptr || p.beta != nullptr;
+    if (p.maskbits != nullptr) {
+      if (affine) epilogue_fwd_fast<T, true, true>(p, ri, yrow, inv_norm, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
+      else epilogue_fwd_fast<T, true, false>(p, ri, yrow, inv_norm, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
+    } else {
+      if (affine) epilogue_fwd_fast<T, false, true>(p, ri, yrow, inv_norm, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
+      else epilogue_fwd_fast<T, false, false>(p, ri, yrow, inv_norm, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
+    }
   } else {
-    epilogue_explain_fast<T>(p, ri, yrow, add_row, j, c0, ncols, v, tl, row);
+    epilogue_explain_fast<T>(p, ri, yrow, add_row, j, c0, ncols, v, tl, row, mb);
   }
+}
+
+// register-resident select of a[j] for a small compile-time sized array (avoids a local-memory array)
+template <int N>
+__device__ __forceinline__ uint32_t pick_word(const uint32_t (&a)[N], int j) {
+  uint32_t r = a[0];
+#pragma unroll
+  for (int i = 1; i < N; ++i) r = (j == i) ? a[i] : r;
+  return r;
 }
 
 // eligibility of the fast form (uniform over the launch)
@@ -459,9 +499,9 @@ template <int MODE, typename T>
 __device__ __forceinline__ void epilogue_chunk(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow, float inv_norm,
                                                int64_t add_row, const float* s_alpha, const float* s_beta, int j, int c0,
                                                int ncols, float (&v)[32], float& sq_acc, const EpiTiles& tl, int row,
-                                               bool fast) {
+                                               bool fast, uint32_t mb) {
   if (fast) {
-    epilogue_chunk_fast<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
+    epilogue_chunk_fast<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row, mb);
   } else {
     // the generic form is an out-of-line call: give it its own copies so that `v` stays in registers on the fast path
     float vv[32];
@@ -476,13 +516,13 @@ __device__ __forceinline__ void epilogue_chunk(const bcosk_igemm_params& p, cons
   }
 }
 
-template <int BN, int MODE, typename T, bool HP>
-__global__ void __launch_bounds__(NUM_THREADS, TileCfg<BN, HP>::kMinBlocks)
+template <int BN, int MODE, typename T, bool HP, bool LIGHT = false>
+__global__ void __launch_bounds__(NUM_THREADS, TileCfg<BN, HP, LIGHT>::kMinBlocks)
 bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out1,
-                   const __grid_constant__ CUtensorMap tmap_out2, const __grid_constant__ bcosk_igemm_params p,
-                   const IgemmAux aux) {
-  using Cfg = TileCfg<BN, HP>;
+                   const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in2,
+                   const __grid_constant__ CUtensorMap tmap_out1, const __grid_constant__ CUtensorMap tmap_out2,
+                   const __grid_constant__ bcosk_igemm_params p, const IgemmAux aux) {
+  using Cfg = TileCfg<BN, HP, LIGHT>;
   constexpr int kSlots = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
@@ -512,7 +552,9 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int total_chunks = p.num_segs * p.num_taps * p.chunks_per_tap;
   const int num_iters = total_chunks / chunks_per_stage;  // host guarantees divisibility
   const bool use_in_tile = Cfg::kTmaEpilogue && aux.tma_in != 0;
-  const int num_stages = use_in_tile ? kSlots - 1 : kSlots;
+  const bool use_in2_tile = use_in_tile && aux.tma_in2 != 0;   // host guarantees >= 2 ring stages remain
+  const int num_stages = kSlots - (use_in_tile ? 1 : 0) - (use_in2_tile ? 1 : 0);
+  if (threadIdx.x == 64) BCOSK_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -537,6 +579,7 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 64) BCOSK_STAMP(1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -544,8 +587,12 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       if (use_in_tile) {
         // residual (forward) / producer gain (explain): whole 128 x BN tile, lands while the main loop runs
         uint8_t* dst = smem + (kSlots - 1) * Cfg::kSlotBytes;
-        mbar_arrive_expect_tx(in_bar, Cfg::kTileBytes);
+        mbar_arrive_expect_tx(in_bar, Cfg::kTileBytes * (use_in2_tile ? 2 : 1));
         for (int b = 0; b < BN / 64; ++b) tma_load_2d(dst + b * 16384, &tmap_in, in_bar, n0 + b * 64, m0);
+        if (use_in2_tile) {
+          uint8_t* dst2 = smem + (kSlots - 2) * Cfg::kSlotBytes;
+          for (int b = 0; b < BN / 64; ++b) tma_load_2d(dst2 + b * 16384, &tmap_in2, in_bar, n0 + b * 64, m0);
+        }
       }
       // first output pixel of this tile -> im2col base coordinates
       const int opq = p.op * p.oq;
@@ -674,8 +721,10 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     float sq_acc = 0.f;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    if (et == 0) BCOSK_STAMP(2);   // setup + patch norm done
     EpiTiles tl;
     tl.in = use_in_tile ? smem_u32(smem + (kSlots - 1) * Cfg::kSlotBytes) : 0u;
+    tl.in2 = use_in2_tile ? smem_u32(smem + (kSlots - 2) * Cfg::kSlotBytes) : 0u;
     tl.out1 = (Cfg::kTmaEpilogue && aux.tma_out1) ? smem_u32(smem) : 0u;
     tl.out2 = (Cfg::kTmaEpilogue && aux.tma_out2) ? smem_u32(smem + Cfg::kSlotBytes) : 0u;
 
@@ -712,9 +761,19 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     } else {
       const bool fast = epilogue_fast_ok<MODE>(p);
+      // explain: the previous block's ReLU mask words of this row (one per 32 columns), fetched before any waiting
+      uint32_t mb_pre[BN / 32];
+#pragma unroll
+      for (int j = 0; j < BN / 32; ++j) {
+        mb_pre[j] = 0xffffffffu;
+        if (MODE == BCOSK_MODE_EXPLAIN && p.mask2 != nullptr && ri.valid && n0 + j * 32 < p.n)
+          mb_pre[j] = __ldg(p.mask2 + (size_t)ri.m * p.mask2_ld + ((n0 + j * 32) >> 5));
+      }
       if (use_in_tile) mbar_wait(in_bar, 0);
+      if (et == 0) BCOSK_STAMP(3);   // input tile landed
       mbar_wait(tmem_full_bar, 0);  // all MMAs done: accumulator complete AND every pipeline slot is drained
       tc_fence_after();
+      if (et == 0) BCOSK_STAMP(4);   // accumulator ready
 #pragma unroll 1
       for (int j = 0; j < BN / 32; ++j) {
         const int c0 = n0 + j * 32;
@@ -727,8 +786,9 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
         epilogue_chunk<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, min(32, p.n - c0), v, sq_acc, tl,
-                                row, fast);
+                                row, fast, pick_word<BN / 32>(mb_pre, j));
       }
+      if (et == 0) BCOSK_STAMP(5);   // epilogue math done
       if (tl.out1 != 0 || tl.out2 != 0) {
         // generic-proxy smem writes -> visible to the async proxy, then one thread issues the bulk tensor stores
         fence_proxy_async_smem();
@@ -741,6 +801,7 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             if (tl.out2 != 0) tma_store_2d_addr(&tmap_out2, tl.out2 + b * 16384, c, m0);
           }
           tma_store_commit_and_wait_read();
+          BCOSK_STAMP(6);   // TMA stores have read their shared-memory tiles
         }
       }
     }
@@ -755,56 +816,65 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+  if (threadIdx.x == 64) BCOSK_STAMP(7);
 }
 
 // =================================================================================================
-// Persistent variant (throughput mode): one CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ...
-//   warp 0  A/B TMA producer (3-4 slot ring, runs ahead across tiles)
+// Persistent variant for the bandwidth-bound launches (64-wide tiles, short K loop): one CTA per SM walks tiles
+// t = blockIdx.x, +gridDim.x, ...  Everything a tile needs is prefetched by dedicated warps while the previous tile is
+// still in its epilogue, so the SM always has loads, math and stores of different tiles in flight:
+//   warp 0  A/B TMA producer (3-slot ring, runs ahead across tiles)
 //   warp 1  TMEM allocator + MMA issuer, two accumulator buffers (tile i -> buffer i&1)
-//   warp 2  epilogue-input producer: residual / producer-gain tile of the NEXT tile, double buffered
-//   warp 3  idle
-//   warps 4..11  epilogue: warp w reads TMEM lane quadrant w%4 and column half (w-4)/4, stages the output tiles in
-//                shared memory; one thread issues the TMA stores, whose shared-memory reads overlap the next tile
-// so a tile's epilogue overlaps the next tile's loads and MMAs inside one CTA.
+//   warp 2  epilogue-input producer: residual / producer-gain tile and the extra-gradient tile, double buffered
+//   warp 3  row-side producer: 1/||patch|| per row (forward) or the ReLU-mask words (explain) + per-channel vectors
+//   warps 4..11  epilogue: warp w reads TMEM lane quadrant w%4, columns 32*((w-4)/4) .., and stages the two output
+//                tiles in shared memory (double buffered); one thread issues the TMA stores of tile i, whose
+//                shared-memory reads overlap the math of tile i+1.  One named barrier per tile.
 // =================================================================================================
 constexpr int P_THREADS = 384;
 constexpr int P_EPI_THREADS = 256;
+constexpr int P_BN = 64;
 
-template <int BN> struct PersistCfg {
-  static constexpr int kSlots = (BN == 128) ? 3 : 4;
-  static constexpr int kBStageBytes = BN * STAGE_K * 2;
-  static constexpr int kSlotBytes = A_STAGE_BYTES + kBStageBytes;
-  static constexpr int kTileBytes = BM * BN * 2;
-  static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kRingBytes = kSlots * kSlotBytes;
-  // ring | in[2] | out1 | out2 | barriers (256 B) | per-channel vectors | sq scratch      (BN=128: 231,680 B of 232,448)
-  static constexpr int kSmemBytes = kRingBytes + 4 * kTileBytes + 256 + 2 * BN * 4 + 2 * BM * 4;
+struct PersistCfg {
+  static constexpr int kSlots = 3;
+  static constexpr int kBStageBytes = P_BN * STAGE_K * 2;
+  static constexpr int kSlotBytes = A_STAGE_BYTES + kBStageBytes;        // 24 KB
+  static constexpr int kTileBytes = BM * P_BN * 2;                       // 16 KB: one 128 x 64 16-bit tile (one TMA box)
+  static constexpr int kTmemCols = 2 * P_BN;
+  static constexpr int kRingBytes = kSlots * kSlotBytes;                 // 72 KB
+  // ring | in[2] | in2[2] | out1[2] | out2[2] | barriers (256 B) | row-side [2][BM] words x2 | alpha/beta [2][2][BN] | sq [2][2][BM]
+  static constexpr int kSideWords = 2 * BM * 2 + 2 * 2 * P_BN + 2 * 2 * BM;
+  static constexpr int kSmemBytes = kRingBytes + 8 * kTileBytes + 256 + kSideWords * 4;
 };
 
-template <int BN, int MODE, typename T>
+template <int MODE, typename T>
 __global__ void __launch_bounds__(P_THREADS, 1)
 bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                              const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out1,
-                              const __grid_constant__ CUtensorMap tmap_out2, const __grid_constant__ bcosk_igemm_params p,
-                              const IgemmAux aux) {
-  using Cfg = PersistCfg<BN>;
+                              const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in2,
+                              const __grid_constant__ CUtensorMap tmap_out1, const __grid_constant__ CUtensorMap tmap_out2,
+                              const __grid_constant__ bcosk_igemm_params p, const IgemmAux aux) {
+  using Cfg = PersistCfg;
+  constexpr int BN = P_BN;
   constexpr int kSlots = Cfg::kSlots;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem = smem_dyn;   // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* in_tile = smem + Cfg::kRingBytes;                 // [2][kTileBytes]
-  uint8_t* out1_tile = in_tile + 2 * Cfg::kTileBytes;
-  uint8_t* out2_tile = out1_tile + Cfg::kTileBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out2_tile + Cfg::kTileBytes);
+  uint8_t* in2_tile = in_tile + 2 * Cfg::kTileBytes;         // [2]
+  uint8_t* out1_tile = in2_tile + 2 * Cfg::kTileBytes;       // [2]
+  uint8_t* out2_tile = out1_tile + 2 * Cfg::kTileBytes;      // [2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out2_tile + 2 * Cfg::kTileBytes);
   uint64_t* empty_bar = full_bar + kSlots;
   uint64_t* acc_full_bar = empty_bar + kSlots;               // [2]
   uint64_t* acc_empty_bar = acc_full_bar + 2;                // [2]
   uint64_t* in_full_bar = acc_empty_bar + 2;                 // [2]
   uint64_t* in_empty_bar = in_full_bar + 2;                  // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(in_empty_bar + 2);
-  float* s_alpha = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
-  float* s_beta = s_alpha + BN;
-  float* s_sq = s_beta + BN;                                 // [2][BM] per-half partial sums of squares
+  uint64_t* side_full_bar = in_empty_bar + 2;                // [2]
+  uint64_t* side_empty_bar = side_full_bar + 2;              // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(side_empty_bar + 2);
+  uint32_t* s_side = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(full_bar) + 256);   // [2][BM][2]: inv_norm | mask words
+  float* s_ab = reinterpret_cast<float*>(s_side + 2 * BM * 2);                                   // [2][alpha BN | beta BN]
+  float* s_sq = s_ab + 2 * 2 * BN;                                                               // [2][2][BM]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -815,6 +885,7 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
   const int chunks_per_stage = STAGE_K / p.kch;
   const int num_iters = (p.num_segs * p.num_taps * p.chunks_per_tap) / chunks_per_stage;
   const bool use_in_tile = aux.tma_in != 0;
+  const bool use_in2_tile = use_in_tile && aux.tma_in2 != 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -828,6 +899,8 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       mbar_init(&acc_empty_bar[s], 8);   // one arrival per epilogue warp
       mbar_init(&in_full_bar[s], 1);
       mbar_init(&in_empty_bar[s], 8);
+      mbar_init(&side_full_bar[s], 1);
+      mbar_init(&side_empty_bar[s], 8);
     }
     fence_barrier_init();
   }
@@ -918,43 +991,118 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
         const uint32_t buf = i & 1u;
         const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
         mbar_wait(&in_empty_bar[buf], ((i >> 1) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&in_full_bar[buf], Cfg::kTileBytes);
-        for (int b = 0; b < BN / 64; ++b)
-          tma_load_2d(in_tile + buf * Cfg::kTileBytes + b * 16384, &tmap_in, &in_full_bar[buf], n0 + b * 64, m0);
+        mbar_arrive_expect_tx(&in_full_bar[buf], Cfg::kTileBytes * (use_in2_tile ? 2 : 1));
+        tma_load_2d(in_tile + buf * Cfg::kTileBytes, &tmap_in, &in_full_bar[buf], n0, m0);
+        if (use_in2_tile) tma_load_2d(in2_tile + buf * Cfg::kTileBytes, &tmap_in2, &in_full_bar[buf], n0, m0);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp == 3) {
+    // ===================== row-side producer =====================
+    uint32_t i = 0;
+    const int opq = p.op * p.oq;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      const uint32_t buf = i & 1u;
+      const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+      mbar_wait(&side_empty_bar[buf], ((i >> 1) & 1u) ^ 1u);
+      uint32_t* side = s_side + buf * (BM * 2);
+      if (MODE == BCOSK_MODE_FWD) {
+        // 1/||patch|| for rows lane, lane+32, lane+64, lane+96: the (tap, part) loops are outermost and the four rows
+        // innermost, so every step issues four independent loads (one dependent-load round trip per step, not per row)
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        int img_r[4], pp_r[4], qq_r[4];
+        bool ok_r[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int m = m0 + lane + 32 * r;
+          ok_r[r] = m < M;
+          const int mm = ok_r[r] ? m : 0;
+          img_r[r] = mm / opq;
+          const int rem = mm - img_r[r] * opq;
+          pp_r[r] = rem / p.oq;
+          qq_r[r] = rem - pp_r[r] * p.oq;
+        }
+        if (p.scale_mode == BCOSK_SCALE_NONE) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[r] = 1.f;
+        } else if (p.inv_norm != nullptr) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[r] = ok_r[r] ? __ldg(p.inv_norm + m0 + lane + 32 * r) : 1.f;
+        } else {
+          const size_t part_stride = (size_t)p.a_nb * p.sq_h * p.sq_w;
+          for (int dy = 0; dy < p.sq_k; ++dy) {
+            for (int dx = 0; dx < p.sq_k; ++dx) {
+              size_t off[4];
+              bool in_r[4];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const int yy = pp_r[r] * p.sq_stride - p.sq_pad + dy;
+                const int xx = qq_r[r] * p.sq_stride - p.sq_pad + dx;
+                in_r[r] = ok_r[r] && yy >= 0 && yy < p.sq_h && xx >= 0 && xx < p.sq_w;
+                off[r] = in_r[r] ? ((size_t)img_r[r] * p.sq_h + yy) * p.sq_w + xx : 0;
+              }
+              for (int tt = 0; tt < p.sq_parts; ++tt) {
+                float x[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) x[r] = in_r[r] ? __ldg(p.sq_in + tt * part_stride + off[r]) : 0.f;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r] += x[r];
+              }
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[r] = 1.0f / (sqrtf(acc[r] + p.sq_eps_in) + p.sq_eps_out);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          side[(lane + 32 * r) * 2] = __float_as_uint(acc[r]);
+          side[(lane + 32 * r) * 2 + 1] = 0xffffffffu;
+        }
+      } else {
+        // ReLU mask words of the previous block for this row's 64 columns
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int m = m0 + lane + 32 * r;
+          uint32_t w0 = 0xffffffffu, w1 = 0xffffffffu;
+          if (m < M && p.mask2 != nullptr) {
+            w0 = __ldg(p.mask2 + (size_t)m * p.mask2_ld + (n0 >> 5));
+            w1 = (n0 + 32 < p.n) ? __ldg(p.mask2 + (size_t)m * p.mask2_ld + (n0 >> 5) + 1) : 0u;
+          }
+          side[(lane + 32 * r) * 2] = w0;
+          side[(lane + 32 * r) * 2 + 1] = w1;
+        }
+      }
+      if (MODE == BCOSK_MODE_FWD) {
+        float* ab = s_ab + buf * (2 * BN);
+        for (int c = lane; c < BN; c += 32) {
+          const int cc = n0 + c;
+          ab[c] = (p.alpha != nullptr && cc < p.n) ? __ldg(p.alpha + cc) : 1.f;
+          ab[BN + c] = (p.beta != nullptr && cc < p.n) ? __ldg(p.beta + cc) : 0.f;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&side_full_bar[buf]);
+    }
+  } else {
     // ===================== epilogue (warps 4..11) =====================
     const int quad = warp & 3;
-    const int half = (warp - 4) >> 2;                  // column half of the tile handled by this warp
-    constexpr int kChunksPerHalf = BN / 64;            // 32-column chunks per half: 2 (BN=128) or 1 (BN=64)
+    const int half = (warp - 4) >> 2;                  // 32-column half of the tile handled by this warp
     const int row = quad * 32 + lane;
     const int et = threadIdx.x - 128;                  // 0..255
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const bool any_out_tile = aux.tma_out1 || aux.tma_out2;
     const bool fast = epilogue_fast_ok<MODE>(p);
+    const bool want_sq = MODE == BCOSK_MODE_FWD && p.sq_out != nullptr;
+    const int opq = p.op * p.oq;
     uint32_t i = 0;
-    int staged_n0 = -1;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
       const uint32_t buf = i & 1u;
+      const uint32_t par = (i >> 1) & 1u;
       const int tile_n = t % n_tiles;
       const int m0 = (t / n_tiles) * BM, n0 = tile_n * BN;
-      if (MODE == BCOSK_MODE_FWD && n0 != staged_n0) {
-        // (re)stage the per-channel vectors of this column tile
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int c = et; c < BN; c += P_EPI_THREADS) {
-          const int cc = n0 + c;
-          s_alpha[c] = (p.alpha != nullptr && cc < p.n) ? __ldg(p.alpha + cc) : 1.f;
-          s_beta[c] = (p.beta != nullptr && cc < p.n) ? __ldg(p.beta + cc) : 0.f;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        staged_n0 = n0;
-      }
       RowInfo ri;
       ri.m = m0 + row;
       ri.valid = ri.m < M;
       {
-        const int opq = p.op * p.oq;
         const int mm = ri.valid ? ri.m : 0;
         ri.img = mm / opq;
         const int rem = mm - ri.img * opq;
@@ -962,88 +1110,64 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
         ri.q = rem - ri.p * p.oq;
       }
       const int64_t yrow = p.os_0 + (int64_t)ri.img * p.os_n + (int64_t)ri.p * p.os_p + (int64_t)ri.q * p.os_q;
-      float inv_norm = 1.f;
       int64_t add_row = -1;
-      if (MODE == BCOSK_MODE_FWD) {
-        if (p.scale_mode != BCOSK_SCALE_NONE && ri.valid) {
-          if (p.inv_norm != nullptr) {
-            inv_norm = __ldg(p.inv_norm + ri.m);
-          } else {
-            const size_t part_stride = (size_t)p.a_nb * p.sq_h * p.sq_w;
-            float acc = 0.f;
-            for (int dy = 0; dy < p.sq_k; ++dy) {
-              const int yy = ri.p * p.sq_stride - p.sq_pad + dy;
-              if (yy < 0 || yy >= p.sq_h) continue;
-              for (int dx = 0; dx < p.sq_k; ++dx) {
-                const int xx = ri.q * p.sq_stride - p.sq_pad + dx;
-                if (xx < 0 || xx >= p.sq_w) continue;
-                const size_t o = ((size_t)ri.img * p.sq_h + yy) * p.sq_w + xx;
-                for (int tt = 0; tt < p.sq_parts; ++tt) acc += __ldg(p.sq_in + tt * part_stride + o);
-              }
-            }
-            inv_norm = 1.0f / (sqrtf(acc + p.sq_eps_in) + p.sq_eps_out);
-          }
-        }
-      } else {
-        if (p.add != nullptr && ri.valid) {
-          const int s = p.add_stride;
-          if (ri.p % s == 0 && ri.q % s == 0 && ri.p / s < p.add_p && ri.q / s < p.add_q)
-            add_row = ((int64_t)ri.img * p.add_p + ri.p / s) * p.add_q + ri.q / s;
-        }
+      if (MODE == BCOSK_MODE_EXPLAIN && p.add != nullptr && ri.valid) {
+        const int s = p.add_stride;
+        if (ri.p % s == 0 && ri.q % s == 0 && ri.p / s < p.add_p && ri.q / s < p.add_q)
+          add_row = ((int64_t)ri.img * p.add_p + ri.p / s) * p.add_q + ri.q / s;
       }
       EpiTiles tl;
       tl.in = use_in_tile ? smem_u32(in_tile + buf * Cfg::kTileBytes) : 0u;
-      tl.out1 = aux.tma_out1 ? smem_u32(out1_tile) : 0u;
-      tl.out2 = aux.tma_out2 ? smem_u32(out2_tile) : 0u;
+      tl.in2 = use_in2_tile ? smem_u32(in2_tile + buf * Cfg::kTileBytes) : 0u;
+      tl.out1 = aux.tma_out1 ? smem_u32(out1_tile + buf * Cfg::kTileBytes) : 0u;
+      tl.out2 = aux.tma_out2 ? smem_u32(out2_tile + buf * Cfg::kTileBytes) : 0u;
 
-      mbar_wait(&acc_full_bar[buf], (i >> 1) & 1u);
+      mbar_wait(&side_full_bar[buf], par);
+      const uint32_t side0 = s_side[buf * (BM * 2) + row * 2];
+      const uint32_t side1 = s_side[buf * (BM * 2) + row * 2 + 1];
+      const float inv_norm = (MODE == BCOSK_MODE_FWD) ? __uint_as_float(side0) : 1.f;
+      const uint32_t mb = (MODE == BCOSK_MODE_EXPLAIN) ? (half ? side1 : side0) : 0xffffffffu;
+      if (use_in_tile) mbar_wait(&in_full_bar[buf], par);
+      mbar_wait(&acc_full_bar[buf], par);
       tc_fence_after();
-      if (use_in_tile) mbar_wait(&in_full_bar[buf], (i >> 1) & 1u);
-      if (any_out_tile && i > 0) {
-        // the previous tile's TMA stores must have finished reading the staging tiles before they are overwritten
-        if (et == 0) tma_store_wait_read();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
+
       float sq_acc = 0.f;
+      const int j = half;                       // chunk index inside the 64-wide tile
+      const int c0 = n0 + j * 32;
+      if (c0 < p.n) {                           // warp-uniform
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(buf * BN + j * 32), raw);
+        tmem_ld_wait();
+        if (ri.valid) {
+          float v[32];
 #pragma unroll
-      for (int jj = 0; jj < kChunksPerHalf; ++jj) {
-        const int j = half * kChunksPerHalf + jj;
-        const int c0 = n0 + j * 32;
-        if (c0 < p.n) {   // warp-uniform
-          uint32_t raw[32];
-          tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(buf * BN + j * 32), raw);
-          tmem_ld_wait();
-          if (ri.valid) {
-            float v[32];
-#pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
-            epilogue_chunk<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, min(32, p.n - c0), v, sq_acc, tl,
-                                    row, fast);
-          }
+          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+          epilogue_chunk<MODE, T>(p, ri, yrow, inv_norm, add_row, s_ab + buf * (2 * BN), s_ab + buf * (2 * BN) + BN, j, c0,
+                                  min(32, p.n - c0), v, sq_acc, tl, row, fast, mb);
         }
       }
-      // accumulator and input tile are consumed: hand them back
+      // accumulator, input tiles and row-side values are consumed: hand the buffers back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&acc_empty_bar[buf]);
         if (use_in_tile) mbar_arrive(&in_empty_bar[buf]);
+        mbar_arrive(&side_empty_bar[buf]);
       }
-      const bool want_sq = MODE == BCOSK_MODE_FWD && p.sq_out != nullptr;
-      if (want_sq) s_sq[half * BM + row] = sq_acc;
-      if (any_out_tile) fence_proxy_async_smem();
-      if (any_out_tile || want_sq) asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (any_out_tile && et == 0) {
-        for (int b = 0; b < BN / 64; ++b) {
-          const int c = n0 + b * 64;
-          if (c >= p.n) break;
-          if (tl.out1 != 0) tma_store_2d_addr(&tmap_out1, tl.out1 + b * 16384, c, m0);
-          if (tl.out2 != 0) tma_store_2d_addr(&tmap_out2, tl.out2 + b * 16384, c, m0);
-        }
+      if (want_sq) s_sq[(buf * 2 + half) * BM + row] = sq_acc;
+      if (any_out_tile) {
+        fence_proxy_async_smem();
+        // the stores of tile i-1 (other staging buffer) must have read their tiles before tile i+1 overwrites them
+        if (et == 0) tma_store_wait_read();
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (any_out_tile && et == 0 && n0 < p.n) {
+        if (tl.out1 != 0) tma_store_2d_addr(&tmap_out1, tl.out1, n0, m0);
+        if (tl.out2 != 0) tma_store_2d_addr(&tmap_out2, tl.out2, n0, m0);
         tma_store_commit();
       }
-      if (want_sq && half == 0 && ri.valid) p.sq_out[(size_t)tile_n * M + ri.m] = s_sq[row] + s_sq[BM + row];
-      if (want_sq) asm volatile("bar.sync 1, 256;" ::: "memory");   // s_sq is rewritten by the next tile
+      if (want_sq && half == 0 && ri.valid)
+        p.sq_out[(size_t)tile_n * M + ri.m] = s_sq[(buf * 2) * BM + row] + s_sq[(buf * 2 + 1) * BM + row];
     }
     if (any_out_tile && et == 0) tma_store_wait_read();
     tc_fence_before();
@@ -1098,14 +1222,14 @@ __global__ void bcosk_debug_a_tile_kernel(const __grid_constant__ CUtensorMap tm
 // host side
 // ---------------------------------------------------------------------------------------------
 struct LaunchMaps {
-  CUtensorMap a, b, in, out1, out2;
+  CUtensorMap a, b, in, in2, out1, out2;
 };
 
-template <int BN, int MODE, bool HP>
+template <int BN, int MODE, bool HP, bool LIGHT = false>
 static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const IgemmAux& aux, cudaStream_t st) {
-  using Cfg = TileCfg<BN, HP>;
-  auto kern = bcosk_igemm_kernel<BN, MODE, __nv_bfloat16, HP>;
-  auto kern_h = bcosk_igemm_kernel<BN, MODE, __half, HP>;
+  using Cfg = TileCfg<BN, HP, LIGHT>;
+  auto kern = bcosk_igemm_kernel<BN, MODE, __nv_bfloat16, HP, LIGHT>;
+  auto kern_h = bcosk_igemm_kernel<BN, MODE, __half, HP, LIGHT>;
   const void* fn = (p.dtype == BCOSK_DTYPE_BF16) ? (const void*)kern : (const void*)kern_h;
   static bool attr_done[2] = {false, false};
   if (!attr_done[p.dtype]) {
@@ -1118,21 +1242,24 @@ static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const
   if (m_tiles * n_tiles > 0x7fffffffLL) return set_error(BCOSK_EUNSUPPORTED, "igemm: grid too large");
   dim3 grid((unsigned)(m_tiles * n_tiles));
   if (p.dtype == BCOSK_DTYPE_BF16)
-    kern<<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.out1, mp.out2, p, aux);
+    kern<<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux);
   else
-    kern_h<<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.out1, mp.out2, p, aux);
+    kern_h<<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux);
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }
 
 static int g_num_sms = 0;
-static bool g_persistent_enabled = true;
+// Measured on B200 (profiles/r01_schedule_ab.md): per-tile + 3 CTAs/SM and the persistent kernel reach the same
+// ~4 TB/s on the bandwidth-bound launches; the per-tile schedule is the default.
+static bool g_persistent_enabled = false;
+static bool g_light_enabled = true;
 
-template <int BN, int MODE>
+template <int MODE>
 static int launch_persistent(const LaunchMaps& mp, const bcosk_igemm_params& p, const IgemmAux& aux, cudaStream_t st) {
-  using Cfg = PersistCfg<BN>;
-  auto kern = bcosk_igemm_persistent_kernel<BN, MODE, __nv_bfloat16>;
-  auto kern_h = bcosk_igemm_persistent_kernel<BN, MODE, __half>;
+  using Cfg = PersistCfg;
+  auto kern = bcosk_igemm_persistent_kernel<MODE, __nv_bfloat16>;
+  auto kern_h = bcosk_igemm_persistent_kernel<MODE, __half>;
   const void* fn = (p.dtype == BCOSK_DTYPE_BF16) ? (const void*)kern : (const void*)kern_h;
   static bool attr_done[2] = {false, false};
   if (!attr_done[p.dtype]) {
@@ -1145,13 +1272,13 @@ static int launch_persistent(const LaunchMaps& mp, const bcosk_igemm_params& p, 
     BCOSK_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const long long M = (long long)p.a_nb * p.op * p.oq;
-  const long long tiles = ((M + BM - 1) / BM) * ((p.n + BN - 1) / BN);
+  const long long tiles = ((M + BM - 1) / BM) * ((p.n + P_BN - 1) / P_BN);
   if (tiles > 0x7fffffffLL) return set_error(BCOSK_EUNSUPPORTED, "igemm: too many tiles");
   dim3 grid((unsigned)(tiles < g_num_sms ? tiles : g_num_sms));
   if (p.dtype == BCOSK_DTYPE_BF16)
-    kern<<<grid, P_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.out1, mp.out2, p, aux);
+    kern<<<grid, P_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux);
   else
-    kern_h<<<grid, P_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.out1, mp.out2, p, aux);
+    kern_h<<<grid, P_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux);
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }
@@ -1201,6 +1328,10 @@ static int make_maps(const bcosk_igemm_params& p, int bn, LaunchMaps* mp, IgemmA
     } else {
       if (p.out2 && p.out2_planes == 1) aux->tma_out2 = map16(&mp->out2, p.out2, p.out2_ld) ? 1 : 0;
       if (p.mul1 && !p.mul1_f32) aux->tma_in = map16(&mp->in, p.mul1, p.mul1_ld) ? 2 : 0;
+      // second input tile: the extra gradient, when it is dense over the same rows (identity shortcuts) and the tile
+      // shape leaves two ring stages (64-wide tiles have 4 slots)
+      if (aux->tma_in && bn == 64 && p.add && p.add_planes == 1 && p.add_stride == 1 && p.add_p == p.op && p.add_q == p.oq)
+        aux->tma_in2 = map16(&mp->in2, p.add, p.add_ld) ? 1 : 0;
     }
   }
   return BCOSK_OK;
@@ -1225,16 +1356,14 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
   rc = make_maps(p, bn, &mp, &aux);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p.hp_accum) aux.tma_in2 = 0;
 #define BCOSK_DISPATCH(BN_)                                                                         \
   case BN_:                                                                                         \
     return p.mode == BCOSK_MODE_FWD ? launch_igemm<BN_, BCOSK_MODE_FWD, false>(mp, p, aux, st)      \
                                     : launch_igemm<BN_, BCOSK_MODE_EXPLAIN, false>(mp, p, aux, st);
-  if (!p.hp_accum && g_persistent_enabled && (bn == 64 || bn == 128)) {
-    if (bn == 64)
-      return p.mode == BCOSK_MODE_FWD ? launch_persistent<64, BCOSK_MODE_FWD>(mp, p, aux, st)
-                                      : launch_persistent<64, BCOSK_MODE_EXPLAIN>(mp, p, aux, st);
-    return p.mode == BCOSK_MODE_FWD ? launch_persistent<128, BCOSK_MODE_FWD>(mp, p, aux, st)
-                                    : launch_persistent<128, BCOSK_MODE_EXPLAIN>(mp, p, aux, st);
+  if (!p.hp_accum && g_persistent_enabled && bn == 64) {
+    return p.mode == BCOSK_MODE_FWD ? launch_persistent<BCOSK_MODE_FWD>(mp, p, aux, st)
+                                    : launch_persistent<BCOSK_MODE_EXPLAIN>(mp, p, aux, st);
   }
   if (p.hp_accum) {
     if (bn == 32)
@@ -1242,6 +1371,13 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
                                       : launch_igemm<32, BCOSK_MODE_EXPLAIN, true>(mp, p, aux, st);
     return p.mode == BCOSK_MODE_FWD ? launch_igemm<64, BCOSK_MODE_FWD, true>(mp, p, aux, st)
                                     : launch_igemm<64, BCOSK_MODE_EXPLAIN, true>(mp, p, aux, st);
+  }
+  if (bn == 64 && g_light_enabled && !aux.tma_in2) {
+    // short K loop (<= 4 stages): the 3-CTA/SM variant
+    const int iters = p.num_segs * p.num_taps * p.chunks_per_tap / (STAGE_K / p.kch);
+    if (iters <= 4)
+      return p.mode == BCOSK_MODE_FWD ? launch_igemm<64, BCOSK_MODE_FWD, false, true>(mp, p, aux, st)
+                                      : launch_igemm<64, BCOSK_MODE_EXPLAIN, false, true>(mp, p, aux, st);
   }
   switch (bn) {
     BCOSK_DISPATCH(32)
@@ -1256,6 +1392,21 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
 extern "C" int bcosk_set_persistent(int32_t enabled) {
   const int prev = g_persistent_enabled ? 1 : 0;
   g_persistent_enabled = enabled != 0;
+  return prev;
+}
+
+#ifdef BCOSK_TIMING
+extern "C" int bcosk_debug_set_timing(void* buf, int32_t capacity_ctas) {
+  unsigned long long* b = reinterpret_cast<unsigned long long*>(buf);
+  BCOSK_CUDA_CHECK(cudaMemcpyToSymbol(g_timing_buf, &b, sizeof(b)));
+  BCOSK_CUDA_CHECK(cudaMemcpyToSymbol(g_timing_cap, &capacity_ctas, sizeof(int)));
+  return BCOSK_OK;
+}
+#endif
+
+extern "C" int bcosk_set_light(int32_t enabled) {
+  const int prev = g_light_enabled ? 1 : 0;
+  g_light_enabled = enabled != 0;
   return prev;
 }
 

@@ -108,8 +108,17 @@ class PlanBase:
         beta = self.sd.get(prefix + ".bias")
         return self._dev(alpha), (None if beta is None else self._dev(beta))
 
-    def _block_n(self, n: int) -> int:
-        return 32 if n <= 32 else (64 if (n <= 64 or self.hp_accum) else 128)
+    # launches whose K loop has at most this many 64-deep stages are bandwidth bound: they use 64-wide tiles, which
+    # the library runs with 3 CTAs per SM (more bytes in flight); 0 disables
+    light_k_iters = 4
+    fold_bn = True   # fold sqrt(BN multiplier) into the conv weights when every multiplier is positive and there is no bias
+
+    def _block_n(self, n: int, k_iters: int = 1 << 30) -> int:
+        if n <= 32:
+            return 32
+        if n <= 64 or self.hp_accum or k_iters <= self.light_k_iters:
+            return 64
+        return 128
 
     # ------------------------------------------------------------------ forward emission
     def _conv_fwd(self, name: str, x: Act, w: Tensor, stride: int, pad_lo: int, pad_hi: int, *, bn: Optional[str],
@@ -133,9 +142,23 @@ class PlanBase:
             if sq_geom is None:
                 assert pad_lo == pad_hi and kh == kw, "asymmetric convs must pass inv_norm or sq_geom"
                 sq_geom = (h, wd, kh, stride, pad_lo)
-        bmat, cpt = P.pack_b(P.fwd_weight_taps(w), self.planes, kch, self.dt)
+            if sq_geom[2] > 3:
+                # large windows (7x7 stem: 49 taps per output pixel) are cheaper as a stand-alone sum-pool launch than as
+                # 49 dependent loads in front of every tile's epilogue (measured: 9 us of a 12 us CTA lifetime)
+                inv_norm = self._empty(M, dtype=torch.float32)
+                self.fwd_ops.append(O.PatchNormOp(name + ".norm", x.sq, x.parts, nb, sq_geom[0], sq_geom[1], sq_geom[2],
+                                                  sq_geom[3], sq_geom[4], 1e-6, 0.0, inv_norm, oh, ow))
+                sq_in = None
         alpha, beta = self._bn_alpha(bn) if bn else (None, None)
-        block_n = self._block_n(o)
+        if (alpha is not None and beta is None and self.fold_bn and self.scale_mode == L.BCOSK_SCALE_B2
+                and bool((alpha > 0).all())):
+            # y = a * lin * |lin| / n == lin' * |lin'| / n with lin' = sqrt(a) * lin: fold sqrt(a) into the weights.  The
+            # explanation pass uses the same folded weights (d y / d x = (|lin'| / n) * W'), so nothing per channel is
+            # left for the epilogues.
+            w = w * alpha.sqrt().to(w.device).view(-1, 1, 1, 1)
+            alpha = None
+        bmat, cpt = P.pack_b(P.fwd_weight_taps(w), self.planes, kch, self.dt)
+        block_n = self._block_n(o, bmat.shape[1] // 64)
         parts = (o + block_n - 1) // block_n
         yp = 1 if y_f32 else self.planes
         y = self._empty(nb, oh, ow, yp * o, dtype=torch.float32 if y_f32 else self.dt)
@@ -193,7 +216,9 @@ class PlanBase:
             name=rec.name + ".dgrad", a=g, b=self._dev(bmat, self.dt), n=n, lo=(lo, lo), up=(up_w, up_h), stride=(1, 1),
             op=oh, oq=ow, kch=kch, chunks_per_tap=cpt, taps=P.conv_taps(k, k),
             seg_a_choff=P.seg_a_offsets(self.planes, rec.cout), dtype=self.dt_code, mode=L.BCOSK_MODE_EXPLAIN,
-            block_n=self._block_n(n), hp_accum=self.hp_accum, y=y, y_planes=1 if y_f32 else self.planes, y_f32=y_f32,
+            block_n=64 if (add is not None and add_stride == 1 and self.planes == 1 and n >= 64)
+            else self._block_n(n, bmat.shape[1] // 64),   # dense extra gradient: 64-wide tiles stage it with TMA
+            hp_accum=self.hp_accum, y=y, y_planes=1 if y_f32 else self.planes, y_f32=y_f32,
             out_map=y_map, add=add, add_planes=self.planes, add_stride=add_stride, mul1=mul1, out2=out2,
             out2_planes=self.planes, mul2=mul2, mask2=mask2, algo_flops=rec.algo_flops,
             a_dense_frac=1.0 / (rec.stride * rec.stride) if rec.ghat_map is not None else 1.0))

@@ -123,9 +123,11 @@ typedef struct bcosk_igemm_params {
 
 int bcosk_igemm(const bcosk_igemm_params* p, void* stream);
 
-/* Scheduling switch for A/B measurements: 1 (default) = persistent one-CTA-per-SM kernel with TMEM double buffering for
- * the throughput mode, 0 = one CTA per tile.  Returns the previous setting.  Results are identical. */
+/* Scheduling switch for A/B measurements: 1 = launches with block_n 64 (the bandwidth-bound ones) run on the persistent
+ * one-CTA-per-SM kernel, 0 (default) = one CTA per tile everywhere.  Returns the previous setting.  Results are identical. */
 int bcosk_set_persistent(int32_t enabled);
+/* 1 (default) = launches with block_n 64 and a K loop of <= 4 stages use the 3-CTA-per-SM variant.  Returns the previous setting. */
+int bcosk_set_light(int32_t enabled);
 
 /* Debug aid: raw bytes of the first A chunk (tile_m, chunk) as TMA im2col lands it in shared memory
  * (128 rows x kch 16-bit values, de-swizzled) -> out[128*kch]. */
