@@ -198,3 +198,25 @@ def channel_affine(x, rows, c, alpha, beta, relu, y, dtype) -> None:
 
 def mul(a, b, n, out, dtype) -> None:
     check(load().bcosk_mul(_p(a), _p(b), C.c_int64(n), _p(out), dtype, _stream()), "bcosk_mul")
+
+
+def nchw_to_nhwc16(x, out, cp, planes, dtype, mul=None, sq=None) -> None:
+    nb, c, h, w = x.shape
+    assert x.dtype.is_floating_point and x.element_size() == 4 and x.is_contiguous()
+    check(load().bcosk_nchw_to_nhwc16(_p(x), nb, c, h, w, _p(out), cp, planes, dtype, _p(mul),
+                                      0 if mul is None else mul.shape[-1], _p(sq), _stream()), "bcosk_nchw_to_nhwc16")
+
+
+def nhwc_to_nchw_f32(y, nb, c, h, w, planes, dtype, out) -> None:
+    import torch
+    check(load().bcosk_nhwc_to_nchw_f32(_p(y), int(y.dtype == torch.float32), nb, c, h, w, y.shape[-1], planes, dtype, _p(out),
+                                        _stream()), "bcosk_nhwc_to_nchw_f32")
+
+
+def scale_bias_nchw(x, nb, c, hw, alpha, beta, smul, sadd, relu, out) -> None:
+    check(load().bcosk_scale_bias_nchw(_p(x), nb, c, C.c_int64(hw), _p(alpha), _p(beta), C.c_float(smul), C.c_float(sadd),
+                                       int(relu), _p(out), _stream()), "bcosk_scale_bias_nchw")
+
+
+def channel_stats_nchw(x, nb, c, hw, mean, var) -> None:
+    check(load().bcosk_channel_stats_nchw(_p(x), nb, c, C.c_int64(hw), _p(mean), _p(var), _stream()), "bcosk_channel_stats_nchw")

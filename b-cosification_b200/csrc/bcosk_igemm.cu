@@ -197,6 +197,11 @@ __device__ __noinline__ void epilogue_chunk_generic(const bcosk_igemm_params& p,
   T* y16 = reinterpret_cast<T*>(p.y);
   float* y32 = reinterpret_cast<float*>(p.y);
   if (MODE == BCOSK_MODE_FWD) {
+    if (p.lin_bias != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < ncols) v[i] += __ldg(p.lin_bias + c0 + i);
+    }
     float t[32];
     if (p.scale_mode == BCOSK_SCALE_B2) {
 #pragma unroll
@@ -490,7 +495,7 @@ template <int MODE>
 __device__ __forceinline__ bool epilogue_fast_ok(const bcosk_igemm_params& p) {
   if (MODE == BCOSK_MODE_FWD)
     return !p.y_f32 && p.y_planes == 1 && (p.gain == nullptr || !p.gain_f32) && (p.res == nullptr || p.res_planes == 1) &&
-           p.scale_mode == BCOSK_SCALE_B2;
+           p.scale_mode == BCOSK_SCALE_B2 && p.lin_bias == nullptr;
   return (p.y_f32 || p.y_planes == 1) && (p.add == nullptr || p.add_planes == 1) && (p.mul1 == nullptr || !p.mul1_f32) &&
          (p.out2 == nullptr || p.out2_planes == 1) && (p.mul2 == nullptr || !p.mul2_f32);
 }

@@ -1,0 +1,188 @@
+// bcosk_layout.cu -- layout / dtype bridges and per-channel helpers for the module-level (un-fused) path.
+//
+// The reference's modules exchange NCHW fp32 tensors; the kernels work on NHWC 16-bit (precision planes).  These
+// bandwidth kernels are the bridge, plus eval/train-mode uncentered batch norm and the logit layer on NCHW fp32.
+// Thread = pixel, looping over 8-channel groups: reads of one channel plane are coalesced across the warp.
+#include "../../include/bcosk.h"
+#include "bcosk_common.cuh"
+#include "bcosk_host.h"
+
+namespace bcosk {
+
+static inline unsigned nblocks(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+template <typename T>
+__global__ void nchw_to_nhwc16_kernel(const float* __restrict__ x, int nb, int c, long long hw, T* __restrict__ out, int cp,
+                                      int planes, const float* __restrict__ mul, int mul_ld, float* __restrict__ sq) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over nb*hw
+  if (pix >= (long long)nb * hw) return;
+  const long long img = pix / hw, sp = pix - img * hw;
+  const float* src = x + img * c * hw + sp;
+  T* dst = out + pix * ((long long)planes * cp);
+  float sqacc = 0.f;
+  for (int g = 0; g < cp / 8; ++g) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = g * 8 + i;
+      float v = (ch < c) ? __ldg(src + (long long)ch * hw) : 0.f;
+      if (mul != nullptr && ch < c) v *= __ldg(mul + pix * mul_ld + ch);
+      f[i] = v;
+    }
+    float r[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r[i] = f[i]; acc[i] = 0.f; }
+    for (int pl = 0; pl < planes; ++pl) {
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        w[k] = Cvt<T>::pack2(r[2 * k], r[2 * k + 1]);
+        const float2 q = Cvt<T>::unpack2(w[k]);
+        r[2 * k] -= q.x; r[2 * k + 1] -= q.y;
+        acc[2 * k] += q.x; acc[2 * k + 1] += q.y;
+      }
+      *reinterpret_cast<uint4*>(dst + (long long)pl * cp + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sqacc = fmaf(acc[i], acc[i], sqacc);
+  }
+  if (sq != nullptr) sq[pix] = sqacc;
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_f32_kernel(const void* __restrict__ y, int y_f32, int nb, int c, long long hw, int ld,
+                                        int planes, float* __restrict__ out) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)nb * hw) return;
+  const long long img = pix / hw, sp = pix - img * hw;
+  float* dst = out + img * c * hw + sp;
+  const int cpl = ld / (y_f32 ? 1 : planes);   // channels per plane (physical)
+  for (int ch0 = 0; ch0 < c; ch0 += 8) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = 0.f;
+    if (y_f32) {
+      const float* src = reinterpret_cast<const float*>(y) + pix * ld + ch0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (ch0 + i < c) f[i] = __ldg(src + i);
+    } else {
+      const T* src = reinterpret_cast<const T*>(y) + pix * ld + ch0;
+      for (int pl = 0; pl < planes; ++pl) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (long long)pl * cpl));
+        float2 q;
+        q = Cvt<T>::unpack2(u.x); f[0] += q.x; f[1] += q.y;
+        q = Cvt<T>::unpack2(u.y); f[2] += q.x; f[3] += q.y;
+        q = Cvt<T>::unpack2(u.z); f[4] += q.x; f[5] += q.y;
+        q = Cvt<T>::unpack2(u.w); f[6] += q.x; f[7] += q.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (ch0 + i < c) dst[(long long)(ch0 + i) * hw] = f[i];
+  }
+}
+
+// y = relu?((x * alpha[c] + beta[c]) * smul + sadd) on NCHW fp32 (alpha/beta optional)
+__global__ void scale_bias_nchw_kernel(const float* __restrict__ x, long long total, int c, long long hw,
+                                       const float* __restrict__ alpha, const float* __restrict__ beta, float smul,
+                                       float sadd, int relu, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = (int)((i / hw) % c);
+  float v = __ldg(x + i);
+  if (alpha != nullptr) v *= __ldg(alpha + ch);
+  if (beta != nullptr) v += __ldg(beta + ch);
+  v = fmaf(v, smul, sadd);
+  out[i] = (relu && v < 0.f) ? 0.f : v;
+}
+
+// per-channel mean and biased variance over (N, H, W) of an NCHW fp32 tensor: one block per channel
+__global__ void channel_stats_nchw_kernel(const float* __restrict__ x, int nb, int c, long long hw, float* __restrict__ mean,
+                                          float* __restrict__ var) {
+  const int ch = blockIdx.x;
+  double s = 0.0, s2 = 0.0;
+  for (int n = 0; n < nb; ++n) {
+    const float* src = x + ((long long)n * c + ch) * hw;
+    for (long long i = threadIdx.x; i < hw; i += blockDim.x) {
+      const double v = (double)__ldg(src + i);
+      s += v;
+      s2 += v * v;
+    }
+  }
+  __shared__ double sh[2][32];
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[0][warp] = s; sh[1][warp] = s2; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    s = lane < nw ? sh[0][lane] : 0.0;
+    s2 = lane < nw ? sh[1][lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+      const double cnt = (double)nb * (double)hw;
+      const double m = s / cnt;
+      mean[ch] = (float)m;
+      var[ch] = (float)fmax(s2 / cnt - m * m, 0.0);
+    }
+  }
+}
+
+}  // namespace bcosk
+
+using namespace bcosk;
+
+static inline cudaStream_t S2(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" int bcosk_nchw_to_nhwc16(const float* x, int32_t nb, int32_t c, int32_t h, int32_t w, void* out, int32_t cp,
+                                    int32_t planes, int32_t dtype, const float* mul, int32_t mul_ld, float* sq,
+                                    void* stream) {
+  if (!x || !out || cp % 8 || cp < c || planes < 1) return set_error(BCOSK_EINVAL, "nchw_to_nhwc16: bad argument");
+  const long long hw = (long long)h * w, n = (long long)nb * hw;
+  if (dtype == BCOSK_DTYPE_BF16)
+    nchw_to_nhwc16_kernel<__nv_bfloat16><<<nblocks(n, 128), 128, 0, S2(stream)>>>(
+        x, nb, c, hw, reinterpret_cast<__nv_bfloat16*>(out), cp, planes, mul, mul_ld, sq);
+  else if (dtype == BCOSK_DTYPE_F16)
+    nchw_to_nhwc16_kernel<__half><<<nblocks(n, 128), 128, 0, S2(stream)>>>(x, nb, c, hw, reinterpret_cast<__half*>(out), cp,
+                                                                           planes, mul, mul_ld, sq);
+  else
+    return set_error(BCOSK_EINVAL, "nchw_to_nhwc16: dtype");
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_nhwc_to_nchw_f32(const void* y, int32_t y_f32, int32_t nb, int32_t c, int32_t h, int32_t w, int32_t ld,
+                                      int32_t planes, int32_t dtype, float* out, void* stream) {
+  if (!y || !out || (!y_f32 && (ld / planes) % 8)) return set_error(BCOSK_EINVAL, "nhwc_to_nchw_f32: bad argument");
+  const long long hw = (long long)h * w, n = (long long)nb * hw;
+  if (dtype == BCOSK_DTYPE_F16)
+    nhwc_to_nchw_f32_kernel<__half><<<nblocks(n, 128), 128, 0, S2(stream)>>>(y, y_f32, nb, c, hw, ld, planes, out);
+  else
+    nhwc_to_nchw_f32_kernel<__nv_bfloat16><<<nblocks(n, 128), 128, 0, S2(stream)>>>(y, y_f32, nb, c, hw, ld, planes, out);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_scale_bias_nchw(const float* x, int32_t nb, int32_t c, int64_t hw, const float* alpha, const float* beta,
+                                     float smul, float sadd, int32_t relu, float* out, void* stream) {
+  if (!x || !out || c < 1) return set_error(BCOSK_EINVAL, "scale_bias_nchw: bad argument");
+  const long long total = (long long)nb * c * hw;
+  scale_bias_nchw_kernel<<<nblocks(total, 256), 256, 0, S2(stream)>>>(x, total, c, hw, alpha, beta, smul, sadd, relu, out);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_channel_stats_nchw(const float* x, int32_t nb, int32_t c, int64_t hw, float* mean, float* var,
+                                        void* stream) {
+  if (!x || !mean || !var) return set_error(BCOSK_EINVAL, "channel_stats_nchw: bad argument");
+  channel_stats_nchw_kernel<<<c, 256, 0, S2(stream)>>>(x, nb, c, hw, mean, var);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}

@@ -124,7 +124,8 @@ class PlanBase:
     def _conv_fwd(self, name: str, x: Act, w: Tensor, stride: int, pad_lo: int, pad_hi: int, *, bn: Optional[str],
                   relu: bool, res: Optional[Act] = None, want_mask: bool = False, y_f32: bool = False,
                   inv_norm: Optional[Tensor] = None, kch: int = 64, want_sq: bool = True,
-                  sq_geom: Optional[Tuple[int, int, int, int, int]] = None) -> Tuple[Act, ConvRec]:
+                  sq_geom: Optional[Tuple[int, int, int, int, int]] = None, lin_bias: Optional[Tensor] = None,
+                  sq_eps: Tuple[float, float] = (1e-6, 0.0)) -> Tuple[Act, ConvRec]:
         """One fused launch: B-cos conv (+BN multiplier, +residual, +ReLU).  The patch norm comes from `x.sq`
         (per-pixel sums of squares written by x's producer) and is evaluated inside the kernel; `sq_geom`
         overrides its (h, w, k, stride, pad) when the GEMM geometry is not the convolution's (space-to-depth stem)."""
@@ -147,7 +148,7 @@ class PlanBase:
                 # 49 dependent loads in front of every tile's epilogue (measured: 9 us of a 12 us CTA lifetime)
                 inv_norm = self._empty(M, dtype=torch.float32)
                 self.fwd_ops.append(O.PatchNormOp(name + ".norm", x.sq, x.parts, nb, sq_geom[0], sq_geom[1], sq_geom[2],
-                                                  sq_geom[3], sq_geom[4], 1e-6, 0.0, inv_norm, oh, ow))
+                                                  sq_geom[3], sq_geom[4], sq_eps[0], sq_eps[1], inv_norm, oh, ow))
                 sq_in = None
         alpha, beta = self._bn_alpha(bn) if bn else (None, None)
         if (alpha is not None and beta is None and self.fold_bn and self.scale_mode == L.BCOSK_SCALE_B2
@@ -173,7 +174,8 @@ class PlanBase:
             up=(pad_hi - (kw - 1), pad_hi - (kh - 1)), stride=(stride, stride), op=oh, oq=ow, kch=kch, chunks_per_tap=cpt,
             taps=P.conv_taps(kh, kw), seg_a_choff=P.seg_a_offsets(self.planes, cin_phys), dtype=self.dt_code,
             mode=L.BCOSK_MODE_FWD, block_n=block_n, scale_mode=self.scale_mode, b_exp=self.b, relu=relu,
-            inv_norm=inv_norm, sq_in=sq_in, sq_geom=sq_geom, alpha=alpha, beta=beta,
+            inv_norm=inv_norm, sq_in=sq_in, sq_geom=sq_geom, sq_eps=sq_eps, alpha=alpha, beta=beta,
+            lin_bias=None if lin_bias is None else self._dev(lin_bias),
             res=None if res is None else res.t, res_planes=self.planes,
             gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32, hp_accum=self.hp_accum,
             algo_flops=2.0 * M * o * float((w != 0).sum().item()) / o))

@@ -45,6 +45,7 @@ class IgemmOp:
     sq_eps: Tuple[float, float] = (1e-6, 0.0)                   # (inside sqrt, outside sqrt)
     alpha: Optional[Tensor] = None
     beta: Optional[Tensor] = None
+    lin_bias: Optional[Tensor] = None      # [n] fp32 bias of the linear map (added before the scale)
     res: Optional[Tensor] = None
     res_planes: int = 1
     gain: Optional[Tensor] = None
@@ -132,6 +133,7 @@ class IgemmOp:
             p.sq_eps_in, p.sq_eps_out = self.sq_eps
         p.set_ptr("alpha", self.alpha)
         p.set_ptr("beta", self.beta)
+        p.set_ptr("lin_bias", self.lin_bias)
         if self.res is not None:
             p.res = self.res.data_ptr()
             p.res_ld = self.res.shape[-1]

@@ -1,0 +1,121 @@
+"""`BcosUtilMixin` / `explanation_mode` -- mirror of reference bcos/common.py:23-436 (plotting excluded).
+
+`explain` runs the forward under explanation mode, back-propagates the chosen logit with
+`Tensor.backward(inputs=[x])` (our modules' autograd nodes launch the explain-dgrad kernels) and returns the dynamic
+linear weights and the contribution map `(x * x.grad).sum(1)`.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Any, Dict
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+__all__ = ["BcosUtilMixin", "explanation_mode", "gradient_to_image"]
+
+
+class explanation_mode:
+    """Context manager / decorator putting every module with `set_explanation_mode` into explanation mode
+    (bcos/common.py:347-384; the module list is cached on first entry like the reference does)."""
+
+    def __init__(self, model: nn.Module):
+        self.model = model
+        self.expl_modules = None
+
+    def find_expl_modules(self) -> None:
+        self.expl_modules = [m for m in self.model.modules() if hasattr(m, "set_explanation_mode")]
+
+    def __enter__(self):
+        if self.expl_modules is None:
+            self.find_expl_modules()
+        for m in self.expl_modules:
+            m.set_explanation_mode(True)
+
+    def __exit__(self, exc_type, exc_val, exc_tb):
+        for m in self.expl_modules:
+            m.set_explanation_mode(False)
+
+    def __call__(self, fn):
+        def wrapped(*a, **k):
+            with self:
+                return fn(*a, **k)
+        return wrapped
+
+
+def gradient_to_image(image: Tensor, linear_mapping: Tensor, smooth: int = 15, alpha_percentile: float = 99.5) -> Tensor:
+    """RGBA explanation [H, W, 4] from a 6-channel image and its dynamic linear weights (bcos/common.py:387-436),
+    in torch on the tensor's device (the reference converts to numpy for plotting)."""
+    contribs = (image * linear_mapping).sum(0, keepdim=True)[0]
+    rgb_grad = linear_mapping / (linear_mapping.abs().max(0, keepdim=True).values + 1e-12)
+    rgb_grad = rgb_grad.clamp(min=0)
+    rgb_grad = rgb_grad[:3] / (rgb_grad[:3] + rgb_grad[3:] + 1e-12)
+    alpha = linear_mapping.norm(p=2, dim=0, keepdim=True)
+    alpha = torch.where(contribs[None] < 0, torch.zeros_like(alpha) + 1e-12, alpha)
+    if smooth:
+        alpha = F.avg_pool2d(alpha, smooth, stride=1, padding=(smooth - 1) // 2)
+    alpha = alpha / torch.quantile(alpha.flatten(), q=alpha_percentile / 100)
+    alpha = alpha.clamp(0, 1)
+    return torch.cat([rgb_grad, alpha], dim=0).permute(1, 2, 0)
+
+
+class BcosUtilMixin:
+    """Explanation helpers for models made of B-cos modules (bcos/common.py:23-344)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.__explanation_mode_ctx = explanation_mode(self)  # noqa
+
+    def explanation_mode(self):
+        return self.__explanation_mode_ctx
+
+    def explain(self, in_tensor: Tensor, idx=None, **grad2img_kwargs) -> Dict[str, Any]:
+        """bcos/common.py:92-188 (batch size 1, like the reference)."""
+        if in_tensor.ndim == 3:
+            raise ValueError("Expected 4-dimensional input tensor")
+        if in_tensor.shape[0] != 1:
+            raise ValueError("Expected batch size of 1")
+        if not in_tensor.requires_grad:
+            warnings.warn("Input tensor did not require grad! Has been set automatically to True!")
+            in_tensor.requires_grad = True
+        if self.training:  # noqa
+            warnings.warn("Model is in training mode! This might lead to unexpected results! Use model.eval()!")
+        result = dict()
+        with torch.enable_grad(), self.explanation_mode():
+            out = self(in_tensor)  # noqa
+            pred_out = out.max(1)
+            result["prediction"] = pred_out.indices.item()
+            if idx is None:
+                to_be_explained_logit = pred_out.values
+                result["explained_class_idx"] = pred_out.indices.item()
+            else:
+                to_be_explained_logit = out[0, idx]
+                result["explained_class_idx"] = idx
+            to_be_explained_logit.backward(inputs=[in_tensor])
+        result["dynamic_linear_weights"] = in_tensor.grad
+        result["contribution_map"] = (in_tensor * in_tensor.grad).sum(1)
+        result["explanation"] = gradient_to_image(in_tensor[0].detach(), in_tensor.grad[0], **grad2img_kwargs)
+        return result
+
+    def explain_batch(self, in_tensor: Tensor) -> Dict[str, Tensor]:
+        """Batched form used by the reference's ExplanationsLogger / Captum path."""
+        xb = in_tensor.detach().clone().requires_grad_(True)
+        with torch.enable_grad(), self.explanation_mode():
+            out = self(xb)  # noqa
+            out.max(1).values.sum().backward(inputs=[xb])
+        return {"logits": out.detach(), "prediction": out.argmax(1), "dynamic_linear_weights": xb.grad,
+                "contribution_map": (xb.detach() * xb.grad).sum(1)}
+
+    def attribute(self, image: Tensor, target: int, **kwargs) -> Tensor:
+        """Input x gradient of one target under explanation mode == Captum InputXGradient (bcos/common.py:280-317,
+        interpretability/explanation_methods/explainers/captum.py:29-32)."""
+        x = image.detach().clone().requires_grad_(True)
+        with torch.enable_grad(), self.explanation_mode():
+            out = self(x)  # noqa
+            out[:, target].sum().backward(inputs=[x])
+        return (x.detach() * x.grad)
+
+    def attribute_selection(self, image: Tensor, targets, **kwargs) -> Tensor:
+        """bcos/common.py:319-344."""
+        return torch.cat([self.attribute(image, t) for t in targets], dim=0)

@@ -1,0 +1,212 @@
+"""B-cos 2-D convolutions -- drop-in mirror of reference bcos/modules/bcosconv2d.py and bcosifyconv2d.py.
+
+Same constructors, attributes (`.linear`, `.weight`, `.b`, `.max_out`, `.detach`, ...) and state-dict keys
+(`*.linear.weight`); the arithmetic runs on libbcosk.so (tcgen05 implicit GEMM with the B-cos epilogue).
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Tuple, Union
+
+import torch
+import torch.linalg as LA
+import torch.nn as nn
+from torch import Tensor
+from torch.nn.modules.utils import _pair
+
+from . import _runtime as R
+from .common import DetachableModule
+
+__all__ = ["NormedConv2d", "BcosConv2d", "BcosConv2dWithScale", "BcosifyConv2d"]
+
+
+class NormedConv2d(nn.Conv2d):
+    """nn.Conv2d whose weights are used with unit L2 norm per output unit (bcosconv2d.py:17-41).  Only a parameter
+    container here: the normalisation is folded into the packed weights by the owning BcosConv2d."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.scale = None
+        self.use_weight_norm = True
+
+    def effective_weight(self) -> Tensor:
+        w = self.weight
+        if self.use_weight_norm:
+            w = w / LA.vector_norm(w, dim=(1, 2, 3), keepdim=True)
+            if self.scale is not None:
+                w = self.scale * w
+        return w
+
+    def forward(self, in_tensor: Tensor) -> Tensor:  # plain linear map (B = 1)
+        raise RuntimeError("NormedConv2d is evaluated through its BcosConv2d")
+
+    def set_scale(self, weight: Tensor, trainable=False):
+        self.scale = nn.Parameter(weight.norm(p=2, dim=(1, 2, 3), keepdim=True), requires_grad=trainable)
+
+    def toggle_weight_norm(self, use_weight_norm):
+        self.use_weight_norm = use_weight_norm
+
+
+def _single(v) -> int:
+    a, b = _pair(v)
+    if a != b:
+        raise NotImplementedError("bcos_b200: only square kernels / strides / paddings are built")
+    return int(a)
+
+
+class BcosConv2d(DetachableModule):
+    """`out = (w_hat . x) * |cos(x, w_hat)|^(B-1)` (bcosconv2d.py:43-262)."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: Union[int, Tuple[int, ...]] = 1,
+                 stride: Union[int, Tuple[int, ...]] = 1, padding: Union[int, Tuple[int, ...]] = 0,
+                 dilation: Union[int, Tuple[int, ...]] = 1, groups: int = 1, padding_mode: str = "zeros", device=None,
+                 dtype=None, bias: bool = False, b: Union[int, float] = 2, max_out: int = 1, **kwargs):
+        assert max_out > 0, f"max_out should be greater than 0, was {max_out}"
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size
+        self.stride = stride
+        self.padding = padding
+        self.dilation = _pair(dilation)
+        self.groups = groups
+        self.padding_mode = padding_mode
+        self.device = device
+        self.dtype = dtype
+        self.bias = None
+        self.b = b
+        self.max_out = max_out
+        if any(d > 1 for d in self.dilation):
+            warnings.warn("dilation > 1 is not built in bcos_b200")
+        self.linear = self._make_linear()
+        self._cache = R._PlanCache()
+
+    def _make_linear(self) -> nn.Module:
+        return NormedConv2d(in_channels=self.in_channels, out_channels=self.out_channels * self.max_out,
+                            kernel_size=self.kernel_size, stride=self.stride, padding=self.padding, dilation=self.dilation,
+                            groups=self.groups, bias=False, padding_mode=self.padding_mode, device=self.device,
+                            dtype=self.dtype)
+
+    # deep copies (EMA, ExplanationsLogger) must not share launch plans
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            setattr(new, k, R._PlanCache() if k == "_cache" else copy.deepcopy(v, memo))
+        return new
+
+    def _effective_weight(self) -> Tensor:
+        return self.linear.effective_weight()
+
+    def forward(self, in_tensor: Tensor) -> Tensor:
+        return self.forward_impl(in_tensor)
+
+    def forward_impl(self, in_tensor: Tensor) -> Tensor:
+        if self.max_out > 1 or self.groups != 1 or any(d > 1 for d in self.dilation) or self.padding_mode != "zeros":
+            raise NotImplementedError("bcos_b200: max_out > 1, groups > 1, dilation > 1 and non-zero padding modes are not "
+                                      "built (no registered B-cosification config uses them)")
+        b = float(self.b.detach()) if isinstance(self.b, torch.Tensor) else float(self.b)
+        lin = self.linear
+        return R.bcos_map(in_tensor, self._cache, lin.weight, getattr(lin, "bias", None), self._effective_weight,
+                          _single(self.stride), _single(self.padding), b, self.detach)
+
+    def calc_patch_norms(self, in_tensor: Tensor) -> Tensor:
+        """||patch|| per output position, [N,1,Ho,Wo] (bcosconv2d.py:196-231) through bcosk_patch_inv_norm."""
+        R._require_cuda(in_tensor, "calc_patch_norms")
+        from .. import _lib as L
+        x = in_tensor.float().contiguous()
+        nb, c, h, w = x.shape
+        k, s, p = _single(self.kernel_size), _single(self.stride), _single(self.padding)
+        cp = (c + 7) // 8 * 8
+        buf = torch.empty(nb, h, w, cp, dtype=torch.bfloat16, device=x.device)
+        sq = torch.empty(nb * h * w, dtype=torch.float32, device=x.device)
+        L.nchw_to_nhwc16(x, buf, cp, 1, 1, None, sq)
+        # exact fp32 sums of squares (the bridge squares what it stored): recompute from x for the public helper
+        sq = (x * x).sum(1).reshape(-1).contiguous()
+        oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+        inv = torch.empty(nb * oh * ow, dtype=torch.float32, device=x.device)
+        L.patch_inv_norm(sq, 1, nb, h, w, k, k, s, p, 1e-6, 0.0, inv, oh, ow)
+        return (1.0 / inv).view(nb, 1, oh, ow)
+
+    def extra_repr(self) -> str:
+        s = "B={b}"
+        if self.max_out > 1:
+            s += ", max_out={max_out}"
+        s += ","
+        extra = dict(b=self.b.data.item()) if isinstance(self.b, nn.Parameter) else {}
+        return s.format(**{**self.__dict__, **extra})
+
+
+class BcosConv2dWithScale(BcosConv2d):
+    """Deprecated reference class (bcosconv2d.py:265-326): output divided by a constant scale."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=1, stride=1, padding=0, dilation=1, groups=1,
+                 padding_mode="zeros", device=None, dtype=None, b=2, max_out=1, scale=None, scale_factor=100.0, **kwargs):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, padding_mode,
+                         device=device, dtype=dtype, b=b, max_out=max_out, **kwargs)
+        if scale is None:
+            ks = kernel_size if not isinstance(kernel_size, tuple) else (kernel_size[0] * kernel_size[1]) ** 0.5
+            self.scale = (ks * (in_channels / groups) ** 0.5) / scale_factor
+        else:
+            assert scale != 1.0, "For scale=1.0, use the normal BcosConv2d instead!"
+            self.scale = scale
+
+    def forward(self, in_tensor: Tensor) -> Tensor:
+        return self.forward_impl(in_tensor) / self.scale
+
+
+class BcosifyConv2d(BcosConv2d):
+    """B-cosified convolution: plain (un-normalised) nn.Conv2d weights, optional bias (bcosifyconv2d.py:7-187)."""
+
+    def __init__(self, *args, clamping: bool = False, b_loss: bool = False, **kwargs):
+        self._want_bias = bool(kwargs.get("bias", False))
+        super().__init__(*args, **kwargs)
+        self.clamping = clamping
+        self.b_loss = b_loss
+
+    def _make_linear(self) -> nn.Module:
+        return nn.Conv2d(in_channels=self.in_channels, out_channels=self.out_channels * self.max_out,
+                         kernel_size=self.kernel_size, stride=self.stride, padding=self.padding, dilation=self.dilation,
+                         groups=self.groups, bias=self._want_bias, padding_mode=self.padding_mode, device=self.device,
+                         dtype=self.dtype)
+
+    @property
+    def weight(self) -> Tensor:  # CLIP reads conv1.weight.dtype (bcosifyconv2d.py:35-37)
+        return self.linear.weight
+
+    def _effective_weight(self) -> Tensor:
+        return self.linear.weight
+
+    def forward_impl(self, in_tensor: Tensor) -> Tensor:
+        if self.clamping or self.b_loss:
+            raise NotImplementedError("bcos_b200: learnable-B variants (clamping / b_loss) are not built (dead in all configs)")
+        return super().forward_impl(in_tensor)
+
+    @classmethod
+    def from_standard_module(cls, mod, model_config):
+        """bcosifyconv2d.py:116-148."""
+        new_mod = cls(in_channels=mod.in_channels, out_channels=mod.out_channels, kernel_size=mod.kernel_size,
+                      stride=mod.stride, padding=mod.padding, dilation=mod.dilation, groups=mod.groups,
+                      bias=mod.bias is not None, padding_mode=mod.padding_mode,
+                      clamping=model_config["bcosify_args"].get("clamping", False),
+                      b_loss=model_config["bcosify_args"].get("learn_b", False), b=model_config["bcos_args"].get("b", 1))
+        if model_config.get("weights", None) is not None:
+            new_mod.linear.weight.data = mod.weight.data
+            if mod.bias is not None:
+                new_mod.linear.bias = nn.Parameter(mod.bias.data)
+        return new_mod
+
+    @classmethod
+    def from_standard_module_linear(cls, mod, model_config):
+        """nn.Linear -> 1x1 B-cos conv for the classifier applied before GAP (bcosifyconv2d.py:151-182)."""
+        new_mod = cls(in_channels=mod.in_features, out_channels=mod.out_features, kernel_size=1, stride=1, padding=0,
+                      dilation=1, groups=1, bias=mod.bias is not None, padding_mode="zeros",
+                      clamping=model_config["bcosify_args"].get("clamping", False),
+                      b_loss=model_config["bcosify_args"].get("learn_b", False), b=model_config["bcos_args"].get("b", 1))
+        if model_config.get("weights", None) is not None:
+            new_mod.linear.weight.data = mod.weight.data.view_as(new_mod.linear.weight.data)
+            if mod.bias is not None:
+                new_mod.linear.bias = nn.Parameter(mod.bias.data)
+        return new_mod

@@ -91,6 +91,8 @@ typedef struct bcosk_igemm_params {
   float sq_eps_in, sq_eps_out;
   const float* alpha;    /* [n] per-channel multiplier (BN weight/sqrt(var+eps)), NULL = 1 */
   const float* beta;     /* [n] per-channel bias, NULL = 0 */
+  const float* lin_bias; /* [n] bias of the linear map itself (added BEFORE the scale: nn.Conv2d/nn.Linear bias of the
+                          * Bcosify modules, bcosifyconv2d.py:68), NULL = none */
   const void* res;       /* [M, res_ld] residual (16-bit planes), NULL = none */
   int32_t res_ld, res_planes, res_plane_stride;
   void* gain;            /* [M, gain_ld] d y / d lin under the detached scale; NULL = not saved */
@@ -197,6 +199,23 @@ int bcosk_channel_affine(const void* x, int64_t rows, int32_t c, const float* al
                          void* y, int32_t dtype, void* stream);
 /* out = a * b element-wise (16-bit), used for g_out * detached scale */
 int bcosk_mul(const void* a, const void* b, int64_t n, void* out, int32_t dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Module-level (un-fused) path: the reference's modules exchange NCHW fp32 tensors
+ * ------------------------------------------------------------------------------------------- */
+/* x [nb,c,h,w] fp32 (optionally * mul[pixel, c], e.g. g_out * detached gain) -> NHWC 16-bit planes
+ * out [nb,h,w,planes*cp] (channels c..cp-1 zero) + optional per-pixel sum of squares (calc_patch_norms' first step) */
+int bcosk_nchw_to_nhwc16(const float* x, int32_t nb, int32_t c, int32_t h, int32_t w, void* out, int32_t cp,
+                         int32_t planes, int32_t dtype, const float* mul, int32_t mul_ld, float* sq, void* stream);
+/* NHWC (fp32, or 16-bit planes summed) -> NCHW fp32 */
+int bcosk_nhwc_to_nchw_f32(const void* y, int32_t y_f32, int32_t nb, int32_t c, int32_t h, int32_t w, int32_t ld,
+                           int32_t planes, int32_t dtype, float* out, void* stream);
+/* out = relu?((x * alpha[c] + beta[c]) * smul + sadd) on NCHW fp32: batch_norm_uncentered_2d (eval / after statistics)
+ * batchnorm_uncentered.py:45-58 and LogitLayer.forward logitlayer.py:22-27 (alpha = beta = NULL) */
+int bcosk_scale_bias_nchw(const float* x, int32_t nb, int32_t c, int64_t hw, const float* alpha, const float* beta, float smul,
+                          float sadd, int32_t relu, float* out, void* stream);
+/* per-channel mean and biased variance over (N,H,W): x.var(dim=(0,2,3), unbiased=False) batchnorm_uncentered.py:39 */
+int bcosk_channel_stats_nchw(const float* x, int32_t nb, int32_t c, int64_t hw, float* mean, float* var, void* stream);
 
 const char* bcosk_last_error(void);
 int bcosk_version(void);

@@ -102,6 +102,8 @@ def run_igemm(op: O.IgemmOp) -> None:
     D = A @ op.b.float().t()                      # [M, n]
     rows = _out_rows(op)
     if op.mode == L.BCOSK_MODE_FWD:
+        if op.lin_bias is not None:
+            D = D + op.lin_bias.float()
         inv_norm = op.inv_norm
         if inv_norm is None and op.sq_in is not None:      # in-kernel patch norm from the producer's sums of squares
             sh, sw, k, st, pd = op.sq_geom
@@ -124,7 +126,7 @@ def run_igemm(op: O.IgemmOp) -> None:
         # throughput path (single 16-bit plane): ReLU / mask are decided on the ROUNDED value (packed 16-bit compare) and
         # the sums of squares use the un-rounded fp32 value; the generic path decides on fp32 and squares what it stored
         fast = (not op.y_f32) and op.y_planes == 1 and (op.gain is None or op.gain.dtype != torch.float32) \
-            and op.res_planes == 1 and op.scale_mode == L.BCOSK_SCALE_B2
+            and op.res_planes == 1 and op.scale_mode == L.BCOSK_SCALE_B2 and op.lin_bias is None
         pos = (v.to(op.y.dtype).float() > 0) if fast else (v > 0)
         if op.relu:
             v = torch.where(pos, v, torch.zeros_like(v))

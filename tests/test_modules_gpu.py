@@ -1,0 +1,119 @@
+"""-m gpu: the drop-in modules (bcos_b200.modules, executed through the C ABI) against the known-answer vectors that the
+reference's own classes produced (tests/golden/modules_kat.npz) and, for the whole network assembled from modules,
+against the reference golden of ResNet-18."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import bcos_oracle as OR
+import bcos_b200.modules as M
+from bcos_b200.bcosify import bcosified_resnet
+from bcos_b200.utils import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a)).cuda()
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    return np.load(os.path.join(golden_dir, "modules_kat.npz"))
+
+
+CONV = ["conv_bcosify_3x3", "conv_bcosify_3x3_s2", "conv_bcosify_1x1", "conv_bcosify_1x1_s2", "conv_bcosify_7x7_s2",
+        "conv_bcos_3x3_normed", "conv_bcos_b1p5", "conv_bcos_b1"]
+
+
+@pytest.mark.parametrize("name", CONV)
+def test_conv_modules_match_reference(bcosk_lib, kat, name):
+    cin, cout, k, s, p, b, mo, normed = kat[name + ".meta"].tolist()
+    cls = M.BcosConv2d if normed else M.BcosifyConv2d
+    mod = cls(int(cin), int(cout), kernel_size=int(k), stride=int(s), padding=int(p), b=b, max_out=int(mo)).cuda()
+    mod.linear.weight.data = _t(kat[name + ".w"])
+    x = _t(kat[name + ".x"])
+    with torch.inference_mode():
+        y = mod(x)
+    e = _rel(y, _t(kat[name + ".y"]))
+    assert e < (2e-5 if b == 2 or b == 1 else 2e-4), (name, e)       # general B uses __powf
+    mod.set_explanation_mode(True)
+    xg = x.clone().requires_grad_(True)
+    ye = mod(xg)
+    (gx,) = torch.autograd.grad((ye * _t(kat[name + ".seed"])).sum(), [xg])
+    eg = _rel(gx, _t(kat[name + ".gx"]))
+    assert eg < (2e-5 if b == 2 or b == 1 else 2e-4), (name, eg)
+    if b != 1:
+        assert _rel(mod.calc_patch_norms(x), _t(kat[name + ".norm"])[:, :1]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["lin_bcosify", "lin_bcos_normed"])
+def test_linear_modules_match_reference(bcosk_lib, kat, name):
+    fin, fout, b, mo, normed = kat[name + ".meta"].tolist()
+    cls = M.BcosLinear if normed else M.BcosifyLinear
+    mod = cls(int(fin), int(fout), b=b, max_out=int(mo)).cuda()
+    mod.linear.weight.data = _t(kat[name + ".w"])
+    x = _t(kat[name + ".x"])
+    assert _rel(mod(x), _t(kat[name + ".y"])) < 2e-5
+    mod.set_explanation_mode(True)
+    xg = x.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad((mod(xg) * _t(kat[name + ".seed"])).sum(), [xg])
+    assert _rel(gx, _t(kat[name + ".gx"])) < 2e-5
+
+
+def test_bias_before_scale(bcosk_lib):
+    g = torch.Generator().manual_seed(4)
+    mod = M.BcosifyConv2d(16, 24, kernel_size=3, padding=1, bias=True, b=2).cuda()
+    x = torch.randn(2, 16, 9, 9, generator=g)
+    ref = OR.bcos_conv2d(x, mod.linear.weight.detach().cpu(), mod.linear.bias.detach().cpu(), 1, 1)
+    assert _rel(mod(x.cuda()), ref.cuda()) < 2e-5
+
+
+def test_norm_and_logit_modules(bcosk_lib, kat):
+    bn = M.BatchNormUncentered2d(12).cuda()
+    bn.weight.data, bn.bias.data, bn.running_var.data = _t(kat["bnu.w"]), _t(kat["bnu.b"]), _t(kat["bnu.rv0"]).clone()
+    x = _t(kat["bnu.x"])
+    bn.eval()
+    assert _rel(bn(x), _t(kat["bnu.y_eval"])) < 1e-6
+    bn.train()
+    assert _rel(bn(x), _t(kat["bnu.y_train"])) < 1e-5
+    assert _rel(bn.running_var, _t(kat["bnu.rv1"])) < 1e-5
+    # explanation-mode gradient = gy * weight / sqrt(var + eps)
+    bn.eval(); bn.set_explanation_mode(True)
+    xg = x.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad(bn(xg).sum(), [xg])
+    alpha = bn.weight / (bn.running_var + bn.eps).sqrt()
+    assert _rel(gx, alpha.view(1, -1, 1, 1).expand_as(x)) < 1e-6
+    ll = M.LogitLayer(logit_temperature=2.0, logit_bias=-1.5)
+    assert _rel(ll(_t(kat["logit.x"])), _t(kat["logit.y"])) < 1e-6
+
+
+def test_module_level_resnet18_matches_golden(bcosk_lib, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "resnet18_b8.npz"))
+    m = bcosified_resnet("resnet18")
+    sd = synth.synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, int(gold["seed"]))
+    off = 0
+    for k, n in zip(gold["bn_keys"].tolist(), gold["bn_sizes"].tolist()):
+        sd[k] = torch.from_numpy(gold["bn_var"][off:off + n].copy()); off += n
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    nb = 2
+    x6 = synth.to_bcos_input(gold["images_u8"][:nb]).cuda()
+    with torch.inference_mode():
+        logits = m(x6)
+    out = m.explain_batch(x6)
+    assert torch.allclose(out["logits"], logits, rtol=1e-6, atol=1e-7)
+    mm = OR.parity_metrics(out["logits"], out["contribution_map"], torch.from_numpy(gold["logits"][:nb]),
+                           torch.from_numpy(gold["contribution_map"][:nb]))
+    print("module-level resnet18 vs reference golden:", mm)
+    assert mm["argmax_equal"] and mm["logit_rel_err"] <= 2e-3 and mm["map_cos_min"] >= 0.999 and mm["map_maxabs_over_range"] <= 1e-3
+    # the official single-image API
+    e = m.explain(x6[:1].clone().requires_grad_(True))
+    assert e["prediction"] == int(gold["logits"][0].argmax())
+    assert tuple(e["explanation"].shape) == (224, 224, 4)
