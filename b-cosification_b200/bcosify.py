@@ -150,3 +150,15 @@ def bcosified_resnet(arch: str = "resnet50") -> BcosifyNetwork:
         if hasattr(mod, "bias") and mod.bias is not None:
             mod.bias = None
     return m
+
+
+def bcosified_densenet(arch: str = "densenet121") -> BcosifyNetwork:
+    """Offline equivalent of the reference's densenet_121 config (experiment_parameters.py:108-129)."""
+    growth, blocks, init = {"densenet121": (32, (6, 12, 24, 16), 64)}[arch]
+    m = BcosifyNetwork(DenseNetBcos(growth, blocks, init), default_config(arch, last_layer_name="classifier"),
+                       add_channels=True, logit_layer=True)
+    m.model.features[3] = nn.AvgPool2d(kernel_size=3, stride=2, padding=1)
+    for mod in m.modules():
+        if hasattr(mod, "bias") and mod.bias is not None:
+            mod.bias = None
+    return m

@@ -303,6 +303,107 @@ class OracleResNet:
 
 
 # ----------------------------------------------------------------------------------------------
+# B-cosified DenseNet (torchvision skeleton; bcos/models/standard_models.py:56-63 DenseNetBcos: classifier (1x1 B-cos
+# conv) before global average pooling; features[3] (pool0) -> AvgPool2d(3,2,1), experiment_parameters.py:108-129)
+# ----------------------------------------------------------------------------------------------
+DENSENET_ARCH = {"densenet121": (32, (6, 12, 24, 16), 64)}
+
+
+def _dn_names(nblocks: int):
+    """State-dict prefixes: `BcosSequential.from_standard_module` (bcos/modules/common.py:46-51) rebuilds every
+    nn.Sequential positionally, so `features` and the transitions lose their child names (features.conv0 ->
+    features.0, transitionK.conv -> features.N.2); dense blocks are ModuleDicts and keep `denselayerL`."""
+    f = "model.features"
+    names = {"conv0": f + ".0", "norm0": f + ".1", "norm5": f + f".{3 + 2 * nblocks}"}
+    for bi in range(1, nblocks + 1):
+        names[f"denseblock{bi}"] = f + f".{2 + 2 * bi}"
+        names[f"transition{bi}.norm"] = f + f".{3 + 2 * bi}.0"
+        names[f"transition{bi}.conv"] = f + f".{3 + 2 * bi}.2"
+    return names
+
+
+def densenet_state_shapes(arch: str, num_classes: int = 1000, bn_size: int = 4) -> Dict[str, Tuple[int, ...]]:
+    growth, blocks, init = DENSENET_ARCH[arch]
+    shapes: Dict[str, Tuple[int, ...]] = {}
+
+    def bn(prefix, c):
+        shapes[prefix + ".weight"] = (c,)
+        shapes[prefix + ".running_mean"] = (c,)
+        shapes[prefix + ".running_var"] = (c,)
+        shapes[prefix + ".num_batches_tracked"] = ()
+
+    nm = _dn_names(len(blocks))
+    shapes[nm["conv0"] + ".linear.weight"] = (init, 6, 7, 7)
+    bn(nm["norm0"], init)
+    c = init
+    for bi, nlayers in enumerate(blocks, start=1):
+        for li in range(1, nlayers + 1):
+            p = nm[f"denseblock{bi}"] + f".denselayer{li}"
+            bn(p + ".norm1", c)
+            shapes[p + ".conv1.linear.weight"] = (bn_size * growth, c, 1, 1)
+            bn(p + ".norm2", bn_size * growth)
+            shapes[p + ".conv2.linear.weight"] = (growth, bn_size * growth, 3, 3)
+            c += growth
+        if bi != len(blocks):
+            bn(nm[f"transition{bi}.norm"], c)
+            shapes[nm[f"transition{bi}.conv"] + ".linear.weight"] = (c // 2, c, 1, 1)
+            c //= 2
+    bn(nm["norm5"], c)
+    shapes["model.classifier.linear.weight"] = (num_classes, c, 1, 1)
+    return shapes
+
+
+class OracleDenseNet:
+    """Functional B-cosified DenseNet over a reference-keyed state dict (torchvision densenet.py layer order:
+    norm -> relu -> conv inside dense layers and transitions)."""
+
+    def __init__(self, arch: str, sd: Dict[str, Tensor], b: float = 2, eps: float = 1e-5,
+                 mean=IMAGENET_MEAN_ADDINVERSE, std=IMAGENET_STD_ADDINVERSE, logit_bias: Optional[float] = LOGIT_BIAS_1000):
+        self.arch, self.sd, self.b, self.eps = arch, sd, b, eps
+        self.growth, self.blocks, self.init = DENSENET_ARCH[arch]
+        self.mean, self.std, self.logit_bias = mean, std, logit_bias
+        self.training, self.momentum = False, 0.1
+
+    def _conv(self, name, x, stride, padding, detach):
+        return bcos_conv2d(x, self.sd[name + ".linear.weight"], None, stride, padding, b=self.b, detach=detach)
+
+    def _bn(self, name, x, detach):
+        return batch_norm_uncentered_2d(x, self.sd[name + ".running_var"], self.sd.get(name + ".weight"),
+                                        self.sd.get(name + ".bias"), self.training, self.momentum, self.eps, detach)
+
+    def forward(self, x6: Tensor, detach: bool = False) -> Tensor:
+        nm = _dn_names(len(self.blocks))
+        x = normalize6(x6, self.mean, self.std)
+        x = F.relu(self._bn(nm["norm0"], self._conv(nm["conv0"], x, 2, 3, detach), detach))
+        x = F.avg_pool2d(x, 3, 2, 1)
+        for bi, nlayers in enumerate(self.blocks, start=1):
+            feats = [x]
+            for li in range(1, nlayers + 1):
+                p = nm[f"denseblock{bi}"] + f".denselayer{li}"
+                cat = torch.cat(feats, 1)
+                h = self._conv(p + ".conv1", F.relu(self._bn(p + ".norm1", cat, detach)), 1, 0, detach)
+                h = self._conv(p + ".conv2", F.relu(self._bn(p + ".norm2", h, detach)), 1, 1, detach)
+                feats.append(h)
+            x = torch.cat(feats, 1)
+            if bi != len(self.blocks):
+                x = self._conv(nm[f"transition{bi}.conv"], F.relu(self._bn(nm[f"transition{bi}.norm"], x, detach)), 1, 0,
+                               detach)
+                x = F.avg_pool2d(x, 2, 2)
+        x = F.relu(self._bn(nm["norm5"], x, detach))
+        x = self._conv("model.classifier", x, 1, 0, detach)       # classifier before GAP (standard_models.py:59-62)
+        x = F.adaptive_avg_pool2d(x, 1).flatten(1)
+        return logit_layer(x, None, self.logit_bias)
+
+    __call__ = forward
+
+    def calibrate_bn(self, x6: Tensor) -> None:
+        self.training, self.momentum = True, 1.0
+        with torch.no_grad():
+            self.forward(x6)
+        self.training, self.momentum = False, 0.1
+
+
+# ----------------------------------------------------------------------------------------------
 # explanation  (bcos/common.py:92-188 `BcosUtilMixin.explain`, batched form SURVEY.md A.4)
 # ----------------------------------------------------------------------------------------------
 def explain_batched(forward: Callable[..., Tensor], x6: Tensor, idx: Optional[Tensor] = None,

@@ -134,6 +134,59 @@ def golden_resnet(arch: str, batch: int, seed: int = 0):
           f"logit std {logits.std():.4f}, pred {logits.argmax(1).tolist()}")
 
 
+def build_reference_densenet(arch: str):
+    refload.load()
+    import bcosify
+    from bcos.models.standard_models import DenseNetBcos
+    growth, blocks, init = O.DENSENET_ARCH[arch]
+    cfg = dict(is_bcos=True, name=arch, last_layer_name="classifier", weights=None, bcos_args=dict(b=2, max_out=1),
+               bcosify_args=dict(fix_b=True, use_bias=False, norm_layer="BnUncV2", manual_optim=False, gap=True,
+                                 act_layer=True))
+    m = bcosify.BcosifyNetwork(DenseNetBcos(growth, blocks, init), cfg, add_channels=True, logit_layer=True)
+    m.model.features[3] = nn.AvgPool2d(kernel_size=3, stride=2, padding=1)
+    for mod in m.modules():
+        if hasattr(mod, "bias") and mod.bias is not None:
+            mod.bias = None
+    return m
+
+
+def golden_densenet(arch: str, batch: int, seed: int = 0):
+    t0 = time.time()
+    m = build_reference_densenet(arch)
+    ref_shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert ref_shapes == O.densenet_state_shapes(arch), "oracle key/shape table differs from the reference state dict"
+    sd = synth.synth_state_dict(ref_shapes, seed)
+    m.load_state_dict(sd, strict=True)
+    u8 = synth.synth_images_u8(batch, 224, seed)
+    x6 = synth.to_bcos_input(u8)
+    reference_calibrate(m, x6)
+    logits, grad, cmap = reference_explain_batched(m, x6)
+    osd = {k: v.clone() for k, v in sd.items()}
+    om = O.OracleDenseNet(arch, osd)
+    om.calibrate_bn(x6)
+    cal = {k: v for k, v in m.state_dict().items() if k.endswith("running_var")}
+    for k, v in cal.items():
+        assert torch.allclose(osd[k], v, rtol=1e-4, atol=0), k
+        osd[k] = v.clone()
+    oe = O.explain_batched(om.forward, x6)
+    pm = O.parity_metrics(oe["logits"], oe["contribution_map"], logits, cmap)
+    print(f"[{arch}] oracle vs reference: {pm}")
+    assert pm["argmax_equal"] and pm["logit_rel_err"] < 1e-5 and pm["map_cos_min"] > 0.99999
+    osd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in osd.items()}
+    e64 = O.explain_batched(O.OracleDenseNet(arch, osd64).forward, x6.double())
+    floor = O.parity_metrics(logits, cmap, e64["logits"], e64["contribution_map"])
+    print(f"[{arch}] reference fp32 vs fp64 evaluation (noise floor): {floor}")
+    keys = sorted(cal)
+    path = os.path.join(GOLD, f"{arch}_b{batch}.npz")
+    np.savez_compressed(
+        path, images_u8=u8, bn_keys=np.array(keys), bn_sizes=np.array([cal[k].numel() for k in keys], dtype=np.int64),
+        bn_var=torch.cat([cal[k].flatten() for k in keys]).numpy(), logits=logits.numpy(), contribution_map=cmap.numpy(),
+        logits_fp64=e64["logits"].numpy(), contribution_map_fp64=e64["contribution_map"].float().numpy(),
+        fp32_noise_floor_maxabs_over_range=np.float64(floor["map_maxabs_over_range"]),
+        fp32_noise_floor_logit_rel_err=np.float64(floor["logit_rel_err"]), seed=np.int64(seed))
+    print(f"[{arch}] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB) in {time.time()-t0:.1f}s; logit std {logits.std():.4f}")
+
+
 def golden_modules(seed: int = 0):
     """Known-answer vectors for single modules, produced by the reference classes themselves."""
     refload.load()
@@ -297,6 +350,8 @@ if __name__ == "__main__":
         golden_resnet("resnet18", 8)
     if "resnet50" in which:
         golden_resnet("resnet50", 4)
+    if "densenet121" in which:
+        golden_densenet("densenet121", 2)
     if "calib" in which:
         calibration_file("resnet18")
         calibration_file("resnet50")

@@ -9,7 +9,7 @@ import torch
 
 import bcos_oracle as OR
 import bcos_b200.modules as M
-from bcos_b200.bcosify import bcosified_resnet
+from bcos_b200.bcosify import bcosified_densenet, bcosified_resnet
 from bcos_b200.utils import synth
 
 pytestmark = pytest.mark.gpu
@@ -117,3 +117,22 @@ def test_module_level_resnet18_matches_golden(bcosk_lib, golden_dir):
     e = m.explain(x6[:1].clone().requires_grad_(True))
     assert e["prediction"] == int(gold["logits"][0].argmax())
     assert tuple(e["explanation"].shape) == (224, 224, 4)
+
+
+def test_module_level_densenet121_matches_golden(bcosk_lib, golden_dir):
+    """config 5's network (DenseNet-121): BN -> ReLU -> conv ordering, channel counts that are not multiples of 64,
+    32-channel growth convs, torch.cat feature reuse - all through the drop-in modules."""
+    gold = np.load(os.path.join(golden_dir, "densenet121_b2.npz"))
+    m = bcosified_densenet("densenet121")
+    sd = synth.synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, int(gold["seed"]))
+    off = 0
+    for k, n in zip(gold["bn_keys"].tolist(), gold["bn_sizes"].tolist()):
+        sd[k] = torch.from_numpy(gold["bn_var"][off:off + n].copy()); off += n
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    x6 = synth.to_bcos_input(gold["images_u8"]).cuda()
+    out = m.explain_batch(x6)
+    mm = OR.parity_metrics(out["logits"], out["contribution_map"], torch.from_numpy(gold["logits"]),
+                           torch.from_numpy(gold["contribution_map"]))
+    print("module-level densenet121 vs reference golden:", mm)
+    assert mm["argmax_equal"] and mm["logit_rel_err"] <= 2e-3 and mm["map_cos_min"] >= 0.999 and mm["map_maxabs_over_range"] <= 1e-3

@@ -144,3 +144,16 @@ def test_oracle_pinned_to_live_reference():
     bn = BatchNormUncentered2d(6).eval()
     x = torch.randn(2, 6, 4, 4, generator=g)
     assert torch.equal(bn(x), OR.batch_norm_uncentered_2d(x, bn.running_var, bn.weight, bn.bias))
+
+
+def test_densenet_golden(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "densenet121_b2.npz"))
+    sd = synth.synth_state_dict(OR.densenet_state_shapes("densenet121"), int(gold["seed"]))
+    off = 0
+    for k, n in zip(gold["bn_keys"].tolist(), gold["bn_sizes"].tolist()):
+        sd[k] = torch.from_numpy(gold["bn_var"][off:off + n].copy())
+        off += n
+    x6 = synth.to_bcos_input(gold["images_u8"][:1])
+    e = OR.explain_batched(OR.OracleDenseNet("densenet121", sd).forward, x6)
+    m = OR.parity_metrics(e["logits"], e["contribution_map"], _t(gold["logits"][:1]), _t(gold["contribution_map"][:1]))
+    assert m["argmax_equal"] and m["logit_rel_err"] < 1e-5 and m["map_cos_min"] > 0.99999, m
