@@ -220,3 +220,22 @@ def scale_bias_nchw(x, nb, c, hw, alpha, beta, smul, sadd, relu, out) -> None:
 
 def channel_stats_nchw(x, nb, c, hw, mean, var) -> None:
     check(load().bcosk_channel_stats_nchw(_p(x), nb, c, C.c_int64(hw), _p(mean), _p(var), _stream()), "bcosk_channel_stats_nchw")
+
+
+def layernorm_fwd(x, rows, d, w, b, eps, y, rstd) -> None:
+    check(load().bcosk_layernorm_fwd(_p(x), C.c_int64(rows), d, _p(w), _p(b), C.c_float(eps), _p(y), _p(rstd), _stream()),
+          "bcosk_layernorm_fwd")
+
+
+def layernorm_explain_bwd(gy, rows, d, w, rstd, gx) -> None:
+    check(load().bcosk_layernorm_explain_bwd(_p(gy), C.c_int64(rows), d, _p(w), _p(rstd), _p(gx), _stream()),
+          "bcosk_layernorm_explain_bwd")
+
+
+def gelu_gate(x, g, n, y) -> None:
+    check(load().bcosk_gelu_gate(_p(x), _p(g), C.c_int64(n), _p(y), _stream()), "bcosk_gelu_gate")
+
+
+def attention(qkv, g, batch, n, heads, dim_head, scale, backward, out) -> None:
+    check(load().bcosk_attention(_p(qkv), _p(g), batch, n, heads, dim_head, C.c_float(scale), int(backward), _p(out), _stream()),
+          "bcosk_attention")

@@ -6,7 +6,9 @@ from .bcoslinear import BcosifyLinear, BcosLinear, NormedLinear
 from .common import BcosSequential, DetachableModule
 from .logitlayer import LogitLayer
 from .norms import BatchNormUncentered2d, NoBias, Unaffine, batch_norm_uncentered_2d
+from .tokens import DetachableLayerNorm, MyGELU, PlainLinear, frozen_attention
 
 __all__ = ["BcosConv2d", "BcosConv2dWithScale", "BcosifyConv2d", "NormedConv2d", "BcosLinear", "BcosifyLinear",
            "NormedLinear", "BcosSequential", "DetachableModule", "LogitLayer", "BatchNormUncentered2d", "NoBias", "Unaffine",
-           "batch_norm_uncentered_2d", "norms", "config", "set_precision"]
+           "batch_norm_uncentered_2d", "DetachableLayerNorm", "MyGELU", "PlainLinear", "frozen_attention", "norms", "config",
+           "set_precision"]

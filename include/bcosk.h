@@ -217,6 +217,25 @@ int bcosk_scale_bias_nchw(const float* x, int32_t nb, int32_t c, int64_t hw, con
 /* per-channel mean and biased variance over (N,H,W): x.var(dim=(0,2,3), unbiased=False) batchnorm_uncentered.py:39 */
 int bcosk_channel_stats_nchw(const float* x, int32_t nb, int32_t c, int64_t hw, float* mean, float* var, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Token models (B-cosified SimpleViT), fp32 I/O
+ * ------------------------------------------------------------------------------------------- */
+/* DetachableLayerNorm.forward bcos/modules/norms/centered_norms.py:187-224: y = w*(x-mean)/sqrt(var+eps)+b per row of d
+ * values; rstd[row] = 1/sqrt(var+eps) is saved for the explanation backward */
+int bcosk_layernorm_fwd(const float* x, int64_t rows, int32_t d, const float* w, const float* b, float eps, float* y,
+                        float* rstd, void* stream);
+/* explanation backward of the above (variance detached :211, mean in graph): gx = (w*gy - mean_d(w*gy)) * rstd */
+int bcosk_layernorm_explain_bwd(const float* gy, int64_t rows, int32_t d, const float* w, const float* rstd, float* gx,
+                                void* stream);
+/* MyGELU bcosify_vit.py:27-32: g == NULL: y = x * gate(x);  g != NULL (explanation backward, gate detached): y = g * gate(x) */
+int bcosk_gelu_gate(const float* x, const float* g, int64_t n, float* y, void* stream);
+/* Attention.forward bcos/models/vit.py:143-158 after to_qkv: qkv [batch, n, 3*heads*64] ->
+ *   backward == 0: out [batch, n, heads*64] = softmax(q k^T * scale) v
+ *   backward == 1: explanation backward with q, k detached (:148-150): out [batch, n, 3*heads*64] (pre-zeroed), v block =
+ *                  P^T g, g [batch, n, heads*64] */
+int bcosk_attention(const float* qkv, const float* g, int32_t batch, int32_t n, int32_t heads, int32_t dim_head, float scale,
+                    int32_t backward, float* out, void* stream);
+
 const char* bcosk_last_error(void);
 int bcosk_version(void);
 /* sizeof(bcosk_igemm_params) as compiled into the library (binding self-check). */

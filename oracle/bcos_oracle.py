@@ -404,6 +404,95 @@ class OracleDenseNet:
 
 
 # ----------------------------------------------------------------------------------------------
+# B-cosified SimpleViT (bcos/models/vit.py:232-339 converted by bcosify_vit.py:45-153; gap_reorder = True:
+# the B-cos head is applied per token before the mean, vit.py:331-334)
+# ----------------------------------------------------------------------------------------------
+VIT_ARCH = {  # name: (dim, depth, heads, mlp_dim)   vit.py:441-467
+    "simple_vit_ti_patch16_224": (192, 12, 3, 768),
+    "simple_vit_s_patch16_224": (384, 12, 6, 1536),
+    "simple_vit_b_patch16_224": (768, 12, 12, 3072),
+}
+
+
+def vit_state_shapes(arch: str, num_classes: int = 1000, patch: int = 16) -> Dict[str, Tuple[int, ...]]:
+    dim, depth, heads, mlp = VIT_ARCH[arch]
+    sh: Dict[str, Tuple[int, ...]] = {"model.to_patch_embedding.linear.linear.weight": (dim, patch * patch * 6)}
+    for i in range(depth):
+        p = f"model.transformer.encoder_{i}"
+        sh[p + ".attn.norm.weight"] = (dim,)
+        sh[p + ".attn.to_qkv.weight"] = (3 * dim, dim)
+        sh[p + ".attn.to_out.linear.weight"] = (dim, dim)
+        sh[p + ".ff.net.norm.weight"] = (dim,)
+        sh[p + ".ff.net.linear1.linear.weight"] = (mlp, dim)
+        sh[p + ".ff.net.linear2.linear.weight"] = (dim, mlp)
+    sh["model.linear_head.norm.weight"] = (dim,)
+    sh["model.linear_head.linear.linear.weight"] = (num_classes, dim)
+    return sh
+
+
+def posemb_sincos_2d(h: int, w: int, dim: int, temperature: float = 10000.0) -> Tensor:
+    """`PosEmbSinCos2d.forward` vit.py:64-86."""
+    y, x = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    omega = torch.arange(dim // 4) / (dim // 4 - 1)
+    omega = 1.0 / (temperature ** omega)
+    y = y.flatten()[:, None] * omega[None, :]
+    x = x.flatten()[:, None] * omega[None, :]
+    return torch.cat((x.sin(), x.cos(), y.sin(), y.cos()), dim=1)
+
+
+def vit_add_channels_linear(w3: Tensor) -> Tensor:
+    """`BcosifyNetwork.add_channels` bcosify_vit.py:84-125: per pixel [W/2, -W/2] interleaved on the (p1 p2 c) axis."""
+    out_f = w3.shape[0]
+    wr = w3.view(out_f, -1, 3) / 2
+    return torch.cat([wr, -wr], dim=2).reshape(out_f, -1)
+
+
+class OracleViT:
+    def __init__(self, arch: str, sd: Dict[str, Tensor], b: float = 2, patch: int = 16, eps: float = 1e-5,
+                 mean=IMAGENET_MEAN_ADDINVERSE, std=IMAGENET_STD_ADDINVERSE, logit_bias: Optional[float] = LOGIT_BIAS_1000,
+                 logit_temperature: Optional[float] = None):
+        self.arch, self.sd, self.b, self.patch, self.eps = arch, sd, b, patch, eps
+        self.dim, self.depth, self.heads, self.mlp = VIT_ARCH[arch]
+        self.mean, self.std, self.logit_bias, self.logit_temperature = mean, std, logit_bias, logit_temperature
+
+    def _lin(self, name, x, detach):
+        return bcos_linear(x, self.sd[name + ".linear.weight"], None, b=self.b, detach=detach)
+
+    def _ln(self, name, x, detach):
+        return layer_norm_detachable(x, self.sd[name + ".weight"], self.sd.get(name + ".bias"), self.eps, detach)
+
+    def forward(self, x6: Tensor, detach: bool = False) -> Tensor:
+        x = normalize6(x6, self.mean, self.std)
+        B, C, H, W = x.shape
+        p = self.patch
+        hh, ww = H // p, W // p
+        # Rearrange "b c (h p1) (w p2) -> b h w (p1 p2 c)"  (vit.py:290-294)
+        x = x.view(B, C, hh, p, ww, p).permute(0, 2, 4, 3, 5, 1).reshape(B, hh, ww, p * p * C)
+        x = self._lin("model.to_patch_embedding.linear", x, detach)
+        x = x.reshape(B, hh * ww, self.dim) + posemb_sincos_2d(hh, ww, self.dim).to(x.dtype)       # vit.py:325-326
+        dh = self.dim // self.heads
+        for i in range(self.depth):
+            pfx = f"model.transformer.encoder_{i}"
+            h = self._ln(pfx + ".attn.norm", x, detach)
+            qkv = F.linear(h, self.sd[pfx + ".attn.to_qkv.weight"]).chunk(3, dim=-1)               # plain linear, vit.py:140
+            q, k, v = (t.view(B, -1, self.heads, dh).transpose(1, 2) for t in qkv)
+            if detach:
+                q, k = q.detach(), k.detach()                                                      # vit.py:148-150
+            attn = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) * dh ** -0.5, dim=-1)
+            o = torch.matmul(attn, v).transpose(1, 2).reshape(B, -1, self.dim)
+            x = self._lin(pfx + ".attn.to_out", o, detach) + x
+            h = self._ln(pfx + ".ff.net.norm", x, detach)
+            h = self._lin(pfx + ".ff.net.linear1", h, detach)
+            h = gelu_detachable(h, detach)
+            x = self._lin(pfx + ".ff.net.linear2", h, detach) + x
+        x = self._lin("model.linear_head.linear", self._ln("model.linear_head.norm", x, detach), detach)   # gap_reorder
+        x = x.mean(dim=1)
+        return logit_layer(x, self.logit_temperature, self.logit_bias)
+
+    __call__ = forward
+
+
+# ----------------------------------------------------------------------------------------------
 # explanation  (bcos/common.py:92-188 `BcosUtilMixin.explain`, batched form SURVEY.md A.4)
 # ----------------------------------------------------------------------------------------------
 def explain_batched(forward: Callable[..., Tensor], x6: Tensor, idx: Optional[Tensor] = None,

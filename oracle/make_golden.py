@@ -187,6 +187,55 @@ def golden_densenet(arch: str, batch: int, seed: int = 0):
     print(f"[{arch}] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB) in {time.time()-t0:.1f}s; logit std {logits.std():.4f}")
 
 
+def build_reference_vit(arch: str):
+    refload.load()
+    import bcosify_vit
+    import bcos.models.vit as rvit
+    from bcos.modules.norms.centered_norms import DetachableGNLayerNorm2d
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        base = getattr(rvit, arch)(linear_layer=nn.Linear, conv2d_layer=nn.Conv2d, norm_layer=nn.LayerNorm,
+                                   norm2d_layer=DetachableGNLayerNorm2d, act_layer=nn.GELU, channels=3)
+    cfg = dict(is_bcos=True, name=arch, weights=None, logit_layer=True, bcos_args=dict(b=2, max_out=1),
+               bcosify_args=dict(use_bias=False), args=dict(gap_reorder=True))
+    m = bcosify_vit.BcosifyNetwork(base, cfg, add_channels=True, logit_layer=True)
+    for mod in m.modules():
+        if hasattr(mod, "bias") and mod.bias is not None:
+            mod.bias = None
+    m.model.gap_reorder = True
+    return m
+
+
+def golden_vit(arch: str, batch: int, seed: int = 0):
+    t0 = time.time()
+    m = build_reference_vit(arch).eval()
+    ref_shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert ref_shapes == O.vit_state_shapes(arch), (set(ref_shapes) ^ set(O.vit_state_shapes(arch)))
+    sd = synth.synth_state_dict(ref_shapes, seed)
+    m.load_state_dict(sd, strict=True)
+    u8 = synth.synth_images_u8(batch, 224, seed)
+    x6 = synth.to_bcos_input(u8)
+    logits, grad, cmap = reference_explain_batched(m, x6)
+    with torch.inference_mode():
+        assert torch.allclose(m(x6), logits, rtol=1e-5, atol=1e-6)
+    oe = O.explain_batched(O.OracleViT(arch, sd).forward, x6)
+    pm = O.parity_metrics(oe["logits"], oe["contribution_map"], logits, cmap)
+    print(f"[{arch}] oracle vs reference: {pm}")
+    assert pm["argmax_equal"] and pm["logit_rel_err"] < 1e-5 and pm["map_cos_min"] > 0.99999
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    e64 = O.explain_batched(O.OracleViT(arch, sd64).forward, x6.double())
+    floor = O.parity_metrics(logits, cmap, e64["logits"], e64["contribution_map"])
+    print(f"[{arch}] reference fp32 vs fp64 evaluation (noise floor): {floor}")
+    path = os.path.join(GOLD, f"{arch}_b{batch}.npz")
+    np.savez_compressed(
+        path, images_u8=u8, logits=logits.numpy(), contribution_map=cmap.numpy(), logits_fp64=e64["logits"].numpy(),
+        contribution_map_fp64=e64["contribution_map"].float().numpy(),
+        fp32_noise_floor_maxabs_over_range=np.float64(floor["map_maxabs_over_range"]),
+        fp32_noise_floor_logit_rel_err=np.float64(floor["logit_rel_err"]), seed=np.int64(seed))
+    print(f"[{arch}] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB) in {time.time()-t0:.1f}s; logit std {logits.std():.4f}")
+
+
 def golden_modules(seed: int = 0):
     """Known-answer vectors for single modules, produced by the reference classes themselves."""
     refload.load()
@@ -352,6 +401,8 @@ if __name__ == "__main__":
         golden_resnet("resnet50", 4)
     if "densenet121" in which:
         golden_densenet("densenet121", 2)
+    if "vit_ti" in which:
+        golden_vit("simple_vit_ti_patch16_224", 2)
     if "calib" in which:
         calibration_file("resnet18")
         calibration_file("resnet50")

@@ -136,3 +136,61 @@ def test_module_level_densenet121_matches_golden(bcosk_lib, golden_dir):
                            torch.from_numpy(gold["contribution_map"]))
     print("module-level densenet121 vs reference golden:", mm)
     assert mm["argmax_equal"] and mm["logit_rel_err"] <= 2e-3 and mm["map_cos_min"] >= 0.999 and mm["map_maxabs_over_range"] <= 1e-3
+
+
+def test_token_modules_match_reference(bcosk_lib, kat):
+    ln = M.DetachableLayerNorm(24).cuda()
+    ln.weight.data = _t(kat["ln.w"]); ln.bias = None
+    x = _t(kat["ln.x"])
+    assert _rel(ln(x), _t(kat["ln.y"])) < 2e-6
+    ln.set_explanation_mode(True)
+    xg = x.clone().requires_grad_(True)
+    ye = ln(xg)
+    assert _rel(ye, _t(kat["ln.y_explain"])) < 2e-6
+    (gx,) = torch.autograd.grad((ye * _t(kat["ln.seed"])).sum(), [xg])
+    assert _rel(gx, _t(kat["ln.gx"])) < 1e-5
+    gelu = M.MyGELU()
+    x = _t(kat["gelu.x"])
+    assert _rel(gelu(x), _t(kat["gelu.y"])) < 2e-6
+    gelu.set_explanation_mode(True)
+    xg = x.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad((gelu(xg) * _t(kat["gelu.seed"])).sum(), [xg])
+    assert _rel(gx, _t(kat["gelu.gx"])) < 2e-6
+
+
+def test_frozen_attention_matches_torch(bcosk_lib):
+    g = torch.Generator().manual_seed(12)
+    B, N, H, D = 2, 196, 3, 64
+    qkv = torch.randn(B, N, 3 * H * D, generator=g)
+    seed = torch.randn(B, N, H * D, generator=g)
+    q, k, v = (t.view(B, N, H, D).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
+    vg = v.clone().requires_grad_(True)
+    attn = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) * D ** -0.5, dim=-1)
+    ref = torch.matmul(attn, vg).transpose(1, 2).reshape(B, N, H * D)
+    (gv,) = torch.autograd.grad((ref * seed).sum(), [vg])
+    xq = qkv.cuda().requires_grad_(True)
+    out = M.frozen_attention(xq, H, D ** -0.5, True)
+    assert _rel(out, ref.detach().cuda()) < 1e-5
+    (gq,) = torch.autograd.grad((out * seed.cuda()).sum(), [xq])
+    gref = torch.zeros_like(qkv)
+    gref[..., 2 * H * D:] = gv.transpose(1, 2).reshape(B, N, H * D)
+    assert _rel(gq, gref.cuda()) < 1e-5
+
+
+def test_module_level_vit_ti_matches_golden(bcosk_lib, golden_dir):
+    from bcos_b200.vit import bcosified_simple_vit
+    arch = "simple_vit_ti_patch16_224"
+    gold = np.load(os.path.join(golden_dir, f"{arch}_b2.npz"))
+    m = bcosified_simple_vit(arch)
+    sd = synth.synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, int(gold["seed"]))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    x6 = synth.to_bcos_input(gold["images_u8"]).cuda()
+    with torch.inference_mode():
+        logits = m(x6)
+    out = m.explain_batch(x6)
+    assert torch.allclose(out["logits"], logits, rtol=1e-6, atol=1e-7)
+    mm = OR.parity_metrics(out["logits"], out["contribution_map"], torch.from_numpy(gold["logits"]),
+                           torch.from_numpy(gold["contribution_map"]))
+    print("module-level ViT-Ti vs reference golden:", mm)
+    assert mm["argmax_equal"] and mm["logit_rel_err"] <= 2e-3 and mm["map_cos_min"] >= 0.999 and mm["map_maxabs_over_range"] <= 1e-3

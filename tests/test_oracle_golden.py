@@ -157,3 +157,17 @@ def test_densenet_golden(golden_dir):
     e = OR.explain_batched(OR.OracleDenseNet("densenet121", sd).forward, x6)
     m = OR.parity_metrics(e["logits"], e["contribution_map"], _t(gold["logits"][:1]), _t(gold["contribution_map"][:1]))
     assert m["argmax_equal"] and m["logit_rel_err"] < 1e-5 and m["map_cos_min"] > 0.99999, m
+
+
+def test_vit_golden(golden_dir):
+    arch = "simple_vit_ti_patch16_224"
+    gold = np.load(os.path.join(golden_dir, f"{arch}_b2.npz"))
+    sd = synth.synth_state_dict(OR.vit_state_shapes(arch), int(gold["seed"]))
+    x6 = synth.to_bcos_input(gold["images_u8"][:1])
+    e = OR.explain_batched(OR.OracleViT(arch, sd).forward, x6)
+    m = OR.parity_metrics(e["logits"], e["contribution_map"], _t(gold["logits"][:1]), _t(gold["contribution_map"][:1]))
+    assert m["argmax_equal"] and m["logit_rel_err"] < 1e-5 and m["map_cos_min"] > 0.99999, m
+    # the patch-embedding weight doubling of bcosify_vit.add_channels: [W/2, -W/2] per pixel
+    w3 = torch.arange(2 * 12, dtype=torch.float32).view(2, 12)
+    w6 = OR.vit_add_channels_linear(w3)
+    assert w6.shape == (2, 24) and torch.equal(w6[:, :3], w3[:, :3] / 2) and torch.equal(w6[:, 3:6], -w3[:, :3] / 2)
