@@ -493,6 +493,125 @@ class OracleViT:
 
 
 # ----------------------------------------------------------------------------------------------
+# B-cos CLIP RN50 image encoder: CLIP/clip/model.py:94-154 `ModifiedResNet` (3-conv stem, anti-aliasing avg pools,
+# CLIP/clip/model.py:10-55 `Bottleneck`) converted by bcosify.py with clip_kd (CLIP mean/std, no LogitLayer) and
+# `BcosAttentionPool2d` (bcos/modules/bcosattnpool.py:22-59) without positional embedding or biases
+# (bcos/experiments/ImageNet/clip_bcosification/model.py:15-23)
+# ----------------------------------------------------------------------------------------------
+def clip_rn_state_shapes(layers=(3, 4, 6, 3), output_dim: int = 1024, width: int = 64) -> Dict[str, Tuple[int, ...]]:
+    sh: Dict[str, Tuple[int, ...]] = {}
+
+    def bn(prefix, c):
+        sh[prefix + ".weight"] = (c,)
+        sh[prefix + ".running_mean"] = (c,)
+        sh[prefix + ".running_var"] = (c,)
+        sh[prefix + ".num_batches_tracked"] = ()
+
+    sh["model.conv1.linear.weight"] = (width // 2, 6, 3, 3); bn("model.bn1", width // 2)
+    sh["model.conv2.linear.weight"] = (width // 2, width // 2, 3, 3); bn("model.bn2", width // 2)
+    sh["model.conv3.linear.weight"] = (width, width // 2, 3, 3); bn("model.bn3", width)
+    inpl = width
+    for li, (planes, nb) in enumerate(zip([width, width * 2, width * 4, width * 8], layers), start=1):
+        for bi in range(nb):
+            stride = 2 if (li > 1 and bi == 0) else 1
+            p = f"model.layer{li}.{bi}"
+            sh[p + ".conv1.linear.weight"] = (planes, inpl, 1, 1); bn(p + ".bn1", planes)
+            sh[p + ".conv2.linear.weight"] = (planes, planes, 3, 3); bn(p + ".bn2", planes)
+            sh[p + ".conv3.linear.weight"] = (planes * 4, planes, 1, 1); bn(p + ".bn3", planes * 4)
+            if stride > 1 or inpl != planes * 4:
+                # BcosSequential rebuilds the ("-1","0","1") Sequential positionally: avgpool=0, conv=1, bn=2
+                sh[p + ".downsample.1.linear.weight"] = (planes * 4, inpl, 1, 1); bn(p + ".downsample.2", planes * 4)
+            inpl = planes * 4
+    e = width * 32
+    for nme in ("k_proj", "q_proj", "v_proj"):
+        sh[f"model.attnpool.{nme}.weight"] = (e, e)
+    sh["model.attnpool.c_proj.linear.weight"] = (output_dim, e)
+    return sh
+
+
+class OracleCLIPResNet:
+    def __init__(self, sd: Dict[str, Tensor], layers=(3, 4, 6, 3), heads: int = 32, b: float = 2, eps: float = 1e-5,
+                 mean=CLIP_MEAN_ADDINVERSE, std=CLIP_STD_ADDINVERSE):
+        self.sd, self.layers, self.heads, self.b, self.eps, self.mean, self.std = sd, layers, heads, b, eps, mean, std
+        self.training, self.momentum = False, 0.1
+
+    def _conv(self, name, x, stride, padding, detach):
+        return bcos_conv2d(x, self.sd[name + ".linear.weight"], None, stride, padding, b=self.b, detach=detach)
+
+    def _bn(self, name, x, detach):
+        return batch_norm_uncentered_2d(x, self.sd[name + ".running_var"], self.sd.get(name + ".weight"),
+                                        self.sd.get(name + ".bias"), self.training, self.momentum, self.eps, detach)
+
+    def _block(self, p, x, stride, detach):
+        out = F.relu(self._bn(p + ".bn1", self._conv(p + ".conv1", x, 1, 0, detach), detach))
+        out = F.relu(self._bn(p + ".bn2", self._conv(p + ".conv2", out, 1, 1, detach), detach))
+        if stride > 1:
+            out = F.avg_pool2d(out, stride)
+        out = self._bn(p + ".bn3", self._conv(p + ".conv3", out, 1, 0, detach), detach)
+        idn = x
+        if (p + ".downsample.1.linear.weight") in self.sd:
+            idn = F.avg_pool2d(x, stride) if stride > 1 else x
+            idn = self._bn(p + ".downsample.2", self._conv(p + ".downsample.1", idn, 1, 0, detach), detach)
+        return F.relu(out + idn)
+
+    def attnpool(self, x: Tensor, detach: bool) -> Tensor:
+        """bcosattnpool.py:34-59 (pooled mode): query = mean token, q/k detached in explanation mode, bias-free
+        projections, `c_proj` used as a plain linear (only its .weight is read)."""
+        N, C = x.shape[0], x.shape[1]
+        t = x.flatten(2).permute(2, 0, 1)
+        t = torch.cat([t.mean(dim=0, keepdim=True), t], dim=0)          # (HW+1) N C
+        q, k = t[:1], t
+        if detach:
+            q, k = q.detach(), k.detach()
+        H, dh = self.heads, C // self.heads
+        qp = F.linear(q, self.sd["model.attnpool.q_proj.weight"]) * dh ** -0.5
+        kp = F.linear(k, self.sd["model.attnpool.k_proj.weight"])
+        vp = F.linear(t, self.sd["model.attnpool.v_proj.weight"])
+        qh = qp.reshape(1, N * H, dh).transpose(0, 1)                   # [N*H, 1, dh]
+        kh = kp.reshape(-1, N * H, dh).transpose(0, 1)
+        vh = vp.reshape(-1, N * H, dh).transpose(0, 1)
+        attn = torch.softmax(torch.bmm(qh, kh.transpose(1, 2)), dim=-1)
+        o = torch.bmm(attn, vh).transpose(0, 1).reshape(1, N, C)
+        return F.linear(o, self.sd["model.attnpool.c_proj.linear.weight"]).squeeze(0)
+
+    def forward(self, x6: Tensor, detach: bool = False) -> Tensor:
+        x = normalize6(x6, self.mean, self.std)
+        x = F.relu(self._bn("model.bn1", self._conv("model.conv1", x, 2, 1, detach), detach))
+        x = F.relu(self._bn("model.bn2", self._conv("model.conv2", x, 1, 1, detach), detach))
+        x = F.relu(self._bn("model.bn3", self._conv("model.conv3", x, 1, 1, detach), detach))
+        x = F.avg_pool2d(x, 2)
+        for li, nb in enumerate(self.layers, start=1):
+            for bi in range(nb):
+                x = self._block(f"model.layer{li}.{bi}", x, 2 if (li > 1 and bi == 0) else 1, detach)
+        return self.attnpool(x, detach)
+
+    __call__ = forward
+
+    def calibrate_bn(self, x6: Tensor) -> None:
+        self.training, self.momentum = True, 1.0
+        with torch.no_grad():
+            self.forward(x6)
+        self.training, self.momentum = False, 0.1
+
+
+def clip_seed_direction(dim: int = 1024, seed: int = 0) -> Tensor:
+    """Fixed unit 'text embedding' t for the CLIP explanation target cos(emb, t)
+    (interpretability/analyses/text_localisation.py:77-100 back-propagates from the image-text cosine)."""
+    g = torch.Generator().manual_seed(4242 + seed)
+    t = torch.randn(dim, generator=g)
+    return t / t.norm()
+
+
+def explain_cosine(forward: Callable[..., Tensor], x6: Tensor, t: Tensor) -> Dict[str, Tensor]:
+    xb = x6.clone().requires_grad_(True)
+    with torch.enable_grad():
+        emb = forward(xb, detach=True)
+        target = F.cosine_similarity(emb, t.to(emb.dtype)[None], dim=1).sum()
+        (grad,) = torch.autograd.grad(target, [xb])
+    return {"embedding": emb.detach(), "dynamic_linear_weights": grad, "contribution_map": (x6 * grad).sum(1)}
+
+
+# ----------------------------------------------------------------------------------------------
 # explanation  (bcos/common.py:92-188 `BcosUtilMixin.explain`, batched form SURVEY.md A.4)
 # ----------------------------------------------------------------------------------------------
 def explain_batched(forward: Callable[..., Tensor], x6: Tensor, idx: Optional[Tensor] = None,

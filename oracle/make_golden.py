@@ -236,6 +236,63 @@ def golden_vit(arch: str, batch: int, seed: int = 0):
     print(f"[{arch}] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB) in {time.time()-t0:.1f}s; logit std {logits.std():.4f}")
 
 
+def golden_clip_rn50(batch: int, seed: int = 0):
+    """config 4: B-cos CLIP RN50 image encoder, explanation target = cos(embedding, fixed unit vector)."""
+    import torch.nn.functional as F
+    t0 = time.time()
+    refload.load()
+    import bcosify
+    from CLIP.clip.model import ModifiedResNet
+    cfg = dict(is_bcos=True, name="resnet50clip", bcos_args=dict(b=2, max_out=1),
+               bcosify_args=dict(clip_kd=True, fix_b=True, norm_layer="BnUncV2", use_bias=False))
+    m = bcosify.BcosifyNetwork(ModifiedResNet((3, 4, 6, 3), 1024, 32, 224, 64).float(), cfg, add_channels=True, logit_layer=False)
+    for mod in m.modules():
+        if hasattr(mod, "bias") and mod.bias is not None:
+            mod.bias = None
+        if hasattr(mod, "positional_embedding") and mod.positional_embedding is not None:
+            mod.positional_embedding = None
+    ref_shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    mine = O.clip_rn_state_shapes()
+    assert ref_shapes == mine, (sorted(set(ref_shapes) ^ set(mine))[:10])
+    sd = synth.synth_state_dict(ref_shapes, seed)
+    m.load_state_dict(sd, strict=True)
+    u8 = synth.synth_images_u8(batch, 224, seed)
+    x6 = synth.to_bcos_input(u8)
+    reference_calibrate(m, x6)
+    tvec = O.clip_seed_direction(1024, seed)
+    xb = x6.clone().requires_grad_(True)
+    with torch.enable_grad(), m.explanation_mode():
+        emb = m(xb)
+        F.cosine_similarity(emb, tvec[None], dim=1).sum().backward(inputs=[xb])
+    cmap = (xb * xb.grad).sum(1).detach()
+    emb = emb.detach()
+    osd = {k: v.clone() for k, v in sd.items()}
+    om = O.OracleCLIPResNet(osd)
+    om.calibrate_bn(x6)
+    cal = {k: v for k, v in m.state_dict().items() if k.endswith("running_var")}
+    for k, v in cal.items():
+        assert torch.allclose(osd[k], v, rtol=1e-4, atol=0), k
+        osd[k] = v.clone()
+    oe = O.explain_cosine(om.forward, x6, tvec)
+    erel = ((oe["embedding"] - emb).abs().max() / emb.abs().max()).item()
+    mrel = ((oe["contribution_map"] - cmap).abs().max() / cmap.abs().max()).item()
+    print(f"[clip_rn50] oracle vs reference: embedding rel err {erel:.2e}, map rel err {mrel:.2e}")
+    assert erel < 1e-5 and mrel < 1e-4
+    osd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in osd.items()}
+    e64 = O.explain_cosine(O.OracleCLIPResNet(osd64).forward, x6.double(), tvec.double())
+    rng = (cmap.flatten(1).max(1).values - cmap.flatten(1).min(1).values)
+    floor = ((cmap.double() - e64["contribution_map"]).abs().flatten(1).max(1).values / rng).max().item()
+    print(f"[clip_rn50] reference fp32 vs fp64 evaluation: map max-abs/range {floor:.2e}; |emb| {emb.norm(dim=1).tolist()}")
+    keys = sorted(cal)
+    path = os.path.join(GOLD, f"clip_rn50_b{batch}.npz")
+    np.savez_compressed(
+        path, images_u8=u8, bn_keys=np.array(keys), bn_sizes=np.array([cal[k].numel() for k in keys], dtype=np.int64),
+        bn_var=torch.cat([cal[k].flatten() for k in keys]).numpy(), embedding=emb.numpy(), contribution_map=cmap.numpy(),
+        contribution_map_fp64=e64["contribution_map"].float().numpy(), embedding_fp64=e64["embedding"].numpy(),
+        fp32_noise_floor_maxabs_over_range=np.float64(floor), seed=np.int64(seed))
+    print(f"[clip_rn50] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB) in {time.time()-t0:.1f}s")
+
+
 def golden_modules(seed: int = 0):
     """Known-answer vectors for single modules, produced by the reference classes themselves."""
     refload.load()
@@ -403,6 +460,8 @@ if __name__ == "__main__":
         golden_densenet("densenet121", 2)
     if "vit_ti" in which:
         golden_vit("simple_vit_ti_patch16_224", 2)
+    if "clip_rn50" in which:
+        golden_clip_rn50(2)
     if "calib" in which:
         calibration_file("resnet18")
         calibration_file("resnet50")

@@ -171,3 +171,17 @@ def test_vit_golden(golden_dir):
     w3 = torch.arange(2 * 12, dtype=torch.float32).view(2, 12)
     w6 = OR.vit_add_channels_linear(w3)
     assert w6.shape == (2, 24) and torch.equal(w6[:, :3], w3[:, :3] / 2) and torch.equal(w6[:, 3:6], -w3[:, :3] / 2)
+
+
+def test_clip_rn50_golden(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "clip_rn50_b2.npz"))
+    sd = synth.synth_state_dict(OR.clip_rn_state_shapes(), int(gold["seed"]))
+    off = 0
+    for k, n in zip(gold["bn_keys"].tolist(), gold["bn_sizes"].tolist()):
+        sd[k] = torch.from_numpy(gold["bn_var"][off:off + n].copy())
+        off += n
+    x6 = synth.to_bcos_input(gold["images_u8"][:1])
+    e = OR.explain_cosine(OR.OracleCLIPResNet(sd).forward, x6, OR.clip_seed_direction(1024, int(gold["seed"])))
+    emb, cm = _t(gold["embedding"][:1]), _t(gold["contribution_map"][:1])
+    assert ((e["embedding"] - emb).abs().max() / emb.abs().max()).item() < 1e-4
+    assert torch.nn.functional.cosine_similarity(e["contribution_map"].flatten(1), cm.flatten(1)).min().item() > 0.9999
