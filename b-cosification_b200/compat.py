@@ -25,7 +25,9 @@ def install_as_bcos() -> None:
     alias("bcos")
     alias("bcos.common", BcosUtilMixin=explain.BcosUtilMixin, explanation_mode=explain.explanation_mode,
           gradient_to_image=explain.gradient_to_image)
-    alias("bcos.modules", BcosAttentionPool2d=getattr(modules, "BcosAttentionPool2d", None), **pub)
+    alias("bcos.modules", **pub)
+    alias("bcos.modules.bcosattnpool", BcosAttentionPool2d=modules.BcosAttentionPool2d)
+    alias("bcos.modules.norms.centered_norms", DetachableLayerNorm=modules.DetachableLayerNorm)
     alias("bcos.modules.common", DetachableModule=common.DetachableModule, BcosSequential=common.BcosSequential)
     alias("bcos.modules.bcosconv2d", BcosConv2d=bcosconv2d.BcosConv2d, NormedConv2d=bcosconv2d.NormedConv2d,
           BcosConv2dWithScale=bcosconv2d.BcosConv2dWithScale)

@@ -82,7 +82,6 @@ install_as_bcos()
 REF = %r
 sys.path.insert(0, REF)
 import bcos_b200.modules as M
-sys.modules['bcos.modules'].BcosAttentionPool2d = object
 for name, path in (('bcos.models', REF + '/bcos/models'), ('CLIP', REF + '/CLIP'), ('CLIP.clip', REF + '/CLIP/clip')):
     m = types.ModuleType(name); m.__path__ = [path]
     m.__spec__ = importlib.machinery.ModuleSpec(name, None, is_package=True); m.__spec__.submodule_search_locations = [path]
