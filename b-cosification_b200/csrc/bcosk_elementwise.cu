@@ -36,6 +36,13 @@ __device__ __forceinline__ void load8_planes(const T* ptr, int planes, int plane
     for (int i = 0; i < 8; ++i) f[i] += g[i];
   }
 }
+// compile-time single-plane variant: a bare 16-byte load, so unrolled callers can overlap many of them
+template <typename T, bool ONE>
+__device__ __forceinline__ void load8_pl(const T* ptr, int planes, int plane_stride, float (&f)[8]) {
+  if (ONE) unpack8<T>(__ldg(reinterpret_cast<const uint4*>(ptr)), f);
+  else load8_planes<T>(ptr, planes, plane_stride, f);
+}
+
 // split-store 8 channels into planes; f returns the stored (representable) value
 template <typename T>
 __device__ __forceinline__ void store8_planes(T* ptr, int planes, int plane_stride, float (&f)[8]) {
@@ -138,28 +145,39 @@ __global__ void input_prep_s2d_kernel(const SRC* __restrict__ x, int nb, int h, 
 // ------------------------------------------------------------------------------------------------
 // patch norm from per-pixel sums of squares
 // ------------------------------------------------------------------------------------------------
+// Block = 16 x 16 outputs of one image.  The (15*stride + k)^2 window of summed partial maps is staged in shared memory
+// (zero outside the image), then every thread adds its k x k taps from shared memory: no per-tap bounds checks or
+// 64-bit index arithmetic (the first version was instruction bound: 860 instructions per output for the 7x7 stem).
+constexpr int PN_TILE = 16;
 __global__ void patch_inv_norm_kernel(const float* __restrict__ sq, int parts, int nb, int h, int w, int kh, int kw,
                                       int stride, int pad, float eps_in, float eps_out, float* __restrict__ inv_norm,
                                       int op, int oq) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)nb * op * oq;
-  if (idx >= total) return;
-  const int q = (int)(idx % oq);
-  const int p = (int)((idx / oq) % op);
-  const int img = (int)(idx / ((long long)oq * op));
+  extern __shared__ float tile[];
+  const int img = blockIdx.z;
+  const int p0 = blockIdx.y * PN_TILE, q0 = blockIdx.x * PN_TILE;
+  const int th = (PN_TILE - 1) * stride + kh, tw = (PN_TILE - 1) * stride + kw;
+  const int y0 = p0 * stride - pad, x0 = q0 * stride - pad;
   const size_t part_stride = (size_t)nb * h * w;
-  float acc = 0.f;
-  for (int dy = 0; dy < kh; ++dy) {
-    const int y = p * stride - pad + dy;
-    if (y < 0 || y >= h) continue;
-    for (int dx = 0; dx < kw; ++dx) {
-      const int xx = q * stride - pad + dx;
-      if (xx < 0 || xx >= w) continue;
-      const size_t o = ((size_t)img * h + y) * w + xx;
-      for (int t = 0; t < parts; ++t) acc += __ldg(sq + t * part_stride + o);
+  const float* base = sq + (size_t)img * h * w;
+  for (int i = threadIdx.x; i < th * tw; i += blockDim.x) {
+    const int ty = i / tw, tx = i - ty * tw;
+    const int yy = y0 + ty, xx = x0 + tx;
+    float v = 0.f;
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+      const int o = yy * w + xx;
+      for (int t = 0; t < parts; ++t) v += __ldg(base + t * part_stride + o);
     }
+    tile[i] = v;
   }
-  inv_norm[idx] = 1.0f / (sqrtf(acc + eps_in) + eps_out);
+  __syncthreads();
+  const int lp = threadIdx.x / PN_TILE, lq = threadIdx.x % PN_TILE;
+  const int p = p0 + lp, q = q0 + lq;
+  if (p >= op || q >= oq) return;
+  float acc = 0.f;
+  const float* t0 = tile + (lp * stride) * tw + lq * stride;
+  for (int dy = 0; dy < kh; ++dy)
+    for (int dx = 0; dx < kw; ++dx) acc += t0[dy * tw + dx];
+  inv_norm[((size_t)img * op + p) * oq + q] = 1.0f / (sqrtf(acc + eps_in) + eps_out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -187,37 +205,55 @@ __global__ void pixel_sqsum_kernel(const T* __restrict__ x, long long rows, int 
 // average pooling (count_include_pad=True) forward / explain-backward
 // ------------------------------------------------------------------------------------------------
 // lanes_per_pix = min(32, c/8) (a power of two); a warp covers 32/lanes_per_pix output pixels.
-template <typename T>
-__global__ void avgpool_fwd_kernel(const T* __restrict__ x, int nb, int h, int w, int c, int planes, int k, int stride,
+template <typename T, int KT, bool ONE>
+__global__ void avgpool_fwd_kernel(const T* __restrict__ x, int nb, int h, int w, int c, int planes, int k_rt, int stride,
                                    int pad, T* __restrict__ y, int op, int oq, float* __restrict__ sq, int lpp) {
+  const int k = KT > 0 ? KT : k_rt;   // compile-time window => the tap loops unroll and their loads overlap
   const int lane = threadIdx.x & 31;
-  const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int img = blockIdx.y;
+  const unsigned warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int ppw = 32 / lpp;  // pixels per warp
-  const long long pix = warp_id * ppw + lane / lpp;
-  const long long total = (long long)nb * op * oq;
-  const bool valid = pix < total;
+  const unsigned ipix = warp_id * ppw + lane / lpp;          // pixel inside the image (32-bit math: no 64-bit divisions)
+  const bool valid = ipix < (unsigned)(op * oq);
+  const size_t pix = (size_t)img * op * oq + ipix;
   const int sub = lane % lpp;
   float sqacc = 0.f;
   if (valid) {
-    const int q = (int)(pix % oq);
-    const int p = (int)((pix / oq) % op);
-    const int img = (int)(pix / ((long long)oq * op));
+    const int p = (int)(ipix / (unsigned)oq);
+    const int q = (int)(ipix - (unsigned)p * oq);
     const float inv = 1.0f / (float)(k * k);
     const int ld = planes * c;
     for (int g = sub; g < c / 8; g += lpp) {
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      for (int dy = 0; dy < k; ++dy) {
-        const int yy = p * stride - pad + dy;
-        if (yy < 0 || yy >= h) continue;
-        for (int dx = 0; dx < k; ++dx) {
-          const int xx = q * stride - pad + dx;
-          if (xx < 0 || xx >= w) continue;
-          float f[8];
-          load8_planes<T>(x + (((size_t)img * h + yy) * w + xx) * ld + g * 8, planes, c, f);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      for (int dy = 0; dy < (KT > 0 ? KT : 1); ++dy) {
+#pragma unroll
+        for (int dx = 0; dx < (KT > 0 ? KT : 1); ++dx) {
+          if (KT > 0) {
+            const int yy = p * stride - pad + dy, xx = q * stride - pad + dx;
+            if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+              float f[8];
+              load8_pl<T, ONE>(x + (((size_t)img * h + yy) * w + xx) * ld + g * 8, planes, c, f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[i] += f[i];
+            }
+          }
+        }
+      }
+      if (KT == 0) {
+        for (int dy = 0; dy < k; ++dy) {
+          const int yy = p * stride - pad + dy;
+          if (yy < 0 || yy >= h) continue;
+          for (int dx = 0; dx < k; ++dx) {
+            const int xx = q * stride - pad + dx;
+            if (xx < 0 || xx >= w) continue;
+            float f[8];
+            load8_planes<T>(x + (((size_t)img * h + yy) * w + xx) * ld + g * 8, planes, c, f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += f[i];
+          }
         }
       }
 #pragma unroll
@@ -233,19 +269,19 @@ __global__ void avgpool_fwd_kernel(const T* __restrict__ x, int nb, int h, int w
   }
 }
 
-template <typename T>
+template <typename T, bool ONE>
 __global__ void avgpool_bwd_mul_kernel(const T* __restrict__ gy, int nb, int h, int w, int c, int planes, int k,
                                        int stride, int pad, int op, int oq, const void* __restrict__ gain, int gain_f32,
                                        T* __restrict__ gx) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cg = c / 8;
-  const long long total = (long long)nb * h * w * cg;
-  if (idx >= total) return;
-  const int g = (int)(idx % cg);
-  const long long pix = idx / cg;
-  const int xx = (int)(pix % w);
-  const int yy = (int)((pix / w) % h);
-  const int img = (int)(pix / ((long long)w * h));
+  const int img = blockIdx.y;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;     // (pixel, channel group) inside the image, 32-bit math
+  if (idx >= (unsigned)(h * w * cg)) return;
+  const unsigned ipix = idx / (unsigned)cg;
+  const int g = (int)(idx - ipix * cg);
+  const int yy = (int)(ipix / (unsigned)w);
+  const int xx = (int)(ipix - (unsigned)yy * w);
+  const size_t pix = (size_t)img * h * w + ipix;
   const int ld = planes * c;
   float acc[8];
 #pragma unroll
@@ -255,13 +291,29 @@ __global__ void avgpool_bwd_mul_kernel(const T* __restrict__ gy, int nb, int h, 
   const int p_hi = min(op - 1, (yy + pad) / stride);
   const int q_lo = max(0, (xx + pad - k + 1 + stride - 1) / stride);
   const int q_hi = min(oq - 1, (xx + pad) / stride);
-  for (int p = p_lo; p <= p_hi; ++p)
-    for (int q = q_lo; q <= q_hi; ++q) {
-      float f[8];
-      load8_planes<T>(gy + (((size_t)img * op + p) * oq + q) * ld + g * 8, planes, c, f);
+  if (p_hi - p_lo <= 1 && q_hi - q_lo <= 1) {
+    // at most 2 x 2 windows cover an input pixel (k <= 2 * stride): unrolled, the loads overlap
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += f[i];
-    }
+    for (int dp = 0; dp < 2; ++dp)
+#pragma unroll
+      for (int dq = 0; dq < 2; ++dq) {
+        const int p = p_lo + dp, q = q_lo + dq;
+        if (p <= p_hi && q <= q_hi) {
+          float f[8];
+          load8_pl<T, ONE>(gy + (((size_t)img * op + p) * oq + q) * ld + g * 8, planes, c, f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        }
+      }
+  } else {
+    for (int p = p_lo; p <= p_hi; ++p)
+      for (int q = q_lo; q <= q_hi; ++q) {
+        float f[8];
+        load8_planes<T>(gy + (((size_t)img * op + p) * oq + q) * ld + g * 8, planes, c, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      }
+  }
   const float inv = 1.0f / (float)(k * k);
   float gn[8];
   if (gain == nullptr) {
@@ -486,9 +538,13 @@ extern "C" int bcosk_patch_inv_norm(const float* sq, int32_t parts, int32_t nb, 
                                     int32_t kw, int32_t stride, int32_t pad, float eps_in, float eps_out, float* inv_norm,
                                     int32_t op, int32_t oq, void* stream) {
   if (!sq || !inv_norm || parts < 1) return set_error(BCOSK_EINVAL, "patch_inv_norm: bad argument");
-  const long long n = (long long)nb * op * oq;
-  patch_inv_norm_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(sq, parts, nb, h, w, kh, kw, stride, pad, eps_in,
-                                                                     eps_out, inv_norm, op, oq);
+  if (nb > 65535) return set_error(BCOSK_EUNSUPPORTED, "patch_inv_norm: batch too large for the grid");
+  const int th = (PN_TILE - 1) * stride + kh, tw = (PN_TILE - 1) * stride + kw;
+  const size_t smem = (size_t)th * tw * sizeof(float);
+  if (smem > 48 * 1024) return set_error(BCOSK_EUNSUPPORTED, "patch_inv_norm: window too large");
+  dim3 grid((oq + PN_TILE - 1) / PN_TILE, (op + PN_TILE - 1) / PN_TILE, nb);
+  patch_inv_norm_kernel<<<grid, PN_TILE * PN_TILE, smem, S(stream)>>>(sq, parts, nb, h, w, kh, kw, stride, pad, eps_in,
+                                                                        eps_out, inv_norm, op, oq);
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }
@@ -514,10 +570,19 @@ extern "C" int bcosk_avgpool_fwd(const void* x, int32_t nb, int32_t h, int32_t w
                                  void* stream) {
   const int lpp = lanes_per_pixel(c);
   if (!x || !y || lpp == 0) return set_error(BCOSK_EUNSUPPORTED, "avgpool_fwd: c/8 must be a power of two or a multiple of 32");
-  const long long pix = (long long)nb * op * oq;
+  if (nb > 65535) return set_error(BCOSK_EUNSUPPORTED, "avgpool_fwd: batch too large for the grid");
+  const long long pix = (long long)op * oq;                       // per image; grid.y walks the images
   const long long warps = (pix + (32 / lpp) - 1) / (32 / lpp);
-  BCOSK_DTYPE_SWITCH(dtype, avgpool_fwd_kernel<T><<<blocks_for(warps, 8), 256, 0, S(stream)>>>(
+  const dim3 pgrid(blocks_for(warps, 8), nb);
+#define BCOSK_POOL_FWD(KT_, ONE_)                                                                                      \
+  BCOSK_DTYPE_SWITCH(dtype, avgpool_fwd_kernel<T, KT_, ONE_><<<pgrid, 256, 0, S(stream)>>>(                                \
       reinterpret_cast<const T*>(x), nb, h, w, c, planes, k, stride, pad, reinterpret_cast<T*>(y), op, oq, sq, lpp);)
+  if (k == 3 && planes == 1) { BCOSK_POOL_FWD(3, true) }
+  else if (k == 3) { BCOSK_POOL_FWD(3, false) }
+  else if (k == 2 && planes == 1) { BCOSK_POOL_FWD(2, true) }
+  else if (k == 2) { BCOSK_POOL_FWD(2, false) }
+  else { BCOSK_POOL_FWD(0, false) }
+#undef BCOSK_POOL_FWD
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }
@@ -526,9 +591,16 @@ extern "C" int bcosk_avgpool_bwd_mul(const void* gy, int32_t nb, int32_t h, int3
                                      int32_t stride, int32_t pad, int32_t op, int32_t oq, const void* gain, int32_t gain_f32,
                                      void* gx, int32_t dtype, void* stream) {
   if (!gy || !gx || c % 8) return set_error(BCOSK_EINVAL, "avgpool_bwd_mul: bad argument");
-  const long long n = (long long)nb * h * w * (c / 8);
-  BCOSK_DTYPE_SWITCH(dtype, avgpool_bwd_mul_kernel<T><<<blocks_for(n, 256), 256, 0, S(stream)>>>(
-      reinterpret_cast<const T*>(gy), nb, h, w, c, planes, k, stride, pad, op, oq, gain, gain_f32, reinterpret_cast<T*>(gx));)
+  if (nb > 65535) return set_error(BCOSK_EUNSUPPORTED, "avgpool_bwd_mul: batch too large for the grid");
+  const long long n = (long long)h * w * (c / 8);
+  const dim3 bgrid(blocks_for(n, 256), nb);
+  if (planes == 1) {
+    BCOSK_DTYPE_SWITCH(dtype, avgpool_bwd_mul_kernel<T, true><<<bgrid, 256, 0, S(stream)>>>(
+        reinterpret_cast<const T*>(gy), nb, h, w, c, planes, k, stride, pad, op, oq, gain, gain_f32, reinterpret_cast<T*>(gx));)
+  } else {
+    BCOSK_DTYPE_SWITCH(dtype, avgpool_bwd_mul_kernel<T, false><<<bgrid, 256, 0, S(stream)>>>(
+        reinterpret_cast<const T*>(gy), nb, h, w, c, planes, k, stride, pad, op, oq, gain, gain_f32, reinterpret_cast<T*>(gx));)
+  }
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }

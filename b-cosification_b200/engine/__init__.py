@@ -1,2 +1,2 @@
 """Fused execution plans over the C-ABI kernels (CUDA only; no fallback)."""
-from .resnet import ResNetPlan  # noqa: F401
+from .resnet import PipelinedExplainer, ResNetPlan  # noqa: F401

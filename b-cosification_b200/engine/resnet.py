@@ -192,3 +192,64 @@ class ResNetPlan(PlanBase):
         if self.grad6 is not None:
             out["dynamic_linear_weights"] = self.grad6
         return out
+
+
+class PipelinedExplainer:
+    """Public end-to-end API for streams of host batches: `submit(images)` returns a ticket, `result(ticket)` the pinned
+    host tensors.  Host->device copies, the CUDA-graph replay and device->host copies of consecutive batches overlap on
+    three streams (copy-in, compute, copy-out) with double-buffered staging, so the steady-state cost per batch is
+    max(compute, PCIe) instead of their sum.  Every batch still pays its own H2D and D2H inside the pipeline."""
+
+    def __init__(self, plan: ResNetPlan, depth: int = 2):
+        assert plan.with_explain
+        if plan._graph_all is None:
+            plan.capture()
+        self.plan, self.depth = plan, depth
+        dev = plan.device
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.s_compute = torch.cuda.current_stream(dev)
+        self.d_in = [torch.empty_like(plan.x_in) for _ in range(depth)]
+        self.d_logits = [torch.empty_like(plan.logits) for _ in range(depth)]
+        self.d_cmap = [torch.empty_like(plan.cmap) for _ in range(depth)]
+        self.h_logits = [torch.empty(plan.logits.shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.h_cmap = [torch.empty(plan.cmap.shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_done = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_free = [torch.cuda.Event() for _ in range(depth)]     # staging input slot consumed by the compute stream
+        self.count = 0
+
+    def submit(self, host_images: Tensor) -> int:
+        i = self.count
+        k = i % self.depth
+        if i >= self.depth:
+            self.ev_out[k].synchronize()          # results of ticket i-depth have left the staging slot
+        with torch.cuda.stream(self.s_in):
+            if i >= self.depth:
+                self.s_in.wait_event(self.ev_free[k])
+            self.d_in[k].copy_(host_images, non_blocking=True)
+            self.ev_in[k].record(self.s_in)
+        self.s_compute.wait_event(self.ev_in[k])
+        self.plan.x_in.copy_(self.d_in[k], non_blocking=True)          # device-to-device, then the slot is free again
+        self.ev_free[k].record(self.s_compute)
+        self.plan.replay_all()
+        self.d_logits[k].copy_(self.plan.logits, non_blocking=True)
+        self.d_cmap[k].copy_(self.plan.cmap, non_blocking=True)
+        self.ev_done[k].record(self.s_compute)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_done[k])
+            self.h_logits[k].copy_(self.d_logits[k], non_blocking=True)
+            self.h_cmap[k].copy_(self.d_cmap[k], non_blocking=True)
+            self.ev_out[k].record(self.s_out)
+        self.count += 1
+        return i
+
+    def result(self, ticket: int) -> Dict[str, Tensor]:
+        k = ticket % self.depth
+        assert self.count - ticket <= self.depth, "result already overwritten by a later submit"
+        self.ev_out[k].synchronize()
+        return {"logits": self.h_logits[k], "contribution_map": self.h_cmap[k]}
+
+    def drain(self) -> None:
+        for e in self.ev_out[: min(self.count, self.depth)]:
+            e.synchronize()

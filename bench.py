@@ -179,23 +179,28 @@ def main():
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
 
     # ---------------- end to end through the public API: pinned host images in, logits + maps out ----------------
-    def e2e_step():
-        out = plan.explain(h_in)                               # H2D copy + graph replay
-        h_logits.copy_(out["logits"], non_blocking=True)       # D2H results
-        h_cmap.copy_(out["contribution_map"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
-    for _ in range(W):
-        e2e_step()
+    # PipelinedExplainer: every step copies its own batch host->device and its own results device->host (pinned memory);
+    # copies of step i+1 / i-1 overlap the compute of step i.  The timed region ends when the last result is on the host.
+    from bcos_b200.engine import PipelinedExplainer
+    pipe = PipelinedExplainer(plan)
+    h_ins = [h_in, h_in.clone().pin_memory()]
+    for i in range(W):
+        pipe.submit(h_ins[i % 2])
+    pipe.drain()
     barrier()
     w0 = time.time()
     e0.record()
-    for _ in range(K):
-        e2e_step()
+    last = 0
+    for i in range(K):
+        last = pipe.submit(h_ins[i % 2])
+    res_last = pipe.result(last)
+    pipe.drain()
+    t_host_done = time.time()
     e1.record()
     barrier()
     windows.append((w0, time.time()))
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    ms_e2e = max_over_ranks((t_host_done - w0) * 1e3)        # host clock: includes the final device->host copies
+    h_logits, h_cmap = res_last["logits"], res_last["contribution_map"]
     sampler.stop()
 
     # ---------------- per-launch timing (eager launches, CUDA events on the launching stream) ----------------
@@ -238,7 +243,8 @@ def main():
         "e2e": {"value": imgs_total / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(h_in.numel() * h_in.element_size()),
                 "d2h_bytes_per_step": int(h_logits.numel() * 4 + h_cmap.numel() * 4),
-                "api": "ResNetPlan.explain(pinned uint8 images) -> logits, contribution maps copied to pinned host memory"},
+                "api": "PipelinedExplainer.submit(pinned uint8 images) / .result(): per-step H2D + CUDA-graph replay + D2H of logits and "
+                       "contribution maps, copies overlapped with the neighbouring steps' compute"},
         "gpu_launches": plan.num_launches() * K,
         "launches_per_step": plan.num_launches(),
         "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"],
