@@ -131,6 +131,7 @@ struct IgemmAux {
   int tma_in2;   // explain: the extra gradient `add` (dense, same rows as y) prefetched into the slot before it
   int tma_out1;  // primary output y staged in slot 0 and written with TMA
   int tma_out2;  // forward: gain, explain: out2 - staged in slot 1 and written with TMA
+  int order;     // persistent kernel: 0 = tiles strided over the grid, 1 = a CTA walks all n tiles of one row block
 };
 
 // Shared-memory tiles of the TMA epilogue: [BN/64 boxes][128 rows][128 bytes], 16-byte units XOR-swizzled by row
@@ -836,6 +837,17 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 //                tiles in shared memory (double buffered); one thread issues the TMA stores of tile i, whose
 //                shared-memory reads overlap the math of tile i+1.  One named barrier per tile.
 // =================================================================================================
+// i-th tile of this CTA, or -1 past the end.  order 1 keeps the n tiles of a row block on one CTA back to back, so the
+// 128-byte segments of each output row reach L2 together and the A tile is fetched once.
+__device__ __forceinline__ int persist_tile(int i, int n_tiles, int m_tiles, int order) {
+  if (order == 0) {
+    const int t = blockIdx.x + i * gridDim.x;
+    return t < m_tiles * n_tiles ? t : -1;
+  }
+  const int g = blockIdx.x + (i / n_tiles) * gridDim.x;
+  return g < m_tiles ? g * n_tiles + i % n_tiles : -1;
+}
+
 constexpr int P_THREADS = 384;
 constexpr int P_EPI_THREADS = 256;
 constexpr int P_BN = 64;
@@ -886,7 +898,6 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
   const int n_tiles = (p.n + BN - 1) / BN;
   const int M = p.a_nb * p.op * p.oq;
   const int m_tiles = (M + BM - 1) / BM;
-  const int total_tiles = m_tiles * n_tiles;
   const int chunks_per_stage = STAGE_K / p.kch;
   const int num_iters = (p.num_segs * p.num_taps * p.chunks_per_tap) / chunks_per_stage;
   const bool use_in_tile = aux.tma_in != 0;
@@ -926,7 +937,7 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       const uint32_t b_chunk_bytes = BN * p.kch * 2;
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int it = 0, t; (t = persist_tile(it, n_tiles, m_tiles, aux.order)) >= 0; ++it) {
         const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
         const int img = m0 / opq;
         const int rem = m0 - img * opq;
@@ -964,7 +975,7 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       int stage = 0;
       uint32_t phase = 0;
       uint32_t i = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      for (int t; (t = persist_tile((int)i, n_tiles, m_tiles, aux.order)) >= 0; ++i) {
         const uint32_t buf = i & 1u;
         mbar_wait(&acc_empty_bar[buf], ((i >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
@@ -992,7 +1003,7 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
     // ===================== epilogue-input producer =====================
     if (lane == 0 && use_in_tile) {
       uint32_t i = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      for (int t; (t = persist_tile((int)i, n_tiles, m_tiles, aux.order)) >= 0; ++i) {
         const uint32_t buf = i & 1u;
         const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
         mbar_wait(&in_empty_bar[buf], ((i >> 1) & 1u) ^ 1u);
@@ -1005,7 +1016,7 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
     // ===================== row-side producer =====================
     uint32_t i = 0;
     const int opq = p.op * p.oq;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+    for (int t; (t = persist_tile((int)i, n_tiles, m_tiles, aux.order)) >= 0; ++i) {
       const uint32_t buf = i & 1u;
       const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
       mbar_wait(&side_empty_bar[buf], ((i >> 1) & 1u) ^ 1u);
@@ -1099,7 +1110,7 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
     const bool want_sq = MODE == BCOSK_MODE_FWD && p.sq_out != nullptr;
     const int opq = p.op * p.oq;
     uint32_t i = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+    for (int t; (t = persist_tile((int)i, n_tiles, m_tiles, aux.order)) >= 0; ++i) {
       const uint32_t buf = i & 1u;
       const uint32_t par = (i >> 1) & 1u;
       const int tile_n = t % n_tiles;
@@ -1257,7 +1268,7 @@ static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const
 static int g_num_sms = 0;
 // Measured on B200 (profiles/r01_schedule_ab.md): per-tile + 3 CTAs/SM and the persistent kernel reach the same
 // ~4 TB/s on the bandwidth-bound launches; the per-tile schedule is the default.
-static bool g_persistent_enabled = false;
+static int g_persistent_enabled = 0;   // 0 off, 1 tiles strided over the grid, 2 row-block order
 static bool g_light_enabled = true;
 
 template <int MODE>
@@ -1357,7 +1368,7 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
   if (p.hp_accum && bn > 64) return set_error(BCOSK_EINVAL, "igemm: hp_accum needs block_n <= 64");
   p.block_n = bn;
   LaunchMaps mp;
-  IgemmAux aux;
+  IgemmAux aux{};
   rc = make_maps(p, bn, &mp, &aux);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1366,7 +1377,10 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
   case BN_:                                                                                         \
     return p.mode == BCOSK_MODE_FWD ? launch_igemm<BN_, BCOSK_MODE_FWD, false>(mp, p, aux, st)      \
                                     : launch_igemm<BN_, BCOSK_MODE_EXPLAIN, false>(mp, p, aux, st);
-  if (!p.hp_accum && g_persistent_enabled && bn == 64) {
+  if (p.sched < 0 || p.sched > 3) return set_error(BCOSK_EINVAL, "igemm: sched must be 0..3");
+  const int persistent = p.sched == 0 ? g_persistent_enabled : p.sched - 1;   // 0 per tile, 1 strided, 2 row blocks
+  if (!p.hp_accum && persistent && bn == 64) {
+    aux.order = persistent == 2 ? 1 : 0;
     return p.mode == BCOSK_MODE_FWD ? launch_persistent<BCOSK_MODE_FWD>(mp, p, aux, st)
                                     : launch_persistent<BCOSK_MODE_EXPLAIN>(mp, p, aux, st);
   }
@@ -1395,8 +1409,8 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
 }
 
 extern "C" int bcosk_set_persistent(int32_t enabled) {
-  const int prev = g_persistent_enabled ? 1 : 0;
-  g_persistent_enabled = enabled != 0;
+  const int prev = g_persistent_enabled;
+  g_persistent_enabled = enabled;
   return prev;
 }
 

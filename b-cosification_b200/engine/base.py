@@ -111,6 +111,7 @@ class PlanBase:
     # launches whose K loop has at most this many 64-deep stages are bandwidth bound: they use 64-wide tiles, which
     # the library runs with 3 CTAs per SM (more bytes in flight); 0 disables
     light_k_iters = 4
+    autotune_default = True          # capture() measures the per-launch schedule first (see autotune)
     fold_bn = True   # fold sqrt(BN multiplier) into the conv weights when every multiplier is positive and there is no bias
 
     def _block_n(self, n: int, k_iters: int = 1 << 30) -> int:
@@ -239,9 +240,49 @@ class PlanBase:
         self._require_gpu()
         O.run_ops(self.bwd_ops)
 
-    def capture(self) -> None:
+    def autotune(self, reps: int = 5) -> dict:
+        """Pick the schedule (include/bcosk.h `sched`) of every 64-wide tensor-core launch by measuring it in place.
+
+        The three schedules give bit-identical outputs (tests/test_kernels_gpu.py); which is fastest depends on N, K and
+        the epilogue streams (measured: profiles/r01_schedule_ab.md), so it is decided per launch, once, before capture.
+        Returns {launch name: chosen sched}.
+        """
+        self._require_gpu()
+        self.run_forward()
+        if self.with_explain:
+            self.run_explain()
+        torch.cuda.synchronize()
+        chosen = {}
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for op in self.fwd_ops + (self.bwd_ops if self.with_explain else []):
+            if not isinstance(op, O.IgemmOp) or op.hp_accum or op.resolved_block_n() != 64:
+                continue
+            best, best_t = 1, float("inf")
+            for sched in (1, 2, 3):
+                if sched == 3 and op.n <= 64:
+                    continue                      # a single n tile: same as 2
+                op.sched = sched
+                op.run()
+                ts = []
+                for _ in range(reps):
+                    ev[0].record()
+                    op.run()
+                    ev[1].record()
+                    ev[1].synchronize()
+                    ts.append(ev[0].elapsed_time(ev[1]))
+                t = sorted(ts)[len(ts) // 2]
+                if t < best_t * 0.98:             # prefer the simpler schedule on a tie
+                    best, best_t = sched, t
+            op.sched = best
+            chosen[op.name] = best
+        self.schedules = chosen
+        return chosen
+
+    def capture(self, autotune: Optional[bool] = None) -> None:
         """Capture forward and forward+explain as CUDA graphs (kernel parameters incl. TMA descriptors are baked in)."""
         self._require_gpu()
+        if (self.autotune_default if autotune is None else autotune) and not self.hp_accum:
+            self.autotune()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

@@ -69,6 +69,7 @@ class IgemmOp:
     algo_flops: float = 0.0
     a_dense_frac: float = 1.0
     hp_accum: bool = False           # per-stage TMEM accumulators summed in registers (parity mode)
+    sched: int = 0                   # include/bcosk.h `sched`: 0 default, 1 per tile, 2 persistent, 3 persistent row blocks
 
     # ---- derived ----
     @property
@@ -180,6 +181,7 @@ class IgemmOp:
             p.mask2 = self.mask2.data_ptr()
             p.mask2_ld = self.mask2.shape[-1]
         p.hp_accum = int(self.hp_accum)
+        p.sched = int(self.sched)
         return p
 
     def run(self) -> None:

@@ -121,6 +121,12 @@ typedef struct bcosk_igemm_params {
    *      The tensor core truncates when aligning addends to a large running sum (measured: relative error ~K*2^-26,
    *      biased), which random-init deep B-cos nets amplify 10^2-10^3 x. */
   int32_t hp_accum;
+  /* ---- schedule of a block_n == 64 launch (ignored otherwise and with hp_accum; results do not depend on it):
+   *      0 = library default (see bcosk_set_persistent / bcosk_set_light), 1 = one CTA per tile,
+   *      2 = persistent CTAs, tiles strided over the grid, 3 = persistent CTAs, each walks all n tiles of one
+   *      128-row block back to back (the segments of an output row reach L2 together).  The host plan measures the
+   *      three per launch once (engine/base.py PlanBase.autotune) - which wins depends on N/K and the epilogue streams. */
+  int32_t sched;
 } bcosk_igemm_params;
 
 int bcosk_igemm(const bcosk_igemm_params* p, void* stream);

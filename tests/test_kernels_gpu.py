@@ -202,7 +202,7 @@ def test_persistent_and_per_tile_schedules_agree(bcosk_lib):
     g = torch.Generator().manual_seed(21)
     nb, h, cin, cout = 4, 28, 128, 256
     outs = []
-    for persistent in (1, 0):
+    for persistent in (2, 1, 0):    # 2 = row-block tile order, 1 = tiles strided over the grid, 0 = one CTA per tile
         prev = bcosk_lib.bcosk_set_persistent(persistent)
         try:
             gg = torch.Generator().manual_seed(21)
@@ -220,11 +220,12 @@ def test_persistent_and_per_tile_schedules_agree(bcosk_lib):
             outs.append([t.cpu() for t in (dops[-1].y, dops[-1].gain, dops[-1].maskbits, dops[-1].sq_out)])
         finally:
             bcosk_lib.bcosk_set_persistent(prev)
-    for k, (a, b) in enumerate(zip(*outs)):
-        if k == 3:      # sums of squares: the persistent kernel adds two half-row partials (different rounding order)
-            assert torch.allclose(a, b, rtol=1e-5, atol=0)
-        else:
-            assert torch.equal(a, b)
+    for other in outs[:-1]:
+        for k, (a, b) in enumerate(zip(other, outs[-1])):
+            if k == 3:      # sums of squares: the persistent kernel adds two half-row partials (different rounding order)
+                assert torch.allclose(a, b, rtol=1e-5, atol=0)
+            else:
+                assert torch.equal(a, b)
 
 
 def test_elementwise_kernels(bcosk_lib):
