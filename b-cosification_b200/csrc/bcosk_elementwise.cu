@@ -332,6 +332,132 @@ __global__ void avgpool_bwd_mul_kernel(const T* __restrict__ gy, int nb, int h, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row-staged variants (single plane, 16-bit, c/8 a power of two <= 32).  One block per (image, output row) resp.
+// (image, input row): whole rows are fetched into shared memory with 1-D bulk copies, so a block has tens of KB in
+// flight from a single instruction instead of one 16-byte load per thread and tap (the direct kernels above were
+// latency bound at 1.3 / 2.4 TB/s; profiles/r01_pool_kernels.md).  Same arithmetic order as the direct kernels.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+avgpool_fwd_rows_kernel(const T* __restrict__ x, int h, int w, int c, int k, int stride, int pad, T* __restrict__ y,
+                        int op, int oq, float* __restrict__ sq) {
+  extern __shared__ __align__(128) uint8_t pool_smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int img = blockIdx.y, p = blockIdx.x;
+  const uint32_t row_bytes = (uint32_t)w * c * sizeof(T);
+  const int y0 = p * stride - pad;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+    uint32_t total = 0;
+    for (int dy = 0; dy < k; ++dy)
+      if (y0 + dy >= 0 && y0 + dy < h) total += row_bytes;
+    mbar_arrive_expect_tx(&bar, total);
+    for (int dy = 0; dy < k; ++dy) {
+      const int yy = y0 + dy;
+      if (yy >= 0 && yy < h) bulk_load_1d(pool_smem + dy * row_bytes, x + ((size_t)img * h + yy) * w * c, row_bytes, &bar);
+    }
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  const int cg = c / 8;
+  const float inv = 1.0f / (float)(k * k);
+  const int items = oq * cg;
+  const int items_pad = (items + 31) & ~31;
+  for (int it = threadIdx.x; it < items_pad; it += blockDim.x) {
+    const bool valid = it < items;
+    const int q = it / cg, g = it - q * cg;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    float sqacc = 0.f;
+    if (valid) {
+      for (int dy = 0; dy < k; ++dy) {
+        if (y0 + dy < 0 || y0 + dy >= h) continue;
+        for (int dx = 0; dx < k; ++dx) {
+          const int xx = q * stride - pad + dx;
+          if (xx < 0 || xx >= w) continue;
+          float f[8];
+          unpack8<T>(*reinterpret_cast<const uint4*>(pool_smem + dy * row_bytes + ((size_t)xx * c + g * 8) * sizeof(T)), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] *= inv;
+      store8_planes<T>(y + (((size_t)img * op + p) * oq + q) * c + g * 8, 1, c, acc);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sqacc = fmaf(acc[i], acc[i], sqacc);
+    }
+    if (sq != nullptr) {
+      for (int o = cg >> 1; o > 0; o >>= 1) sqacc += __shfl_xor_sync(0xffffffffu, sqacc, o);
+      if (valid && g == 0) sq[((size_t)img * op + p) * oq + q] = sqacc;
+    }
+  }
+}
+
+// gx[yy, :, :] = gain[yy, :, :] * (sum of the <= 2 x 2 output gradients whose windows cover the pixel) / k^2, staged and
+// written back as one row.
+template <typename T>
+__global__ void __launch_bounds__(256)
+avgpool_bwd_mul_rows_kernel(const T* __restrict__ gy, int h, int w, int c, int k, int stride, int pad, int op, int oq,
+                            const T* __restrict__ gain, T* __restrict__ gx) {
+  extern __shared__ __align__(128) uint8_t pool_smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int img = blockIdx.y, yy = blockIdx.x;
+  const uint32_t row_bytes = (uint32_t)w * c * sizeof(T);
+  const uint32_t grow_bytes = (uint32_t)oq * c * sizeof(T);
+  const int p_lo = max(0, (yy + pad - k + 1 + stride - 1) / stride);
+  const int p_hi = min(op - 1, (yy + pad) / stride);
+  uint8_t* s_gain = pool_smem;                 // [w][c], overwritten with the result
+  uint8_t* s_gy = pool_smem + row_bytes;       // [2][oq][c]
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(&bar, row_bytes + (uint32_t)(p_hi - p_lo + 1) * grow_bytes);
+    bulk_load_1d(s_gain, gain + ((size_t)img * h + yy) * w * c, row_bytes, &bar);
+    for (int p = p_lo; p <= p_hi; ++p)
+      bulk_load_1d(s_gy + (p - p_lo) * grow_bytes, gy + ((size_t)img * op + p) * oq * c, grow_bytes, &bar);
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  const int cg = c / 8;
+  const float inv = 1.0f / (float)(k * k);
+  for (int it = threadIdx.x; it < w * cg; it += blockDim.x) {
+    const int xx = it / cg, g = it - xx * cg;
+    const int q_lo = max(0, (xx + pad - k + 1 + stride - 1) / stride);
+    const int q_hi = min(oq - 1, (xx + pad) / stride);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int p = p_lo; p <= p_hi; ++p)
+      for (int q = q_lo; q <= q_hi; ++q) {
+        float f[8];
+        unpack8<T>(*reinterpret_cast<const uint4*>(s_gy + (p - p_lo) * grow_bytes + ((size_t)q * c + g * 8) * sizeof(T)), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      }
+    uint4* slot = reinterpret_cast<uint4*>(s_gain + ((size_t)xx * c + g * 8) * sizeof(T));
+    float gn[8];
+    unpack8<T>(*slot, gn);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= inv * gn[i];
+    uint4 o;
+    o.x = Cvt<T>::pack2(acc[0], acc[1]);
+    o.y = Cvt<T>::pack2(acc[2], acc[3]);
+    o.z = Cvt<T>::pack2(acc[4], acc[5]);
+    o.w = Cvt<T>::pack2(acc[6], acc[7]);
+    *slot = o;
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bulk_store_1d(gx + ((size_t)img * h + yy) * w * c, s_gain, row_bytes);
+    tma_store_commit_and_wait_read();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // classifier tail: GAP + logit layer + argmax (one block per image)
 // ------------------------------------------------------------------------------------------------
 __global__ void gap_logits_kernel(const float* __restrict__ fc, int npix, int ncls, float inv_temp, float bias,
@@ -571,6 +697,16 @@ extern "C" int bcosk_avgpool_fwd(const void* x, int32_t nb, int32_t h, int32_t w
   const int lpp = lanes_per_pixel(c);
   if (!x || !y || lpp == 0) return set_error(BCOSK_EUNSUPPORTED, "avgpool_fwd: c/8 must be a power of two or a multiple of 32");
   if (nb > 65535) return set_error(BCOSK_EUNSUPPORTED, "avgpool_fwd: batch too large for the grid");
+  {
+    // row-staged kernel: single plane, <= 32 lanes per pixel, k full input rows fit the default shared-memory window
+    const size_t smem = (size_t)k * w * c * 2;
+    if (planes == 1 && c / 8 <= 32 && (c / 8 & (c / 8 - 1)) == 0 && c % 8 == 0 && smem <= 48 * 1024 && op <= 65535) {
+      BCOSK_DTYPE_SWITCH(dtype, avgpool_fwd_rows_kernel<T><<<dim3(op, nb), 256, smem, S(stream)>>>(
+          reinterpret_cast<const T*>(x), h, w, c, k, stride, pad, reinterpret_cast<T*>(y), op, oq, sq);)
+      BCOSK_CUDA_CHECK(cudaGetLastError());
+      return BCOSK_OK;
+    }
+  }
   const long long pix = (long long)op * oq;                       // per image; grid.y walks the images
   const long long warps = (pix + (32 / lpp) - 1) / (32 / lpp);
   const dim3 pgrid(blocks_for(warps, 8), nb);
@@ -592,6 +728,17 @@ extern "C" int bcosk_avgpool_bwd_mul(const void* gy, int32_t nb, int32_t h, int3
                                      void* gx, int32_t dtype, void* stream) {
   if (!gy || !gx || c % 8) return set_error(BCOSK_EINVAL, "avgpool_bwd_mul: bad argument");
   if (nb > 65535) return set_error(BCOSK_EUNSUPPORTED, "avgpool_bwd_mul: batch too large for the grid");
+  {
+    // row-staged kernel: single plane, 16-bit gain, at most two output rows cover an input row (k <= 2 * stride)
+    const size_t smem = ((size_t)w + 2 * (size_t)oq) * c * 2;
+    if (planes == 1 && gain != nullptr && !gain_f32 && k <= 2 * stride && smem <= 48 * 1024 && h <= 65535) {
+      BCOSK_DTYPE_SWITCH(dtype, avgpool_bwd_mul_rows_kernel<T><<<dim3(h, nb), 256, smem, S(stream)>>>(
+          reinterpret_cast<const T*>(gy), h, w, c, k, stride, pad, op, oq, reinterpret_cast<const T*>(gain),
+          reinterpret_cast<T*>(gx));)
+      BCOSK_CUDA_CHECK(cudaGetLastError());
+      return BCOSK_OK;
+    }
+  }
   const long long n = (long long)h * w * (c / 8);
   const dim3 bgrid(blocks_for(n, 256), nb);
   if (planes == 1) {
