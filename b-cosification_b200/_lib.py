@@ -146,10 +146,18 @@ def _is_u8(x) -> bool:
     return False
 
 
+def _pixel_pitches(t):
+    """(row pitch, image pitch) in pixels of an NHWC tensor or view (pixels themselves must be contiguous)."""
+    assert t.stride(3) == 1 and t.stride(2) == t.shape[3], "pixels of an NHWC view must be contiguous"
+    assert t.stride(1) % t.stride(2) == 0 and t.stride(0) % t.stride(2) == 0
+    return t.stride(1) // t.stride(2), t.stride(0) // t.stride(2)
+
+
 def input_prep_s2d(x, mean6, inv_std6, out, cp, planes, dtype, sq) -> None:
     nb, _, h, w = x.shape
     fn = load().bcosk_input_prep_s2d_u8 if _is_u8(x) else load().bcosk_input_prep_s2d
-    check(fn(_p(x), nb, h, w, _f6(mean6), _f6(inv_std6), _p(out), cp, planes, dtype, _p(sq), _stream()),
+    rp, ip = _pixel_pitches(out)
+    check(fn(_p(x), nb, h, w, _f6(mean6), _f6(inv_std6), _p(out), cp, planes, dtype, _p(sq), rp, ip, _stream()),
           "bcosk_input_prep_s2d")
 
 
@@ -169,8 +177,9 @@ def avgpool_fwd(x, nb, h, w, c, planes, k, stride, pad, y, op, oq, dtype, sq) ->
 
 
 def avgpool_bwd_mul(gy, nb, h, w, c, planes, k, stride, pad, op, oq, gain, gain_f32, gx, dtype) -> None:
+    rp, ip = _pixel_pitches(gx)
     check(load().bcosk_avgpool_bwd_mul(_p(gy), nb, h, w, c, planes, k, stride, pad, op, oq, _p(gain), int(gain_f32), _p(gx),
-                                       dtype, _stream()), "bcosk_avgpool_bwd_mul")
+                                       dtype, rp, ip, _stream()), "bcosk_avgpool_bwd_mul")
 
 
 def gap_logits(fc, nb, npix, ncls, inv_temp, bias, logits, pred) -> None:

@@ -101,6 +101,33 @@ int make_tiled_map_2d(CUtensorMap* map, const void* base, long long cols, long l
   return BCOSK_OK;
 }
 
+// General tiled map (up to 3-D) with explicit byte strides; elem_bytes 2 (16-bit) or 4 (fp32).
+int make_tiled_map_nd(CUtensorMap* map, const void* base, int elem_bytes, int rank, const long long* dims,
+                      const long long* strides_bytes, const int* box, int swizzle_bytes) {
+  int rc = resolve_driver();
+  if (rc) return rc;
+  if (rank < 2 || rank > 3) return set_error(BCOSK_EINVAL, "tiled map: rank");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(BCOSK_EINVAL, "tiled map: base not 16B aligned");
+  cuuint64_t d[3], st[2];
+  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    d[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    if (strides_bytes[i] % 16 != 0) return set_error(BCOSK_EINVAL, "tiled map: stride not a multiple of 16 bytes");
+    st[i] = (cuuint64_t)strides_bytes[i];
+  }
+  CUresult r = g_encode_tiled(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                              (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              swizzle_enum(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(BCOSK_ECUDA, "cuTensorMapEncodeTiled (rank %d) failed: CUresult %d (dims %lld %lld %lld box %d %d %d)", rank,
+                     (int)r, dims[0], dims[1], rank > 2 ? dims[2] : 0ll, box[0], box[1], rank > 2 ? box[2] : 0);
+  return BCOSK_OK;
+}
+
 }  // namespace bcosk
 
 extern "C" const char* bcosk_last_error(void) { return bcosk::g_err; }

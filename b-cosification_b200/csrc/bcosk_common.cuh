@@ -99,6 +99,11 @@ __device__ __forceinline__ void tma_store_2d_addr(const void* desc, uint32_t sme
                : "memory");
 }
 // close the bulk group and wait until the TMA unit has finished READING shared memory (stores may still be in flight)
+__device__ __forceinline__ void tma_store_3d_addr(const void* desc, uint32_t smem_addr, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(desc), "r"(smem_addr),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit_and_wait_read() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -175,6 +180,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc_kmajor(uint32_t smem_addr, ui
   d |= layout << 61;
   return d;
 }
+// A tile may start at any ROW of a larger swizzled buffer (start address = base + r * row_bytes, base 1024-aligned):
+// the tensor core, like the TMA unit, derives the swizzle phase from the absolute shared-memory address, so the same
+// descriptor form is correct and bits [49,52) ("base offset") stay 0 (measured: scripts/exp, tests flat_*; setting
+// them to (addr >> 7) & 7 reads the wrong rows).
 // kind::f16 instruction descriptor: fp32 accumulate, A/B both K-major, `fmt` 0 = fp16, 1 = bf16.
 // Bits: [4,6) c_format=1 | [7,10) a_format | [10,13) b_format | 15 a_major=0 | 16 b_major=0 | [17,23) N>>3 | [24,29) M>>4.
 __host__ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t fmt, uint32_t M, uint32_t N) {

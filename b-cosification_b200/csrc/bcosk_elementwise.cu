@@ -99,7 +99,7 @@ __device__ __forceinline__ void load_patch6<uint8_t>(const uint8_t* __restrict__
 
 template <typename T, typename SRC>
 __global__ void input_prep_s2d_kernel(const SRC* __restrict__ x, int nb, int h, int w, Norm6 nm, T* __restrict__ out,
-                                      int cp, int planes, float* __restrict__ sq) {
+                                      int cp, int planes, float* __restrict__ sq, int row_pitch, int img_pitch) {
   const int h2 = h >> 1, w2 = w >> 1;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)nb * h2 * w2) return;
@@ -113,7 +113,7 @@ __global__ void input_prep_s2d_kernel(const SRC* __restrict__ x, int nb, int h, 
   for (int d = 0; d < 4; ++d)
 #pragma unroll
     for (int c = 0; c < 6; ++c) v[d * 6 + c] = (v[d * 6 + c] - nm.mean[c]) * nm.inv_std[c];
-  T* dst = out + (size_t)idx * ((size_t)planes * cp);
+  T* dst = out + ((size_t)img * img_pitch + (size_t)r * row_pitch + s) * ((size_t)planes * cp);
   float st[24];
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
@@ -272,7 +272,7 @@ __global__ void avgpool_fwd_kernel(const T* __restrict__ x, int nb, int h, int w
 template <typename T, bool ONE>
 __global__ void avgpool_bwd_mul_kernel(const T* __restrict__ gy, int nb, int h, int w, int c, int planes, int k,
                                        int stride, int pad, int op, int oq, const void* __restrict__ gain, int gain_f32,
-                                       T* __restrict__ gx) {
+                                       T* __restrict__ gx, int row_pitch, int img_pitch) {
   const int cg = c / 8;
   const int img = blockIdx.y;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;     // (pixel, channel group) inside the image, 32-bit math
@@ -328,7 +328,7 @@ __global__ void avgpool_bwd_mul_kernel(const T* __restrict__ gy, int nb, int h, 
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] *= inv * gn[i];
-  store8_planes<T>(gx + (size_t)pix * ld + g * 8, planes, c, acc);
+  store8_planes<T>(gx + ((size_t)img * img_pitch + (size_t)yy * row_pitch + xx) * ld + g * 8, planes, c, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -401,7 +401,7 @@ avgpool_fwd_rows_kernel(const T* __restrict__ x, int h, int w, int c, int k, int
 template <typename T>
 __global__ void __launch_bounds__(256)
 avgpool_bwd_mul_rows_kernel(const T* __restrict__ gy, int h, int w, int c, int k, int stride, int pad, int op, int oq,
-                            const T* __restrict__ gain, T* __restrict__ gx) {
+                            const T* __restrict__ gain, T* __restrict__ gx, int row_pitch, int img_pitch) {
   extern __shared__ __align__(128) uint8_t pool_smem[];
   __shared__ __align__(8) uint64_t bar;
   const int img = blockIdx.y, yy = blockIdx.x;
@@ -452,7 +452,7 @@ avgpool_bwd_mul_rows_kernel(const T* __restrict__ gy, int h, int w, int c, int k
   fence_proxy_async_smem();
   __syncthreads();
   if (threadIdx.x == 0) {
-    bulk_store_1d(gx + ((size_t)img * h + yy) * w * c, s_gain, row_bytes);
+    bulk_store_1d(gx + ((size_t)img * img_pitch + (size_t)yy * row_pitch) * c, s_gain, row_bytes);
     tma_store_commit_and_wait_read();
   }
 }
@@ -636,28 +636,33 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 
 template <typename SRC>
 static int input_prep_impl(const SRC* x, int32_t nb, int32_t h, int32_t w, const float* mean6, const float* inv_std6,
-                           void* out, int32_t cp, int32_t planes, int32_t dtype, float* sq, void* stream) {
+                           void* out, int32_t cp, int32_t planes, int32_t dtype, float* sq, int32_t row_pitch,
+                           int32_t img_pitch, void* stream) {
   if (!x || !out || !mean6 || !inv_std6) return set_error(BCOSK_EINVAL, "input_prep: null pointer");
+  if (row_pitch == 0) row_pitch = w / 2;
+  if (img_pitch == 0) img_pitch = (h / 2) * row_pitch;
+  if (row_pitch < w / 2 || img_pitch < (h / 2) * row_pitch) return set_error(BCOSK_EINVAL, "input_prep: bad output pitch");
   if (h % 2 || w % 2 || cp < 24 || cp % 8) return set_error(BCOSK_EINVAL, "input_prep: need even h,w and cp>=24, cp%%8==0");
   Norm6 nm;
   for (int i = 0; i < 6; ++i) { nm.mean[i] = mean6[i]; nm.inv_std[i] = inv_std6[i]; }  // host pointers
   const long long n = (long long)nb * (h / 2) * (w / 2);
   BCOSK_DTYPE_SWITCH(dtype, input_prep_s2d_kernel<T, SRC><<<blocks_for(n, 256), 256, 0, S(stream)>>>(
-      x, nb, h, w, nm, reinterpret_cast<T*>(out), cp, planes, sq);)
+      x, nb, h, w, nm, reinterpret_cast<T*>(out), cp, planes, sq, row_pitch, img_pitch);)
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }
 
 extern "C" int bcosk_input_prep_s2d(const float* x, int32_t nb, int32_t h, int32_t w, const float* mean6,
                                     const float* inv_std6, void* out, int32_t cp, int32_t planes, int32_t dtype, float* sq,
-                                    void* stream) {
-  return input_prep_impl<float>(x, nb, h, w, mean6, inv_std6, out, cp, planes, dtype, sq, stream);
+                                    int32_t out_row_pitch, int32_t out_img_pitch, void* stream) {
+  return input_prep_impl<float>(x, nb, h, w, mean6, inv_std6, out, cp, planes, dtype, sq, out_row_pitch, out_img_pitch, stream);
 }
 
 extern "C" int bcosk_input_prep_s2d_u8(const uint8_t* x, int32_t nb, int32_t h, int32_t w, const float* mean6,
                                        const float* inv_std6, void* out, int32_t cp, int32_t planes, int32_t dtype,
-                                       float* sq, void* stream) {
-  return input_prep_impl<uint8_t>(x, nb, h, w, mean6, inv_std6, out, cp, planes, dtype, sq, stream);
+                                       float* sq, int32_t out_row_pitch, int32_t out_img_pitch, void* stream) {
+  return input_prep_impl<uint8_t>(x, nb, h, w, mean6, inv_std6, out, cp, planes, dtype, sq, out_row_pitch, out_img_pitch,
+                                  stream);
 }
 
 extern "C" int bcosk_patch_inv_norm(const float* sq, int32_t parts, int32_t nb, int32_t h, int32_t w, int32_t kh,
@@ -725,8 +730,11 @@ extern "C" int bcosk_avgpool_fwd(const void* x, int32_t nb, int32_t h, int32_t w
 
 extern "C" int bcosk_avgpool_bwd_mul(const void* gy, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t k,
                                      int32_t stride, int32_t pad, int32_t op, int32_t oq, const void* gain, int32_t gain_f32,
-                                     void* gx, int32_t dtype, void* stream) {
+                                     void* gx, int32_t dtype, int32_t row_pitch, int32_t img_pitch, void* stream) {
   if (!gy || !gx || c % 8) return set_error(BCOSK_EINVAL, "avgpool_bwd_mul: bad argument");
+  if (row_pitch == 0) row_pitch = w;
+  if (img_pitch == 0) img_pitch = h * row_pitch;
+  if (row_pitch < w || img_pitch < h * row_pitch) return set_error(BCOSK_EINVAL, "avgpool_bwd_mul: bad output pitch");
   if (nb > 65535) return set_error(BCOSK_EUNSUPPORTED, "avgpool_bwd_mul: batch too large for the grid");
   {
     // row-staged kernel: single plane, 16-bit gain, at most two output rows cover an input row (k <= 2 * stride)
@@ -734,7 +742,7 @@ extern "C" int bcosk_avgpool_bwd_mul(const void* gy, int32_t nb, int32_t h, int3
     if (planes == 1 && gain != nullptr && !gain_f32 && k <= 2 * stride && smem <= 48 * 1024 && h <= 65535) {
       BCOSK_DTYPE_SWITCH(dtype, avgpool_bwd_mul_rows_kernel<T><<<dim3(h, nb), 256, smem, S(stream)>>>(
           reinterpret_cast<const T*>(gy), h, w, c, k, stride, pad, op, oq, reinterpret_cast<const T*>(gain),
-          reinterpret_cast<T*>(gx));)
+          reinterpret_cast<T*>(gx), row_pitch, img_pitch);)
       BCOSK_CUDA_CHECK(cudaGetLastError());
       return BCOSK_OK;
     }
@@ -743,10 +751,12 @@ extern "C" int bcosk_avgpool_bwd_mul(const void* gy, int32_t nb, int32_t h, int3
   const dim3 bgrid(blocks_for(n, 256), nb);
   if (planes == 1) {
     BCOSK_DTYPE_SWITCH(dtype, avgpool_bwd_mul_kernel<T, true><<<bgrid, 256, 0, S(stream)>>>(
-        reinterpret_cast<const T*>(gy), nb, h, w, c, planes, k, stride, pad, op, oq, gain, gain_f32, reinterpret_cast<T*>(gx));)
+        reinterpret_cast<const T*>(gy), nb, h, w, c, planes, k, stride, pad, op, oq, gain, gain_f32, reinterpret_cast<T*>(gx),
+        row_pitch, img_pitch);)
   } else {
     BCOSK_DTYPE_SWITCH(dtype, avgpool_bwd_mul_kernel<T, false><<<bgrid, 256, 0, S(stream)>>>(
-        reinterpret_cast<const T*>(gy), nb, h, w, c, planes, k, stride, pad, op, oq, gain, gain_f32, reinterpret_cast<T*>(gx));)
+        reinterpret_cast<const T*>(gy), nb, h, w, c, planes, k, stride, pad, op, oq, gain, gain_f32, reinterpret_cast<T*>(gx),
+        row_pitch, img_pitch);)
   }
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;

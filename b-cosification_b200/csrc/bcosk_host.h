@@ -26,4 +26,8 @@ int make_im2col_map_nhwc(CUtensorMap* map, const void* base, int nb, int h, int 
 int make_tiled_map_2d(CUtensorMap* map, const void* base, long long cols, long long rows, int box_cols, int box_rows,
                       int swizzle_bytes);
 
+// General tiled descriptor (rank 2 or 3) with explicit byte strides; elem_bytes 2 or 4.  dims[0] is the contiguous one.
+int make_tiled_map_nd(CUtensorMap* map, const void* base, int elem_bytes, int rank, const long long* dims,
+                      const long long* strides_bytes, const int* box, int swizzle_bytes);
+
 }  // namespace bcosk

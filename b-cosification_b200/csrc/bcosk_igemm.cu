@@ -49,8 +49,16 @@ __device__ int g_timing_cap = 0;
   do {                                                                                                     \
     if (g_timing_buf != nullptr && (int)blockIdx.x < g_timing_cap) g_timing_buf[blockIdx.x * 8 + (slot)] = clock64(); \
   } while (0)
+// accumulate a duration into slot `slot` of this CTA (each slot has one writer thread)
+#define BCOSK_TACC_BEGIN() const long long _tacc0 = clock64()
+#define BCOSK_TACC(slot)                                                                                      \
+  do {                                                                                                        \
+    if (g_timing_buf != nullptr && (int)blockIdx.x < g_timing_cap) g_timing_buf[blockIdx.x * 8 + (slot)] += clock64() - _tacc0; \
+  } while (0)
 #else
 #define BCOSK_STAMP(slot) do { } while (0)
+#define BCOSK_TACC_BEGIN() do { } while (0)
+#define BCOSK_TACC(slot) do { } while (0)
 #endif
 
 struct RowInfo {
@@ -1196,6 +1204,284 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
   }
 }
 
+// =================================================================================================
+// Flat-window variant (bcosk_igemm_params.a_flat): stride-1 k x k gathers over a zero-bordered buffer.
+// Persistent, one CTA per SM.  The packed weights stay resident in shared memory, every tile fetches ONE window of
+// 128 + max tap offset pixel rows with <= 2 tiled TMA boxes (double buffered) and each tap's MMA reads it through a
+// descriptor shifted by (off_h * a_wp + off_w) rows.  Per tile that is ~4x fewer bytes from L2 than one im2col box
+// per tap for the 4 x 4 stem (16 boxes), which is what bounded it.
+//   warp 0  producer (weights once, then windows)   warp 1  TMEM allocator + MMA issuer (two accumulators)
+//   warps 2..  epilogue: one TMEM lane quadrant x 32-column slice each; 16-bit outputs are staged in swizzled tiles
+//              and copied out as full 128-byte lines (the tile's rows belong to up to three image rows; positions
+//              x >= oq are skipped)
+// =================================================================================================
+struct FlatGeom {
+  int box_rows;    // rows per window box (multiple of 8, <= 256)
+  int nbox;        // 1 or 2
+  int tiles_img;   // 128-position tiles per image
+};
+
+template <int BN>
+struct FlatCfg {
+  static constexpr int kEpiWarps = (BN / 32) * 4;
+  static constexpr int kThreads = 64 + kEpiWarps * 32;
+  static constexpr int kTileBytes = BM * 128;          // one staged output tile (64 x 16-bit columns)
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+};
+
+template <int BN, int MODE, typename T>
+__global__ void __launch_bounds__(FlatCfg<BN>::kThreads, 1)
+bcosk_igemm_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        const __grid_constant__ bcosk_igemm_params p, const IgemmAux aux, const FlatGeom geo) {
+  using Cfg = FlatCfg<BN>;
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  uint8_t* smem = smem_dyn;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const uint32_t row_bytes = (uint32_t)p.kch * 2;
+  const uint32_t b_chunk_bytes = BN * row_bytes;
+  const uint32_t b_bytes = (uint32_t)p.num_taps * b_chunk_bytes;
+  const uint32_t win_bytes = (uint32_t)geo.nbox * geo.box_rows * row_bytes;
+  const bool any_out_tile = aux.tma_out1 || aux.tma_out2;
+  uint8_t* s_b = smem;
+  uint8_t* s_win = s_b + ((b_bytes + 1023u) & ~1023u);                         // [2][win_bytes], 1024-aligned
+  const uint32_t win_stride = (win_bytes + 1023u) & ~1023u;
+  uint8_t* s_out = s_win + 2 * win_stride;                                     // [2 bufs][out1 | out2] (if staged)
+  uint8_t* s_tail = s_out + (any_out_tile ? 4 * Cfg::kTileBytes : 0);
+  uint64_t* b_full_bar = reinterpret_cast<uint64_t*>(s_tail);
+  uint64_t* win_full_bar = b_full_bar + 1;      // [2]
+  uint64_t* win_empty_bar = win_full_bar + 2;   // [2]
+  uint64_t* acc_full_bar = win_empty_bar + 2;   // [2]
+  uint64_t* acc_empty_bar = acc_full_bar + 2;   // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty_bar + 2);
+  float* s_ab = reinterpret_cast<float*>(s_tail + 128);                        // [alpha BN | beta BN]
+  float* s_sq = s_ab + 2 * BN;                                                 // [2][BN/32][BM]
+  uint32_t* s_aoff = reinterpret_cast<uint32_t*>(s_sq + 2 * (BN / 32) * BM);   // [BCOSK_MAX_TAPS] tap offsets >> 4
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.a_nb * geo.tiles_img;
+  const int img_rows = p.a_hp * p.a_wp;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    mbar_init(b_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&win_full_bar[s], 1);
+      mbar_init(&win_empty_bar[s], 1);
+      mbar_init(&acc_full_bar[s], 1);
+      mbar_init(&acc_empty_bar[s], Cfg::kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+    tmem_relinquish();
+    for (int t = lane; t < p.num_taps; t += 32)
+      s_aoff[t] = ((uint32_t)(p.tap_off_h[t] * p.a_wp + p.tap_off_w[t]) * row_bytes) >> 4;
+  }
+  if (MODE == BCOSK_MODE_FWD && warp >= 2) {
+    for (int c = threadIdx.x - 64; c < BN; c += Cfg::kEpiWarps * 32) {
+      s_ab[c] = (p.alpha != nullptr && c < p.n) ? __ldg(p.alpha + c) : 1.f;
+      s_ab[BN + c] = (p.beta != nullptr && c < p.n) ? __ldg(p.beta + c) : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(b_full_bar, b_bytes);
+      for (int c = 0; c < p.num_taps; ++c) tma_load_2d(s_b + c * b_chunk_bytes, &tmap_b, b_full_bar, c * p.kch, 0);
+      uint32_t i = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        const uint32_t buf = i & 1u, par = (i >> 1) & 1u;
+        const int img = t / geo.tiles_img;
+        const int m0 = (t - img * geo.tiles_img) * BM;
+        {
+          BCOSK_TACC_BEGIN();
+          mbar_wait(&win_empty_bar[buf], par ^ 1u);
+          BCOSK_TACC(0);
+        }
+        mbar_arrive_expect_tx(&win_full_bar[buf], win_bytes);
+        for (int bx = 0; bx < geo.nbox; ++bx)
+          tma_load_2d(s_win + buf * win_stride + bx * geo.box_rows * row_bytes, &tmap_a, &win_full_bar[buf], 0,
+                      img * img_rows + m0 + bx * geo.box_rows);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(p.dtype == BCOSK_DTYPE_BF16 ? 1u : 0u, BM, BN);
+      const int ksteps = p.kch / 16;
+      const uint64_t db0 = umma_smem_desc_kmajor(smem_u32(s_b), row_bytes);
+      const uint64_t b_chunk16 = b_chunk_bytes >> 4;
+      mbar_wait(b_full_bar, 0);
+      uint32_t i = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        const uint32_t buf = i & 1u, par = (i >> 1) & 1u;
+        {
+          BCOSK_TACC_BEGIN();
+          mbar_wait(&acc_empty_bar[buf], par ^ 1u);
+          BCOSK_TACC(2);
+        }
+        {
+          BCOSK_TACC_BEGIN();
+          mbar_wait(&win_full_bar[buf], par);
+          BCOSK_TACC(1);
+        }
+        tc_fence_after();
+        BCOSK_TACC_BEGIN();
+        // one LDS + two 64-bit adds per tap, then the K steps unrolled: the issuing thread must stay well under the
+        // ~48 cycles a 128 x 64 x 16 MMA takes (measured: scripts/exp/mma_rate.cu), a naive loop costs ~240 per MMA
+        const uint64_t da0 = umma_smem_desc_kmajor(smem_u32(s_win + buf * win_stride), row_bytes);
+        uint64_t db = db0;
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        {
+          const uint64_t da = da0 + s_aoff[0];
+          umma_f16(tmem_d, da, db, idesc, 0);
+          umma_f16(tmem_d, da + 2, db + 2, idesc, 1);
+          if (ksteps == 4) {
+            umma_f16(tmem_d, da + 4, db + 4, idesc, 1);
+            umma_f16(tmem_d, da + 6, db + 6, idesc, 1);
+          }
+        }
+#pragma unroll 1
+        for (int tap = 1; tap < p.num_taps; ++tap) {
+          const uint64_t da = da0 + s_aoff[tap];
+          db += b_chunk16;
+          umma_f16(tmem_d, da, db, idesc, 1);
+          umma_f16(tmem_d, da + 2, db + 2, idesc, 1);
+          if (ksteps == 4) {
+            umma_f16(tmem_d, da + 4, db + 4, idesc, 1);
+            umma_f16(tmem_d, da + 6, db + 6, idesc, 1);
+          }
+        }
+        umma_commit(&win_empty_bar[buf]);
+        umma_commit(&acc_full_bar[buf]);
+        BCOSK_TACC(3);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;
+    const int j = (warp - 2) >> 2;                     // 32-column slice of the tile handled by this warp
+    const int row = quad * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const bool fast = epilogue_fast_ok<MODE>(p);
+    const bool want_sq = MODE == BCOSK_MODE_FWD && p.sq_out != nullptr;
+    const int c0 = j * 32;
+    uint32_t i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      const uint32_t buf = i & 1u, par = (i >> 1) & 1u;
+      const int img = t / geo.tiles_img;
+      const int m0 = (t - img * geo.tiles_img) * BM;
+      const int mf = m0 + row;                         // flattened position p * a_wp + x
+      RowInfo ri;
+      ri.img = img;
+      ri.p = mf / p.a_wp;
+      ri.q = mf - ri.p * p.a_wp;
+      ri.valid = ri.p < p.op && ri.q < p.oq;
+      ri.m = ri.valid ? (img * p.op + ri.p) * p.oq + ri.q : 0;
+      const int64_t yrow = p.os_0 + (int64_t)ri.img * p.os_n + (int64_t)ri.p * p.os_p + (int64_t)ri.q * p.os_q;
+      float inv_norm = 1.f;
+      uint32_t mb = 0xffffffffu;
+      int64_t add_row = -1;
+      if (ri.valid) {
+        if (MODE == BCOSK_MODE_FWD && p.scale_mode != BCOSK_SCALE_NONE) inv_norm = __ldg(p.inv_norm + ri.m);
+        if (MODE == BCOSK_MODE_EXPLAIN && p.mask2 != nullptr && c0 < p.n)
+          mb = __ldg(p.mask2 + (size_t)ri.m * p.mask2_ld + (c0 >> 5));
+        if (MODE == BCOSK_MODE_EXPLAIN && p.add != nullptr) {
+          const int s = p.add_stride;
+          if (ri.p % s == 0 && ri.q % s == 0 && ri.p / s < p.add_p && ri.q / s < p.add_q)
+            add_row = ((int64_t)ri.img * p.add_p + ri.p / s) * p.add_q + ri.q / s;
+        }
+      }
+      EpiTiles tl;
+      tl.in = 0u;
+      tl.in2 = 0u;
+      tl.out1 = aux.tma_out1 ? smem_u32(s_out + (buf * 2) * Cfg::kTileBytes) : 0u;
+      tl.out2 = aux.tma_out2 ? smem_u32(s_out + (buf * 2 + 1) * Cfg::kTileBytes) : 0u;
+
+#ifdef BCOSK_TIMING
+      const long long _t_a = clock64();
+#endif
+      mbar_wait(&acc_full_bar[buf], par);
+#ifdef BCOSK_TIMING
+      const long long _t_b = clock64();
+#endif
+      tc_fence_after();
+      float sq_acc = 0.f;
+      if (c0 < p.n) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(buf * BN + c0), raw);
+        tmem_ld_wait();
+        if (ri.valid) {
+          float v[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(raw[k]);
+          epilogue_chunk<MODE, T>(p, ri, yrow, inv_norm, add_row, s_ab, s_ab + BN, j, c0, min(32, p.n - c0), v, sq_acc, tl,
+                                  row, fast, mb);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty_bar[buf]);
+      float* sq_buf = s_sq + buf * (BN / 32) * BM;
+      if (want_sq) sq_buf[j * BM + row] = sq_acc;
+#ifdef BCOSK_TIMING
+      const long long _t_c = clock64();
+#endif
+      asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kEpiWarps * 32) : "memory");
+      if (any_out_tile) {
+        // copy the staged tiles out: 8 lanes per row write one 128-byte line each, rows at x >= oq are skipped.
+        // (TMA stores cannot do this: a tile's rows belong to up to three image rows and a negative start coordinate
+        // is an illegal instruction for cp.async.bulk.tensor stores - scripts/exp/tma_store3d.cu.)
+        T* y16 = reinterpret_cast<T*>(p.y);
+        T* g16 = reinterpret_cast<T*>(p.gain);
+        for (int it = et; it < BM * 8; it += Cfg::kEpiWarps * 32) {
+          const int r = it >> 3, u = it & 7;
+          const int mfr = m0 + r;
+          const int pr = mfr / p.a_wp;
+          const int xr = mfr - pr * p.a_wp;
+          if (pr < p.op && xr < p.oq && u * 8 < p.n) {
+            const size_t d = (size_t)(img * p.op + pr) * p.oq + xr;
+            const uint32_t off = (uint32_t)(r << 7) + (uint32_t)((u ^ (r & 7)) << 4);
+            if (tl.out1 != 0) *reinterpret_cast<uint4*>(y16 + d * p.y_ld + u * 8) = lds128(tl.out1 + off);
+            if (tl.out2 != 0) *reinterpret_cast<uint4*>(g16 + d * p.gain_ld + u * 8) = lds128(tl.out2 + off);
+          }
+        }
+      }
+      if (want_sq && j == 0 && ri.valid) {
+        float s = sq_buf[row];
+#pragma unroll
+        for (int h = 1; h < BN / 32; ++h) s += sq_buf[h * BM + row];
+        p.sq_out[ri.m] = s;
+      }
+#ifdef BCOSK_TIMING
+      if (et == 0 && g_timing_buf != nullptr && (int)blockIdx.x < g_timing_cap) {
+        const long long _t_d = clock64();
+        g_timing_buf[blockIdx.x * 8 + 4] += _t_b - _t_a;   // waiting for the accumulator
+        g_timing_buf[blockIdx.x * 8 + 5] += _t_c - _t_b;   // TMEM load + epilogue math + staging
+        g_timing_buf[blockIdx.x * 8 + 6] += _t_d - _t_c;   // barrier + copy-out
+        g_timing_buf[blockIdx.x * 8 + 7] += 1;             // tiles
+      }
+#endif
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // debug: land one A chunk in smem via the im2col tensor map and copy it out de-swizzled
 // ---------------------------------------------------------------------------------------------
@@ -1299,6 +1585,84 @@ static int launch_persistent(const LaunchMaps& mp, const bcosk_igemm_params& p, 
   return BCOSK_OK;
 }
 
+template <int BN, int MODE>
+static int launch_flat_bn(const bcosk_igemm_params& p, cudaStream_t st) {
+  using Cfg = FlatCfg<BN>;
+  const int wp = p.a_wp, hp = p.a_hp;
+  int max_off = 0;
+  for (int t = 0; t < p.num_taps; ++t) {
+    if (p.tap_off_h[t] < 0 || p.tap_off_w[t] < 0) return set_error(BCOSK_EINVAL, "igemm(flat): negative tap offset");
+    max_off = max(max_off, p.tap_off_h[t] * wp + p.tap_off_w[t]);
+  }
+  FlatGeom geo;
+  const int need = BM + max_off;
+  geo.nbox = need <= 256 ? 1 : 2;
+  geo.box_rows = (((need + geo.nbox - 1) / geo.nbox) + 7) & ~7;
+  if (geo.box_rows > 256) return set_error(BCOSK_EUNSUPPORTED, "igemm(flat): window of %d rows does not fit two TMA boxes", need);
+  geo.tiles_img = ((p.op - 1) * wp + p.oq + BM - 1) / BM;
+  const int row_bytes = p.kch * 2;
+  const long long b_bytes = (long long)p.num_taps * BN * row_bytes;
+  const long long win_stride = ((long long)geo.nbox * geo.box_rows * row_bytes + 1023) & ~1023ll;
+
+  LaunchMaps mp;
+  memset(&mp, 0, sizeof(mp));
+  IgemmAux aux{};
+  {
+    const uint8_t* origin = reinterpret_cast<const uint8_t*>(p.a) + ((long long)p.lo_h * wp + p.lo_w) * p.a_c * 2;
+    const long long dims[2] = {p.a_c, p.a_flat_rows};
+    const long long strides[1] = {(long long)p.a_c * 2};
+    const int box[2] = {p.kch, geo.box_rows};
+    int rc = make_tiled_map_nd(&mp.a, origin, 2, 2, dims, strides, box, row_bytes);
+    if (rc) return rc;
+    rc = make_tiled_map_2d(&mp.b, p.b, (long long)p.num_taps * p.kch, p.n, p.kch, BN, row_bytes);
+    if (rc) return rc;
+  }
+  const bool dense_out = p.os_0 == 0 && p.os_q == 1 && p.os_p == p.oq && p.os_n == (long long)p.op * p.oq;
+  auto stageable = [&](const void* base, int ld) -> bool {
+    return (reinterpret_cast<uintptr_t>(base) & 15) == 0 && ld % 8 == 0;
+  };
+  if (MODE == BCOSK_MODE_FWD && BN == 64 && dense_out) {   // 16-bit outputs staged in shared memory, written as full lines
+    if (!p.y_f32 && p.y_planes == 1) aux.tma_out1 = stageable(p.y, p.y_ld) ? 1 : 0;
+    if (p.gain && !p.gain_f32) aux.tma_out2 = stageable(p.gain, p.gain_ld) ? 1 : 0;
+  }
+  const long long smem = ((b_bytes + 1023) & ~1023ll) + 2 * win_stride +
+                         ((aux.tma_out1 || aux.tma_out2) ? 4 * Cfg::kTileBytes : 0) + 128 + 2 * BN * 4 +
+                         2 * (BN / 32) * BM * 4 + BCOSK_MAX_TAPS * 4;
+  if (smem > 227 * 1024) return set_error(BCOSK_EUNSUPPORTED, "igemm(flat): %lld bytes of shared memory needed", smem);
+  auto kern = bcosk_igemm_flat_kernel<BN, MODE, __nv_bfloat16>;
+  auto kern_h = bcosk_igemm_flat_kernel<BN, MODE, __half>;
+  const void* fn = (p.dtype == BCOSK_DTYPE_BF16) ? (const void*)kern : (const void*)kern_h;
+  BCOSK_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (g_num_sms == 0) {
+    int dev = 0;
+    BCOSK_CUDA_CHECK(cudaGetDevice(&dev));
+    BCOSK_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long tiles = (long long)p.a_nb * geo.tiles_img;
+  if (tiles > 0x7fffffffLL || (long long)p.a_nb * hp * wp > 0x7fffffffLL) return set_error(BCOSK_EUNSUPPORTED, "igemm(flat): too large");
+  dim3 grid((unsigned)(tiles < g_num_sms ? tiles : g_num_sms));
+  if (p.dtype == BCOSK_DTYPE_BF16)
+    kern<<<grid, Cfg::kThreads, smem, st>>>(mp.a, mp.b, p, aux, geo);
+  else
+    kern_h<<<grid, Cfg::kThreads, smem, st>>>(mp.a, mp.b, p, aux, geo);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+static int launch_flat(const bcosk_igemm_params& p, cudaStream_t st) {
+  if (p.hp_accum || p.num_segs != 1 || p.chunks_per_tap != 1 || p.stride_w != 1 || p.stride_h != 1 || p.n > 64)
+    return set_error(BCOSK_EUNSUPPORTED, "igemm(flat): needs stride 1, one segment, one chunk per tap, n <= 64, no hp_accum");
+  if (p.a_wp < p.a_w || p.a_hp < p.a_h || p.a_flat_rows < 1 || p.a_c < p.kch || p.seg_a_choff[0] != 0)
+    return set_error(BCOSK_EINVAL, "igemm(flat): bad buffer geometry");
+  if (p.oq > p.a_wp) return set_error(BCOSK_EINVAL, "igemm(flat): oq exceeds the buffer pitch");
+  if (p.mode == BCOSK_MODE_FWD && p.scale_mode != BCOSK_SCALE_NONE && !p.inv_norm)
+    return set_error(BCOSK_EUNSUPPORTED, "igemm(flat): inv_norm must be precomputed");
+  if (p.res_planes > 1 || p.y_planes > 1 && !p.y_f32) return set_error(BCOSK_EUNSUPPORTED, "igemm(flat): single plane only");
+  if (p.mode == BCOSK_MODE_FWD)
+    return p.n <= 32 ? launch_flat_bn<32, BCOSK_MODE_FWD>(p, st) : launch_flat_bn<64, BCOSK_MODE_FWD>(p, st);
+  return p.n <= 32 ? launch_flat_bn<32, BCOSK_MODE_EXPLAIN>(p, st) : launch_flat_bn<64, BCOSK_MODE_EXPLAIN>(p, st);
+}
+
 static int validate(const bcosk_igemm_params& p) {
   if (!p.a || !p.b || !p.y) return set_error(BCOSK_EINVAL, "igemm: null a/b/y");
   if (p.kch != 64 && p.kch != 32) return set_error(BCOSK_EINVAL, "igemm: kch must be 32 or 64");
@@ -1367,6 +1731,7 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return set_error(BCOSK_EINVAL, "igemm: block_n");
   if (p.hp_accum && bn > 64) return set_error(BCOSK_EINVAL, "igemm: hp_accum needs block_n <= 64");
   p.block_n = bn;
+  if (p.a_flat) return launch_flat(p, reinterpret_cast<cudaStream_t>(stream));
   LaunchMaps mp;
   IgemmAux aux{};
   rc = make_maps(p, bn, &mp, &aux);

@@ -95,6 +95,12 @@ class PlanBase:
         # zeros (not empty): tails that the kernels never write must stay finite
         return torch.zeros(*shape, dtype=dtype or self.dt, device=self.device)
 
+    def _padded(self, nb: int, h: int, w: int, c: int, lo: int, hi: int) -> Tensor:
+        """Interior [nb, h, w, c] view of a zero-bordered buffer (`lo` pixels before, `hi` after, rows and columns): the
+        operand layout of the flat-window launches (include/bcosk.h `a_flat`).  Producers write the view, never the border."""
+        buf = torch.zeros(nb, h + lo + hi, w + lo + hi, c, dtype=self.dt, device=self.device)
+        return buf[:, lo:lo + h, lo:lo + w, :]
+
     def _dev(self, t: Tensor, dtype=torch.float32) -> Tensor:
         return t.to(device=self.device, dtype=dtype).contiguous()
 
@@ -111,6 +117,7 @@ class PlanBase:
     # launches whose K loop has at most this many 64-deep stages are bandwidth bound: they use 64-wide tiles, which
     # the library runs with 3 CTAs per SM (more bytes in flight); 0 disables
     light_k_iters = 4
+    flat_stem = True                 # stem and its data gradient as flat-window launches (throughput mode only)
     autotune_default = True          # capture() measures the per-launch schedule first (see autotune)
     fold_bn = True   # fold sqrt(BN multiplier) into the conv weights when every multiplier is positive and there is no bias
 
@@ -126,7 +133,7 @@ class PlanBase:
                   relu: bool, res: Optional[Act] = None, want_mask: bool = False, y_f32: bool = False,
                   inv_norm: Optional[Tensor] = None, kch: int = 64, want_sq: bool = True,
                   sq_geom: Optional[Tuple[int, int, int, int, int]] = None, lin_bias: Optional[Tensor] = None,
-                  sq_eps: Tuple[float, float] = (1e-6, 0.0)) -> Tuple[Act, ConvRec]:
+                  sq_eps: Tuple[float, float] = (1e-6, 0.0), flat: bool = False) -> Tuple[Act, ConvRec]:
         """One fused launch: B-cos conv (+BN multiplier, +residual, +ReLU).  The patch norm comes from `x.sq`
         (per-pixel sums of squares written by x's producer) and is evaluated inside the kernel; `sq_geom`
         overrides its (h, w, k, stride, pad) when the GEMM geometry is not the convolution's (space-to-depth stem)."""
@@ -178,7 +185,7 @@ class PlanBase:
             inv_norm=inv_norm, sq_in=sq_in, sq_geom=sq_geom, sq_eps=sq_eps, alpha=alpha, beta=beta,
             lin_bias=None if lin_bias is None else self._dev(lin_bias),
             res=None if res is None else res.t, res_planes=self.planes,
-            gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32, hp_accum=self.hp_accum,
+            gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32, hp_accum=self.hp_accum, flat=flat,
             algo_flops=2.0 * M * o * float((w != 0).sum().item()) / o))
         rec.algo_flops = self.fwd_ops[-1].algo_flops
         return Act(y, o, sq, parts), rec
@@ -199,7 +206,7 @@ class PlanBase:
 
     def _dgrad(self, rec: ConvRec, *, y: Tensor, y_map=None, mul1: Optional[Tensor] = None, add: Optional[Tensor] = None,
                add_stride: int = 1, out2: Optional[Tensor] = None, mul2: Optional[Tensor] = None,
-               mask2: Optional[Tensor] = None, y_f32: bool = False, kch: int = 64) -> None:
+               mask2: Optional[Tensor] = None, y_f32: bool = False, kch: int = 64, flat: bool = False) -> None:
         """Data gradient of `rec` as a stride-1 gather over rec.ghat (tcgen05 implicit GEMM, explain epilogue)."""
         g = rec.ghat
         k = rec.k
@@ -223,7 +230,7 @@ class PlanBase:
             else self._block_n(n, bmat.shape[1] // 64),   # dense extra gradient: 64-wide tiles stage it with TMA
             hp_accum=self.hp_accum, y=y, y_planes=1 if y_f32 else self.planes, y_f32=y_f32,
             out_map=y_map, add=add, add_planes=self.planes, add_stride=add_stride, mul1=mul1, out2=out2,
-            out2_planes=self.planes, mul2=mul2, mask2=mask2, algo_flops=rec.algo_flops,
+            out2_planes=self.planes, mul2=mul2, mask2=mask2, flat=flat, algo_flops=rec.algo_flops,
             a_dense_frac=1.0 / (rec.stride * rec.stride) if rec.ghat_map is not None else 1.0))
 
     # ------------------------------------------------------------------ execution
@@ -255,7 +262,7 @@ class PlanBase:
         chosen = {}
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         for op in self.fwd_ops + (self.bwd_ops if self.with_explain else []):
-            if not isinstance(op, O.IgemmOp) or op.hp_accum or op.resolved_block_n() != 64:
+            if not isinstance(op, O.IgemmOp) or op.hp_accum or op.flat or op.resolved_block_n() != 64:
                 continue
             best, best_t = 1, float("inf")
             for sched in (1, 2, 3):

@@ -70,6 +70,7 @@ class IgemmOp:
     a_dense_frac: float = 1.0
     hp_accum: bool = False           # per-stage TMEM accumulators summed in registers (parity mode)
     sched: int = 0                   # include/bcosk.h `sched`: 0 default, 1 per tile, 2 persistent, 3 persistent row blocks
+    flat: bool = False               # include/bcosk.h `a_flat`: `a` is the interior view of a zero-bordered buffer
 
     # ---- derived ----
     @property
@@ -101,6 +102,24 @@ class IgemmOp:
                   self.mul1, self.out2, self.mul2, self.mask2):
             total += nbytes(t)
         return total
+
+    def flat_geometry(self) -> Tuple[int, int, int, int]:
+        """(row pitch, image pitch in rows, window origin, buffer size) in pixels of the zero-bordered buffer behind `a`."""
+        nb, h, w, ac = self.a.shape
+        s_n, s_h, s_w, s_c = self.a.stride()
+        assert s_c == 1 and s_w == ac and s_h % ac == 0 and s_n % s_h == 0, (self.name, "not a padded NHWC view")
+        wp, hp = s_h // ac, s_n // s_h
+        base = self.a._base if self.a._base is not None else self.a
+        assert self.a.storage_offset() % ac == 0
+        off = self.a.storage_offset() // ac
+        top, left = off // wp, off % wp
+        kw = max(t[0] for t in self.taps) + 1
+        kh = max(t[1] for t in self.taps) + 1
+        lo_w, lo_h = self.lo
+        assert left >= -lo_w and wp - w - left >= kw - 1 + lo_w, (self.name, "horizontal border too narrow")
+        assert top >= -lo_h and hp - h - top >= kh - 1 + lo_h, (self.name, "vertical border too narrow")
+        assert self.stride == (1, 1) and len(self.seg_a_choff) == 1 and self.chunks_per_tap == 1 and self.n <= 64
+        return wp, hp, off + lo_h * wp + lo_w, base.numel() // ac
 
     def resolved_block_n(self) -> int:
         if self.block_n:
@@ -182,6 +201,9 @@ class IgemmOp:
             p.mask2_ld = self.mask2.shape[-1]
         p.hp_accum = int(self.hp_accum)
         p.sched = int(self.sched)
+        if self.flat:
+            wp, hp, origin, total = self.flat_geometry()
+            p.a_flat, p.a_wp, p.a_hp, p.a_flat_rows = 1, wp, hp, total - origin
         return p
 
     def run(self) -> None:

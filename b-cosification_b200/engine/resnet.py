@@ -65,14 +65,16 @@ class ResNetPlan(PlanBase):
         self.x_in = self._empty(nb, 3, S, S, dtype=torch.uint8) if self.input_u8 else self._empty(nb, 6, S, S, dtype=torch.float32)
         # ---- stem: normalise + space-to-depth, 7x7/2 conv as a 4x4/1 conv, BN, ReLU
         h2 = S // 2
-        a0 = self._empty(nb, h2, h2, pl * self.stem_cp)
+        # throughput mode: the stem reads a zero-bordered buffer (pad 2 before / 1 after) through one window per tile
+        self.stem_flat = self.flat_stem and pl == 1 and not self.hp_accum
+        a0 = self._padded(nb, h2, h2, self.stem_cp, 2, 1) if self.stem_flat else self._empty(nb, h2, h2, pl * self.stem_cp)
         sq0 = self._empty(1, nb * S * S, dtype=torch.float32)
         self.fwd_ops.append(O.InputPrepOp("input_prep", self.x_in, self.mean, self.inv_std, a0, self.stem_cp, pl,
                                           self.dt_code, sq0))
         w4 = P.stem_s2d_weight(sd["model.conv1.linear.weight"], self.stem_cp)
         # the patch norm is the ORIGINAL 7x7/2 pad-3 window over the full-resolution sums of squares
         y1, self.stem = self._conv_fwd("stem", Act(a0, self.stem_cp, sq0, 1), w4, 1, 2, 1, bn="model.bn1", relu=True,
-                                       kch=self.stem_kch, want_sq=False, sq_geom=(S, S, 7, 2, 3))
+                                       kch=self.stem_kch, want_sq=False, sq_geom=(S, S, 7, 2, 3), flat=self.stem_flat)
         # ---- AvgPool2d(3, 2, 1) (replaces maxpool)
         hp = (h2 + 2 - 3) // 2 + 1
         p1 = self._empty(nb, hp, hp, pl * 64)
@@ -131,6 +133,8 @@ class ResNetPlan(PlanBase):
             else:
                 blk.side = self._zeros(*blk.y.t.shape)
         self._alloc_ghat(self.stem)
+        if self.stem_flat:     # the transposed 4x4 gather pads 1 before / 2 after
+            self.stem.ghat = self._padded(nb, self.stem.out_hw[0], self.stem.out_hw[1], self.stem.cout, 1, 2)
         last = self.blocks[-1]
         assert last.ds is None, "classifier seed kernel expects an identity shortcut in the last block"
         # ---- seed: d logit[target] / d fc-input, straight through GAP and the classifier's detached scale
@@ -164,7 +168,7 @@ class ResNetPlan(PlanBase):
                                               self.dt_code))
         h2 = self.size // 2
         self.g0 = self._zeros(nb, h2, h2, self.stem_cp, dtype=torch.float32)
-        self._dgrad(self.stem, y=self.g0, y_f32=True, kch=64)
+        self._dgrad(self.stem, y=self.g0, y_f32=True, kch=64, flat=self.stem_flat)
         self.cmap = self._zeros(nb, self.size, self.size, dtype=torch.float32)
         self.grad6 = self._zeros(nb, 6, self.size, self.size, dtype=torch.float32) if want_grad6 else None
         self.bwd_ops.append(O.ContribMapOp("contrib_map", self.g0, self.x_in, self.stem_cp, self.inv_std,

@@ -127,6 +127,17 @@ typedef struct bcosk_igemm_params {
    *      128-row block back to back (the segments of an output row reach L2 together).  The host plan measures the
    *      three per launch once (engine/base.py PlanBase.autotune) - which wins depends on N/K and the epilogue streams. */
   int32_t sched;
+  /* ---- flat-window gather (a_flat = 1): `a` points at pixel (0,0) of a [a_nb, a_h, a_w, a_c] VIEW into a larger
+   *      zero-bordered buffer whose rows are a_wp pixels and whose images are a_hp rows apart (borders at least as wide
+   *      as the padding, never written).  For stride-1 convolutions the rows of every tap are then one contiguous run of
+   *      the flattened buffer, so a CTA fetches ONE window of 128 + max tap offset pixels per tile (tiled TMA) and feeds
+   *      every tap's MMA from shifted shared-memory descriptors, instead of one im2col box per tap (k*k x less L2->SM
+   *      traffic; the 7x7 stem and its data gradient were bound by it).  Tiles walk the flattened positions p*a_wp + x
+   *      of one image; positions with x >= oq are computed and dropped.  Requires stride 1, num_segs 1,
+   *      chunks_per_tap 1, n <= 64.  a_flat_rows = pixels from the window origin (a + (lo_h*a_wp + lo_w) pixels) to
+   *      the end of the buffer.  Results are identical to the im2col gather. */
+  int32_t a_flat, a_wp, a_hp;
+  int64_t a_flat_rows;
 } bcosk_igemm_params;
 
 int bcosk_igemm(const bcosk_igemm_params* p, void* stream);
@@ -151,12 +162,15 @@ int bcosk_debug_a_tile(const bcosk_igemm_params* p, int32_t tile_m, int32_t chun
  *   out  [nb, h/2, w/2, planes * cp]   channel (dy*2+dx)*6 + c, zero padded to cp
  *   sq   [nb, h, w] fp32  sum_c xn^2 per ORIGINAL pixel (for the stem patch norm); may be NULL */
 int bcosk_input_prep_s2d(const float* x, int32_t nb, int32_t h, int32_t w, const float* mean6, const float* inv_std6,
-                         void* out, int32_t cp, int32_t planes, int32_t dtype, float* sq, void* stream);
+                         void* out, int32_t cp, int32_t planes, int32_t dtype, float* sq, int32_t out_row_pitch,
+                         int32_t out_img_pitch, void* stream);
 /* Same, from uint8 RGB images x [nb, 3, h, w]: x/255 and the inverse channels 1 - x/255 (AddInverse,
  * bcos/data/transforms.py:42-55) are formed on the fly (8x fewer host->device bytes than fp32 6-channel input). */
 int bcosk_input_prep_s2d_u8(const uint8_t* x, int32_t nb, int32_t h, int32_t w, const float* mean6,
                             const float* inv_std6, void* out, int32_t cp, int32_t planes, int32_t dtype, float* sq,
-                            void* stream);
+                            int32_t out_row_pitch, int32_t out_img_pitch, void* stream);
+/* out_row_pitch / out_img_pitch (both entry points): pixels between consecutive rows / images of `out`; 0 = dense
+ * (w/2 and h/2*w/2).  Non-dense pitches let `out` be a view into the zero-bordered buffer of a flat-window launch. */
 
 /* BcosConv2d.calc_patch_norms bcosconv2d.py:196-231: inv_norm[img,p,q] = 1/sqrt(sumpool_k,s,p(sq) + eps_in) (conv)
  * or 1/(sqrt(sq) + eps_out) (linear, bcoslinear.py:113).  sq holds `parts` partial maps [parts][nb*h*w]. */
@@ -173,10 +187,11 @@ int bcosk_avgpool_fwd(const void* x, int32_t nb, int32_t h, int32_t w, int32_t c
                       int32_t stride, int32_t pad, void* y, int32_t op, int32_t oq, int32_t dtype, float* sq,
                       void* stream);
 
-/* Explain backward of AvgPool2d fused with the producer's gain: gx = avgpool_bwd(gy) * gain. */
+/* Explain backward of AvgPool2d fused with the producer's gain: gx = avgpool_bwd(gy) * gain.
+ * gx_row_pitch / gx_img_pitch: pixels between rows / images of gx, 0 = dense (see bcosk_input_prep_s2d). */
 int bcosk_avgpool_bwd_mul(const void* gy, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t k,
                           int32_t stride, int32_t pad, int32_t op, int32_t oq, const void* gain, int32_t gain_f32,
-                          void* gx, int32_t dtype, void* stream);
+                          void* gx, int32_t dtype, int32_t gx_row_pitch, int32_t gx_img_pitch, void* stream);
 
 /* ResNetBcos._forward_impl standard_models.py:50-52 tail + LogitLayer logitlayer.py:22-27:
  * logits[img, cls] = mean_pix fc[img, pix, cls] * inv_temp + bias; pred[img] = argmax (first max). */

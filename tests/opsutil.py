@@ -29,7 +29,14 @@ def to_device(op, device, memo: Dict[int, Tensor] | None = None):
         v = getattr(op, f.name)
         if isinstance(v, Tensor):
             if id(v) not in memo:
-                memo[id(v)] = v.detach().clone().to(device)
+                base = v._base
+                if base is not None and not v.is_contiguous():
+                    # strided view (interior of a zero-bordered buffer): move the whole buffer, keep the view
+                    if id(base) not in memo:
+                        memo[id(base)] = base.detach().clone().to(device)
+                    memo[id(v)] = memo[id(base)].as_strided(v.shape, v.stride(), v.storage_offset())
+                else:
+                    memo[id(v)] = v.detach().clone().to(device)
             changes[f.name] = memo[id(v)]
     return dataclasses.replace(op, **changes)
 

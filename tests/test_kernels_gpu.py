@@ -153,6 +153,70 @@ def test_igemm_explain_dgrad(bcosk_lib, case):
     print(name, errs)
 
 
+def _padded_act(plan, g, nb, h, w, c, lo, hi):
+    """random activation stored in the interior view of a zero-bordered buffer (flat-window operand layout)"""
+    t = plan._padded(nb, h, w, c, lo, hi)
+    v = torch.randn(nb, h, w, c, generator=g)
+    t.copy_(v.to(t.dtype))
+    sq = (t.float() ** 2).sum(-1).reshape(1, -1).contiguous()
+    return Act(t, c, sq, 1)
+
+
+FLAT_FWD_CASES = [
+    # name, nb, h, w, cin, cout, k, pad_lo, pad_hi, kch, relu
+    ("flat_4x4_stem_like", 3, 20, 20, 32, 64, 4, 2, 1, 32, True),
+    ("flat_4x4_wide_rows", 2, 9, 100, 32, 64, 4, 2, 1, 32, True),      # rows almost as long as a tile
+    ("flat_3x3_c64", 2, 14, 14, 64, 64, 3, 1, 1, 64, True),
+    ("flat_3x3_n32", 2, 11, 13, 64, 32, 3, 1, 1, 64, False),
+    ("flat_1x1_c64", 2, 12, 12, 64, 64, 1, 0, 0, 64, True),
+]
+
+
+@pytest.mark.parametrize("case", FLAT_FWD_CASES, ids=[c[0] for c in FLAT_FWD_CASES])
+def test_igemm_flat_window_forward(bcosk_lib, case):
+    """flat-window gather (one shared-memory window per tile, shifted descriptors per tap) == the emulator's conv"""
+    name, nb, h, wd, cin, cout, k, plo, phi, kch, relu = case
+    g = torch.Generator().manual_seed(hash(name) % 2**31)
+    plan = _mini_plan(nb, 1)
+    x = _padded_act(plan, g, nb, h, wd, cin, plo, phi)
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    oh, ow = h + plo + phi - k + 1, wd + plo + phi - k + 1
+    inv_norm = torch.rand(nb * oh * ow, generator=g) + 0.5
+    plan.sd = {"bn.running_var": torch.rand(cout, generator=g) + 0.5, "bn.weight": torch.rand(cout, generator=g) + 0.5}
+    for fold in (True, False):         # BN folded into the weights / applied as alpha in the epilogue
+        plan.fold_bn = fold
+        plan.fwd_ops.clear()
+        plan._conv_fwd(name, x, w, 1, plo, phi, bn="bn", relu=relu, want_mask=True, kch=kch, inv_norm=inv_norm, flat=True)
+        assert plan.fwd_ops[-1].flat
+        print(name, fold, _run_and_compare(plan.fwd_ops))
+
+
+@pytest.mark.parametrize("case", [("flat_d_4x4_n32_f32", 2, 18, 32, 64, 4, 2, 1, True),
+                                  ("flat_d_3x3_n64", 2, 12, 64, 64, 3, 1, 1, False)], ids=lambda c: c[0])
+def test_igemm_flat_window_dgrad(bcosk_lib, case):
+    name, nb, h, cin, cout, k, plo, phi, f32 = case
+    g = torch.Generator().manual_seed(hash(name) % 2**31)
+    plan = _mini_plan(nb, 1)
+    x = _rand_act(g, nb, h, h, cin, 1)
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    oh = h + plo + phi - k + 1
+    inv_norm = torch.rand(nb * oh * oh, generator=g) + 0.5
+    _, rec = plan._conv_fwd(name, x, w, 1, plo, phi, bn=None, relu=True, want_mask=True, inv_norm=inv_norm,
+                            kch=32 if cin == 32 else 64)
+    rec.ghat = plan._padded(nb, oh, oh, cout, k - 1 - plo, k - 1 - phi)
+    rec.ghat_map = None
+    rec.ghat.copy_(torch.randn(nb, oh, oh, cout, generator=g).to(plan.dt))
+    M = nb * h * h
+    yb = torch.zeros(nb, h, h, cin, dtype=torch.float32 if f32 else plan.dt)
+    mul1 = None if f32 else (torch.rand(M, cin, generator=g) + 0.5).to(plan.gain_dt)
+    add = None if f32 else _rand_act(g, nb, h, h, cin, 1).t
+    out2 = None if f32 else torch.zeros(nb, h, h, cin, dtype=plan.dt)
+    mask2 = None if f32 else torch.randint(-2**31, 2**31 - 1, (M, (cin + 31) // 32), generator=g, dtype=torch.int64).to(torch.int32)
+    plan._dgrad(rec, y=yb, mul1=mul1, add=add, out2=out2, mask2=mask2, y_f32=f32, flat=True)
+    assert plan.bwd_ops[-1].flat
+    print(name, _run_and_compare(plan.bwd_ops))
+
+
 def test_igemm_dgrad_strided_add_and_outmap(bcosk_lib):
     """conv1x1 data gradient that adds a half-resolution tensor and writes zero-inserted rows"""
     g = torch.Generator().manual_seed(11)
@@ -250,6 +314,12 @@ def test_elementwise_kernels(bcosk_lib):
         gain = (torch.rand(nb * 256, 64, generator=g)).to(dt if planes == 1 else torch.float32)
         gx = torch.zeros(nb, 16, 16, planes * 64, dtype=dt)
         ops.append(O.AvgPoolBwdMulOp("poolbwd", gy, 64, planes, 3, 2, 1, gain, gx, 1))
+        if planes == 1:     # the same two kernels writing the interior view of a zero-bordered buffer
+            plan = _mini_plan(nb, 1)
+            outp = plan._padded(nb, S // 2, S // 2, 32, 2, 1)
+            ops.append(O.InputPrepOp("prep_padded", x6, mean, istd, outp, 32, 1, 1, torch.zeros(1, nb * S * S)))
+            gxp = plan._padded(nb, 16, 16, 64, 1, 2)
+            ops.append(O.AvgPoolBwdMulOp("poolbwd_padded", gy, 64, 1, 3, 2, 1, gain, gxp, 1))
         fc = torch.randn(nb * 49, 1000, generator=g)
         logits = torch.zeros(nb, 1000)
         pred = torch.zeros(nb, dtype=torch.int32)
