@@ -140,6 +140,10 @@ struct IgemmAux {
   int tma_out1;  // primary output y staged in slot 0 and written with TMA
   int tma_out2;  // forward: gain, explain: out2 - staged in slot 1 and written with TMA
   int order;     // persistent kernel: 0 = tiles strided over the grid, 1 = a CTA walks all n tiles of one row block
+  int cluster;   // per-tile kernel: CTAs of `cluster` consecutive row blocks (same n tile) form a thread-block cluster;
+                 // each fetches 1/cluster of the weight tile and multicasts it to the others (0/1 = no cluster)
+  int pair;      // cluster == 2 run as a CTA pair: one cta_group::2 MMA over both row blocks, each CTA keeps only its half
+                 // of the weight tile (no multicast: the tensor core reads the other half from the peer's shared memory)
 };
 
 // Shared-memory tiles of the TMA epilogue: [BN/64 boxes][128 rows][128 bytes], 16-byte units XOR-swizzled by row
@@ -530,7 +534,7 @@ __device__ __forceinline__ void epilogue_chunk(const bcosk_igemm_params& p, cons
   }
 }
 
-template <int BN, int MODE, typename T, bool HP, bool LIGHT = false>
+template <int BN, int MODE, typename T, bool HP, bool LIGHT = false, bool PAIR = false>
 __global__ void __launch_bounds__(NUM_THREADS, TileCfg<BN, HP, LIGHT>::kMinBlocks)
 bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in2,
@@ -556,8 +560,13 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = (p.n + BN - 1) / BN;
-  const int tile_n = blockIdx.x % n_tiles;
-  const int tile_m = blockIdx.x / n_tiles;
+  const int cl = aux.cluster > 1 ? aux.cluster : 1;
+  constexpr bool pair = PAIR;                                      // own instantiation (cta_group::2 code needs a cluster launch); implies cl == 2
+  const int cl_rank = (int)(blockIdx.x % (unsigned)cl);            // == %cluster_ctarank for (cl,1,1) clusters
+  const int cl_id = blockIdx.x / cl;
+  const int tile_n = cl_id % n_tiles;
+  const int tile_m = (cl_id / n_tiles) * cl + cl_rank;
+  const uint16_t cl_mask = (uint16_t)((1u << cl) - 1u);
   const int M = p.a_nb * p.op * p.oq;
   const int m0 = tile_m * BM;
   const int n0 = tile_n * BN;
@@ -574,8 +583,9 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < kSlots; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      // pair: the leader's barrier counts both producers' arrivals and both CTAs' bytes; one multicast commit frees a slot
+      mbar_init(&full_bar[s], pair ? 2 : 1);
+      mbar_init(&empty_bar[s], pair ? 1 : cl);   // multicast: free when every CTA that receives this slot's data consumed it
     }
     mbar_init(tmem_full_bar, 1);
     for (int s = 0; s < 2; ++s) {
@@ -586,11 +596,17 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_2cta(tmem_ptr_smem, Cfg::kTmemCols);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync_all();        // peers' barriers exist before any multicast data or remote arrival reaches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (threadIdx.x == 64) BCOSK_STAMP(1);
@@ -624,12 +640,38 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       for (int it = 0; it < num_iters; ++it) {
         uint8_t* slot = smem + stage * Cfg::kSlotBytes;
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if constexpr (PAIR) {
+          // both CTAs' stages are counted on the LEADER's barrier (it alone issues the pair MMA)
+          const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (cl_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + (BN / 2) * STAGE_K * 2));
+          else mbar_arrive_remote(lead_bar);
+          const uint32_t b_half_chunk = (BN / 2) * p.kch * 2;
+          for (int j = 0; j < chunks_per_stage; ++j) {
+            const int ci = it * chunks_per_stage + j;
+            tma_load_im2col_4d_2cta(slot + j * a_chunk_bytes, &tmap_a, lead_bar, p.seg_a_choff[seg] + kc * p.kch, base_w,
+                                    base_h, img, p.tap_off_w[tap], p.tap_off_h[tap]);
+            tma_load_2d_2cta(slot + A_STAGE_BYTES + j * b_half_chunk, &tmap_b, lead_bar, ci * p.kch, n0 + cl_rank * (BN / 2));
+            if (++kc == p.chunks_per_tap) {
+              kc = 0;
+              if (++tap == p.num_taps) { tap = 0; ++seg; }
+            }
+          }
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kSlotBytes);
         for (int j = 0; j < chunks_per_stage; ++j) {
           const int ci = it * chunks_per_stage + j;
           tma_load_im2col_4d(slot + j * a_chunk_bytes, &tmap_a, &full_bar[stage], p.seg_a_choff[seg] + kc * p.kch, base_w,
                              base_h, img, p.tap_off_w[tap], p.tap_off_h[tap]);
-          tma_load_2d(slot + A_STAGE_BYTES + j * b_chunk_bytes, &tmap_b, &full_bar[stage], ci * p.kch, n0);
+          if (cl > 1) {
+            // this CTA's share of the weight tile, delivered to every CTA of the cluster
+            const int rows = BN / cl;
+            tma_load_2d_mc(slot + A_STAGE_BYTES + j * b_chunk_bytes + cl_rank * rows * p.kch * 2, &tmap_b, &full_bar[stage],
+                           ci * p.kch, n0 + cl_rank * rows, cl_mask);
+          } else {
+            tma_load_2d(slot + A_STAGE_BYTES + j * b_chunk_bytes, &tmap_b, &full_bar[stage], ci * p.kch, n0);
+          }
           if (++kc == p.chunks_per_tap) {
             kc = 0;
             if (++tap == p.num_taps) { tap = 0; ++seg; }
@@ -640,7 +682,35 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if constexpr (PAIR) {
+      // CTA pair: the leader issues one 256 x BN MMA per K step over both CTAs' stages; commits reach both CTAs
+      if (lane == 0 && cl_rank == 0) {
+        const uint32_t idesc = umma_idesc_f16((uint32_t)p.dtype, 2 * BM, BN);
+        const uint32_t row_bytes = p.kch * 2;
+        const uint32_t a_chunk_bytes = BM * p.kch * 2;
+        const uint32_t b_half_chunk = (BN / 2) * p.kch * 2;
+        const int mma_per_chunk = p.kch / 16;
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t accumulate = 0;
+        for (int it = 0; it < num_iters; ++it) {
+          uint8_t* slot = smem + stage * Cfg::kSlotBytes;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          for (int j = 0; j < chunks_per_stage; ++j) {
+            const uint64_t da = umma_smem_desc_kmajor(smem_u32(slot + j * a_chunk_bytes), row_bytes);
+            const uint64_t db = umma_smem_desc_kmajor(smem_u32(slot + A_STAGE_BYTES + j * b_half_chunk), row_bytes);
+            for (int k = 0; k < mma_per_chunk; ++k) {
+              umma_f16_2cta(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit_2cta(&empty_bar[stage], 0x3);
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(tmem_full_bar, 0x3);
+      }
+    } else if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16((uint32_t)p.dtype, BM, BN);
       const uint32_t row_bytes = p.kch * 2;
       const uint32_t a_chunk_bytes = BM * p.kch * 2;
@@ -671,7 +741,9 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             accumulate = 1;
           }
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        // frees the smem slot once these MMAs have read it (in every CTA of the cluster: their multicasts land here too)
+        if (cl > 1) umma_commit_mc(&empty_bar[stage], cl_mask);
+        else umma_commit(&empty_bar[stage]);
         if (HP) umma_commit(&acc_full_bar[it & 1]);
         if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
@@ -826,9 +898,11 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
 
   __syncthreads();
+  if (cl > 1) cluster_sync_all();        // no CTA leaves while a peer's commit may still arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
   if (threadIdx.x == 64) BCOSK_STAMP(7);
 }
@@ -1527,11 +1601,11 @@ struct LaunchMaps {
   CUtensorMap a, b, in, in2, out1, out2;
 };
 
-template <int BN, int MODE, bool HP, bool LIGHT = false>
+template <int BN, int MODE, bool HP, bool LIGHT = false, bool PAIR = false>
 static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const IgemmAux& aux, cudaStream_t st) {
   using Cfg = TileCfg<BN, HP, LIGHT>;
-  auto kern = bcosk_igemm_kernel<BN, MODE, __nv_bfloat16, HP, LIGHT>;
-  auto kern_h = bcosk_igemm_kernel<BN, MODE, __half, HP, LIGHT>;
+  auto kern = bcosk_igemm_kernel<BN, MODE, __nv_bfloat16, HP, LIGHT, PAIR>;
+  auto kern_h = bcosk_igemm_kernel<BN, MODE, __half, HP, LIGHT, PAIR>;
   const void* fn = (p.dtype == BCOSK_DTYPE_BF16) ? (const void*)kern : (const void*)kern_h;
   static bool attr_done[2] = {false, false};
   if (!attr_done[p.dtype]) {
@@ -1543,6 +1617,26 @@ static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const
   const long long n_tiles = (p.n + BN - 1) / BN;
   if (m_tiles * n_tiles > 0x7fffffffLL) return set_error(BCOSK_EUNSUPPORTED, "igemm: grid too large");
   dim3 grid((unsigned)(m_tiles * n_tiles));
+  if (aux.cluster > 1) {
+    if (m_tiles % aux.cluster != 0) return set_error(BCOSK_EINVAL, "igemm: cluster size must divide the row blocks");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)aux.cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (p.dtype == BCOSK_DTYPE_BF16)
+      BCOSK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux));
+    else
+      BCOSK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern_h, mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux));
+    return BCOSK_OK;
+  }
   if (p.dtype == BCOSK_DTYPE_BF16)
     kern<<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux);
   else
@@ -1552,6 +1646,7 @@ static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const
 }
 
 static int g_num_sms = 0;
+static int g_cluster = 1;              // 1 none; 2/4 weight-tile multicast across row blocks; 3 = CTA pairs (cta_group::2)
 // Measured on B200 (profiles/r01_schedule_ab.md): per-tile + 3 CTAs/SM and the persistent kernel reach the same
 // ~4 TB/s on the bandwidth-bound launches; the per-tile schedule is the default.
 static int g_persistent_enabled = 0;   // 0 off, 1 tiles strided over the grid, 2 row-block order
@@ -1683,14 +1778,14 @@ static int validate(const bcosk_igemm_params& p) {
   return BCOSK_OK;
 }
 
-static int make_maps(const bcosk_igemm_params& p, int bn, LaunchMaps* mp, IgemmAux* aux) {
+static int make_maps(const bcosk_igemm_params& p, int bn, int cluster, LaunchMaps* mp, IgemmAux* aux) {
   memset(mp, 0, sizeof(*mp));
   memset(aux, 0, sizeof(*aux));
   int rc = make_im2col_map_nhwc(&mp->a, p.a, p.a_nb, p.a_h, p.a_w, p.a_c, p.lo_w, p.lo_h, p.up_w, p.up_h, p.stride_w,
                                 p.stride_h, p.kch, BM, p.kch == 64 ? 128 : 64);
   if (rc) return rc;
   const long long ktot = (long long)p.num_segs * p.num_taps * p.chunks_per_tap * p.kch;
-  rc = make_tiled_map_2d(&mp->b, p.b, ktot, p.n, p.kch, bn, p.kch == 64 ? 128 : 64);
+  rc = make_tiled_map_2d(&mp->b, p.b, ktot, p.n, p.kch, bn / cluster, p.kch == 64 ? 128 : 64);   // each CTA fetches its share
   if (rc) return rc;
   // ---- TMA epilogue (throughput mode): 16-bit single-plane tensors addressed densely by output row
   const long long M = (long long)p.a_nb * p.op * p.oq;
@@ -1732,10 +1827,24 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
   if (p.hp_accum && bn > 64) return set_error(BCOSK_EINVAL, "igemm: hp_accum needs block_n <= 64");
   p.block_n = bn;
   if (p.a_flat) return launch_flat(p, reinterpret_cast<cudaStream_t>(stream));
+  // weight-tile multicast: 128-wide tiles with a long K loop are bound by L2 -> shared-memory traffic (A and B stages
+  // of every tile come from L2: ~13 TB/s at 800 TFLOP/s, the L2 limit); CTAs of neighbouring row blocks share B
+  int cluster = 1;
+  {
+    const long long m_tiles = ((long long)p.a_nb * p.op * p.oq + BM - 1) / BM;
+    const int iters = p.num_segs * p.num_taps * p.chunks_per_tap / (STAGE_K / p.kch);
+    const int persistent_req = p.sched == 0 ? g_persistent_enabled : p.sched - 1;
+    const int want = g_cluster == 3 ? 2 : g_cluster;
+    if (want > 1 && !p.hp_accum && bn == 128 && p.n % bn == 0 && iters >= 8 && m_tiles % want == 0 &&
+        !(persistent_req && bn == 64))
+      cluster = want;
+  }
   LaunchMaps mp;
   IgemmAux aux{};
-  rc = make_maps(p, bn, &mp, &aux);
+  rc = make_maps(p, bn, cluster, &mp, &aux);
   if (rc) return rc;
+  aux.cluster = cluster;
+  aux.pair = (cluster == 2 && g_cluster == 3) ? 1 : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (p.hp_accum) aux.tma_in2 = 0;
 #define BCOSK_DISPATCH(BN_)                                                                         \
@@ -1763,6 +1872,9 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
       return p.mode == BCOSK_MODE_FWD ? launch_igemm<64, BCOSK_MODE_FWD, false, true>(mp, p, aux, st)
                                       : launch_igemm<64, BCOSK_MODE_EXPLAIN, false, true>(mp, p, aux, st);
   }
+  if (aux.pair && bn == 128)
+    return p.mode == BCOSK_MODE_FWD ? launch_igemm<128, BCOSK_MODE_FWD, false, false, true>(mp, p, aux, st)
+                                    : launch_igemm<128, BCOSK_MODE_EXPLAIN, false, false, true>(mp, p, aux, st);
   switch (bn) {
     BCOSK_DISPATCH(32)
     BCOSK_DISPATCH(64)
@@ -1787,6 +1899,12 @@ extern "C" int bcosk_debug_set_timing(void* buf, int32_t capacity_ctas) {
   return BCOSK_OK;
 }
 #endif
+
+extern "C" int bcosk_set_cluster(int32_t size) {
+  const int prev = g_cluster;
+  if (size >= 1 && size <= 4) g_cluster = size;
+  return prev;
+}
 
 extern "C" int bcosk_set_light(int32_t enabled) {
   const int prev = g_light_enabled ? 1 : 0;

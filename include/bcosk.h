@@ -145,6 +145,13 @@ int bcosk_igemm(const bcosk_igemm_params* p, void* stream);
 /* Scheduling switch for A/B measurements: 1 = launches with block_n 64 (the bandwidth-bound ones) run on the persistent
  * one-CTA-per-SM kernel, 0 (default) = one CTA per tile everywhere.  Returns the previous setting.  Results are identical. */
 int bcosk_set_persistent(int32_t enabled);
+/* Cluster mode of the 128-wide launches with >= 8 K stages.  1 = none.  2 / 4 = the CTAs of that many neighbouring
+ * 128-row blocks each fetch a share of the weight tile and multicast it (TMA .multicast::cluster).  3 = CTA pairs:
+ * two row blocks run ONE tcgen05.mma.cta_group::2 (256 x 128) issued by the leader CTA, each CTA keeps only its half of
+ * the weight tile in shared memory (25 % fewer bytes into each SM per FLOP).  Returns the previous setting.  Results are
+ * identical in every mode (tests/test_kernels_gpu.py). */
+int bcosk_set_cluster(int32_t size);
+
 /* 1 (default) = launches with block_n 64 and a K loop of <= 4 stages use the 3-CTA-per-SM variant.  Returns the previous setting. */
 int bcosk_set_light(int32_t enabled);
 

@@ -16,19 +16,23 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--arch", default="resnet50")
 ap.add_argument("--only", default="")
 ap.add_argument("--planes", type=int, default=1)
-ap.add_argument("--persistent", type=int, default=1)
+ap.add_argument("--persistent", type=int, default=0)
+ap.add_argument("--cluster", type=int, default=1)
 a = ap.parse_args()
 from bcos_b200 import _lib
 _lib.load().bcosk_set_persistent(a.persistent)
+_lib.load().bcosk_set_cluster(a.cluster)
 plan = synthetic_resnet_plan(a.arch, a.batch, planes=a.planes, device="cuda", input_u8=True)
 imgs = torch.from_numpy(synth.synth_images_u8(32, 224, 5)).repeat((a.batch + 31) // 32, 1, 1, 1)[:a.batch].contiguous()
 plan.load_input(imgs)
 ops = plan.fwd_ops + plan.bwd_ops
-for _ in range(2):
+sel = [s for s in a.only.split(",") if s]
+for _ in range(1 if sel else 2):
     for o in ops:
         o.run()
 torch.cuda.synchronize()
-sel = [s for s in a.only.split(",") if s]
+n_tile = sum(1 for o in ops if type(o).__name__ == "IgemmOp" and not o.flat)
+print("per-tile/persistent igemm launches in the warm step:", n_tile, "(use as ncu --launch-skip with -k regex:bcosk_igemm)")
 for o in ops:
     if not sel or o.name in sel:
         o.run()

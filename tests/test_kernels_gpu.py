@@ -292,6 +292,46 @@ def test_persistent_and_per_tile_schedules_agree(bcosk_lib):
                 assert torch.equal(a, b)
 
 
+def test_cluster_multicast_matches_single_cta(bcosk_lib):
+    """128-wide, K-heavy launches with the weight tile multicast across a cluster of 2 / 4 row blocks == no cluster"""
+    outs = {}
+    for cl in (1, 2, 4, 3):                         # 3 = CTA pairs (cta_group::2)
+        prev = bcosk_lib.bcosk_set_cluster(cl)
+        try:
+            g = torch.Generator().manual_seed(33)
+            nb, h, cin, cout = 4, 16, 64, 256          # M = 1024 -> 8 row blocks, K = 576 -> 9 stages, two n tiles
+            plan = _mini_plan(nb, 1)
+            x = _rand_act(g, nb, h, h, cin, 1)
+            w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+            plan.sd = {"bn.running_var": torch.rand(cout, generator=g) + 0.5, "bn.weight": torch.rand(cout, generator=g) + 0.5}
+            res = _rand_act(g, nb, h, h, cout, 1)
+            y, rec = plan._conv_fwd("c", x, w, 1, 1, 1, bn="bn", relu=True, res=res, want_mask=True)
+            assert plan.fwd_ops[-1].resolved_block_n() == 128
+            # its data gradient: K = 9 * 256
+            plan._alloc_ghat(rec)
+            rec.ghat.copy_(torch.randn(nb, h, h, cout, generator=g).to(plan.dt))
+            yb = torch.zeros(nb, h, h, 128, dtype=plan.dt)
+            w2 = torch.randn(cout, 128, 3, 3, generator=g) / 48
+            rec2 = type(rec)("d", w2, 1, 1, 1, (h, h), (h, h), 128)
+            rec2.ghat, rec2.ghat_map, rec2.algo_flops = rec.ghat, None, 0.0
+            plan._dgrad(rec2, y=yb, mul1=(torch.rand(nb * h * h, 128, generator=g) + 0.5).to(plan.gain_dt))
+            assert plan.bwd_ops[-1].resolved_block_n() == 128
+            ops = plan.fwd_ops + plan.bwd_ops
+            if cl == 1:
+                print(_run_and_compare(ops))
+            memo = {}
+            dops = [U.to_device(o, "cuda", memo) for o in ops]
+            for o in dops:
+                o.run()
+            torch.cuda.synchronize()
+            outs[cl] = [t.cpu() for t in (dops[0].y, dops[0].gain, dops[0].maskbits, dops[0].sq_out, dops[1].y)]
+        finally:
+            bcosk_lib.bcosk_set_cluster(prev)
+    for cl in (2, 4, 3):
+        for a, b in zip(outs[cl], outs[1]):
+            assert torch.equal(a, b), cl
+
+
 def test_elementwise_kernels(bcosk_lib):
     g = torch.Generator().manual_seed(5)
     nb, S = 3, 32
