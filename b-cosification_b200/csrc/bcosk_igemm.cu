@@ -41,14 +41,21 @@ template <int BN, bool HP = false, bool LIGHT = false> struct TileCfg {
   static constexpr int kSmemBytes = kStages * (A_STAGE_BYTES + kBStageBytes) + 1024 + 256 + 2 * BN * 4;
 };
 
+#ifdef BCOSK_TIMING2
+#define BCOSK_TIMING
+#endif
 #ifdef BCOSK_TIMING
 // Experiment-only instrumentation (never in the shipped library): per-CTA clock64 stamps of the per-tile kernel.
 __device__ unsigned long long* g_timing_buf = nullptr;
 __device__ int g_timing_cap = 0;
+#ifdef BCOSK_TIMING2
+#define BCOSK_STAMP(slot) do { } while (0)
+#else
 #define BCOSK_STAMP(slot)                                                                                  \
   do {                                                                                                     \
     if (g_timing_buf != nullptr && (int)blockIdx.x < g_timing_cap) g_timing_buf[blockIdx.x * 8 + (slot)] = clock64(); \
   } while (0)
+#endif
 // accumulate a duration into slot `slot` of this CTA (each slot has one writer thread)
 #define BCOSK_TACC_BEGIN() const long long _tacc0 = clock64()
 #define BCOSK_TACC(slot)                                                                                      \
@@ -59,6 +66,13 @@ __device__ int g_timing_cap = 0;
 #define BCOSK_STAMP(slot) do { } while (0)
 #define BCOSK_TACC_BEGIN() do { } while (0)
 #define BCOSK_TACC(slot) do { } while (0)
+#endif
+#ifdef BCOSK_TIMING2
+#define BCOSK_TACC2_BEGIN() BCOSK_TACC_BEGIN()
+#define BCOSK_TACC2(slot) BCOSK_TACC(slot)
+#else
+#define BCOSK_TACC2_BEGIN() do { } while (0)
+#define BCOSK_TACC2(slot) do { } while (0)
 #endif
 
 struct RowInfo {
@@ -639,7 +653,11 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       int seg = 0, tap = 0, kc = 0;
       for (int it = 0; it < num_iters; ++it) {
         uint8_t* slot = smem + stage * Cfg::kSlotBytes;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        {
+          BCOSK_TACC2_BEGIN();
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          BCOSK_TACC2(0);
+        }
         if constexpr (PAIR) {
           // both CTAs' stages are counted on the LEADER's barrier (it alone issues the pair MMA)
           const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
@@ -695,17 +713,33 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         uint32_t accumulate = 0;
         for (int it = 0; it < num_iters; ++it) {
           uint8_t* slot = smem + stage * Cfg::kSlotBytes;
-          mbar_wait(&full_bar[stage], phase);
+          {
+            BCOSK_TACC2_BEGIN();
+            mbar_wait(&full_bar[stage], phase);
+            BCOSK_TACC2(1);
+          }
           tc_fence_after();
-          for (int j = 0; j < chunks_per_stage; ++j) {
-            const uint64_t da = umma_smem_desc_kmajor(smem_u32(slot + j * a_chunk_bytes), row_bytes);
-            const uint64_t db = umma_smem_desc_kmajor(smem_u32(slot + A_STAGE_BYTES + j * b_half_chunk), row_bytes);
-            for (int k = 0; k < mma_per_chunk; ++k) {
-              umma_f16_2cta(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
-              accumulate = 1;
+          BCOSK_TACC2_BEGIN();
+          if (chunks_per_stage == 1) {
+            const uint64_t da = umma_smem_desc_kmajor(smem_u32(smem), 128) + (uint64_t)stage * (Cfg::kSlotBytes >> 4);
+            const uint64_t db = da + (A_STAGE_BYTES >> 4);
+            umma_f16_2cta(tmem_base, da, db, idesc, accumulate);
+            umma_f16_2cta(tmem_base, da + 2, db + 2, idesc, 1);
+            umma_f16_2cta(tmem_base, da + 4, db + 4, idesc, 1);
+            umma_f16_2cta(tmem_base, da + 6, db + 6, idesc, 1);
+            accumulate = 1;
+          } else {
+            for (int j = 0; j < chunks_per_stage; ++j) {
+              const uint64_t da = umma_smem_desc_kmajor(smem_u32(slot + j * a_chunk_bytes), row_bytes);
+              const uint64_t db = umma_smem_desc_kmajor(smem_u32(slot + A_STAGE_BYTES + j * b_half_chunk), row_bytes);
+              for (int k = 0; k < mma_per_chunk; ++k) {
+                umma_f16_2cta(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
+                accumulate = 1;
+              }
             }
           }
           umma_commit_2cta(&empty_bar[stage], 0x3);
+          BCOSK_TACC2(3);
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
         umma_commit_2cta(tmem_full_bar, 0x3);
@@ -716,6 +750,8 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const uint32_t a_chunk_bytes = BM * p.kch * 2;
       const uint32_t b_chunk_bytes = BN * p.kch * 2;
       const int mma_per_chunk = p.kch / 16;
+      const uint64_t da_stage0 = umma_smem_desc_kmajor(smem_u32(smem), 128);
+      const uint64_t slot16 = Cfg::kSlotBytes >> 4;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t accumulate = 0;
@@ -730,20 +766,38 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           accumulate = 0;
         }
         uint8_t* slot = smem + stage * Cfg::kSlotBytes;
-        mbar_wait(&full_bar[stage], phase);
+        {
+          BCOSK_TACC2_BEGIN();
+          mbar_wait(&full_bar[stage], phase);
+          BCOSK_TACC2(1);
+        }
         tc_fence_after();
-        for (int j = 0; j < chunks_per_stage; ++j) {
-          const uint64_t da = umma_smem_desc_kmajor(smem_u32(slot + j * a_chunk_bytes), row_bytes);
-          const uint64_t db = umma_smem_desc_kmajor(smem_u32(slot + A_STAGE_BYTES + j * b_chunk_bytes), row_bytes);
-          for (int k = 0; k < mma_per_chunk; ++k) {
-            // advance 16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
-            accumulate = 1;
+        BCOSK_TACC2_BEGIN();
+        if (chunks_per_stage == 1) {
+          // 64-channel chunks: four K steps per stage, descriptors differ by constants only (the issuing thread must
+          // stay below the 64 cycles a 128 x 128 x 16 MMA takes; the generic loop below costs ~170 per MMA)
+          const uint64_t da = da_stage0 + (uint64_t)stage * slot16;
+          const uint64_t db = da + (A_STAGE_BYTES >> 4);
+          umma_f16(tmem_d, da, db, idesc, accumulate);
+          umma_f16(tmem_d, da + 2, db + 2, idesc, 1);
+          umma_f16(tmem_d, da + 4, db + 4, idesc, 1);
+          umma_f16(tmem_d, da + 6, db + 6, idesc, 1);
+          accumulate = 1;
+        } else {
+          for (int j = 0; j < chunks_per_stage; ++j) {
+            const uint64_t da = umma_smem_desc_kmajor(smem_u32(slot + j * a_chunk_bytes), row_bytes);
+            const uint64_t db = umma_smem_desc_kmajor(smem_u32(slot + A_STAGE_BYTES + j * b_chunk_bytes), row_bytes);
+            for (int k = 0; k < mma_per_chunk; ++k) {
+              // advance 16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
+              umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, accumulate);
+              accumulate = 1;
+            }
           }
         }
         // frees the smem slot once these MMAs have read it (in every CTA of the cluster: their multicasts land here too)
         if (cl > 1) umma_commit_mc(&empty_bar[stage], cl_mask);
         else umma_commit(&empty_bar[stage]);
+        BCOSK_TACC2(3);
         if (HP) umma_commit(&acc_full_bar[it & 1]);
         if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
@@ -857,8 +911,13 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
       if (use_in_tile) mbar_wait(in_bar, 0);
       if (et == 0) BCOSK_STAMP(3);   // input tile landed
-      mbar_wait(tmem_full_bar, 0);  // all MMAs done: accumulator complete AND every pipeline slot is drained
+      {
+        BCOSK_TACC2_BEGIN();
+        mbar_wait(tmem_full_bar, 0);  // all MMAs done: accumulator complete AND every pipeline slot is drained
+        if (et == 0) { BCOSK_TACC2(4); }
+      }
       tc_fence_after();
+      BCOSK_TACC2_BEGIN();
       if (et == 0) BCOSK_STAMP(4);   // accumulator ready
 #pragma unroll 1
       for (int j = 0; j < BN / 32; ++j) {
@@ -875,6 +934,7 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                                 row, fast, pick_word<BN / 32>(mb_pre, j));
       }
       if (et == 0) BCOSK_STAMP(5);   // epilogue math done
+      if (et == 0) { BCOSK_TACC2(5); }
       if (tl.out1 != 0 || tl.out2 != 0) {
         // generic-proxy smem writes -> visible to the async proxy, then one thread issues the bulk tensor stores
         fence_proxy_async_smem();
