@@ -829,6 +829,7 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       ri.q = rem - ri.p * p.oq;
     }
     const int64_t yrow = p.os_0 + (int64_t)ri.img * p.os_n + (int64_t)ri.p * p.os_p + (int64_t)ri.q * p.os_q;
+    if (MODE == BCOSK_MODE_EXPLAIN && p.side_mapped) ri.m = (int)yrow;   // side tensors follow the mapped output row
     float inv_norm = 1.f;
     int64_t add_row = -1;
     if (MODE == BCOSK_MODE_FWD) {
@@ -1268,6 +1269,7 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
         ri.q = rem - ri.p * p.oq;
       }
       const int64_t yrow = p.os_0 + (int64_t)ri.img * p.os_n + (int64_t)ri.p * p.os_p + (int64_t)ri.q * p.os_q;
+    if (MODE == BCOSK_MODE_EXPLAIN && p.side_mapped) ri.m = (int)yrow;   // side tensors follow the mapped output row
       int64_t add_row = -1;
       if (MODE == BCOSK_MODE_EXPLAIN && p.add != nullptr && ri.valid) {
         const int s = p.add_stride;
@@ -1522,6 +1524,7 @@ bcosk_igemm_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       ri.valid = ri.p < p.op && ri.q < p.oq;
       ri.m = ri.valid ? (img * p.op + ri.p) * p.oq + ri.q : 0;
       const int64_t yrow = p.os_0 + (int64_t)ri.img * p.os_n + (int64_t)ri.p * p.os_p + (int64_t)ri.q * p.os_q;
+    if (MODE == BCOSK_MODE_EXPLAIN && p.side_mapped) ri.m = (int)yrow;   // side tensors follow the mapped output row
       float inv_norm = 1.f;
       uint32_t mb = 0xffffffffu;
       int64_t add_row = -1;
@@ -1835,6 +1838,8 @@ static int validate(const bcosk_igemm_params& p) {
     return set_error(BCOSK_EINVAL, "igemm: bad sq_in geometry");
   if (p.y_ld % (p.y_f32 ? 4 : 8) != 0) return set_error(BCOSK_EINVAL, "igemm: y_ld alignment");
   if (p.a_nb < 1 || p.op < 1 || p.oq < 1) return set_error(BCOSK_EINVAL, "igemm: empty problem");
+  if (p.side_mapped && (p.mode != BCOSK_MODE_EXPLAIN || p.add != nullptr))
+    return set_error(BCOSK_EINVAL, "igemm: side_mapped needs explain mode without an extra gradient");
   return BCOSK_OK;
 }
 
@@ -1861,8 +1866,8 @@ static int make_maps(const bcosk_igemm_params& p, int bn, int cluster, LaunchMap
       if (p.gain && !p.gain_f32) aux->tma_out2 = map16(&mp->out2, p.gain, p.gain_ld) ? 1 : 0;
       if (p.res && p.res_planes == 1) aux->tma_in = map16(&mp->in, p.res, p.res_ld) ? 1 : 0;
     } else {
-      if (p.out2 && p.out2_planes == 1) aux->tma_out2 = map16(&mp->out2, p.out2, p.out2_ld) ? 1 : 0;
-      if (p.mul1 && !p.mul1_f32) aux->tma_in = map16(&mp->in, p.mul1, p.mul1_ld) ? 2 : 0;
+      if (p.out2 && p.out2_planes == 1 && !p.side_mapped) aux->tma_out2 = map16(&mp->out2, p.out2, p.out2_ld) ? 1 : 0;
+      if (p.mul1 && !p.mul1_f32 && !p.side_mapped) aux->tma_in = map16(&mp->in, p.mul1, p.mul1_ld) ? 2 : 0;
       // second input tile: the extra gradient, when it is dense over the same rows (identity shortcuts) and the tile
       // shape leaves two ring stages (64-wide tiles have 4 slots)
       if (aux->tma_in && bn == 64 && p.add && p.add_planes == 1 && p.add_stride == 1 && p.add_p == p.op && p.add_q == p.oq)

@@ -117,6 +117,7 @@ class PlanBase:
     # launches whose K loop has at most this many 64-deep stages are bandwidth bound: they use 64-wide tiles, which
     # the library runs with 3 CTAs per SM (more bytes in flight); 0 disables
     light_k_iters = 4
+    parity_dgrad = True              # strided k x k data gradients as stride^2 parity-class launches (no zero insertion)
     flat_stem = True                 # stem and its data gradient as flat-window launches (throughput mode only)
     autotune_default = True          # capture() measures the per-launch schedule first (see autotune)
     fold_bn = True   # fold sqrt(BN multiplier) into the conv weights when every multiplier is positive and there is no bias
@@ -191,11 +192,11 @@ class PlanBase:
         return Act(y, o, sq, parts), rec
 
     # ------------------------------------------------------------------ explanation emission
-    def _alloc_ghat(self, rec: ConvRec) -> None:
+    def _alloc_ghat(self, rec: ConvRec, classes: bool = False) -> None:
         """Buffer for g_out * gain of `rec`.  A strided k>1 conv reads it zero-inserted at input resolution so
         that its data gradient is a stride-1 gather."""
         nb, pl = self.nb, self.planes
-        if rec.stride > 1 and rec.k > 1:
+        if rec.stride > 1 and rec.k > 1 and not (classes and self.parity_dgrad):
             h, w = rec.in_hw
             assert rec.stride * (rec.out_hw[0] - 1) <= h - 1 and rec.stride * (rec.out_hw[1] - 1) <= w - 1
             rec.ghat = self._zeros(nb, h, w, pl * rec.cout)
@@ -210,6 +211,9 @@ class PlanBase:
         """Data gradient of `rec` as a stride-1 gather over rec.ghat (tcgen05 implicit GEMM, explain epilogue)."""
         g = rec.ghat
         k = rec.k
+        if rec.stride > 1 and k > 1 and rec.ghat_map is None:
+            assert add is None and out2 is None and y_map is None and not y_f32 and not flat
+            return self._dgrad_classes(rec, y=y, mul1=mul1, kch=kch)
         if rec.stride > 1 and k == 1:
             oh, ow = rec.out_hw      # dense GEMM at output resolution; consumer adds it sub-sampled
         else:
@@ -232,6 +236,46 @@ class PlanBase:
             out_map=y_map, add=add, add_planes=self.planes, add_stride=add_stride, mul1=mul1, out2=out2,
             out2_planes=self.planes, mul2=mul2, mask2=mask2, flat=flat, algo_flops=rec.algo_flops,
             a_dense_frac=1.0 / (rec.stride * rec.stride) if rec.ghat_map is not None else 1.0))
+
+    def _dgrad_classes(self, rec: ConvRec, *, y: Tensor, mul1: Optional[Tensor], kch: int = 64) -> None:
+        """Strided k x k data gradient over the DENSE gradient tensor, one launch per parity class of the input pixel.
+
+        gx[s*i+py, s*j+px] = sum over the taps dy = ry + s*t (ry = (py+pad) % s) of g[i + cy - t, ...] W[dy, dx]^T with
+        cy = (py + pad - ry) / s: a stride-1 gather with Ty x Tx taps whose lower corner is cy - (Ty - 1).  The s*s launches
+        do k*k/(s*s) taps per input pixel; a zero-inserted gradient would cost k*k (include/bcosk.h `side_mapped`)."""
+        g = rec.ghat
+        k, s, pad = rec.k, rec.stride, rec.pad_lo
+        assert rec.pad_lo == rec.pad_hi
+        ih, iw = rec.in_hw
+        n = rec.cin_phys
+        nz = float((rec.w != 0).sum().item())
+        for py in range(s):
+            ry = (py + pad) % s
+            dys = list(range(ry, k, s))
+            cy = (py + pad - ry) // s
+            for px in range(s):
+                rx = (px + pad) % s
+                dxs = list(range(rx, k, s))
+                cx = (px + pad - rx) // s
+                ty, tx = len(dys), len(dxs)
+                assert ty > 0 and tx > 0, "a parity class without taps (k < stride) is not handled here"
+                oh, ow = (ih - py + s - 1) // s, (iw - px + s - 1) // s
+                lo_h, lo_w = cy - (ty - 1), cx - (tx - 1)
+                # tap (jx, jy) reads g[i + lo_h + jy] -> t = ty - 1 - jy -> dy = ry + s * (ty - 1 - jy)
+                sel = [(dys[ty - 1 - jy], dxs[tx - 1 - jx]) for jy in range(ty) for jx in range(tx)]
+                wt = torch.stack([rec.w[:, :, dy, dx].t() for dy, dx in sel], 1)       # [c, taps, o]
+                if wt.shape[0] < n:
+                    wt = torch.cat([wt, wt.new_zeros(n - wt.shape[0], *wt.shape[1:])], 0)
+                bmat, cpt = P.pack_b(wt, self.planes, kch, self.dt)
+                self.bwd_ops.append(O.IgemmOp(
+                    name=f"{rec.name}.dgrad.c{py}{px}", a=g, b=self._dev(bmat, self.dt), n=n, lo=(lo_w, lo_h),
+                    up=(ow - g.shape[2] + lo_w, oh - g.shape[1] + lo_h), stride=(1, 1), op=oh, oq=ow, kch=kch,
+                    chunks_per_tap=cpt, taps=[(jx, jy) for jy in range(ty) for jx in range(tx)],
+                    seg_a_choff=P.seg_a_offsets(self.planes, rec.cout), dtype=self.dt_code, mode=L.BCOSK_MODE_EXPLAIN,
+                    block_n=self._block_n(n, bmat.shape[1] // 64), hp_accum=self.hp_accum, y=y, y_planes=self.planes,
+                    out_map=(py * iw + px, ih * iw, s * iw, s), mul1=mul1, side_mapped=True,
+                    algo_flops=rec.algo_flops * (sum(float((rec.w[:, :, dy, dx] != 0).sum().item()) for dy, dx in sel) / nz),
+                    a_dense_frac=1.0 / (s * s)))    # the s*s launches together read the gradient once
 
     # ------------------------------------------------------------------ execution
     def _require_gpu(self) -> None:

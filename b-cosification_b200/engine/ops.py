@@ -71,6 +71,7 @@ class IgemmOp:
     hp_accum: bool = False           # per-stage TMEM accumulators summed in registers (parity mode)
     sched: int = 0                   # include/bcosk.h `sched`: 0 default, 1 per tile, 2 persistent, 3 persistent row blocks
     flat: bool = False               # include/bcosk.h `a_flat`: `a` is the interior view of a zero-bordered buffer
+    side_mapped: bool = False        # include/bcosk.h `side_mapped`: mul1 / out2 / ... follow the mapped output row
 
     # ---- derived ----
     @property
@@ -98,9 +99,13 @@ class IgemmOp:
         total += ydense
         if self.inv_norm is None and self.sq_in is not None:
             total += nbytes(self.sq_in)
-        for t in (self.inv_norm, self.alpha, self.beta, self.res, self.gain, self.maskbits, self.sq_out, self.add,
-                  self.mul1, self.out2, self.mul2, self.mask2):
+        for t in (self.inv_norm, self.alpha, self.beta, self.res, self.gain, self.maskbits, self.sq_out, self.add):
             total += nbytes(t)
+        for t in (self.mul1, self.out2, self.mul2, self.mask2):
+            if t is not None and self.side_mapped:      # a parity-class launch touches only its own rows of these
+                total += float(self.M * t.shape[-1] * t.element_size())
+            else:
+                total += nbytes(t)
         return total
 
     def flat_geometry(self) -> Tuple[int, int, int, int]:
@@ -201,6 +206,7 @@ class IgemmOp:
             p.mask2_ld = self.mask2.shape[-1]
         p.hp_accum = int(self.hp_accum)
         p.sched = int(self.sched)
+        p.side_mapped = int(self.side_mapped)
         if self.flat:
             wp, hp, origin, total = self.flat_geometry()
             p.a_flat, p.a_wp, p.a_hp, p.a_flat_rows = 1, wp, hp, total - origin

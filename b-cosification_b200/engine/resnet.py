@@ -125,8 +125,10 @@ class ResNetPlan(PlanBase):
     def _build_explain(self, want_grad6: bool) -> None:
         nb, pl = self.nb, self.planes
         for blk in self.blocks:
-            for r in blk.convs:
-                self._alloc_ghat(r)
+            for j, r in enumerate(blk.convs):
+                # convs after the first get their gradient from a plain data-gradient epilogue (no shortcut terms):
+                # their own strided data gradient can run as parity classes over the dense tensor
+                self._alloc_ghat(r, classes=j > 0)
             if blk.ds is not None:
                 self._alloc_ghat(blk.ds)
                 blk.side = blk.ds.ghat

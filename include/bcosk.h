@@ -138,6 +138,12 @@ typedef struct bcosk_igemm_params {
    *      the end of the buffer.  Results are identical to the im2col gather. */
   int32_t a_flat, a_wp, a_hp;
   int64_t a_flat_rows;
+  /* ---- explain mode: 1 = mul1 / mul2 / out2 / mask2 are addressed by the MAPPED output row
+   *      (os_0 + img*os_n + p*os_p + q*os_q) like y, not by the launch's dense row.  Used by the parity-class launches
+   *      of a strided k x k data gradient: class (py, px) computes the input pixels (s*i + py, s*j + px) from the taps
+   *      that reach them, so the s*s launches together do k*k/(s*s) taps per pixel instead of k*k over a zero-inserted
+   *      gradient.  `add` is not supported together with it. */
+  int32_t side_mapped;
 } bcosk_igemm_params;
 
 int bcosk_igemm(const bcosk_igemm_params* p, void* stream);

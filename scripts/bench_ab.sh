@@ -1,8 +1,8 @@
 #!/bin/bash
-# A/B bench over library switches: usage  bench_ab.sh "name:persistent:light:light_k_iters[:autotune[:flat_stem[:cluster]]]" ...
+# A/B bench over library switches: usage  bench_ab.sh "name:persistent:light:light_k_iters[:autotune[:flat_stem[:cluster[:parity_dgrad]]]]" ...
 mkdir -p gpurun_out
 for cfg in "$@"; do
-IFS=: read NAME P L LK AT FS CL <<< "$cfg"
+IFS=: read NAME P L LK AT FS CL PD <<< "$cfg"
 python - <<PY 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$NAME', 'value', round(d['value']), 'ms', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value']), 'hbm_frac', round(d['roofline']['frac'],3), 'tc', round(d['roofline_tensor']['achieved']))"
 import sys, runpy
 sys.path.insert(0, ".")
@@ -14,6 +14,7 @@ _lib.load().bcosk_set_cluster(${CL:-2})
 PlanBase.light_k_iters = $LK
 PlanBase.autotune_default = bool(${AT:-1})
 PlanBase.flat_stem = bool(${FS:-1})
+PlanBase.parity_dgrad = bool(${PD:-1})
 sys.argv = ["bench.py", "--steps", "10", "--warmup", "3", "--no-cpu-baseline", "--layer-table", "gpurun_out/layers_$NAME.json"]
 runpy.run_path("bench.py", run_name="__main__")
 PY

@@ -160,14 +160,18 @@ def run_igemm(op: O.IgemmOp) -> None:
             ww = min(op.oq, (aq - 1) * s + 1)
             full[:, 0:hh:s, 0:ww:s] = addv[:, :(hh + s - 1) // s, :(ww + s - 1) // s]
             tot = tot + full.reshape(M, n)
+        side = rows if op.side_mapped else torch.arange(M)       # side tensors: mapped output row or dense launch row
         if op.out2 is not None:
             o = tot.clone()
             if op.mul2 is not None:
-                o = o * op.mul2.float()
+                o = o * op.mul2.float()[side]
             if op.mask2 is not None:
-                o = o * _mask_bits(op.mask2, n)
-            _split_store(op.out2.view(M, -1), o, op.out2_planes)
-        v = tot * op.mul1.float() if op.mul1 is not None else tot
+                o = o * _mask_bits(op.mask2, n)[side]
+            o2 = op.out2.view(-1, op.out2.shape[-1])
+            tmp2 = torch.zeros(M, op.out2.shape[-1], dtype=op.out2.dtype)
+            _split_store(tmp2, o, op.out2_planes)
+            o2[side] = tmp2
+        v = tot * op.mul1.float()[side] if op.mul1 is not None else tot
         y2 = op.y.view(-1, op.y.shape[-1])
         if op.y_f32:
             y2[rows] = v

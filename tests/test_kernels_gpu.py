@@ -217,6 +217,40 @@ def test_igemm_flat_window_dgrad(bcosk_lib, case):
     print(name, _run_and_compare(plan.bwd_ops))
 
 
+@pytest.mark.parametrize("case", [("dc_3x3_s2", 2, 12, 64, 128, 3, 2, 1, 1), ("dc_3x3_s2_odd", 3, 14, 64, 64, 3, 2, 1, 1),
+                                  ("dc_3x3_s2_planes2", 1, 8, 64, 64, 3, 2, 1, 2)], ids=lambda c: c[0])
+def test_igemm_dgrad_parity_classes(bcosk_lib, case):
+    """strided 3x3 data gradient as stride^2 parity-class launches over the dense gradient (side tensors by mapped row)"""
+    name, nb, h, cin, cout, k, stride, pad, planes = case
+    g = torch.Generator().manual_seed(hash(name) % 2**31)
+    plan = _mini_plan(nb, planes)
+    x = _rand_act(g, nb, h, h, cin, planes)
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    _, rec = plan._conv_fwd(name, x, w, stride, pad, pad, bn=None, relu=True, want_mask=True)
+    plan._alloc_ghat(rec, classes=True)
+    assert rec.ghat_map is None and tuple(rec.ghat.shape[1:3]) == rec.out_hw
+    oh, ow = rec.out_hw
+    tmp = torch.zeros(nb, oh, ow, planes * cout, dtype=plan.dt)
+    E._split_store(tmp, torch.randn(nb, oh, ow, cout, generator=g), planes)
+    rec.ghat.copy_(tmp)
+    M = nb * h * h
+    yb = torch.zeros(nb, h, h, planes * cin, dtype=plan.dt)
+    mul1 = (torch.rand(M, cin, generator=g) + 0.5).to(plan.gain_dt)
+    plan._dgrad(rec, y=yb, mul1=mul1)
+    assert len(plan.bwd_ops) == stride * stride and all(o.side_mapped for o in plan.bwd_ops)
+    print(name, _run_and_compare(plan.bwd_ops, tol16=BF16_TOL if planes == 1 else 2e-4))
+    # and against the zero-inserted single launch
+    plan2 = _mini_plan(nb, planes)
+    _, rec2 = plan2._conv_fwd(name, x, w, stride, pad, pad, bn=None, relu=True, want_mask=True)
+    plan2._alloc_ghat(rec2)
+    rec2.ghat[:, ::stride, ::stride][:, :oh, :ow] = tmp
+    yb2 = torch.zeros_like(yb)
+    plan2._dgrad(rec2, y=yb2, mul1=mul1)
+    E.run(plan2.bwd_ops)
+    a, b = E._join(yb, planes), E._join(yb2, planes)
+    assert (a - b).abs().max() <= (2e-2 if planes == 1 else 1e-4) * b.abs().max()
+
+
 def test_igemm_dgrad_strided_add_and_outmap(bcosk_lib):
     """conv1x1 data gradient that adds a half-resolution tensor and writes zero-inserted rows"""
     g = torch.Generator().manual_seed(11)
