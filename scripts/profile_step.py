@@ -18,6 +18,7 @@ ap.add_argument("--only", default="")
 ap.add_argument("--planes", type=int, default=1)
 ap.add_argument("--persistent", type=int, default=0)
 ap.add_argument("--cluster", type=int, default=1)
+ap.add_argument("--autotune", type=int, default=0, help="pick per-launch schedules first (as capture() does); use with ncu --profile-from-start off")
 a = ap.parse_args()
 from bcos_b200 import _lib
 _lib.load().bcosk_set_persistent(a.persistent)
@@ -27,14 +28,18 @@ imgs = torch.from_numpy(synth.synth_images_u8(32, 224, 5)).repeat((a.batch + 31)
 plan.load_input(imgs)
 ops = plan.fwd_ops + plan.bwd_ops
 sel = [s for s in a.only.split(",") if s]
+if a.autotune:
+    plan.autotune()
 for _ in range(1 if sel else 2):
     for o in ops:
         o.run()
 torch.cuda.synchronize()
 n_tile = sum(1 for o in ops if type(o).__name__ == "IgemmOp" and not o.flat)
 print("per-tile/persistent igemm launches in the warm step:", n_tile, "(use as ncu --launch-skip with -k regex:bcosk_igemm)")
+torch.cuda.profiler.start()          # ncu --profile-from-start off captures only this step
 for o in ops:
     if not sel or o.name in sel:
         o.run()
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("launches per step", len(ops), "igemm", sum(type(o).__name__ == "IgemmOp" for o in ops))
