@@ -156,6 +156,8 @@ struct IgemmAux {
   int order;     // persistent kernel: 0 = tiles strided over the grid, 1 = a CTA walks all n tiles of one row block
   int cluster;   // per-tile kernel: CTAs of `cluster` consecutive row blocks (same n tile) form a thread-block cluster;
                  // each fetches 1/cluster of the weight tile and multicasts it to the others (0/1 = no cluster)
+  int late_in;   // long K loops: fetch the epilogue input tile AFTER the main loop (into the last slot, once its final
+                 // stage is consumed) so that the ring keeps all its stages while the MMAs run
   int pair;      // cluster == 2 run as a CTA pair: one cta_group::2 MMA over both row blocks, each CTA keeps only its half
                  // of the weight tile (no multicast: the tensor core reads the other half from the peer's shared memory)
 };
@@ -590,7 +592,8 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int num_iters = total_chunks / chunks_per_stage;  // host guarantees divisibility
   const bool use_in_tile = Cfg::kTmaEpilogue && aux.tma_in != 0;
   const bool use_in2_tile = use_in_tile && aux.tma_in2 != 0;   // host guarantees >= 2 ring stages remain
-  const int num_stages = kSlots - (use_in_tile ? 1 : 0) - (use_in2_tile ? 1 : 0);
+  const bool late_in = use_in_tile && !use_in2_tile && aux.late_in != 0;
+  const int num_stages = kSlots - ((use_in_tile && !late_in) ? 1 : 0) - (use_in2_tile ? 1 : 0);
   if (threadIdx.x == 64) BCOSK_STAMP(0);
 
   if (warp == 0 && lane == 0) {
@@ -628,7 +631,7 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      if (use_in_tile) {
+      if (use_in_tile && !late_in) {
         // residual (forward) / producer gain (explain): whole 128 x BN tile, lands while the main loop runs
         uint8_t* dst = smem + (kSlots - 1) * Cfg::kSlotBytes;
         mbar_arrive_expect_tx(in_bar, Cfg::kTileBytes * (use_in2_tile ? 2 : 1));
@@ -696,6 +699,16 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         }
         if (++stage == num_stages) { stage = 0; phase ^= 1; }
+      }
+      if (late_in) {
+        // the last slot's final stage has been consumed -> it now takes the epilogue input tile
+        while (stage != kSlots - 1) {
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
+        }
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* dst = smem + (kSlots - 1) * Cfg::kSlotBytes;
+        mbar_arrive_expect_tx(in_bar, Cfg::kTileBytes);
+        for (int b = 0; b < BN / 64; ++b) tma_load_2d(dst + b * 16384, &tmap_in, in_bar, n0 + b * 64, m0);
       }
     }
   } else if (warp == 1) {
@@ -1709,6 +1722,7 @@ static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const
 }
 
 static int g_num_sms = 0;
+static int g_late_in_iters = 8;        // K stages from which the epilogue input tile is fetched after the main loop (0 = never)
 static int g_cluster = 1;              // 1 none; 2/4 weight-tile multicast across row blocks; 3 = CTA pairs (cta_group::2)
 // Measured on B200 (profiles/r01_schedule_ab.md): per-tile + 3 CTAs/SM and the persistent kernel reach the same
 // ~4 TB/s on the bandwidth-bound launches; the per-tile schedule is the default.
@@ -1909,6 +1923,10 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
   rc = make_maps(p, bn, cluster, &mp, &aux);
   if (rc) return rc;
   aux.cluster = cluster;
+  {
+    const int iters = p.num_segs * p.num_taps * p.chunks_per_tap / (STAGE_K / p.kch);
+    aux.late_in = (g_late_in_iters > 0 && bn == 128 && iters >= g_late_in_iters) ? 1 : 0;
+  }
   aux.pair = (cluster == 2 && g_cluster == 3) ? 1 : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (p.hp_accum) aux.tma_in2 = 0;
@@ -1964,6 +1982,12 @@ extern "C" int bcosk_debug_set_timing(void* buf, int32_t capacity_ctas) {
   return BCOSK_OK;
 }
 #endif
+
+extern "C" int bcosk_set_late_input(int32_t min_k_stages) {
+  const int prev = g_late_in_iters;
+  g_late_in_iters = min_k_stages;
+  return prev;
+}
 
 extern "C" int bcosk_set_cluster(int32_t size) {
   const int prev = g_cluster;

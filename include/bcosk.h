@@ -151,6 +151,11 @@ int bcosk_igemm(const bcosk_igemm_params* p, void* stream);
 /* Scheduling switch for A/B measurements: 1 = launches with block_n 64 (the bandwidth-bound ones) run on the persistent
  * one-CTA-per-SM kernel, 0 (default) = one CTA per tile everywhere.  Returns the previous setting.  Results are identical. */
 int bcosk_set_persistent(int32_t enabled);
+/* 128-wide launches whose K loop has at least `min_k_stages` 64-deep stages fetch their epilogue input tile (residual /
+ * producer gain) after the main loop instead of parking it in a ring slot, so the MMAs run on 3 stages instead of 2
+ * (0 = never).  Returns the previous setting.  Results are identical. */
+int bcosk_set_late_input(int32_t min_k_stages);
+
 /* Cluster mode of the 128-wide launches with >= 8 K stages.  1 = none.  2 / 4 = the CTAs of that many neighbouring
  * 128-row blocks each fetch a share of the weight tile and multicast it (TMA .multicast::cluster).  3 = CTA pairs:
  * two row blocks run ONE tcgen05.mma.cta_group::2 (256 x 128) issued by the leader CTA, each CTA keeps only its half of
