@@ -1722,7 +1722,7 @@ static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const
 }
 
 static int g_num_sms = 0;
-static int g_late_in_iters = 8;        // K stages from which the epilogue input tile is fetched after the main loop (0 = never)
+static int g_late_in_iters = 4;        // K stages from which the epilogue input tile is fetched after the main loop (0 = never)
 static int g_cluster = 1;              // 1 none; 2/4 weight-tile multicast across row blocks; 3 = CTA pairs (cta_group::2)
 // Measured on B200 (profiles/r01_schedule_ab.md): per-tile + 3 CTAs/SM and the persistent kernel reach the same
 // ~4 TB/s on the bandwidth-bound launches; the per-tile schedule is the default.
