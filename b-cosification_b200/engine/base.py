@@ -292,11 +292,12 @@ class PlanBase:
         O.run_ops(self.bwd_ops)
 
     def autotune(self, reps: int = 5) -> dict:
-        """Pick the schedule (include/bcosk.h `sched`) of every 64-wide tensor-core launch by measuring it in place.
+        """Pick the schedule (include/bcosk.h `sched`) of every 64-wide tensor-core launch, and the tile width (64 / 128) of
+        the launches that write no per-tile sums of squares, by measuring each candidate in place.
 
         The three schedules give bit-identical outputs (tests/test_kernels_gpu.py); which is fastest depends on N, K and
         the epilogue streams (measured: profiles/r01_schedule_ab.md), so it is decided per launch, once, before capture.
-        Returns {launch name: chosen sched}.
+        Returns {launch name: (block_n, sched)}.
         """
         self._require_gpu()
         self.run_forward()
@@ -305,27 +306,40 @@ class PlanBase:
         torch.cuda.synchronize()
         chosen = {}
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        for op in self.fwd_ops + (self.bwd_ops if self.with_explain else []):
-            if not isinstance(op, O.IgemmOp) or op.hp_accum or op.flat or op.resolved_block_n() != 64:
-                continue
-            best, best_t = 1, float("inf")
-            for sched in (1, 2, 3):
-                if sched == 3 and op.n <= 64:
-                    continue                      # a single n tile: same as 2
-                op.sched = sched
+
+        def timed(op) -> float:
+            op.run()
+            ts = []
+            for _ in range(reps):
+                ev[0].record()
                 op.run()
-                ts = []
-                for _ in range(reps):
-                    ev[0].record()
-                    op.run()
-                    ev[1].record()
-                    ev[1].synchronize()
-                    ts.append(ev[0].elapsed_time(ev[1]))
-                t = sorted(ts)[len(ts) // 2]
-                if t < best_t * 0.98:             # prefer the simpler schedule on a tie
-                    best, best_t = sched, t
-            op.sched = best
+                ev[1].record()
+                ev[1].synchronize()
+                ts.append(ev[0].elapsed_time(ev[1]))
+            return sorted(ts)[len(ts) // 2]
+
+        for op in self.fwd_ops + (self.bwd_ops if self.with_explain else []):
+            if not isinstance(op, O.IgemmOp) or op.hp_accum or op.flat:
+                continue
+            # tile width: free to choose where no per-tile partial sums of squares are written (their layout follows it)
+            widths = [op.resolved_block_n()]
+            if op.sq_out is None and op.n >= 128 and widths[0] in (64, 128):
+                widths = [64, 128]
+            if widths == [128]:
+                continue
+            best, best_t = (widths[0], 1 if widths[0] == 64 else 0), float("inf")
+            for bn in widths:
+                op.block_n = bn
+                for sched in ((1, 2, 3) if bn == 64 else (0,)):
+                    if sched == 3 and op.n <= 64:
+                        continue                      # a single n tile: same as 2
+                    op.sched = sched
+                    t = timed(op)
+                    if t < best_t * 0.98:             # prefer the earlier (simpler) candidate on a tie
+                        best, best_t = (bn, sched), t
+            op.block_n, op.sched = best
             chosen[op.name] = best
+            op.run()                                  # leave the tensors as the chosen configuration writes them
         self.schedules = chosen
         return chosen
 
