@@ -106,10 +106,10 @@ int make_tiled_map_nd(CUtensorMap* map, const void* base, int elem_bytes, int ra
                       const long long* strides_bytes, const int* box, int swizzle_bytes) {
   int rc = resolve_driver();
   if (rc) return rc;
-  if (rank < 2 || rank > 3) return set_error(BCOSK_EINVAL, "tiled map: rank");
+  if (rank < 2 || rank > 4) return set_error(BCOSK_EINVAL, "tiled map: rank");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(BCOSK_EINVAL, "tiled map: base not 16B aligned");
-  cuuint64_t d[3], st[2];
-  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  cuuint64_t d[4], st[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) {
     d[i] = (cuuint64_t)dims[i];
     bx[i] = (cuuint32_t)box[i];

@@ -1368,6 +1368,12 @@ struct FlatGeom {
   int box_rows;    // rows per window box (multiple of 8, <= 256)
   int nbox;        // 1 or 2
   int tiles_img;   // 128-position tiles per image
+  int pitch;       // pixels per (padded) row of the flattened positions
+  int dense;       // 1: `a` is a plain dense tensor; the zero borders exist only in shared memory (one 4-D TMA box of
+                   // `nrows` x `pitch` pixels per tile whose out-of-range pixels are zero filled)
+  int nrows;
+  int tma_store;   // 1: a tile is a whole number of image rows (128 % pitch == 0): staged outputs leave through clipped
+                   // 3-D TMA stores with non-negative start coordinates (one per image row) instead of the copy-out loop
 };
 
 template <int BN>
@@ -1381,6 +1387,7 @@ struct FlatCfg {
 template <int BN, int MODE, typename T>
 __global__ void __launch_bounds__(FlatCfg<BN>::kThreads, 1)
 bcosk_igemm_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        const __grid_constant__ CUtensorMap tmap_out1, const __grid_constant__ CUtensorMap tmap_out2,
                         const __grid_constant__ bcosk_igemm_params p, const IgemmAux aux, const FlatGeom geo) {
   using Cfg = FlatCfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -1389,7 +1396,7 @@ bcosk_igemm_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   const uint32_t row_bytes = (uint32_t)p.kch * 2;
   const uint32_t b_chunk_bytes = BN * row_bytes;
   const uint32_t b_bytes = (uint32_t)p.num_taps * b_chunk_bytes;
-  const uint32_t win_bytes = (uint32_t)geo.nbox * geo.box_rows * row_bytes;
+  const uint32_t win_bytes = geo.dense ? (uint32_t)geo.nrows * geo.pitch * row_bytes : (uint32_t)geo.nbox * geo.box_rows * row_bytes;
   const bool any_out_tile = aux.tma_out1 || aux.tma_out2;
   uint8_t* s_b = smem;
   uint8_t* s_win = s_b + ((b_bytes + 1023u) & ~1023u);                         // [2][win_bytes], 1024-aligned
@@ -1427,7 +1434,7 @@ bcosk_igemm_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
     tmem_relinquish();
     for (int t = lane; t < p.num_taps; t += 32)
-      s_aoff[t] = ((uint32_t)(p.tap_off_h[t] * p.a_wp + p.tap_off_w[t]) * row_bytes) >> 4;
+      s_aoff[t] = ((uint32_t)(p.tap_off_h[t] * geo.pitch + p.tap_off_w[t]) * row_bytes) >> 4;
   }
   if (MODE == BCOSK_MODE_FWD && warp >= 2) {
     for (int c = threadIdx.x - 64; c < BN; c += Cfg::kEpiWarps * 32) {
@@ -1456,9 +1463,14 @@ bcosk_igemm_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
           BCOSK_TACC(0);
         }
         mbar_arrive_expect_tx(&win_full_bar[buf], win_bytes);
-        for (int bx = 0; bx < geo.nbox; ++bx)
-          tma_load_2d(s_win + buf * win_stride + bx * geo.box_rows * row_bytes, &tmap_a, &win_full_bar[buf], 0,
-                      img * img_rows + m0 + bx * geo.box_rows);
+        if (geo.dense) {
+          // input rows p0 + lo_h .. of this image, pixels lo_w .. lo_w + pitch - 1: borders arrive as zeros
+          tma_load_4d(s_win + buf * win_stride, &tmap_a, &win_full_bar[buf], 0, p.lo_w, m0 / geo.pitch + p.lo_h, img);
+        } else {
+          for (int bx = 0; bx < geo.nbox; ++bx)
+            tma_load_2d(s_win + buf * win_stride + bx * geo.box_rows * row_bytes, &tmap_a, &win_full_bar[buf], 0,
+                        img * img_rows + m0 + bx * geo.box_rows);
+        }
       }
     }
   } else if (warp == 1) {
@@ -1486,7 +1498,11 @@ bcosk_igemm_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         BCOSK_TACC_BEGIN();
         // one LDS + two 64-bit adds per tap, then the K steps unrolled: the issuing thread must stay well under the
         // ~48 cycles a 128 x 64 x 16 MMA takes (measured: scripts/exp/mma_rate.cu), a naive loop costs ~240 per MMA
-        const uint64_t da0 = umma_smem_desc_kmajor(smem_u32(s_win + buf * win_stride), row_bytes);
+        uint64_t da0 = umma_smem_desc_kmajor(smem_u32(s_win + buf * win_stride), row_bytes);
+        if (geo.dense) {
+          const int m0 = (t % geo.tiles_img) * BM;
+          da0 += ((uint32_t)(m0 % geo.pitch) * row_bytes) >> 4;      // the window starts at the tile's first image row
+        }
         uint64_t db = db0;
         const uint32_t tmem_d = tmem_base + buf * BN;
         {
@@ -1532,8 +1548,8 @@ bcosk_igemm_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       const int mf = m0 + row;                         // flattened position p * a_wp + x
       RowInfo ri;
       ri.img = img;
-      ri.p = mf / p.a_wp;
-      ri.q = mf - ri.p * p.a_wp;
+      ri.p = mf / geo.pitch;
+      ri.q = mf - ri.p * geo.pitch;
       ri.valid = ri.p < p.op && ri.q < p.oq;
       ri.m = ri.valid ? (img * p.op + ri.p) * p.oq + ri.q : 0;
       const int64_t yrow = p.os_0 + (int64_t)ri.img * p.os_n + (int64_t)ri.p * p.os_p + (int64_t)ri.q * p.os_q;
@@ -1586,23 +1602,38 @@ bcosk_igemm_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 #ifdef BCOSK_TIMING
       const long long _t_c = clock64();
 #endif
+      if (any_out_tile && geo.tma_store) {
+        fence_proxy_async_smem();
+        if (et == 0) tma_store_wait_read();           // tile i-1's stores have read the other staging buffer
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kEpiWarps * 32) : "memory");
-      if (any_out_tile) {
+      if (any_out_tile && geo.tma_store) {
+        if (et == 0) {
+          const int p0 = m0 / geo.pitch;              // the tile starts at x = 0 of image row p0
+          for (int k = 0; k < BM / geo.pitch && p0 + k < p.op; ++k) {
+            const uint32_t off = (uint32_t)(k * geo.pitch) << 7;
+            if (tl.out1 != 0) tma_store_3d_addr(&tmap_out1, tl.out1 + off, 0, 0, img * p.op + p0 + k);
+            if (tl.out2 != 0) tma_store_3d_addr(&tmap_out2, tl.out2 + off, 0, 0, img * p.op + p0 + k);
+          }
+          tma_store_commit();
+        }
+      } else if (any_out_tile) {
         // copy the staged tiles out: 8 lanes per row write one 128-byte line each, rows at x >= oq are skipped.
         // (TMA stores cannot do this: a tile's rows belong to up to three image rows and a negative start coordinate
         // is an illegal instruction for cp.async.bulk.tensor stores - scripts/exp/tma_store3d.cu.)
         T* y16 = reinterpret_cast<T*>(p.y);
-        T* g16 = reinterpret_cast<T*>(p.gain);
+        T* g16 = reinterpret_cast<T*>(MODE == BCOSK_MODE_FWD ? p.gain : p.out2);
+        const int g_ld = MODE == BCOSK_MODE_FWD ? p.gain_ld : p.out2_ld;
         for (int it = et; it < BM * 8; it += Cfg::kEpiWarps * 32) {
           const int r = it >> 3, u = it & 7;
           const int mfr = m0 + r;
-          const int pr = mfr / p.a_wp;
-          const int xr = mfr - pr * p.a_wp;
+          const int pr = mfr / geo.pitch;
+          const int xr = mfr - pr * geo.pitch;
           if (pr < p.op && xr < p.oq && u * 8 < p.n) {
             const size_t d = (size_t)(img * p.op + pr) * p.oq + xr;
             const uint32_t off = (uint32_t)(r << 7) + (uint32_t)((u ^ (r & 7)) << 4);
             if (tl.out1 != 0) *reinterpret_cast<uint4*>(y16 + d * p.y_ld + u * 8) = lds128(tl.out1 + off);
-            if (tl.out2 != 0) *reinterpret_cast<uint4*>(g16 + d * p.gain_ld + u * 8) = lds128(tl.out2 + off);
+            if (tl.out2 != 0) *reinterpret_cast<uint4*>(g16 + d * g_ld + u * 8) = lds128(tl.out2 + off);
           }
         }
       }
@@ -1622,6 +1653,7 @@ bcosk_igemm_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       }
 #endif
     }
+    if (any_out_tile && geo.tma_store && et == 0) tma_store_wait_read();
     tc_fence_before();
   }
 
@@ -1760,31 +1792,51 @@ static int launch_persistent(const LaunchMaps& mp, const bcosk_igemm_params& p, 
 template <int BN, int MODE>
 static int launch_flat_bn(const bcosk_igemm_params& p, cudaStream_t st) {
   using Cfg = FlatCfg<BN>;
-  const int wp = p.a_wp, hp = p.a_hp;
-  int max_off = 0;
+  const bool dense = p.a_flat == 2;
+  int kw = 1, kh = 1;
   for (int t = 0; t < p.num_taps; ++t) {
     if (p.tap_off_h[t] < 0 || p.tap_off_w[t] < 0) return set_error(BCOSK_EINVAL, "igemm(flat): negative tap offset");
-    max_off = max(max_off, p.tap_off_h[t] * wp + p.tap_off_w[t]);
+    kw = max(kw, p.tap_off_w[t] + 1);
+    kh = max(kh, p.tap_off_h[t] + 1);
   }
   FlatGeom geo;
+  memset(&geo, 0, sizeof(geo));
+  geo.dense = dense ? 1 : 0;
+  // dense input: the pitch only exists in shared memory; rows must start on a swizzle-pattern boundary (8 pixels)
+  geo.pitch = dense ? ((p.a_w + kw - 1 + 7) & ~7) : p.a_wp;
+  const int wp = geo.pitch, hp = dense ? p.a_h : p.a_hp;
+  const int max_off = (kh - 1) * wp + (kw - 1);
   const int need = BM + max_off;
   geo.nbox = need <= 256 ? 1 : 2;
   geo.box_rows = (((need + geo.nbox - 1) / geo.nbox) + 7) & ~7;
-  if (geo.box_rows > 256) return set_error(BCOSK_EUNSUPPORTED, "igemm(flat): window of %d rows does not fit two TMA boxes", need);
+  if (!dense && geo.box_rows > 256)
+    return set_error(BCOSK_EUNSUPPORTED, "igemm(flat): window of %d rows does not fit two TMA boxes", need);
   geo.tiles_img = ((p.op - 1) * wp + p.oq + BM - 1) / BM;
+  // dense: image rows touched by a tile that may start at any position of a row, plus the taps' rows
+  geo.nrows = ((BM % wp == 0 ? 0 : wp - 1) + BM - 1) / wp + kh;
+  if (dense && (geo.nrows > 256 || wp > 256)) return set_error(BCOSK_EUNSUPPORTED, "igemm(flat): window too large for one TMA box");
   const int row_bytes = p.kch * 2;
   const long long b_bytes = (long long)p.num_taps * BN * row_bytes;
-  const long long win_stride = ((long long)geo.nbox * geo.box_rows * row_bytes + 1023) & ~1023ll;
+  const long long win_stride = dense ? (((long long)geo.nrows * wp * row_bytes + 1023) & ~1023ll)
+                                     : (((long long)geo.nbox * geo.box_rows * row_bytes + 1023) & ~1023ll);
 
   LaunchMaps mp;
   memset(&mp, 0, sizeof(mp));
   IgemmAux aux{};
   {
-    const uint8_t* origin = reinterpret_cast<const uint8_t*>(p.a) + ((long long)p.lo_h * wp + p.lo_w) * p.a_c * 2;
-    const long long dims[2] = {p.a_c, p.a_flat_rows};
-    const long long strides[1] = {(long long)p.a_c * 2};
-    const int box[2] = {p.kch, geo.box_rows};
-    int rc = make_tiled_map_nd(&mp.a, origin, 2, 2, dims, strides, box, row_bytes);
+    int rc;
+    if (dense) {
+      const long long dims[4] = {p.a_c, p.a_w, p.a_h, p.a_nb};
+      const long long strides[3] = {(long long)p.a_c * 2, (long long)p.a_w * p.a_c * 2, (long long)p.a_h * p.a_w * p.a_c * 2};
+      const int box[4] = {p.kch, wp, geo.nrows, 1};
+      rc = make_tiled_map_nd(&mp.a, p.a, 2, 4, dims, strides, box, row_bytes);
+    } else {
+      const uint8_t* origin = reinterpret_cast<const uint8_t*>(p.a) + ((long long)p.lo_h * wp + p.lo_w) * p.a_c * 2;
+      const long long dims[2] = {p.a_c, p.a_flat_rows};
+      const long long strides[1] = {(long long)p.a_c * 2};
+      const int box[2] = {p.kch, geo.box_rows};
+      rc = make_tiled_map_nd(&mp.a, origin, 2, 2, dims, strides, box, row_bytes);
+    }
     if (rc) return rc;
     rc = make_tiled_map_2d(&mp.b, p.b, (long long)p.num_taps * p.kch, p.n, p.kch, BN, row_bytes);
     if (rc) return rc;
@@ -1793,9 +1845,22 @@ static int launch_flat_bn(const bcosk_igemm_params& p, cudaStream_t st) {
   auto stageable = [&](const void* base, int ld) -> bool {
     return (reinterpret_cast<uintptr_t>(base) & 15) == 0 && ld % 8 == 0;
   };
-  if (MODE == BCOSK_MODE_FWD && BN == 64 && dense_out) {   // 16-bit outputs staged in shared memory, written as full lines
+  if (BN == 64 && dense_out) {   // 16-bit outputs staged in shared memory, written as full lines
     if (!p.y_f32 && p.y_planes == 1) aux.tma_out1 = stageable(p.y, p.y_ld) ? 1 : 0;
-    if (p.gain && !p.gain_f32) aux.tma_out2 = stageable(p.gain, p.gain_ld) ? 1 : 0;
+    if (MODE == BCOSK_MODE_FWD && p.gain && !p.gain_f32) aux.tma_out2 = stageable(p.gain, p.gain_ld) ? 1 : 0;
+    if (MODE == BCOSK_MODE_EXPLAIN && p.out2 && p.out2_planes == 1) aux.tma_out2 = stageable(p.out2, p.out2_ld) ? 1 : 0;
+  }
+  if ((aux.tma_out1 || aux.tma_out2) && BM % wp == 0) {
+    // a tile is BM / pitch whole image rows: one clipped 3-D store per row and tensor (x >= oq falls outside the map)
+    auto map_out = [&](CUtensorMap* m, const void* base, int ld) -> bool {
+      const long long dims[3] = {p.n, p.oq, (long long)p.a_nb * p.op};
+      const long long strides[2] = {(long long)ld * 2, (long long)p.oq * ld * 2};
+      const int box[3] = {64, wp, 1};
+      return make_tiled_map_nd(m, base, 2, 3, dims, strides, box, 128) == BCOSK_OK;
+    };
+    const void* o2 = MODE == BCOSK_MODE_FWD ? p.gain : p.out2;
+    const int o2_ld = MODE == BCOSK_MODE_FWD ? p.gain_ld : p.out2_ld;
+    geo.tma_store = (!aux.tma_out1 || map_out(&mp.out1, p.y, p.y_ld)) && (!aux.tma_out2 || map_out(&mp.out2, o2, o2_ld)) ? 1 : 0;
   }
   const long long smem = ((b_bytes + 1023) & ~1023ll) + 2 * win_stride +
                          ((aux.tma_out1 || aux.tma_out2) ? 4 * Cfg::kTileBytes : 0) + 128 + 2 * BN * 4 +
@@ -1814,9 +1879,9 @@ static int launch_flat_bn(const bcosk_igemm_params& p, cudaStream_t st) {
   if (tiles > 0x7fffffffLL || (long long)p.a_nb * hp * wp > 0x7fffffffLL) return set_error(BCOSK_EUNSUPPORTED, "igemm(flat): too large");
   dim3 grid((unsigned)(tiles < g_num_sms ? tiles : g_num_sms));
   if (p.dtype == BCOSK_DTYPE_BF16)
-    kern<<<grid, Cfg::kThreads, smem, st>>>(mp.a, mp.b, p, aux, geo);
+    kern<<<grid, Cfg::kThreads, smem, st>>>(mp.a, mp.b, mp.out1, mp.out2, p, aux, geo);
   else
-    kern_h<<<grid, Cfg::kThreads, smem, st>>>(mp.a, mp.b, p, aux, geo);
+    kern_h<<<grid, Cfg::kThreads, smem, st>>>(mp.a, mp.b, mp.out1, mp.out2, p, aux, geo);
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }
@@ -1824,9 +1889,13 @@ static int launch_flat_bn(const bcosk_igemm_params& p, cudaStream_t st) {
 static int launch_flat(const bcosk_igemm_params& p, cudaStream_t st) {
   if (p.hp_accum || p.num_segs != 1 || p.chunks_per_tap != 1 || p.stride_w != 1 || p.stride_h != 1 || p.n > 64)
     return set_error(BCOSK_EUNSUPPORTED, "igemm(flat): needs stride 1, one segment, one chunk per tap, n <= 64, no hp_accum");
-  if (p.a_wp < p.a_w || p.a_hp < p.a_h || p.a_flat_rows < 1 || p.a_c < p.kch || p.seg_a_choff[0] != 0)
-    return set_error(BCOSK_EINVAL, "igemm(flat): bad buffer geometry");
-  if (p.oq > p.a_wp) return set_error(BCOSK_EINVAL, "igemm(flat): oq exceeds the buffer pitch");
+  if (p.a_c < p.kch || p.seg_a_choff[0] != 0) return set_error(BCOSK_EINVAL, "igemm(flat): bad channel geometry");
+  if (p.a_flat == 1) {
+    if (p.a_wp < p.a_w || p.a_hp < p.a_h || p.a_flat_rows < 1) return set_error(BCOSK_EINVAL, "igemm(flat): bad buffer geometry");
+    if (p.oq > p.a_wp) return set_error(BCOSK_EINVAL, "igemm(flat): oq exceeds the buffer pitch");
+  } else if (p.a_flat != 2) {
+    return set_error(BCOSK_EINVAL, "igemm(flat): a_flat must be 1 or 2");
+  }
   if (p.mode == BCOSK_MODE_FWD && p.scale_mode != BCOSK_SCALE_NONE && !p.inv_norm)
     return set_error(BCOSK_EUNSUPPORTED, "igemm(flat): inv_norm must be precomputed");
   if (p.res_planes > 1 || p.y_planes > 1 && !p.y_f32) return set_error(BCOSK_EUNSUPPORTED, "igemm(flat): single plane only");

@@ -118,6 +118,7 @@ class PlanBase:
     # the library runs with 3 CTAs per SM (more bytes in flight); 0 disables
     light_k_iters = 4
     parity_dgrad = True              # strided k x k data gradients as stride^2 parity-class launches (no zero insertion)
+    flat_3x3 = True                  # 64 -> <=64 channel stride-1 k x k convs and their data gradients as flat-window launches
     flat_stem = True                 # stem and its data gradient as flat-window launches (throughput mode only)
     autotune_default = True          # capture() measures the per-launch schedule first (see autotune)
     fold_bn = True   # fold sqrt(BN multiplier) into the conv weights when every multiplier is positive and there is no bias
@@ -146,13 +147,17 @@ class PlanBase:
         M = nb * oh * ow
         cin_phys = x.t.shape[-1] // self.planes
         assert c <= cin_phys
+        # stride-1 k x k convs over 64 channels with <= 64 outputs (ResNet layer1 conv2): flat-window gather, the zero
+        # borders are produced in shared memory by the TMA box (include/bcosk.h a_flat = 2)
+        flat = flat or (self.flat_3x3 and self.planes == 1 and not self.hp_accum and stride == 1 and kh == kw and kh > 1
+                        and cin_phys == 64 and kch == 64 and o <= 64 and res is None and not y_f32 and x.t.is_contiguous())
         sq_in = None
         if inv_norm is None and self.scale_mode != L.BCOSK_SCALE_NONE:
             sq_in = x.sq
             if sq_geom is None:
                 assert pad_lo == pad_hi and kh == kw, "asymmetric convs must pass inv_norm or sq_geom"
                 sq_geom = (h, wd, kh, stride, pad_lo)
-            if sq_geom[2] > 3:
+            if sq_geom[2] > 3 or flat:
                 # large windows (7x7 stem: 49 taps per output pixel) are cheaper as a stand-alone sum-pool launch than as
                 # 49 dependent loads in front of every tile's epilogue (measured: 9 us of a 12 us CTA lifetime)
                 inv_norm = self._empty(M, dtype=torch.float32)
@@ -218,6 +223,9 @@ class PlanBase:
             oh, ow = rec.out_hw      # dense GEMM at output resolution; consumer adds it sub-sampled
         else:
             oh, ow = rec.in_hw
+        flat = flat or (self.flat_3x3 and self.planes == 1 and not self.hp_accum and rec.stride == 1 and k > 1
+                        and rec.cout == 64 and kch == 64 and rec.cin_phys <= 64 and add is None and out2 is None
+                        and y_map is None and not y_f32 and g.is_contiguous())
         lo = rec.pad_lo - (k - 1)
         up_h = oh - g.shape[1] + lo
         up_w = ow - g.shape[2] + lo

@@ -207,7 +207,10 @@ class IgemmOp:
         p.hp_accum = int(self.hp_accum)
         p.sched = int(self.sched)
         p.side_mapped = int(self.side_mapped)
-        if self.flat:
+        if self.flat and self.a.is_contiguous():
+            p.a_flat = 2                      # dense tensor: the zero borders are made in shared memory
+            assert self.stride == (1, 1) and len(self.seg_a_choff) == 1 and self.chunks_per_tap == 1 and self.n <= 64
+        elif self.flat:
             wp, hp, origin, total = self.flat_geometry()
             p.a_flat, p.a_wp, p.a_hp, p.a_flat_rows = 1, wp, hp, total - origin
         return p

@@ -135,7 +135,11 @@ typedef struct bcosk_igemm_params {
    *      traffic; the 7x7 stem and its data gradient were bound by it).  Tiles walk the flattened positions p*a_wp + x
    *      of one image; positions with x >= oq are computed and dropped.  Requires stride 1, num_segs 1,
    *      chunks_per_tap 1, n <= 64.  a_flat_rows = pixels from the window origin (a + (lo_h*a_wp + lo_w) pixels) to
-   *      the end of the buffer.  Results are identical to the im2col gather. */
+   *      the end of the buffer.  Results are identical to the im2col gather.
+   *      a_flat = 2: `a` is an ordinary dense [a_nb, a_h, a_w, a_c] tensor and the zero borders exist only in shared
+   *      memory: each tile fetches its image rows with ONE 4-D tiled TMA box that starts at pixel lo_w (negative) and is
+   *      (a_w + kw - 1 rounded up to 8) pixels wide, so the out-of-range pixels arrive as zeros (a_wp/a_hp/a_flat_rows
+   *      unused). */
   int32_t a_flat, a_wp, a_hp;
   int64_t a_flat_rows;
   /* ---- explain mode: 1 = mul1 / mul2 / out2 / mask2 are addressed by the MAPPED output row

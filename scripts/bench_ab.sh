@@ -15,6 +15,7 @@ _lib.load().bcosk_set_late_input(${LI:-12})
 PlanBase.light_k_iters = $LK
 PlanBase.autotune_default = bool(${AT:-1})
 PlanBase.flat_stem = bool(${FS:-1})
+PlanBase.flat_3x3 = bool(${FS:-1})
 PlanBase.parity_dgrad = bool(${PD:-1})
 sys.argv = ["bench.py", "--steps", "10", "--warmup", "3", "--no-cpu-baseline", "--layer-table", "gpurun_out/layers_$NAME.json"]
 runpy.run_path("bench.py", run_name="__main__")

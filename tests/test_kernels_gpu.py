@@ -22,7 +22,9 @@ F32_TOL = 3e-5
 
 
 def _mini_plan(nb, planes, explain=True, b=2.0):
-    return PlanBase(nb, planes=planes, dtype="bf16", device="cpu", explain=explain, b=b)
+    plan = PlanBase(nb, planes=planes, dtype="bf16", device="cpu", explain=explain, b=b)
+    plan.flat_3x3 = False      # the per-kernel tests choose the gather explicitly (flat=True where they want it)
+    return plan
 
 
 def _rand_act(g, nb, h, w, c, planes, dt=torch.bfloat16, scale=1.0):
@@ -169,6 +171,11 @@ FLAT_FWD_CASES = [
     ("flat_3x3_c64", 2, 14, 14, 64, 64, 3, 1, 1, 64, True),
     ("flat_3x3_n32", 2, 11, 13, 64, 32, 3, 1, 1, 64, False),
     ("flat_1x1_c64", 2, 12, 12, 64, 64, 1, 0, 0, 64, True),
+    # dense input (a_flat = 2): the zero borders are made in shared memory by the TMA box
+    ("flatdense_3x3_c64_w56", 2, 10, 56, 64, 64, 3, 1, 1, 64, True),
+    ("flatdense_3x3_c64_w13", 3, 11, 13, 64, 64, 3, 1, 1, 64, True),
+    ("flatdense_3x3_n32_w30", 2, 9, 30, 64, 32, 3, 1, 1, 64, False),
+    ("flatdense_4x4_kch32", 2, 20, 20, 32, 64, 4, 2, 1, 32, True),
 ]
 
 
@@ -178,7 +185,7 @@ def test_igemm_flat_window_forward(bcosk_lib, case):
     name, nb, h, wd, cin, cout, k, plo, phi, kch, relu = case
     g = torch.Generator().manual_seed(hash(name) % 2**31)
     plan = _mini_plan(nb, 1)
-    x = _padded_act(plan, g, nb, h, wd, cin, plo, phi)
+    x = _rand_act(g, nb, h, wd, cin, 1) if name.startswith("flatdense") else _padded_act(plan, g, nb, h, wd, cin, plo, phi)
     w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
     oh, ow = h + plo + phi - k + 1, wd + plo + phi - k + 1
     inv_norm = torch.rand(nb * oh * ow, generator=g) + 0.5
@@ -192,7 +199,8 @@ def test_igemm_flat_window_forward(bcosk_lib, case):
 
 
 @pytest.mark.parametrize("case", [("flat_d_4x4_n32_f32", 2, 18, 32, 64, 4, 2, 1, True),
-                                  ("flat_d_3x3_n64", 2, 12, 64, 64, 3, 1, 1, False)], ids=lambda c: c[0])
+                                  ("flat_d_3x3_n64", 2, 12, 64, 64, 3, 1, 1, False),
+                                  ("flatdense_d_3x3_n64", 2, 14, 64, 64, 3, 1, 1, False)], ids=lambda c: c[0])
 def test_igemm_flat_window_dgrad(bcosk_lib, case):
     name, nb, h, cin, cout, k, plo, phi, f32 = case
     g = torch.Generator().manual_seed(hash(name) % 2**31)
@@ -203,7 +211,8 @@ def test_igemm_flat_window_dgrad(bcosk_lib, case):
     inv_norm = torch.rand(nb * oh * oh, generator=g) + 0.5
     _, rec = plan._conv_fwd(name, x, w, 1, plo, phi, bn=None, relu=True, want_mask=True, inv_norm=inv_norm,
                             kch=32 if cin == 32 else 64)
-    rec.ghat = plan._padded(nb, oh, oh, cout, k - 1 - plo, k - 1 - phi)
+    rec.ghat = torch.zeros(nb, oh, oh, cout, dtype=plan.dt) if name.startswith("flatdense") \
+        else plan._padded(nb, oh, oh, cout, k - 1 - plo, k - 1 - phi)
     rec.ghat_map = None
     rec.ghat.copy_(torch.randn(nb, oh, oh, cout, generator=g).to(plan.dt))
     M = nb * h * h
