@@ -1104,7 +1104,11 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
         int seg = 0, tap = 0, kc = 0;
         for (int it = 0; it < num_iters; ++it) {
           uint8_t* slot = smem + stage * Cfg::kSlotBytes;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          {
+            BCOSK_TACC2_BEGIN();
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            BCOSK_TACC2(0);
+          }
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kSlotBytes);
           for (int j = 0; j < chunks_per_stage; ++j) {
             const int ci = it * chunks_per_stage + j;
@@ -1133,13 +1137,21 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       uint32_t i = 0;
       for (int t; (t = persist_tile((int)i, n_tiles, m_tiles, aux.order)) >= 0; ++i) {
         const uint32_t buf = i & 1u;
-        mbar_wait(&acc_empty_bar[buf], ((i >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        {
+          BCOSK_TACC2_BEGIN();
+          mbar_wait(&acc_empty_bar[buf], ((i >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+          BCOSK_TACC2(2);
+        }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
         uint32_t accumulate = 0;
         for (int it = 0; it < num_iters; ++it) {
           uint8_t* slot = smem + stage * Cfg::kSlotBytes;
-          mbar_wait(&full_bar[stage], phase);
+          {
+            BCOSK_TACC2_BEGIN();
+            mbar_wait(&full_bar[stage], phase);
+            BCOSK_TACC2(1);
+          }
           tc_fence_after();
           for (int j = 0; j < chunks_per_stage; ++j) {
             const uint64_t da = umma_smem_desc_kmajor(smem_u32(slot + j * a_chunk_bytes), row_bytes);
@@ -1162,7 +1174,11 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       for (int t; (t = persist_tile((int)i, n_tiles, m_tiles, aux.order)) >= 0; ++i) {
         const uint32_t buf = i & 1u;
         const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
-        mbar_wait(&in_empty_bar[buf], ((i >> 1) & 1u) ^ 1u);
+        {
+          BCOSK_TACC2_BEGIN();
+          mbar_wait(&in_empty_bar[buf], ((i >> 1) & 1u) ^ 1u);
+          BCOSK_TACC2(3);
+        }
         mbar_arrive_expect_tx(&in_full_bar[buf], Cfg::kTileBytes * (use_in2_tile ? 2 : 1));
         tma_load_2d(in_tile + buf * Cfg::kTileBytes, &tmap_in, &in_full_bar[buf], n0, m0);
         if (use_in2_tile) tma_load_2d(in2_tile + buf * Cfg::kTileBytes, &tmap_in2, &in_full_bar[buf], n0, m0);
@@ -1295,13 +1311,22 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       tl.out1 = aux.tma_out1 ? smem_u32(out1_tile + buf * Cfg::kTileBytes) : 0u;
       tl.out2 = aux.tma_out2 ? smem_u32(out2_tile + buf * Cfg::kTileBytes) : 0u;
 
+#ifdef BCOSK_TIMING2
+      const long long _t0 = clock64();
+#endif
       mbar_wait(&side_full_bar[buf], par);
       const uint32_t side0 = s_side[buf * (BM * 2) + row * 2];
       const uint32_t side1 = s_side[buf * (BM * 2) + row * 2 + 1];
       const float inv_norm = (MODE == BCOSK_MODE_FWD) ? __uint_as_float(side0) : 1.f;
       const uint32_t mb = (MODE == BCOSK_MODE_EXPLAIN) ? (half ? side1 : side0) : 0xffffffffu;
       if (use_in_tile) mbar_wait(&in_full_bar[buf], par);
+#ifdef BCOSK_TIMING2
+      const long long _t1 = clock64();
+#endif
       mbar_wait(&acc_full_bar[buf], par);
+#ifdef BCOSK_TIMING2
+      const long long _t2 = clock64();
+#endif
       tc_fence_after();
 
       float sq_acc = 0.f;
@@ -1341,6 +1366,15 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       }
       if (want_sq && half == 0 && ri.valid)
         p.sq_out[(size_t)tile_n * M + ri.m] = s_sq[(buf * 2) * BM + row] + s_sq[(buf * 2 + 1) * BM + row];
+#ifdef BCOSK_TIMING2
+      if (et == 0 && g_timing_buf != nullptr && (int)blockIdx.x < g_timing_cap) {
+        const long long _t3 = clock64();
+        g_timing_buf[blockIdx.x * 8 + 4] += _t1 - _t0;
+        g_timing_buf[blockIdx.x * 8 + 5] += _t2 - _t1;
+        g_timing_buf[blockIdx.x * 8 + 6] += _t3 - _t2;
+        g_timing_buf[blockIdx.x * 8 + 7] += 1;
+      }
+#endif
     }
     if (any_out_tile && et == 0) tma_store_wait_read();
     tc_fence_before();
