@@ -182,6 +182,14 @@ def avgpool_bwd_mul(gy, nb, h, w, c, planes, k, stride, pad, op, oq, gain, gain_
                                        dtype, rp, ip, _stream()), "bcosk_avgpool_bwd_mul")
 
 
+def explanation_rgba(grad6, x, smooth, percentile, tmp, out) -> None:
+    nb, _, h, w = grad6.shape
+    assert tmp.numel() >= 2 * nb * h * w + nb and tuple(out.shape) == (nb, h, w, 4)
+    fn = load().bcosk_explanation_rgba_u8 if _is_u8(x) else load().bcosk_explanation_rgba
+    check(fn(_p(grad6), _p(x), nb, h, w, int(smooth), C.c_float(percentile), _p(tmp), _p(out), _stream()),
+          "bcosk_explanation_rgba")
+
+
 def gap_logits(fc, nb, npix, ncls, inv_temp, bias, logits, pred) -> None:
     check(load().bcosk_gap_logits(_p(fc), nb, npix, ncls, C.c_float(inv_temp), C.c_float(bias), _p(logits), _p(pred),
                                   _stream()), "bcosk_gap_logits")

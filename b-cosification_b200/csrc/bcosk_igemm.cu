@@ -421,9 +421,11 @@ __device__ __forceinline__ void epilogue_fwd_fast(const bcosk_igemm_params& p, c
       const uint32_t m = Pk<T>::gt0_mask(ywk) | relu_off;                          // 0xFFFF per kept half
       yw[k] = ywk & m;
       tw[k] = Cvt<T>::pack2(t.x, t.y) & m;
+#ifndef BCOSK_EXP_SKIP
       if (MASK) mbits |= ((m & 1u) | ((m >> 15) & 2u)) << (2 * k);
       const float2 ym = Cvt<T>::unpack2(yw[k]);                                    // what the consumer will read
       sq2 = __ffma2_rn(ym, ym, sq2);
+#endif
     }
   }
   if (MASK) p.maskbits[(size_t)ri.m * p.mask_ld + (c0 >> 5)] = mbits;

@@ -86,6 +86,7 @@ class PlanBase:
         self.bwd_ops: List = []
         self._graph_fwd = None
         self._graph_all = None
+        self._graph_bwd = None
 
     # ------------------------------------------------------------------ allocation helpers
     def _zeros(self, *shape, dtype=None) -> Tensor:
@@ -372,12 +373,21 @@ class PlanBase:
             with torch.cuda.graph(self._graph_all):
                 O.run_ops(self.fwd_ops)
                 O.run_ops(self.bwd_ops)
+            self._graph_bwd = torch.cuda.CUDAGraph()      # explanation pass alone: further targets reuse one forward
+            with torch.cuda.graph(self._graph_bwd):
+                O.run_ops(self.bwd_ops)
 
     def replay_forward(self) -> None:
         if self._graph_fwd is not None:
             self._graph_fwd.replay()
         else:
             self.run_forward()
+
+    def replay_explain(self) -> None:
+        if self._graph_bwd is not None:
+            self._graph_bwd.replay()
+        else:
+            self.run_explain()
 
     def replay_all(self) -> None:
         if self._graph_all is not None:

@@ -354,6 +354,21 @@ class ContribMapOp:
         L.contrib_map_s2d(self.g, self.x, nb, h, w, self.cp, self.inv_std6, self.out_scale, self.cmap, self.grad6)
 
 
+@dataclass
+class ExplanationImageOp:
+    """RGBA explanation images of the batch (gradient_to_image, bcos/common.py:387-436) from grad6 and the input."""
+    name: str
+    grad6: Tensor        # [nb, 6, h, w] fp32 dynamic linear weights
+    x: Tensor            # [nb, 6, h, w] fp32 or uint8 RGB [nb, 3, h, w]
+    smooth: int
+    percentile: float
+    tmp: Tensor          # [2*nb*h*w + nb] fp32 scratch
+    out: Tensor          # [nb, h, w, 4] fp32
+
+    def run(self) -> None:
+        L.explanation_rgba(self.grad6, self.x, self.smooth, self.percentile, self.tmp, self.out)
+
+
 def run_ops(ops) -> None:
     for o in ops:
         o.run()

@@ -39,7 +39,8 @@ class ResNetPlan(PlanBase):
                  device="cuda", image_size: int = 224, explain: bool = True, want_grad6: bool = False, b: float = 2.0,
                  bn_eps: float = 1e-5, mean=IMAGENET_MEAN_ADDINVERSE, std=IMAGENET_STD_ADDINVERSE,
                  logit_bias: Optional[float] = -math.log(1000 - 1), logit_temperature: Optional[float] = None,
-                 seed_scale: float = 1.0, stem_kch: int = 32, input_u8: bool = False):
+                 seed_scale: float = 1.0, stem_kch: int = 32, input_u8: bool = False, want_rgba: bool = False,
+                 rgba_smooth: int = 15, rgba_percentile: float = 99.5):
         super().__init__(batch, planes=planes, dtype=dtype, device=device, explain=explain, b=b, bn_eps=bn_eps,
                          state_dict=state_dict)
         self.arch = arch
@@ -53,10 +54,11 @@ class ResNetPlan(PlanBase):
         self.stem_cp = 32 if stem_kch == 32 else 64
         self.size = image_size
         self.input_u8 = input_u8
+        self.want_rgba, self.rgba_smooth, self.rgba_percentile = want_rgba, rgba_smooth, rgba_percentile
         self.blocks: List[BlockRec] = []
         self._build_forward()
         if explain:
-            self._build_explain(want_grad6)
+            self._build_explain(want_grad6 or want_rgba)
 
     def _build_forward(self) -> None:
         nb, S, pl = self.nb, self.size, self.planes
@@ -175,6 +177,13 @@ class ResNetPlan(PlanBase):
         self.grad6 = self._zeros(nb, 6, self.size, self.size, dtype=torch.float32) if want_grad6 else None
         self.bwd_ops.append(O.ContribMapOp("contrib_map", self.g0, self.x_in, self.stem_cp, self.inv_std,
                                            1.0 / self.seed_scale, self.cmap, self.grad6))
+        self.rgba = None
+        if self.want_rgba:
+            # the reference's published artefact: RGBA explanation images (gradient_to_image) for the whole batch
+            self.rgba = self._zeros(nb, self.size, self.size, 4, dtype=torch.float32)
+            tmp = self._zeros(2 * nb * self.size * self.size + nb, dtype=torch.float32)
+            self.bwd_ops.append(O.ExplanationImageOp("explanation_rgba", self.grad6, self.x_in, self.rgba_smooth,
+                                                     self.rgba_percentile, tmp, self.rgba))
 
     def load_input(self, x6: Tensor) -> None:
         """x6: [nb, 6, H, W] float32 `[x, 1-x]`, or uint8 RGB [nb, 3, H, W] for an `input_u8` plan (host or device)."""
@@ -197,6 +206,46 @@ class ResNetPlan(PlanBase):
         out = {"logits": self.logits, "prediction": self.pred, "contribution_map": self.cmap}
         if self.grad6 is not None:
             out["dynamic_linear_weights"] = self.grad6
+        if self.rgba is not None:
+            out["explanation"] = self.rgba
+        return out
+
+
+    def explain_targets(self, x6: Optional[Tensor], targets: Tensor) -> Dict[str, Tensor]:
+        """Explanations of several logits per image from ONE forward pass.
+
+        targets: int tensor [T, nb] (class index to explain, per target set and image).  The reference recomputes the forward
+        for every target (Captum InputXGradient, bcos/common.py:280-344; localisation runs 4-9 targets per grid image);
+        here the forward state (gains, masks) is kept and only the explanation pass is replayed per target set.
+        Returns stacked tensors: contribution_map [T, nb, H, W] (+ dynamic_linear_weights / explanation when enabled)."""
+        if not self.with_explain:
+            raise RuntimeError("plan was built with explain=False")
+        targets = torch.as_tensor(targets)
+        if targets.ndim == 1:
+            targets = targets[None]
+        assert targets.shape[1] == self.nb, (targets.shape, self.nb)
+        if x6 is not None:
+            self.load_input(x6)
+        self.replay_forward()
+        pred = self.pred.clone()
+        tg = targets.to(device=self.pred.device, dtype=torch.int32)
+        out = {"logits": self.logits.clone(), "prediction": pred, "contribution_map": []}
+        if self.grad6 is not None:
+            out["dynamic_linear_weights"] = []
+        if self.rgba is not None:
+            out["explanation"] = []
+        for t in range(tg.shape[0]):
+            self.pred.copy_(tg[t])                # the seed kernel reads the class to explain from here
+            self.replay_explain()
+            out["contribution_map"].append(self.cmap.clone())
+            if self.grad6 is not None:
+                out["dynamic_linear_weights"].append(self.grad6.clone())
+            if self.rgba is not None:
+                out["explanation"].append(self.rgba.clone())
+        self.pred.copy_(pred)
+        for k in ("contribution_map", "dynamic_linear_weights", "explanation"):
+            if k in out:
+                out[k] = torch.stack(out[k])
         return out
 
 

@@ -236,6 +236,17 @@ int bcosk_contrib_map_s2d(const float* g, const float* x, int32_t nb, int32_t h,
 int bcosk_contrib_map_s2d_u8(const float* g, const uint8_t* x, int32_t nb, int32_t h, int32_t w, int32_t cp,
                              const float* inv_std6, float out_scale, float* cmap, float* grad6, void* stream);
 
+/* RGBA explanation images for a batch, on the device (replaces gradient_to_image bcos/common.py:387-436, which handles
+ * one image and ends in numpy): out [nb, h, w, 4] fp32 = (r, g, b, alpha).  grad6 [nb,6,h,w] = dynamic linear weights,
+ * x = the network input ([nb,6,h,w] fp32, or uint8 RGB [nb,3,h,w] with the inverse channels formed on the fly).
+ * smooth = odd box-filter window of the alpha channel (15 in the reference, 0 = none), percentile in [0,100] (99.5):
+ * alpha is divided by that per-image percentile (torch.quantile: linear interpolation of the two neighbouring order
+ * statistics, found by radix select) and clipped to [0,1].  tmp: 2*nb*h*w + nb floats of scratch. */
+int bcosk_explanation_rgba(const float* grad6, const float* x, int32_t nb, int32_t h, int32_t w, int32_t smooth,
+                           float percentile, float* tmp, float* out, void* stream);
+int bcosk_explanation_rgba_u8(const float* grad6, const uint8_t* x, int32_t nb, int32_t h, int32_t w, int32_t smooth,
+                              float percentile, float* tmp, float* out, void* stream);
+
 /* Generic element-wise helpers for the module-level (un-fused) path. */
 /* batch_norm_uncentered_2d eval (batchnorm_uncentered.py:49-58) / ReLU on NHWC 16-bit: y = relu?(x*alpha[c]+beta[c]) */
 int bcosk_channel_affine(const void* x, int64_t rows, int32_t c, const float* alpha, const float* beta, int32_t relu,

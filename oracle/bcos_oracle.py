@@ -676,3 +676,23 @@ def parity_metrics(logits: Tensor, maps: Tensor, ref_logits: Tensor, ref_maps: T
         "map_cos_min": cos.min().item(),
         "map_maxabs_over_range": mar.max().item(),
     }
+
+
+def gradient_to_image_batched(x6: Tensor, grad6: Tensor, smooth: int = 15, alpha_percentile: float = 99.5) -> Tensor:
+    """RGBA explanations [nb, H, W, 4] - the reference's gradient_to_image (bcos/common.py:387-436) applied per image:
+    colour = clamp(w / (max|w| + 1e-12), 0), rgb = c[:3] / (c[:3] + c[3:] + 1e-12); alpha = ||w||_2, 1e-12 where the
+    contribution (x * w).sum(0) is negative; avg_pool2d(alpha, smooth, 1, (smooth-1)//2); / torch.quantile; clip."""
+    import torch.nn.functional as F
+    outs = []
+    for image, lin in zip(x6, grad6):
+        contribs = (image * lin).sum(0, keepdim=True)
+        rgb = lin / (lin.abs().max(0, keepdim=True).values + 1e-12)
+        rgb = rgb.clamp(min=0)
+        rgb = rgb[:3] / (rgb[:3] + rgb[3:] + 1e-12)
+        alpha = lin.norm(p=2, dim=0, keepdim=True)
+        alpha = torch.where(contribs < 0, torch.full_like(alpha, 1e-12), alpha)
+        if smooth:
+            alpha = F.avg_pool2d(alpha, smooth, stride=1, padding=(smooth - 1) // 2)
+        alpha = (alpha / torch.quantile(alpha, q=alpha_percentile / 100)).clip(0, 1)
+        outs.append(torch.cat([rgb, alpha], 0).permute(1, 2, 0))
+    return torch.stack(outs)

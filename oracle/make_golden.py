@@ -425,6 +425,27 @@ def golden_modules(seed: int = 0):
     print(f"[modules] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB), {len(out)} arrays")
 
 
+def golden_gradient_to_image(seed: int = 3):
+    """RGBA explanation images from the reference's own gradient_to_image (bcos/common.py:387-436), per image."""
+    refload.load()
+    import bcos.common as BC
+    g = torch.Generator().manual_seed(seed)
+    nb, S = 3, 48
+    x3 = torch.rand(nb, 3, S, S, generator=g)
+    x6 = torch.cat([x3, 1 - x3], 1)
+    grad6 = torch.randn(nb, 6, S, S, generator=g) * torch.rand(nb, 1, S, S, generator=g)
+    out = {"x6": x6.numpy(), "grad6": grad6.numpy()}
+    for name, (smooth, pct) in {"default": (15, 99.5), "nosmooth_p90": (0, 90.0), "s3_p100": (3, 100.0)}.items():
+        ref = np.stack([BC.gradient_to_image(x6[i], grad6[i], smooth=smooth, alpha_percentile=pct) for i in range(nb)])
+        mine = O.gradient_to_image_batched(x6, grad6, smooth, pct).numpy()
+        assert np.array_equal(ref, mine), (name, np.abs(ref - mine).max())      # same ATen calls: bit exact
+        out[name + ".rgba"] = ref
+        out[name + ".args"] = np.array([smooth, pct], dtype=np.float64)
+    path = os.path.join(GOLD, "gradient_to_image_kat.npz")
+    np.savez_compressed(path, **out)
+    print(f"[g2i] wrote {path} ({os.path.getsize(path)/1e3:.0f} kB); oracle == reference bit exact")
+
+
 def calibration_file(arch: str, batch: int = 16, seed: int = 100):
     """BN running variances for the synthetic benchmark checkpoint (weights seed 0), calibrated on `batch` synthetic
     images by the oracle (== the reference, see golden_resnet).  Shipped with the package so that bench.py needs no
@@ -462,6 +483,8 @@ if __name__ == "__main__":
         golden_vit("simple_vit_ti_patch16_224", 2)
     if "clip_rn50" in which:
         golden_clip_rn50(2)
+    if "g2i" in which:
+        golden_gradient_to_image()
     if "calib" in which:
         calibration_file("resnet18")
         calibration_file("resnet50")

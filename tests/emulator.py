@@ -259,10 +259,15 @@ def run_contrib_map(op: O.ContribMapOp) -> None:
         op.grad6.copy_(g6)
 
 
+def run_explanation_image(op: O.ExplanationImageOp) -> None:
+    import bcos_oracle as R   # tests/conftest.py puts oracle/ on the path
+    op.out.copy_(R.gradient_to_image_batched(_x6(op.x), op.grad6, op.smooth, op.percentile))
+
+
 _DISPATCH = {
     O.IgemmOp: run_igemm, O.InputPrepOp: run_input_prep, O.PatchNormOp: run_patch_norm, O.AvgPoolFwdOp: run_avgpool_fwd,
     O.AvgPoolBwdMulOp: run_avgpool_bwd_mul, O.GapLogitsOp: run_gap_logits, O.FcSeedOp: run_fc_seed,
-    O.ContribMapOp: run_contrib_map,
+    O.ContribMapOp: run_contrib_map, O.ExplanationImageOp: run_explanation_image,
 }
 
 

@@ -18,6 +18,7 @@ OUTPUT_FIELDS = {
     O.GapLogitsOp: ["logits", "pred"],
     O.FcSeedOp: ["out1", "out2"],
     O.ContribMapOp: ["cmap", "grad6"],
+    O.ExplanationImageOp: ["out"],
 }
 
 

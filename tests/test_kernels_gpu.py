@@ -420,3 +420,17 @@ def test_elementwise_kernels(bcosk_lib):
         grad6 = torch.zeros(nb, 6, S, S)
         ops.append(O.ContribMapOp("cmap", g0, x6, 32, istd, 0.25, cmap, grad6))
         print(planes, _run_and_compare(ops, tol16=BF16_TOL if planes == 1 else 2e-4))
+
+
+@pytest.mark.parametrize("u8", [False, True], ids=["x6_f32", "rgb_u8"])
+def test_explanation_rgba(bcosk_lib, u8):
+    """device gradient_to_image for a batch (colour, alpha, 15x15 box filter, per-image 99.5 percentile by radix select)
+    against the oracle's restatement of bcos/common.py:387-436"""
+    g = torch.Generator().manual_seed(77)
+    nb, S = 3, 64
+    x3 = torch.rand(nb, 3, S, S, generator=g)
+    x = (x3 * 255).round().to(torch.uint8) if u8 else torch.cat([x3, 1 - x3], 1).contiguous()
+    grad6 = torch.randn(nb, 6, S, S, generator=g) * torch.rand(nb, 1, S, S, generator=g)
+    for smooth, pct in ((15, 99.5), (0, 90.0), (3, 100.0)):
+        op = O.ExplanationImageOp("rgba", grad6, x, smooth, pct, torch.zeros(2 * nb * S * S + nb), torch.zeros(nb, S, S, 4))
+        print(smooth, pct, _run_and_compare([op], tol32=2e-5))

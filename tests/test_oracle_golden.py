@@ -185,3 +185,19 @@ def test_clip_rn50_golden(golden_dir):
     emb, cm = _t(gold["embedding"][:1]), _t(gold["contribution_map"][:1])
     assert ((e["embedding"] - emb).abs().max() / emb.abs().max()).item() < 1e-4
     assert torch.nn.functional.cosine_similarity(e["contribution_map"].flatten(1), cm.flatten(1)).min().item() > 0.9999
+
+
+def test_gradient_to_image_known_answers(golden_dir):
+    """oracle restatement of gradient_to_image (bcos/common.py:387-436) == what the reference produced"""
+    kat = np.load(os.path.join(golden_dir, "gradient_to_image_kat.npz"))
+    x6, grad6 = _t(kat["x6"]), _t(kat["grad6"])
+    for name in ("default", "nosmooth_p90", "s3_p100"):
+        smooth, pct = kat[name + ".args"].tolist()
+        out = OR.gradient_to_image_batched(x6, grad6, int(smooth), float(pct))
+        assert torch.equal(out, _t(kat[name + ".rgba"])), name
+        if refload.available():
+            refload.load()
+            import bcos.common as BC
+            ref = np.stack([BC.gradient_to_image(x6[i], grad6[i], smooth=int(smooth), alpha_percentile=float(pct))
+                            for i in range(x6.shape[0])])
+            assert np.array_equal(out.numpy(), ref), name

@@ -99,3 +99,36 @@ def test_golden_throughput_modes_report(bcosk_lib, golden_dir, arch, batch, plan
     print(f"REPORT {arch} planes={planes} vs reference golden: {m}")
     assert torch.isfinite(out["logits"]).all() and torch.isfinite(out["contribution_map"]).all()
     assert m["map_cos_min"] > (0.99 if planes == 2 else 0.3)
+
+
+def test_multi_target_explain_and_rgba(bcosk_lib):
+    """several explained classes per image from one forward (bcos/common.py:280-344 recomputes it per target) and the
+    RGBA explanation images (gradient_to_image) on the device, parity mode, against the oracle"""
+    arch, S, nb = "resnet18", 64, 2
+    sd = synth.synth_state_dict(OR.resnet_state_shapes(arch), 0)
+    x6 = synth.to_bcos_input(synth.synth_images_u8(nb, S, 1))
+    om = OR.OracleResNet(arch, sd)
+    om.calibrate_bn(x6)
+    targets = torch.tensor([[3, 7], [500, 999], [0, 1]], dtype=torch.int32)
+    for captured in (False, True):
+        plan = ResNetPlan(arch, sd, nb, planes=3, device="cuda", image_size=S, want_rgba=True)
+        if captured:
+            plan.capture()
+        out = plan.explain_targets(x6, targets)
+        torch.cuda.synchronize()
+        for t in range(targets.shape[0]):
+            ref = OR.explain_batched(om.forward, x6, idx=targets[t].long())
+            m = OR.parity_metrics(out["logits"], out["contribution_map"][t], ref["logits"], ref["contribution_map"])
+            print("target set", t, "captured", captured, m)
+            assert m["logit_rel_err"] <= 2e-3 and m["map_cos_min"] >= 0.999 and m["map_maxabs_over_range"] <= 1e-3
+            rgba_ref = OR.gradient_to_image_batched(x6, ref["dynamic_linear_weights"])
+            rgba = out["explanation"][t].cpu()
+            # colour of (almost) unweighted pixels is ill conditioned (w / max|w|): compare where alpha is visible
+            vis = rgba_ref[..., 3] > 0.05
+            assert (rgba[..., 3] - rgba_ref[..., 3]).abs().max() <= 2e-2
+            assert (rgba[..., :3] - rgba_ref[..., :3])[vis].abs().max() <= 5e-2
+        # the default explanation (predicted class) still works afterwards and the prediction is untouched
+        out2 = plan.explain(x6)
+        ref = OR.explain_batched(om.forward, x6)
+        torch.cuda.synchronize()
+        assert torch.equal(out2["prediction"].cpu().long(), ref["prediction"].long())
