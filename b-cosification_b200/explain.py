@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
 
-__all__ = ["BcosUtilMixin", "explanation_mode", "gradient_to_image"]
+__all__ = ["BcosUtilMixin", "explanation_mode", "gradient_to_image", "gradient_to_image_batch"]
 
 
 class explanation_mode:
@@ -45,19 +45,28 @@ class explanation_mode:
 
 
 def gradient_to_image(image: Tensor, linear_mapping: Tensor, smooth: int = 15, alpha_percentile: float = 99.5) -> Tensor:
-    """RGBA explanation [H, W, 4] from a 6-channel image and its dynamic linear weights (bcos/common.py:387-436),
-    in torch on the tensor's device (the reference converts to numpy for plotting)."""
-    contribs = (image * linear_mapping).sum(0, keepdim=True)[0]
-    rgb_grad = linear_mapping / (linear_mapping.abs().max(0, keepdim=True).values + 1e-12)
-    rgb_grad = rgb_grad.clamp(min=0)
-    rgb_grad = rgb_grad[:3] / (rgb_grad[:3] + rgb_grad[3:] + 1e-12)
-    alpha = linear_mapping.norm(p=2, dim=0, keepdim=True)
-    alpha = torch.where(contribs[None] < 0, torch.zeros_like(alpha) + 1e-12, alpha)
-    if smooth:
-        alpha = F.avg_pool2d(alpha, smooth, stride=1, padding=(smooth - 1) // 2)
-    alpha = alpha / torch.quantile(alpha.flatten(), q=alpha_percentile / 100)
-    alpha = alpha.clamp(0, 1)
-    return torch.cat([rgb_grad, alpha], dim=0).permute(1, 2, 0)
+    """RGBA explanation [H, W, 4] from a 6-channel image and its dynamic linear weights (bcos/common.py:387-436), computed
+    by `bcosk_explanation_rgba` on the tensor's CUDA device (the reference converts to numpy for plotting; call
+    `.cpu().numpy()` on the result for that).  Batches: `gradient_to_image_batch`."""
+    return gradient_to_image_batch(image[None], linear_mapping[None], smooth, alpha_percentile)[0]
+
+
+def gradient_to_image_batch(images: Tensor, linear_mappings: Tensor, smooth: int = 15,
+                            alpha_percentile: float = 99.5) -> Tensor:
+    """[nb, 6, H, W] inputs and dynamic linear weights -> [nb, H, W, 4] RGBA, one launch sequence for the batch."""
+    from . import _lib as L
+    if not images.is_cuda:
+        raise L.BcoskError("gradient_to_image runs on a CUDA device (sm_100a); move the tensors there")
+    L.require_device()
+    nb, c, h, w = images.shape
+    if c != 6 or linear_mappings.shape != images.shape:
+        raise ValueError("expected [nb, 6, H, W] image and linear mapping")
+    x = images.detach().float().contiguous()
+    g = linear_mappings.detach().float().contiguous()
+    out = torch.empty(nb, h, w, 4, dtype=torch.float32, device=images.device)
+    tmp = torch.empty(2 * nb * h * w + nb, dtype=torch.float32, device=images.device)
+    L.explanation_rgba(g, x, smooth, alpha_percentile, tmp, out)
+    return out
 
 
 class BcosUtilMixin:
