@@ -28,9 +28,12 @@ constexpr int NUM_THREADS = 192;
 
 // LIGHT: 3 small slots and 3 CTAs per SM - for the bandwidth-bound launches with a short K loop, where what matters is
 // how many tiles (i.e. how many bytes) are in flight per SM, not the depth of the MMA pipeline.
-template <int BN, bool HP = false, bool LIGHT = false> struct TileCfg {
-  static constexpr int kStages = LIGHT ? 3 : ((BN == 128) ? 3 : 4);   // pipeline slots; the last may hold the input tile
-  static constexpr int kMinBlocks = LIGHT ? 3 : ((BN <= 128) ? 2 : 1);
+// LIGHT = 2: two slots and 4 CTAs per SM for forward launches whose K loop is ONE stage (K = 64).  Slot 0 is the stage and
+// afterwards the y tile; slot 1 holds the residual tile and the gain tile is staged over it - every thread reads its own
+// residual words before it writes the same words of the gain tile, so the alias is safe.
+template <int BN, bool HP = false, int LIGHT = 0> struct TileCfg {
+  static constexpr int kStages = LIGHT == 2 ? 2 : (LIGHT ? 3 : ((BN == 128) ? 3 : 4));   // pipeline slots; the last may hold the input tile
+  static constexpr int kMinBlocks = LIGHT == 2 ? 4 : (LIGHT ? 3 : ((BN <= 128) ? 2 : 1));
   static constexpr int kBStageBytes = BN * STAGE_K * 2;
   static constexpr int kSlotBytes = A_STAGE_BYTES + kBStageBytes;   // A stage followed by its B stage
   static constexpr int kTileBytes = BM * BN * 2;                    // one 16-bit epilogue tile (BN/64 boxes of 16 KB)
@@ -552,7 +555,7 @@ __device__ __forceinline__ void epilogue_chunk(const bcosk_igemm_params& p, cons
   }
 }
 
-template <int BN, int MODE, typename T, bool HP, bool LIGHT = false, bool PAIR = false>
+template <int BN, int MODE, typename T, bool HP, int LIGHT = 0, bool PAIR = false>
 __global__ void __launch_bounds__(NUM_THREADS, TileCfg<BN, HP, LIGHT>::kMinBlocks)
 bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in2,
@@ -1745,7 +1748,7 @@ struct LaunchMaps {
   CUtensorMap a, b, in, in2, out1, out2;
 };
 
-template <int BN, int MODE, bool HP, bool LIGHT = false, bool PAIR = false>
+template <int BN, int MODE, bool HP, int LIGHT = 0, bool PAIR = false>
 static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const IgemmAux& aux, cudaStream_t st) {
   using Cfg = TileCfg<BN, HP, LIGHT>;
   auto kern = bcosk_igemm_kernel<BN, MODE, __nv_bfloat16, HP, LIGHT, PAIR>;
@@ -1796,6 +1799,7 @@ static int g_cluster = 1;              // 1 none; 2/4 weight-tile multicast acro
 // ~4 TB/s on the bandwidth-bound launches; the per-tile schedule is the default.
 static int g_persistent_enabled = 0;   // 0 off, 1 tiles strided over the grid, 2 row-block order
 static bool g_light_enabled = true;
+static bool g_light4_enabled = true;
 
 template <int MODE>
 static int launch_persistent(const LaunchMaps& mp, const bcosk_igemm_params& p, const IgemmAux& aux, cudaStream_t st) {
@@ -2056,9 +2060,11 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
   if (bn == 64 && g_light_enabled && !aux.tma_in2) {
     // short K loop (<= 4 stages): the 3-CTA/SM variant
     const int iters = p.num_segs * p.num_taps * p.chunks_per_tap / (STAGE_K / p.kch);
+    if (iters == 1 && p.mode == BCOSK_MODE_FWD && g_light4_enabled && aux.tma_out1 && (aux.tma_out2 || !p.gain))
+      return launch_igemm<64, BCOSK_MODE_FWD, false, 2>(mp, p, aux, st);      // one K stage: 4 CTAs per SM
     if (iters <= 4)
-      return p.mode == BCOSK_MODE_FWD ? launch_igemm<64, BCOSK_MODE_FWD, false, true>(mp, p, aux, st)
-                                      : launch_igemm<64, BCOSK_MODE_EXPLAIN, false, true>(mp, p, aux, st);
+      return p.mode == BCOSK_MODE_FWD ? launch_igemm<64, BCOSK_MODE_FWD, false, 1>(mp, p, aux, st)
+                                      : launch_igemm<64, BCOSK_MODE_EXPLAIN, false, 1>(mp, p, aux, st);
   }
   if (aux.pair && bn == 128)
     return p.mode == BCOSK_MODE_FWD ? launch_igemm<128, BCOSK_MODE_FWD, false, false, true>(mp, p, aux, st)
@@ -2101,8 +2107,9 @@ extern "C" int bcosk_set_cluster(int32_t size) {
 }
 
 extern "C" int bcosk_set_light(int32_t enabled) {
-  const int prev = g_light_enabled ? 1 : 0;
-  g_light_enabled = enabled != 0;
+  const int prev = (g_light_enabled ? 1 : 0) | (g_light4_enabled ? 2 : 0);
+  g_light_enabled = (enabled & 1) != 0;
+  g_light4_enabled = (enabled & 2) != 0;
   return prev;
 }
 

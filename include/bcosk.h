@@ -167,7 +167,9 @@ int bcosk_set_late_input(int32_t min_k_stages);
  * identical in every mode (tests/test_kernels_gpu.py). */
 int bcosk_set_cluster(int32_t size);
 
-/* 1 (default) = launches with block_n 64 and a K loop of <= 4 stages use the 3-CTA-per-SM variant.  Returns the previous setting. */
+/* Bit 0: launches with block_n 64 and a K loop of <= 4 stages use the 3-CTA-per-SM variant.  Bit 1: forward launches with
+ * a single K stage use the 4-CTA-per-SM variant (the gain tile is staged over the consumed residual tile).  Default 3.
+ * Returns the previous setting.  Results are identical. */
 int bcosk_set_light(int32_t enabled);
 
 /* Debug aid: raw bytes of the first A chunk (tile_m, chunk) as TMA im2col lands it in shared memory
