@@ -25,6 +25,9 @@ constexpr int BM = 128;       // CTA tile M (= UMMA M, one TMEM lane per output 
 constexpr int STAGE_K = 64;   // K elements per pipeline stage (128 bytes of 16-bit data per row)
 constexpr int A_STAGE_BYTES = BM * STAGE_K * 2;
 constexpr int NUM_THREADS = 192;
+#ifndef BCOSK_LIGHT2_BLOCKS
+#define BCOSK_LIGHT2_BLOCKS 4   // CTAs per SM of the single-stage forward variant (5 spills ~200 B per thread)
+#endif
 
 // LIGHT: 3 small slots and 3 CTAs per SM - for the bandwidth-bound launches with a short K loop, where what matters is
 // how many tiles (i.e. how many bytes) are in flight per SM, not the depth of the MMA pipeline.
@@ -33,15 +36,17 @@ constexpr int NUM_THREADS = 192;
 // residual words before it writes the same words of the gain tile, so the alias is safe.
 template <int BN, bool HP = false, int LIGHT = 0> struct TileCfg {
   static constexpr int kStages = LIGHT == 2 ? 2 : (LIGHT ? 3 : ((BN == 128) ? 3 : 4));   // pipeline slots; the last may hold the input tile
-  static constexpr int kMinBlocks = LIGHT == 2 ? 4 : (LIGHT ? 3 : ((BN <= 128) ? 2 : 1));
+  static constexpr int kMinBlocks = LIGHT == 2 ? BCOSK_LIGHT2_BLOCKS : (LIGHT ? 3 : ((BN <= 128) ? 2 : 1));
   static constexpr int kBStageBytes = BN * STAGE_K * 2;
   static constexpr int kSlotBytes = A_STAGE_BYTES + kBStageBytes;   // A stage followed by its B stage
   static constexpr int kTileBytes = BM * BN * 2;                    // one 16-bit epilogue tile (BN/64 boxes of 16 KB)
   static constexpr bool kTmaEpilogue = !HP && (BN == 64 || BN == 128);
   // HP (high-precision accumulation): two TMEM accumulators that the epilogue warps drain every pipeline stage
   static constexpr int kTmemCols = (BN < 32 ? 32 : BN) * (HP ? 2 : 1);
+  // LIGHT = 2: the last slot only ever holds a 16 KB tile, its last 8 KB are not allocated
+  static constexpr int kBarOffset = kStages * (A_STAGE_BYTES + kBStageBytes) - (LIGHT == 2 ? 8192 : 0);
   // stages + 1 KB alignment slack + barriers/params
-  static constexpr int kSmemBytes = kStages * (A_STAGE_BYTES + kBStageBytes) + 1024 + 256 + 2 * BN * 4;
+  static constexpr int kSmemBytes = kBarOffset + 1024 + 256 + 2 * BN * 4;
 };
 
 #ifdef BCOSK_TIMING2
@@ -568,7 +573,7 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // slot s = [A stage 16 KB | B stage BN*128 B]; after the main loop slots 0/1 hold the output tiles, and when an
   // epilogue input tile is prefetched it owns the last slot (the ring then has kSlots-1 stages)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSlots * Cfg::kSlotBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOffset);
   uint64_t* empty_bar = full_bar + kSlots;
   uint64_t* tmem_full_bar = empty_bar + kSlots;    // non-HP: accumulator complete
   uint64_t* acc_full_bar = tmem_full_bar + 1;      // HP: [2] partial accumulator ready
