@@ -117,7 +117,7 @@ class PlanBase:
 
     # launches whose K loop has at most this many 64-deep stages are bandwidth bound: they use 64-wide tiles, which
     # the library runs with 3 CTAs per SM (more bytes in flight); 0 disables
-    light_k_iters = 4
+    light_k_iters = 3
     parity_dgrad = True              # strided k x k data gradients as stride^2 parity-class launches (no zero insertion)
     flat_3x3 = True                  # 64 -> <=64 channel stride-1 k x k convs and their data gradients as flat-window launches
     flat_stem = True                 # stem and its data gradient as flat-window launches (throughput mode only)
