@@ -228,6 +228,14 @@ def main():
         return
 
     pk = peaks()
+    # measured DRAM bytes of the same launches from the committed ncu capture (dram__bytes_read + dram__bytes_write over
+    # one step of this workload); only meaningful for the configuration it was captured on
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_final_dram_traffic.json")
+    if os.path.exists(tpath) and args.arch == "resnet50" and B == 256 and args.planes == 1:
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        traffic, traffic_src = float(tj["igemm_dram_bytes_per_step"]), "profiles/r01_final_dram_traffic.json (ncu, bytes per step)"
     hbm_ach = ig_bytes / (ig_ms * 1e-3) / 1e9
     tc_ach = ig_flops / (ig_ms * 1e-3) / 1e12
     tpk = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
@@ -248,7 +256,8 @@ def main():
         "gpu_launches": plan.num_launches() * K,
         "launches_per_step": plan.num_launches(),
         "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"],
-                     "traffic": None, "kernel": "bcosk_igemm_kernel (all conv / dgrad launches of one step)",
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": "bcosk_igemm_* (all conv / dgrad launches of one step)",
                      "peak_source": pk["source"], "kernel_ms_per_step": ig_ms, "kernel_share_of_step": ig_ms / step_ms_eager,
                      "algorithmic_bytes_per_step": ig_bytes},
         "roofline_tensor": {"bound": "tensor", "achieved": tc_ach, "peak": tpk, "unit": "TFLOP/s", "frac": tc_ach / tpk,
