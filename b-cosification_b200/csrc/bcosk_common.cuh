@@ -229,6 +229,12 @@ __device__ __forceinline__ void tma_load_im2col_4d_2cta(void* smem_dst, const vo
       "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
+// Programmatic dependent launch: a grid launched with the programmatic-serialization attribute may start while its
+// predecessor is still draining; grid_dependency_wait() blocks until the predecessor has completed and its writes are
+// visible (no-op without the attribute), grid_launch_dependents() lets the successor's CTAs be scheduled as soon as every
+// CTA of this grid has started.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

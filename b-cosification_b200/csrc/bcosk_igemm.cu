@@ -636,6 +636,9 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (cl > 1) cluster_sync_all();        // peers' barriers exist before any multicast data or remote arrival reaches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // everything above touched only parameters, shared memory and TMEM: it may overlap the previous launch's tail
+  grid_launch_dependents();
+  grid_dependency_wait();
   if (threadIdx.x == 64) BCOSK_STAMP(1);
 
   if (warp == 0) {
@@ -1094,6 +1097,8 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  grid_launch_dependents();     // prologue done: it may overlap the previous launch's tail
+  grid_dependency_wait();       // from here on global memory written by the previous launch is read
 
   if (warp == 0) {
     // ===================== A/B producer =====================
@@ -1490,6 +1495,8 @@ bcosk_igemm_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  grid_launch_dependents();     // prologue done: it may overlap the previous launch's tail
+  grid_dependency_wait();       // from here on global memory written by the previous launch is read
 
   if (warp == 0) {
     // ===================== producer =====================
@@ -1753,6 +1760,25 @@ struct LaunchMaps {
   CUtensorMap a, b, in, in2, out1, out2;
 };
 
+static int g_pdl_enabled = 0;          // programmatic dependent launch of the tensor-core kernels (prologue overlaps the previous
+                                       // tail): measured 13.77 -> 13.73 ms / step, not worth a default
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-serialization attribute when enabled
+template <typename Kern, typename... Args>
+static cudaError_t launch_pdl(Kern kern, dim3 grid, int threads, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <int BN, int MODE, bool HP, int LIGHT = 0, bool PAIR = false>
 static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const IgemmAux& aux, cudaStream_t st) {
   using Cfg = TileCfg<BN, HP, LIGHT>;
@@ -1790,10 +1816,9 @@ static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const
     return BCOSK_OK;
   }
   if (p.dtype == BCOSK_DTYPE_BF16)
-    kern<<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux);
+    BCOSK_CUDA_CHECK(launch_pdl(kern, grid, NUM_THREADS, Cfg::kSmemBytes, st, mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux));
   else
-    kern_h<<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux);
-  BCOSK_CUDA_CHECK(cudaGetLastError());
+    BCOSK_CUDA_CHECK(launch_pdl(kern_h, grid, NUM_THREADS, Cfg::kSmemBytes, st, mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux));
   return BCOSK_OK;
 }
 
@@ -1827,10 +1852,9 @@ static int launch_persistent(const LaunchMaps& mp, const bcosk_igemm_params& p, 
   if (tiles > 0x7fffffffLL) return set_error(BCOSK_EUNSUPPORTED, "igemm: too many tiles");
   dim3 grid((unsigned)(tiles < g_num_sms ? tiles : g_num_sms));
   if (p.dtype == BCOSK_DTYPE_BF16)
-    kern<<<grid, P_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux);
+    BCOSK_CUDA_CHECK(launch_pdl(kern, grid, P_THREADS, Cfg::kSmemBytes, st, mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux));
   else
-    kern_h<<<grid, P_THREADS, Cfg::kSmemBytes, st>>>(mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux);
-  BCOSK_CUDA_CHECK(cudaGetLastError());
+    BCOSK_CUDA_CHECK(launch_pdl(kern_h, grid, P_THREADS, Cfg::kSmemBytes, st, mp.a, mp.b, mp.in, mp.in2, mp.out1, mp.out2, p, aux));
   return BCOSK_OK;
 }
 
@@ -1924,10 +1948,9 @@ static int launch_flat_bn(const bcosk_igemm_params& p, cudaStream_t st) {
   if (tiles > 0x7fffffffLL || (long long)p.a_nb * hp * wp > 0x7fffffffLL) return set_error(BCOSK_EUNSUPPORTED, "igemm(flat): too large");
   dim3 grid((unsigned)(tiles < g_num_sms ? tiles : g_num_sms));
   if (p.dtype == BCOSK_DTYPE_BF16)
-    kern<<<grid, Cfg::kThreads, smem, st>>>(mp.a, mp.b, mp.out1, mp.out2, p, aux, geo);
+    BCOSK_CUDA_CHECK(launch_pdl(kern, grid, Cfg::kThreads, (size_t)smem, st, mp.a, mp.b, mp.out1, mp.out2, p, aux, geo));
   else
-    kern_h<<<grid, Cfg::kThreads, smem, st>>>(mp.a, mp.b, mp.out1, mp.out2, p, aux, geo);
-  BCOSK_CUDA_CHECK(cudaGetLastError());
+    BCOSK_CUDA_CHECK(launch_pdl(kern_h, grid, Cfg::kThreads, (size_t)smem, st, mp.a, mp.b, mp.out1, mp.out2, p, aux, geo));
   return BCOSK_OK;
 }
 
@@ -2098,6 +2121,12 @@ extern "C" int bcosk_debug_set_timing(void* buf, int32_t capacity_ctas) {
   return BCOSK_OK;
 }
 #endif
+
+extern "C" int bcosk_set_pdl(int32_t enabled) {
+  const int prev = g_pdl_enabled;
+  g_pdl_enabled = enabled != 0;
+  return prev;
+}
 
 extern "C" int bcosk_set_late_input(int32_t min_k_stages) {
   const int prev = g_late_in_iters;

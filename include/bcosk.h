@@ -155,6 +155,11 @@ int bcosk_igemm(const bcosk_igemm_params* p, void* stream);
 /* Scheduling switch for A/B measurements: 1 = launches with block_n 64 (the bandwidth-bound ones) run on the persistent
  * one-CTA-per-SM kernel, 0 (default) = one CTA per tile everywhere.  Returns the previous setting.  Results are identical. */
 int bcosk_set_persistent(int32_t enabled);
+/* 1 = the tensor-core kernels are launched with programmatic stream serialization (default 0: measured gain 0.3 %): their prologue (barrier
+ * init, TMEM allocation, descriptor prefetch) overlaps the previous launch's tail and `griddepcontrol.wait` orders every
+ * global-memory access after the previous launch's completion.  Returns the previous setting.  Results are identical. */
+int bcosk_set_pdl(int32_t enabled);
+
 /* 128-wide launches whose K loop has at least `min_k_stages` 64-deep stages fetch their epilogue input tile (residual /
  * producer gain) after the main loop instead of parking it in a ring slot, so the MMAs run on 3 stages instead of 2
  * (0 = never).  Returns the previous setting.  Results are identical. */
