@@ -2085,6 +2085,15 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
     return p.mode == BCOSK_MODE_FWD ? launch_igemm<64, BCOSK_MODE_FWD, true>(mp, p, aux, st)
                                     : launch_igemm<64, BCOSK_MODE_EXPLAIN, true>(mp, p, aux, st);
   }
+  {
+    // explain launches with ONE K stage and both input tiles (producer gain + extra gradient): the 3-slot variant fits
+    // them too - stage | extra-gradient tile | gain tile - with out2 staged over the extra-gradient tile, whose words
+    // every thread has consumed before it writes the same words of out2 (epilogue_explain_fast order)
+    const int iters = p.num_segs * p.num_taps * p.chunks_per_tap / (STAGE_K / p.kch);
+    if (bn == 64 && g_light_enabled && aux.tma_in2 && iters == 1 && p.mode == BCOSK_MODE_EXPLAIN && aux.tma_in &&
+        aux.tma_out1 && (aux.tma_out2 || !p.out2) && !p.y_f32 && p.y_planes == 1 && !p.mul2_f32)
+      return launch_igemm<64, BCOSK_MODE_EXPLAIN, false, 1>(mp, p, aux, st);
+  }
   if (bn == 64 && g_light_enabled && !aux.tma_in2) {
     // short K loop (<= 4 stages): the 3-CTA/SM variant
     const int iters = p.num_segs * p.num_taps * p.chunks_per_tap / (STAGE_K / p.kch);
