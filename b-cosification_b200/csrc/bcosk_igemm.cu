@@ -25,6 +25,13 @@ constexpr int BM = 128;       // CTA tile M (= UMMA M, one TMEM lane per output 
 constexpr int STAGE_K = 64;   // K elements per pipeline stage (128 bytes of 16-bit data per row)
 constexpr int A_STAGE_BYTES = BM * STAGE_K * 2;
 constexpr int NUM_THREADS = 192;
+#ifndef BCOSK_BN128_STAGES
+// Ring slots / CTAs per SM of the 128-wide per-tile kernel.  Three CTAs with two 32 KB stages each beat two CTAs with
+// three (measured: -0.63 ms of 14.3 per step, every 128-wide launch 4-20 % faster): a tile's load -> MMA -> epilogue ->
+// store chain is latency bound, so independent tiles in flight matter more than the depth of one tile's ring.
+#define BCOSK_BN128_STAGES 2
+#define BCOSK_BN128_BLOCKS 3
+#endif
 #ifndef BCOSK_LIGHT2_BLOCKS
 #define BCOSK_LIGHT2_BLOCKS 4   // CTAs per SM of the single-stage forward variant (5 spills ~200 B per thread)
 #endif
@@ -35,8 +42,8 @@ constexpr int NUM_THREADS = 192;
 // afterwards the y tile; slot 1 holds the residual tile and the gain tile is staged over it - every thread reads its own
 // residual words before it writes the same words of the gain tile, so the alias is safe.
 template <int BN, bool HP = false, int LIGHT = 0> struct TileCfg {
-  static constexpr int kStages = LIGHT == 2 ? 2 : (LIGHT ? 3 : ((BN == 128) ? 3 : 4));   // pipeline slots; the last may hold the input tile
-  static constexpr int kMinBlocks = LIGHT == 2 ? BCOSK_LIGHT2_BLOCKS : (LIGHT ? 3 : ((BN <= 128) ? 2 : 1));
+  static constexpr int kStages = LIGHT == 2 ? 2 : (LIGHT ? 3 : ((BN == 128) ? BCOSK_BN128_STAGES : 4));   // pipeline slots; the last may hold the input tile
+  static constexpr int kMinBlocks = LIGHT == 2 ? BCOSK_LIGHT2_BLOCKS : (LIGHT ? 3 : (BN == 128 ? BCOSK_BN128_BLOCKS : ((BN < 128) ? 2 : 1)));
   static constexpr int kBStageBytes = BN * STAGE_K * 2;
   static constexpr int kSlotBytes = A_STAGE_BYTES + kBStageBytes;   // A stage followed by its B stage
   static constexpr int kTileBytes = BM * BN * 2;                    // one 16-bit epilogue tile (BN/64 boxes of 16 KB)
@@ -892,8 +899,12 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     EpiTiles tl;
     tl.in = use_in_tile ? smem_u32(smem + (kSlots - 1) * Cfg::kSlotBytes) : 0u;
     tl.in2 = use_in2_tile ? smem_u32(smem + (kSlots - 2) * Cfg::kSlotBytes) : 0u;
-    tl.out1 = (Cfg::kTmaEpilogue && aux.tma_out1) ? smem_u32(smem) : 0u;
-    tl.out2 = (Cfg::kTmaEpilogue && aux.tma_out2) ? smem_u32(smem + Cfg::kSlotBytes) : 0u;
+    // two-slot rings: the input tile shares slot 1 with an output tile.  Forward reads the residual before it writes the
+    // gain (out2 in slot 1); explain writes out2 BEFORE it reads the producer gain, so there y (out1) takes slot 1 - it is
+    // written after the gain words of the same thread were read - and out2 goes to slot 0.
+    constexpr bool kSwapOut = MODE == BCOSK_MODE_EXPLAIN && kSlots == 2;
+    tl.out1 = (Cfg::kTmaEpilogue && aux.tma_out1) ? smem_u32(smem + (kSwapOut ? Cfg::kSlotBytes : 0)) : 0u;
+    tl.out2 = (Cfg::kTmaEpilogue && aux.tma_out2) ? smem_u32(smem + (kSwapOut ? 0 : Cfg::kSlotBytes)) : 0u;
 
     if constexpr (HP) {
       float acc[BN];
@@ -1823,7 +1834,7 @@ static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const
 }
 
 static int g_num_sms = 0;
-static int g_late_in_iters = 4;        // K stages from which the epilogue input tile is fetched after the main loop (0 = never)
+static int g_late_in_iters = 2;        // K stages from which the epilogue input tile is fetched after the main loop (0 = never)
 static int g_cluster = 1;              // 1 none; 2/4 weight-tile multicast across row blocks; 3 = CTA pairs (cta_group::2)
 // Measured on B200 (profiles/r01_schedule_ab.md): per-tile + 3 CTAs/SM and the persistent kernel reach the same
 // ~4 TB/s on the bandwidth-bound launches; the per-tile schedule is the default.
