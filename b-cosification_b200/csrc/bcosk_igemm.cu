@@ -50,8 +50,7 @@ template <int BN, bool HP = false, int LIGHT = 0> struct TileCfg {
   static constexpr bool kTmaEpilogue = !HP && (BN == 64 || BN == 128);
   // HP (high-precision accumulation): two TMEM accumulators that the epilogue warps drain every pipeline stage
   static constexpr int kTmemCols = (BN < 32 ? 32 : BN) * (HP ? 2 : 1);
-  // LIGHT = 2: the last slot only ever holds a 16 KB tile, its last 8 KB are not allocated
-  static constexpr int kBarOffset = kStages * (A_STAGE_BYTES + kBStageBytes) - (LIGHT == 2 ? 8192 : 0);
+  static constexpr int kBarOffset = kStages * (A_STAGE_BYTES + kBStageBytes);
   // stages + 1 KB alignment slack + barriers/params
   static constexpr int kSmemBytes = kBarOffset + 1024 + 256 + 2 * BN * 4;
 };
@@ -1841,6 +1840,7 @@ static int g_cluster = 1;              // 1 none; 2/4 weight-tile multicast acro
 static int g_persistent_enabled = 0;   // 0 off, 1 tiles strided over the grid, 2 row-block order
 static bool g_light_enabled = true;
 static bool g_light4_enabled = true;
+static int g_light4_max_iters = 4;
 
 template <int MODE>
 static int launch_persistent(const LaunchMaps& mp, const bcosk_igemm_params& p, const IgemmAux& aux, cudaStream_t st) {
@@ -2108,8 +2108,14 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
   if (bn == 64 && g_light_enabled && !aux.tma_in2) {
     // short K loop (<= 4 stages): the 3-CTA/SM variant
     const int iters = p.num_segs * p.num_taps * p.chunks_per_tap / (STAGE_K / p.kch);
-    if (iters == 1 && p.mode == BCOSK_MODE_FWD && g_light4_enabled && aux.tma_out1 && (aux.tma_out2 || !p.gain))
-      return launch_igemm<64, BCOSK_MODE_FWD, false, 2>(mp, p, aux, st);      // one K stage: 4 CTAs per SM
+    // two-slot variant, 4 CTAs per SM: one K stage with the input tile prefetched, or up to four stages with the input
+    // tile fetched after the loop (aux.late_in); the second output tile is staged over the consumed input tile
+    const bool out_tiles = aux.tma_out1 && (aux.tma_out2 || !(p.mode == BCOSK_MODE_FWD ? p.gain : p.out2));
+    if (iters <= g_light4_max_iters && g_light4_enabled && out_tiles) {
+      aux.late_in = (aux.tma_in && iters >= 2) ? 1 : 0;
+      return p.mode == BCOSK_MODE_FWD ? launch_igemm<64, BCOSK_MODE_FWD, false, 2>(mp, p, aux, st)
+                                      : launch_igemm<64, BCOSK_MODE_EXPLAIN, false, 2>(mp, p, aux, st);
+    }
     if (iters <= 4)
       return p.mode == BCOSK_MODE_FWD ? launch_igemm<64, BCOSK_MODE_FWD, false, 1>(mp, p, aux, st)
                                       : launch_igemm<64, BCOSK_MODE_EXPLAIN, false, 1>(mp, p, aux, st);
@@ -2164,6 +2170,7 @@ extern "C" int bcosk_set_light(int32_t enabled) {
   const int prev = (g_light_enabled ? 1 : 0) | (g_light4_enabled ? 2 : 0);
   g_light_enabled = (enabled & 1) != 0;
   g_light4_enabled = (enabled & 2) != 0;
+  g_light4_max_iters = (enabled & 4) ? 1 : 4;      // bit 2: only single-stage launches use the 4-CTA variant (A/B)
   return prev;
 }
 
