@@ -2170,7 +2170,7 @@ extern "C" int bcosk_set_light(int32_t enabled) {
   const int prev = (g_light_enabled ? 1 : 0) | (g_light4_enabled ? 2 : 0);
   g_light_enabled = (enabled & 1) != 0;
   g_light4_enabled = (enabled & 2) != 0;
-  g_light4_max_iters = (enabled & 4) ? 1 : 4;      // bit 2: only single-stage launches use the 4-CTA variant (A/B)
+  g_light4_max_iters = (enabled & 4) ? 1 : ((enabled & 8) ? 1 << 20 : 4);   // bit 2: single-stage launches only; bit 3: any K (A/B)
   return prev;
 }
 

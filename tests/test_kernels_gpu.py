@@ -375,6 +375,72 @@ def test_cluster_multicast_matches_single_cta(bcosk_lib):
             assert torch.equal(a, b), cl
 
 
+def test_launch_variants_are_bit_identical(bcosk_lib):
+    """the scheduling switches (CTAs per SM / ring slots, late input tile, programmatic dependent launch) only change
+    how tiles are scheduled: every output must be bit-identical"""
+    def build():
+        g = torch.Generator().manual_seed(91)
+        nb, h = 4, 16
+        plan = _mini_plan(nb, 1)
+        ops = []
+        # forward 1x1, ONE K stage, residual (2-slot / 4-CTA variant) and TWO K stages (late input tile)
+        for cin in (64, 128):
+            x = _rand_act(g, nb, h, h, cin, 1)
+            w = torch.randn(256, cin, 1, 1, generator=g) / math.sqrt(cin)
+            plan.sd = {"bn.running_var": torch.rand(256, generator=g) + 0.5, "bn.weight": torch.rand(256, generator=g) + 0.5}
+            res = _rand_act(g, nb, h, h, 256, 1)
+            plan.fwd_ops.clear()
+            _, rec = plan._conv_fwd(f"f{cin}", x, w, 1, 0, 0, bn="bn", relu=True, res=res, want_mask=True)
+            ops += list(plan.fwd_ops)
+        # 128-wide, long K loop, residual
+        x = _rand_act(g, nb, h, h, 128, 1)
+        w = torch.randn(256, 128, 3, 3, generator=g) / math.sqrt(128 * 9)
+        res = _rand_act(g, nb, h, h, 256, 1)
+        plan.fwd_ops.clear()
+        _, rec3 = plan._conv_fwd("f3x3", x, w, 1, 1, 1, bn="bn", relu=True, res=res, want_mask=True)
+        ops += list(plan.fwd_ops)
+        # explain 1x1: one K stage, producer gain + extra gradient + second output + mask
+        xe = _rand_act(g, nb, h, h, 256, 1)
+        we = torch.randn(64, 256, 1, 1, generator=g) / 16
+        plan.fwd_ops.clear()
+        _, rece = plan._conv_fwd("e", xe, we, 1, 0, 0, bn=None, relu=True)
+        plan._alloc_ghat(rece)
+        rece.ghat.copy_(torch.randn(nb, h, h, 64, generator=g).to(plan.dt))
+        M = nb * h * h
+        plan._dgrad(rece, y=torch.zeros(nb, h, h, 256, dtype=plan.dt), mul1=(torch.rand(M, 256, generator=g) + 0.5).to(plan.gain_dt),
+                    add=_rand_act(g, nb, h, h, 256, 1).t, out2=torch.zeros(nb, h, h, 256, dtype=plan.dt),
+                    mask2=torch.randint(-2**31, 2**31 - 1, (M, 8), generator=g, dtype=torch.int64).to(torch.int32))
+        # explain 3x3 128-wide with producer gain (late input tile, swapped output slots)
+        plan._alloc_ghat(rec3)
+        rec3.ghat.copy_(torch.randn(nb, h, h, 256, generator=g).to(plan.dt))
+        plan._dgrad(rec3, y=torch.zeros(nb, h, h, 128, dtype=plan.dt), mul1=(torch.rand(M, 128, generator=g) + 0.5).to(plan.gain_dt))
+        return ops + list(plan.bwd_ops)
+
+    def run(light, late, pdl):
+        prev = (bcosk_lib.bcosk_set_light(light), bcosk_lib.bcosk_set_late_input(late), bcosk_lib.bcosk_set_pdl(pdl))
+        try:
+            memo = {}
+            dops = [U.to_device(o, "cuda", memo) for o in build()]
+            for o in dops:
+                o.run()
+            torch.cuda.synchronize()
+            outs = []
+            for o in dops:
+                outs += [t.cpu() for t in (o.y, o.gain, o.maskbits, o.sq_out, o.out2) if t is not None]
+            return outs
+        finally:
+            bcosk_lib.bcosk_set_light(prev[0]); bcosk_lib.bcosk_set_late_input(prev[1]); bcosk_lib.bcosk_set_pdl(prev[2])
+
+    ref_ops = build()
+    print(_run_and_compare(ref_ops))                 # default switches against the emulator
+    base = run(0, 0, 0)                              # 2 CTAs / SM everywhere, input tile parked in a ring slot
+    for cfg in ((1, 0, 0), (3, 2, 0), (3, 2, 1), (11, 2, 0), (7, 1, 0)):
+        outs = run(*cfg)
+        assert len(outs) == len(base)
+        for a, b in zip(outs, base):
+            assert torch.equal(a, b), cfg
+
+
 def test_elementwise_kernels(bcosk_lib):
     g = torch.Generator().manual_seed(5)
     nb, S = 3, 32
