@@ -176,10 +176,10 @@ def avgpool_fwd(x, nb, h, w, c, planes, k, stride, pad, y, op, oq, dtype, sq) ->
           "bcosk_avgpool_fwd")
 
 
-def avgpool_bwd_mul(gy, nb, h, w, c, planes, k, stride, pad, op, oq, gain, gain_f32, gx, dtype) -> None:
+def avgpool_bwd_mul(gy, nb, h, w, c, planes, k, stride, pad, op, oq, gain, gain_f32, gx, dtype, gain_sqrt_scale=None) -> None:
     rp, ip = _pixel_pitches(gx)
     check(load().bcosk_avgpool_bwd_mul(_p(gy), nb, h, w, c, planes, k, stride, pad, op, oq, _p(gain), int(gain_f32), _p(gx),
-                                       dtype, rp, ip, _stream()), "bcosk_avgpool_bwd_mul")
+                                       dtype, rp, ip, _p(gain_sqrt_scale), _stream()), "bcosk_avgpool_bwd_mul")
 
 
 def explanation_rgba(grad6, x, smooth, percentile, tmp, out) -> None:

@@ -401,7 +401,8 @@ avgpool_fwd_rows_kernel(const T* __restrict__ x, int h, int w, int c, int k, int
 template <typename T>
 __global__ void __launch_bounds__(256)
 avgpool_bwd_mul_rows_kernel(const T* __restrict__ gy, int h, int w, int c, int k, int stride, int pad, int op, int oq,
-                            const T* __restrict__ gain, T* __restrict__ gx, int row_pitch, int img_pitch) {
+                            const T* __restrict__ gain, T* __restrict__ gx, int row_pitch, int img_pitch,
+                            const float* __restrict__ gain_sqrt_scale) {
   extern __shared__ __align__(128) uint8_t pool_smem[];
   __shared__ __align__(8) uint64_t bar;
   const int img = blockIdx.y, yy = blockIdx.x;
@@ -440,6 +441,12 @@ avgpool_bwd_mul_rows_kernel(const T* __restrict__ gy, int h, int w, int c, int k
     uint4* slot = reinterpret_cast<uint4*>(s_gain + ((size_t)xx * c + g * 8) * sizeof(T));
     float gn[8];
     unpack8<T>(*slot, gn);
+    if (gain_sqrt_scale != nullptr) {
+      // `gain` holds the producer's ReLU output: the multiplier is sqrt(y / ||patch||)
+      const float sc = __ldg(gain_sqrt_scale + ((size_t)img * h + yy) * w + xx);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gn[i] = fast_sqrt(gn[i] * sc);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] *= inv * gn[i];
     uint4 o;
@@ -730,7 +737,8 @@ extern "C" int bcosk_avgpool_fwd(const void* x, int32_t nb, int32_t h, int32_t w
 
 extern "C" int bcosk_avgpool_bwd_mul(const void* gy, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t k,
                                      int32_t stride, int32_t pad, int32_t op, int32_t oq, const void* gain, int32_t gain_f32,
-                                     void* gx, int32_t dtype, int32_t row_pitch, int32_t img_pitch, void* stream) {
+                                     void* gx, int32_t dtype, int32_t row_pitch, int32_t img_pitch,
+                                     const float* gain_sqrt_scale, void* stream) {
   if (!gy || !gx || c % 8) return set_error(BCOSK_EINVAL, "avgpool_bwd_mul: bad argument");
   if (row_pitch == 0) row_pitch = w;
   if (img_pitch == 0) img_pitch = h * row_pitch;
@@ -742,11 +750,13 @@ extern "C" int bcosk_avgpool_bwd_mul(const void* gy, int32_t nb, int32_t h, int3
     if (planes == 1 && gain != nullptr && !gain_f32 && k <= 2 * stride && smem <= 48 * 1024 && h <= 65535) {
       BCOSK_DTYPE_SWITCH(dtype, avgpool_bwd_mul_rows_kernel<T><<<dim3(h, nb), 256, smem, S(stream)>>>(
           reinterpret_cast<const T*>(gy), h, w, c, k, stride, pad, op, oq, reinterpret_cast<const T*>(gain),
-          reinterpret_cast<T*>(gx), row_pitch, img_pitch);)
+          reinterpret_cast<T*>(gx), row_pitch, img_pitch, gain_sqrt_scale);)
       BCOSK_CUDA_CHECK(cudaGetLastError());
       return BCOSK_OK;
     }
   }
+  if (gain_sqrt_scale != nullptr)
+    return set_error(BCOSK_EUNSUPPORTED, "avgpool_bwd_mul: gain_sqrt_scale needs the row-staged path (one 16-bit plane, k <= 2*stride)");
   const long long n = (long long)h * w * (c / 8);
   const dim3 bgrid(blocks_for(n, 256), nb);
   if (planes == 1) {

@@ -92,6 +92,7 @@ __device__ int g_timing_cap = 0;
 struct RowInfo {
   int m, img, p, q;
   bool valid;
+  float gscale;   // explain: mul1_sqrt_scale[row] (the multiplier is sqrt(mul1 * gscale)) or unused
 };
 
 // 16-bit row segment (32 columns starting at `ptr`) -> 32 floats, adding over precision planes
@@ -333,6 +334,10 @@ __device__ __noinline__ void epilogue_chunk_generic(const bcosk_igemm_params& p,
       if (tl.in != 0) tile_load32<T>(tl.in, row, j, g);
       else if (p.mul1_f32) load32_f32(reinterpret_cast<const float*>(p.mul1) + (size_t)ri.m * p.mul1_ld + c0, ncols, g);
       else load32_planes<T>(reinterpret_cast<const T*>(p.mul1) + (size_t)ri.m * p.mul1_ld + c0, 1, 0, ncols, g);
+      if (p.mul1_sqrt_scale != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) g[i] = fast_sqrt(g[i] * ri.gscale);
+      }
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] *= g[i];
     }
@@ -489,11 +494,22 @@ __device__ __forceinline__ void epilogue_explain_fast(const bcosk_igemm_params& 
   if (p.mul1 != nullptr) {
     if (tl.in != 0) tile_load_words(tl.in, row, j, w);
     else global_load_words(reinterpret_cast<const T*>(p.mul1) + (size_t)ri.m * p.mul1_ld + c0, ncols, w);
+    if (p.mul1_sqrt_scale != nullptr) {
+      // mul1 holds the producer's ReLU output: gain = sqrt(y / ||patch||)
+      const float2 s2 = make_float2(ri.gscale, ri.gscale);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float2 g = __fmul2_rn(make_float2(v[2 * k], v[2 * k + 1]), Cvt<T>::unpack2(w[k]));
-      v[2 * k] = g.x;
-      v[2 * k + 1] = g.y;
+      for (int k = 0; k < 16; ++k) {
+        const float2 ys = __fmul2_rn(Cvt<T>::unpack2(w[k]), s2);
+        v[2 * k] *= fast_sqrt(ys.x);
+        v[2 * k + 1] *= fast_sqrt(ys.y);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float2 g = __fmul2_rn(make_float2(v[2 * k], v[2 * k + 1]), Cvt<T>::unpack2(w[k]));
+        v[2 * k] = g.x;
+        v[2 * k + 1] = g.y;
+      }
     }
   }
   if (p.y_f32) {
@@ -862,6 +878,7 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     const int64_t yrow = p.os_0 + (int64_t)ri.img * p.os_n + (int64_t)ri.p * p.os_p + (int64_t)ri.q * p.os_q;
     if (MODE == BCOSK_MODE_EXPLAIN && p.side_mapped) ri.m = (int)yrow;   // side tensors follow the mapped output row
+    ri.gscale = (MODE == BCOSK_MODE_EXPLAIN && p.mul1_sqrt_scale != nullptr && ri.valid) ? __ldg(p.mul1_sqrt_scale + ri.m) : 1.f;
     float inv_norm = 1.f;
     int64_t add_row = -1;
     if (MODE == BCOSK_MODE_FWD) {
@@ -990,6 +1007,7 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     if (MODE == BCOSK_MODE_FWD) {
       if (p.sq_out != nullptr && ri.valid) p.sq_out[(size_t)tile_n * M + ri.m] = sq_acc;
+      if (p.inv_norm_out != nullptr && tile_n == 0 && ri.valid && warp >= 2) p.inv_norm_out[ri.m] = inv_norm;
     }
     tc_fence_before();
   }
@@ -1324,6 +1342,7 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       }
       const int64_t yrow = p.os_0 + (int64_t)ri.img * p.os_n + (int64_t)ri.p * p.os_p + (int64_t)ri.q * p.os_q;
     if (MODE == BCOSK_MODE_EXPLAIN && p.side_mapped) ri.m = (int)yrow;   // side tensors follow the mapped output row
+    ri.gscale = (MODE == BCOSK_MODE_EXPLAIN && p.mul1_sqrt_scale != nullptr && ri.valid) ? __ldg(p.mul1_sqrt_scale + ri.m) : 1.f;
       int64_t add_row = -1;
       if (MODE == BCOSK_MODE_EXPLAIN && p.add != nullptr && ri.valid) {
         const int s = p.add_stride;
@@ -1391,6 +1410,8 @@ bcosk_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       }
       if (want_sq && half == 0 && ri.valid)
         p.sq_out[(size_t)tile_n * M + ri.m] = s_sq[(buf * 2) * BM + row] + s_sq[(buf * 2 + 1) * BM + row];
+      if (MODE == BCOSK_MODE_FWD && p.inv_norm_out != nullptr && tile_n == 0 && half == 0 && ri.valid)
+        p.inv_norm_out[ri.m] = inv_norm;
 #ifdef BCOSK_TIMING2
       if (et == 0 && g_timing_buf != nullptr && (int)blockIdx.x < g_timing_cap) {
         const long long _t3 = clock64();
@@ -1615,6 +1636,7 @@ bcosk_igemm_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       ri.m = ri.valid ? (img * p.op + ri.p) * p.oq + ri.q : 0;
       const int64_t yrow = p.os_0 + (int64_t)ri.img * p.os_n + (int64_t)ri.p * p.os_p + (int64_t)ri.q * p.os_q;
     if (MODE == BCOSK_MODE_EXPLAIN && p.side_mapped) ri.m = (int)yrow;   // side tensors follow the mapped output row
+    ri.gscale = (MODE == BCOSK_MODE_EXPLAIN && p.mul1_sqrt_scale != nullptr && ri.valid) ? __ldg(p.mul1_sqrt_scale + ri.m) : 1.f;
       float inv_norm = 1.f;
       uint32_t mb = 0xffffffffu;
       int64_t add_row = -1;
@@ -1704,6 +1726,7 @@ bcosk_igemm_flat_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         for (int h = 1; h < BN / 32; ++h) s += sq_buf[h * BM + row];
         p.sq_out[ri.m] = s;
       }
+      if (MODE == BCOSK_MODE_FWD && p.inv_norm_out != nullptr && j == 0 && ri.valid) p.inv_norm_out[ri.m] = inv_norm;
 #ifdef BCOSK_TIMING
       if (et == 0 && g_timing_buf != nullptr && (int)blockIdx.x < g_timing_cap) {
         const long long _t_d = clock64();
@@ -2000,6 +2023,9 @@ static int validate(const bcosk_igemm_params& p) {
     return set_error(BCOSK_EINVAL, "igemm: bad sq_in geometry");
   if (p.y_ld % (p.y_f32 ? 4 : 8) != 0) return set_error(BCOSK_EINVAL, "igemm: y_ld alignment");
   if (p.a_nb < 1 || p.op < 1 || p.oq < 1) return set_error(BCOSK_EINVAL, "igemm: empty problem");
+  if (p.mul1_sqrt_scale && (p.mode != BCOSK_MODE_EXPLAIN || !p.mul1 || p.mul1_f32))
+    return set_error(BCOSK_EINVAL, "igemm: mul1_sqrt_scale needs explain mode and a 16-bit mul1");
+  if (p.inv_norm_out && p.mode != BCOSK_MODE_FWD) return set_error(BCOSK_EINVAL, "igemm: inv_norm_out is a forward output");
   if (p.side_mapped && (p.mode != BCOSK_MODE_EXPLAIN || p.add != nullptr))
     return set_error(BCOSK_EINVAL, "igemm: side_mapped needs explain mode without an extra gradient");
   return BCOSK_OK;

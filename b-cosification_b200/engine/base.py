@@ -46,6 +46,9 @@ class ConvRec:
     ghat: Optional[Tensor] = None          # gradient wrt the pre-scale linear output (x gain), maybe zero-inserted
     ghat_map: Optional[Tuple[int, int, int, int]] = None
     algo_flops: float = 0.0
+    # gain not stored (include/bcosk.h mul1_sqrt_scale): recomputed as sqrt(y * inv) from the ReLU output and 1/||patch||
+    gain_y: Optional[Tensor] = None
+    gain_inv: Optional[Tensor] = None
 
     @property
     def k(self) -> int:
@@ -119,6 +122,9 @@ class PlanBase:
     # the library runs with 3 CTAs per SM (more bytes in flight); 0 disables
     light_k_iters = 3
     parity_dgrad = True              # strided k x k data gradients as stride^2 parity-class launches (no zero insertion)
+    # do not store gains that are sqrt(y / ||patch||) of a stored ReLU output.  Measured: the forward launches save 0.20 ms
+    # of gain writes per step and the consumers pay 0.21 ms for the square roots (MUFU, 16 per cycle per SM): off.
+    recompute_gain = False
     flat_3x3 = True                  # 64 -> <=64 channel stride-1 k x k convs and their data gradients as flat-window launches
     flat_stem = True                 # stem and its data gradient as flat-window launches (throughput mode only)
     autotune_default = True          # capture() measures the per-launch schedule first (see autotune)
@@ -179,8 +185,22 @@ class PlanBase:
         yp = 1 if y_f32 else self.planes
         y = self._empty(nb, oh, ow, yp * o, dtype=torch.float32 if y_f32 else self.dt)
         rec = ConvRec(name, w, stride, pad_lo, pad_hi, (h, wd), (oh, ow), cin_phys)
+        # y = lin |lin| / n, clamped at 0: the explanation gain |lin| / n is sqrt(y / n) - not stored where that holds
+        # (ReLU, no residual, BN multiplier folded, b = 2, throughput mode)
+        lazy_gain = (self.with_explain and self.recompute_gain and self.planes == 1 and not self.hp_accum and relu
+                     and res is None and alpha is None and beta is None and lin_bias is None and not y_f32
+                     and self.scale_mode == L.BCOSK_SCALE_B2)
+        inv_out = None
+        if lazy_gain:
+            rec.gain_y = y.view(M, o)
+            if inv_norm is None:
+                inv_out = self._empty(M, dtype=torch.float32)
+                rec.gain_inv = inv_out
+            else:
+                rec.gain_inv = inv_norm
         if self.with_explain:
-            rec.gain = self._empty(M, o, dtype=self.gain_dt)
+            if not lazy_gain:
+                rec.gain = self._empty(M, o, dtype=self.gain_dt)
             if want_mask:
                 rec.mask = self._zeros(M, (o + 31) // 32, dtype=torch.int32)
         sq = self._empty(parts, M, dtype=torch.float32) if want_sq else None
@@ -193,11 +213,17 @@ class PlanBase:
             lin_bias=None if lin_bias is None else self._dev(lin_bias),
             res=None if res is None else res.t, res_planes=self.planes,
             gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32, hp_accum=self.hp_accum, flat=flat,
+            inv_norm_out=inv_out,
             algo_flops=2.0 * M * o * float((w != 0).sum().item()) / o))
         rec.algo_flops = self.fwd_ops[-1].algo_flops
         return Act(y, o, sq, parts), rec
 
     # ------------------------------------------------------------------ explanation emission
+    @staticmethod
+    def _gain_of(rec: ConvRec):
+        """(mul1, mul1_sqrt_scale) the consumer's explain epilogue multiplies by: the stored gain, or the ReLU output + 1/norm"""
+        return (rec.gain, None) if rec.gain is not None else (rec.gain_y, rec.gain_inv)
+
     def _alloc_ghat(self, rec: ConvRec, classes: bool = False) -> None:
         """Buffer for g_out * gain of `rec`.  A strided k>1 conv reads it zero-inserted at input resolution so
         that its data gradient is a stride-1 gather."""
@@ -213,13 +239,14 @@ class PlanBase:
 
     def _dgrad(self, rec: ConvRec, *, y: Tensor, y_map=None, mul1: Optional[Tensor] = None, add: Optional[Tensor] = None,
                add_stride: int = 1, out2: Optional[Tensor] = None, mul2: Optional[Tensor] = None,
-               mask2: Optional[Tensor] = None, y_f32: bool = False, kch: int = 64, flat: bool = False) -> None:
+               mask2: Optional[Tensor] = None, y_f32: bool = False, kch: int = 64, flat: bool = False,
+               mul1_sqrt_scale: Optional[Tensor] = None) -> None:
         """Data gradient of `rec` as a stride-1 gather over rec.ghat (tcgen05 implicit GEMM, explain epilogue)."""
         g = rec.ghat
         k = rec.k
         if rec.stride > 1 and k > 1 and rec.ghat_map is None:
             assert add is None and out2 is None and y_map is None and not y_f32 and not flat
-            return self._dgrad_classes(rec, y=y, mul1=mul1, kch=kch)
+            return self._dgrad_classes(rec, y=y, mul1=mul1, kch=kch, mul1_sqrt_scale=mul1_sqrt_scale)
         if rec.stride > 1 and k == 1:
             oh, ow = rec.out_hw      # dense GEMM at output resolution; consumer adds it sub-sampled
         else:
@@ -243,10 +270,12 @@ class PlanBase:
             else self._block_n(n, bmat.shape[1] // 64),   # dense extra gradient: 64-wide tiles stage it with TMA
             hp_accum=self.hp_accum, y=y, y_planes=1 if y_f32 else self.planes, y_f32=y_f32,
             out_map=y_map, add=add, add_planes=self.planes, add_stride=add_stride, mul1=mul1, out2=out2,
-            out2_planes=self.planes, mul2=mul2, mask2=mask2, flat=flat, algo_flops=rec.algo_flops,
+            out2_planes=self.planes, mul2=mul2, mask2=mask2, flat=flat, mul1_sqrt_scale=mul1_sqrt_scale,
+            algo_flops=rec.algo_flops,
             a_dense_frac=1.0 / (rec.stride * rec.stride) if rec.ghat_map is not None else 1.0))
 
-    def _dgrad_classes(self, rec: ConvRec, *, y: Tensor, mul1: Optional[Tensor], kch: int = 64) -> None:
+    def _dgrad_classes(self, rec: ConvRec, *, y: Tensor, mul1: Optional[Tensor], kch: int = 64,
+                       mul1_sqrt_scale: Optional[Tensor] = None) -> None:
         """Strided k x k data gradient over the DENSE gradient tensor, one launch per parity class of the input pixel.
 
         gx[s*i+py, s*j+px] = sum over the taps dy = ry + s*t (ry = (py+pad) % s) of g[i + cy - t, ...] W[dy, dx]^T with
@@ -282,7 +311,7 @@ class PlanBase:
                     chunks_per_tap=cpt, taps=[(jx, jy) for jy in range(ty) for jx in range(tx)],
                     seg_a_choff=P.seg_a_offsets(self.planes, rec.cout), dtype=self.dt_code, mode=L.BCOSK_MODE_EXPLAIN,
                     block_n=self._block_n(n, bmat.shape[1] // 64), hp_accum=self.hp_accum, y=y, y_planes=self.planes,
-                    out_map=(py * iw + px, ih * iw, s * iw, s), mul1=mul1, side_mapped=True,
+                    out_map=(py * iw + px, ih * iw, s * iw, s), mul1=mul1, side_mapped=True, mul1_sqrt_scale=mul1_sqrt_scale,
                     algo_flops=rec.algo_flops * (sum(float((rec.w[:, :, dy, dx] != 0).sum().item()) for dy, dx in sel) / nz),
                     a_dense_frac=1.0 / (s * s)))    # the s*s launches together read the gradient once
 

@@ -72,6 +72,8 @@ class IgemmOp:
     sched: int = 0                   # include/bcosk.h `sched`: 0 default, 1 per tile, 2 persistent, 3 persistent row blocks
     flat: bool = False               # include/bcosk.h `a_flat`: `a` is the interior view of a zero-bordered buffer
     side_mapped: bool = False        # include/bcosk.h `side_mapped`: mul1 / out2 / ... follow the mapped output row
+    inv_norm_out: Optional[Tensor] = None      # forward: [M] fp32, receives the 1/||patch|| the launch used
+    mul1_sqrt_scale: Optional[Tensor] = None   # explain: mul1 holds the producer's ReLU output, gain = sqrt(mul1 * this[row])
 
     # ---- derived ----
     @property
@@ -99,7 +101,8 @@ class IgemmOp:
         total += ydense
         if self.inv_norm is None and self.sq_in is not None:
             total += nbytes(self.sq_in)
-        for t in (self.inv_norm, self.alpha, self.beta, self.res, self.gain, self.maskbits, self.sq_out, self.add):
+        for t in (self.inv_norm, self.alpha, self.beta, self.res, self.gain, self.maskbits, self.sq_out, self.add,
+                  self.inv_norm_out, self.mul1_sqrt_scale):
             total += nbytes(t)
         for t in (self.mul1, self.out2, self.mul2, self.mask2):
             if t is not None and self.side_mapped:      # a parity-class launch touches only its own rows of these
@@ -207,6 +210,8 @@ class IgemmOp:
         p.hp_accum = int(self.hp_accum)
         p.sched = int(self.sched)
         p.side_mapped = int(self.side_mapped)
+        p.set_ptr("inv_norm_out", self.inv_norm_out)
+        p.set_ptr("mul1_sqrt_scale", self.mul1_sqrt_scale)
         if self.flat and self.a.is_contiguous():
             p.a_flat = 2                      # dense tensor: the zero borders are made in shared memory
             assert self.stride == (1, 1) and len(self.seg_a_choff) == 1 and self.chunks_per_tap == 1 and self.n <= 64
@@ -288,12 +293,13 @@ class AvgPoolBwdMulOp:
     gain: Optional[Tensor]  # [nb*h*w, c]
     gx: Tensor           # [nb, h, w, planes*c]
     dtype: int
+    gain_sqrt_scale: Optional[Tensor] = None   # [nb*h*w] fp32: `gain` holds the ReLU output y, multiplier = sqrt(y * this)
 
     def run(self) -> None:
         nb, h, w, _ = self.gx.shape
         L.avgpool_bwd_mul(self.gy, nb, h, w, self.c, self.planes, self.k, self.stride, self.pad, self.gy.shape[1],
                           self.gy.shape[2], self.gain, self.gain is not None and self.gain.dtype == torch.float32,
-                          self.gx, self.dtype)
+                          self.gx, self.dtype, self.gain_sqrt_scale)
 
 
 @dataclass

@@ -154,7 +154,8 @@ class ResNetPlan(PlanBase):
             blk = self.blocks[bi]
             convs = blk.convs
             for j in range(len(convs) - 1, 0, -1):       # conv_j's data gradient feeds conv_{j-1}'s ghat
-                self._dgrad(convs[j], y=convs[j - 1].ghat, y_map=convs[j - 1].ghat_map, mul1=convs[j - 1].gain)
+                m1, m1s = self._gain_of(convs[j - 1])
+                self._dgrad(convs[j], y=convs[j - 1].ghat, y_map=convs[j - 1].ghat_map, mul1=m1, mul1_sqrt_scale=m1s)
             add, add_stride = blk.side, 1
             if blk.ds is not None:
                 dds = self._zeros(nb, blk.ds.out_hw[0], blk.ds.out_hw[1], pl * blk.ds.cin_phys) if blk.ds.stride > 1 \
@@ -168,8 +169,8 @@ class ResNetPlan(PlanBase):
             else:
                 self._dgrad(convs[0], y=self.g_pool, add=add, add_stride=add_stride)
         # ---- pool backward x stem gain, stem data gradient (space-to-depth), contribution map
-        self.bwd_ops.append(O.AvgPoolBwdMulOp("pool.bwd", self.g_pool, 64, pl, 3, 2, 1, self.stem.gain, self.stem.ghat,
-                                              self.dt_code))
+        m1, m1s = self._gain_of(self.stem)
+        self.bwd_ops.append(O.AvgPoolBwdMulOp("pool.bwd", self.g_pool, 64, pl, 3, 2, 1, m1, self.stem.ghat, self.dt_code, m1s))
         h2 = self.size // 2
         self.g0 = self._zeros(nb, h2, h2, self.stem_cp, dtype=torch.float32)
         self._dgrad(self.stem, y=self.g0, y_f32=True, kch=64, flat=self.stem_flat)

@@ -148,6 +148,14 @@ typedef struct bcosk_igemm_params {
    *      that reach them, so the s*s launches together do k*k/(s*s) taps per pixel instead of k*k over a zero-inserted
    *      gradient.  `add` is not supported together with it. */
   int32_t side_mapped;
+  /* ---- gains that are not stored.  For a B-cos conv followed by ReLU with no residual and the BN multiplier folded into
+   *      the weights, y = lin |lin| / n (clamped at 0), so the gain the explanation pass needs, |lin| / n, equals
+   *      sqrt(y / n): it is recomputed from the activation the next layer keeps anyway instead of being written (-1.7 GB
+   *      of writes per RN50 step).  Forward: inv_norm_out [M] (optional) receives the 1/||patch|| the launch used.
+   *      Explain: mul1_sqrt_scale [M] non-NULL means `mul1` holds that ReLU output y and the multiplier is
+   *      sqrt(mul1 * mul1_sqrt_scale[row]).  Both are addressed like mul1 (dense row, or mapped row with side_mapped). */
+  float* inv_norm_out;
+  const float* mul1_sqrt_scale;
 } bcosk_igemm_params;
 
 int bcosk_igemm(const bcosk_igemm_params* p, void* stream);
@@ -220,7 +228,10 @@ int bcosk_avgpool_fwd(const void* x, int32_t nb, int32_t h, int32_t w, int32_t c
  * gx_row_pitch / gx_img_pitch: pixels between rows / images of gx, 0 = dense (see bcosk_input_prep_s2d). */
 int bcosk_avgpool_bwd_mul(const void* gy, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t k,
                           int32_t stride, int32_t pad, int32_t op, int32_t oq, const void* gain, int32_t gain_f32,
-                          void* gx, int32_t dtype, int32_t gx_row_pitch, int32_t gx_img_pitch, void* stream);
+                          void* gx, int32_t dtype, int32_t gx_row_pitch, int32_t gx_img_pitch,
+                          const float* gain_sqrt_scale, void* stream);
+/* gain_sqrt_scale [nb*h*w] non-NULL: `gain` holds the producer's ReLU output y and the multiplier is
+ * sqrt(gain * gain_sqrt_scale[pixel]) (see bcosk_igemm_params.mul1_sqrt_scale); single 16-bit plane only. */
 
 /* ResNetBcos._forward_impl standard_models.py:50-52 tail + LogitLayer logitlayer.py:22-27:
  * logits[img, cls] = mean_pix fc[img, pix, cls] * inv_temp + bias; pred[img] = argmax (first max). */

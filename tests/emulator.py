@@ -135,6 +135,8 @@ def run_igemm(op: O.IgemmOp) -> None:
             op.maskbits.copy_(_pack_mask(pos if op.relu else torch.ones_like(pos)))
         if op.gain is not None:
             op.gain.copy_(t.to(op.gain.dtype))
+        if op.inv_norm_out is not None:
+            op.inv_norm_out.copy_(inv_norm.float().reshape(-1))
         y2 = op.y.view(-1, op.y.shape[-1])
         if op.y_f32:
             y2[rows] = v
@@ -171,7 +173,11 @@ def run_igemm(op: O.IgemmOp) -> None:
             tmp2 = torch.zeros(M, op.out2.shape[-1], dtype=op.out2.dtype)
             _split_store(tmp2, o, op.out2_planes)
             o2[side] = tmp2
-        v = tot * op.mul1.float()[side] if op.mul1 is not None else tot
+        if op.mul1 is not None and op.mul1_sqrt_scale is not None:      # gain recomputed from the producer's ReLU output
+            gsc = (op.mul1.float().view(-1, op.mul1.shape[-1])[side] * op.mul1_sqrt_scale.float().view(-1)[side][:, None]).sqrt()
+            v = tot * gsc
+        else:
+            v = tot * op.mul1.float().view(-1, op.mul1.shape[-1])[side] if op.mul1 is not None else tot
         y2 = op.y.view(-1, op.y.shape[-1])
         if op.y_f32:
             y2[rows] = v
@@ -226,7 +232,9 @@ def run_avgpool_bwd_mul(op: O.AvgPoolBwdMulOp) -> None:
     y = torch.nn.functional.avg_pool2d(x, op.k, stride=op.stride, padding=op.pad)
     (gx,) = torch.autograd.grad(y, x, gy)
     gx = gx.permute(0, 2, 3, 1)
-    if op.gain is not None:
+    if op.gain is not None and op.gain_sqrt_scale is not None:
+        gx = gx * (op.gain.float().view(nb, h, w, op.c) * op.gain_sqrt_scale.float().view(nb, h, w, 1)).sqrt()
+    elif op.gain is not None:
         gx = gx * op.gain.float().view(nb, h, w, op.c)
     _split_store(op.gx, gx.contiguous(), op.planes)
 

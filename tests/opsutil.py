@@ -31,8 +31,9 @@ def to_device(op, device, memo: Dict[int, Tensor] | None = None):
         if isinstance(v, Tensor):
             if id(v) not in memo:
                 base = v._base
-                if base is not None and not v.is_contiguous():
-                    # strided view (interior of a zero-bordered buffer): move the whole buffer, keep the view
+                if base is not None:
+                    # a view (interior of a zero-bordered buffer, or a reshaped alias of another operand): move the whole
+                    # buffer once and keep the view, so that aliasing between launch records survives the copy
                     if id(base) not in memo:
                         memo[id(base)] = base.detach().clone().to(device)
                     memo[id(v)] = memo[id(base)].as_strided(v.shape, v.stride(), v.storage_offset())

@@ -441,6 +441,44 @@ def test_launch_variants_are_bit_identical(bcosk_lib):
             assert torch.equal(a, b), cfg
 
 
+@pytest.mark.parametrize("case", [("lazy_1x1", 1, False, 64), ("lazy_3x3", 3, False, 64), ("lazy_3x3_flat", 3, True, 64),
+                                  ("lazy_1x1_n256", 1, False, 256)], ids=lambda c: c[0])
+def test_gain_recomputed_from_relu_output(bcosk_lib, case):
+    """gains that are not stored: forward writes 1/||patch|| (inv_norm_out), the consumer's explain epilogue multiplies by
+    sqrt(y * inv) read from the producer's ReLU output (mul1_sqrt_scale)"""
+    name, k, flat, cout = case
+    g = torch.Generator().manual_seed(hash(name) % 2**31)
+    nb, h, cin = 3, 12, 64
+    plan = _mini_plan(nb, 1)
+    plan.recompute_gain = True
+    x = _rand_act(g, nb, h, h, cin, 1)
+    wa = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    ya, ra = plan._conv_fwd("a", x, wa, 1, k // 2, k // 2, bn=None, relu=True, flat=flat)
+    assert ra.gain is None and ra.gain_y is not None and ra.gain_inv is not None
+    assert plan.fwd_ops[-1].gain is None and (flat or plan.fwd_ops[-1].inv_norm_out is not None)
+    wb = torch.randn(64, cout, 3, 3, generator=g) / math.sqrt(cout * 9)
+    yb, rb = plan._conv_fwd("b", ya, wb, 1, 1, 1, bn=None, relu=False)
+    plan._alloc_ghat(rb)
+    plan._alloc_ghat(ra)
+    rb.ghat.copy_(torch.randn(nb, h, h, 64, generator=g).to(plan.dt))
+    m1, m1s = plan._gain_of(ra)
+    plan._dgrad(rb, y=ra.ghat, mul1=m1, mul1_sqrt_scale=m1s)
+    assert plan.bwd_ops[-1].mul1_sqrt_scale is not None
+    print(name, _run_and_compare(plan.fwd_ops + plan.bwd_ops))
+    # and the same gradient with the gain stored the ordinary way
+    plan2 = _mini_plan(nb, 1)
+    plan2.recompute_gain = False
+    ya2, ra2 = plan2._conv_fwd("a", x, wa, 1, k // 2, k // 2, bn=None, relu=True, flat=flat)
+    yb2, rb2 = plan2._conv_fwd("b", ya2, wb, 1, 1, 1, bn=None, relu=False)
+    plan2._alloc_ghat(rb2)
+    plan2._alloc_ghat(ra2)
+    rb2.ghat.copy_(rb.ghat)
+    plan2._dgrad(rb2, y=ra2.ghat, mul1=ra2.gain)
+    E.run(plan2.fwd_ops + plan2.bwd_ops)
+    a, b = ra.ghat.float(), ra2.ghat.float()
+    assert (a - b).abs().max() <= 2e-2 * b.abs().max()
+
+
 def test_elementwise_kernels(bcosk_lib):
     g = torch.Generator().manual_seed(5)
     nb, S = 3, 32
@@ -469,6 +507,9 @@ def test_elementwise_kernels(bcosk_lib):
             ops.append(O.InputPrepOp("prep_padded", x6, mean, istd, outp, 32, 1, 1, torch.zeros(1, nb * S * S)))
             gxp = plan._padded(nb, 16, 16, 64, 1, 2)
             ops.append(O.AvgPoolBwdMulOp("poolbwd_padded", gy, 64, 1, 3, 2, 1, gain, gxp, 1))
+            # the multiplier recomputed as sqrt(y * scale) from a ReLU output
+            ops.append(O.AvgPoolBwdMulOp("poolbwd_lazy_gain", gy, 64, 1, 3, 2, 1, gain, torch.zeros(nb, 16, 16, 64, dtype=dt), 1,
+                                         torch.rand(nb * 256, generator=g) + 0.5))
         fc = torch.randn(nb * 49, 1000, generator=g)
         logits = torch.zeros(nb, 1000)
         pred = torch.zeros(nb, dtype=torch.int32)
