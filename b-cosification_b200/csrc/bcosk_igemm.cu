@@ -32,6 +32,10 @@ constexpr int NUM_THREADS = 192;
 #define BCOSK_BN128_STAGES 2
 #define BCOSK_BN128_BLOCKS 3
 #endif
+#ifndef BCOSK_BN256_STAGES
+#define BCOSK_BN256_STAGES 4   // 256-wide per-tile kernel (experiment knobs; the plans do not pick 256-wide tiles)
+#define BCOSK_BN256_BLOCKS 1
+#endif
 #ifndef BCOSK_LIGHT2_BLOCKS
 #define BCOSK_LIGHT2_BLOCKS 4   // CTAs per SM of the single-stage forward variant (5 spills ~200 B per thread)
 #endif
@@ -42,8 +46,8 @@ constexpr int NUM_THREADS = 192;
 // afterwards the y tile; slot 1 holds the residual tile and the gain tile is staged over it - every thread reads its own
 // residual words before it writes the same words of the gain tile, so the alias is safe.
 template <int BN, bool HP = false, int LIGHT = 0> struct TileCfg {
-  static constexpr int kStages = LIGHT == 2 ? 2 : (LIGHT ? 3 : ((BN == 128) ? BCOSK_BN128_STAGES : 4));   // pipeline slots; the last may hold the input tile
-  static constexpr int kMinBlocks = LIGHT == 2 ? BCOSK_LIGHT2_BLOCKS : (LIGHT ? 3 : (BN == 128 ? BCOSK_BN128_BLOCKS : ((BN < 128) ? 2 : 1)));
+  static constexpr int kStages = LIGHT == 2 ? 2 : (LIGHT ? 3 : ((BN == 128) ? BCOSK_BN128_STAGES : (BN == 256 ? BCOSK_BN256_STAGES : 4)));   // pipeline slots; the last may hold the input tile
+  static constexpr int kMinBlocks = LIGHT == 2 ? BCOSK_LIGHT2_BLOCKS : (LIGHT ? 3 : (BN == 128 ? BCOSK_BN128_BLOCKS : ((BN < 128) ? 2 : BCOSK_BN256_BLOCKS)));
   static constexpr int kBStageBytes = BN * STAGE_K * 2;
   static constexpr int kSlotBytes = A_STAGE_BYTES + kBStageBytes;   // A stage followed by its B stage
   static constexpr int kTileBytes = BM * BN * 2;                    // one 16-bit epilogue tile (BN/64 boxes of 16 KB)
