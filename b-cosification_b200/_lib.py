@@ -190,6 +190,16 @@ def explanation_rgba(grad6, x, smooth, percentile, tmp, out) -> None:
           "bcosk_explanation_rgba")
 
 
+def maxout_bcos_fwd(lin, inv_norm, rows, o, m, scale_mode, b_exp, y, gain, amax) -> None:
+    check(load().bcosk_maxout_bcos_fwd(_p(lin), _p(inv_norm), C.c_int64(rows), o, m, scale_mode, C.c_float(b_exp), _p(y), _p(gain),
+                                       _p(amax), _stream()), "bcosk_maxout_bcos_fwd")
+
+
+def maxout_scatter(src, amax, rows, o, m, planes, dtype, dst) -> None:
+    check(load().bcosk_maxout_scatter(_p(src), _p(amax), C.c_int64(rows), o, m, planes, dtype, _p(dst), _stream()),
+          "bcosk_maxout_scatter")
+
+
 def gap_logits(fc, nb, npix, ncls, inv_temp, bias, logits, pred) -> None:
     check(load().bcosk_gap_logits(_p(fc), nb, npix, ncls, C.c_float(inv_temp), C.c_float(bias), _p(logits), _p(pred),
                                   _stream()), "bcosk_gap_logits")

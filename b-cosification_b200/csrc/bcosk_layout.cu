@@ -186,3 +186,78 @@ extern "C" int bcosk_channel_stats_nchw(const float* x, int32_t nb, int32_t c, i
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// MaxOut for the module-level path (bcosconv2d.py:166-170, bcoslinear.py:107-110): the linear map has O*M units,
+// unit c = o*M + m; the output keeps the largest of the M candidates (first one on ties, like torch.max) and the
+// B-cos scale is computed from it.  The explanation gradient reaches only that unit.
+// ------------------------------------------------------------------------------------------------
+namespace bcosk {
+
+__global__ void maxout_bcos_fwd_kernel(const float* __restrict__ lin, const float* __restrict__ inv_norm, long long rows, int o,
+                                       int m, int scale_mode, float b_exp, float* __restrict__ y, float* __restrict__ gain,
+                                       uint8_t* __restrict__ amax) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * o) return;
+  const long long r = idx / o;
+  const float* src = lin + idx * m;            // (r * o + oo) * m
+  float best = __ldg(src);
+  int bi = 0;
+  for (int k = 1; k < m; ++k) {
+    const float v = __ldg(src + k);
+    if (v > best) { best = v; bi = k; }
+  }
+  float s = 1.f;
+  if (scale_mode == BCOSK_SCALE_B2) s = fabsf(best) * __ldg(inv_norm + r);
+  else if (scale_mode == BCOSK_SCALE_POW) s = powf(fabsf(best) * __ldg(inv_norm + r) + 1e-6f, b_exp - 1.f);
+  y[idx] = best * s;
+  if (gain != nullptr) gain[idx] = s;
+  if (amax != nullptr) amax[idx] = (uint8_t)bi;
+}
+
+// dst[r, pl, oo*m + k] = (k == amax[r, oo]) ? src[r, pl, oo] : 0      (16-bit planes)
+template <typename T>
+__global__ void maxout_scatter_kernel(const T* __restrict__ src, const uint8_t* __restrict__ amax, long long rows, int o,
+                                      int m, int planes, T* __restrict__ dst) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = rows * planes * o * m;
+  if (idx >= total) return;
+  const int om = o * m;
+  const int c = (int)(idx % om);
+  const long long rp = idx / om;               // r * planes + pl
+  const long long r = rp / planes;
+  const int oo = c / m, k = c - oo * m;
+  dst[idx] = (k == (int)__ldg(amax + r * o + oo)) ? src[rp * o + oo] : T(0.f);
+}
+
+}  // namespace bcosk
+
+extern "C" int bcosk_maxout_bcos_fwd(const float* lin, const float* inv_norm, int64_t rows, int32_t o, int32_t m,
+                                     int32_t scale_mode, float b_exp, float* y, float* gain, uint8_t* amax, void* stream) {
+  using namespace bcosk;
+  if (!lin || !y || rows < 1 || o < 1 || m < 1 || m > 255) return set_error(BCOSK_EINVAL, "maxout_bcos_fwd: bad argument");
+  if (scale_mode != BCOSK_SCALE_NONE && !inv_norm) return set_error(BCOSK_EINVAL, "maxout_bcos_fwd: inv_norm required");
+  const long long n = rows * o;
+  maxout_bcos_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      lin, inv_norm, rows, o, m, scale_mode, b_exp, y, gain, amax);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_maxout_scatter(const void* src, const uint8_t* amax, int64_t rows, int32_t o, int32_t m, int32_t planes,
+                                    int32_t dtype, void* dst, void* stream) {
+  using namespace bcosk;
+  if (!src || !amax || !dst || rows < 1 || o < 1 || m < 1 || planes < 1) return set_error(BCOSK_EINVAL, "maxout_scatter: bad argument");
+  const long long n = rows * planes * o * m;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == BCOSK_DTYPE_BF16)
+    maxout_scatter_kernel<__nv_bfloat16><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(src), amax, rows, o, m, planes, reinterpret_cast<__nv_bfloat16*>(dst));
+  else if (dtype == BCOSK_DTYPE_F16)
+    maxout_scatter_kernel<__half><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const __half*>(src), amax, rows, o, m, planes, reinterpret_cast<__half*>(dst));
+  else
+    return set_error(BCOSK_EINVAL, "maxout_scatter: dtype");
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}

@@ -104,13 +104,15 @@ class BcosConv2d(DetachableModule):
         return self.forward_impl(in_tensor)
 
     def forward_impl(self, in_tensor: Tensor) -> Tensor:
-        if self.max_out > 1 or self.groups != 1 or any(d > 1 for d in self.dilation) or self.padding_mode != "zeros":
-            raise NotImplementedError("bcos_b200: max_out > 1, groups > 1, dilation > 1 and non-zero padding modes are not "
+        if self.groups != 1 or any(d > 1 for d in self.dilation) or self.padding_mode != "zeros":
+            raise NotImplementedError("bcos_b200: groups > 1, dilation > 1 and non-zero padding modes are not "
                                       "built (no registered B-cosification config uses them)")
+        if self.max_out > 1 and self.out_channels % 8 != 0:
+            raise NotImplementedError("bcos_b200: MaxOut needs out_channels % 8 == 0")
         b = float(self.b.detach()) if isinstance(self.b, torch.Tensor) else float(self.b)
         lin = self.linear
         return R.bcos_map(in_tensor, self._cache, lin.weight, getattr(lin, "bias", None), self._effective_weight,
-                          _single(self.stride), _single(self.padding), b, self.detach)
+                          _single(self.stride), _single(self.padding), b, self.detach, max_out=self.max_out)
 
     def calc_patch_norms(self, in_tensor: Tensor) -> Tensor:
         """||patch|| per output position, [N,1,Ho,Wo] (bcosconv2d.py:196-231) through bcosk_patch_inv_norm."""

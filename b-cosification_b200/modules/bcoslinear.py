@@ -56,14 +56,14 @@ class BcosLinear(DetachableModule):
         return self.linear.effective_weight()[:, :, None, None]
 
     def forward(self, in_tensor: Tensor) -> Tensor:
-        if self.max_out > 1:
-            raise NotImplementedError("bcos_b200: max_out > 1 is not built (no registered B-cosification config uses it)")
+        if self.max_out > 1 and self.out_features % 8 != 0:
+            raise NotImplementedError("bcos_b200: MaxOut needs out_features % 8 == 0")
         b = float(self.b.detach()) if isinstance(self.b, torch.Tensor) else float(self.b)
         lead = in_tensor.shape[:-1]
         x = in_tensor.reshape(-1, self.in_features, 1, 1)
         lin = self.linear
         y = R.bcos_map(x, self._cache, lin.weight, getattr(lin, "bias", None), self._effective_weight, 1, 0, b, self.detach,
-                       linear_eps=True)
+                       linear_eps=True, max_out=self.max_out)
         return y.reshape(*lead, self.out_features)
 
     def extra_repr(self) -> str:

@@ -265,6 +265,16 @@ int bcosk_explanation_rgba(const float* grad6, const float* x, int32_t nb, int32
 int bcosk_explanation_rgba_u8(const float* grad6, const uint8_t* x, int32_t nb, int32_t h, int32_t w, int32_t smooth,
                               float percentile, float* tmp, float* out, void* stream);
 
+/* MaxOut for the module-level path (bcosconv2d.py:166-170 `lin.unflatten(1, (O, M)).max(2)`, bcoslinear.py:107-110):
+ * lin [rows, o*m] fp32 (unit c = oo*m + k) -> y [rows, o] = best * scale(best, inv_norm[row]) with the launch's scale mode
+ * and B; gain [rows, o] = that scale (optional), amax [rows, o] = index of the kept unit (optional, first on ties). */
+int bcosk_maxout_bcos_fwd(const float* lin, const float* inv_norm, int64_t rows, int32_t o, int32_t m, int32_t scale_mode,
+                          float b_exp, float* y, float* gain, uint8_t* amax, void* stream);
+/* Explanation backward of MaxOut on 16-bit planes: dst [rows, planes*o*m] gets src [rows, planes*o] at the kept unit of
+ * every group and zeros elsewhere (autograd of torch.max). */
+int bcosk_maxout_scatter(const void* src, const uint8_t* amax, int64_t rows, int32_t o, int32_t m, int32_t planes,
+                         int32_t dtype, void* dst, void* stream);
+
 /* Generic element-wise helpers for the module-level (un-fused) path. */
 /* batch_norm_uncentered_2d eval (batchnorm_uncentered.py:49-58) / ReLU on NHWC 16-bit: y = relu?(x*alpha[c]+beta[c]) */
 int bcosk_channel_affine(const void* x, int64_t rows, int32_t c, const float* alpha, const float* beta, int32_t relu,

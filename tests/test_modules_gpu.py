@@ -29,7 +29,7 @@ def kat(golden_dir):
 
 
 CONV = ["conv_bcosify_3x3", "conv_bcosify_3x3_s2", "conv_bcosify_1x1", "conv_bcosify_1x1_s2", "conv_bcosify_7x7_s2",
-        "conv_bcos_3x3_normed", "conv_bcos_b1p5", "conv_bcos_b1"]
+        "conv_bcos_3x3_normed", "conv_bcos_b1p5", "conv_bcos_b1", "conv_bcos_b2p5_mo2", "conv_bcos_b2_mo3"]
 
 
 @pytest.mark.parametrize("name", CONV)
@@ -53,18 +53,19 @@ def test_conv_modules_match_reference(bcosk_lib, kat, name):
         assert _rel(mod.calc_patch_norms(x), _t(kat[name + ".norm"])[:, :1]) < 1e-5
 
 
-@pytest.mark.parametrize("name", ["lin_bcosify", "lin_bcos_normed"])
+@pytest.mark.parametrize("name", ["lin_bcosify", "lin_bcos_normed", "lin_bcos_b1p5_mo2"])
 def test_linear_modules_match_reference(bcosk_lib, kat, name):
     fin, fout, b, mo, normed = kat[name + ".meta"].tolist()
     cls = M.BcosLinear if normed else M.BcosifyLinear
     mod = cls(int(fin), int(fout), b=b, max_out=int(mo)).cuda()
     mod.linear.weight.data = _t(kat[name + ".w"])
     x = _t(kat[name + ".x"])
-    assert _rel(mod(x), _t(kat[name + ".y"])) < 2e-5
+    tol = 2e-5 if b in (1, 2) else 2e-4          # general B uses powf
+    assert _rel(mod(x), _t(kat[name + ".y"])) < tol
     mod.set_explanation_mode(True)
     xg = x.clone().requires_grad_(True)
     (gx,) = torch.autograd.grad((mod(xg) * _t(kat[name + ".seed"])).sum(), [xg])
-    assert _rel(gx, _t(kat[name + ".gx"])) < 2e-5
+    assert _rel(gx, _t(kat[name + ".gx"])) < tol
 
 
 def test_bias_before_scale(bcosk_lib):
