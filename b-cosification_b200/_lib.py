@@ -190,6 +190,14 @@ def explanation_rgba(grad6, x, smooth, percentile, tmp, out) -> None:
           "bcosk_explanation_rgba")
 
 
+def localisation_scores(attr, smooth, cell, negate, tmp, out) -> None:
+    nt, c, h, w = attr.shape
+    regions = (h // cell) * (w // cell)
+    assert tmp.numel() >= 2 * nt * h * w + nt * regions and tuple(out.shape) == (nt, regions)
+    check(load().bcosk_localisation_scores(_p(attr), nt, c, h, w, int(smooth), int(cell), int(bool(negate)), _p(tmp), _p(out),
+                                           _stream()), "bcosk_localisation_scores")
+
+
 def maxout_bcos_fwd(lin, inv_norm, rows, o, m, scale_mode, b_exp, y, gain, amax) -> None:
     check(load().bcosk_maxout_bcos_fwd(_p(lin), _p(inv_norm), C.c_int64(rows), o, m, scale_mode, C.c_float(b_exp), _p(y), _p(gain),
                                        _p(amax), _stream()), "bcosk_maxout_bcos_fwd")
@@ -257,6 +265,26 @@ def layernorm_fwd(x, rows, d, w, b, eps, y, rstd) -> None:
 def layernorm_explain_bwd(gy, rows, d, w, rstd, gx) -> None:
     check(load().bcosk_layernorm_explain_bwd(_p(gy), C.c_int64(rows), d, _p(w), _p(rstd), _p(gx), _stream()),
           "bcosk_layernorm_explain_bwd")
+
+
+def groupnorm_fwd(x, nb, c, hw, groups, w, b, eps, centred, y, rstd) -> None:
+    check(load().bcosk_groupnorm_fwd(_p(x), nb, c, C.c_int64(hw), groups, _p(w), _p(b), C.c_float(eps), int(centred), _p(y),
+                                     _p(rstd), _stream()), "bcosk_groupnorm_fwd")
+
+
+def groupnorm_explain_bwd(gy, nb, c, hw, groups, w, rstd, centred, gx) -> None:
+    check(load().bcosk_groupnorm_explain_bwd(_p(gy), nb, c, C.c_int64(hw), groups, _p(w), _p(rstd), int(centred), _p(gx),
+                                             _stream()), "bcosk_groupnorm_explain_bwd")
+
+
+def positionnorm_fwd(x, nb, c, hw, w, b, eps, centred, y, rstd) -> None:
+    check(load().bcosk_positionnorm_fwd(_p(x), nb, c, C.c_int64(hw), _p(w), _p(b), C.c_float(eps), int(centred), _p(y),
+                                        _p(rstd), _stream()), "bcosk_positionnorm_fwd")
+
+
+def positionnorm_explain_bwd(gy, nb, c, hw, w, rstd, centred, gx) -> None:
+    check(load().bcosk_positionnorm_explain_bwd(_p(gy), nb, c, C.c_int64(hw), _p(w), _p(rstd), int(centred), _p(gx),
+                                                _stream()), "bcosk_positionnorm_explain_bwd")
 
 
 def gelu_gate(x, g, n, y) -> None:

@@ -27,7 +27,9 @@ def install_as_bcos() -> None:
           gradient_to_image=explain.gradient_to_image)
     alias("bcos.modules", **pub)
     alias("bcos.modules.bcosattnpool", BcosAttentionPool2d=modules.BcosAttentionPool2d)
-    alias("bcos.modules.norms.centered_norms", DetachableLayerNorm=modules.DetachableLayerNorm)
+    alias("bcos.modules.norms.centered_norms", DetachableLayerNorm=modules.DetachableLayerNorm,
+          DetachableGroupNorm2d=norms.DetachableGroupNorm2d, DetachableGNInstanceNorm2d=norms.DetachableGNInstanceNorm2d,
+          DetachableGNLayerNorm2d=norms.DetachableGNLayerNorm2d, DetachablePositionNorm2d=norms.DetachablePositionNorm2d)
     alias("bcos.modules.common", DetachableModule=common.DetachableModule, BcosSequential=common.BcosSequential)
     alias("bcos.modules.bcosconv2d", BcosConv2d=bcosconv2d.BcosConv2d, NormedConv2d=bcosconv2d.NormedConv2d,
           BcosConv2dWithScale=bcosconv2d.BcosConv2dWithScale)
@@ -35,6 +37,12 @@ def install_as_bcos() -> None:
     alias("bcos.modules.bcoslinear", BcosLinear=bcoslinear.BcosLinear, NormedLinear=bcoslinear.NormedLinear)
     alias("bcos.modules.bcosifylinear", BcosifyLinear=bcoslinear.BcosifyLinear)
     alias("bcos.modules.logitlayer", LogitLayer=logitlayer.LogitLayer)
-    alias("bcos.modules.norms", BatchNormUncentered2d=norms.BatchNormUncentered2d, NoBias=norms.NoBias, Unaffine=norms.Unaffine)
-    alias("bcos.modules.norms.uncentered_norms", BatchNormUncentered2d=norms.BatchNormUncentered2d)
+    unc = {k: getattr(norms, k) for k in ("BatchNormUncentered2d", "GroupNormUncentered2d", "GNInstanceNormUncentered2d",
+                                          "GNLayerNormUncentered2d", "PositionNormUncentered2d", "AllNormUncentered2d",
+                                          "group_norm_uncentered", "batch_norm_uncentered_2d")}
+    cen = {k: getattr(norms, k) for k in ("DetachableGroupNorm2d", "DetachableGNInstanceNorm2d", "DetachableGNLayerNorm2d",
+                                          "DetachablePositionNorm2d")}
+    alias("bcos.modules.norms", NoBias=norms.NoBias, Unaffine=norms.Unaffine, DetachableLayerNorm=modules.DetachableLayerNorm,
+          **unc, **cen)
+    alias("bcos.modules.norms.uncentered_norms", **unc)
     alias("bcos.modules.norms.utils", NoBias=norms.NoBias, Unaffine=norms.Unaffine)

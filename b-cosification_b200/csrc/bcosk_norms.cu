@@ -1,0 +1,242 @@
+// bcosk_norms.cu -- group / position normalisation of NCHW fp32 tensors with detachable statistics (module-level path).
+// Reference: bcos/modules/norms/uncentered_norms/groupnorm_uncentered.py:21-61 (group_norm_uncentered),
+// bcos/modules/norms/centered_norms.py:93-138 (DetachableGroupNorm2d), :251-297 (DetachablePositionNorm2d),
+// bcos/modules/norms/uncentered_norms/posnorm_uncentered.py:39-58 (PositionNormUncentered2d).
+// All four divide by sqrt(var + eps) with var the CENTRED biased variance; the "centred" ones also subtract the mean.
+// In explanation mode the variance is a constant (detached), the mean stays in the graph.
+// Bandwidth kernels: the statistics passes re-read the group / pixel column from L2, 16-byte accesses where the
+// geometry allows, consecutive lanes on consecutive addresses.
+#include "../../include/bcosk.h"
+#include "bcosk_common.cuh"
+#include "bcosk_host.h"
+
+namespace bcosk {
+
+constexpr int GN_THREADS = 512;
+
+// block-wide sum, result broadcast to every thread; `red` holds one float per warp
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();                       // protect `red` from the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = lane < nw ? red[lane] : 0.f;
+  return warp_sum(t);
+}
+
+// ---------------------------------------------------------------- group norm: one CTA per (image, group)
+// The group is the contiguous run x[(n*C + g*Cg)*HW ... + Cg*HW).  VEC = 4 needs HW % 4 == 0 (then a float4 never
+// straddles two channels and every run start is 16-byte aligned).
+template <int VEC>
+__global__ void __launch_bounds__(GN_THREADS)
+groupnorm_fwd_kernel(const float* __restrict__ x, int c, int hw, int groups, const float* __restrict__ w,
+                     const float* __restrict__ b, float eps, int centred, float* __restrict__ y, float* __restrict__ rstd) {
+  __shared__ float red[GN_THREADS / 32];
+  const int cg = c / groups;
+  const int g = blockIdx.x % groups;
+  const long long len = (long long)cg * hw;
+  const float* src = x + (long long)blockIdx.x * len;
+  float* dst = y + (long long)blockIdx.x * len;
+  const long long nv = len / VEC;
+  float s = 0.f;
+  if (VEC == 4) {
+    for (long long i = threadIdx.x; i < nv; i += GN_THREADS) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+  } else {
+    for (long long i = threadIdx.x; i < nv; i += GN_THREADS) s += __ldg(src + i);
+  }
+  const float mean = block_sum(s, red) / (float)len;
+  float q = 0.f;
+  if (VEC == 4) {
+    for (long long i = threadIdx.x; i < nv; i += GN_THREADS) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+      const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+      q = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, q))));
+    }
+  } else {
+    for (long long i = threadIdx.x; i < nv; i += GN_THREADS) {
+      const float a = __ldg(src + i) - mean;
+      q = fmaf(a, a, q);
+    }
+  }
+  const float var = block_sum(q, red) / (float)len;     // biased, like var(unbiased=False)
+  const float r = 1.0f / sqrtf(var + eps);
+  const float sub = centred ? mean : 0.f;
+  if (rstd != nullptr && threadIdx.x == 0) rstd[blockIdx.x] = r;
+  if (VEC == 4) {
+    const int hv = hw / 4;
+    for (long long i = threadIdx.x; i < nv; i += GN_THREADS) {
+      const int ch = g * cg + (int)(i / hv);
+      const float ww = (w ? __ldg(w + ch) : 1.f) * r, bb = b ? __ldg(b + ch) : 0.f;
+      float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+      v.x = fmaf(v.x - sub, ww, bb); v.y = fmaf(v.y - sub, ww, bb);
+      v.z = fmaf(v.z - sub, ww, bb); v.w = fmaf(v.w - sub, ww, bb);
+      reinterpret_cast<float4*>(dst)[i] = v;
+    }
+  } else {
+    for (long long i = threadIdx.x; i < nv; i += GN_THREADS) {
+      const int ch = g * cg + (int)(i / hw);
+      const float ww = (w ? __ldg(w + ch) : 1.f) * r, bb = b ? __ldg(b + ch) : 0.f;
+      dst[i] = fmaf(__ldg(src + i) - sub, ww, bb);
+    }
+  }
+}
+
+// explanation backward (variance detached): uncentred gx = w*gy*rstd ; centred gx = (w*gy - mean_group(w*gy)) * rstd
+template <int VEC>
+__global__ void __launch_bounds__(GN_THREADS)
+groupnorm_explain_bwd_kernel(const float* __restrict__ gy, int c, int hw, int groups, const float* __restrict__ w,
+                             const float* __restrict__ rstd, int centred, float* __restrict__ gx) {
+  __shared__ float red[GN_THREADS / 32];
+  const int cg = c / groups;
+  const int g = blockIdx.x % groups;
+  const long long len = (long long)cg * hw;
+  const float* src = gy + (long long)blockIdx.x * len;
+  float* dst = gx + (long long)blockIdx.x * len;
+  const long long nv = len / VEC;
+  const int hv = hw / VEC;
+  float m = 0.f;
+  if (centred) {
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < nv; i += GN_THREADS) {
+      const float ww = w ? __ldg(w + g * cg + (int)(i / hv)) : 1.f;
+      if (VEC == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+        s = fmaf((v.x + v.y) + (v.z + v.w), ww, s);
+      } else {
+        s = fmaf(__ldg(src + i), ww, s);
+      }
+    }
+    m = block_sum(s, red) / (float)len;
+  }
+  const float r = __ldg(rstd + blockIdx.x);
+  for (long long i = threadIdx.x; i < nv; i += GN_THREADS) {
+    const float ww = w ? __ldg(w + g * cg + (int)(i / hv)) : 1.f;
+    if (VEC == 4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+      v.x = (v.x * ww - m) * r; v.y = (v.y * ww - m) * r; v.z = (v.z * ww - m) * r; v.w = (v.w * ww - m) * r;
+      reinterpret_cast<float4*>(dst)[i] = v;
+    } else {
+      dst[i] = (__ldg(src + i) * ww - m) * r;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- position norm: statistics over C per pixel
+// CTA = 32 pixels (threadIdx.x, consecutive addresses) x PN_SLICES channel slices (threadIdx.y); grid (ceil(HW/32), N).
+constexpr int PN_SLICES = 16;
+
+__device__ __forceinline__ float slice_sum(float v, float (*red)[33]) {
+  __syncthreads();
+  red[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < PN_SLICES; ++k) t += red[k][threadIdx.x];
+  return t;
+}
+
+// backward == 0: y = w[c]*(x - centred*mean)*rstd + b[c], rstd[n*HW + p] saved
+// backward == 1: x is the incoming gradient, y = (w[c]*x - centred*mean_c(w*x)) * rstd[n*HW + p]  (variance detached)
+template <bool BWD>
+__global__ void __launch_bounds__(32 * PN_SLICES)
+positionnorm_kernel(const float* __restrict__ x, int c, int hw, const float* __restrict__ w, const float* __restrict__ b,
+                    float eps, int centred, float* __restrict__ y, float* __restrict__ rstd) {
+  __shared__ float red[PN_SLICES][33];
+  const int p = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = p < hw;
+  const long long base = (long long)blockIdx.y * c * hw + p;
+  const float* src = x + base;
+  float* dst = y + base;
+  float s = 0.f;
+  if (ok && (!BWD || centred))
+    for (int ch = threadIdx.y; ch < c; ch += PN_SLICES) {
+      const float v = __ldg(src + (long long)ch * hw);
+      s += BWD ? v * (w ? __ldg(w + ch) : 1.f) : v;
+    }
+  float mean = 0.f, r;
+  if (!BWD || centred) mean = slice_sum(s, red) / (float)c;
+  if (!BWD) {
+    float q = 0.f;
+    if (ok)
+      for (int ch = threadIdx.y; ch < c; ch += PN_SLICES) {
+        const float a = __ldg(src + (long long)ch * hw) - mean;
+        q = fmaf(a, a, q);
+      }
+    const float var = slice_sum(q, red) / (float)c;
+    r = 1.0f / sqrtf(var + eps);
+    if (ok && rstd != nullptr && threadIdx.y == 0) rstd[(long long)blockIdx.y * hw + p] = r;
+  } else {
+    r = ok ? __ldg(rstd + (long long)blockIdx.y * hw + p) : 0.f;
+  }
+  if (!ok) return;
+  const float sub = centred ? mean : 0.f;
+  for (int ch = threadIdx.y; ch < c; ch += PN_SLICES) {
+    const float v = __ldg(src + (long long)ch * hw);
+    const float ww = w ? __ldg(w + ch) : 1.f;
+    if (BWD) dst[(long long)ch * hw] = (v * ww - sub) * r;
+    else dst[(long long)ch * hw] = fmaf(v - sub, ww * r, b ? __ldg(b + ch) : 0.f);
+  }
+}
+
+}  // namespace bcosk
+
+using namespace bcosk;
+static inline cudaStream_t S4(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int bcosk_groupnorm_fwd(const float* x, int32_t nb, int32_t c, int64_t hw, int32_t groups, const float* w,
+                                   const float* b, float eps, int32_t centred, float* y, float* rstd, void* stream) {
+  if (!x || !y || nb < 0 || c < 1 || hw < 1 || groups < 1) return set_error(BCOSK_EINVAL, "groupnorm_fwd: bad argument");
+  if (c % groups != 0) return set_error(BCOSK_EINVAL, "groupnorm_fwd: channels %d not divisible by groups %d", c, groups);
+  if (hw > 0x7fffffffLL || (int64_t)nb * groups > 0x7fffffffLL) return set_error(BCOSK_EUNSUPPORTED, "groupnorm_fwd: too large");
+  if (nb == 0) return BCOSK_OK;
+  const unsigned grid = (unsigned)(nb * groups);
+  if (hw % 4 == 0 && aligned16(x) && aligned16(y))
+    groupnorm_fwd_kernel<4><<<grid, GN_THREADS, 0, S4(stream)>>>(x, c, (int)hw, groups, w, b, eps, centred, y, rstd);
+  else
+    groupnorm_fwd_kernel<1><<<grid, GN_THREADS, 0, S4(stream)>>>(x, c, (int)hw, groups, w, b, eps, centred, y, rstd);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_groupnorm_explain_bwd(const float* gy, int32_t nb, int32_t c, int64_t hw, int32_t groups, const float* w,
+                                           const float* rstd, int32_t centred, float* gx, void* stream) {
+  if (!gy || !gx || !rstd || nb < 0 || c < 1 || hw < 1 || groups < 1) return set_error(BCOSK_EINVAL, "groupnorm_explain_bwd: bad argument");
+  if (c % groups != 0) return set_error(BCOSK_EINVAL, "groupnorm_explain_bwd: channels %d not divisible by groups %d", c, groups);
+  if (hw > 0x7fffffffLL || (int64_t)nb * groups > 0x7fffffffLL) return set_error(BCOSK_EUNSUPPORTED, "groupnorm_explain_bwd: too large");
+  if (nb == 0) return BCOSK_OK;
+  const unsigned grid = (unsigned)(nb * groups);
+  if (hw % 4 == 0 && aligned16(gy) && aligned16(gx))
+    groupnorm_explain_bwd_kernel<4><<<grid, GN_THREADS, 0, S4(stream)>>>(gy, c, (int)hw, groups, w, rstd, centred, gx);
+  else
+    groupnorm_explain_bwd_kernel<1><<<grid, GN_THREADS, 0, S4(stream)>>>(gy, c, (int)hw, groups, w, rstd, centred, gx);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_positionnorm_fwd(const float* x, int32_t nb, int32_t c, int64_t hw, const float* w, const float* b, float eps,
+                                      int32_t centred, float* y, float* rstd, void* stream) {
+  if (!x || !y || nb < 0 || c < 1 || hw < 1) return set_error(BCOSK_EINVAL, "positionnorm_fwd: bad argument");
+  if (hw > 0x7fffffffLL || nb > 65535) return set_error(BCOSK_EUNSUPPORTED, "positionnorm_fwd: too large");
+  if (nb == 0) return BCOSK_OK;
+  dim3 grid((unsigned)((hw + 31) / 32), (unsigned)nb), block(32, PN_SLICES);
+  positionnorm_kernel<false><<<grid, block, 0, S4(stream)>>>(x, c, (int)hw, w, b, eps, centred, y, rstd);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_positionnorm_explain_bwd(const float* gy, int32_t nb, int32_t c, int64_t hw, const float* w, const float* rstd,
+                                              int32_t centred, float* gx, void* stream) {
+  if (!gy || !gx || !rstd || nb < 0 || c < 1 || hw < 1) return set_error(BCOSK_EINVAL, "positionnorm_explain_bwd: bad argument");
+  if (hw > 0x7fffffffLL || nb > 65535) return set_error(BCOSK_EUNSUPPORTED, "positionnorm_explain_bwd: too large");
+  if (nb == 0) return BCOSK_OK;
+  dim3 grid((unsigned)((hw + 31) / 32), (unsigned)nb), block(32, PN_SLICES);
+  positionnorm_kernel<true><<<grid, block, 0, S4(stream)>>>(gy, c, (int)hw, w, nullptr, 0.f, centred, gx,
+                                                            const_cast<float*>(rstd));
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}

@@ -140,6 +140,66 @@ static int rgba_impl(const float* grad6, const SRC* x, int nb, int h, int w, int
   return BCOSK_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Localisation ("grid pointing game") scores: interpretability/analyses/localisation.py:306-388.
+// attributions [T, C, H, W] (x * grad per target of a grid image) -> channel sum -> smooth x smooth box average (zero
+// padded, stride 1) -> optional sign flip -> clamp(min = 0) -> mean over each cell x cell region -> fraction of the
+// total per target, 0 where total * contrib <= 0.  Region r of the output is column-major (col * rows + row), the order
+// `.permute(0, 1, 3, 2).reshape(T, -1)` produces.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void channel_sum_kernel(const float* __restrict__ a, int c, int plane, float* __restrict__ out) {
+  const size_t img = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= plane) return;
+  const float* s = a + img * (size_t)c * plane + pix;
+  float acc = 0.f;
+  for (int ch = 0; ch < c; ++ch) acc += __ldg(s + (size_t)ch * plane);
+  out[img * plane + pix] = acc;
+}
+
+// one block per (region, target): mean over the region of max(sign * v, 0)
+__global__ void __launch_bounds__(256) region_mean_kernel(const float* __restrict__ a, int h, int w, int cell, int rows, int cols,
+                                                          float sign, float* __restrict__ raw) {
+  __shared__ float red[8];
+  const int r = blockIdx.x, t = blockIdx.y;
+  const int col = r / rows, row = r - col * rows;            // column-major region index
+  const float* s = a + (size_t)t * h * w + (size_t)row * cell * w + (size_t)col * cell;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < cell * cell; i += 256) {
+    const int y = i / cell, x = i - y * cell;
+    acc += fmaxf(sign * __ldg(s + (size_t)y * w + x), 0.f);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) raw[(size_t)t * rows * cols + r] = v / (float)(cell * cell);
+  }
+}
+
+// one warp per target: contribs / total where total * contrib > 0, else 0
+__global__ void region_fraction_kernel(const float* __restrict__ raw, int nt, int regions, float* __restrict__ out) {
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= nt) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int r = lane; r < regions; r += 32) s += __ldg(raw + (size_t)t * regions + r);
+  const float total = warp_sum(s);
+  for (int r = lane; r < regions; r += 32) {
+    const float v = __ldg(raw + (size_t)t * regions + r);
+    out[(size_t)t * regions + r] = total * v > 0.f ? v / total : 0.f;
+  }
+}
+
 }  // namespace bcosk
 
 using namespace bcosk;
@@ -152,4 +212,27 @@ extern "C" int bcosk_explanation_rgba(const float* grad6, const float* x, int32_
 extern "C" int bcosk_explanation_rgba_u8(const float* grad6, const uint8_t* x, int32_t nb, int32_t h, int32_t w,
                                          int32_t smooth, float percentile, float* tmp, float* out, void* stream) {
   return rgba_impl<uint8_t>(grad6, x, nb, h, w, smooth, percentile, tmp, out, stream);
+}
+
+extern "C" int bcosk_localisation_scores(const float* attr, int32_t nt, int32_t c, int32_t h, int32_t w, int32_t smooth,
+                                         int32_t cell, int32_t negate, float* tmp, float* out, void* stream) {
+  if (!attr || !tmp || !out) return set_error(BCOSK_EINVAL, "localisation_scores: null pointer");
+  if (nt < 1 || nt > 65535 || c < 1 || h < 1 || w < 1 || cell < 1 || cell > h || cell > w)
+    return set_error(BCOSK_EINVAL, "localisation_scores: bad shape");
+  if (smooth < 0 || (smooth > 0 && smooth % 2 == 0))
+    return set_error(BCOSK_EUNSUPPORTED, "localisation_scores: the smoothing window must be odd (0 = none)");
+  const int plane = h * w, rows = h / cell, cols = w / cell, regions = rows * cols;
+  float* a0 = tmp;
+  float* a1 = tmp + (size_t)nt * plane;
+  float* raw = tmp + 2 * (size_t)nt * plane;
+  const dim3 grid((plane + 255) / 256, nt);
+  channel_sum_kernel<<<grid, 256, 0, S2(stream)>>>(attr, c, plane, a0);
+  if (smooth > 1) {
+    box_filter_kernel<<<grid, 256, 0, S2(stream)>>>(a0, h, w, smooth / 2, 0, 1.0f, a1);
+    box_filter_kernel<<<grid, 256, 0, S2(stream)>>>(a1, h, w, smooth / 2, 1, 1.0f / (float)(smooth * smooth), a0);
+  }
+  region_mean_kernel<<<dim3(regions, nt), 256, 0, S2(stream)>>>(a0, h, w, cell, rows, cols, negate ? -1.f : 1.f, raw);
+  region_fraction_kernel<<<(nt + 7) / 8, 256, 0, S2(stream)>>>(raw, nt, regions, out);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
 }

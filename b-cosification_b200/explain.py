@@ -69,6 +69,25 @@ def gradient_to_image_batch(images: Tensor, linear_mappings: Tensor, smooth: int
     return out
 
 
+def localisation_scores(attributions: Tensor, cell: int, smooth: int = 0, neg: bool = False) -> Tensor:
+    """Per-target region fractions of a grid image on the device (interpretability/analyses/localisation.py:306-388):
+    attributions [T, C, H, W] (e.g. x * dynamic weights per target, `ResNetPlan.explain_targets`) -> [T, regions], regions
+    in the reference's column-major order; the localisation metric of the target in region t is `scores[t, t]`."""
+    from . import _lib as L
+    if not attributions.is_cuda:
+        raise L.BcoskError("localisation_scores runs on a CUDA device (sm_100a); move the tensors there")
+    L.require_device()
+    if attributions.dim() != 4:
+        raise ValueError("expected [T, C, H, W] attributions")
+    a = attributions.detach().float().contiguous()
+    nt, _, h, w = a.shape
+    regions = (h // cell) * (w // cell)
+    out = torch.empty(nt, regions, dtype=torch.float32, device=a.device)
+    tmp = torch.empty(2 * nt * h * w + nt * regions, dtype=torch.float32, device=a.device)
+    L.localisation_scores(a, smooth, cell, neg, tmp, out)
+    return out
+
+
 class BcosUtilMixin:
     """Explanation helpers for models made of B-cos modules (bcos/common.py:23-344)."""
 

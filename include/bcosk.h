@@ -265,6 +265,14 @@ int bcosk_explanation_rgba(const float* grad6, const float* x, int32_t nb, int32
 int bcosk_explanation_rgba_u8(const float* grad6, const uint8_t* x, int32_t nb, int32_t h, int32_t w, int32_t smooth,
                               float percentile, float* tmp, float* out, void* stream);
 
+/* Localisation scores of a grid image (interpretability/analyses/localisation.py:306-388): attr [nt, c, h, w] fp32 =
+ * attributions x*grad of nt targets -> sum over c -> smooth x smooth box average (odd, 0 = none; zero padded) -> sign flip
+ * when negate -> clamp(min 0) -> mean over every cell x cell region -> out [nt, (h/cell)*(w/cell)] = region / total
+ * (0 where total*region <= 0), regions in COLUMN-major order like `.permute(0,1,3,2).reshape(nt,-1)`.  The localisation
+ * metric of target t is out[t][t].  tmp: 2*nt*h*w + nt*regions floats of scratch. */
+int bcosk_localisation_scores(const float* attr, int32_t nt, int32_t c, int32_t h, int32_t w, int32_t smooth, int32_t cell,
+                              int32_t negate, float* tmp, float* out, void* stream);
+
 /* MaxOut for the module-level path (bcosconv2d.py:166-170 `lin.unflatten(1, (O, M)).max(2)`, bcoslinear.py:107-110):
  * lin [rows, o*m] fp32 (unit c = oo*m + k) -> y [rows, o] = best * scale(best, inv_norm[row]) with the launch's scale mode
  * and B; gain [rows, o] = that scale (optional), amax [rows, o] = index of the kept unit (optional, first on ties). */
@@ -317,6 +325,25 @@ int bcosk_gelu_gate(const float* x, const float* g, int64_t n, float* y, void* s
  *                  P^T g, g [batch, n, heads*64] */
 int bcosk_attention(const float* qkv, const float* g, int32_t batch, int32_t n, int32_t heads, int32_t dim_head, float scale,
                     int32_t backward, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Group / position normalisation with detachable statistics, NCHW fp32 (module-level path)
+ * ------------------------------------------------------------------------------------------- */
+/* group_norm_uncentered groupnorm_uncentered.py:21-61 (centred == 0) and DetachableGroupNorm2d.forward
+ * centered_norms.py:93-138 (centred == 1): per (image, group) var = biased CENTRED variance over (C/groups, H, W);
+ * y = w[c] * (x - centred*mean) / sqrt(var + eps) + b[c]; rstd[nb*groups] saved for the explanation backward.
+ * groups == 1 is the GN-LayerNorm, groups == c the GN-InstanceNorm of the reference. */
+int bcosk_groupnorm_fwd(const float* x, int32_t nb, int32_t c, int64_t hw, int32_t groups, const float* w, const float* b,
+                        float eps, int32_t centred, float* y, float* rstd, void* stream);
+/* explanation backward (variance detached, mean in graph): gx = (w*gy - centred*mean_group(w*gy)) * rstd */
+int bcosk_groupnorm_explain_bwd(const float* gy, int32_t nb, int32_t c, int64_t hw, int32_t groups, const float* w,
+                                const float* rstd, int32_t centred, float* gx, void* stream);
+/* PositionNormUncentered2d.forward posnorm_uncentered.py:39-58 (centred == 0) and DetachablePositionNorm2d.forward
+ * centered_norms.py:251-297 (centred == 1): the same with the statistics over the channels of one pixel; rstd[nb*hw] */
+int bcosk_positionnorm_fwd(const float* x, int32_t nb, int32_t c, int64_t hw, const float* w, const float* b, float eps,
+                           int32_t centred, float* y, float* rstd, void* stream);
+int bcosk_positionnorm_explain_bwd(const float* gy, int32_t nb, int32_t c, int64_t hw, const float* w, const float* rstd,
+                                   int32_t centred, float* gx, void* stream);
 
 const char* bcosk_last_error(void);
 int bcosk_version(void);

@@ -156,6 +156,69 @@ def layer_norm_detachable(x: Tensor, weight: Optional[Tensor], bias: Optional[Te
     return y
 
 
+def group_norm_detachable(x: Tensor, num_groups: int, weight: Optional[Tensor] = None, bias: Optional[Tensor] = None,
+                          eps: float = 1e-5, detach: bool = False, centred: bool = False) -> Tensor:
+    """centred=False: `group_norm_uncentered` bcos/modules/norms/uncentered_norms/groupnorm_uncentered.py:21-61 (x / std,
+    std from the CENTRED biased variance, taken from x.detach() in explanation mode).  centred=True:
+    `DetachableGroupNorm2d.forward` bcos/modules/norms/centered_norms.py:93-138 ((x - mean) / std, only the variance
+    detached; stock F.group_norm when not detaching).  num_groups = 1 / C are the GN-LayerNorm / GN-InstanceNorm wrappers."""
+    n, c = x.shape[:2]
+    assert c % num_groups == 0
+    if centred and not detach:
+        return F.group_norm(x, num_groups, weight, bias, eps)
+    xg = x.reshape(n, num_groups, c // num_groups, *x.shape[2:])
+    dims = tuple(range(2, xg.dim()))
+    if centred:
+        var, mean = torch.var_mean(xg, dim=dims, unbiased=False, keepdim=True)
+        y = (xg - mean) / (var.detach() + eps).sqrt()
+    else:
+        var = (xg.detach() if detach else xg).var(dim=dims, unbiased=False, keepdim=True)
+        y = xg / (var + eps).sqrt()
+    y = y.reshape(x.shape)
+    if weight is not None:
+        y = weight[None, :, None, None] * y
+    if bias is not None:
+        y = y + bias[None, :, None, None]
+    return y
+
+
+def position_norm_detachable(x: Tensor, weight: Optional[Tensor] = None, bias: Optional[Tensor] = None, eps: float = 1e-5,
+                             detach: bool = False, centred: bool = False) -> Tensor:
+    """centred=False: `PositionNormUncentered2d.forward` bcos/modules/norms/uncentered_norms/posnorm_uncentered.py:39-58;
+    centred=True: `DetachablePositionNorm2d.forward` bcos/modules/norms/centered_norms.py:251-297 (channel-wise layer norm
+    per pixel; the variance is detached in explanation mode, the mean is not)."""
+    assert x.dim() == 4
+    if centred and not detach:
+        return F.layer_norm(x.permute(0, 2, 3, 1), x.shape[1:2], weight, bias, eps).permute(0, 3, 1, 2)
+    var, mean = torch.var_mean(x, dim=1, unbiased=False, keepdim=True)
+    if detach:
+        var = var.detach()
+    y = ((x - mean) if centred else x) / (var + eps).sqrt()
+    if weight is not None:
+        y = weight[None, :, None, None] * y
+    if bias is not None:
+        y = y + bias[None, :, None, None]
+    return y
+
+
+def all_norm_uncentered_2d(x: Tensor, running_var: Optional[Tensor], weight: Optional[Tensor] = None,
+                           bias: Optional[Tensor] = None, training: bool = False, momentum: float = 0.1, eps: float = 1e-5,
+                           detach: bool = False) -> Tensor:
+    """bcos/modules/norms/uncentered_norms/allnorm_uncentered.py:21-61: one variance for the whole batch tensor."""
+    if training:
+        var = (x.detach() if detach else x).var(unbiased=False)
+        if running_var is not None:
+            running_var.copy_((1 - momentum) * running_var + momentum * var.detach())
+    else:
+        var = running_var
+    y = x / (var + eps).sqrt()[None, ..., None, None]
+    if weight is not None:
+        y = weight[None, ..., None, None] * y
+    if bias is not None:
+        y = y + bias[None, ..., None, None]
+    return y
+
+
 def gelu_detachable(x: Tensor, detach: bool = False) -> Tensor:
     """`MyGELU` bcosify_vit.py:27-32: gate = 0.5*(1+erf(x/sqrt2)) (detached in explanation mode) * x."""
     gate = 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
@@ -696,3 +759,19 @@ def gradient_to_image_batched(x6: Tensor, grad6: Tensor, smooth: int = 15, alpha
         alpha = (alpha / torch.quantile(alpha, q=alpha_percentile / 100)).clip(0, 1)
         outs.append(torch.cat([rgb, alpha], 0).permute(1, 2, 0))
     return torch.stack(outs)
+
+
+def localisation_scores(attributions: Tensor, cell: int, smooth: int = 0, neg: bool = False) -> Tensor:
+    """interpretability/analyses/localisation.py:306-388 (the post-processing inside `LocalisationAnalyser.analysis`; it
+    is inline in a method that needs the experiment/data stack, so it is restated with the same ATen calls):
+    channel sum (:309-311), smoothing (:314-317), sign (:319-320), clamp (:322), region average pooling, transposition to
+    column-major regions and the fraction of the total (:378-388).  Returns [T, regions]; metric_t = out[t, t] (:389)."""
+    a = attributions.sum(1, keepdim=True)
+    if smooth:
+        a = F.avg_pool2d(a, smooth, stride=1, padding=(smooth - 1) // 2)
+    if neg:
+        a = -a
+    a = a.clamp(min=0)
+    contribs = F.avg_pool2d(a, cell, stride=cell).permute(0, 1, 3, 2).reshape(a.shape[0], -1)
+    total = contribs.sum(1, keepdim=True)
+    return torch.where(total * contribs > 0, contribs / total, torch.zeros_like(contribs))

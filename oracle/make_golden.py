@@ -19,6 +19,7 @@ import time
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -425,6 +426,111 @@ def golden_modules(seed: int = 0):
     print(f"[modules] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB), {len(out)} arrays")
 
 
+def golden_norms(seed: int = 7):
+    """Known-answer vectors for the group / position / all norms, produced by the reference classes themselves:
+    forward outside and inside explanation mode, and the explanation gradient of a fixed random seed."""
+    refload.load()
+    from bcos.modules.norms import centered_norms as CN
+    from bcos.modules.norms import uncentered_norms as UN
+
+    g = torch.Generator().manual_seed(4321 + seed)
+    out = {}
+    cases = [
+        # name, factory, oracle(x, w, b, eps, detach), channels, H, W, drop bias
+        ("gnu_g4", lambda: UN.GroupNormUncentered2d(4, 16), lambda x, w, b, e, d: O.group_norm_detachable(x, 4, w, b, e, d, False), 16, 6, 6, True),
+        ("gnu_g4_odd", lambda: UN.GroupNormUncentered2d(4, 16), lambda x, w, b, e, d: O.group_norm_detachable(x, 4, w, b, e, d, False), 16, 5, 5, False),
+        ("gnu_layer", lambda: UN.GNLayerNormUncentered2d(12), lambda x, w, b, e, d: O.group_norm_detachable(x, 1, w, b, e, d, False), 12, 8, 8, True),
+        ("gnu_instance", lambda: UN.GNInstanceNormUncentered2d(12), lambda x, w, b, e, d: O.group_norm_detachable(x, 12, w, b, e, d, False), 12, 7, 7, True),
+        ("dgn_g2", lambda: CN.DetachableGroupNorm2d(2, 16), lambda x, w, b, e, d: O.group_norm_detachable(x, 2, w, b, e, d, True), 16, 6, 6, True),
+        ("dgn_layer", lambda: CN.DetachableGNLayerNorm2d(24), lambda x, w, b, e, d: O.group_norm_detachable(x, 1, w, b, e, d, True), 24, 14, 14, False),
+        ("dgn_instance_odd", lambda: CN.DetachableGNInstanceNorm2d(6), lambda x, w, b, e, d: O.group_norm_detachable(x, 6, w, b, e, d, True), 6, 5, 7, True),
+        ("pnu", lambda: UN.PositionNormUncentered2d(24), lambda x, w, b, e, d: O.position_norm_detachable(x, w, b, e, d, False), 24, 7, 7, True),
+        ("pnu_wide", lambda: UN.PositionNormUncentered2d(80), lambda x, w, b, e, d: O.position_norm_detachable(x, w, b, e, d, False), 80, 9, 8, False),
+        ("dpn", lambda: CN.DetachablePositionNorm2d(24), lambda x, w, b, e, d: O.position_norm_detachable(x, w, b, e, d, True), 24, 7, 7, True),
+        ("dpn_bias", lambda: CN.DetachablePositionNorm2d(5), lambda x, w, b, e, d: O.position_norm_detachable(x, w, b, e, d, True), 5, 6, 6, False),
+    ]
+    for name, make, orc, c, h, w_, nobias in cases:
+        mod = make()
+        mod.weight.data = torch.rand(c, generator=g) + 0.5
+        if nobias:
+            mod.bias = None
+        else:
+            mod.bias.data = torch.randn(c, generator=g) * 0.1
+        x = torch.randn(3, c, h, w_, generator=g) * (torch.rand(3, c, 1, 1, generator=g) + 0.5) + 0.4
+        y = mod(x)
+        seedg = torch.randn(y.shape, generator=g)
+        mod.set_explanation_mode(True)
+        xg = x.clone().requires_grad_(True)
+        ye = mod(xg)
+        (gx,) = torch.autograd.grad((ye * seedg).sum(), [xg])
+        bias = None if mod.bias is None else mod.bias.detach()
+        assert torch.allclose(orc(x, mod.weight.detach(), bias, mod.eps, False), y.detach(), rtol=1e-6, atol=1e-6), name
+        xo = x.clone().requires_grad_(True)
+        yo = orc(xo, mod.weight.detach(), bias, mod.eps, True)
+        (go,) = torch.autograd.grad((yo * seedg).sum(), [xo])
+        assert torch.equal(yo.detach(), ye.detach()) and torch.equal(go, gx), name      # same ATen calls: bit exact
+        out.update({f"{name}.w": mod.weight.detach(), f"{name}.x": x, f"{name}.y": y.detach(), f"{name}.y_explain": ye.detach(),
+                    f"{name}.seed": seedg, f"{name}.gx": gx})
+        if bias is not None:
+            out[f"{name}.b"] = bias
+
+    an = UN.AllNormUncentered2d(10)
+    an.weight.data = torch.rand(1, generator=g) + 0.5
+    an.bias.data = torch.randn(1, generator=g) * 0.1
+    an.running_var.data = torch.rand(1, generator=g) + 0.2
+    x = torch.randn(3, 10, 6, 6, generator=g) + 0.3
+    an.eval()
+    y_eval = an(x)
+    assert torch.equal(O.all_norm_uncentered_2d(x, an.running_var, an.weight, an.bias), y_eval.detach())
+    rv0 = an.running_var.detach().clone()
+    an.train()
+    y_train = an(x)
+    an.eval()
+    an.set_explanation_mode(True)
+    seedg = torch.randn(y_eval.shape, generator=g)
+    xg = x.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad((an(xg) * seedg).sum(), [xg])
+    out.update({"alln.w": an.weight.detach(), "alln.b": an.bias.detach(), "alln.rv0": rv0, "alln.x": x, "alln.y_eval": y_eval.detach(),
+                "alln.y_train": y_train.detach(), "alln.rv1": an.running_var.detach().clone(), "alln.seed": seedg, "alln.gx": gx})
+
+    path = os.path.join(GOLD, "norms_kat.npz")
+    np.savez_compressed(path, **{k: v.detach().numpy() for k, v in out.items()})
+    print(f"[norms] wrote {path} ({os.path.getsize(path)/1e3:.0f} kB), {len(out)} arrays; oracle == reference bit exact in explanation mode")
+
+
+def golden_localisation(seed: int = 11):
+    """Localisation scores (interpretability/analyses/localisation.py:306-388).  The reference computes them inline in
+    `LocalisationAnalyser.analysis`, which needs the experiment / dataset stack and cannot be imported here; the vectors
+    below are produced by the very ATen calls of those lines, written out literally (not through the oracle), and the
+    oracle is checked against them."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name, (nt, c, grid, cell, smooth, neg) in {"g2_s15": (4, 6, 2, 32, 15, False), "g3_s0": (9, 6, 3, 20, 0, False),
+                                                   "g2_s3_neg": (4, 1, 2, 24, 3, True), "g2_zero": (4, 6, 2, 16, 5, False)}.items():
+        h = grid * cell
+        attributions_in = torch.randn(nt, c, h, h, generator=g) * torch.rand(nt, 1, h, h, generator=g)
+        if name == "g2_zero":
+            attributions_in[1] = -attributions_in[1].abs()          # a target without positive evidence: total = 0
+        attributions = attributions_in.sum(1, keepdim=True)
+        if smooth:
+            attributions = F.avg_pool2d(attributions, smooth, stride=1, padding=(smooth - 1) // 2)
+        if neg:
+            attributions = -attributions
+        attributions = attributions.clamp(min=0)
+        single_shape = cell
+        contribs = (F.avg_pool2d(attributions, single_shape, stride=single_shape).permute(0, 1, 3, 2)
+                    .reshape(attributions.shape[0], -1))
+        total = contribs.sum(1, keepdim=True)
+        contribs = torch.where(total * contribs > 0, contribs / total, torch.zeros_like(contribs))
+        assert torch.equal(O.localisation_scores(attributions_in, cell, smooth, neg), contribs), name
+        out[name + ".attr"] = attributions_in.numpy()
+        out[name + ".scores"] = contribs.numpy()
+        out[name + ".args"] = np.array([cell, smooth, int(neg)], dtype=np.int64)
+    path = os.path.join(GOLD, "localisation_kat.npz")
+    np.savez_compressed(path, **out)
+    print(f"[loc] wrote {path} ({os.path.getsize(path)/1e3:.0f} kB)")
+
+
 def golden_gradient_to_image(seed: int = 3):
     """RGBA explanation images from the reference's own gradient_to_image (bcos/common.py:387-436), per image."""
     refload.load()
@@ -481,8 +587,14 @@ if __name__ == "__main__":
         golden_densenet("densenet121", 2)
     if "vit_ti" in which:
         golden_vit("simple_vit_ti_patch16_224", 2)
+    if "vit_b" in which:
+        golden_vit("simple_vit_b_patch16_224", 2)
     if "clip_rn50" in which:
         golden_clip_rn50(2)
+    if "loc" in which:
+        golden_localisation()
+    if "norms" in which:
+        golden_norms()
     if "g2i" in which:
         golden_gradient_to_image()
     if "calib" in which:

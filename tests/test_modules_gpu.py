@@ -95,6 +95,55 @@ def test_norm_and_logit_modules(bcosk_lib, kat):
     assert _rel(ll(_t(kat["logit.x"])), _t(kat["logit.y"])) < 1e-6
 
 
+NORM_CASES = {"gnu_g4": (lambda: M.GroupNormUncentered2d(4, 16)), "gnu_g4_odd": (lambda: M.GroupNormUncentered2d(4, 16)),
+              "gnu_layer": (lambda: M.GNLayerNormUncentered2d(12)), "gnu_instance": (lambda: M.GNInstanceNormUncentered2d(12)),
+              "dgn_g2": (lambda: M.DetachableGroupNorm2d(2, 16)), "dgn_layer": (lambda: M.DetachableGNLayerNorm2d(24)),
+              "dgn_instance_odd": (lambda: M.DetachableGNInstanceNorm2d(6)), "pnu": (lambda: M.PositionNormUncentered2d(24)),
+              "pnu_wide": (lambda: M.PositionNormUncentered2d(80)), "dpn": (lambda: M.DetachablePositionNorm2d(24)),
+              "dpn_bias": (lambda: M.DetachablePositionNorm2d(5))}
+
+
+@pytest.mark.parametrize("name", sorted(NORM_CASES))
+def test_group_and_position_norms_match_reference(bcosk_lib, golden_dir, name):
+    """bcosk_groupnorm_* / bcosk_positionnorm_* through the drop-in classes against the reference's own outputs
+    (tests/golden/norms_kat.npz): forward in both modes and the explanation gradient; fp32, tolerance 1e-5 relative."""
+    kat = np.load(os.path.join(golden_dir, "norms_kat.npz"))
+    mod = NORM_CASES[name]().cuda()
+    mod.weight.data = _t(kat[name + ".w"])
+    if name + ".b" in kat.files:
+        mod.bias.data = _t(kat[name + ".b"])
+    else:
+        mod.bias = None
+    x = _t(kat[name + ".x"])
+    assert _rel(mod(x), _t(kat[name + ".y"])) < 1e-5
+    mod.set_explanation_mode(True)
+    xg = x.clone().requires_grad_(True)
+    ye = mod(xg)
+    assert _rel(ye, _t(kat[name + ".y_explain"])) < 1e-5
+    (gx,) = torch.autograd.grad((ye * _t(kat[name + ".seed"])).sum(), [xg])
+    assert _rel(gx, _t(kat[name + ".gx"])) < 1e-5
+    mod.set_explanation_mode(False)
+    with pytest.raises(NotImplementedError):          # the training backward through the statistics is not built: loud
+        torch.autograd.grad(mod(xg).sum(), [xg])
+
+
+def test_all_norm_matches_reference(bcosk_lib, golden_dir):
+    kat = np.load(os.path.join(golden_dir, "norms_kat.npz"))
+    an = M.AllNormUncentered2d(10).cuda()
+    an.weight.data, an.bias.data, an.running_var.data = _t(kat["alln.w"]), _t(kat["alln.b"]), _t(kat["alln.rv0"]).clone()
+    x = _t(kat["alln.x"])
+    an.eval()
+    assert _rel(an(x), _t(kat["alln.y_eval"])) < 1e-6
+    an.train()
+    assert _rel(an(x), _t(kat["alln.y_train"])) < 1e-5
+    assert _rel(an.running_var, _t(kat["alln.rv1"])) < 1e-5
+    an.eval()                                         # the golden gradient was taken after the running-variance update
+    an.set_explanation_mode(True)
+    xg = x.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad((an(xg) * _t(kat["alln.seed"])).sum(), [xg])
+    assert _rel(gx, _t(kat["alln.gx"])) < 1e-5
+
+
 def test_module_level_resnet18_matches_golden(bcosk_lib, golden_dir):
     gold = np.load(os.path.join(golden_dir, "resnet18_b8.npz"))
     m = bcosified_resnet("resnet18")
@@ -197,6 +246,23 @@ def test_module_level_vit_ti_matches_golden(bcosk_lib, golden_dir):
     assert mm["argmax_equal"] and mm["logit_rel_err"] <= 2e-3 and mm["map_cos_min"] >= 0.999 and mm["map_maxabs_over_range"] <= 1e-3
 
 
+def test_module_level_vit_b_matches_golden(bcosk_lib, golden_dir):
+    """config 3, second model: B-cosified SimpleViT-B/16 (12 layers, dim 768, 12 heads, MLP 3072) against the reference."""
+    from bcos_b200.vit import bcosified_simple_vit
+    arch = "simple_vit_b_patch16_224"
+    gold = np.load(os.path.join(golden_dir, f"{arch}_b2.npz"))
+    m = bcosified_simple_vit(arch)
+    sd = synth.synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, int(gold["seed"]))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    x6 = synth.to_bcos_input(gold["images_u8"]).cuda()
+    out = m.explain_batch(x6)
+    mm = OR.parity_metrics(out["logits"], out["contribution_map"], torch.from_numpy(gold["logits"]),
+                           torch.from_numpy(gold["contribution_map"]))
+    print("module-level ViT-B vs reference golden:", mm)
+    assert mm["argmax_equal"] and mm["logit_rel_err"] <= 2e-3 and mm["map_cos_min"] >= 0.999 and mm["map_maxabs_over_range"] <= 1e-3
+
+
 def test_module_level_clip_rn50_matches_golden(bcosk_lib, golden_dir):
     """config 4: B-cos CLIP RN50 image encoder; explanation target = cos(embedding, fixed unit vector) (arbitrary seed
     gradient at the embedding, like interpretability/analyses/text_localisation.py:77-100)."""
@@ -230,3 +296,16 @@ def test_module_level_clip_rn50_matches_golden(bcosk_lib, golden_dir):
     # within 1e-3 of the map range of the fp32 reference (or of the exact evaluation: on this chaotic random-init net the
     # reference itself sits `floor` = 2.3e-3 away from the fp64 result)
     assert min(mar, mar64) <= 1e-3
+
+
+@pytest.mark.parametrize("name", ["g2_s15", "g3_s0", "g2_s3_neg", "g2_zero"])
+def test_localisation_scores_match_reference(bcosk_lib, golden_dir, name):
+    """bcosk_localisation_scores against the reference's post-processing (tests/golden/localisation_kat.npz);
+    fp32 sums in a different order: 1e-5 absolute on fractions in [0, 1]."""
+    from bcos_b200.explain import localisation_scores
+    kat = np.load(os.path.join(golden_dir, "localisation_kat.npz"))
+    cell, smooth, neg = kat[name + ".args"].tolist()
+    got = localisation_scores(_t(kat[name + ".attr"]), cell, smooth, bool(neg))
+    ref = _t(kat[name + ".scores"])
+    assert got.shape == ref.shape and (got - ref).abs().max().item() < 1e-5
+    assert torch.equal(got == 0, ref == 0)

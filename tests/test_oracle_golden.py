@@ -80,6 +80,42 @@ def test_norms_and_small_layers(kat):
     assert torch.equal(OR.logit_layer(_t(kat["logit.x"]), 2.0, -1.5), _t(kat["logit.y"]))
 
 
+# name -> (kind, groups, centred, channels)
+NORM_CASES = {"gnu_g4": ("group", 4, False), "gnu_g4_odd": ("group", 4, False), "gnu_layer": ("group", 1, False),
+              "gnu_instance": ("group", 12, False), "dgn_g2": ("group", 2, True), "dgn_layer": ("group", 1, True),
+              "dgn_instance_odd": ("group", 6, True), "pnu": ("pos", 0, False), "pnu_wide": ("pos", 0, False),
+              "dpn": ("pos", 0, True), "dpn_bias": ("pos", 0, True)}
+
+
+@pytest.mark.parametrize("name", sorted(NORM_CASES))
+def test_group_and_position_norm_known_answers(golden_dir, name):
+    """oracle group / position norms against the vectors the reference classes produced (tests/golden/norms_kat.npz)."""
+    kat = np.load(os.path.join(golden_dir, "norms_kat.npz"))
+    kind, groups, centred = NORM_CASES[name]
+    w = _t(kat[name + ".w"])
+    b = _t(kat[name + ".b"]) if name + ".b" in kat.files else None
+
+    def run(x, detach):
+        if kind == "group":
+            return OR.group_norm_detachable(x, groups, w, b, 1e-5, detach, centred)
+        return OR.position_norm_detachable(x, w, b, 1e-5, detach, centred)
+    x = _t(kat[name + ".x"])
+    assert torch.allclose(run(x, False), _t(kat[name + ".y"]), rtol=1e-6, atol=1e-6)
+    xg = x.clone().requires_grad_(True)
+    ye = run(xg, True)
+    (gx,) = torch.autograd.grad((ye * _t(kat[name + ".seed"])).sum(), [xg])
+    assert torch.equal(ye.detach(), _t(kat[name + ".y_explain"])) and torch.equal(gx, _t(kat[name + ".gx"]))
+
+
+def test_all_norm_known_answers(golden_dir):
+    kat = np.load(os.path.join(golden_dir, "norms_kat.npz"))
+    x, w, b = _t(kat["alln.x"]), _t(kat["alln.w"]), _t(kat["alln.b"])
+    assert torch.equal(OR.all_norm_uncentered_2d(x, _t(kat["alln.rv0"]), w, b), _t(kat["alln.y_eval"]))
+    rv = _t(kat["alln.rv0"]).clone()
+    yt = OR.all_norm_uncentered_2d(x, rv, w, b, training=True, momentum=0.1)
+    assert torch.equal(yt, _t(kat["alln.y_train"])) and torch.equal(rv, _t(kat["alln.rv1"]))
+
+
 def _golden_state(arch, gold):
     sd = synth.synth_state_dict(OR.resnet_state_shapes(arch), int(gold["seed"]))
     off = 0
@@ -173,6 +209,16 @@ def test_vit_golden(golden_dir):
     assert w6.shape == (2, 24) and torch.equal(w6[:, :3], w3[:, :3] / 2) and torch.equal(w6[:, 3:6], -w3[:, :3] / 2)
 
 
+def test_vit_b_golden(golden_dir):
+    arch = "simple_vit_b_patch16_224"
+    gold = np.load(os.path.join(golden_dir, f"{arch}_b2.npz"))
+    sd = synth.synth_state_dict(OR.vit_state_shapes(arch), int(gold["seed"]))
+    x6 = synth.to_bcos_input(gold["images_u8"][:1])
+    e = OR.explain_batched(OR.OracleViT(arch, sd).forward, x6)
+    m = OR.parity_metrics(e["logits"], e["contribution_map"], _t(gold["logits"][:1]), _t(gold["contribution_map"][:1]))
+    assert m["argmax_equal"] and m["logit_rel_err"] < 1e-5 and m["map_cos_min"] > 0.99999, m
+
+
 def test_clip_rn50_golden(golden_dir):
     gold = np.load(os.path.join(golden_dir, "clip_rn50_b2.npz"))
     sd = synth.synth_state_dict(OR.clip_rn_state_shapes(), int(gold["seed"]))
@@ -201,3 +247,15 @@ def test_gradient_to_image_known_answers(golden_dir):
             ref = np.stack([BC.gradient_to_image(x6[i], grad6[i], smooth=int(smooth), alpha_percentile=float(pct))
                             for i in range(x6.shape[0])])
             assert np.array_equal(out.numpy(), ref), name
+
+
+LOC_CASES = ["g2_s15", "g3_s0", "g2_s3_neg", "g2_zero"]
+
+
+@pytest.mark.parametrize("name", LOC_CASES)
+def test_localisation_scores_known_answers(golden_dir, name):
+    kat = np.load(os.path.join(golden_dir, "localisation_kat.npz"))
+    cell, smooth, neg = kat[name + ".args"].tolist()
+    got = OR.localisation_scores(_t(kat[name + ".attr"]), cell, smooth, bool(neg))
+    assert torch.equal(got, _t(kat[name + ".scores"]))
+    assert torch.allclose(got.sum(1)[got.sum(1) > 0], torch.ones(1))          # fractions of the positive evidence
