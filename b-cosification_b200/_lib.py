@@ -287,6 +287,14 @@ def positionnorm_explain_bwd(gy, nb, c, hw, w, rstd, centred, gx) -> None:
                                                 _stream()), "bcosk_positionnorm_explain_bwd")
 
 
+def l2norm_rows(x, rows, d, y, inv) -> None:
+    check(load().bcosk_l2norm_rows(_p(x), C.c_int64(rows), d, _p(y), _p(inv), _stream()), "bcosk_l2norm_rows")
+
+
+def row_scale(x, rows, d, s, y) -> None:
+    check(load().bcosk_row_scale(_p(x), C.c_int64(rows), d, _p(s), _p(y), _stream()), "bcosk_row_scale")
+
+
 def gelu_gate(x, g, n, y) -> None:
     check(load().bcosk_gelu_gate(_p(x), _p(g), C.c_int64(n), _p(y), _stream()), "bcosk_gelu_gate")
 

@@ -48,7 +48,7 @@ class Bottleneck(nn.Module):
 
 
 class ModifiedResNet(nn.Module):
-    def __init__(self, layers, output_dim, heads, input_resolution=224, width=64):
+    def __init__(self, layers, output_dim, heads, input_resolution=224, width=64, attn_unpool=False):
         super().__init__()
         self.output_dim, self.input_resolution = output_dim, input_resolution
         self.conv1 = nn.Conv2d(3, width // 2, kernel_size=3, stride=2, padding=1, bias=False)
@@ -66,7 +66,7 @@ class ModifiedResNet(nn.Module):
         self.layer2 = self._make_layer(width * 2, layers[1], stride=2)
         self.layer3 = self._make_layer(width * 4, layers[2], stride=2)
         self.layer4 = self._make_layer(width * 8, layers[3], stride=2)
-        self.attnpool = BcosAttentionPool2d(input_resolution // 32, width * 32, heads, output_dim)
+        self.attnpool = BcosAttentionPool2d(input_resolution // 32, width * 32, heads, output_dim, attn_unpool)
 
     def _make_layer(self, planes, blocks, stride=1):
         layers = [Bottleneck(self._inplanes, planes, stride)]
@@ -84,11 +84,13 @@ class ModifiedResNet(nn.Module):
         return self.attnpool(x)
 
 
-def bcosified_clip_rn50() -> BcosifyNetwork:
-    """Offline equivalent of clip_bcosification/model.py:8-25 for `resnet_50_clip_b2_noBias...` (random init)."""
+def bcosified_clip_rn50(attn_unpool: bool = False) -> BcosifyNetwork:
+    """Offline equivalent of clip_bcosification/model.py:8-25 for `resnet_50_clip_b2_noBias...` (random init).
+    `attn_unpool=True` is the `model_config["attn_unpool"]` variant (bcosattnpool.py:65): per-token unit embeddings
+    (HW) x N x D' instead of the pooled one, used by the text-localisation analysis."""
     cfg = dict(is_bcos=True, name="resnet50clip", bcos_args=dict(b=2, max_out=1),
                bcosify_args=dict(clip_kd=True, fix_b=True, norm_layer="BnUncV2", use_bias=False))
-    m = BcosifyNetwork(ModifiedResNet((3, 4, 6, 3), 1024, 32, 224, 64), cfg, add_channels=True, logit_layer=False)
+    m = BcosifyNetwork(ModifiedResNet((3, 4, 6, 3), 1024, 32, 224, 64, attn_unpool), cfg, add_channels=True, logit_layer=False)
     # bcosify.py:81-83,97: inside the attention pool only c_proj becomes a BcosifyLinear object (its weight is what is used)
     ap = m.model.attnpool
     if isinstance(ap.c_proj, nn.Linear):

@@ -47,6 +47,32 @@ __global__ void layernorm_explain_bwd_kernel(const float* __restrict__ gy, long 
   for (int i = lane; i < d; i += 32) gx[row * d + i] = (__ldg(src + i) * (w ? __ldg(w + i) : 1.f) - m) * r;
 }
 
+
+// ---------------------------------------------------------------- per-row L2 normalisation (attn_unpool head)
+// y = x / ||x||_2 per row of d values, inv[row] = 1 / ||x||_2 saved for the explanation backward; one warp per row
+__global__ void l2norm_rows_kernel(const float* __restrict__ x, long long rows, int d, float* __restrict__ y,
+                                   float* __restrict__ inv) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* src = x + row * d;
+  float s = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    const float v = __ldg(src + i);
+    s = fmaf(v, v, s);
+  }
+  const float r = 1.0f / sqrtf(warp_sum(s));
+  for (int i = lane; i < d; i += 32) y[row * d + i] = __ldg(src + i) * r;
+  if (inv != nullptr && lane == 0) inv[row] = r;
+}
+// y = x * s[row]   (explanation backward of the above with the norm detached)
+__global__ void row_scale_kernel(const float* __restrict__ x, long long rows, int d, const float* __restrict__ s,
+                                 float* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * d) return;
+  y[i] = __ldg(x + i) * __ldg(s + i / d);
+}
+
 // ---------------------------------------------------------------- GELU with detachable gate
 // mode 0: y = x * gate(x); mode 1 (explanation backward): y = g * gate(x)
 __global__ void gelu_gate_kernel(const float* __restrict__ x, const float* __restrict__ g, long long n, float* __restrict__ y) {
@@ -152,6 +178,22 @@ extern "C" int bcosk_layernorm_explain_bwd(const float* gy, int64_t rows, int32_
                                            void* stream) {
   if (!gy || !gx || !rstd) return set_error(BCOSK_EINVAL, "layernorm_explain_bwd: bad argument");
   layernorm_explain_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, S3(stream)>>>(gy, rows, d, w, rstd, gx);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_l2norm_rows(const float* x, int64_t rows, int32_t d, float* y, float* inv, void* stream) {
+  if (!x || !y || d < 1 || rows < 0) return set_error(BCOSK_EINVAL, "l2norm_rows: bad argument");
+  if (rows == 0) return BCOSK_OK;
+  l2norm_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, S3(stream)>>>(x, rows, d, y, inv);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_row_scale(const float* x, int64_t rows, int32_t d, const float* s, float* y, void* stream) {
+  if (!x || !y || !s || d < 1 || rows < 0) return set_error(BCOSK_EINVAL, "row_scale: bad argument");
+  if (rows == 0) return BCOSK_OK;
+  row_scale_kernel<<<(unsigned)((rows * d + 255) / 256), 256, 0, S3(stream)>>>(x, rows, d, s, y);
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }

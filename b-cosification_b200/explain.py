@@ -88,6 +88,32 @@ def localisation_scores(attributions: Tensor, cell: int, smooth: int = 0, neg: b
     return out
 
 
+def text_localisation_target(out: Tensor, zeroshot_weight: Tensor, attn_unpool: bool, pool_cosine: float = 1,
+                             norm_max_cosine: bool = False) -> Tensor:
+    """The scalar that `compute_attributions` back-propagates (interpretability/analyses/text_localisation.py:80-105):
+    cosine of the (per-token, with attn_unpool) image embedding with a text embedding [D, 1]; tokens are pooled by
+    `mean(cos * |cos|^(p-1))` (p = pool_cosine > 1), by the arg-max token (p = 0) or by the plain mean (p = 1).
+    Plain torch on the caller's device: a few hundred scalars; the encoder before it is the kernel path."""
+    img_features = out / out.norm(dim=-1, keepdim=True)
+    logits = img_features @ zeroshot_weight
+    if attn_unpool:
+        logits = logits.reshape(-1, 1)
+        if pool_cosine == 0:
+            num_features = logits.shape[0]
+            logits = logits.reshape(-1, num_features)
+            mask = torch.zeros_like(logits)
+            mask[torch.arange(logits.shape[0], device=logits.device), logits.argmax(dim=1)] = 1.0
+            logits = (logits * mask.detach()).reshape(1, num_features)
+        if norm_max_cosine:
+            logits = logits / logits.abs().detach().max(dim=0, keepdim=True)[0]
+        if pool_cosine > 1:
+            logits = logits * torch.pow(logits, pool_cosine - 1).abs().detach()
+        logits = logits.mean(dim=0)
+    if logits.dim() == 1:
+        logits = logits.unsqueeze(0)
+    return logits.max(1).values
+
+
 class BcosUtilMixin:
     """Explanation helpers for models made of B-cos modules (bcos/common.py:23-344)."""
 

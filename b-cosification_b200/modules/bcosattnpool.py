@@ -9,7 +9,7 @@ from torch import Tensor
 
 from . import _runtime as R
 from .common import DetachableModule
-from .tokens import frozen_attention
+from .tokens import frozen_attention, l2_normalize_rows
 
 __all__ = ["BcosAttentionPool2d"]
 
@@ -44,7 +44,7 @@ class BcosAttentionPool2d(DetachableModule):
 
     def forward(self, x):
         if self.attn_unpool:
-            raise NotImplementedError("bcos_b200: the attn_unpool variant (per-token cosine pooling) is a 'next' row (SURVEY 8f.3)")
+            return self._forward_unpool(x)
         for lin in (self.q_proj, self.k_proj, self.v_proj, self.c_proj):
             if getattr(lin, "bias", None) is not None:
                 raise NotImplementedError("bcos_b200: attention pooling is built bias-free (all registered configs strip biases)")
@@ -58,6 +58,20 @@ class BcosAttentionPool2d(DetachableModule):
         o = frozen_attention(qkv, self.num_heads, dh ** -0.5, True)[:, 0]
         cw = self.c_proj.weight if isinstance(self.c_proj, nn.Linear) else self.c_proj.linear.weight
         return self._plain(o, self._out_cache, cw, cw)                     # c_proj acts as a plain linear (:56)
+
+    def _forward_unpool(self, x):
+        """bcosattnpool.py:23-33: every spatial token goes through v_proj (plain) and c_proj (a B-cos linear once
+        bcosified, bcosify.py:81-97) and is L2-normalised with a detachable norm; output (HW) x N x D'."""
+        for lin in (self.v_proj, self.c_proj):
+            if getattr(lin, "bias", None) is not None:
+                raise NotImplementedError("bcos_b200: attention pooling is built bias-free (all registered configs strip biases)")
+        t = x.flatten(start_dim=2).permute(2, 0, 1).contiguous()           # NCHW -> (HW) N C
+        t = self._plain(t, self._qkv_cache, self.v_proj.weight, self.v_proj.weight)
+        if isinstance(self.c_proj, nn.Linear):
+            t = self._plain(t, self._out_cache, self.c_proj.weight, self.c_proj.weight)
+        else:
+            t = self.c_proj(t)
+        return l2_normalize_rows(t, self.detach)
 
     @classmethod
     def from_standard_module(cls, model, module, model_config):

@@ -12,7 +12,7 @@ from .. import _lib as L
 from . import _runtime as R
 from .common import DetachableModule
 
-__all__ = ["DetachableLayerNorm", "MyGELU", "PlainLinear", "frozen_attention"]
+__all__ = ["DetachableLayerNorm", "MyGELU", "PlainLinear", "frozen_attention", "l2_normalize_rows"]
 
 _NOT_BUILT = ("bcos_b200: only the explanation-mode backward (detached dynamic weights) is built; "
               "the full training backward is outside this round's scope")
@@ -66,6 +66,36 @@ class DetachableLayerNorm(nn.LayerNorm, DetachableModule):
             if standard_module.bias is not None:
                 new_mod.bias.data = standard_module.bias.data
         return new_mod
+
+
+class _L2NormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, detach):
+        d = x.shape[-1]
+        rows = x.numel() // d
+        y = torch.empty_like(x)
+        inv = torch.empty(rows, dtype=torch.float32, device=x.device)
+        L.l2norm_rows(x, rows, d, y, inv)
+        ctx.detach = detach
+        ctx.save_for_backward(inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        if not ctx.detach:
+            raise NotImplementedError(_NOT_BUILT)
+        (inv,) = ctx.saved_tensors
+        gy = gy.contiguous()
+        d = gy.shape[-1]
+        gx = torch.empty_like(gy)
+        L.row_scale(gy, gy.numel() // d, d, inv, gx)
+        return gx, None
+
+
+def l2_normalize_rows(x: Tensor, detach: bool) -> Tensor:
+    """x / x.norm(dim=-1, keepdim=True) with the norm detached in explanation mode (bcosattnpool.py:29-32)."""
+    R._require_cuda(x, "l2_normalize_rows")
+    return _L2NormFn.apply(x.float().contiguous(), detach).type(x.dtype)
 
 
 class _GeluFn(torch.autograd.Function):

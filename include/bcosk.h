@@ -317,6 +317,11 @@ int bcosk_layernorm_fwd(const float* x, int64_t rows, int32_t d, const float* w,
 /* explanation backward of the above (variance detached :211, mean in graph): gx = (w*gy - mean_d(w*gy)) * rstd */
 int bcosk_layernorm_explain_bwd(const float* gy, int64_t rows, int32_t d, const float* w, const float* rstd, float* gx,
                                 void* stream);
+/* attn_unpool head of BcosAttentionPool2d.forward bcos/modules/bcosattnpool.py:23-33: y = x / ||x||_2 per row (token) of d
+ * values, inv[row] = 1/||x||_2 saved; with the norm detached (:30-31) the explanation backward is bcosk_row_scale(gy, inv) */
+int bcosk_l2norm_rows(const float* x, int64_t rows, int32_t d, float* y, float* inv, void* stream);
+/* y[row, :] = x[row, :] * s[row] */
+int bcosk_row_scale(const float* x, int64_t rows, int32_t d, const float* s, float* y, void* stream);
 /* MyGELU bcosify_vit.py:27-32: g == NULL: y = x * gate(x);  g != NULL (explanation backward, gate detached): y = g * gate(x) */
 int bcosk_gelu_gate(const float* x, const float* g, int64_t n, float* y, void* stream);
 /* Attention.forward bcos/models/vit.py:143-158 after to_qkv: qkv [batch, n, 3*heads*64] ->

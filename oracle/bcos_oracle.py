@@ -561,7 +561,8 @@ class OracleViT:
 # `BcosAttentionPool2d` (bcos/modules/bcosattnpool.py:22-59) without positional embedding or biases
 # (bcos/experiments/ImageNet/clip_bcosification/model.py:15-23)
 # ----------------------------------------------------------------------------------------------
-def clip_rn_state_shapes(layers=(3, 4, 6, 3), output_dim: int = 1024, width: int = 64) -> Dict[str, Tuple[int, ...]]:
+def clip_rn_state_shapes(layers=(3, 4, 6, 3), output_dim: int = 1024, width: int = 64,
+                         attn_unpool: bool = False) -> Dict[str, Tuple[int, ...]]:
     sh: Dict[str, Tuple[int, ...]] = {}
 
     def bn(prefix, c):
@@ -586,7 +587,7 @@ def clip_rn_state_shapes(layers=(3, 4, 6, 3), output_dim: int = 1024, width: int
                 sh[p + ".downsample.1.linear.weight"] = (planes * 4, inpl, 1, 1); bn(p + ".downsample.2", planes * 4)
             inpl = planes * 4
     e = width * 32
-    for nme in ("k_proj", "q_proj", "v_proj"):
+    for nme in (("v_proj",) if attn_unpool else ("k_proj", "q_proj", "v_proj")):
         sh[f"model.attnpool.{nme}.weight"] = (e, e)
     sh["model.attnpool.c_proj.linear.weight"] = (output_dim, e)
     return sh
@@ -597,6 +598,7 @@ class OracleCLIPResNet:
                  mean=CLIP_MEAN_ADDINVERSE, std=CLIP_STD_ADDINVERSE):
         self.sd, self.layers, self.heads, self.b, self.eps, self.mean, self.std = sd, layers, heads, b, eps, mean, std
         self.training, self.momentum = False, 0.1
+        self.unpool = "model.attnpool.q_proj.weight" not in sd        # attn_unpool variant has no q/k projections (:15-17)
 
     def _conv(self, name, x, stride, padding, detach):
         return bcos_conv2d(x, self.sd[name + ".linear.weight"], None, stride, padding, b=self.b, detach=detach)
@@ -637,6 +639,18 @@ class OracleCLIPResNet:
         o = torch.bmm(attn, vh).transpose(0, 1).reshape(1, N, C)
         return F.linear(o, self.sd["model.attnpool.c_proj.linear.weight"]).squeeze(0)
 
+    def attn_unpool(self, x: Tensor, detach: bool) -> Tensor:
+        """bcosattnpool.py:23-33 (`attn_unpool=True`): every spatial token -> v_proj (plain, stays nn.Linear
+        bcosify.py:95) -> c_proj (BcosifyLinear, b=2) -> divided by its L2 norm, the norm detached in explanation mode.
+        Returns (HW) x N x D'."""
+        t = x.flatten(2).permute(2, 0, 1)
+        t = F.linear(t, self.sd["model.attnpool.v_proj.weight"])
+        t = bcos_linear(t, self.sd["model.attnpool.c_proj.linear.weight"], None, b=self.b, detach=detach, normalize_weight=False)
+        norm = t.norm(dim=-1, keepdim=True)
+        if detach:
+            norm = norm.detach()
+        return t / norm
+
     def forward(self, x6: Tensor, detach: bool = False) -> Tensor:
         x = normalize6(x6, self.mean, self.std)
         x = F.relu(self._bn("model.bn1", self._conv("model.conv1", x, 2, 1, detach), detach))
@@ -646,7 +660,7 @@ class OracleCLIPResNet:
         for li, nb in enumerate(self.layers, start=1):
             for bi in range(nb):
                 x = self._block(f"model.layer{li}.{bi}", x, 2 if (li > 1 and bi == 0) else 1, detach)
-        return self.attnpool(x, detach)
+        return self.attn_unpool(x, detach) if self.unpool else self.attnpool(x, detach)
 
     __call__ = forward
 
@@ -775,3 +789,30 @@ def localisation_scores(attributions: Tensor, cell: int, smooth: int = 0, neg: b
     contribs = F.avg_pool2d(a, cell, stride=cell).permute(0, 1, 3, 2).reshape(a.shape[0], -1)
     total = contribs.sum(1, keepdim=True)
     return torch.where(total * contribs > 0, contribs / total, torch.zeros_like(contribs))
+
+
+def text_localisation_target(out: Tensor, zeroshot_weight: Tensor, attn_unpool: bool, pool_cosine: float = 1,
+                             norm_max_cosine: bool = False) -> Tensor:
+    """interpretability/analyses/text_localisation.py:80-105 (`compute_attributions`): the scalar whose gradient is the
+    explanation -- cosine of the image embedding (per token with attn_unpool) with the text embedding [D, 1], tokens
+    pooled by mean(cos * |cos|^(p-1)) for p > 1 (:97-98), arg-max token for p = 0 (:87-94), plain mean for p = 1."""
+    img_features = out / out.norm(dim=-1, keepdim=True)
+    logits = img_features @ zeroshot_weight
+    if attn_unpool:
+        logits = logits.reshape(-1, 1)
+        if pool_cosine == 0:
+            num_features = logits.shape[0]
+            logits = logits.reshape(-1, num_features)
+            max_locations = logits.argmax(dim=1)
+            mask = torch.zeros_like(logits)
+            for i in range(logits.shape[0]):
+                mask[i, max_locations[i]] = 1.0
+            logits = (logits * mask.detach()).reshape(1, num_features)
+        if norm_max_cosine:
+            logits = logits / logits.abs().detach().max(dim=0, keepdim=True)[0]
+        if pool_cosine > 1:
+            logits = logits * torch.pow(logits, pool_cosine - 1).abs().detach()
+        logits = logits.mean(dim=0)
+    if logits.dim() == 1:
+        logits = logits.unsqueeze(0)
+    return logits.max(1).values

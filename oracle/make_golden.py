@@ -294,6 +294,90 @@ def golden_clip_rn50(batch: int, seed: int = 0):
     print(f"[clip_rn50] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB) in {time.time()-t0:.1f}s")
 
 
+def golden_clip_unpool(seed: int = 0):
+    """the attn_unpool head (bcosattnpool.py:23-33) and the text-localisation target
+    (interpretability/analyses/text_localisation.py:68-105) on the reference CLIP RN50, image 0 of the clip_rn50_b2 golden
+    (same weights and BN calibration: the state dict is per-key deterministic).  text_localisation.py imports matplotlib /
+    the CLIP tokenizer and cannot be imported here, so lines 77-105 are executed literally below on the reference model."""
+    t0 = time.time()
+    refload.load()
+    import bcosify
+    from CLIP.clip.model import ModifiedResNet
+    base = np.load(os.path.join(GOLD, "clip_rn50_b2.npz"))
+    cfg = dict(is_bcos=True, name="resnet50clip", bcos_args=dict(b=2, max_out=1), attn_unpool=True,
+               bcosify_args=dict(clip_kd=True, fix_b=True, norm_layer="BnUncV2", use_bias=False))
+    model = bcosify.BcosifyNetwork(ModifiedResNet((3, 4, 6, 3), 1024, 32, 224, 64).float(), cfg, add_channels=True, logit_layer=False)
+    for mod in model.modules():
+        if hasattr(mod, "bias") and mod.bias is not None:
+            mod.bias = None
+        if hasattr(mod, "positional_embedding") and mod.positional_embedding is not None:
+            mod.positional_embedding = None
+    assert model.model.attnpool.attn_unpool
+    ref_shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert ref_shapes == O.clip_rn_state_shapes(attn_unpool=True), sorted(set(ref_shapes) ^ set(O.clip_rn_state_shapes(attn_unpool=True)))
+    sd = synth.synth_state_dict(ref_shapes, seed)
+    off = 0
+    for k, n in zip(base["bn_keys"].tolist(), base["bn_sizes"].tolist()):
+        sd[k] = torch.from_numpy(base["bn_var"][off:off + n].copy()); off += n
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    test_img = synth.to_bcos_input(base["images_u8"][:1])[0]
+    zeroshot_weight = O.clip_seed_direction(1024, seed).unsqueeze(1)
+    out = {}
+    for pool_cosine in (1, 2, 0):
+        # ---- text_localisation.py:77-105, verbatim semantics ----
+        with torch.enable_grad(), model.explanation_mode():
+            imga = test_img[None].requires_grad_()
+            outa = model(imga)
+            img_features = outa / outa.norm(dim=-1, keepdim=True)
+            logits = img_features @ zeroshot_weight
+            if model.model.attnpool.attn_unpool:
+                logits = logits.reshape(-1, 1)
+                if pool_cosine == 0:
+                    num_features = logits.shape[0]
+                    logits = logits.reshape(-1, num_features)
+                    max_locations = logits.argmax(dim=1)
+                    mask = torch.zeros_like(logits)
+                    for i in range(logits.shape[0]):
+                        mask[i, max_locations[i]] = 1.0
+                    logits = logits * mask.detach()
+                    logits = logits.reshape(1, num_features)
+                if pool_cosine > 1:
+                    logits = logits * torch.pow(logits, pool_cosine - 1).abs().detach()
+                logits = logits.mean(dim=0)
+            if logits.dim() == 1:
+                logits = logits.unsqueeze(0)
+            target = logits.max(1).values
+            target.backward(inputs=[imga])
+            grada = imga.grad.detach()[0]
+        contribs = (test_img * grada).sum(0)
+        # ---- oracle ----
+        om = O.OracleCLIPResNet(sd)
+        xb = test_img[None].clone().requires_grad_(True)
+        with torch.enable_grad():
+            oo = om.forward(xb, detach=True)
+            ot = O.text_localisation_target(oo, zeroshot_weight, True, pool_cosine)
+            (og,) = torch.autograd.grad(ot.sum(), [xb])
+        erel = ((oo.detach() - outa.detach()).abs().max() / outa.detach().abs().max()).item()
+        grel = ((og[0] - grada).abs().max() / grada.abs().max()).item()
+        print(f"[clip_unpool p={pool_cosine}] oracle vs reference: tokens rel err {erel:.2e}, target {ot.item():.6f} vs {target.item():.6f}, grad rel err {grel:.2e}")
+        assert erel < 1e-5 and grel < 1e-4 and abs(ot.item() - target.item()) < 1e-6
+        sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+        x64 = test_img[None].double().clone().requires_grad_(True)
+        with torch.enable_grad():
+            t64 = O.text_localisation_target(O.OracleCLIPResNet(sd64).forward(x64, detach=True), zeroshot_weight.double(), True, pool_cosine)
+            (g64,) = torch.autograd.grad(t64.sum(), [x64])
+        c64 = (test_img.double() * g64[0]).sum(0)
+        out[f"p{pool_cosine}.target"] = target.detach().numpy()
+        out[f"p{pool_cosine}.contribution_map"] = contribs.numpy()
+        out[f"p{pool_cosine}.contribution_map_fp64"] = c64.float().numpy()
+        if pool_cosine == 1:
+            out["tokens"] = outa.detach().numpy()
+    path = os.path.join(GOLD, "clip_rn50_unpool_b1.npz")
+    np.savez_compressed(path, seed=np.int64(seed), **out)
+    print(f"[clip_unpool] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB) in {time.time()-t0:.1f}s")
+
+
 def golden_modules(seed: int = 0):
     """Known-answer vectors for single modules, produced by the reference classes themselves."""
     refload.load()
@@ -595,6 +679,8 @@ if __name__ == "__main__":
         golden_localisation()
     if "norms" in which:
         golden_norms()
+    if "clip_unpool" in which:
+        golden_clip_unpool()
     if "g2i" in which:
         golden_gradient_to_image()
     if "calib" in which:

@@ -309,3 +309,43 @@ def test_localisation_scores_match_reference(bcosk_lib, golden_dir, name):
     ref = _t(kat[name + ".scores"])
     assert got.shape == ref.shape and (got - ref).abs().max().item() < 1e-5
     assert torch.equal(got == 0, ref == 0)
+
+
+def test_module_level_clip_unpool_text_localisation(bcosk_lib, golden_dir):
+    """CLIP RN50 with the attn_unpool head (per-token unit embeddings, bcosattnpool.py:23-33) and the
+    text-localisation targets (text_localisation.py:77-105: mean cosine, cosine-power pooling p=2, arg-max token) against
+    the reference run; tolerances of the north star (cosine >= 0.999, max-abs <= 1e-3 of the map range vs the reference or
+    its fp64 evaluation)."""
+    from bcos_b200.clip_rn import bcosified_clip_rn50
+    from bcos_b200.explain import text_localisation_target
+    base = np.load(os.path.join(golden_dir, "clip_rn50_b2.npz"))
+    gold = np.load(os.path.join(golden_dir, "clip_rn50_unpool_b1.npz"))
+    m = bcosified_clip_rn50(attn_unpool=True)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert shapes == OR.clip_rn_state_shapes(attn_unpool=True)
+    sd = synth.synth_state_dict(shapes, int(gold["seed"]))
+    off = 0
+    for k, n in zip(base["bn_keys"].tolist(), base["bn_sizes"].tolist()):
+        sd[k] = torch.from_numpy(base["bn_var"][off:off + n].copy()); off += n
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    x6 = synth.to_bcos_input(base["images_u8"][:1]).cuda()
+    zw = OR.clip_seed_direction(1024, int(gold["seed"])).unsqueeze(1).cuda()
+    for p in (1, 2, 0):
+        xb = x6.clone().requires_grad_(True)
+        with torch.enable_grad(), m.explanation_mode():
+            tok = m(xb)
+            tgt = text_localisation_target(tok, zw, True, p)
+            tgt.backward(inputs=[xb])
+        assert tok.shape == (49, 1, 1024)
+        if p == 1:
+            assert _rel(tok.detach(), _t(gold["tokens"])) <= 2e-3
+        cmap = (xb.detach() * xb.grad).sum(1)[0]
+        ref, ref64 = _t(gold[f"p{p}.contribution_map"]), _t(gold[f"p{p}.contribution_map_fp64"])
+        cos = torch.nn.functional.cosine_similarity(cmap.flatten().double(), ref.flatten().double(), dim=0).item()
+        rng = (ref.max() - ref.min()).item()
+        mar, mar64 = (cmap - ref).abs().max().item() / rng, (cmap - ref64).abs().max().item() / rng
+        print(f"CLIP unpool p={p}: target {tgt.item():.6f} (ref {float(gold[f'p{p}.target'][0]):.6f}), map cosine {cos:.8f}, "
+              f"max-abs/range {mar:.2e} (vs fp64 {mar64:.2e})")
+        assert abs(tgt.item() - float(gold[f"p{p}.target"][0])) <= 2e-3 * max(abs(float(gold[f"p{p}.target"][0])), 1e-2)
+        assert cos >= 0.999 and min(mar, mar64) <= 1e-3

@@ -259,3 +259,28 @@ def test_localisation_scores_known_answers(golden_dir, name):
     got = OR.localisation_scores(_t(kat[name + ".attr"]), cell, smooth, bool(neg))
     assert torch.equal(got, _t(kat[name + ".scores"]))
     assert torch.allclose(got.sum(1)[got.sum(1) > 0], torch.ones(1))          # fractions of the positive evidence
+
+
+def test_clip_unpool_text_localisation_golden(golden_dir):
+    """attn_unpool head + text-localisation target: oracle vs the reference run stored in the golden."""
+    base = np.load(os.path.join(golden_dir, "clip_rn50_b2.npz"))
+    gold = np.load(os.path.join(golden_dir, "clip_rn50_unpool_b1.npz"))
+    sd = synth.synth_state_dict(OR.clip_rn_state_shapes(attn_unpool=True), int(gold["seed"]))
+    off = 0
+    for k, n in zip(base["bn_keys"].tolist(), base["bn_sizes"].tolist()):
+        sd[k] = torch.from_numpy(base["bn_var"][off:off + n].copy()); off += n
+    x6 = synth.to_bcos_input(base["images_u8"][:1])
+    zw = OR.clip_seed_direction(1024, int(gold["seed"])).unsqueeze(1)
+    om = OR.OracleCLIPResNet(sd)
+    assert om.unpool
+    xb = x6.clone().requires_grad_(True)
+    tok = om.forward(xb, detach=True)
+    assert tok.shape == (49, 1, 1024) and torch.allclose(tok.norm(dim=-1), torch.ones(49, 1), atol=1e-5)
+    assert ((tok.detach() - _t(gold["tokens"])).abs().max() / _t(gold["tokens"]).abs().max()).item() < 1e-5
+    for p in (1, 2, 0):
+        tgt = OR.text_localisation_target(tok, zw, True, p)
+        (g,) = torch.autograd.grad(tgt.sum(), [xb], retain_graph=True)
+        cmap = (x6 * g).sum(1)[0]
+        ref = _t(gold[f"p{p}.contribution_map"])
+        assert abs(tgt.item() - float(gold[f"p{p}.target"][0])) < 1e-6
+        assert ((cmap - ref).abs().max() / ref.abs().max()).item() < 1e-4, p
