@@ -72,3 +72,30 @@ def test_split_planes_reconstruct():
         pl = P.split_planes(x, planes, torch.bfloat16)
         rec = sum(p.float() for p in pl)
         assert ((rec - x).abs() / x.abs()).max() <= tol
+
+
+def test_released_checkpoint_formats(tmp_path):
+    """Lightning `last.ckpt` (with EMA copy) and stripped `.pth` files of the reference load into the plan
+    under the reference's key names; a checkpoint of another architecture is refused with the list of mismatches."""
+    from bcos_b200 import checkpoint as C
+    shapes = resnet_state_shapes("resnet18")
+    sd = synth.synth_state_dict(shapes, 0)
+    ema = {k: (v * 0.5 if v.is_floating_point() else v) for k, v in sd.items()}
+    pl = {"epoch": 89, "state_dict": {**{"model." + k: v for k, v in sd.items()}, **{"ema.module." + k: v for k, v in ema.items()},
+                                      "criterion.off_label": torch.zeros(1)}}
+    torch.save(pl, tmp_path / "last.ckpt")
+    torch.save(sd, tmp_path / "stripped.pth")
+    a = C.load_state_dict_file(tmp_path / "last.ckpt")
+    b = C.load_state_dict_file(tmp_path / "stripped.pth")
+    e = C.load_state_dict_file(tmp_path / "last.ckpt", ema=True)
+    assert set(a) == set(b) == set(e) == set(sd)
+    k = "model.layer1.0.conv1.linear.weight"
+    assert torch.equal(a[k], sd[k]) and torch.equal(b[k], sd[k]) and torch.equal(e[k], sd[k] * 0.5)
+    C.check_state_dict(a, shapes)
+    with pytest.raises(ValueError, match="does not match the architecture"):
+        C.check_state_dict(a, resnet_state_shapes("resnet50"))
+    with pytest.raises(ValueError):
+        C.load_state_dict_file(tmp_path / "stripped.pth", ema=True)
+    plan = C.resnet_plan_from_checkpoint("resnet18", tmp_path / "last.ckpt", 1, device="cpu", image_size=64)
+    ref = ResNetPlan("resnet18", sd, 1, device="cpu", image_size=64)
+    assert len(plan.fwd_ops) == len(ref.fwd_ops) and plan.num_launches() == ref.num_launches()
