@@ -353,3 +353,46 @@ def test_module_level_clip_unpool_text_localisation(bcosk_lib, golden_dir):
         # against the reference, or being at least as close to the exact result as the reference is
         floor = (ref - ref64).abs().max().item() / rng
         assert cos >= 0.999 and (mar <= 1e-3 or mar64 <= max(1e-3, floor)), (mar, mar64, floor)
+
+
+@pytest.mark.parametrize("shape,groups,centred", [((4, 64, 56, 56), 1, True), ((2, 128, 56, 56), 1, False),
+                                                  ((3, 96, 40, 40), 2, True), ((2, 8, 30, 30), 1, True)])
+def test_group_norm_large_groups_cluster_kernel(bcosk_lib, shape, groups, centred):
+    """Groups of >= 512 KB run on the thread-block-cluster kernel (chunk cached in shared memory, partial sums through
+    distributed shared memory; the second case has a tail that is re-read from L2, the last one is below the threshold and
+    stays on the one-CTA kernel) - same results as the oracle, forward and explanation backward."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(*shape, generator=g) * (torch.rand(shape[0], shape[1], 1, 1, generator=g) + 0.5) + 0.3
+    w = torch.rand(shape[1], generator=g) + 0.5
+    seed = torch.randn(*shape, generator=g)
+    xo = x.clone().requires_grad_(True)
+    yo = OR.group_norm_detachable(xo, groups, w, None, 1e-5, True, centred)
+    (go,) = torch.autograd.grad((yo * seed).sum(), [xo])
+    mod = (M.DetachableGroupNorm2d if centred else M.GroupNormUncentered2d)(groups, shape[1]).cuda()
+    mod.weight.data, mod.bias = w.cuda(), None
+    mod.set_explanation_mode(True)
+    xg = x.cuda().requires_grad_(True)
+    y = mod(xg)
+    (gx,) = torch.autograd.grad((y * seed.cuda()).sum(), [xg])
+    assert _rel(y.detach(), yo.detach().cuda()) < 2e-5 and _rel(gx, go.cuda()) < 2e-5
+
+
+@pytest.mark.parametrize("c", [24, 200, 300, 1100])
+@pytest.mark.parametrize("centred", [False, True])
+def test_position_norm_register_variants(bcosk_lib, c, centred):
+    """Every register-cache width of the position-norm kernel (C <= 64 / 256 / 1024) and the re-reading fallback."""
+    g = torch.Generator().manual_seed(c)
+    x = torch.randn(2, c, 9, 13, generator=g) + 0.2
+    w = torch.rand(c, generator=g) + 0.5
+    b = torch.randn(c, generator=g) * 0.1
+    seed = torch.randn(2, c, 9, 13, generator=g)
+    xo = x.clone().requires_grad_(True)
+    yo = OR.position_norm_detachable(xo, w, b, 1e-5, True, centred)
+    (go,) = torch.autograd.grad((yo * seed).sum(), [xo])
+    mod = (M.DetachablePositionNorm2d if centred else M.PositionNormUncentered2d)(c).cuda()
+    mod.weight.data, mod.bias.data = w.cuda(), b.cuda()
+    mod.set_explanation_mode(True)
+    xg = x.cuda().requires_grad_(True)
+    y = mod(xg)
+    (gx,) = torch.autograd.grad((y * seed.cuda()).sum(), [xg])
+    assert _rel(y.detach(), yo.detach().cuda()) < 2e-5 and _rel(gx, go.cuda()) < 2e-5
