@@ -101,11 +101,11 @@ template <typename T, typename SRC>
 __global__ void input_prep_s2d_kernel(const SRC* __restrict__ x, int nb, int h, int w, Norm6 nm, T* __restrict__ out,
                                       int cp, int planes, float* __restrict__ sq, int row_pitch, int img_pitch) {
   const int h2 = h >> 1, w2 = w >> 1;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)nb * h2 * w2) return;
-  const int s = (int)(idx % w2);
-  const int r = (int)((idx / w2) % h2);
-  const int img = (int)(idx / ((long long)w2 * h2));
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;        // 32-bit index math, the image on blockIdx.y
+  if (idx >= h2 * w2) return;
+  const int r = idx / w2;
+  const int s = idx - r * w2;
+  const int img = blockIdx.y;
   float v[24];  // channel (dy*2+dx)*6 + c
   load_patch6<SRC>(x, img, r, s, h, w, v);
   const size_t plane = (size_t)h * w;
@@ -561,12 +561,12 @@ __global__ void contrib_map_s2d_kernel(const float* __restrict__ g, const SRC* _
                                        int cp, InvStd6 is, float out_scale, float* __restrict__ cmap,
                                        float* __restrict__ grad6) {
   const int h2 = h >> 1, w2 = w >> 1;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)nb * h2 * w2) return;
-  const int s = (int)(idx % w2);
-  const int r = (int)((idx / w2) % h2);
-  const int img = (int)(idx / ((long long)w2 * h2));
-  const float4* gp = reinterpret_cast<const float4*>(g + (size_t)idx * cp);
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;        // 32-bit index math, the image on blockIdx.y
+  if (pix >= h2 * w2) return;
+  const int r = pix / w2;
+  const int s = pix - r * w2;
+  const int img = blockIdx.y;
+  const float4* gp = reinterpret_cast<const float4*>(g + ((size_t)img * h2 * w2 + pix) * cp);
   float gv[24];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
@@ -652,8 +652,9 @@ static int input_prep_impl(const SRC* x, int32_t nb, int32_t h, int32_t w, const
   if (h % 2 || w % 2 || cp < 24 || cp % 8) return set_error(BCOSK_EINVAL, "input_prep: need even h,w and cp>=24, cp%%8==0");
   Norm6 nm;
   for (int i = 0; i < 6; ++i) { nm.mean[i] = mean6[i]; nm.inv_std[i] = inv_std6[i]; }  // host pointers
-  const long long n = (long long)nb * (h / 2) * (w / 2);
-  BCOSK_DTYPE_SWITCH(dtype, input_prep_s2d_kernel<T, SRC><<<blocks_for(n, 256), 256, 0, S(stream)>>>(
+  if (nb < 1 || nb > 65535) return set_error(BCOSK_EINVAL, "input_prep: batch must be in [1, 65535]");
+  const dim3 grid((unsigned)(((h / 2) * (w / 2) + 255) / 256), (unsigned)nb);
+  BCOSK_DTYPE_SWITCH(dtype, input_prep_s2d_kernel<T, SRC><<<grid, 256, 0, S(stream)>>>(
       x, nb, h, w, nm, reinterpret_cast<T*>(out), cp, planes, sq, row_pitch, img_pitch);)
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
@@ -800,8 +801,9 @@ static int contrib_map_impl(const float* g, const SRC* x, int32_t nb, int32_t h,
   if (!g || !x || !cmap || !inv_std6 || cp < 24 || cp % 4) return set_error(BCOSK_EINVAL, "contrib_map: bad argument");
   InvStd6 is;
   for (int i = 0; i < 6; ++i) is.v[i] = inv_std6[i];
-  const long long n = (long long)nb * (h / 2) * (w / 2);
-  contrib_map_s2d_kernel<SRC><<<blocks_for(n, 256), 256, 0, S(stream)>>>(g, x, nb, h, w, cp, is, out_scale, cmap, grad6);
+  if (nb < 1 || nb > 65535) return set_error(BCOSK_EINVAL, "contrib_map: batch must be in [1, 65535]");
+  const dim3 grid((unsigned)(((h / 2) * (w / 2) + 255) / 256), (unsigned)nb);
+  contrib_map_s2d_kernel<SRC><<<grid, 256, 0, S(stream)>>>(g, x, nb, h, w, cp, is, out_scale, cmap, grad6);
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }

@@ -72,7 +72,7 @@ groupnorm_fwd_kernel(const float* __restrict__ x, int c, int hw, int groups, con
   if (VEC == 4) {
     const int hv = hw / 4;
     for (long long i = threadIdx.x; i < nv; i += GN_THREADS) {
-      const int ch = g * cg + (int)(i / hv);
+      const int ch = g * cg + (int)((unsigned)i / (unsigned)hv);
       const float ww = (w ? __ldg(w + ch) : 1.f) * r, bb = b ? __ldg(b + ch) : 0.f;
       float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
       v.x = fmaf(v.x - sub, ww, bb); v.y = fmaf(v.y - sub, ww, bb);
@@ -81,7 +81,7 @@ groupnorm_fwd_kernel(const float* __restrict__ x, int c, int hw, int groups, con
     }
   } else {
     for (long long i = threadIdx.x; i < nv; i += GN_THREADS) {
-      const int ch = g * cg + (int)(i / hw);
+      const int ch = g * cg + (int)((unsigned)i / (unsigned)hw);
       const float ww = (w ? __ldg(w + ch) : 1.f) * r, bb = b ? __ldg(b + ch) : 0.f;
       dst[i] = fmaf(__ldg(src + i) - sub, ww, bb);
     }
@@ -105,7 +105,7 @@ groupnorm_explain_bwd_kernel(const float* __restrict__ gy, int c, int hw, int gr
   if (centred) {
     float s = 0.f;
     for (long long i = threadIdx.x; i < nv; i += GN_THREADS) {
-      const float ww = w ? __ldg(w + g * cg + (int)(i / hv)) : 1.f;
+      const float ww = w ? __ldg(w + g * cg + (int)((unsigned)i / (unsigned)hv)) : 1.f;
       if (VEC == 4) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
         s = fmaf((v.x + v.y) + (v.z + v.w), ww, s);
@@ -117,7 +117,7 @@ groupnorm_explain_bwd_kernel(const float* __restrict__ gy, int c, int hw, int gr
   }
   const float r = __ldg(rstd + blockIdx.x);
   for (long long i = threadIdx.x; i < nv; i += GN_THREADS) {
-    const float ww = w ? __ldg(w + g * cg + (int)(i / hv)) : 1.f;
+    const float ww = w ? __ldg(w + g * cg + (int)((unsigned)i / (unsigned)hv)) : 1.f;
     if (VEC == 4) {
       float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
       v.x = (v.x * ww - m) * r; v.y = (v.y * ww - m) * r; v.z = (v.z * ww - m) * r; v.w = (v.w * ww - m) * r;
@@ -146,40 +146,54 @@ __device__ __forceinline__ float cluster_sum(float v, float* red, float* slot, c
 }
 
 // BWD == false: forward (mean, centred variance, write); BWD == true: explanation backward (x = gy, rstd read)
+// 32-bit element indices (the host keeps len < 2^31); the streaming pass issues GNC_UNROLL independent 16-byte loads per
+// thread before consuming them (one CTA per SM: the bytes in flight have to come from instruction-level parallelism).
+constexpr int GNC_THREADS = 1024;
+constexpr int GNC_UNROLL = 4;
+
+__device__ __forceinline__ float4 scale4(float4 v, float s) { v.x *= s; v.y *= s; v.z *= s; v.w *= s; return v; }
+
 template <bool BWD>
-__global__ void __launch_bounds__(GN_THREADS, 1)
+__global__ void __launch_bounds__(GNC_THREADS, 1)
 groupnorm_cluster_kernel(const float* __restrict__ x, int c, int hw, int groups, const float* __restrict__ w,
                          const float* __restrict__ b, float eps, int centred, float* __restrict__ y, float* __restrict__ rstd) {
   extern __shared__ float4 cache[];
-  __shared__ float red[GN_THREADS / 32];
+  __shared__ float red[GNC_THREADS / 32];
   __shared__ float slots[2];
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned S = cluster.num_blocks(), rank = cluster.block_rank();
-  const int grp = blockIdx.x / S;                       // (image, group)
-  const int cg_ = c / groups;
-  const int g = grp % groups;
-  const long long len = (long long)cg_ * hw;
-  const long long nv = len / 4 / S;                     // float4 per CTA
-  const long long v0 = (long long)rank * nv;            // first float4 of this CTA inside the group
-  const float4* src = reinterpret_cast<const float4*>(x + (long long)grp * len) + v0;
-  float4* dst = reinterpret_cast<float4*>(y + (long long)grp * len) + v0;
-  const long long ncache = nv < GNC_SMEM_FLOATS / 4 ? nv : GNC_SMEM_FLOATS / 4;
-  const int hv = hw / 4;
+  const unsigned grp = blockIdx.x / S;                  // (image, group)
+  const unsigned cg_ = (unsigned)(c / groups);
+  const unsigned g = grp % (unsigned)groups;
+  const unsigned len = cg_ * (unsigned)hw;
+  const unsigned nv = len / 4 / S;                      // float4 per CTA
+  const unsigned v0 = rank * nv;                        // first float4 of this CTA inside the group
+  const float4* src = reinterpret_cast<const float4*>(x + (size_t)grp * len) + v0;
+  float4* dst = reinterpret_cast<float4*>(y + (size_t)grp * len) + v0;
+  const unsigned ncache = nv < GNC_SMEM_FLOATS / 4 ? nv : GNC_SMEM_FLOATS / 4;
+  const unsigned hv = (unsigned)hw / 4;
+  const float* wg = w ? w + g * cg_ : nullptr;
   float s = 0.f;
-  for (long long i = threadIdx.x; i < nv; i += GN_THREADS) {
-    float4 v = __ldg(src + i);
-    if (BWD) {
-      const float ww = w ? __ldg(w + g * cg_ + (int)((v0 + i) / hv)) : 1.f;
-      v.x *= ww; v.y *= ww; v.z *= ww; v.w *= ww;
+  for (unsigned i0 = threadIdx.x; i0 < nv; i0 += GNC_THREADS * GNC_UNROLL) {
+    float4 v[GNC_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GNC_UNROLL; ++u) {
+      const unsigned i = i0 + u * GNC_THREADS;
+      v[u] = i < nv ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (i < ncache) cache[i] = v;
-    s += (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+    for (int u = 0; u < GNC_UNROLL; ++u) {
+      const unsigned i = i0 + u * GNC_THREADS;
+      if (BWD && wg != nullptr && i < nv) v[u] = scale4(v[u], __ldg(wg + (v0 + i) / hv));
+      if (i < ncache) cache[i] = v[u];
+      s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+    }
   }
   float mean = 0.f, r;
   if (!BWD || centred) mean = cluster_sum(s, red, &slots[0], cluster) / (float)len;
   if (!BWD) {
     float q = 0.f;
-    for (long long i = threadIdx.x; i < nv; i += GN_THREADS) {
+    for (unsigned i = threadIdx.x; i < nv; i += GNC_THREADS) {
       const float4 v = i < ncache ? cache[i] : __ldg(src + i);
       const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
       q = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, q))));
@@ -191,22 +205,19 @@ groupnorm_cluster_kernel(const float* __restrict__ x, int c, int hw, int groups,
     r = __ldg(rstd + grp);
   }
   const float sub = centred ? mean : 0.f;
-  for (long long i = threadIdx.x; i < nv; i += GN_THREADS) {
-    const int ch = g * cg_ + (int)((v0 + i) / hv);
+  for (unsigned i = threadIdx.x; i < nv; i += GNC_THREADS) {
+    const unsigned ch = (v0 + i) / hv;                  // channel inside the group
     float4 v;
     if (i < ncache) {
       v = cache[i];
     } else {
       v = __ldg(src + i);
-      if (BWD) {
-        const float ww = w ? __ldg(w + ch) : 1.f;
-        v.x *= ww; v.y *= ww; v.z *= ww; v.w *= ww;
-      }
+      if (BWD && wg != nullptr) v = scale4(v, __ldg(wg + ch));
     }
     if (BWD) {
       v.x = (v.x - sub) * r; v.y = (v.y - sub) * r; v.z = (v.z - sub) * r; v.w = (v.w - sub) * r;
     } else {
-      const float ww = (w ? __ldg(w + ch) : 1.f) * r, bb = b ? __ldg(b + ch) : 0.f;
+      const float ww = (wg ? __ldg(wg + ch) : 1.f) * r, bb = b ? __ldg(b + g * cg_ + ch) : 0.f;
       v.x = fmaf(v.x - sub, ww, bb); v.y = fmaf(v.y - sub, ww, bb);
       v.z = fmaf(v.z - sub, ww, bb); v.w = fmaf(v.w - sub, ww, bb);
     }
@@ -307,7 +318,8 @@ positionnorm_kernel(const float* __restrict__ x, int c, int hw, const float* __r
 template <bool BWD>
 static void launch_positionnorm(dim3 grid, dim3 block, cudaStream_t st, const float* x, int c, int hw, const float* w,
                                 const float* b, float eps, int centred, float* y, float* rstd) {
-  if (c <= 4 * PN_SLICES) positionnorm_kernel<BWD, 4><<<grid, block, 0, st>>>(x, c, hw, w, b, eps, centred, y, rstd);
+  if (BWD && !centred) positionnorm_kernel<BWD, 0><<<grid, block, 0, st>>>(x, c, hw, w, b, eps, centred, y, rstd);   // one streaming pass
+  else if (c <= 4 * PN_SLICES) positionnorm_kernel<BWD, 4><<<grid, block, 0, st>>>(x, c, hw, w, b, eps, centred, y, rstd);
   else if (c <= 16 * PN_SLICES) positionnorm_kernel<BWD, 16><<<grid, block, 0, st>>>(x, c, hw, w, b, eps, centred, y, rstd);
   else if (c <= 64 * PN_SLICES) positionnorm_kernel<BWD, 64><<<grid, block, 0, st>>>(x, c, hw, w, b, eps, centred, y, rstd);
   else positionnorm_kernel<BWD, 0><<<grid, block, 0, st>>>(x, c, hw, w, b, eps, centred, y, rstd);
@@ -327,7 +339,7 @@ static int launch_groupnorm_cluster(const float* x, int nb, int c, int hw, int g
                                     int centred, float* y, float* rstd, cudaStream_t st, bool* done) {
   *done = false;
   const long long len = (long long)(c / groups) * hw;
-  if (len * 4 < GNC_MIN_BYTES || hw % 4 != 0 || !aligned16(x) || !aligned16(y)) return BCOSK_OK;
+  if (len * 4 < GNC_MIN_BYTES || len >= (1LL << 31) || hw % 4 != 0 || !aligned16(x) || !aligned16(y)) return BCOSK_OK;
   int S = 1;
   while (S < 8 && len / S > GNC_SMEM_FLOATS) S *= 2;
   if (len % (4LL * S) != 0) return BCOSK_OK;
@@ -340,7 +352,7 @@ static int launch_groupnorm_cluster(const float* x, int nb, int c, int hw, int g
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((long long)nb * groups * S));
-  cfg.blockDim = dim3(GN_THREADS);
+  cfg.blockDim = dim3(GNC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -360,7 +372,8 @@ extern "C" int bcosk_groupnorm_fwd(const float* x, int32_t nb, int32_t c, int64_
                                    const float* b, float eps, int32_t centred, float* y, float* rstd, void* stream) {
   if (!x || !y || nb < 0 || c < 1 || hw < 1 || groups < 1) return set_error(BCOSK_EINVAL, "groupnorm_fwd: bad argument");
   if (c % groups != 0) return set_error(BCOSK_EINVAL, "groupnorm_fwd: channels %d not divisible by groups %d", c, groups);
-  if (hw > 0x7fffffffLL || (int64_t)nb * groups > 0x7fffffffLL) return set_error(BCOSK_EUNSUPPORTED, "groupnorm_fwd: too large");
+  if ((int64_t)(c / groups) * hw > 0x7fffffffLL || (int64_t)nb * groups > 0x7fffffffLL)
+    return set_error(BCOSK_EUNSUPPORTED, "groupnorm_fwd: too large");
   if (nb == 0) return BCOSK_OK;
   bool done = false;
   const int rc = launch_groupnorm_cluster<false>(x, nb, c, (int)hw, groups, w, b, eps, centred, y, rstd, S4(stream), &done);
@@ -378,7 +391,8 @@ extern "C" int bcosk_groupnorm_explain_bwd(const float* gy, int32_t nb, int32_t 
                                            const float* rstd, int32_t centred, float* gx, void* stream) {
   if (!gy || !gx || !rstd || nb < 0 || c < 1 || hw < 1 || groups < 1) return set_error(BCOSK_EINVAL, "groupnorm_explain_bwd: bad argument");
   if (c % groups != 0) return set_error(BCOSK_EINVAL, "groupnorm_explain_bwd: channels %d not divisible by groups %d", c, groups);
-  if (hw > 0x7fffffffLL || (int64_t)nb * groups > 0x7fffffffLL) return set_error(BCOSK_EUNSUPPORTED, "groupnorm_explain_bwd: too large");
+  if ((int64_t)(c / groups) * hw > 0x7fffffffLL || (int64_t)nb * groups > 0x7fffffffLL)
+    return set_error(BCOSK_EUNSUPPORTED, "groupnorm_explain_bwd: too large");
   if (nb == 0) return BCOSK_OK;
   bool done = false;
   const int rc = launch_groupnorm_cluster<true>(gy, nb, c, (int)hw, groups, w, nullptr, 0.f, centred, gx,
