@@ -130,10 +130,10 @@ groupnorm_explain_bwd_kernel(const float* __restrict__ gy, int c, int hw, int gr
 
 // ---------------------------------------------------------------- large groups: one thread-block CLUSTER per (image, group)
 // A group of several MB (GN-LayerNorm of a 256 x 56 x 56 map = 3.2 MB) read three times by ONE CTA streams from HBM three
-// times once all resident groups exceed L2.  Here the group is split over the S CTAs of a cluster (1 CTA per SM): every
+// times once all resident groups exceed L2.  Here the group is split over the S CTAs of a cluster (2 CTAs per SM): every
 // CTA keeps the head of its chunk in shared memory (GNC_SMEM_FLOATS), re-reads only the tail from L2, and the partial sums
 // are exchanged through distributed shared memory.  len % (4*S) == 0 and hw % 4 == 0 are required (host checks).
-constexpr int GNC_SMEM_FLOATS = 48 * 1024;      // 192 KB
+constexpr int GNC_SMEM_FLOATS = 24 * 1024;      // 96 KB: two CTAs per SM, so one CTA's streaming pass overlaps its neighbour's shared-memory passes
 
 __device__ __forceinline__ float cluster_sum(float v, float* red, float* slot, cg::cluster_group& cluster) {
   const float local = block_sum(v, red);
@@ -148,13 +148,13 @@ __device__ __forceinline__ float cluster_sum(float v, float* red, float* slot, c
 // BWD == false: forward (mean, centred variance, write); BWD == true: explanation backward (x = gy, rstd read)
 // 32-bit element indices (the host keeps len < 2^31); the streaming pass issues GNC_UNROLL independent 16-byte loads per
 // thread before consuming them (one CTA per SM: the bytes in flight have to come from instruction-level parallelism).
-constexpr int GNC_THREADS = 1024;
+constexpr int GNC_THREADS = 512;
 constexpr int GNC_UNROLL = 4;
 
 __device__ __forceinline__ float4 scale4(float4 v, float s) { v.x *= s; v.y *= s; v.z *= s; v.w *= s; return v; }
 
 template <bool BWD>
-__global__ void __launch_bounds__(GNC_THREADS, 1)
+__global__ void __launch_bounds__(GNC_THREADS, 2)
 groupnorm_cluster_kernel(const float* __restrict__ x, int c, int hw, int groups, const float* __restrict__ w,
                          const float* __restrict__ b, float eps, int centred, float* __restrict__ y, float* __restrict__ rstd) {
   extern __shared__ float4 cache[];
@@ -245,7 +245,7 @@ __device__ __forceinline__ float slice_sum(float v, float (*red)[33]) {
 // NC > 0: every thread keeps its NC = ceil(C / PN_SLICES) channel values in registers, so the tensor is read ONCE
 // (C <= 16*NC); NC == 0: any C, the column is re-read (from L1/L2) for every pass.
 template <bool BWD, int NC>
-__global__ void __launch_bounds__(32 * PN_SLICES)
+__global__ void __launch_bounds__(32 * PN_SLICES, NC <= 16 ? 3 : 1)
 positionnorm_kernel(const float* __restrict__ x, int c, int hw, const float* __restrict__ w, const float* __restrict__ b,
                     float eps, int centred, float* __restrict__ y, float* __restrict__ rstd) {
   __shared__ float red[PN_SLICES][33];

@@ -33,7 +33,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arch", default="resnet50")
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--planes", type=int, default=1, help="precision planes (1 = bf16 throughput mode)")
+    ap.add_argument("--planes", type=int, default=1, help="precision planes (1 = 16-bit throughput mode)")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
+                    help="operand format of the tensor-core launches (BASELINE names bf16; fp16 runs at the same rate)")
     ap.add_argument("--cpu-batch", type=int, default=32, help="images per CPU-baseline / reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default=None, help="write the per-launch timing table (JSON) here")
@@ -149,7 +151,8 @@ def main():
     bbuild.build()
 
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
-    plan = synthetic_resnet_plan(args.arch, B, planes=args.planes, dtype="bf16", device=f"cuda:{local_rank}", input_u8=True)
+    plan = synthetic_resnet_plan(args.arch, B, planes=args.planes, dtype=args.dtype, device=f"cuda:{local_rank}", input_u8=True,
+                                seed_scale=4096.0 if args.dtype == "fp16" else 1.0)
     imgs = torch.from_numpy(synth.synth_images_u8(min(B, 64), 224, 1000 + rank))
     imgs = imgs.repeat((B + imgs.shape[0] - 1) // imgs.shape[0], 1, 1, 1)[:B].contiguous()
     h_in = imgs.pin_memory()
@@ -242,7 +245,7 @@ def main():
     imgs_total = world * B * K
     res = {
         "metric": METRIC, "value": imgs_total / (ms_dev * 1e-3), "unit": "img/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "arch": args.arch, "image": 224, "batch_per_gpu": B, "precision_planes": args.planes,
                    "parallelism": f"batch-sharded x{world}, no collective", "weights": "random-init synthetic checkpoint, BN calibrated",

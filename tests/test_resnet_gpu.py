@@ -86,6 +86,41 @@ def test_golden_parity_mode(bcosk_lib, golden_dir, arch, batch):
     assert torch.equal(out2["logits"], out["logits"]) or torch.allclose(out2["logits"], out["logits"], rtol=1e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("arch,batch", [("resnet18", 8), ("resnet50", 4)])
+def test_golden_parity_fp16_two_planes(bcosk_lib, golden_dir, arch, batch):
+    """The cheapest mode that meets the whole contract: two fp16 planes (22 mantissa bits), fp32-faithful accumulation, the
+    explanation seed scaled by 4096 so that the 16-bit gradients stay in the normal range (the maps are divided by the same
+    factor).  Same launches as the three-bf16-plane mode with 3 instead of 6 operand segments."""
+    gold = np.load(os.path.join(golden_dir, f"{arch}_b{batch}.npz"))
+    sd = golden_state(arch, gold)
+    x6 = synth.to_bcos_input(gold["images_u8"])
+    plan = ResNetPlan(arch, sd, batch, planes=2, dtype="fp16", seed_scale=4096.0, device="cuda")
+    out = plan.explain(x6)
+    torch.cuda.synchronize()
+    m = OR.parity_metrics(out["logits"], out["contribution_map"], torch.from_numpy(gold["logits"]),
+                          torch.from_numpy(gold["contribution_map"]))
+    print(arch, "parity mode (fp16x2) vs reference golden:", m)
+    assert m["argmax_equal"] and m["logit_rel_err"] <= 2e-3 and m["map_cos_min"] >= 0.999
+    assert m["map_maxabs_over_range"] <= 1e-3            # strict, against the fp32 reference itself
+
+
+@pytest.mark.parametrize("arch,batch", [("resnet18", 8), ("resnet50", 4)])
+def test_golden_fp16_throughput_mode(bcosk_lib, golden_dir, arch, batch):
+    """One fp16 plane runs at the speed of one bf16 plane (bench.py --dtype fp16) and keeps argmax, logits (<= 2e-3) and the
+    map direction (cosine >= 0.998; 0.9989 on the random-init ResNet-50, 0.9999 on ResNet-18); the max-abs criterion
+    (1e-3 of the range) needs the second plane."""
+    gold = np.load(os.path.join(golden_dir, f"{arch}_b{batch}.npz"))
+    sd = golden_state(arch, gold)
+    x6 = synth.to_bcos_input(gold["images_u8"])
+    plan = ResNetPlan(arch, sd, batch, planes=1, dtype="fp16", seed_scale=4096.0, device="cuda")
+    out = plan.explain(x6)
+    torch.cuda.synchronize()
+    m = OR.parity_metrics(out["logits"], out["contribution_map"], torch.from_numpy(gold["logits"]),
+                          torch.from_numpy(gold["contribution_map"]))
+    print(f"REPORT {arch} fp16 x1 vs reference golden: {m}")
+    assert m["argmax_equal"] and m["logit_rel_err"] <= 2e-3 and m["map_cos_min"] >= 0.998
+
+
 @pytest.mark.parametrize("arch,batch,planes", [("resnet18", 8, 1), ("resnet18", 8, 2), ("resnet50", 4, 1), ("resnet50", 4, 2)])
 def test_golden_throughput_modes_report(bcosk_lib, golden_dir, arch, batch, planes):
     gold = np.load(os.path.join(golden_dir, f"{arch}_b{batch}.npz"))
