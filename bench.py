@@ -20,6 +20,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (printed at communicator creation when
+# NCCL_DEBUG is set) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "B-cos RN50 fwd+explain img/s @224 at 1/2/4/8 B200; BcosConv tensor-pipe % peak"
 WORKLOAD = "B-cosified ResNet-50 forward + explanation maps, batch 256 per GPU bf16, 1/2/4/8 B200"
