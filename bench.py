@@ -20,9 +20,31 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (printed at communicator creation when
-# NCCL_DEBUG is set) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line.  Native libraries print there too (NCCL's "NCCL version ..." banner at
+    communicator creation when NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the whole run and the
+    result line is written to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return out
+
+
+def _host_threads() -> int:
+    """Threads for the CPU arm: the physical cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to every rank;
+    the reference arm runs on rank 0 alone and takes all the cores."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False)
+        if phys:
+            n = min(n, phys)
+    except Exception:
+        pass
+    return max(1, n)
+
 
 METRIC = "B-cos RN50 fwd+explain img/s @224 at 1/2/4/8 B200; BcosConv tensor-pipe % peak"
 WORKLOAD = "B-cosified ResNet-50 forward + explanation maps, batch 256 per GPU bf16, 1/2/4/8 B200"
@@ -110,6 +132,8 @@ def cpu_reference_arm(args, steps, warmup):
     import bcos_oracle as OR
     from bcos_b200.models import resnet_state_shapes
     from bcos_b200.utils import synth
+    if torch.get_num_threads() < _host_threads():
+        torch.set_num_threads(_host_threads())
     sd = synth.synthetic_checkpoint(args.arch, resnet_state_shapes(args.arch))
     x6 = synth.to_bcos_input(synth.synth_images_u8(args.cpu_batch, 224, 7))
     model = OR.OracleResNet(args.arch, sd)
@@ -126,6 +150,7 @@ def cpu_reference_arm(args, steps, warmup):
 
 def main():
     args = parse_args()
+    real_stdout = _claim_stdout()
     from bcos_b200.utils import dist as D
     rank, local_rank, world = D.env_rank()
 
@@ -140,7 +165,7 @@ def main():
             "config": {"workload": WORKLOAD, "arch": args.arch, "image": 224, "batch_per_step": args.cpu_batch},
             "cpu_baseline": {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        }), file=real_stdout, flush=True)
         return
 
     import torch
@@ -285,7 +310,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         c = cpu_reference_arm(args, 16, 1)     # ~10 s of host work: 16 steps of 32 images
         res["cpu_baseline"] = {"value": c["value"], "unit": "img/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]}
-    print(json.dumps(res))
+    print(json.dumps(res), file=real_stdout, flush=True)
     D.shutdown()
 
 
