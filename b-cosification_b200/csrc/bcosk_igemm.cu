@@ -239,7 +239,7 @@ __device__ __forceinline__ void tile_store32(uint32_t tile, int r, int j, float 
 // One 32-column slice of one output row: everything after the accumulator is in registers.
 // Generic (scalar) form: any scale mode, precision planes, fp32 side tensors.
 template <int MODE, typename T>
-__device__ __noinline__ void epilogue_chunk_generic(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow, float inv_norm,
+__device__ __forceinline__ void epilogue_chunk_generic_inl(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow, float inv_norm,
                                                int64_t add_row, const float* s_alpha, const float* s_beta, int j, int c0,
                                                int ncols, float (&v)[32], float& sq_acc, const EpiTiles& tl, int row) {
   T* y16 = reinterpret_cast<T*>(p.y);
@@ -355,6 +355,16 @@ __device__ __noinline__ void epilogue_chunk_generic(const bcosk_igemm_params& p,
   }
 }
 
+
+// Out-of-line copy for the kernels where the generic form is only the fallback (keeps their register budget); the arrays
+// passed by reference live in local memory there.  The parity-mode (HP) kernels call the inline form: ncu showed more
+// local-memory than global-memory sectors in their launches (profiles/r01_parity_mode_ncu.md).
+template <int MODE, typename T>
+__device__ __noinline__ void epilogue_chunk_generic(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow, float inv_norm,
+                                               int64_t add_row, const float* s_alpha, const float* s_beta, int j, int c0,
+                                               int ncols, float (&v)[32], float& sq_acc, const EpiTiles& tl, int row) {
+  epilogue_chunk_generic_inl<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Fast form for the throughput mode (single 16-bit plane, B=2 or no scale): the math runs on float2 pairs with the
@@ -953,8 +963,8 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = acc[j * 32 + i];
-          epilogue_chunk_generic<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, min(32, p.n - c0), v,
-                                          sq_acc, tl, row);
+          epilogue_chunk_generic_inl<MODE, T>(p, ri, yrow, inv_norm, add_row, s_alpha, s_beta, j, c0, min(32, p.n - c0), v,
+                                              sq_acc, tl, row);
         }
       }
     } else {
