@@ -14,7 +14,8 @@ from typing import Dict, List, Tuple
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 HEADER = os.path.join(ROOT, "include", "bcosk.h")
-LIB_PATH = os.path.join(PKG, "libbcosk.so")
+# $BCOSK_LIB: an alternative build of the same sources (experiment variants compiled with -D knobs); never a fallback
+LIB_PATH = os.environ.get("BCOSK_LIB") or os.path.join(PKG, "libbcosk.so")
 
 _CT = {
     "int32_t": C.c_int32, "uint32_t": C.c_uint32, "int64_t": C.c_int64, "uint16_t": C.c_uint16,

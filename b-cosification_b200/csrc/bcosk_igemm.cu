@@ -45,6 +45,9 @@ constexpr int NUM_THREADS = 192;
 // LIGHT = 2: two slots and 4 CTAs per SM for forward launches whose K loop is ONE stage (K = 64).  Slot 0 is the stage and
 // afterwards the y tile; slot 1 holds the residual tile and the gain tile is staged over it - every thread reads its own
 // residual words before it writes the same words of the gain tile, so the alias is safe.
+#ifndef BCOSK_HP_CHUNK
+#define BCOSK_HP_CHUNK 1   // pipeline stages (64 K-elements each) accumulated by the tensor core before the epilogue warps drain them
+#endif
 template <int BN, bool HP = false, int LIGHT = 0> struct TileCfg {
   static constexpr int kStages = LIGHT == 2 ? 2 : (LIGHT ? 3 : ((BN == 128) ? BCOSK_BN128_STAGES : (BN == 256 ? BCOSK_BN256_STAGES : 4)));   // pipeline slots; the last may hold the input tile
   static constexpr int kMinBlocks = LIGHT == 2 ? BCOSK_LIGHT2_BLOCKS : (LIGHT ? 3 : (BN == 128 ? BCOSK_BN128_BLOCKS : ((BN < 128) ? 2 : BCOSK_BN256_BLOCKS)));
@@ -822,10 +825,13 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (HP) {
           // fresh accumulator per stage: the tensor core truncates when it aligns addends to a large running sum,
           // so long dot products are summed in registers (round-to-nearest fp32) by the epilogue warps instead
-          const int buf = it & 1;
-          mbar_wait(&acc_empty_bar[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+          // (BCOSK_HP_CHUNK consecutive stages may share one accumulator: experiment knob, 1 in the shipped library)
+          const int d = it / BCOSK_HP_CHUNK, buf = d & 1;
+          if (it % BCOSK_HP_CHUNK == 0) {
+            mbar_wait(&acc_empty_bar[buf], (((uint32_t)d >> 1) & 1u) ^ 1u);
+            accumulate = 0;
+          }
           tmem_d = tmem_base + (uint32_t)(buf * BN);
-          accumulate = 0;
         }
         uint8_t* slot = smem + stage * Cfg::kSlotBytes;
         {
@@ -860,7 +866,8 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (cl > 1) umma_commit_mc(&empty_bar[stage], cl_mask);
         else umma_commit(&empty_bar[stage]);
         BCOSK_TACC2(3);
-        if (HP) umma_commit(&acc_full_bar[it & 1]);
+        if (HP && (it % BCOSK_HP_CHUNK == BCOSK_HP_CHUNK - 1 || it == num_iters - 1))
+          umma_commit(&acc_full_bar[(it / BCOSK_HP_CHUNK) & 1]);
         if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
       if (!HP) umma_commit(tmem_full_bar);  // accumulator complete
@@ -940,7 +947,8 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       float acc[BN];
 #pragma unroll
       for (int i = 0; i < BN; ++i) acc[i] = 0.f;
-      for (int it = 0; it < num_iters; ++it) {
+      const int num_drains = (num_iters + BCOSK_HP_CHUNK - 1) / BCOSK_HP_CHUNK;
+      for (int it = 0; it < num_drains; ++it) {
         const int buf = it & 1;
         mbar_wait(&acc_full_bar[buf], ((uint32_t)it >> 1) & 1u);
         tc_fence_after();
