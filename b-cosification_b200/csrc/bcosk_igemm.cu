@@ -944,6 +944,29 @@ bcosk_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     tl.out2 = (Cfg::kTmaEpilogue && aux.tma_out2) ? smem_u32(smem + (kSwapOut ? 0 : Cfg::kSlotBytes)) : 0u;
 
     if constexpr (HP) {
+      // The generic epilogue reads this row's side tensors (residual / extra gradient / gains) with plain loads after the
+      // last drain; with 12 warps per SM nothing hides their DRAM latency (ncu: long-scoreboard stalls).  Pull the lines
+      // into L2 now, while the K loop runs.
+      if (ri.valid) {
+        const int tile_cols = min(BN, p.n - n0);
+        auto prefetch_row = [&](const void* base, size_t elem_off, int elem_bytes) {
+          const char* b = reinterpret_cast<const char*>(base) + elem_off * (size_t)elem_bytes;
+          const char* e = b + (size_t)tile_cols * elem_bytes;
+          for (const char* q = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(b) & ~(uintptr_t)127); q < e; q += 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        };
+        if (MODE == BCOSK_MODE_FWD) {
+          if (p.res != nullptr && tl.in == 0)
+            for (int pl = 0; pl < p.res_planes; ++pl)
+              prefetch_row(p.res, (size_t)ri.m * p.res_ld + n0 + (size_t)pl * p.res_plane_stride, 2);
+        } else {
+          if (add_row >= 0)
+            for (int pl = 0; pl < p.add_planes; ++pl)
+              prefetch_row(p.add, (size_t)add_row * p.add_ld + n0 + (size_t)pl * p.add_plane_stride, 2);
+          if (p.mul1 != nullptr && tl.in == 0) prefetch_row(p.mul1, (size_t)ri.m * p.mul1_ld + n0, p.mul1_f32 ? 4 : 2);
+          if (p.out2 != nullptr && p.mul2 != nullptr) prefetch_row(p.mul2, (size_t)ri.m * p.mul2_ld + n0, p.mul2_f32 ? 4 : 2);
+        }
+      }
       float acc[BN];
 #pragma unroll
       for (int i = 0; i < BN; ++i) acc[i] = 0.f;
