@@ -69,6 +69,7 @@ class IgemmOp:
     algo_flops: float = 0.0
     a_dense_frac: float = 1.0
     hp_accum: bool = False           # per-stage TMEM accumulators summed in registers (parity mode)
+    hp_chunk: int = 0                # include/bcosk.h `hp_chunk`: K stages per TMEM accumulation of the leading segment (0 = default)
     sched: int = 0                   # include/bcosk.h `sched`: 0 default, 1 per tile, 2 persistent, 3 persistent row blocks
     flat: bool = False               # include/bcosk.h `a_flat`: `a` is the interior view of a zero-bordered buffer
     side_mapped: bool = False        # include/bcosk.h `side_mapped`: mul1 / out2 / ... follow the mapped output row
@@ -208,6 +209,7 @@ class IgemmOp:
             p.mask2 = self.mask2.data_ptr()
             p.mask2_ld = self.mask2.shape[-1]
         p.hp_accum = int(self.hp_accum)
+        p.hp_chunk = int(self.hp_chunk)
         p.sched = int(self.sched)
         p.side_mapped = int(self.side_mapped)
         p.set_ptr("inv_norm_out", self.inv_norm_out)

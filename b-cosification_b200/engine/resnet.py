@@ -40,9 +40,9 @@ class ResNetPlan(PlanBase):
                  bn_eps: float = 1e-5, mean=IMAGENET_MEAN_ADDINVERSE, std=IMAGENET_STD_ADDINVERSE,
                  logit_bias: Optional[float] = -math.log(1000 - 1), logit_temperature: Optional[float] = None,
                  seed_scale: float = 1.0, stem_kch: int = 32, input_u8: bool = False, want_rgba: bool = False,
-                 rgba_smooth: int = 15, rgba_percentile: float = 99.5):
+                 rgba_smooth: int = 15, rgba_percentile: float = 99.5, explain_planes: Optional[int] = None):
         super().__init__(batch, planes=planes, dtype=dtype, device=device, explain=explain, b=b, bn_eps=bn_eps,
-                         state_dict=state_dict)
+                         state_dict=state_dict, explain_planes=explain_planes)
         self.arch = arch
         self.kind, self.layers = RESNET_ARCH[arch]
         self.mean, self.std = tuple(mean), tuple(std)
@@ -125,7 +125,7 @@ class ResNetPlan(PlanBase):
                                           self.logit_bias, self.logits, self.pred))
 
     def _build_explain(self, want_grad6: bool) -> None:
-        nb, pl = self.nb, self.planes
+        nb, pl = self.nb, self.bplanes
         for blk in self.blocks:
             for j, r in enumerate(blk.convs):
                 # convs after the first get their gradient from a plain data-gradient epilogue (no shortcut terms):
@@ -135,9 +135,10 @@ class ResNetPlan(PlanBase):
                 self._alloc_ghat(blk.ds)
                 blk.side = blk.ds.ghat
             else:
-                blk.side = self._zeros(*blk.y.t.shape)
+                blk.side = self._zeros(nb, blk.y.hw[0], blk.y.hw[1], pl * blk.y.c)
         self._alloc_ghat(self.stem)
-        if self.stem_flat:     # the transposed 4x4 gather pads 1 before / 2 after
+        self.stem_flat_bwd = self.flat_stem and pl == 1 and not self.bwd_hp
+        if self.stem_flat_bwd:     # the transposed 4x4 gather pads 1 before / 2 after
             self.stem.ghat = self._padded(nb, self.stem.out_hw[0], self.stem.out_hw[1], self.stem.cout, 1, 2)
         last = self.blocks[-1]
         assert last.ds is None, "classifier seed kernel expects an identity shortcut in the last block"
@@ -149,7 +150,7 @@ class ResNetPlan(PlanBase):
                                        last.convs[-1].ghat.view(nb * self.npix, pl * c_last), last.mask,
                                        last.side.view(nb * self.npix, pl * c_last), pl, self.dt_code))
         # ---- blocks in reverse
-        self.g_pool = self._zeros(*self.pool_out.t.shape)
+        self.g_pool = self._zeros(nb, self.pool_out.hw[0], self.pool_out.hw[1], pl * self.pool_out.c)
         for bi in range(len(self.blocks) - 1, -1, -1):
             blk = self.blocks[bi]
             convs = blk.convs
@@ -159,7 +160,7 @@ class ResNetPlan(PlanBase):
             add, add_stride = blk.side, 1
             if blk.ds is not None:
                 dds = self._zeros(nb, blk.ds.out_hw[0], blk.ds.out_hw[1], pl * blk.ds.cin_phys) if blk.ds.stride > 1 \
-                    else self._zeros(*blk.x.t.shape)
+                    else self._zeros(nb, blk.x.hw[0], blk.x.hw[1], pl * blk.x.c)
                 self._dgrad(blk.ds, y=dds)
                 add, add_stride = dds, blk.ds.stride
             if bi > 0:
@@ -173,7 +174,7 @@ class ResNetPlan(PlanBase):
         self.bwd_ops.append(O.AvgPoolBwdMulOp("pool.bwd", self.g_pool, 64, pl, 3, 2, 1, m1, self.stem.ghat, self.dt_code, m1s))
         h2 = self.size // 2
         self.g0 = self._zeros(nb, h2, h2, self.stem_cp, dtype=torch.float32)
-        self._dgrad(self.stem, y=self.g0, y_f32=True, kch=64, flat=self.stem_flat)
+        self._dgrad(self.stem, y=self.g0, y_f32=True, kch=64, flat=self.stem_flat_bwd)
         self.cmap = self._zeros(nb, self.size, self.size, dtype=torch.float32)
         self.grad6 = self._zeros(nb, 6, self.size, self.size, dtype=torch.float32) if want_grad6 else None
         self.bwd_ops.append(O.ContribMapOp("contrib_map", self.g0, self.x_in, self.stem_cp, self.inv_std,

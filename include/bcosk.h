@@ -121,6 +121,10 @@ typedef struct bcosk_igemm_params {
    *      The tensor core truncates when aligning addends to a large running sum (measured: relative error ~K*2^-26,
    *      biased), which random-init deep B-cos nets amplify 10^2-10^3 x. */
   int32_t hp_accum;
+  /* hp_accum only: K stages (64 deep each) of the leading operand segment (a-plane 0 x b-plane 0) that one TMEM
+   *      accumulation covers before the epilogue warps add it to their registers; 0 = library default
+   *      (bcosk_set_hp_chunk, initially 1).  All cross-term segments (a0 b1, a1 b0, ...) share one further accumulation. */
+  int32_t hp_chunk;
   /* ---- schedule of a block_n == 64 launch (ignored otherwise and with hp_accum; results do not depend on it):
    *      0 = library default (see bcosk_set_persistent / bcosk_set_light), 1 = one CTA per tile,
    *      2 = persistent CTAs, tiles strided over the grid, 3 = persistent CTAs, each walks all n tiles of one
@@ -159,6 +163,14 @@ typedef struct bcosk_igemm_params {
 } bcosk_igemm_params;
 
 int bcosk_igemm(const bcosk_igemm_params* p, void* stream);
+
+/* Parity-mode (hp_accum) launches: default for bcosk_igemm_params.hp_chunk == 0 (>= 1).  Returns the previous setting. */
+int bcosk_set_hp_chunk(int32_t stages);
+/* Parity-mode launches, A/B measurement switches (results are identical).  Bit 0 (default 1): epilogue tensors move as TMA
+ * boxes through shared memory instead of per-row 16-byte accesses.  Bit 1 (default 0): the generic epilogue arithmetic runs
+ * even where the packed two-plane form applies.  Bits 8..: when non-zero, 1 + the number of K stages up to which the input
+ * boxes are fetched at kernel start (default 4) instead of after the last MMA.  Returns the previous setting. */
+int bcosk_set_hp_boxes(int32_t enabled);
 
 /* Scheduling switch for A/B measurements: 1 = launches with block_n 64 (the bandwidth-bound ones) run on the persistent
  * one-CTA-per-SM kernel, 0 (default) = one CTA per tile everywhere.  Returns the previous setting.  Results are identical. */
