@@ -9,7 +9,8 @@
 //     2^-11 (fp16) / 2^-8 (bf16) of the leading one.  The tensor core truncates when it aligns an addend to a large
 //     running sum (measured: relative error ~ K 2^-26, biased), so the LEADING segment is accumulated `chunk` K stages at a
 //     time into one of two TMEM accumulators and the epilogue warps sum those partials in registers with round-to-nearest
-//     fp32 adds; all cross-term segments share ONE further accumulation (their truncation error is below 2^-34 of the result).
+//     fp32 adds; with fp16 planes all cross-term segments run back to back in ONE further accumulation (its truncation error
+//     is below 2^-34 of the result), with bf16 planes they are chunked like the leading segment.
 //   * Epilogue I/O goes through shared memory and TMA like the throughput kernels: every plane of a 16-bit tensor is a
 //     [128 rows][64 columns] SWIZZLE_128B box at a column offset of the same 2-D tensor, fp32 side tensors (saved gain /
 //     producer gain) are [128][32]-float boxes.  Output boxes are staged in the drained pipeline ring (or over the input
@@ -42,7 +43,8 @@ constexpr int SLOT_BYTES = A_BYTES + B_BYTES;  // 24 KB
 constexpr int BOX_BYTES = BM * 128;            // one [128 rows][128 bytes] swizzled box
 constexpr int THREADS = 320;
 constexpr int MAX_STAGES = 8;
-constexpr int TMEM_COLS = 2 * BN;
+constexpr int TMEM_COLS = 4 * BN;             // two ping-pong partial accumulators + the cross-term accumulator (power of two)
+constexpr int PAIR_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // paired stage: [A plane 0 | A plane 1 | B plane 0 | B plane 1] = 48 KB
 constexpr int TAIL_BYTES = 256 + 2 * BN * 4 + BM * 4;   // barriers | alpha, beta | sum-of-squares exchange
 constexpr int MAX_SMEM = 115712;               // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
 }  // namespace hp
@@ -50,6 +52,10 @@ constexpr int MAX_SMEM = 115712;               // two CTAs per SM: (228 KB - 2 x
 struct HpAux {
   int stages;        // ring slots (2..8)
   int chunk;         // K stages of segment 0 summed by the tensor core before the epilogue warps take over
+  int xchunk;        // the same for the cross-term segments (all of them back to back)
+  int paired;        // two-plane operands: one stage carries both planes of A and B for one (tap, channel chunk) and feeds three
+                     // MMA groups (a0 b0 -> partial accumulator, a0 b1 + a1 b0 -> cross-term accumulator): 48 KB per 3 groups
+                     // instead of 72 KB (a0 is fetched once, not twice)
   int in16_planes;   // forward: residual planes / explain: extra-gradient planes fetched as boxes (0 = per-row loads)
   int in32;          // explain: fp32 producer gain fetched as boxes
   int early_in;      // input boxes live outside the ring and are fetched at kernel start (else after the last MMA)
@@ -233,8 +239,8 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   const int stages = aux.stages;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + aux.tail);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* acc_full_bar = empty_bar + MAX_STAGES;   // [2] partial accumulator complete
-  uint64_t* acc_empty_bar = acc_full_bar + 2;        // [2] partial accumulator drained
+  uint64_t* acc_full_bar = empty_bar + MAX_STAGES;   // [3] partial accumulator complete; [2] = cross-term accumulator (paired mode)
+  uint64_t* acc_empty_bar = acc_full_bar + 3;        // [2] partial accumulator drained
   uint64_t* mma_done_bar = acc_empty_bar + 2;        // every MMA has read its operands: the ring is free
   uint64_t* in_bar = mma_done_bar + 1;               // epilogue input boxes landed
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(in_bar + 1);
@@ -253,9 +259,9 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
   const int chunks_per_stage = STAGE_K / p.kch;                                  // 1 (kch = 64) or 2 (kch = 32)
   const int seg_iters = (p.num_taps * p.chunks_per_tap) / chunks_per_stage;      // K stages per segment (host: divisible)
-  const int num_iters = p.num_segs * seg_iters;
+  const int num_iters = aux.paired ? seg_iters : p.num_segs * seg_iters;    // paired: one stage per (tap, chunk), both planes
   const int main_drains = (seg_iters + aux.chunk - 1) / aux.chunk;
-  const int num_drains = main_drains + (p.num_segs > 1 ? 1 : 0);
+  const int num_drains = aux.paired ? main_drains : main_drains + (num_iters - seg_iters + aux.xchunk - 1) / aux.xchunk;
   const int boxes32 = min(2, (p.n - n0 + 31) >> 5);                              // fp32 boxes of this tile inside the tensor
   const bool any_in = aux.in16_planes != 0 || aux.in32 != 0;
 
@@ -270,6 +276,7 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_init(&acc_full_bar[s], 1);
       mbar_init(&acc_empty_bar[s], 8);   // one arrival per epilogue warp
     }
+    mbar_init(&acc_full_bar[2], 1);
     mbar_init(mma_done_bar, 1);
     mbar_init(in_bar, 1);
     fence_barrier_init();
@@ -318,6 +325,23 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       int seg = 0, tap = 0, kc = 0;
+      if (aux.paired) {
+        // segments are {a0 b0, a0 b1, a1 b0} (engine/pack.py SEGMENTS[2]): stage = [a0 | a1 | b0 | b1] of one (tap, chunk)
+        const int seg_cols = p.num_taps * p.chunks_per_tap * p.kch;      // B columns per segment
+        for (int it = 0; it < num_iters; ++it) {
+          uint8_t* slot = smem + stage * PAIR_BYTES;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], PAIR_BYTES);
+          tma_load_im2col_4d(slot, &tmap_a, &full_bar[stage], p.seg_a_choff[0] + kc * p.kch, base_w, base_h, img, p.tap_off_w[tap],
+                             p.tap_off_h[tap]);
+          tma_load_im2col_4d(slot + A_BYTES, &tmap_a, &full_bar[stage], p.seg_a_choff[2] + kc * p.kch, base_w, base_h, img,
+                             p.tap_off_w[tap], p.tap_off_h[tap]);
+          tma_load_2d(slot + 2 * A_BYTES, &tmap_b, &full_bar[stage], it * p.kch, n0);
+          tma_load_2d(slot + 2 * A_BYTES + B_BYTES, &tmap_b, &full_bar[stage], seg_cols + it * p.kch, n0);
+          if (++kc == p.chunks_per_tap) { kc = 0; ++tap; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      } else
       for (int it = 0; it < num_iters; ++it) {
         uint8_t* slot = smem + stage * SLOT_BYTES;
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -353,9 +377,53 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       uint32_t phase = 0;
       uint32_t accumulate = 0;
       int d = 0;                        // accumulation (drain) index
+      if (aux.paired) {
+        const uint64_t pair16 = PAIR_BYTES >> 4;
+        const uint32_t tmem_x = tmem_base + 2 * BN;      // cross-term accumulator
+        for (int it = 0; it < num_iters; ++it) {
+          const bool first = it % aux.chunk == 0;
+          const bool last = it % aux.chunk == aux.chunk - 1 || it == num_iters - 1;
+          const uint32_t buf = (uint32_t)d & 1u;
+          if (first) {
+            mbar_wait(&acc_empty_bar[buf], (((uint32_t)d >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+          }
+          const uint32_t tmem_d = tmem_base + buf * BN;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da0 = da_stage0 + (uint64_t)stage * pair16;
+          const uint64_t da1 = da0 + (A_BYTES >> 4);
+          const uint64_t db0 = da0 + (2 * A_BYTES >> 4);
+          const uint64_t db1 = db0 + (B_BYTES >> 4);
+          // a0 b0 -> partial accumulator of the leading term
+          umma_f16(tmem_d, da0, db0, idesc, first ? 0u : 1u);
+          umma_f16(tmem_d, da0 + 2, db0 + 2, idesc, 1);
+          umma_f16(tmem_d, da0 + 4, db0 + 4, idesc, 1);
+          umma_f16(tmem_d, da0 + 6, db0 + 6, idesc, 1);
+          if (last) {
+            umma_commit(&acc_full_bar[buf]);
+            ++d;
+          }
+          // a0 b1 + a1 b0 -> cross-term accumulator (one accumulation over all of K)
+          umma_f16(tmem_x, da0, db1, idesc, it == 0 ? 0u : 1u);
+          umma_f16(tmem_x, da0 + 2, db1 + 2, idesc, 1);
+          umma_f16(tmem_x, da0 + 4, db1 + 4, idesc, 1);
+          umma_f16(tmem_x, da0 + 6, db1 + 6, idesc, 1);
+          umma_f16(tmem_x, da1, db0, idesc, 1);
+          umma_f16(tmem_x, da1 + 2, db0 + 2, idesc, 1);
+          umma_f16(tmem_x, da1 + 4, db0 + 4, idesc, 1);
+          umma_f16(tmem_x, da1 + 6, db0 + 6, idesc, 1);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full_bar[2]);
+        umma_commit(mma_done_bar);
+      } else {
       for (int it = 0; it < num_iters; ++it) {
-        const bool first = it < seg_iters ? (it % aux.chunk == 0) : (it == seg_iters);
-        const bool last = it < seg_iters ? (it % aux.chunk == aux.chunk - 1 || it == seg_iters - 1) : (it == num_iters - 1);
+        const int xi = it - seg_iters;   // position among the cross-term stages
+        const bool first = it < seg_iters ? (it % aux.chunk == 0) : (xi % aux.xchunk == 0);
+        const bool last = it < seg_iters ? (it % aux.chunk == aux.chunk - 1 || it == seg_iters - 1)
+                                         : (xi % aux.xchunk == aux.xchunk - 1 || it == num_iters - 1);
         const uint32_t buf = (uint32_t)d & 1u;
         if (first) {
           mbar_wait(&acc_empty_bar[buf], (((uint32_t)d >> 1) & 1u) ^ 1u);
@@ -392,6 +460,7 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
       umma_commit(mma_done_bar);
+      }
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
@@ -488,6 +557,16 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty_bar[buf]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(raw[i]);
+    }
+    if (aux.paired) {
+      mbar_wait(&acc_full_bar[2], 0);
+      tc_fence_after();
+      uint32_t raw[32];
+      tmem_ld_32x32(taddr + 2 * BN, raw);
+      tmem_ld_wait();
+      tc_fence_before();
 #pragma unroll
       for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(raw[i]);
     }
@@ -733,6 +812,7 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 // host side
 // ---------------------------------------------------------------------------------------------
 static int g_hp_chunk = 2;       // default K stages of the leading segment per TMEM accumulation (bcosk_set_hp_chunk)
+static int g_hp_xchunk = 0;      // experiment override of the cross-term accumulation length (0 = by operand format)
 static int g_hp_stage_boxes = 1; // 0 = per-row epilogue I/O everywhere (A/B measurements)
 static int g_hp_early_iters = 4; // K loops of at most this many stages fetch their input boxes at kernel start
 
@@ -767,6 +847,11 @@ static int launch_hp_mode(const bcosk_igemm_params& p, cudaStream_t st) {
   HpAux aux;
   memset(&aux, 0, sizeof(aux));
   aux.chunk = p.hp_chunk > 0 ? p.hp_chunk : g_hp_chunk;
+  // cross terms are 2^-11 of the leading segment with fp16 planes: one accumulation over all of them adds a truncation
+  // error below 2^-34 of the result.  bf16 planes (2^-8, and second-order terms at 2^-16 on top of first-order ones) keep
+  // the chunk length of the leading segment.
+  aux.xchunk = p.dtype == BCOSK_DTYPE_F16 ? (1 << 20) : aux.chunk;
+  if (g_hp_xchunk > 0) aux.xchunk = g_hp_xchunk;
   if (g_hp_stage_boxes & 1) {
     if (!p.y_f32 && dense_out && planes_ok(p.y_planes) && p.y_planes <= 3 && map16(&mout1, p.y, p.y_ld, M)) aux.out1_planes = p.y_planes;
     if (MODE == BCOSK_MODE_FWD) {
@@ -788,7 +873,13 @@ static int launch_hp_mode(const bcosk_igemm_params& p, cudaStream_t st) {
   //      replaces.  Inputs: next to the ring and fetched at kernel start when the K loop is short, else into the ring
   //      after the last MMA.  When the boxes do not fit two CTAs per SM, tensors drop back to per-row accesses one by one.
   const int tail_bytes = MODE == BCOSK_MODE_FWD ? TAIL_BYTES : 256;
-  const int iters = p.num_segs * p.num_taps * p.chunks_per_tap / (STAGE_K / p.kch);
+  // two-plane operands in the canonical segment order {a0 b0, a0 b1, a1 b0}: paired stages (a0 fetched once)
+  aux.paired = (g_hp_stage_boxes & 4) == 0 && p.kch == 64 && p.num_segs == 3 && p.seg_b_plane[0] == 0 && p.seg_b_plane[1] == 1 &&
+               p.seg_b_plane[2] == 0 && p.seg_a_choff[0] == p.seg_a_choff[1] && p.seg_a_choff[2] != p.seg_a_choff[0];
+  const int slot_b = aux.paired ? PAIR_BYTES : SLOT_BYTES;
+  const int max_ring = aux.paired ? 2 : 4;        // ring slots that fit two CTAs per SM
+  const int iters = aux.paired ? p.num_taps * p.chunks_per_tap : p.num_segs * p.num_taps * p.chunks_per_tap / (STAGE_K / p.kch);
+  const int early_iters = aux.paired ? (g_hp_early_iters + 2) / 3 : g_hp_early_iters;
   int stages = 0, extra = 0;
   auto place = [&]() -> bool {
     const int in16_b = aux.in16_planes * BOX_BYTES, in32_b = aux.in32 ? 2 * BOX_BYTES : 0;
@@ -797,19 +888,19 @@ static int launch_hp_mode(const bcosk_igemm_params& p, cudaStream_t st) {
                                           : (aux.out2_kind == 2 ? aux.out2_planes * BOX_BYTES : (aux.out2_kind == 3 ? BOX_BYTES : 0));
     aux.early_in = 0;
     extra = 0;
-    if ((in16_b || in32_b) && iters <= g_hp_early_iters) {
+    if ((in16_b || in32_b) && iters <= early_iters) {
       // early inputs: [ring | in16 | in32]; y over in16 when present (same plane count), else in the ring; out2 in the ring
       const bool y_over_in = in16_b != 0 && aux.out1_planes == aux.in16_planes;
       const int ring_need = (y_over_in ? 0 : out1_b) + out2_b;
-      int s = (ring_need + SLOT_BYTES - 1) / SLOT_BYTES;
-      if (s < 2) s = 2;
-      if (s <= 4 && s * SLOT_BYTES + in16_b + in32_b + tail_bytes <= MAX_SMEM) {
+      int s = (ring_need + slot_b - 1) / slot_b;
+      if (s < (aux.paired ? 1 : 2)) s = aux.paired ? 1 : 2;
+      if (s <= max_ring && s * slot_b + in16_b + in32_b + tail_bytes <= MAX_SMEM) {
         // the deepest useful ring that still fits
-        while (s < 4 && s < iters && (s + 1) * SLOT_BYTES + in16_b + in32_b + tail_bytes <= MAX_SMEM) ++s;
+        while (s < max_ring && s < iters && (s + 1) * slot_b + in16_b + in32_b + tail_bytes <= MAX_SMEM) ++s;
         stages = s;
         extra = in16_b + in32_b;
         aux.early_in = 1;
-        aux.off_in16 = (uint32_t)(stages * SLOT_BYTES);
+        aux.off_in16 = (uint32_t)(stages * slot_b);
         aux.off_in32 = aux.off_in16 + (uint32_t)in16_b;
         aux.off_out1 = y_over_in ? aux.off_in16 : 0u;
         aux.off_out2 = y_over_in ? 0u : (uint32_t)out1_b;
@@ -821,9 +912,9 @@ static int launch_hp_mode(const bcosk_igemm_params& p, cudaStream_t st) {
     const int b_b = MODE == BCOSK_MODE_FWD ? out2_b : in32_b;
     const int c_b = MODE == BCOSK_MODE_FWD ? 0 : out2_b;
     const int need = a_b + b_b + c_b;
-    stages = (need + SLOT_BYTES - 1) / SLOT_BYTES;
-    if (stages < 4) stages = 4;
-    if (stages > MAX_STAGES || stages * SLOT_BYTES + tail_bytes > MAX_SMEM) return false;
+    stages = (need + slot_b - 1) / slot_b;
+    if (stages < max_ring) stages = max_ring;
+    if (stages > MAX_STAGES || stages * slot_b + tail_bytes > MAX_SMEM) return false;
     aux.off_in16 = 0;
     aux.off_out1 = 0;
     aux.off_in32 = (uint32_t)a_b;
@@ -847,7 +938,7 @@ static int launch_hp_mode(const bcosk_igemm_params& p, cudaStream_t st) {
                (!p.out2 || (aux.out2_kind == 2 && aux.out2_planes == 2)) && (!p.mul2 || p.mul2_f32);
   if (g_hp_stage_boxes & 2) aux.fast = 0;      // A/B: generic epilogue arithmetic over the same boxes
   aux.stages = stages;
-  aux.tail = (uint32_t)(stages * SLOT_BYTES + extra);
+  aux.tail = (uint32_t)(stages * slot_b + extra);
   const int smem = (int)aux.tail + tail_bytes;
   auto kern = bcosk_igemm_hp_kernel<MODE, __nv_bfloat16>;
   auto kern_h = bcosk_igemm_hp_kernel<MODE, __half>;
@@ -878,14 +969,15 @@ int launch_hp(const bcosk_igemm_params& p, cudaStream_t st) {
 }  // namespace bcosk
 
 extern "C" int bcosk_set_hp_chunk(int32_t stages) {
-  const int prev = bcosk::g_hp_chunk;
-  if (stages >= 1) bcosk::g_hp_chunk = stages;
+  const int prev = bcosk::g_hp_chunk | (bcosk::g_hp_xchunk << 16);
+  if ((stages & 0xffff) >= 1) bcosk::g_hp_chunk = stages & 0xffff;
+  bcosk::g_hp_xchunk = stages >> 16;            // bits 16..: experiment override of the cross-term accumulation length
   return prev;
 }
 
 extern "C" int bcosk_set_hp_boxes(int32_t enabled) {
   const int prev = bcosk::g_hp_stage_boxes | (bcosk::g_hp_early_iters << 8);
-  bcosk::g_hp_stage_boxes = enabled & 3;        // bit 0: boxes, bit 1: generic arithmetic even where the packed form applies
+  bcosk::g_hp_stage_boxes = enabled & 7;        // bit 0: boxes, bit 1: generic arithmetic, bit 2: no paired stages
   if (enabled >> 8) bcosk::g_hp_early_iters = (enabled >> 8) - 1;   // bits 8..: 1 + K stages up to which input boxes are fetched early
   return prev;
 }

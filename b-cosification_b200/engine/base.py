@@ -138,6 +138,7 @@ class PlanBase:
     flat_3x3 = True                  # 64 -> <=64 channel stride-1 k x k convs and their data gradients as flat-window launches
     flat_stem = True                 # stem and its data gradient as flat-window launches (throughput mode only)
     autotune_default = True          # capture() measures the per-launch schedule first (see autotune)
+    hp_chunk = 0     # parity-mode launches: K stages per TMEM accumulation of the leading segment (0 = library default)
     fold_bn = True   # fold sqrt(BN multiplier) into the conv weights when every multiplier is positive and there is no bias
 
     def _block_n(self, n: int, k_iters: int = 1 << 30, hp: Optional[bool] = None) -> int:
@@ -220,12 +221,12 @@ class PlanBase:
         self.fwd_ops.append(O.IgemmOp(
             name=name, a=x.t, b=self._dev(bmat, self.dt), n=o, lo=(-pad_lo, -pad_lo),
             up=(pad_hi - (kw - 1), pad_hi - (kh - 1)), stride=(stride, stride), op=oh, oq=ow, kch=kch, chunks_per_tap=cpt,
-            taps=P.conv_taps(kh, kw), seg_a_choff=P.seg_a_offsets(self.planes, cin_phys), dtype=self.dt_code,
+            taps=P.conv_taps(kh, kw), seg_a_choff=P.seg_a_offsets(self.planes, cin_phys), seg_b_plane=P.seg_b_planes(self.planes), dtype=self.dt_code,
             mode=L.BCOSK_MODE_FWD, block_n=block_n, scale_mode=self.scale_mode, b_exp=self.b, relu=relu,
             inv_norm=inv_norm, sq_in=sq_in, sq_geom=sq_geom, sq_eps=sq_eps, alpha=alpha, beta=beta,
             lin_bias=None if lin_bias is None else self._dev(lin_bias),
             res=None if res is None else res.t, res_planes=self.planes,
-            gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32, hp_accum=self.hp_accum, flat=flat,
+            gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32, hp_accum=self.hp_accum, hp_chunk=self.hp_chunk, flat=flat,
             inv_norm_out=inv_out,
             algo_flops=2.0 * M * o * float((w != 0).sum().item()) / o))
         rec.algo_flops = self.fwd_ops[-1].algo_flops
@@ -278,10 +279,10 @@ class PlanBase:
         self.bwd_ops.append(O.IgemmOp(
             name=rec.name + ".dgrad", a=g, b=self._dev(bmat, self.dt), n=n, lo=(lo, lo), up=(up_w, up_h), stride=(1, 1),
             op=oh, oq=ow, kch=kch, chunks_per_tap=cpt, taps=P.conv_taps(k, k),
-            seg_a_choff=P.seg_a_offsets(self.bplanes, rec.cout), dtype=self.dt_code, mode=L.BCOSK_MODE_EXPLAIN,
+            seg_a_choff=P.seg_a_offsets(self.bplanes, rec.cout), seg_b_plane=P.seg_b_planes(self.bplanes), dtype=self.dt_code, mode=L.BCOSK_MODE_EXPLAIN,
             block_n=64 if (add is not None and add_stride == 1 and self.bplanes == 1 and n >= 64)
             else self._block_n(n, bmat.shape[1] // 64, hp=self.bwd_hp),   # dense extra gradient: 64-wide tiles stage it with TMA
-            hp_accum=self.bwd_hp, y=y, y_planes=1 if y_f32 else self.bplanes, y_f32=y_f32,
+            hp_accum=self.bwd_hp, hp_chunk=self.hp_chunk, y=y, y_planes=1 if y_f32 else self.bplanes, y_f32=y_f32,
             out_map=y_map, add=add, add_planes=self.bplanes, add_stride=add_stride, mul1=mul1, out2=out2,
             out2_planes=self.bplanes, mul2=mul2, mask2=mask2, flat=flat, mul1_sqrt_scale=mul1_sqrt_scale,
             algo_flops=rec.algo_flops,
@@ -322,8 +323,8 @@ class PlanBase:
                     name=f"{rec.name}.dgrad.c{py}{px}", a=g, b=self._dev(bmat, self.dt), n=n, lo=(lo_w, lo_h),
                     up=(ow - g.shape[2] + lo_w, oh - g.shape[1] + lo_h), stride=(1, 1), op=oh, oq=ow, kch=kch,
                     chunks_per_tap=cpt, taps=[(jx, jy) for jy in range(ty) for jx in range(tx)],
-                    seg_a_choff=P.seg_a_offsets(self.bplanes, rec.cout), dtype=self.dt_code, mode=L.BCOSK_MODE_EXPLAIN,
-                    block_n=self._block_n(n, bmat.shape[1] // 64, hp=self.bwd_hp), hp_accum=self.bwd_hp, y=y, y_planes=self.bplanes,
+                    seg_a_choff=P.seg_a_offsets(self.bplanes, rec.cout), seg_b_plane=P.seg_b_planes(self.bplanes), dtype=self.dt_code, mode=L.BCOSK_MODE_EXPLAIN,
+                    block_n=self._block_n(n, bmat.shape[1] // 64, hp=self.bwd_hp), hp_accum=self.bwd_hp, hp_chunk=self.hp_chunk, y=y, y_planes=self.bplanes,
                     out_map=(py * iw + px, ih * iw, s * iw, s), mul1=mul1, side_mapped=True, mul1_sqrt_scale=mul1_sqrt_scale,
                     algo_flops=rec.algo_flops * (sum(float((rec.w[:, :, dy, dx] != 0).sum().item()) for dy, dx in sel) / nz),
                     a_dense_frac=1.0 / (s * s)))    # the s*s launches together read the gradient once

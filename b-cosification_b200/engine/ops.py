@@ -33,6 +33,7 @@ class IgemmOp:
     taps: List[Tuple[int, int]]    # (off_w, off_h)
     seg_a_choff: List[int]
     dtype: int
+    seg_b_plane: Optional[List[int]] = None   # B plane per segment (engine/pack.py SEGMENTS); None = [0] for one segment
     mode: int = 0
     block_n: int = 0
     # forward epilogue
@@ -148,6 +149,8 @@ class IgemmOp:
         p.num_taps, p.num_segs = len(self.taps), len(self.seg_a_choff)
         for i, o in enumerate(self.seg_a_choff):
             p.seg_a_choff[i] = o
+        for i, bp in enumerate(self.seg_b_plane or []):
+            p.seg_b_plane[i] = bp
         for i, (ow, oh) in enumerate(self.taps):
             p.tap_off_w[i], p.tap_off_h[i] = ow, oh
         assert self.b.shape == (self.n, self.ktot), (self.name, self.b.shape, self.n, self.ktot)

@@ -56,6 +56,10 @@ def seg_a_offsets(planes: int, a_plane_channels: int) -> List[int]:
     return [ap * a_plane_channels for ap, _ in SEGMENTS[planes]]
 
 
+def seg_b_planes(planes: int) -> List[int]:
+    return [bp for _, bp in SEGMENTS[planes]]
+
+
 def conv_taps(kh: int, kw: int, dil: int = 1) -> List[Tuple[int, int]]:
     """Tap order (kh-major) as (off_w, off_h)."""
     return [(j * dil, i * dil) for i in range(kh) for j in range(kw)]

@@ -37,6 +37,7 @@ def _require_cuda(x: Tensor, who: str) -> None:
 
 class LayerPlan(PlanBase):
     """Launches for one conv / linear module at one input shape."""
+    hp_chunk = 1      # three bf16 planes: every K stage of the leading segment gets its own accumulation (strictest)
 
     def __init__(self, weight: Tensor, bias: Optional[Tensor], in_shape: Tuple[int, int, int, int], stride: int, pad: int,
                  b: float, linear_eps: bool, max_out: int = 1):

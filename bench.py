@@ -58,10 +58,13 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arch", default="resnet50")
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--planes", type=int, default=1, help="precision planes (1 = 16-bit throughput mode)")
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
-                    help="operand format of the tensor-core launches (BASELINE names bf16; fp16 runs at the same rate)")
-    ap.add_argument("--cpu-batch", type=int, default=32, help="images per CPU-baseline / reference-arm step")
+    ap.add_argument("--mode", default="parity", choices=["parity", "parity_full", "throughput", "throughput_fp16"],
+                    help="operand format (engine/resnet.py PRECISION_MODES).  parity (default): two fp16 planes + fp32-faithful "
+                         "accumulation forward, one fp16 plane in the explanation pass - meets the parity contract.  throughput: one "
+                         "bf16 plane, the format BASELINE.json names - faster, does not meet the map tolerances")
+    ap.add_argument("--no-throughput-record", action="store_true", help="skip the extra bf16 x1 measurement")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline / reference-arm step (8 = the CPU's best)")
+    ap.add_argument("--cpu-steps", type=int, default=64, help="steps of the in-run CPU baseline (~10-20 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default=None, help="write the per-launch timing table (JSON) here")
     return ap.parse_args()
@@ -162,7 +165,8 @@ def main():
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "img/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "arch": args.arch, "image": 224, "batch_per_step": args.cpu_batch},
+            "config": {"workload": WORKLOAD, "arch": args.arch, "image": 224, "batch_per_step": args.cpu_batch,
+                       "note": "bounded sample of the workload: the CPU's best step size (8 images; 32-image steps are ~1.5x slower per image)"},
             "cpu_baseline": {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }), file=real_stdout, flush=True)
@@ -171,54 +175,71 @@ def main():
     import torch
     from bcos_b200 import build as bbuild
     from bcos_b200.engine import ops as O
+    from bcos_b200.engine import PipelinedExplainer
     from bcos_b200.models import synthetic_resnet_plan
     from bcos_b200.utils import synth
 
     torch.cuda.set_device(local_rank)
     D.init("nccl")
     bbuild.build()
+    barrier, max_over_ranks = D.barrier, D.max_over_ranks
 
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
-    plan = synthetic_resnet_plan(args.arch, B, planes=args.planes, dtype=args.dtype, device=f"cuda:{local_rank}", input_u8=True,
-                                seed_scale=4096.0 if args.dtype == "fp16" else 1.0)
+    dev = f"cuda:{local_rank}"
     imgs = torch.from_numpy(synth.synth_images_u8(min(B, 64), 224, 1000 + rank))
     imgs = imgs.repeat((B + imgs.shape[0] - 1) // imgs.shape[0], 1, 1, 1)[:B].contiguous()
     h_in = imgs.pin_memory()
-    h_logits = torch.empty(B, plan.ncls, dtype=torch.float32).pin_memory()
-    h_cmap = torch.empty(B, 224, 224, dtype=torch.float32).pin_memory()
-    plan.load_input(h_in)
-    plan.capture()
 
-    barrier, max_over_ranks = D.barrier, D.max_over_ranks
+    def device_resident_ms(pl):
+        """W warm-ups, then K CUDA-graph replays of forward + explanation with the inputs resident in HBM; device time, max over ranks"""
+        for _ in range(W):
+            pl.replay_all()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        for _ in range(K):
+            pl.replay_all()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), (w0, time.time())
 
     sampler = ClockSampler(local_rank)
-    sampler.start()
     windows = []
 
+    # ---------------- optional extra record: the opt-in bf16 x1 throughput mode (BASELINE's named format), device resident -------
+    thr = None
+    if args.mode != "throughput" and not args.no_throughput_record:
+        tplan = synthetic_resnet_plan(args.arch, B, mode="throughput", device=dev, input_u8=True)
+        tplan.load_input(h_in)
+        tplan.capture()
+        ms_t, _ = device_resident_ms(tplan)
+        thr = {"mode": "throughput", "operands": "bf16 x1", "ms_per_step": ms_t / K, "value": world * B * K / (ms_t * 1e-3), "unit": "img/s",
+               "launches_per_step": tplan.num_launches(),
+               "note": "device-resident, same timing method; does NOT meet the map tolerances (see `parity_check.throughput`)"}
+        del tplan
+        torch.cuda.empty_cache()
+
+    plan = synthetic_resnet_plan(args.arch, B, mode=args.mode, device=dev, input_u8=True)
+    prec = plan.precision
+    plan.load_input(h_in)
+    plan.capture()
+    sampler.start()
+
     # ---------------- device-resident throughput: inputs already in HBM, K graph replays ----------------
-    for _ in range(W):
-        plan.replay_all()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0 = time.time()
-    e0.record()
-    for _ in range(K):
-        plan.replay_all()
-    e1.record()
-    barrier()
-    windows.append((w0, time.time()))
-    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    ms_dev, win = device_resident_ms(plan)
+    windows.append(win)
 
     # ---------------- end to end through the public API: pinned host images in, logits + maps out ----------------
     # PipelinedExplainer: every step copies its own batch host->device and its own results device->host (pinned memory);
     # copies of step i+1 / i-1 overlap the compute of step i.  The timed region ends when the last result is on the host.
-    from bcos_b200.engine import PipelinedExplainer
     pipe = PipelinedExplainer(plan)
     h_ins = [h_in, h_in.clone().pin_memory()]
     for i in range(W):
         pipe.submit(h_ins[i % 2])
     pipe.drain()
     barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
     e0.record()
     last = 0
@@ -250,32 +271,44 @@ def main():
                 per_op[i] += evs[i].elapsed_time(evs[i + 1]) / reps
     ig = [(o, t) for o, t in zip(all_ops, per_op) if isinstance(o, O.IgemmOp)]
     ig_ms = sum(t for _, t in ig)
-    ig_bytes = sum(o.algo_bytes() for o, _ in ig)
+    ig_design_bytes = sum(o.algo_bytes() for o, _ in ig)
     ig_flops = sum(o.algo_flops for o, _ in ig)
+    ig_exec_flops = sum(o.flops() for o, _ in ig)
     step_ms_eager = sum(per_op)
+    # tensor-class launches: the ones SURVEY 8(d) marks tensor bound (3x3 at <= 28^2, K >= 1024 1x1, fc)
+    tc = [(o, t) for o, t in ig if (len(o.taps) > 1 and o.op <= 28 and o.n >= 128) or (len(o.taps) == 1 and o.ktot // len(o.seg_a_choff) >= 1024)]
+    tc_ms, tc_flops = sum(t for _, t in tc), sum(o.algo_flops for o, _ in tc)
 
     if rank != 0:
         D.shutdown()
         return
 
+    # ---------------- parity of the benchmarked mode against the reference golden (4 images, same code path) ----------------
+    parity_check = run_parity_check(args, prec, dev)
+
     pk = peaks()
-    # measured DRAM bytes of the same launches from the committed ncu capture (dram__bytes_read + dram__bytes_write over
-    # one step of this workload); only meaningful for the configuration it was captured on
+    # 133 MB per image forward + explanation (bf16: x, y, gain, g_out, g_in, weights once each) - the yardstick
+    # for every operand mode.  The design's own traffic (every tensor the launches touch once; includes second planes, masks,
+    # shortcut streams) and the measured DRAM bytes of the same launches (ncu) are reported beside it.
+    SURVEY_BYTES_PER_IMG = 133e6
+    alg_bytes = SURVEY_BYTES_PER_IMG * B if args.arch == "resnet50" else ig_design_bytes
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_final_dram_traffic.json")
-    if os.path.exists(tpath) and args.arch == "resnet50" and B == 256 and args.planes == 1:
+    tpath = os.path.join(ROOT, "profiles", f"r02_dram_traffic_{args.mode}.json")
+    if os.path.exists(tpath) and args.arch == "resnet50" and B == 256:
         with open(tpath) as fh:
             tj = json.load(fh)
-        traffic, traffic_src = float(tj["igemm_dram_bytes_per_step"]), "profiles/r01_final_dram_traffic.json (ncu, bytes per step)"
-    hbm_ach = ig_bytes / (ig_ms * 1e-3) / 1e9
+        traffic, traffic_src = float(tj["igemm_dram_bytes_per_step"]), f"profiles/r02_dram_traffic_{args.mode}.json (ncu, bytes per step)"
+    hbm_ach = alg_bytes / (ig_ms * 1e-3) / 1e9
     tc_ach = ig_flops / (ig_ms * 1e-3) / 1e12
-    tpk = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
     imgs_total = world * B * K
     res = {
         "metric": METRIC, "value": imgs_total / (ms_dev * 1e-3), "unit": "img/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": prec["dtype"],
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "arch": args.arch, "image": 224, "batch_per_gpu": B, "precision_planes": args.planes,
+        "config": {"workload": WORKLOAD, "arch": args.arch, "image": 224, "batch_per_gpu": B, "mode": args.mode,
+                   "precision": {"forward_planes": prec["planes"], "explain_planes": prec["explain_planes"] or prec["planes"],
+                                 "operand_dtype": prec["dtype"], "accumulate": "fp32" + (" (fresh TMEM accumulator per K chunk, RN adds)" if prec["planes"] > 1 else ""),
+                                 "seed_scale": prec["seed_scale"]},
                    "parallelism": f"batch-sharded x{world}, no collective", "weights": "random-init synthetic checkpoint, BN calibrated",
                    "l2": "per-layer activations (>=100 MB at batch 256) exceed the 126 MB L2; no explicit flush",
                    "cuda_graph": True},
@@ -286,32 +319,85 @@ def main():
                        "contribution maps, copies overlapped with the neighbouring steps' compute"},
         "gpu_launches": plan.num_launches() * K,
         "launches_per_step": plan.num_launches(),
+        "parity_check": parity_check,
         "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk["hbm_gbs"],
                      "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": "bcosk_igemm_* (all conv / dgrad launches of one step)",
                      "peak_source": pk["source"], "kernel_ms_per_step": ig_ms, "kernel_share_of_step": ig_ms / step_ms_eager,
-                     "algorithmic_bytes_per_step": ig_bytes},
-        "roofline_tensor": {"bound": "tensor", "achieved": tc_ach, "peak": tpk, "unit": "TFLOP/s", "frac": tc_ach / tpk,
-                            "algorithmic_flops_per_step": ig_flops, "peak_source": pk["source"] + " sustained"},
+                     "algorithmic_bytes_per_step": alg_bytes, "algorithmic_bytes_source": "SURVEY.md 8(d): 133 MB / image x batch",
+                     "design_traffic_bytes_per_step": ig_design_bytes,
+                     "design_traffic_frac_of_peak": ig_design_bytes / (ig_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
+        "roofline_tensor": {"bound": "tensor", "achieved": tc_ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tc_ach / pk["bf16_tflops"],
+                            "algorithmic_flops_per_step": ig_flops, "executed_flops_per_step": ig_exec_flops,
+                            "executed_tflops": ig_exec_flops / (ig_ms * 1e-3) / 1e12, "peak_source": pk["source"] + " burst",
+                            "tensor_class_launches": {"count": len(tc), "ms": tc_ms, "algorithmic_tflops": tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else None,
+                                                      "frac_of_burst_peak": tc_flops / (tc_ms * 1e-3) / 1e12 / pk["bf16_tflops"] if tc_ms else None,
+                                                      "what": "3x3 at <= 28^2 and K >= 1024 1x1 launches (SURVEY 8d tensor-bound rows)"}},
         "clocks": sampler.summary(windows),
     }
+    if thr is not None:
+        res["throughput_mode"] = thr
     if args.layer_table:
         rows = []
         for o, t in zip(all_ops, per_op):
             row = {"name": o.name, "kind": type(o).__name__, "ms": t}
             if isinstance(o, O.IgemmOp):
-                row.update(M=o.M, N=o.n, K=o.ktot, block_n=o.resolved_block_n(), gflop=o.algo_flops / 1e9,
-                           mbytes=o.algo_bytes() / 1e6, tflops=o.algo_flops / (t * 1e-3) / 1e12,
+                row.update(M=o.M, N=o.n, K=o.ktot, block_n=o.resolved_block_n(), hp=bool(o.hp_accum), gflop=o.algo_flops / 1e9,
+                           mbytes=o.algo_bytes() / 1e6, tflops=o.algo_flops / (t * 1e-3) / 1e12, exec_tflops=o.flops() / (t * 1e-3) / 1e12,
                            gbs=o.algo_bytes() / (t * 1e-3) / 1e9)
             rows.append(row)
         os.makedirs(os.path.dirname(os.path.abspath(args.layer_table)), exist_ok=True)
         with open(args.layer_table, "w") as fh:
-            json.dump({"batch": B, "arch": args.arch, "planes": args.planes, "step_ms_eager": step_ms_eager, "rows": rows}, fh, indent=1)
+            json.dump({"batch": B, "arch": args.arch, "mode": args.mode, "step_ms_eager": step_ms_eager, "rows": rows}, fh, indent=1)
     if world == 1 and not args.no_cpu_baseline:
-        c = cpu_reference_arm(args, 16, 1)     # ~10 s of host work: 16 steps of 32 images
+        c = cpu_reference_arm(args, args.cpu_steps, 2)
         res["cpu_baseline"] = {"value": c["value"], "unit": "img/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]}
     print(json.dumps(res), file=real_stdout, flush=True)
     D.shutdown()
+
+
+def _metrics(logits, maps, ref_logits, ref_maps):
+    """argmax equality, logit relative error, per-image map cosine (min) and max-abs / range (max) - BASELINE.json's criteria"""
+    import torch
+    logits, maps, ref_logits, ref_maps = (t.detach().double().cpu() for t in (logits, maps, ref_logits, ref_maps))
+    a, r = maps.flatten(1), ref_maps.flatten(1)
+    cos = torch.nn.functional.cosine_similarity(a, r, dim=1)
+    rng = r.max(1).values - r.min(1).values
+    return {"argmax_equal": bool((logits.argmax(1) == ref_logits.argmax(1)).all()),
+            "logit_rel_err": float((logits - ref_logits).abs().max() / ref_logits.abs().max()),
+            "map_cos_min": float(cos.min()), "map_maxabs_over_range": float(((a - r).abs().max(1).values / rng).max())}
+
+
+def run_parity_check(args, prec, dev):
+    """The benchmarked operand mode (and the bf16 x1 throughput mode) on the committed reference golden of this network
+    (tests/golden/<arch>_b<n>.npz: weights seed, calibrated BN variances, images, reference fp32 logits and maps)."""
+    import numpy as np
+    import torch
+    from bcos_b200.engine import ResNetPlan
+    from bcos_b200.models import resnet_state_shapes
+    from bcos_b200.utils import synth
+    nb = {"resnet50": 4, "resnet18": 8}.get(args.arch)
+    path = os.path.join(ROOT, "tests", "golden", f"{args.arch}_b{nb}.npz")
+    if nb is None or not os.path.exists(path):
+        return None
+    gold = np.load(path)
+    sd = synth.synth_state_dict(resnet_state_shapes(args.arch), int(gold["seed"]))
+    off = 0
+    for k, n in zip(gold["bn_keys"].tolist(), gold["bn_sizes"].tolist()):
+        sd[k] = torch.from_numpy(gold["bn_var"][off:off + n].copy())
+        off += n
+    imgs = torch.from_numpy(gold["images_u8"])
+    out = {"golden": f"tests/golden/{args.arch}_b{nb}.npz (reference fp32 run, {nb} images)",
+           "contract": {"argmax_equal": True, "logit_rel_err": 2e-3, "map_cos_min": 0.999, "map_maxabs_over_range": 1e-3}}
+    for name in dict.fromkeys([args.mode, "throughput"]):
+        plan = ResNetPlan(args.arch, sd, nb, mode=name, input_u8=True, device=dev)
+        o = plan.explain(imgs)
+        torch.cuda.synchronize()
+        m = _metrics(o["logits"], o["contribution_map"], torch.from_numpy(gold["logits"]), torch.from_numpy(gold["contribution_map"]))
+        m["meets_contract"] = bool(m["argmax_equal"] and m["logit_rel_err"] <= 2e-3 and m["map_cos_min"] >= 0.999 and m["map_maxabs_over_range"] <= 1e-3)
+        out[name] = m
+        del plan
+    return out
 
 
 if __name__ == "__main__":

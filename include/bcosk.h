@@ -71,6 +71,9 @@ typedef struct bcosk_igemm_params {
   int32_t num_taps;
   int32_t num_segs;
   int32_t seg_a_choff[BCOSK_MAX_SEGS]; /* first channel of the A plane used by segment s */
+  int32_t seg_b_plane[BCOSK_MAX_SEGS]; /* precision plane of B that segment s multiplies with (informational: the B columns of
+                                        * segment s already hold that plane).  With hp_accum, the canonical two-plane order
+                                        * {a0 b0, a0 b1, a1 b0} lets the kernel fetch a0 once for two segments. */
   uint16_t tap_off_w[BCOSK_MAX_TAPS];
   uint16_t tap_off_h[BCOSK_MAX_TAPS];
   /* ---- B operand: packed weights [n][num_segs*num_taps*chunks_per_tap*kch], 16-bit, K-major */
@@ -123,7 +126,8 @@ typedef struct bcosk_igemm_params {
   int32_t hp_accum;
   /* hp_accum only: K stages (64 deep each) of the leading operand segment (a-plane 0 x b-plane 0) that one TMEM
    *      accumulation covers before the epilogue warps add it to their registers; 0 = library default
-   *      (bcosk_set_hp_chunk, initially 1).  All cross-term segments (a0 b1, a1 b0, ...) share one further accumulation. */
+   *      (bcosk_set_hp_chunk, initially 2).  With fp16 planes the cross-term segments (a0 b1, a1 b0; each 2^-11 of the leading one) run back
+   *      to back in ONE further accumulation; with bf16 planes they are chunked like the leading segment. */
   int32_t hp_chunk;
   /* ---- schedule of a block_n == 64 launch (ignored otherwise and with hp_accum; results do not depend on it):
    *      0 = library default (see bcosk_set_persistent / bcosk_set_light), 1 = one CTA per tile,
@@ -168,7 +172,8 @@ int bcosk_igemm(const bcosk_igemm_params* p, void* stream);
 int bcosk_set_hp_chunk(int32_t stages);
 /* Parity-mode launches, A/B measurement switches (results are identical).  Bit 0 (default 1): epilogue tensors move as TMA
  * boxes through shared memory instead of per-row 16-byte accesses.  Bit 1 (default 0): the generic epilogue arithmetic runs
- * even where the packed two-plane form applies.  Bits 8..: when non-zero, 1 + the number of K stages up to which the input
+ * even where the packed two-plane form applies.  Bit 2 (default 0): no paired stages (every segment fetches its own A plane).
+ * Bits 8..: when non-zero, 1 + the number of K stages up to which the input
  * boxes are fetched at kernel start (default 4) instead of after the last MMA.  Returns the previous setting. */
 int bcosk_set_hp_boxes(int32_t enabled);
 

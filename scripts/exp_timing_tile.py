@@ -10,7 +10,7 @@ from bcos_b200 import _lib as L
 from bcos_b200.models import synthetic_resnet_plan
 from bcos_b200.utils import synth
 lib = L.load()
-plan = synthetic_resnet_plan("resnet50", 256, device="cuda", input_u8=True)
+plan = synthetic_resnet_plan("resnet50", 256, mode="throughput", device="cuda", input_u8=True)
 imgs = torch.from_numpy(synth.synth_images_u8(32, 224, 5)).repeat(8, 1, 1, 1).contiguous()
 plan.load_input(imgs)
 ops = plan.fwd_ops + plan.bwd_ops

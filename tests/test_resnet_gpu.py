@@ -167,3 +167,122 @@ def test_multi_target_explain_and_rgba(bcosk_lib):
         ref = OR.explain_batched(om.forward, x6)
         torch.cuda.synchronize()
         assert torch.equal(out2["prediction"].cpu().long(), ref["prediction"].long())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The default operand mode and the benchmarked configuration (VERDICT r01 "next round" items 1-2)
+# ---------------------------------------------------------------------------------------------------------------------
+def _assert_contract(m, what):
+    """BASELINE.json north_star tolerances, strict, against the fp32 reference golden."""
+    print(f"REPORT {what}: {m}")
+    assert m["argmax_equal"], (what, m)
+    assert m["logit_rel_err"] <= 2e-3, (what, m)
+    assert m["map_cos_min"] >= 0.999, (what, m)
+    assert m["map_maxabs_over_range"] <= 1e-3, (what, m)
+
+
+@pytest.mark.parametrize("arch,batch", [("resnet18", 8), ("resnet50", 4)])
+def test_default_mode_meets_the_contract(bcosk_lib, golden_dir, arch, batch):
+    """`ResNetPlan(arch, state_dict, batch)` with no precision arguments - what checkpoint.resnet_plan_from_checkpoint,
+    models.synthetic_resnet_plan and bench.py build - is the contract-meeting mode: two fp16 planes with fp32-faithful
+    accumulation forward, one fp16 plane in the explanation pass."""
+    gold = np.load(os.path.join(golden_dir, f"{arch}_b{batch}.npz"))
+    sd = golden_state(arch, gold)
+    x6 = synth.to_bcos_input(gold["images_u8"])
+    plan = ResNetPlan(arch, sd, batch, device="cuda")
+    assert plan.precision == dict(planes=2, dtype="fp16", explain_planes=1, seed_scale=4096.0)
+    out = plan.explain(x6)
+    torch.cuda.synchronize()
+    _assert_contract(OR.parity_metrics(out["logits"], out["contribution_map"], torch.from_numpy(gold["logits"]),
+                                       torch.from_numpy(gold["contribution_map"])), f"{arch} default mode")
+    plan.capture()
+    out2 = plan.explain(x6)
+    torch.cuda.synchronize()
+    _assert_contract(OR.parity_metrics(out2["logits"], out2["contribution_map"], torch.from_numpy(gold["logits"]),
+                                       torch.from_numpy(gold["contribution_map"])), f"{arch} default mode, autotuned + captured")
+
+
+def test_benchmark_configuration_parity(bcosk_lib, golden_dir):
+    """bench.py's configuration - ResNet-50, batch 256, uint8 input, autotuned schedules, CUDA-graph replay - checked against
+    the reference: images 0-3 of the batch are the golden images (images are independent in eval mode).  The opt-in
+    throughput mode (one bf16 plane) is bit-compared with a batch-4 plan of the same mode."""
+    gold = np.load(os.path.join(golden_dir, "resnet50_b4.npz"))
+    sd = golden_state("resnet50", gold)
+    B = 256
+    imgs = torch.from_numpy(np.concatenate([gold["images_u8"], synth.synth_images_u8(B - 4, 224, 77)], 0))
+    plan = ResNetPlan("resnet50", sd, B, input_u8=True, device="cuda")
+    plan.load_input(imgs)
+    plan.capture()
+    out = plan.explain(imgs)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out["logits"]).all() and torch.isfinite(out["contribution_map"]).all()
+    _assert_contract(OR.parity_metrics(out["logits"][:4], out["contribution_map"][:4], torch.from_numpy(gold["logits"]),
+                                       torch.from_numpy(gold["contribution_map"])), "resnet50 batch 256 (bench configuration), default mode")
+    del plan, out
+    torch.cuda.empty_cache()
+    big = ResNetPlan("resnet50", sd, B, mode="throughput", input_u8=True, device="cuda")
+    big.load_input(imgs)
+    big.capture()
+    o_big = big.explain(imgs)
+    small = ResNetPlan("resnet50", sd, 4, mode="throughput", input_u8=True, device="cuda")
+    o_small = small.explain(imgs[:4])
+    torch.cuda.synchronize()
+    assert torch.equal(o_big["prediction"][:4], o_small["prediction"])
+    assert torch.equal(o_big["logits"][:4], o_small["logits"])
+    assert torch.equal(o_big["contribution_map"][:4], o_small["contribution_map"])
+
+
+def test_pipelined_explainer_matches_plan(bcosk_lib):
+    """The end-to-end API bench.py times (`PipelinedExplainer.submit / result`): three different host batches through the
+    three-stream pipeline give exactly what `plan.explain` gives for the same batch."""
+    from bcos_b200.engine import PipelinedExplainer
+    arch, S, nb = "resnet18", 64, 4
+    sd = synth.synth_state_dict(OR.resnet_state_shapes(arch), 0)
+    om = OR.OracleResNet(arch, sd)
+    om.calibrate_bn(synth.to_bcos_input(synth.synth_images_u8(nb, S, 1)))
+    plan = ResNetPlan(arch, sd, nb, image_size=S, input_u8=True, device="cuda")
+    pipe = PipelinedExplainer(plan)
+    batches = [torch.from_numpy(synth.synth_images_u8(nb, S, 10 + i)).pin_memory() for i in range(3)]
+    got = []
+    for b in batches:
+        t = pipe.submit(b)
+        r = pipe.result(t)
+        got.append({k: v.clone() for k, v in r.items()})
+    # and back to back (results of the last `depth` tickets are still staged)
+    t0, t1 = pipe.submit(batches[0]), pipe.submit(batches[1])
+    r0 = {k: v.clone() for k, v in pipe.result(t0).items()}
+    r1 = {k: v.clone() for k, v in pipe.result(t1).items()}
+    pipe.drain()
+    for i, b in enumerate(batches):
+        ref = plan.explain(b)
+        torch.cuda.synchronize()
+        assert torch.equal(got[i]["logits"], ref["logits"].cpu()), i
+        assert torch.equal(got[i]["contribution_map"], ref["contribution_map"].cpu()), i
+    assert torch.equal(r0["contribution_map"], got[0]["contribution_map"]) and torch.equal(r1["logits"], got[1]["logits"])
+    # sanity against the oracle (default = contract mode)
+    ref = OR.explain_batched(om.forward, synth.to_bcos_input(batches[2].numpy()))
+    m = OR.parity_metrics(got[2]["logits"], got[2]["contribution_map"], ref["logits"], ref["contribution_map"])
+    assert m["argmax_equal"] and m["logit_rel_err"] <= 2e-3 and m["map_cos_min"] >= 0.999, m
+
+
+def test_plan_from_released_checkpoint_matches_golden(bcosk_lib, golden_dir, tmp_path):
+    """SURVEY 8f row 4 on the device: a Lightning `last.ckpt` (model + EMA copy) written with the reference's key names is
+    loaded by `checkpoint.resnet_plan_from_checkpoint` and the resulting plan reproduces the reference golden."""
+    from bcos_b200 import checkpoint as C
+    arch, batch = "resnet18", 8
+    gold = np.load(os.path.join(golden_dir, f"{arch}_b{batch}.npz"))
+    sd = golden_state(arch, gold)
+    ema = {k: (v * 0.5 if v.is_floating_point() and v.ndim == 4 else v) for k, v in sd.items()}
+    ck = {"epoch": 89, "state_dict": {**{"model." + k: v for k, v in sd.items()}, **{"ema.module." + k: v for k, v in ema.items()},
+                                      "criterion.off_label": torch.zeros(1)}}
+    torch.save(ck, tmp_path / "last.ckpt")
+    plan = C.resnet_plan_from_checkpoint(arch, tmp_path / "last.ckpt", batch, device="cuda")
+    out = plan.explain(synth.to_bcos_input(gold["images_u8"]))
+    torch.cuda.synchronize()
+    _assert_contract(OR.parity_metrics(out["logits"], out["contribution_map"], torch.from_numpy(gold["logits"]),
+                                       torch.from_numpy(gold["contribution_map"])), "plan from last.ckpt")
+    # the EMA copy holds different conv weights -> a different network
+    plan_ema = C.resnet_plan_from_checkpoint(arch, tmp_path / "last.ckpt", batch, ema=True, device="cuda")
+    out_ema = plan_ema.explain(synth.to_bcos_input(gold["images_u8"]))
+    torch.cuda.synchronize()
+    assert not torch.allclose(out_ema["logits"], out["logits"])
