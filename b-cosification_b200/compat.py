@@ -2,13 +2,64 @@
 `install_as_bcos()` registers our modules under the reference's import paths (`bcos.modules`, `bcos.common`, ...)."""
 from __future__ import annotations
 
+import importlib.machinery
+import os
 import sys
 import types
+from typing import Optional
+
+# packages of the reference whose __init__ pulls in the training stack (torchmetrics, pytorch_lightning, ftfy ...): when a
+# reference checkout is known they are registered as path-only packages so that their hot-path submodules
+# (bcos.models.resnet / standard_models / vit, CLIP.clip.model) import without it
+_PATH_ONLY = (("bcos.models", "bcos/models"), ("CLIP", "CLIP"), ("CLIP.clip", "CLIP/clip"))
 
 
-def install_as_bcos() -> None:
+def _find_reference_root(explicit: Optional[str]) -> Optional[str]:
+    cands = [explicit, os.environ.get("BCOS_REFERENCE_ROOT")]
+    real = sys.modules.get("bcos")
+    if real is not None and not getattr(real, "__bcos_b200__", False) and getattr(real, "__path__", None):
+        cands.append(os.path.dirname(list(real.__path__)[0]))
+    cands += list(sys.path)
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "bcos", "modules", "bcosconv2d.py")):
+            return os.path.abspath(c)
+    return None
+
+
+def _path_package(name: str, path: str) -> types.ModuleType:
+    m = types.ModuleType(name)
+    m.__path__ = [path]
+    m.__spec__ = importlib.machinery.ModuleSpec(name, None, is_package=True)
+    m.__spec__.submodule_search_locations = [path]
+    return m
+
+
+def install_as_bcos(reference_root: Optional[str] = None) -> Optional[str]:
+    """Register the bcos_b200 modules under the reference's import paths.
+
+    Only `bcos.modules[.*]` and `bcos.common` are replaced.  A real `bcos` package that is already imported stays in place
+    (its other subpackages - bcos.models, bcos.data, bcos.experiments, bcos.training - keep working); when none is imported,
+    `bcos` becomes a path-only package over the reference checkout (argument, $BCOS_REFERENCE_ROOT, or a sys.path entry that
+    holds bcos/modules/bcosconv2d.py), so `import bcos.models.resnet` etc. resolve to the reference's own files.
+    Returns the reference root in use (None: no checkout found, only the replaced modules are importable)."""
     from . import explain, modules
     from .modules import bcosconv2d, bcoslinear, common, logitlayer, norms
+
+    ref = _find_reference_root(reference_root)
+    top = sys.modules.get("bcos")
+    if top is None or getattr(top, "__bcos_b200__", False):
+        top = _path_package("bcos", os.path.join(ref, "bcos")) if ref else types.ModuleType("bcos")
+        if not ref:
+            top.__path__ = []
+        top.__bcos_b200__ = True
+        sys.modules["bcos"] = top
+    if ref:
+        for name, rel in _PATH_ONLY:
+            if name not in sys.modules:
+                sys.modules[name] = _path_package(name, os.path.join(ref, rel))
+                parent, _, leaf = name.rpartition(".")
+                if parent in sys.modules:
+                    setattr(sys.modules[parent], leaf, sys.modules[name])
 
     def alias(name, **attrs):
         m = sys.modules.get(name)
@@ -17,12 +68,14 @@ def install_as_bcos() -> None:
             m.__bcos_b200__ = True
             m.__path__ = []
             sys.modules[name] = m
+            parent, _, leaf = name.rpartition(".")
+            if parent in sys.modules:
+                setattr(sys.modules[parent], leaf, m)       # `bcos.modules` attribute access, also on a real parent package
         for k, v in attrs.items():
             setattr(m, k, v)
         return m
 
     pub = {k: getattr(modules, k) for k in modules.__all__ if k not in ("norms", "config", "set_precision")}
-    alias("bcos")
     alias("bcos.common", BcosUtilMixin=explain.BcosUtilMixin, explanation_mode=explain.explanation_mode,
           gradient_to_image=explain.gradient_to_image)
     alias("bcos.modules", **pub)
@@ -46,3 +99,4 @@ def install_as_bcos() -> None:
           **unc, **cen)
     alias("bcos.modules.norms.uncentered_norms", **unc)
     alias("bcos.modules.norms.utils", NoBias=norms.NoBias, Unaffine=norms.Unaffine)
+    return ref

@@ -339,12 +339,13 @@ __global__ void avgpool_bwd_mul_kernel(const T* __restrict__ gy, int nb, int h, 
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-avgpool_fwd_rows_kernel(const T* __restrict__ x, int h, int w, int c, int k, int stride, int pad, T* __restrict__ y,
+avgpool_fwd_rows_kernel(const T* __restrict__ x, int h, int w, int c, int planes, int k, int stride, int pad, T* __restrict__ y,
                         int op, int oq, float* __restrict__ sq) {
   extern __shared__ __align__(128) uint8_t pool_smem[];
   __shared__ __align__(8) uint64_t bar;
   const int img = blockIdx.y, p = blockIdx.x;
-  const uint32_t row_bytes = (uint32_t)w * c * sizeof(T);
+  const int ld = planes * c;                               // precision planes side by side in every pixel
+  const uint32_t row_bytes = (uint32_t)w * ld * sizeof(T);
   const int y0 = p * stride - pad;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
@@ -355,7 +356,7 @@ avgpool_fwd_rows_kernel(const T* __restrict__ x, int h, int w, int c, int k, int
     mbar_arrive_expect_tx(&bar, total);
     for (int dy = 0; dy < k; ++dy) {
       const int yy = y0 + dy;
-      if (yy >= 0 && yy < h) bulk_load_1d(pool_smem + dy * row_bytes, x + ((size_t)img * h + yy) * w * c, row_bytes, &bar);
+      if (yy >= 0 && yy < h) bulk_load_1d(pool_smem + dy * row_bytes, x + ((size_t)img * h + yy) * w * ld, row_bytes, &bar);
     }
   }
   __syncthreads();
@@ -377,15 +378,22 @@ avgpool_fwd_rows_kernel(const T* __restrict__ x, int h, int w, int c, int k, int
         for (int dx = 0; dx < k; ++dx) {
           const int xx = q * stride - pad + dx;
           if (xx < 0 || xx >= w) continue;
+          // the tap's fp32 value first (sum of its planes: exact), then the running sum - the order F.avg_pool2d adds in
           float f[8];
-          unpack8<T>(*reinterpret_cast<const uint4*>(pool_smem + dy * row_bytes + ((size_t)xx * c + g * 8) * sizeof(T)), f);
+          unpack8<T>(*reinterpret_cast<const uint4*>(pool_smem + dy * row_bytes + ((size_t)xx * ld + g * 8) * sizeof(T)), f);
+          for (int pl = 1; pl < planes; ++pl) {
+            float f2[8];
+            unpack8<T>(*reinterpret_cast<const uint4*>(pool_smem + dy * row_bytes + ((size_t)xx * ld + pl * c + g * 8) * sizeof(T)), f2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += f2[i];
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc[i] += f[i];
         }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] *= inv;
-      store8_planes<T>(y + (((size_t)img * op + p) * oq + q) * c + g * 8, 1, c, acc);
+      store8_planes<T>(y + (((size_t)img * op + p) * oq + q) * ld + g * 8, planes, c, acc);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sqacc = fmaf(acc[i], acc[i], sqacc);
     }
@@ -711,11 +719,15 @@ extern "C" int bcosk_avgpool_fwd(const void* x, int32_t nb, int32_t h, int32_t w
   if (!x || !y || lpp == 0) return set_error(BCOSK_EUNSUPPORTED, "avgpool_fwd: c/8 must be a power of two or a multiple of 32");
   if (nb > 65535) return set_error(BCOSK_EUNSUPPORTED, "avgpool_fwd: batch too large for the grid");
   {
-    // row-staged kernel: single plane, <= 32 lanes per pixel, k full input rows fit the default shared-memory window
-    const size_t smem = (size_t)k * w * c * 2;
-    if (planes == 1 && c / 8 <= 32 && (c / 8 & (c / 8 - 1)) == 0 && c % 8 == 0 && smem <= 48 * 1024 && op <= 65535) {
+    // row-staged kernel: <= 32 lanes per pixel, k full input rows (all planes) fit shared memory
+    const size_t smem = (size_t)k * w * planes * c * 2;
+    if (c / 8 <= 32 && (c / 8 & (c / 8 - 1)) == 0 && c % 8 == 0 && smem <= 100 * 1024 && op <= 65535) {
+      if (smem > 48 * 1024) {
+        BCOSK_DTYPE_SWITCH(dtype, BCOSK_CUDA_CHECK(cudaFuncSetAttribute(avgpool_fwd_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                         100 * 1024));)
+      }
       BCOSK_DTYPE_SWITCH(dtype, avgpool_fwd_rows_kernel<T><<<dim3(op, nb), 256, smem, S(stream)>>>(
-          reinterpret_cast<const T*>(x), h, w, c, k, stride, pad, reinterpret_cast<T*>(y), op, oq, sq);)
+          reinterpret_cast<const T*>(x), h, w, c, planes, k, stride, pad, reinterpret_cast<T*>(y), op, oq, sq);)
       BCOSK_CUDA_CHECK(cudaGetLastError());
       return BCOSK_OK;
     }

@@ -1724,11 +1724,8 @@ static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const
   auto kern = bcosk_igemm_kernel<BN, MODE, __nv_bfloat16, HP, LIGHT, PAIR>;
   auto kern_h = bcosk_igemm_kernel<BN, MODE, __half, HP, LIGHT, PAIR>;
   const void* fn = (p.dtype == BCOSK_DTYPE_BF16) ? (const void*)kern : (const void*)kern_h;
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[p.dtype]) {
-    BCOSK_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done[p.dtype] = true;
-  }
+  // per launch: the attribute belongs to (function, device); a process may drive several GPUs and threads
+  BCOSK_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const long long M = (long long)p.a_nb * p.op * p.oq;
   const long long m_tiles = (M + BM - 1) / BM;
   const long long n_tiles = (p.n + BN - 1) / BN;
@@ -1761,7 +1758,7 @@ static int launch_igemm(const LaunchMaps& mp, const bcosk_igemm_params& p, const
   return BCOSK_OK;
 }
 
-static int g_num_sms = 0;
+static int g_num_sms = 0;             // refreshed per launch from the current device (a process may drive several GPUs)
 static int g_late_in_iters = 2;        // K stages from which the epilogue input tile is fetched after the main loop (0 = never)
 static int g_cluster = 1;              // 1 none; 2/4 weight-tile multicast across row blocks; 3 = CTA pairs (cta_group::2)
 // Measured on B200 (profiles/r01_schedule_ab.md): per-tile + 3 CTAs/SM and the persistent kernel reach the same
@@ -1777,12 +1774,9 @@ static int launch_persistent(const LaunchMaps& mp, const bcosk_igemm_params& p, 
   auto kern = bcosk_igemm_persistent_kernel<MODE, __nv_bfloat16>;
   auto kern_h = bcosk_igemm_persistent_kernel<MODE, __half>;
   const void* fn = (p.dtype == BCOSK_DTYPE_BF16) ? (const void*)kern : (const void*)kern_h;
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[p.dtype]) {
-    BCOSK_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done[p.dtype] = true;
-  }
-  if (g_num_sms == 0) {
+  // per launch: the attribute belongs to (function, device); a process may drive several GPUs and threads
+  BCOSK_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  {
     int dev = 0;
     BCOSK_CUDA_CHECK(cudaGetDevice(&dev));
     BCOSK_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1879,7 +1873,7 @@ static int launch_flat_bn(const bcosk_igemm_params& p, cudaStream_t st) {
   auto kern_h = bcosk_igemm_flat_kernel<BN, MODE, __half>;
   const void* fn = (p.dtype == BCOSK_DTYPE_BF16) ? (const void*)kern : (const void*)kern_h;
   BCOSK_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (g_num_sms == 0) {
+  {
     int dev = 0;
     BCOSK_CUDA_CHECK(cudaGetDevice(&dev));
     BCOSK_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));

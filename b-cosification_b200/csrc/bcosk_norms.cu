@@ -343,13 +343,9 @@ static int launch_groupnorm_cluster(const float* x, int nb, int c, int hw, int g
   int S = 1;
   while (S < 8 && len / S > GNC_SMEM_FLOATS) S *= 2;
   if (len % (4LL * S) != 0) return BCOSK_OK;
-  static bool attr[2] = {false, false};
   const void* fn = (const void*)groupnorm_cluster_kernel<BWD>;
   const size_t smem = (size_t)GNC_SMEM_FLOATS * sizeof(float);
-  if (!attr[BWD ? 1 : 0]) {
-    BCOSK_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr[BWD ? 1 : 0] = true;
-  }
+  BCOSK_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per (function, device)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((long long)nb * groups * S));
   cfg.blockDim = dim3(GNC_THREADS);

@@ -211,12 +211,8 @@ extern "C" int bcosk_attention(const float* qkv, const float* g, int32_t batch, 
   if (dim_head != ATT_D) return set_error(BCOSK_EUNSUPPORTED, "attention: dim_head must be 64");
   const size_t smem = ((size_t)n * n + (size_t)n * (ATT_D + 1)) * sizeof(float);
   if (smem > 227 * 1024) return set_error(BCOSK_EUNSUPPORTED, "attention: sequence too long for the shared-memory kernel (n <= 208)");
-  static bool attr[2] = {false, false};
   const void* fn = backward ? (const void*)attention_kernel<true> : (const void*)attention_kernel<false>;
-  if (!attr[backward ? 1 : 0]) {
-    BCOSK_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr[backward ? 1 : 0] = true;
-  }
+  BCOSK_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per (function, device)
   if (backward) attention_kernel<true><<<batch * heads, 256, smem, S3(stream)>>>(qkv, g, n, heads, scale, out);
   else attention_kernel<false><<<batch * heads, 256, smem, S3(stream)>>>(qkv, g, n, heads, scale, out);
   BCOSK_CUDA_CHECK(cudaGetLastError());

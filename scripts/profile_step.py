@@ -15,8 +15,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--arch", default="resnet50")
 ap.add_argument("--only", default="")
-ap.add_argument("--planes", type=int, default=1)
-ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+ap.add_argument("--mode", default=None, help="engine/resnet.py PRECISION_MODES name (default: parity); overrides --planes / --dtype")
+ap.add_argument("--planes", type=int, default=None)
+ap.add_argument("--dtype", default=None, choices=["bf16", "fp16"])
 ap.add_argument("--persistent", type=int, default=0)
 ap.add_argument("--cluster", type=int, default=1)
 ap.add_argument("--autotune", type=int, default=0, help="pick per-launch schedules first (as capture() does); use with ncu --profile-from-start off")
@@ -24,8 +25,11 @@ a = ap.parse_args()
 from bcos_b200 import _lib
 _lib.load().bcosk_set_persistent(a.persistent)
 _lib.load().bcosk_set_cluster(a.cluster)
-plan = synthetic_resnet_plan(a.arch, a.batch, planes=a.planes, dtype=a.dtype, device="cuda", input_u8=True,
-                            seed_scale=4096.0 if a.dtype == "fp16" else 1.0)
+if a.planes is None and a.dtype is None:
+    plan = synthetic_resnet_plan(a.arch, a.batch, mode=a.mode or "parity", device="cuda", input_u8=True)
+else:
+    plan = synthetic_resnet_plan(a.arch, a.batch, planes=a.planes or 1, dtype=a.dtype or "bf16", device="cuda", input_u8=True,
+                                seed_scale=4096.0 if a.dtype == "fp16" else 1.0)
 imgs = torch.from_numpy(synth.synth_images_u8(32, 224, 5)).repeat((a.batch + 31) // 32, 1, 1, 1)[:a.batch].contiguous()
 plan.load_input(imgs)
 ops = plan.fwd_ops + plan.bwd_ops

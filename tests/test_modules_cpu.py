@@ -78,14 +78,12 @@ import sys, importlib.machinery, types
 sys.dont_write_bytecode = True
 sys.path.insert(0, %r); sys.path.insert(0, %r)
 from bcos_b200.compat import install_as_bcos
-install_as_bcos()
 REF = %r
 sys.path.insert(0, REF)
+assert install_as_bcos() == REF                  # finds the checkout on sys.path; no hand-made package stubs
 import bcos_b200.modules as M
-for name, path in (('bcos.models', REF + '/bcos/models'), ('CLIP', REF + '/CLIP'), ('CLIP.clip', REF + '/CLIP/clip')):
-    m = types.ModuleType(name); m.__path__ = [path]
-    m.__spec__ = importlib.machinery.ModuleSpec(name, None, is_package=True); m.__spec__.submodule_search_locations = [path]
-    sys.modules[name] = m
+import bcos.models.resnet, bcos.models.vit       # untouched reference subpackages resolve to the reference's files
+assert bcos.models.resnet.__file__.startswith(REF)
 import torch.nn as nn
 import bcosify                                   # the reference file, unmodified
 from bcos.models.standard_models import ResNetBcos
