@@ -23,11 +23,8 @@ _CT = {
 }
 
 
-def _parse_header() -> Tuple[Dict[str, int], List[Tuple[str, object]], List[str]]:
-    with open(HEADER) as fh:
-        src = fh.read()
-    defines = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(BCOSK_\w+)\s+\(?(-?\d+)\)?", src)}
-    body = re.search(r"typedef struct bcosk_igemm_params \{(.*?)\} bcosk_igemm_params;", src, re.S).group(1)
+def _parse_struct(src: str, name: str, defines: Dict[str, int]) -> List[Tuple[str, object]]:
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), src, re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields: List[Tuple[str, object]] = []
     for decl in body.split(";"):
@@ -48,11 +45,18 @@ def _parse_header() -> Tuple[Dict[str, int], List[Tuple[str, object]], List[str]
                 fields.append((arr.group(1), _CT[base] * n))
             else:
                 fields.append((nm, _CT[base]))
+    return fields
+
+
+def _parse_header():
+    with open(HEADER) as fh:
+        src = fh.read()
+    defines = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(BCOSK_\w+)\s+\(?(-?\d+)\)?", src)}
     protos = re.findall(r"^(?:int|const char\*)\s+(bcosk_\w+)\(", src, re.M)
-    return defines, fields, protos
+    return defines, _parse_struct(src, "bcosk_igemm_params", defines), _parse_struct(src, "bcosk_wgrad_params", defines), protos
 
 
-DEFINES, _FIELDS, EXPORTS = _parse_header()
+DEFINES, _FIELDS, _WGRAD_FIELDS, EXPORTS = _parse_header()
 globals().update(DEFINES)  # BCOSK_OK, BCOSK_MODE_FWD, ...
 
 
@@ -61,6 +65,10 @@ class IgemmParams(C.Structure):
 
     def set_ptr(self, name: str, tensor) -> None:
         setattr(self, name, None if tensor is None else tensor.data_ptr())
+
+
+class WgradParams(C.Structure):
+    _fields_ = _WGRAD_FIELDS
 
 
 class BcoskError(RuntimeError):
@@ -85,6 +93,8 @@ def load():
     if lib.bcosk_sizeof_igemm_params() != C.sizeof(IgemmParams):
         raise BcoskError(f"bcosk_igemm_params layout mismatch: lib {lib.bcosk_sizeof_igemm_params()} vs "
                          f"binding {C.sizeof(IgemmParams)}")
+    if lib.bcosk_sizeof_wgrad_params() != C.sizeof(WgradParams):
+        raise BcoskError(f"bcosk_wgrad_params layout mismatch: lib {lib.bcosk_sizeof_wgrad_params()} vs binding {C.sizeof(WgradParams)}")
     _lib = lib
     return lib
 
@@ -303,3 +313,66 @@ def gelu_gate(x, g, n, y) -> None:
 def attention(qkv, g, batch, n, heads, dim_head, scale, backward, out) -> None:
     check(load().bcosk_attention(_p(qkv), _p(g), batch, n, heads, dim_head, C.c_float(scale), int(backward), _p(out), _stream()),
           "bcosk_attention")
+
+
+# ------------------------------------------------------------------------------------------------
+# fine-tuning step (csrc/bcosk_train.cu, csrc/bcosk_wgrad.cu)
+# ------------------------------------------------------------------------------------------------
+def wgrad(p: "WgradParams") -> None:
+    check(load().bcosk_wgrad(C.byref(p), _stream()), "bcosk_wgrad")
+
+
+def bnu_stats_nhwc(x, rows, c, dtype, sums) -> None:
+    check(load().bcosk_bnu_stats_nhwc(_p(x), C.c_int64(rows), c, dtype, _p(sums), _stream()), "bcosk_bnu_stats_nhwc")
+
+
+def bnu_finalize(sums, rows, c, weight, eps, momentum, running_var, alpha, mean, rstd) -> None:
+    check(load().bcosk_bnu_finalize(_p(sums), C.c_int64(rows), c, _p(weight), C.c_float(eps), C.c_float(momentum), _p(running_var),
+                                    _p(alpha), _p(mean), _p(rstd), _stream()), "bcosk_bnu_finalize")
+
+
+def bnu_apply_nhwc(x, rows, c, alpha, res, relu, y, sq, dtype) -> None:
+    check(load().bcosk_bnu_apply_nhwc(_p(x), C.c_int64(rows), c, _p(alpha), _p(res), int(relu), _p(y), _p(sq), dtype, _stream()),
+          "bcosk_bnu_apply_nhwc")
+
+
+def train_bwd_reduce(ga, ga_f32, gb, xpost, tn, relu, out, out_f32, rows, c, s_out, dtype) -> None:
+    check(load().bcosk_train_bwd_reduce(_p(ga), int(ga_f32), _p(gb), _p(xpost), _p(tn), int(relu), _p(out), int(out_f32),
+                                        C.c_int64(rows), c, _p(s_out), dtype, _stream()), "bcosk_train_bwd_reduce")
+
+
+def bnu_bwd_finalize(s, rstd, weight, rows, c, kcoef, g_weight) -> None:
+    check(load().bcosk_bnu_bwd_finalize(_p(s), _p(rstd), _p(weight), C.c_int64(rows), c, _p(kcoef), _p(g_weight), _stream()),
+          "bcosk_bnu_bwd_finalize")
+
+
+def train_bwd_apply(ga, ga_f32, gb, xpost, tn, relu, out, out_f32, scale, alpha, kcoef, mean, inv_norm, rows, c, g_lin, gnt, g_y,
+                    dtype) -> None:
+    check(load().bcosk_train_bwd_apply(_p(ga), int(ga_f32), _p(gb), _p(xpost), _p(tn), int(relu), _p(out), int(out_f32), _p(scale),
+                                       _p(alpha), _p(kcoef), _p(mean), _p(inv_norm), C.c_int64(rows), c, _p(g_lin), _p(gnt), _p(g_y),
+                                       dtype, _stream()), "bcosk_train_bwd_apply")
+
+
+def grad_combine(ga, gb, x, tn, rows, c, out, dtype) -> None:
+    check(load().bcosk_grad_combine(_p(ga), _p(gb), _p(x), _p(tn), C.c_int64(rows), c, _p(out), dtype, _stream()), "bcosk_grad_combine")
+
+
+def sumpool_transpose(gnt, nb, h, w, k, stride, pad, op, oq, accumulate, tn) -> None:
+    check(load().bcosk_sumpool_transpose(_p(gnt), nb, h, w, k, stride, pad, op, oq, int(accumulate), _p(tn), _stream()),
+          "bcosk_sumpool_transpose")
+
+
+def bce_uniform_off(logits, labels, n, c, off_label, inv_temp, npix, grad_scale, loss, g_fc, g_logits, dtype) -> None:
+    check(load().bcosk_bce_uniform_off(_p(logits), _p(labels), n, c, C.c_float(off_label), C.c_float(inv_temp), npix,
+                                       C.c_float(grad_scale), _p(loss), _p(g_fc), _p(g_logits), dtype, _stream()),
+          "bcosk_bce_uniform_off")
+
+
+def gather_cast(src, idx, n, out, dtype) -> None:
+    check(load().bcosk_gather_cast(_p(src), _p(idx), C.c_int64(n), _p(out), dtype, _stream()), "bcosk_gather_cast")
+
+
+def agc_adamw(w, g, gidx, m, v, units, cols, grad_scale, lr, beta1, beta2, eps, weight_decay, clip_factor, agc_eps, step) -> None:
+    check(load().bcosk_agc_adamw(_p(w), _p(g), _p(gidx), _p(m), _p(v), units, cols, C.c_float(grad_scale), C.c_float(lr),
+                                 C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_float(clip_factor),
+                                 C.c_float(agc_eps), step, _stream()), "bcosk_agc_adamw")

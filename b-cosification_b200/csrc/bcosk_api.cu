@@ -136,6 +136,8 @@ extern "C" int bcosk_version(void) { return 100; }
 
 extern "C" int bcosk_sizeof_igemm_params(void) { return (int)sizeof(bcosk_igemm_params); }
 
+extern "C" int bcosk_sizeof_wgrad_params(void) { return (int)sizeof(bcosk_wgrad_params); }
+
 extern "C" int bcosk_device_supported(void) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;

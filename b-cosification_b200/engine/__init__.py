@@ -1,2 +1,3 @@
 """Fused execution plans over the C-ABI kernels (CUDA only; no fallback)."""
-from .resnet import PipelinedExplainer, ResNetPlan  # noqa: F401
+from .resnet import PRECISION_MODES, PipelinedExplainer, ResNetPlan  # noqa: F401
+from .train import ResNetTrainPlan  # noqa: F401

@@ -49,6 +49,7 @@ class ConvRec:
     # gain not stored (include/bcosk.h mul1_sqrt_scale): recomputed as sqrt(y * inv) from the ReLU output and 1/||patch||
     gain_y: Optional[Tensor] = None
     gain_inv: Optional[Tensor] = None
+    inv: Optional[Tensor] = None           # [M] fp32 1/||patch|| the forward launch used (kept for the training backward)
 
     @property
     def k(self) -> int:
@@ -151,12 +152,18 @@ class PlanBase:
             return 256                    # experiment: 256-wide tiles for long K loops (off: wide_k_iters = 0)
         return 128
 
+    def _pack_b(self, wt: Tensor, planes: int, kch: int) -> Tuple[Tensor, int]:
+        """[n, taps, c] fp32 -> (packed K-major device operand, chunks per tap).  The training plan overrides this to keep the
+        operand refreshable from its fp32 master weights."""
+        bmat, cpt = P.pack_b(wt, planes, kch, self.dt)
+        return self._dev(bmat, self.dt), cpt
+
     # ------------------------------------------------------------------ forward emission
     def _conv_fwd(self, name: str, x: Act, w: Tensor, stride: int, pad_lo: int, pad_hi: int, *, bn: Optional[str],
                   relu: bool, res: Optional[Act] = None, want_mask: bool = False, y_f32: bool = False,
                   inv_norm: Optional[Tensor] = None, kch: int = 64, want_sq: bool = True,
                   sq_geom: Optional[Tuple[int, int, int, int, int]] = None, lin_bias: Optional[Tensor] = None,
-                  sq_eps: Tuple[float, float] = (1e-6, 0.0), flat: bool = False) -> Tuple[Act, ConvRec]:
+                  sq_eps: Tuple[float, float] = (1e-6, 0.0), flat: bool = False, want_inv: bool = False) -> Tuple[Act, ConvRec]:
         """One fused launch: B-cos conv (+BN multiplier, +residual, +ReLU).  The patch norm comes from `x.sq`
         (per-pixel sums of squares written by x's producer) and is evaluated inside the kernel; `sq_geom`
         overrides its (h, w, k, stride, pad) when the GEMM geometry is not the convolution's (space-to-depth stem)."""
@@ -193,7 +200,7 @@ class PlanBase:
             # left for the epilogues.
             w = w * alpha.sqrt().to(w.device).view(-1, 1, 1, 1)
             alpha = None
-        bmat, cpt = P.pack_b(P.fwd_weight_taps(w), self.planes, kch, self.dt)
+        bmat, cpt = self._pack_b(P.fwd_weight_taps(w), self.planes, kch)
         block_n = self._block_n(o, bmat.shape[1] // 64)
         parts = (o + block_n - 1) // block_n
         yp = 1 if y_f32 else self.planes
@@ -212,6 +219,10 @@ class PlanBase:
                 rec.gain_inv = inv_out
             else:
                 rec.gain_inv = inv_norm
+        if want_inv and not lazy_gain:        # training: 1/||patch|| is needed again by the backward of the scale
+            if inv_norm is None and self.scale_mode != L.BCOSK_SCALE_NONE:
+                inv_out = self._empty(M, dtype=torch.float32)
+            rec.inv = inv_norm if inv_norm is not None else inv_out
         if self.with_explain:
             if not lazy_gain:
                 rec.gain = self._empty(M, o, dtype=self.gain_dt)
@@ -219,7 +230,7 @@ class PlanBase:
                 rec.mask = self._zeros(M, (o + 31) // 32, dtype=torch.int32)
         sq = self._empty(parts, M, dtype=torch.float32) if want_sq else None
         self.fwd_ops.append(O.IgemmOp(
-            name=name, a=x.t, b=self._dev(bmat, self.dt), n=o, lo=(-pad_lo, -pad_lo),
+            name=name, a=x.t, b=bmat, n=o, lo=(-pad_lo, -pad_lo),
             up=(pad_hi - (kw - 1), pad_hi - (kh - 1)), stride=(stride, stride), op=oh, oq=ow, kch=kch, chunks_per_tap=cpt,
             taps=P.conv_taps(kh, kw), seg_a_choff=P.seg_a_offsets(self.planes, cin_phys), seg_b_plane=P.seg_b_planes(self.planes), dtype=self.dt_code,
             mode=L.BCOSK_MODE_FWD, block_n=block_n, scale_mode=self.scale_mode, b_exp=self.b, relu=relu,
@@ -275,9 +286,9 @@ class PlanBase:
         wt = P.dgrad_weight_taps(rec.w)                      # [c, taps, o]
         if wt.shape[0] < n:                                  # physical input channels beyond the logical ones
             wt = torch.cat([wt, wt.new_zeros(n - wt.shape[0], *wt.shape[1:])], 0)
-        bmat, cpt = P.pack_b(wt, self.bplanes, kch, self.dt)
+        bmat, cpt = self._pack_b(wt, self.bplanes, kch)
         self.bwd_ops.append(O.IgemmOp(
-            name=rec.name + ".dgrad", a=g, b=self._dev(bmat, self.dt), n=n, lo=(lo, lo), up=(up_w, up_h), stride=(1, 1),
+            name=rec.name + ".dgrad", a=g, b=bmat, n=n, lo=(lo, lo), up=(up_w, up_h), stride=(1, 1),
             op=oh, oq=ow, kch=kch, chunks_per_tap=cpt, taps=P.conv_taps(k, k),
             seg_a_choff=P.seg_a_offsets(self.bplanes, rec.cout), seg_b_plane=P.seg_b_planes(self.bplanes), dtype=self.dt_code, mode=L.BCOSK_MODE_EXPLAIN,
             block_n=64 if (add is not None and add_stride == 1 and self.bplanes == 1 and n >= 64)
@@ -318,9 +329,9 @@ class PlanBase:
                 wt = torch.stack([rec.w[:, :, dy, dx].t() for dy, dx in sel], 1)       # [c, taps, o]
                 if wt.shape[0] < n:
                     wt = torch.cat([wt, wt.new_zeros(n - wt.shape[0], *wt.shape[1:])], 0)
-                bmat, cpt = P.pack_b(wt, self.bplanes, kch, self.dt)
+                bmat, cpt = self._pack_b(wt, self.bplanes, kch)
                 self.bwd_ops.append(O.IgemmOp(
-                    name=f"{rec.name}.dgrad.c{py}{px}", a=g, b=self._dev(bmat, self.dt), n=n, lo=(lo_w, lo_h),
+                    name=f"{rec.name}.dgrad.c{py}{px}", a=g, b=bmat, n=n, lo=(lo_w, lo_h),
                     up=(ow - g.shape[2] + lo_w, oh - g.shape[1] + lo_h), stride=(1, 1), op=oh, oq=ow, kch=kch,
                     chunks_per_tap=cpt, taps=[(jx, jy) for jy in range(ty) for jx in range(tx)],
                     seg_a_choff=P.seg_a_offsets(self.bplanes, rec.cout), seg_b_plane=P.seg_b_planes(self.bplanes), dtype=self.dt_code, mode=L.BCOSK_MODE_EXPLAIN,

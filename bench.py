@@ -63,6 +63,9 @@ def parse_args():
                          "accumulation forward, one fp16 plane in the explanation pass - meets the parity contract.  throughput: one "
                          "bf16 plane, the format BASELINE.json names - faster, does not meet the map tolerances")
     ap.add_argument("--no-throughput-record", action="store_true", help="skip the extra bf16 x1 measurement")
+    ap.add_argument("--no-train-record", action="store_true", help="skip the fine-tuning-step measurement (BASELINE config 5)")
+    ap.add_argument("--train-batch", type=int, default=64, help="images per GPU of the fine-tuning step (reference recipe: 64)")
+    ap.add_argument("--train-steps", type=int, default=8)
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline / reference-arm step (8 = the CPU's best)")
     ap.add_argument("--cpu-steps", type=int, default=64, help="steps of the in-run CPU baseline (~10-20 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -220,6 +223,11 @@ def main():
         del tplan
         torch.cuda.empty_cache()
 
+    # ---------------- extra record: the fine-tuning step (config 5), batch sharded, gradients all-reduced over NCCL ----------------
+    train = None
+    if not args.no_train_record:
+        train = measure_train_step(args, dev, rank, world, barrier, max_over_ranks)
+
     plan = synthetic_resnet_plan(args.arch, B, mode=args.mode, device=dev, input_u8=True)
     prec = plan.precision
     plan.load_input(h_in)
@@ -337,6 +345,8 @@ def main():
     }
     if thr is not None:
         res["throughput_mode"] = thr
+    if train is not None:
+        res["train_step"] = train
     if args.layer_table:
         rows = []
         for o, t in zip(all_ops, per_op):
@@ -354,6 +364,43 @@ def main():
         res["cpu_baseline"] = {"value": c["value"], "unit": "img/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]}
     print(json.dumps(res), file=real_stdout, flush=True)
     D.shutdown()
+
+
+def measure_train_step(args, dev, rank, world, barrier, max_over_ranks):
+    """BASELINE config 5: one fine-tuning step (forward in train mode, UniformOffLabelsBCE loss, full backward incl. the
+    tcgen05 weight-gradient kernel, bucketed NCCL all-reduce of the gradients on a side stream, AGC + AdamW) per call."""
+    import torch
+    from bcos_b200.engine import ResNetTrainPlan
+    from bcos_b200.models import resnet_state_shapes
+    from bcos_b200.utils import synth
+    Bt, Kt = args.train_batch, args.train_steps
+    sd = synth.synthetic_checkpoint(args.arch, resnet_state_shapes(args.arch))
+    plan = ResNetTrainPlan(args.arch, sd, Bt, dtype="bf16", device=dev, world_size=world)
+    imgs = torch.from_numpy(synth.synth_images_u8(Bt, 224, 2000 + rank)).to(dev)
+    labels = (torch.arange(Bt) * 37 + rank) % 1000
+    plan.load_batch(imgs, labels.to(dev))
+    losses = []
+    for _ in range(3):
+        losses.append(float(plan.train_step()))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(Kt):
+        plan.train_step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / Kt
+    losses.append(float(plan.loss))
+    rec = {"workload": "B-cosification fine-tuning step of ResNet-50, batch-sharded backward, NCCL gradient all-reduce (BASELINE config 5)",
+           "batch_per_gpu": Bt, "n_gpus": world, "steps": Kt, "ms_per_step": ms, "value": world * Bt / (ms * 1e-3), "unit": "img/s",
+           "dtype": "bf16 operands, fp32 accumulate / master weights / optimizer state",
+           "tflops_per_gpu": plan.train_flops() / (ms * 1e-3) / 1e12, "launches_per_step": plan.num_train_launches(),
+           "collective": None if world == 1 else f"NCCL all_reduce(sum) of {len(plan.buckets)} fp32 gradient buckets on a side stream, overlapped with the backward pass",
+           "allreduce_bytes_per_step": 0 if world == 1 else int(plan.g_flat.numel() * 4),
+           "loss_first_steps": losses[:3], "loss_last": losses[-1], "loss_decreases_on_fixed_batch": bool(losses[-1] < losses[0])}
+    del plan
+    torch.cuda.empty_cache()
+    return rec
 
 
 def _metrics(logits, maps, gold):

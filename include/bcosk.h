@@ -207,6 +207,78 @@ int bcosk_set_light(int32_t enabled);
 int bcosk_debug_a_tile(const bcosk_igemm_params* p, int32_t tile_m, int32_t chunk, void* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fine-tuning step (BASELINE config 5): reference bcos/training/trainer.py:666-784 (training_step:
+ * forward in train mode, loss, autograd backward), bcos/training/agc.py:28-42, bcos/modules/losses.py:99-139,
+ * batchnorm_uncentered.py:36-43 (batch statistics).  The gradient all-reduce is NCCL (torch.distributed) on the host side.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Weight gradient of a convolution / linear map (autograd's ConvolutionBackward grad_weight):
+ *   dw[o, (tap, c)] += sum_m g[m, o] * x_patch[m, (tap, c)],  m = output pixel of the forward launch, x_patch gathered by the
+ * forward launch's own TMA im2col traversal (same lo / up / stride / taps).  tcgen05 implicit GEMM over MN-major operands
+ * (the NHWC boxes are used as they land), split-K over the pixels with 16-byte vector reductions into dw.
+ * dw is fp32 in the packed operand layout of the forward launch, [n][num_taps * chunks_per_tap * kch]; the caller zeroes it. */
+typedef struct bcosk_wgrad_params {
+  const void* x;              /* forward input, NHWC 16-bit */
+  int32_t a_nb, a_h, a_w, a_c;
+  int32_t lo_w, lo_h, up_w, up_h, stride_w, stride_h, op, oq;
+  int32_t kch, chunks_per_tap, num_taps;
+  uint16_t tap_off_w[BCOSK_MAX_TAPS];
+  uint16_t tap_off_h[BCOSK_MAX_TAPS];
+  const void* g;              /* gradient wrt the linear output, [M, g_ld] 16-bit, dense rows */
+  int32_t n, g_ld;
+  float* dw;
+  int32_t dtype;
+  int32_t split_k;            /* CTAs along the pixel axis; 0 = choose (~4 waves) */
+} bcosk_wgrad_params;
+int bcosk_wgrad(const bcosk_wgrad_params* p, void* stream);
+int bcosk_sizeof_wgrad_params(void);
+
+/* Uncentred batch norm with batch statistics on NHWC 16-bit rows (batchnorm_uncentered.py:36-43):
+ * stats: sums[0..c) += sum_rows x, sums[c..2c) += sum_rows x^2 (caller zeroes sums);
+ * finalize: mean, rstd = 1/sqrt(E[x^2] - E[x]^2 + eps), alpha = weight * rstd, running_var EMA with the biased variance;
+ * apply: y = relu?(x * alpha[c] + res), sq[row] = sum_c y^2 (feeds the next layer's patch norm). */
+int bcosk_bnu_stats_nhwc(const void* x, int64_t rows, int32_t c, int32_t dtype, float* sums, void* stream);
+int bcosk_bnu_finalize(const float* sums, int64_t rows, int32_t c, const float* weight, float eps, float momentum,
+                       float* running_var, float* alpha, float* mean, float* rstd, void* stream);
+int bcosk_bnu_apply_nhwc(const void* x, int64_t rows, int32_t c, const float* alpha, const void* res, int32_t relu, void* y,
+                         float* sq, int32_t dtype, void* stream);
+
+/* Backward of [B-cos conv -> uncentred batch norm (batch statistics) -> (+ residual) -> ReLU] between two contractions.
+ * Incoming gradient of the layer's output z:  g_z = ga + gb + xpost * tn[row]  (data gradients of the consumers, and the
+ * consumers' patch-norm path: d||patch|| / dx = x / ||patch||);  g_y = g_z * [xpost > 0] when relu.
+ *   reduce:   s_out[c] += sum_rows g_y * out                                  (caller zeroes s_out)
+ *   finalize: kcoef[c] = -rstd^3 * weight * s / rows;  g_weight[c] = s * rstd
+ *   apply:    g_out = g_y * alpha[c] + (out - mean[c]) * kcoef[c]             (alpha NULL: g_out = g_y, no norm layer)
+ *             g_lin = 2 * g_out * scale        (out = lin |lin| / n: the B-cos scale is part of the graph, bcosconv2d.py:186-194)
+ *             gnt[row] = -sum_c g_out * out * inv_norm[row]^2;  g_y optionally stored (identity / downsample branch)
+ * ga / out may be fp32 (ga_f32 / out_f32), everything else 16-bit of `dtype`. */
+int bcosk_train_bwd_reduce(const void* ga, int32_t ga_f32, const void* gb, const void* xpost, const float* tn, int32_t relu,
+                           const void* out, int32_t out_f32, int64_t rows, int32_t c, float* s_out, int32_t dtype, void* stream);
+int bcosk_bnu_bwd_finalize(const float* s, const float* rstd, const float* weight, int64_t rows, int32_t c, float* kcoef,
+                           float* g_weight, void* stream);
+int bcosk_train_bwd_apply(const void* ga, int32_t ga_f32, const void* gb, const void* xpost, const float* tn, int32_t relu,
+                          const void* out, int32_t out_f32, const void* scale, const float* alpha, const float* kcoef,
+                          const float* mean, const float* inv_norm, int64_t rows, int32_t c, void* g_lin, float* gnt, void* g_y,
+                          int32_t dtype, void* stream);
+/* out = ga + gb + x * tn[row] (16-bit rows; gb / tn optional): gradient of a tensor that is not a norm layer's output */
+int bcosk_grad_combine(const void* ga, const void* gb, const void* x, const float* tn, int64_t rows, int32_t c, void* out,
+                       int32_t dtype, void* stream);
+/* tn[img, y, x] (+)= sum of gnt over the output pixels whose k x k window (stride, pad) covers input pixel (y, x) */
+int bcosk_sumpool_transpose(const float* gnt, int32_t nb, int32_t h, int32_t w, int32_t k, int32_t stride, int32_t pad,
+                            int32_t op, int32_t oq, int32_t accumulate, float* tn, void* stream);
+/* UniformOffLabelsBCEWithLogitsLoss (losses.py:99-139, mean reduction): loss += mean BCE(logits, clamp(one_hot, min = off_label));
+ * g_fc[n, pix, c] = d loss / d logits[n, c] * inv_temp / npix * grad_scale (through LogitLayer and the global average pool). */
+int bcosk_bce_uniform_off(const float* logits, const int32_t* labels, int32_t n, int32_t c, float off_label, float inv_temp,
+                          int32_t npix, float grad_scale, float* loss, void* g_fc, float* g_logits, int32_t dtype, void* stream);
+/* out[i] = idx[i] >= 0 ? src[idx[i]] : 0, cast to 16 bit: fp32 master weights -> packed operand layouts */
+int bcosk_gather_cast(const float* src, const int32_t* idx, int64_t n, void* out, int32_t dtype, void* stream);
+/* Unit-wise adaptive gradient clipping (agc.py:28-42; one unit = one row of `cols` elements, 1-D parameters are one unit)
+ * followed by AdamW on fp32 master weights.  The gradient of element i is g[gidx ? gidx[i] : i] * grad_scale. */
+int bcosk_agc_adamw(float* w, const float* g, const int32_t* gidx, float* m, float* v, int32_t units, int32_t cols,
+                    float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay, float clip_factor,
+                    float agc_eps, int32_t step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Bandwidth kernels (coalesced, 16-byte vectorised, warp-shuffle reductions)
  * ------------------------------------------------------------------------------------------- */
 

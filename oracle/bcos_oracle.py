@@ -816,3 +816,63 @@ def text_localisation_target(out: Tensor, zeroshot_weight: Tensor, attn_unpool: 
     if logits.dim() == 1:
         logits = logits.unsqueeze(0)
     return logits.max(1).values
+
+# ----------------------------------------------------------------------------------------------
+# fine-tuning step  (bcos/training/trainer.py:666-784 `training_step`, bcos/modules/losses.py:99-139,
+# bcos/training/agc.py:28-42; SURVEY.md 8f row 2 / BASELINE config 5)
+# ----------------------------------------------------------------------------------------------
+def uniform_off_labels_bce(logits: Tensor, labels: Tensor, off_label: Optional[float] = None) -> Tensor:
+    """`UniformOffLabelsBCEWithLogitsLoss.forward` losses.py:119-131 (reduction "mean")."""
+    num_classes = logits.shape[-1]
+    off_value = off_label or (1.0 / num_classes)
+    target = F.one_hot(labels.long(), num_classes=num_classes).to(dtype=logits.dtype).clamp(min=off_value)
+    return F.binary_cross_entropy_with_logits(logits, target, reduction="mean")
+
+
+def unitwise_norm(x: Tensor) -> Tensor:
+    """agc.py:12-25"""
+    if x.squeeze().ndim <= 1:
+        return x.norm(2.0)
+    if x.ndim in (2, 3):
+        return x.norm(2.0, dim=1, keepdim=True)
+    return x.norm(2.0, dim=(1, 2, 3), keepdim=True)
+
+
+def adaptive_clip_grad(p: Tensor, g: Tensor, clip_factor: float = 0.01, eps: float = 1e-3) -> Tensor:
+    """agc.py:28-42 for one parameter: returns the clipped gradient."""
+    max_norm = unitwise_norm(p).clamp(min=eps) * clip_factor
+    grad_norm = unitwise_norm(g)
+    clipped = g * (max_norm / grad_norm.clamp(min=1e-6))
+    return torch.where(grad_norm < max_norm, g, clipped)
+
+
+def train_step_reference(model: "OracleResNet", x6: Tensor, labels: Tensor, lr: float = 1e-4, betas=(0.9, 0.999), adam_eps: float = 1e-8,
+                         weight_decay: float = 0.0, agc_clip: float = 0.01, agc_eps: float = 1e-3, off_label: Optional[float] = None,
+                         momentum: float = 0.1) -> Dict[str, object]:
+    """One fine-tuning step in fp32: forward in train mode (batch statistics, scales in the graph), loss, autograd gradients of
+    every conv / classifier / norm weight, AGC, the first AdamW step.  Returns loss, logits, gradients, updated weights and the
+    updated running variances (all keyed like the reference's state dict)."""
+    keys = [k for k, v in model.sd.items() if v.is_floating_point() and (k.endswith(".linear.weight") or (k.endswith(".weight") and v.ndim == 1))]
+    saved = {k: model.sd[k] for k in model.sd}
+    params = {k: model.sd[k].detach().clone().requires_grad_(True) for k in keys}
+    model.sd = {**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in saved.items()}, **params}
+    model.training, model.momentum = True, momentum
+    try:
+        with torch.enable_grad():
+            logits = model.forward(x6, detach=False)
+            loss = uniform_off_labels_bce(logits, labels, off_label)
+            grads = torch.autograd.grad(loss, [params[k] for k in keys])
+        running = {k: v.detach().clone() for k, v in model.sd.items() if k.endswith("running_var")}
+    finally:
+        model.training, model.momentum = False, 0.1
+        model.sd = saved
+    grads = dict(zip(keys, grads))
+    new_w = {}
+    for k in keys:
+        p = params[k].detach()
+        g = adaptive_clip_grad(p, grads[k], agc_clip, agc_eps) if agc_clip > 0 else grads[k]
+        m = (1 - betas[0]) * g
+        v = (1 - betas[1]) * g * g
+        p2 = p * (1 - lr * weight_decay)
+        new_w[k] = p2 - lr * (m / (1 - betas[0])) / ((v / (1 - betas[1])).sqrt() + adam_eps)
+    return {"loss": loss.detach(), "logits": logits.detach(), "grads": grads, "weights": new_w, "running_var": running}
