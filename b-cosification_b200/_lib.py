@@ -322,13 +322,14 @@ def wgrad(p: "WgradParams") -> None:
     check(load().bcosk_wgrad(C.byref(p), _stream()), "bcosk_wgrad")
 
 
-def bnu_stats_nhwc(x, rows, c, dtype, sums) -> None:
-    check(load().bcosk_bnu_stats_nhwc(_p(x), C.c_int64(rows), c, dtype, _p(sums), _stream()), "bcosk_bnu_stats_nhwc")
+def bnu_stats_nhwc(x, rows, c, dtype, partials) -> None:
+    """partials: [nblk, 2c] fp32 (one row per launched block, summed in order by bnu_finalize)"""
+    check(load().bcosk_bnu_stats_nhwc(_p(x), C.c_int64(rows), c, dtype, _p(partials), partials.shape[0], _stream()), "bcosk_bnu_stats_nhwc")
 
 
-def bnu_finalize(sums, rows, c, weight, eps, momentum, running_var, alpha, mean, rstd) -> None:
-    check(load().bcosk_bnu_finalize(_p(sums), C.c_int64(rows), c, _p(weight), C.c_float(eps), C.c_float(momentum), _p(running_var),
-                                    _p(alpha), _p(mean), _p(rstd), _stream()), "bcosk_bnu_finalize")
+def bnu_finalize(partials, rows, c, weight, eps, momentum, running_var, alpha, mean, rstd) -> None:
+    check(load().bcosk_bnu_finalize(_p(partials), partials.shape[0], C.c_int64(rows), c, _p(weight), C.c_float(eps), C.c_float(momentum),
+                                    _p(running_var), _p(alpha), _p(mean), _p(rstd), _stream()), "bcosk_bnu_finalize")
 
 
 def bnu_apply_nhwc(x, rows, c, alpha, res, relu, y, sq, dtype) -> None:
@@ -336,14 +337,14 @@ def bnu_apply_nhwc(x, rows, c, alpha, res, relu, y, sq, dtype) -> None:
           "bcosk_bnu_apply_nhwc")
 
 
-def train_bwd_reduce(ga, ga_f32, gb, xpost, tn, relu, out, out_f32, rows, c, s_out, dtype) -> None:
+def train_bwd_reduce(ga, ga_f32, gb, xpost, tn, relu, out, out_f32, rows, c, partials, dtype) -> None:
     check(load().bcosk_train_bwd_reduce(_p(ga), int(ga_f32), _p(gb), _p(xpost), _p(tn), int(relu), _p(out), int(out_f32),
-                                        C.c_int64(rows), c, _p(s_out), dtype, _stream()), "bcosk_train_bwd_reduce")
+                                        C.c_int64(rows), c, _p(partials), partials.shape[0], dtype, _stream()), "bcosk_train_bwd_reduce")
 
 
-def bnu_bwd_finalize(s, rstd, weight, rows, c, kcoef, g_weight) -> None:
-    check(load().bcosk_bnu_bwd_finalize(_p(s), _p(rstd), _p(weight), C.c_int64(rows), c, _p(kcoef), _p(g_weight), _stream()),
-          "bcosk_bnu_bwd_finalize")
+def bnu_bwd_finalize(partials, rstd, weight, rows, c, kcoef, g_weight, s_out=None) -> None:
+    check(load().bcosk_bnu_bwd_finalize(_p(partials), partials.shape[0], _p(rstd), _p(weight), C.c_int64(rows), c, _p(kcoef),
+                                        _p(g_weight), _p(s_out), _stream()), "bcosk_bnu_bwd_finalize")
 
 
 def train_bwd_apply(ga, ga_f32, gb, xpost, tn, relu, out, out_f32, scale, alpha, kcoef, mean, inv_norm, rows, c, g_lin, gnt, g_y,

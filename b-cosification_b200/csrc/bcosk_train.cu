@@ -63,7 +63,7 @@ struct SlabMap {
 
 // ---------------------------------------------------------------- per-channel sums (sum x, sum x^2) over the rows
 template <typename T>
-__global__ void __launch_bounds__(256) bnu_stats_kernel(const T* __restrict__ x, long long M, int C, float* __restrict__ sums) {
+__global__ void __launch_bounds__(256) bnu_stats_kernel(const T* __restrict__ x, long long M, int C, float* __restrict__ partials) {
   extern __shared__ float sm[];          // [RP][2][C]
   const SlabMap mp(C);
   const int g = threadIdx.x % mp.G, rl = threadIdx.x / mp.G;
@@ -84,21 +84,28 @@ __global__ void __launch_bounds__(256) bnu_stats_kernel(const T* __restrict__ x,
     }
   }
   __syncthreads();
+  // every block owns one row of `partials` (fixed summation order: the statistics are bit-reproducible run to run - a
+  // random-init deep B-cos net amplifies even fp32 reordering noise of the statistics into O(10 %) gradient differences)
   for (int i = threadIdx.x; i < 2 * C; i += 256) {
     float a = 0.f;
     for (int r = 0; r < mp.RP; ++r) a += sm[r * 2 * C + i];
-    atomicAdd(sums + i, a);
+    partials[(size_t)blockIdx.x * 2 * C + i] = a;
   }
 }
 
 // mean, biased centred variance -> rstd, alpha = w * rstd; running_var <- (1 - momentum) running_var + momentum var
-__global__ void bnu_finalize_kernel(const float* __restrict__ sums, double inv_m, int C, const float* __restrict__ w, float eps,
-                                    float momentum, float* __restrict__ running_var, float* __restrict__ alpha,
+__global__ void bnu_finalize_kernel(const float* __restrict__ partials, int nblk, double inv_m, int C, const float* __restrict__ w,
+                                    float eps, float momentum, float* __restrict__ running_var, float* __restrict__ alpha,
                                     float* __restrict__ mean, float* __restrict__ rstd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double m = (double)sums[c] * inv_m;
-  double var = (double)sums[C + c] * inv_m - m * m;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s1 += (double)partials[(size_t)b * 2 * C + c];
+    s2 += (double)partials[(size_t)b * 2 * C + C + c];
+  }
+  const double m = s1 * inv_m;
+  double var = s2 * inv_m - m * m;
   if (var < 0.0) var = 0.0;
   const float r = (float)(1.0 / sqrt(var + (double)eps));
   mean[c] = (float)m;
@@ -181,7 +188,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) train_bwd_reduce_kernel(const void* __restrict__ gA, int ga_f32, const T* __restrict__ gB,
                                                                const T* __restrict__ xpost, const float* __restrict__ Tn, int relu,
                                                                const void* __restrict__ out, int out_f32, long long M, int C,
-                                                               float* __restrict__ S) {
+                                                               float* __restrict__ partials) {
   extern __shared__ float sm[];          // [RP][C]
   const SlabMap mp(C);
   const int g = threadIdx.x % mp.G, rl = threadIdx.x / mp.G;
@@ -203,18 +210,22 @@ __global__ void __launch_bounds__(256) train_bwd_reduce_kernel(const void* __res
   for (int i = threadIdx.x; i < C; i += 256) {
     float a = 0.f;
     for (int r = 0; r < mp.RP; ++r) a += sm[r * C + i];
-    atomicAdd(S + i, a);
+    partials[(size_t)blockIdx.x * C + i] = a;            // one row per block: fixed summation order
   }
 }
 
 // kcoef[c] = -rstd^3 w S / M;  g_w[c] += S rstd  (d z / d w = out * rstd)
-__global__ void bnu_bwd_finalize_kernel(const float* __restrict__ S, const float* __restrict__ rstd, const float* __restrict__ w,
-                                        double inv_m, int C, float* __restrict__ kcoef, float* __restrict__ g_w) {
+__global__ void bnu_bwd_finalize_kernel(const float* __restrict__ partials, int nblk, const float* __restrict__ rstd,
+                                        const float* __restrict__ w, double inv_m, int C, float* __restrict__ kcoef,
+                                        float* __restrict__ g_w, float* __restrict__ s_out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  double S = 0.0;
+  for (int b = 0; b < nblk; ++b) S += (double)partials[(size_t)b * C + c];
   const float r = rstd[c], ww = w != nullptr ? w[c] : 1.f;
-  kcoef[c] = (float)(-(double)r * r * r * ww * (double)S[c] * inv_m);
-  if (g_w != nullptr) g_w[c] = S[c] * r;
+  kcoef[c] = (float)(-(double)r * r * r * ww * S * inv_m);
+  if (g_w != nullptr) g_w[c] = (float)(S * r);
+  if (s_out != nullptr) s_out[c] = (float)S;
 }
 
 // g_lin, gnT (and optionally g_y) of one layer
@@ -412,23 +423,22 @@ static int check_channels(int c, const char* who) {
   return BCOSK_OK;
 }
 
-extern "C" int bcosk_bnu_stats_nhwc(const void* x, int64_t rows, int32_t c, int32_t dtype, float* sums, void* stream) {
-  if (!x || !sums) return set_error(BCOSK_EINVAL, "bnu_stats: null pointer");
+extern "C" int bcosk_bnu_stats_nhwc(const void* x, int64_t rows, int32_t c, int32_t dtype, float* partials, int32_t nblk, void* stream) {
+  if (!x || !partials || nblk < 1) return set_error(BCOSK_EINVAL, "bnu_stats: bad argument");
   int rc = check_channels(c, "bnu_stats");
   if (rc) return rc;
   const int G = c / 8, RP = 256 / G < 1 ? 1 : 256 / G;
   const size_t smem = (size_t)RP * 2 * c * sizeof(float);
-  const unsigned grid = grid_for(rows, RP * 16, 148 * 8);
-  BCOSK_T_SWITCH(dtype, bnu_stats_kernel<T><<<grid, 256, smem, S_(stream)>>>(reinterpret_cast<const T*>(x), rows, c, sums);)
+  BCOSK_T_SWITCH(dtype, bnu_stats_kernel<T><<<(unsigned)nblk, 256, smem, S_(stream)>>>(reinterpret_cast<const T*>(x), rows, c, partials);)
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }
 
-extern "C" int bcosk_bnu_finalize(const float* sums, int64_t rows, int32_t c, const float* weight, float eps, float momentum,
-                                  float* running_var, float* alpha, float* mean, float* rstd, void* stream) {
-  if (!sums || !alpha || !mean || !rstd || rows < 1) return set_error(BCOSK_EINVAL, "bnu_finalize: bad argument");
-  bnu_finalize_kernel<<<(c + 127) / 128, 128, 0, S_(stream)>>>(sums, 1.0 / (double)rows, c, weight, eps, momentum, running_var, alpha,
-                                                             mean, rstd);
+extern "C" int bcosk_bnu_finalize(const float* partials, int32_t nblk, int64_t rows, int32_t c, const float* weight, float eps,
+                                  float momentum, float* running_var, float* alpha, float* mean, float* rstd, void* stream) {
+  if (!partials || nblk < 1 || !alpha || !mean || !rstd || rows < 1) return set_error(BCOSK_EINVAL, "bnu_finalize: bad argument");
+  bnu_finalize_kernel<<<(c + 127) / 128, 128, 0, S_(stream)>>>(partials, nblk, 1.0 / (double)rows, c, weight, eps, momentum, running_var,
+                                                             alpha, mean, rstd);
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }
@@ -447,25 +457,25 @@ extern "C" int bcosk_bnu_apply_nhwc(const void* x, int64_t rows, int32_t c, cons
 }
 
 extern "C" int bcosk_train_bwd_reduce(const void* ga, int32_t ga_f32, const void* gb, const void* xpost, const float* tn, int32_t relu,
-                                      const void* out, int32_t out_f32, int64_t rows, int32_t c, float* s_out, int32_t dtype,
-                                      void* stream) {
-  if (!ga || !out || !s_out) return set_error(BCOSK_EINVAL, "train_bwd_reduce: null pointer");
+                                      const void* out, int32_t out_f32, int64_t rows, int32_t c, float* partials, int32_t nblk,
+                                      int32_t dtype, void* stream) {
+  if (!ga || !out || !partials || nblk < 1) return set_error(BCOSK_EINVAL, "train_bwd_reduce: bad argument");
   if ((relu || tn) && !xpost) return set_error(BCOSK_EINVAL, "train_bwd_reduce: ReLU mask / norm path need the layer's output tensor");
   int rc = check_channels(c, "train_bwd_reduce");
   if (rc) return rc;
   const int G = c / 8, RP = 256 / G < 1 ? 1 : 256 / G;
   const size_t smem = (size_t)RP * c * sizeof(float);
-  const unsigned grid = grid_for(rows, RP * 16, 148 * 8);
-  BCOSK_T_SWITCH(dtype, train_bwd_reduce_kernel<T><<<grid, 256, smem, S_(stream)>>>(
-      ga, ga_f32, reinterpret_cast<const T*>(gb), reinterpret_cast<const T*>(xpost), tn, relu, out, out_f32, rows, c, s_out);)
+  BCOSK_T_SWITCH(dtype, train_bwd_reduce_kernel<T><<<(unsigned)nblk, 256, smem, S_(stream)>>>(
+      ga, ga_f32, reinterpret_cast<const T*>(gb), reinterpret_cast<const T*>(xpost), tn, relu, out, out_f32, rows, c, partials);)
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }
 
-extern "C" int bcosk_bnu_bwd_finalize(const float* s, const float* rstd, const float* weight, int64_t rows, int32_t c, float* kcoef,
-                                      float* g_weight, void* stream) {
-  if (!s || !rstd || !kcoef || rows < 1) return set_error(BCOSK_EINVAL, "bnu_bwd_finalize: bad argument");
-  bnu_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, S_(stream)>>>(s, rstd, weight, 1.0 / (double)rows, c, kcoef, g_weight);
+extern "C" int bcosk_bnu_bwd_finalize(const float* partials, int32_t nblk, const float* rstd, const float* weight, int64_t rows, int32_t c,
+                                      float* kcoef, float* g_weight, float* s_out, void* stream) {
+  if (!partials || nblk < 1 || !rstd || !kcoef || rows < 1) return set_error(BCOSK_EINVAL, "bnu_bwd_finalize: bad argument");
+  bnu_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, S_(stream)>>>(partials, nblk, rstd, weight, 1.0 / (double)rows, c, kcoef, g_weight,
+                                                                 s_out);
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }

@@ -133,6 +133,7 @@ class ResNetTrainPlan(PlanBase):
         self.loss_scale = float(loss_scale)      # fp16 operands: gradients are carried scaled by this power of two
         self.bucket_bytes = int(bucket_mb * 1e6)
         self.step_count = 0
+        self.red_blocks = 296                    # blocks (= rows of partial sums) of the per-channel reductions: two per SM
         self.layers: List[TrainLayer] = []
         self.packs: List[Tuple[Tensor, Tensor]] = []          # (packed operand, int32 source index into w_flat)
         self._cur_w_off = 0
@@ -176,7 +177,8 @@ class ResNetTrainPlan(PlanBase):
         if bn is not None:
             f32 = dict(dtype=torch.float32)
             lay.alpha, lay.mean, lay.rstd = self._empty(o, **f32), self._empty(o, **f32), self._empty(o, **f32)
-            lay.sums, lay.kcoef, lay.s_red = self._empty(2 * o, **f32), self._empty(o, **f32), self._empty(o, **f32)
+            # per-block partial sums (no atomics: forward statistics and the backward reduction are bit-reproducible)
+            lay.sums, lay.kcoef, lay.s_red = self._empty(self.red_blocks, 2 * o, **f32), self._empty(o, **f32), self._empty(self.red_blocks, o, **f32)
             z = self._empty(*y.t.shape)
             zsq = self._empty(1, M, dtype=torch.float32) if want_z_sq else None
             lay.z = Act(z, o, zsq, 1)
@@ -186,7 +188,6 @@ class ResNetTrainPlan(PlanBase):
             rv = self._dev(self.sd[bn + ".running_var"])
             self.running_var[bn] = rv
             dtc = self.dt_code
-            self.fwd_ops.append(FnOp(name + ".bn.zero", lay.sums.zero_))
             self.fwd_ops.append(FnOp(name + ".bn.stats", lambda l=lay: L.bnu_stats_nhwc(l.out, l.out.shape[0], l.out.shape[1], dtc, l.sums)))
             self.fwd_ops.append(FnOp(name + ".bn.finalize", lambda l=lay, rv=rv: L.bnu_finalize(
                 l.sums, l.out.shape[0], l.out.shape[1], self.w_flat[l.bnw_off:l.bnw_off + l.out.shape[1]], self.bn_eps, self.momentum, rv,
@@ -281,7 +282,6 @@ class ResNetTrainPlan(PlanBase):
         glin = lay.rec.ghat.view(M, o)
         gy = self._empty(M, o) if want_gy else None
         if lay.bn is not None:
-            self.bwd_ops.append(FnOp(lay.name + ".bwd.zero", lay.s_red.zero_))
             self.bwd_ops.append(FnOp(lay.name + ".bwd.reduce", lambda: L.train_bwd_reduce(ga, ga_f32, gb, xpost, tn, relu, lay.out, out_f32, M, o,
                                                                                          lay.s_red, dtc)))
             self.bwd_ops.append(FnOp(lay.name + ".bwd.finalize", lambda: L.bnu_bwd_finalize(

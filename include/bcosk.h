@@ -234,11 +234,12 @@ int bcosk_wgrad(const bcosk_wgrad_params* p, void* stream);
 int bcosk_sizeof_wgrad_params(void);
 
 /* Uncentred batch norm with batch statistics on NHWC 16-bit rows (batchnorm_uncentered.py:36-43):
- * stats: sums[0..c) += sum_rows x, sums[c..2c) += sum_rows x^2 (caller zeroes sums);
- * finalize: mean, rstd = 1/sqrt(E[x^2] - E[x]^2 + eps), alpha = weight * rstd, running_var EMA with the biased variance;
+ * stats: block b of the nblk launched writes partials[b][0..c) = sum of x, partials[b][c..2c) = sum of x^2 over its rows
+ *        (no atomics: the statistics are bit-reproducible; partials is [nblk][2c] fp32, nblk ~ 2 x SM count);
+ * finalize: sums the partials in a fixed order (fp64); mean, rstd = 1/sqrt(E[x^2] - E[x]^2 + eps), alpha = weight * rstd, running_var EMA with the biased variance;
  * apply: y = relu?(x * alpha[c] + res), sq[row] = sum_c y^2 (feeds the next layer's patch norm). */
-int bcosk_bnu_stats_nhwc(const void* x, int64_t rows, int32_t c, int32_t dtype, float* sums, void* stream);
-int bcosk_bnu_finalize(const float* sums, int64_t rows, int32_t c, const float* weight, float eps, float momentum,
+int bcosk_bnu_stats_nhwc(const void* x, int64_t rows, int32_t c, int32_t dtype, float* partials, int32_t nblk, void* stream);
+int bcosk_bnu_finalize(const float* partials, int32_t nblk, int64_t rows, int32_t c, const float* weight, float eps, float momentum,
                        float* running_var, float* alpha, float* mean, float* rstd, void* stream);
 int bcosk_bnu_apply_nhwc(const void* x, int64_t rows, int32_t c, const float* alpha, const void* res, int32_t relu, void* y,
                          float* sq, int32_t dtype, void* stream);
@@ -246,16 +247,17 @@ int bcosk_bnu_apply_nhwc(const void* x, int64_t rows, int32_t c, const float* al
 /* Backward of [B-cos conv -> uncentred batch norm (batch statistics) -> (+ residual) -> ReLU] between two contractions.
  * Incoming gradient of the layer's output z:  g_z = ga + gb + xpost * tn[row]  (data gradients of the consumers, and the
  * consumers' patch-norm path: d||patch|| / dx = x / ||patch||);  g_y = g_z * [xpost > 0] when relu.
- *   reduce:   s_out[c] += sum_rows g_y * out                                  (caller zeroes s_out)
- *   finalize: kcoef[c] = -rstd^3 * weight * s / rows;  g_weight[c] = s * rstd
+ *   reduce:   partials[b][c] = sum over block b's rows of g_y * out          ([nblk][c] fp32, fixed summation order)
+ *   finalize: s = sum_b partials[b];  kcoef[c] = -rstd^3 * weight * s / rows;  g_weight[c] = s * rstd;  s_out[c] = s (optional)
  *   apply:    g_out = g_y * alpha[c] + (out - mean[c]) * kcoef[c]             (alpha NULL: g_out = g_y, no norm layer)
  *             g_lin = 2 * g_out * scale        (out = lin |lin| / n: the B-cos scale is part of the graph, bcosconv2d.py:186-194)
  *             gnt[row] = -sum_c g_out * out * inv_norm[row]^2;  g_y optionally stored (identity / downsample branch)
  * ga / out may be fp32 (ga_f32 / out_f32), everything else 16-bit of `dtype`. */
 int bcosk_train_bwd_reduce(const void* ga, int32_t ga_f32, const void* gb, const void* xpost, const float* tn, int32_t relu,
-                           const void* out, int32_t out_f32, int64_t rows, int32_t c, float* s_out, int32_t dtype, void* stream);
-int bcosk_bnu_bwd_finalize(const float* s, const float* rstd, const float* weight, int64_t rows, int32_t c, float* kcoef,
-                           float* g_weight, void* stream);
+                           const void* out, int32_t out_f32, int64_t rows, int32_t c, float* partials, int32_t nblk, int32_t dtype,
+                           void* stream);
+int bcosk_bnu_bwd_finalize(const float* partials, int32_t nblk, const float* rstd, const float* weight, int64_t rows, int32_t c,
+                           float* kcoef, float* g_weight, float* s_out, void* stream);
 int bcosk_train_bwd_apply(const void* ga, int32_t ga_f32, const void* gb, const void* xpost, const float* tn, int32_t relu,
                           const void* out, int32_t out_f32, const void* scale, const float* alpha, const float* kcoef,
                           const float* mean, const float* inv_norm, int64_t rows, int32_t c, void* g_lin, float* gnt, void* g_y,

@@ -78,7 +78,7 @@ def test_train_backward_kernels_match_torch(bcosk_lib, C, M, relu, use_bn):
     tn = torch.randn(M, device=dev) * 0.01
     w = torch.rand(C, device=dev) + 0.5
     # forward statistics with our kernels
-    sums = torch.zeros(2 * C, device=dev)
+    sums = torch.empty(37, 2 * C, device=dev)
     alpha, mean, rstd = (torch.empty(C, device=dev) for _ in range(3))
     rv = torch.ones(C, device=dev)
     L.bnu_stats_nhwc(out16, M, C, dtc, sums)
@@ -105,11 +105,11 @@ def test_train_backward_kernels_match_torch(bcosk_lib, C, M, relu, use_bn):
     g_lin_ref = 2 * g_out * s16.float()
     inv_n = 1.0 / n
     gnt_ref = -(g_out * o32).sum(1) * inv_n * inv_n
-    s_red = torch.zeros(C, device=dev)
-    kcoef, gw = torch.empty(C, device=dev), torch.empty(C, device=dev)
+    s_part = torch.empty(53, C, device=dev)
+    kcoef, gw, s_red = torch.empty(C, device=dev), torch.empty(C, device=dev), torch.empty(C, device=dev)
     if use_bn:
-        L.train_bwd_reduce(ga, False, gb, z16, tn, relu, out16, False, M, C, s_red, dtc)
-        L.bnu_bwd_finalize(s_red, rstd, w, M, C, kcoef, gw)
+        L.train_bwd_reduce(ga, False, gb, z16, tn, relu, out16, False, M, C, s_part, dtc)
+        L.bnu_bwd_finalize(s_part, rstd, w, M, C, kcoef, gw, s_red)
         assert _rel(s_red, S) < 1e-4 and _rel(gw, S * rstd) < 1e-4
     g_lin = torch.empty(M, C, device=dev, dtype=dt)
     gnt = torch.empty(M, device=dev)
@@ -216,3 +216,17 @@ def test_resnet18_train_step_matches_oracle(bcosk_lib, dtype, loss_scale, min_co
     # a second step runs on the refreshed operands and lowers the loss on the same batch
     loss2 = float(plan.train_step(torch.from_numpy(imgs), labels))
     assert math.isfinite(loss2)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NCCL all-reduce of the gradient buckets)")
+def test_two_rank_nccl_allreduce_matches_manual_sum():
+    """scripts/exp_train_ddp.py under torchrun: the bucketed side-stream all-reduce equals all_reduce of the ranks' local
+    gradients, and both ranks hold identical weights after the step"""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", os.path.join(root, "scripts", "exp_train_ddp.py")], capture_output=True, text=True, timeout=600)
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert line, out.stdout + out.stderr
+    r = json.loads(line[-1])
+    assert r["grad_sum_rel_err_vs_manual_allreduce"] < 1e-5 and r["weights_identical_across_ranks"]
