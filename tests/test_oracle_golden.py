@@ -284,3 +284,46 @@ def test_clip_unpool_text_localisation_golden(golden_dir):
         ref = _t(gold[f"p{p}.contribution_map"])
         assert abs(tgt.item() - float(gold[f"p{p}.target"][0])) < 1e-6
         assert ((cmap - ref).abs().max() / ref.abs().max()).item() < 1e-4, p
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference checkout not present (GPU box)")
+def test_oracle_train_step_pinned_to_live_reference():
+    """the oracle's fine-tuning step (train-mode forward, UniformOffLabelsBCE, autograd, AGC, first AdamW step)
+    against the reference's own modules, loss and AGC code on the same weights and batch."""
+    import make_golden as MG
+    import importlib.util
+    arch, nb, S = "resnet18", 4, 64
+    m = MG.build_reference_resnet(arch)
+    sd = synth.synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 0)
+    x6 = synth.to_bcos_input(synth.synth_images_u8(nb, S, 1))
+    labels = torch.tensor([3, 500, 999, 0])
+    m.load_state_dict(sd, strict=True)
+    MG.reference_calibrate(m, x6)
+    sd_cal = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    om = OR.OracleResNet(arch, {k: v.clone() for k, v in sd_cal.items()})
+    ref = OR.train_step_reference(om, x6, labels, lr=1e-4, agc_clip=0.01)
+
+    def load_ref(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(refload.REF, rel))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    import bcos.modules.losses as losses              # the reference's file (relative import of .common resolves through refload)
+    agc = load_ref("_ref_agc", "bcos/training/agc.py")
+    m.train()
+    params = {k: p for k, p in m.named_parameters()}
+    opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=0.0)
+    out = m(x6)
+    loss = losses.UniformOffLabelsBCEWithLogitsLoss()(out, labels)
+    loss.backward()
+    assert torch.allclose(loss.detach(), ref["loss"], rtol=1e-6, atol=1e-8)
+    assert set(ref["grads"]) == set(params)
+    for k, p in params.items():
+        assert torch.allclose(p.grad, ref["grads"][k], rtol=1e-4, atol=1e-9), k
+    agc.adaptive_clip_grad_(list(params.values()), clip_factor=0.01)
+    opt.step()
+    for k, p in params.items():
+        assert torch.allclose(p.detach(), ref["weights"][k], rtol=0, atol=1e-6), k      # 1 % of the 1e-4 step
+    for k, v in m.state_dict().items():
+        if k.endswith("running_var"):
+            assert torch.allclose(v, ref["running_var"][k], rtol=1e-5, atol=1e-8), k
