@@ -11,6 +11,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Tuple
 
+import weakref
+
 import torch
 from torch import Tensor
 
@@ -153,34 +155,107 @@ class _PlanCache:
         return lp
 
 
-class BcosMapFn(torch.autograd.Function):
-    """y = B-cos transform of x (conv geometry); backward = dynamic-linear (explanation) gradient."""
+# ---------------------------------------------------------------------------------------------------------------------
+# torch custom ops (`torch.library.custom_op` + `register_fake` + `register_autograd`).  A LayerPlan (device
+# buffers, packed weights, launch records) is not a tensor: the ops take an integer handle into `_PLANS`; everything the
+# fake-tensor tracer needs (output shapes / dtypes) is derived from the plan without touching the device.
+# ---------------------------------------------------------------------------------------------------------------------
+_PLANS: "weakref.WeakValueDictionary[int, LayerPlan]" = weakref.WeakValueDictionary()
+_next_handle = [1]
 
-    @staticmethod
-    def forward(ctx, x: Tensor, lp: LayerPlan, detach: bool, want_grad: bool):
-        y, gain = lp.forward(x, want_grad)
-        ctx.lp, ctx.detach = lp, detach
-        if gain is not None:
-            ctx.save_for_backward(*(gain if isinstance(gain, tuple) else (gain,)))
-        return y
 
-    @staticmethod
-    def backward(ctx, gy: Tensor):
-        if not ctx.detach:
-            raise NotImplementedError(
-                "bcos_b200: only the explanation-mode backward (detached dynamic scale; reference bcos/common.py:163-177) "
-                "is built; the full training backward is outside this round's scope")
-        saved = ctx.saved_tensors
-        return ctx.lp.explain_backward(gy, *saved), None, None, None
+def _handle_of(lp: LayerPlan) -> int:
+    h = getattr(lp, "_handle", None)
+    if h is None:
+        h = lp._handle = _next_handle[0]
+        _next_handle[0] += 1
+        _PLANS[h] = lp
+    return h
+
+
+def _out_geometry(lp: LayerPlan):
+    nb = lp.nb
+    oh, ow = lp.rec.out_hw
+    o = lp.mo_o if lp.max_out > 1 else lp.rec.cout
+    return nb, o, oh, ow
+
+
+@torch.library.custom_op("bcos_b200::bcos_map", mutates_args=())
+def bcos_map_op(x: Tensor, handle: int, detach: bool, want_gain: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """y = B-cos transform of x (conv geometry of plan `handle`), plus what the explanation backward needs: the gain
+    d y / d lin under the detached scale and, for MaxOut, the index of the kept unit (empty tensors when not requested)."""
+    lp = _PLANS[handle]
+    y, gain = lp.forward(x, want_gain)
+    empty = x.new_empty(0)
+    if gain is None:
+        return y, empty, empty.to(torch.uint8)
+    if isinstance(gain, tuple):
+        return y, gain[0], gain[1]
+    return y, gain, empty.to(torch.uint8)
+
+
+@bcos_map_op.register_fake
+def _bcos_map_fake(x, handle, detach, want_gain):
+    lp = _PLANS[handle]
+    nb, o, oh, ow = _out_geometry(lp)
+    y = x.new_empty((nb, o, oh, ow), dtype=torch.float32)
+    if not want_gain:
+        return y, x.new_empty(0), x.new_empty(0, dtype=torch.uint8)
+    if lp.max_out > 1:
+        return y, x.new_empty((nb * oh * ow, o), dtype=torch.float32), x.new_empty((nb * oh * ow, o), dtype=torch.uint8)
+    return y, x.new_empty((nb * oh * ow, o), dtype=lp.gain_dt), x.new_empty(0, dtype=torch.uint8)
+
+
+@torch.library.custom_op("bcos_b200::bcos_map_explain_bwd", mutates_args=())
+def bcos_map_explain_bwd_op(gy: Tensor, gain: Tensor, amax: Tensor, handle: int) -> Tensor:
+    """Dynamic-linear (explanation) gradient: W^T (g_out * gain), reference bcos/common.py:163-177 with detached scales."""
+    lp = _PLANS[handle]
+    return lp.explain_backward(gy, gain, amax if amax.numel() else None)
+
+
+@bcos_map_explain_bwd_op.register_fake
+def _bcos_map_explain_bwd_fake(gy, gain, amax, handle):
+    lp = _PLANS[handle]
+    h, w = lp.rec.in_hw
+    return gy.new_empty((lp.nb, lp.cin, h, w), dtype=torch.float32)
+
+
+def _bcos_map_setup(ctx, inputs, output):
+    _, handle, detach, want_gain = inputs
+    ctx.handle, ctx.detach, ctx.have_gain = handle, detach, want_gain
+    ctx.save_for_backward(output[1], output[2])
+
+
+def _bcos_map_backward(ctx, gy, _g_gain, _g_amax):
+    if not ctx.detach:
+        raise NotImplementedError(
+            "bcos_b200 modules: only the explanation-mode backward (detached dynamic scale; reference bcos/common.py:163-177) runs "
+            "through the module-level ops; the full training backward is engine.ResNetTrainPlan (fused fine-tuning step)")
+    if not ctx.have_gain:
+        raise RuntimeError("bcos_b200::bcos_map: backward requested but the forward ran without saving the gain")
+    gain, amax = ctx.saved_tensors
+    return torch.ops.bcos_b200.bcos_map_explain_bwd(gy.contiguous(), gain, amax, ctx.handle), None, None, None
+
+
+torch.library.register_autograd("bcos_b200::bcos_map", _bcos_map_backward, setup_context=_bcos_map_setup)
+
+
+def _is_fake(x: Tensor) -> bool:
+    try:
+        from torch._subclasses.fake_tensor import FakeTensor
+        return isinstance(x, FakeTensor)
+    except Exception:  # noqa: BLE001
+        return False
 
 
 def bcos_map(x: Tensor, cache: _PlanCache, weight: Tensor, bias: Optional[Tensor], eff_weight_fn, stride: int, pad: int,
              b: float, detach: bool, linear_eps: bool = False, max_out: int = 1) -> Tensor:
-    _require_cuda(x, "B-cos module")
+    if not _is_fake(x):
+        _require_cuda(x, "B-cos module")
     x32 = x.float().contiguous()
     lp = cache.get(weight, bias, eff_weight_fn, tuple(x32.shape), stride, pad, b, linear_eps, max_out)
     want_grad = torch.is_grad_enabled() and x.requires_grad
-    y = BcosMapFn.apply(x32, lp, detach, want_grad)
+    y = torch.ops.bcos_b200.bcos_map(x32, _handle_of(lp), bool(detach), bool(want_grad))[0]
     return y if x.dtype == torch.float32 else y.to(x.dtype)
 
 

@@ -111,8 +111,19 @@ class BcosConv2d(DetachableModule):
             raise NotImplementedError("bcos_b200: MaxOut needs out_channels % 8 == 0")
         b = float(self.b.detach()) if isinstance(self.b, torch.Tensor) else float(self.b)
         lin = self.linear
+        k, st, pd = _single(self.kernel_size), _single(self.stride), _single(self.padding)
+        if k == st and pd == 0 and k * k > 64:
+            # patch-embedding convolution (CLIP ViT conv1: 16x16 / 32x32 non-overlapping patches): the same B-cos transform is
+            # a 1x1 map over the unfolded patches, channel order (c, i, j) = the weight's own flattening; the patch norm sums
+            # the whole patch either way.  (The implicit GEMM walks at most 64 filter taps.)
+            n, c, h, w = in_tensor.shape
+            assert h % k == 0 and w % k == 0, "patch-embedding conv needs an input that is a whole number of patches"
+            xp = in_tensor.reshape(n, c, h // k, k, w // k, k).permute(0, 1, 3, 5, 2, 4).reshape(n, c * k * k, h // k, w // k)
+            return R.bcos_map(xp, self._cache, lin.weight, getattr(lin, "bias", None),
+                              lambda: self._effective_weight().reshape(lin.weight.shape[0], c * k * k, 1, 1), 1, 0, b, self.detach,
+                              max_out=self.max_out)
         return R.bcos_map(in_tensor, self._cache, lin.weight, getattr(lin, "bias", None), self._effective_weight,
-                          _single(self.stride), _single(self.padding), b, self.detach, max_out=self.max_out)
+                          st, pd, b, self.detach, max_out=self.max_out)
 
     def calc_patch_norms(self, in_tensor: Tensor) -> Tensor:
         """||patch|| per output position, [N,1,Ho,Wo] (bcosconv2d.py:196-231) through bcosk_patch_inv_norm."""
@@ -163,7 +174,9 @@ class BcosifyConv2d(BcosConv2d):
     """B-cosified convolution: plain (un-normalised) nn.Conv2d weights, optional bias (bcosifyconv2d.py:7-187)."""
 
     def __init__(self, *args, clamping: bool = False, b_loss: bool = False, **kwargs):
-        self._want_bias = bool(kwargs.get("bias", False))
+        # the reference builds its nn.Conv2d with bias=self.bias, which BcosConv2d.__init__ has set to None: no `linear.bias`
+        # exists unless from_standard_module copies one in together with the weights (bcosifyconv2d.py:14-30, 143-147)
+        self._want_bias = False
         super().__init__(*args, **kwargs)
         self.clamping = clamping
         self.b_loss = b_loss

@@ -84,8 +84,10 @@ class BcosifyLinear(BcosLinear):
         self.b_loss = b_loss
 
     def _make_linear(self, bias: bool) -> nn.Module:
-        self.bias = bias
-        return nn.Linear(in_features=self.in_features, out_features=self.out_features * self.max_out, bias=bool(bias),
+        # the reference passes bias=self.bias, which BcosLinear.__init__ leaves False/None: no `linear.bias` exists unless
+        # from_standard_module copies one in together with the weights (bcosifylinear.py:28-34, 128-132)
+        self.bias = None
+        return nn.Linear(in_features=self.in_features, out_features=self.out_features * self.max_out, bias=False,
                          device=self.device, dtype=self.dtype)
 
     @property

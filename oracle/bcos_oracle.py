@@ -671,6 +671,64 @@ class OracleCLIPResNet:
         self.training, self.momentum = False, 0.1
 
 
+# ----------------------------------------------------------------------------------------------
+# B-cos CLIP ViT image encoder (CLIP/clip/model.py:157-241 converted by bcosify.py:74-113 with clip_kd; biases and the
+# positional embedding stripped by clip_bcosification/model.py:17-25).  Only conv1, mlp.c_fc and mlp.c_proj are B-cos
+# transforms; LayerNorm, QuickGELU and the attention (incl. its out_proj weight) are the stock, non-detachable torch ops.
+# ----------------------------------------------------------------------------------------------
+def clip_vit_state_shapes(input_resolution: int = 224, patch: int = 32, width: int = 768, layers: int = 12,
+                          output_dim: int = 512) -> Dict[str, Tuple[int, ...]]:
+    s: Dict[str, Tuple[int, ...]] = {"model.class_embedding": (width,), "model.proj": (width, output_dim),
+                                     "model.conv1.linear.weight": (width, 6, patch, patch), "model.ln_pre.weight": (width,),
+                                     "model.ln_post.weight": (width,)}
+    for i in range(layers):
+        p = f"model.transformer.resblocks.{i}"
+        s[p + ".attn.in_proj_weight"] = (3 * width, width)
+        s[p + ".attn.in_proj_bias"] = (3 * width,)
+        s[p + ".attn.out_proj.linear.weight"] = (width, width)
+        s[p + ".ln_1.weight"] = (width,)
+        s[p + ".ln_2.weight"] = (width,)
+        # bcosify.py:101-103 turns the named nn.Sequential into a BcosSequential built from its values: positional keys
+        s[p + ".mlp.0.linear.weight"] = (4 * width, width)
+        s[p + ".mlp.2.linear.weight"] = (width, 4 * width)
+    return s
+
+
+class OracleCLIPViT:
+    def __init__(self, sd: Dict[str, Tensor], heads: int = 12, b: float = 2, mean=CLIP_MEAN_ADDINVERSE, std=CLIP_STD_ADDINVERSE):
+        self.sd, self.heads, self.b, self.mean, self.std = sd, heads, b, mean, std
+        self.layers = len([k for k in sd if k.endswith(".attn.in_proj_weight")])
+
+    def forward(self, x6: Tensor, detach: bool = False) -> Tensor:
+        sd = self.sd
+        x = normalize6(x6, self.mean, self.std)
+        w = sd["model.conv1.linear.weight"]
+        x = bcos_conv2d(x, w, None, w.shape[-1], 0, b=self.b, detach=detach)         # patch embedding: stride = kernel
+        x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
+        cls = sd["model.class_embedding"].to(x.dtype) + torch.zeros(x.shape[0], 1, x.shape[-1], dtype=x.dtype)
+        x = torch.cat([cls, x], dim=1)
+        d = x.shape[-1]
+        x = F.layer_norm(x, (d,), sd["model.ln_pre.weight"], None, 1e-5)
+        x = x.permute(1, 0, 2)
+        for i in range(self.layers):
+            p = f"model.transformer.resblocks.{i}"
+            y = F.layer_norm(x, (d,), sd[p + ".ln_1.weight"], None, 1e-5)
+            a, _ = F.multi_head_attention_forward(y, y, y, d, self.heads, sd[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"],
+                                                  None, None, False, 0.0, sd[p + ".attn.out_proj.linear.weight"], None,
+                                                  training=False, need_weights=False)
+            x = x + a
+            y = F.layer_norm(x, (d,), sd[p + ".ln_2.weight"], None, 1e-5)
+            y = bcos_linear(y, sd[p + ".mlp.0.linear.weight"], None, b=self.b, detach=detach)
+            y = y * torch.sigmoid(1.702 * y)
+            y = bcos_linear(y, sd[p + ".mlp.2.linear.weight"], None, b=self.b, detach=detach)
+            x = x + y
+        x = x.permute(1, 0, 2)
+        x = F.layer_norm(x[:, 0, :], (d,), sd["model.ln_post.weight"], None, 1e-5)
+        return x @ sd["model.proj"]
+
+    __call__ = forward
+
+
 def clip_seed_direction(dim: int = 1024, seed: int = 0) -> Tensor:
     """Fixed unit 'text embedding' t for the CLIP explanation target cos(emb, t)
     (interpretability/analyses/text_localisation.py:77-100 back-propagates from the image-text cosine)."""

@@ -294,6 +294,57 @@ def golden_clip_rn50(batch: int, seed: int = 0):
     print(f"[clip_rn50] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB) in {time.time()-t0:.1f}s")
 
 
+def golden_clip_vit(batch: int = 2, seed: int = 0, patch: int = 32, width: int = 768, layers: int = 12, heads: int = 12, out_dim: int = 512):
+    """north_star's "CLIP ... ViT image encoder": CLIP's VisionTransformer (ViT-B/32 geometry) converted by the reference's
+    bcosify.py with clip_kd, biases and positional embedding stripped (clip_bcosification/model.py:17-25); explanation target =
+    cos(embedding, fixed unit vector) like the CLIP RN50 golden."""
+    import torch.nn.functional as F
+    t0 = time.time()
+    refload.load()
+    import bcosify
+    from CLIP.clip.model import VisionTransformer
+    cfg = dict(is_bcos=True, name="vitclip", bcos_args=dict(b=2, max_out=1),
+               bcosify_args=dict(clip_kd=True, fix_b=True, norm_layer="BnUncV2", use_bias=False))
+    m = bcosify.BcosifyNetwork(VisionTransformer(224, patch, width, layers, heads, out_dim).float(), cfg, add_channels=True, logit_layer=False)
+    for mod in m.modules():
+        if hasattr(mod, "bias") and mod.bias is not None:
+            mod.bias = None
+        if hasattr(mod, "positional_embedding") and mod.positional_embedding is not None:
+            mod.positional_embedding = None
+    ref_shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    mine = O.clip_vit_state_shapes(224, patch, width, layers, out_dim)
+    assert ref_shapes == mine, (sorted(set(ref_shapes) ^ set(mine))[:10])
+    sd = synth.synth_state_dict(ref_shapes, seed)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    u8 = synth.synth_images_u8(batch, 224, seed)
+    x6 = synth.to_bcos_input(u8)
+    tvec = O.clip_seed_direction(out_dim, seed)
+    xb = x6.clone().requires_grad_(True)
+    with torch.enable_grad(), m.explanation_mode():
+        emb = m(xb)
+        F.cosine_similarity(emb, tvec[None], dim=1).sum().backward(inputs=[xb])
+    cmap = (xb * xb.grad).sum(1).detach()
+    emb = emb.detach()
+    om = O.OracleCLIPViT({k: v.clone() for k, v in sd.items()}, heads)
+    oe = O.explain_cosine(om.forward, x6, tvec)
+    erel = ((oe["embedding"] - emb).abs().max() / emb.abs().max()).item()
+    mrel = ((oe["contribution_map"] - cmap).abs().max() / cmap.abs().max()).item()
+    print(f"[clip_vit] oracle vs reference: embedding rel err {erel:.2e}, map rel err {mrel:.2e}")
+    assert erel < 1e-5 and mrel < 1e-4
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    e64 = O.explain_cosine(O.OracleCLIPViT(sd64, heads).forward, x6.double(), tvec.double())
+    rng = (cmap.flatten(1).max(1).values - cmap.flatten(1).min(1).values)
+    floor = ((cmap.double() - e64["contribution_map"]).abs().flatten(1).max(1).values / rng).max().item()
+    print(f"[clip_vit] reference fp32 vs fp64 evaluation: map max-abs/range {floor:.2e}; |emb| {emb.norm(dim=1).tolist()}")
+    path = os.path.join(GOLD, f"clip_vit_b32_b{batch}.npz")
+    np.savez_compressed(path, images_u8=u8, embedding=emb.numpy(), contribution_map=cmap.numpy(),
+                        contribution_map_fp64=e64["contribution_map"].float().numpy(), embedding_fp64=e64["embedding"].numpy(),
+                        fp32_noise_floor_maxabs_over_range=np.float64(floor), seed=np.int64(seed),
+                        geometry=np.array([224, patch, width, layers, heads, out_dim], dtype=np.int64))
+    print(f"[clip_vit] wrote {path} ({os.path.getsize(path)/1e6:.2f} MB) in {time.time()-t0:.1f}s")
+
+
 def golden_clip_unpool(seed: int = 0):
     """the attn_unpool head (bcosattnpool.py:23-33) and the text-localisation target
     (interpretability/analyses/text_localisation.py:68-105) on the reference CLIP RN50, image 0 of the clip_rn50_b2 golden
@@ -675,6 +726,8 @@ if __name__ == "__main__":
         golden_vit("simple_vit_b_patch16_224", 2)
     if "clip_rn50" in which:
         golden_clip_rn50(2)
+    if "clip_vit" in which:
+        golden_clip_vit(2)
     if "loc" in which:
         golden_localisation()
     if "norms" in which:

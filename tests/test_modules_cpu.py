@@ -25,9 +25,18 @@ def test_constructor_signatures_and_attributes():
     assert c.linear.weight.shape == (16, 8, 3, 3) and c.bias is None and c.detach is False
     c.set_explanation_mode(True)
     assert c.is_in_explanation_mode
+    # like the reference (checked against the live classes): the constructor never creates `linear.bias` (BcosConv2d sets
+    # self.bias = None before the nn.Conv2d is built); only from_standard_module copies one in together with the weights
     bc = M.BcosifyConv2d(8, 16, kernel_size=1, bias=True, b=2)
-    assert bc.weight is bc.linear.weight and bc.linear.bias is not None
-    assert list(bc.state_dict().keys()) == ["linear.weight", "linear.bias"]
+    assert bc.weight is bc.linear.weight and bc.linear.bias is None
+    assert list(bc.state_dict().keys()) == ["linear.weight"]
+    import torch.nn as nn
+    cfg = dict(weights=None, bcos_args=dict(b=2), bcosify_args={})
+    assert list(M.BcosifyConv2d.from_standard_module(nn.Conv2d(3, 4, 3, bias=True), cfg).state_dict()) == ["linear.weight"]
+    assert list(M.BcosifyLinear.from_standard_module(nn.Linear(8, 4, bias=True), cfg).state_dict()) == ["linear.weight"]
+    cfg["weights"] = "IMAGENET1K_V1"
+    assert list(M.BcosifyConv2d.from_standard_module(nn.Conv2d(3, 4, 3, bias=True), cfg).state_dict()) == ["linear.weight", "linear.bias"]
+    assert list(M.BcosifyLinear.from_standard_module(nn.Linear(8, 4, bias=True), cfg).state_dict()) == ["linear.weight", "linear.bias"]
     lin = M.BcosLinear(32, 10, b=2, max_out=2)
     assert lin.linear.weight.shape == (20, 32) and lin.bias is False
     bl = M.BcosifyLinear(32, 10, bias=False, b=2)
@@ -67,6 +76,20 @@ def test_resnet_builder_matches_reference_state_dict_layout_and_deepcopies():
     with m.explanation_mode():
         assert all(mod.detach for mod in m.modules() if hasattr(mod, "set_explanation_mode"))
     assert not any(mod.detach for mod in m.modules() if hasattr(mod, "set_explanation_mode"))
+
+
+def test_clip_vit_mirror_has_the_reference_state_dict_layout():
+    """CLIP ViT image encoder (CLIP/clip/model.py:166-241) after bcosify.py with clip_kd: conv1 / mlp -> B-cos modules with
+    `.linear.weight` keys, out_proj a BcosifyLinear object inside nn.MultiheadAttention, Sequentials -> BcosSequential with
+    positional keys; biases and positional embedding stripped by the factory (clip_bcosification/model.py:17-25)."""
+    from bcos_b200.clip_vit import bcosified_clip_vit
+    from bcos_oracle import clip_vit_state_shapes
+    m = bcosified_clip_vit(64, 32, 64, 2, 2, 32)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == clip_vit_state_shapes(64, 32, 64, 2, 32)
+    blk = m.model.transformer.resblocks[0]
+    assert isinstance(m.model.conv1, M.BcosifyConv2d) and isinstance(blk.mlp, M.BcosSequential)
+    assert isinstance(blk.mlp[0], M.BcosifyLinear) and isinstance(blk.attn.out_proj, M.BcosifyLinear)
+    assert m.model.positional_embedding is None and blk.mlp[0].linear.bias is None
 
 
 @pytest.mark.skipif(not refload.available(), reason="reference checkout not present (GPU box)")

@@ -70,7 +70,10 @@ def test_linear_modules_match_reference(bcosk_lib, kat, name):
 
 def test_bias_before_scale(bcosk_lib):
     g = torch.Generator().manual_seed(4)
-    mod = M.BcosifyConv2d(16, 24, kernel_size=3, padding=1, bias=True, b=2).cuda()
+    # a bias exists only where from_standard_module copies pretrained weights in (bcosifyconv2d.py:143-147)
+    cfg = dict(weights="IMAGENET1K_V1", bcos_args=dict(b=2), bcosify_args={})
+    mod = M.BcosifyConv2d.from_standard_module(torch.nn.Conv2d(16, 24, kernel_size=3, padding=1, bias=True), cfg).cuda()
+    assert mod.linear.bias is not None
     x = torch.randn(2, 16, 9, 9, generator=g)
     ref = OR.bcos_conv2d(x, mod.linear.weight.detach().cpu(), mod.linear.bias.detach().cpu(), 1, 1)
     assert _rel(mod(x.cuda()), ref.cuda()) < 2e-5
@@ -298,6 +301,38 @@ def test_module_level_clip_rn50_matches_golden(bcosk_lib, golden_dir):
     assert min(mar, mar64) <= 1e-3
 
 
+def test_module_level_clip_vit_matches_golden(bcosk_lib, golden_dir):
+    """north_star's CLIP ViT image encoder (CLIP/clip/model.py:166-241 converted by bcosify.py:74-113 with clip_kd): the patch
+    embedding and the MLP B-cos transforms run on libbcosk.so; LayerNorm / QuickGELU / nn.MultiheadAttention are the stock torch
+    modules the reference itself leaves in place.  Explanation target = cos(embedding, fixed unit vector)."""
+    from bcos_b200.clip_vit import bcosified_clip_vit
+    gold = np.load(os.path.join(golden_dir, "clip_vit_b32_b2.npz"))
+    res, patch, width, layers, heads, out_dim = gold["geometry"].tolist()
+    m = bcosified_clip_vit(res, patch, width, layers, heads, out_dim)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert shapes == OR.clip_vit_state_shapes(res, patch, width, layers, out_dim)
+    m.load_state_dict(synth.synth_state_dict(shapes, int(gold["seed"])), strict=True)
+    m = m.cuda().eval()
+    x6 = synth.to_bcos_input(gold["images_u8"]).cuda()
+    t = OR.clip_seed_direction(out_dim, int(gold["seed"])).cuda()
+    xb = x6.clone().requires_grad_(True)
+    with torch.enable_grad(), m.explanation_mode():
+        emb = m(xb)
+        torch.nn.functional.cosine_similarity(emb, t[None], dim=1).sum().backward(inputs=[xb])
+    cmap = (xb.detach() * xb.grad).sum(1)
+    e_rel = _rel(emb.detach(), torch.from_numpy(gold["embedding"]).cuda())
+    ref = torch.from_numpy(gold["contribution_map"]).cuda()
+    ref64 = torch.from_numpy(gold["contribution_map_fp64"]).cuda()
+    cos = torch.nn.functional.cosine_similarity(cmap.flatten(1).double(), ref.flatten(1).double()).min().item()
+    rng = ref.flatten(1).max(1).values - ref.flatten(1).min(1).values
+    mar = ((cmap - ref).abs().flatten(1).max(1).values / rng).max().item()
+    mar64 = ((cmap - ref64).abs().flatten(1).max(1).values / rng).max().item()
+    floor = float(gold["fp32_noise_floor_maxabs_over_range"])
+    print(f"module-level CLIP ViT-B/32: embedding rel err {e_rel:.2e}, map cosine {cos:.8f}, max-abs/range vs reference {mar:.2e} "
+          f"(reference's own fp32 floor {floor:.2e}), vs fp64 {mar64:.2e}")
+    assert e_rel <= 2e-3 and cos >= 0.999 and min(mar, mar64) <= 1e-3
+
+
 @pytest.mark.parametrize("name", ["g2_s15", "g3_s0", "g2_s3_neg", "g2_zero"])
 def test_localisation_scores_match_reference(bcosk_lib, golden_dir, name):
     """bcosk_localisation_scores against the reference's post-processing (tests/golden/localisation_kat.npz);
@@ -396,3 +431,32 @@ def test_position_norm_register_variants(bcosk_lib, c, centred):
     y = mod(xg)
     (gx,) = torch.autograd.grad((y * seed.cuda()).sum(), [xg])
     assert _rel(y.detach(), yo.detach().cuda()) < 2e-5 and _rel(gx, go.cuda()) < 2e-5
+
+
+def test_bcos_map_is_a_registered_custom_op(bcosk_lib):
+    """the module-level B-cos transform is a `torch.library.custom_op` with a fake (meta) implementation and a
+    registered autograd formula: schema / fake-tensor checks of `torch.library.opcheck`, and a module forward traced on fake
+    tensors gives the real output's shape and dtype."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from bcos_b200.modules import BcosConv2d, _runtime as R
+    torch.manual_seed(0)
+    m = BcosConv2d(8, 16, 3, padding=1).cuda()
+    x = torch.randn(2, 8, 10, 10, device="cuda", requires_grad=True)
+    with m.explanation_mode() if hasattr(m, "explanation_mode") else torch.enable_grad():
+        pass
+    m.set_explanation_mode(True)
+    y = m(x)
+    (gx,) = torch.autograd.grad(y.sum(), [x])
+    assert gx.shape == x.shape and torch.isfinite(gx).all()
+    lp = next(iter(m._cache.plans.values()))
+    h = R._handle_of(lp)
+    torch.library.opcheck(torch.ops.bcos_b200.bcos_map.default, (x.detach(), h, True, True), test_utils=("test_schema", "test_faketensor"))
+    gain = torch.ops.bcos_b200.bcos_map(x.detach(), h, True, True)[1]
+    torch.library.opcheck(torch.ops.bcos_b200.bcos_map_explain_bwd.default, (torch.ones_like(y).detach(), gain, gain.new_empty(0, dtype=torch.uint8), h),
+                          test_utils=("test_schema", "test_faketensor"))
+    with FakeTensorMode(allow_non_fake_inputs=True) as fm:
+        yf = m(fm.from_tensor(x.detach()))
+    assert tuple(yf.shape) == tuple(y.shape) and yf.dtype == y.dtype
+    m.set_explanation_mode(False)
+    with pytest.raises(NotImplementedError):
+        torch.autograd.grad(m(x).sum(), [x])

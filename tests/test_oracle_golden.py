@@ -233,6 +233,19 @@ def test_clip_rn50_golden(golden_dir):
     assert torch.nn.functional.cosine_similarity(e["contribution_map"].flatten(1), cm.flatten(1)).min().item() > 0.9999
 
 
+def test_clip_vit_golden(golden_dir):
+    """B-cos CLIP ViT image encoder (CLIP/clip/model.py:206-241 through bcosify.py with clip_kd): oracle == what the reference
+    produced (embedding and contribution map of cos(embedding, fixed unit vector)), image 0 of the golden batch."""
+    gold = np.load(os.path.join(golden_dir, "clip_vit_b32_b2.npz"))
+    res, patch, width, layers, heads, out_dim = gold["geometry"].tolist()
+    sd = synth.synth_state_dict(OR.clip_vit_state_shapes(res, patch, width, layers, out_dim), int(gold["seed"]))
+    x6 = synth.to_bcos_input(gold["images_u8"][:1])
+    e = OR.explain_cosine(OR.OracleCLIPViT(sd, heads).forward, x6, OR.clip_seed_direction(out_dim, int(gold["seed"])))
+    emb, cm = _t(gold["embedding"][:1]), _t(gold["contribution_map"][:1])
+    assert ((e["embedding"] - emb).abs().max() / emb.abs().max()).item() < 1e-4
+    assert torch.nn.functional.cosine_similarity(e["contribution_map"].flatten(1), cm.flatten(1)).min().item() > 0.9999
+
+
 def test_gradient_to_image_known_answers(golden_dir):
     """oracle restatement of gradient_to_image (bcos/common.py:387-436) == what the reference produced"""
     kat = np.load(os.path.join(golden_dir, "gradient_to_image_kat.npz"))
