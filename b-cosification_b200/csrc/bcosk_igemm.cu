@@ -114,6 +114,10 @@ __device__ __forceinline__ void epilogue_chunk_generic_inl(const bcosk_igemm_par
       for (int i = 0; i < 32; ++i)
         if (i < ncols) v[i] += __ldg(p.lin_bias + c0 + i);
     }
+    if (p.max_out > 1) {      // MaxOut: n / max_out columns leave this row (per-row stores; see maxout_fwd_tail)
+      sq_acc += maxout_fwd_tail<T, 32>(p, v, inv_norm, ri.m, yrow, c0, ncols);
+      return;
+    }
     float t[32];
     if (p.scale_mode == BCOSK_SCALE_B2) {
 #pragma unroll
@@ -434,7 +438,7 @@ template <int MODE>
 __device__ __forceinline__ bool epilogue_fast_ok(const bcosk_igemm_params& p) {
   if (MODE == BCOSK_MODE_FWD)
     return !p.y_f32 && p.y_planes == 1 && (p.gain == nullptr || !p.gain_f32) && (p.res == nullptr || p.res_planes == 1) &&
-           p.scale_mode == BCOSK_SCALE_B2 && p.lin_bias == nullptr;
+           p.scale_mode == BCOSK_SCALE_B2 && p.lin_bias == nullptr && p.max_out <= 1;
   return (p.y_f32 || p.y_planes == 1) && (p.add == nullptr || p.add_planes == 1) && (p.mul1 == nullptr || !p.mul1_f32) &&
          (p.out2 == nullptr || p.out2_planes == 1) && (p.mul2 == nullptr || !p.mul2_f32);
 }
@@ -1921,13 +1925,23 @@ static int validate(const bcosk_igemm_params& p) {
     return set_error(BCOSK_EINVAL, "igemm: inv_norm or sq_in required for a B-cos scale");
   if (!p.inv_norm && p.sq_in && (p.sq_parts < 1 || p.sq_k < 1 || p.sq_stride < 1 || p.sq_h < 1 || p.sq_w < 1))
     return set_error(BCOSK_EINVAL, "igemm: bad sq_in geometry");
-  if (p.y_ld % (p.y_f32 ? 4 : 8) != 0) return set_error(BCOSK_EINVAL, "igemm: y_ld alignment");
   if (p.a_nb < 1 || p.op < 1 || p.oq < 1) return set_error(BCOSK_EINVAL, "igemm: empty problem");
   if (p.mul1_sqrt_scale && (p.mode != BCOSK_MODE_EXPLAIN || !p.mul1 || p.mul1_f32))
     return set_error(BCOSK_EINVAL, "igemm: mul1_sqrt_scale needs explain mode and a 16-bit mul1");
   if (p.inv_norm_out && p.mode != BCOSK_MODE_FWD) return set_error(BCOSK_EINVAL, "igemm: inv_norm_out is a forward output");
   if (p.side_mapped && (p.mode != BCOSK_MODE_EXPLAIN || p.add != nullptr))
     return set_error(BCOSK_EINVAL, "igemm: side_mapped needs explain mode without an extra gradient");
+  if (p.max_out > 1) {
+    if (p.mode != BCOSK_MODE_FWD || (p.max_out != 2 && p.max_out != 4 && p.max_out != 8) || p.n % p.max_out != 0)
+      return set_error(BCOSK_EINVAL, "igemm: max_out must be 2, 4 or 8, divide n, and belongs to a forward launch");
+    if (p.alpha || p.beta || p.res || p.relu || p.maskbits || p.a_flat || p.inv_norm_out)
+      return set_error(BCOSK_EINVAL, "igemm: max_out is not combined with alpha / beta / res / relu / maskbits / a_flat / inv_norm_out");
+    if (p.amax && p.amax_ld < p.n / p.max_out) return set_error(BCOSK_EINVAL, "igemm: amax_ld < n / max_out");
+    if (p.y_ld < p.n / p.max_out || (p.gain && p.gain_ld < p.n / p.max_out))
+      return set_error(BCOSK_EINVAL, "igemm: y_ld / gain_ld < n / max_out");
+  } else if (p.y_ld % (p.y_f32 ? 4 : 8) != 0) {
+    return set_error(BCOSK_EINVAL, "igemm: y_ld alignment");
+  }
   return BCOSK_OK;
 }
 
@@ -1942,7 +1956,7 @@ static int make_maps(const bcosk_igemm_params& p, int bn, int cluster, LaunchMap
   if (rc) return rc;
   // ---- TMA epilogue (throughput mode): 16-bit single-plane tensors addressed densely by output row
   const long long M = (long long)p.a_nb * p.op * p.oq;
-  const bool tile_ok = !p.hp_accum && (bn == 64 || bn == 128);
+  const bool tile_ok = !p.hp_accum && (bn == 64 || bn == 128) && p.max_out <= 1;   // MaxOut rows leave with per-row stores
   const bool dense_out = p.os_0 == 0 && p.os_q == 1 && p.os_p == p.oq && p.os_n == (long long)p.op * p.oq;
   auto map16 = [&](CUtensorMap* m, const void* base, int ld) -> bool {
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ld % 8 != 0) return false;
@@ -1979,6 +1993,7 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return set_error(BCOSK_EINVAL, "igemm: block_n");
   if (p.hp_accum && bn > 64) return set_error(BCOSK_EINVAL, "igemm: hp_accum needs block_n <= 64");
   p.block_n = bn;
+  if (p.max_out > 1) p.sched = 1;        // MaxOut: the per-tile kernel (generic epilogue, per-row stores)
   if (p.a_flat) return launch_flat(p, reinterpret_cast<cudaStream_t>(stream));
   if (p.hp_accum) return launch_hp(p, reinterpret_cast<cudaStream_t>(stream));   // parity mode: bcosk_igemm_hp.cu
   // weight-tile multicast: 128-wide tiles with a long K loop are bound by L2 -> shared-memory traffic (A and B stages

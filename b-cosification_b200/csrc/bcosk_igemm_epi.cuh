@@ -78,6 +78,66 @@ __device__ __forceinline__ void store32_f32(float* ptr, int ncols, const float (
       reinterpret_cast<float4*>(ptr)[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// MaxOut forward tail (include/bcosk.h `max_out`): NV consecutive accumulator columns of one output row (bias already
+// added), first GEMM column c0 (a multiple of NV), NV % G == 0.  Keeps the largest unit of every group of G adjacent
+// columns (first one on ties), applies the B-cos scale of the kept unit and writes the NV/G results of this row at
+// column c0/G: y (fp32 or precision planes), gain, amax.  Returns the sum of the squared outputs as stored.
+// Per-row scalar stores: the MaxOut layers belong to the module-level path, not to the benchmarked plans.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int NV, int G>
+__device__ __forceinline__ float maxout_fwd_tail_g(const bcosk_igemm_params& p, const float (&v)[NV], float inv_norm, int64_t m_row,
+                                                   int64_t yrow, int c0, int ncols) {
+  constexpr int NO = NV / G;
+  const int o0 = c0 / G;
+  float sq = 0.f;
+#pragma unroll
+  for (int o = 0; o < NO; ++o) {
+    if (o * G < ncols) {
+      float best = v[o * G];
+      int bi = 0;
+#pragma unroll
+      for (int k = 1; k < G; ++k) {
+        const bool gt = v[o * G + k] > best;
+        best = gt ? v[o * G + k] : best;
+        bi = gt ? k : bi;
+      }
+      float t = 1.f;
+      if (p.scale_mode == BCOSK_SCALE_B2) t = fabsf(best) * inv_norm;
+      else if (p.scale_mode == BCOSK_SCALE_POW) t = __powf(fabsf(best) * inv_norm + 1e-6f, p.b_exp - 1.f);
+      float y = best * t;
+      if (p.y_f32) {
+        reinterpret_cast<float*>(p.y)[(size_t)yrow * p.y_ld + o0 + o] = y;
+      } else {
+        T* yp = reinterpret_cast<T*>(p.y) + (size_t)yrow * p.y_ld + o0 + o;
+        float r = y, acc = 0.f;
+        for (int pl = 0; pl < p.y_planes; ++pl) {
+          const float h = Cvt<T>::round1(r);
+          yp[(size_t)pl * p.y_plane_stride] = T(h);
+          r -= h;
+          acc += h;
+        }
+        y = acc;
+      }
+      if (p.gain != nullptr) {
+        if (p.gain_f32) reinterpret_cast<float*>(p.gain)[(size_t)m_row * p.gain_ld + o0 + o] = t;
+        else reinterpret_cast<T*>(p.gain)[(size_t)m_row * p.gain_ld + o0 + o] = T(t);
+      }
+      if (p.amax != nullptr) p.amax[(size_t)m_row * p.amax_ld + o0 + o] = (uint8_t)bi;
+      sq = fmaf(y, y, sq);
+    }
+  }
+  return sq;
+}
+
+template <typename T, int NV>
+__device__ __forceinline__ float maxout_fwd_tail(const bcosk_igemm_params& p, const float (&v)[NV], float inv_norm, int64_t m_row,
+                                                 int64_t yrow, int c0, int ncols) {
+  if (p.max_out == 2) return maxout_fwd_tail_g<T, NV, 2>(p, v, inv_norm, m_row, yrow, c0, ncols);
+  if (p.max_out == 4) return maxout_fwd_tail_g<T, NV, 4>(p, v, inv_norm, m_row, yrow, c0, ncols);
+  return maxout_fwd_tail_g<T, NV, 8>(p, v, inv_norm, m_row, yrow, c0, ncols);
+}
+
 // Library-internal launch state (decided by the host launcher, see launch_igemm)
 struct IgemmAux {
   int tma_in;    // 0 none, 1 = forward residual, 2 = explain mul1: prefetched as a tile into the last pipeline slot

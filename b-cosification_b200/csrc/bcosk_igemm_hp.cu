@@ -609,6 +609,10 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] += __ldg(p.lin_bias + cg + i);
               }
+              if (p.max_out > 1) {     // MaxOut: 8 / max_out columns of this row leave through per-row stores
+                sq_acc += maxout_fwd_tail<T, 8>(p, v, inv_norm, ri.m, yrow, cg, 8);
+                continue;
+              }
               float t[8];
               const float4 a0 = *reinterpret_cast<const float4*>(s_alpha + j * 32 + g * 8);
               const float4 a1 = *reinterpret_cast<const float4*>(s_alpha + j * 32 + g * 8 + 4);
@@ -852,7 +856,7 @@ static int launch_hp_mode(const bcosk_igemm_params& p, cudaStream_t st) {
   // the chunk length of the leading segment.
   aux.xchunk = p.dtype == BCOSK_DTYPE_F16 ? (1 << 20) : aux.chunk;
   if (g_hp_xchunk > 0) aux.xchunk = g_hp_xchunk;
-  if (g_hp_stage_boxes & 1) {
+  if ((g_hp_stage_boxes & 1) && p.max_out <= 1) {      // MaxOut rows (n / max_out columns) leave with per-row stores
     if (!p.y_f32 && dense_out && planes_ok(p.y_planes) && p.y_planes <= 3 && map16(&mout1, p.y, p.y_ld, M)) aux.out1_planes = p.y_planes;
     if (MODE == BCOSK_MODE_FWD) {
       if (p.gain && p.gain_f32 && map32(&mout2, p.gain, p.gain_ld, M)) aux.out2_kind = 1;

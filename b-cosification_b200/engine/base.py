@@ -50,6 +50,7 @@ class ConvRec:
     gain_y: Optional[Tensor] = None
     gain_inv: Optional[Tensor] = None
     inv: Optional[Tensor] = None           # [M] fp32 1/||patch|| the forward launch used (kept for the training backward)
+    amax: Optional[Tensor] = None          # MaxOut: [M, cout / max_out] uint8 index of the kept unit of every group
 
     @property
     def k(self) -> int:
@@ -163,10 +164,13 @@ class PlanBase:
                   relu: bool, res: Optional[Act] = None, want_mask: bool = False, y_f32: bool = False,
                   inv_norm: Optional[Tensor] = None, kch: int = 64, want_sq: bool = True,
                   sq_geom: Optional[Tuple[int, int, int, int, int]] = None, lin_bias: Optional[Tensor] = None,
-                  sq_eps: Tuple[float, float] = (1e-6, 0.0), flat: bool = False, want_inv: bool = False) -> Tuple[Act, ConvRec]:
+                  sq_eps: Tuple[float, float] = (1e-6, 0.0), flat: bool = False, want_inv: bool = False,
+                  max_out: int = 1) -> Tuple[Act, ConvRec]:
         """One fused launch: B-cos conv (+BN multiplier, +residual, +ReLU).  The patch norm comes from `x.sq`
         (per-pixel sums of squares written by x's producer) and is evaluated inside the kernel; `sq_geom`
-        overrides its (h, w, k, stride, pad) when the GEMM geometry is not the convolution's (space-to-depth stem)."""
+        overrides its (h, w, k, stride, pad) when the GEMM geometry is not the convolution's (space-to-depth stem).
+        `max_out` = G > 1: the o GEMM columns are o/G groups of G adjacent units; the epilogue keeps the largest unit of each
+        group, scales it and writes o/G columns (y, gain) plus the kept index (`rec.amax`), bcosconv2d.py:166-170."""
         nb = self.nb
         h, wd = x.hw
         o, c, kh, kw = w.shape
@@ -177,7 +181,9 @@ class PlanBase:
         assert c <= cin_phys
         # stride-1 k x k convs over 64 channels with <= 64 outputs (ResNet layer1 conv2): flat-window gather, the zero
         # borders are produced in shared memory by the TMA box (include/bcosk.h a_flat = 2)
-        flat = flat or (self.flat_3x3 and self.planes == 1 and not self.hp_accum and stride == 1 and kh == kw and kh > 1
+        if max_out > 1:
+            assert max_out in (2, 4, 8) and o % max_out == 0 and bn is None and not relu and res is None and not want_mask and not flat
+        flat = flat or (self.flat_3x3 and max_out == 1 and self.planes == 1 and not self.hp_accum and stride == 1 and kh == kw and kh > 1
                         and cin_phys == 64 and kch == 64 and o <= 64 and res is None and not y_f32 and x.t.is_contiguous())
         sq_in = None
         if inv_norm is None and self.scale_mode != L.BCOSK_SCALE_NONE:
@@ -204,11 +210,12 @@ class PlanBase:
         block_n = self._block_n(o, bmat.shape[1] // 64)
         parts = (o + block_n - 1) // block_n
         yp = 1 if y_f32 else self.planes
-        y = self._empty(nb, oh, ow, yp * o, dtype=torch.float32 if y_f32 else self.dt)
+        oy = o // max_out                 # columns that leave the epilogue
+        y = self._empty(nb, oh, ow, yp * oy, dtype=torch.float32 if y_f32 else self.dt)
         rec = ConvRec(name, w, stride, pad_lo, pad_hi, (h, wd), (oh, ow), cin_phys)
         # y = lin |lin| / n, clamped at 0: the explanation gain |lin| / n is sqrt(y / n) - not stored where that holds
         # (ReLU, no residual, BN multiplier folded, b = 2, throughput mode)
-        lazy_gain = (self.with_explain and self.recompute_gain and self.planes == 1 and not self.hp_accum and relu
+        lazy_gain = (self.with_explain and self.recompute_gain and max_out == 1 and self.planes == 1 and not self.hp_accum and relu
                      and res is None and alpha is None and beta is None and lin_bias is None and not y_f32
                      and self.scale_mode == L.BCOSK_SCALE_B2)
         inv_out = None
@@ -225,7 +232,9 @@ class PlanBase:
             rec.inv = inv_norm if inv_norm is not None else inv_out
         if self.with_explain:
             if not lazy_gain:
-                rec.gain = self._empty(M, o, dtype=self.gain_dt)
+                rec.gain = self._empty(M, oy, dtype=self.gain_dt)
+            if max_out > 1:
+                rec.amax = torch.zeros(M, oy, dtype=torch.uint8, device=self.device)
             if want_mask:
                 rec.mask = self._zeros(M, (o + 31) // 32, dtype=torch.int32)
         sq = self._empty(parts, M, dtype=torch.float32) if want_sq else None
@@ -238,10 +247,10 @@ class PlanBase:
             lin_bias=None if lin_bias is None else self._dev(lin_bias),
             res=None if res is None else res.t, res_planes=self.planes,
             gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32, hp_accum=self.hp_accum, hp_chunk=self.hp_chunk, flat=flat,
-            inv_norm_out=inv_out,
+            inv_norm_out=inv_out, max_out=max_out, amax=rec.amax,
             algo_flops=2.0 * M * o * float((w != 0).sum().item()) / o))
         rec.algo_flops = self.fwd_ops[-1].algo_flops
-        return Act(y, o, sq, parts), rec
+        return Act(y, oy, sq, parts), rec
 
     # ------------------------------------------------------------------ explanation emission
     @staticmethod

@@ -76,6 +76,8 @@ class IgemmOp:
     side_mapped: bool = False        # include/bcosk.h `side_mapped`: mul1 / out2 / ... follow the mapped output row
     inv_norm_out: Optional[Tensor] = None      # forward: [M] fp32, receives the 1/||patch|| the launch used
     mul1_sqrt_scale: Optional[Tensor] = None   # explain: mul1 holds the producer's ReLU output, gain = sqrt(mul1 * this[row])
+    max_out: int = 1                           # include/bcosk.h `max_out`: groups of adjacent units reduced in the forward epilogue
+    amax: Optional[Tensor] = None              # [M, n / max_out] uint8: index of the kept unit
 
     # ---- derived ----
     @property
@@ -217,6 +219,10 @@ class IgemmOp:
         p.side_mapped = int(self.side_mapped)
         p.set_ptr("inv_norm_out", self.inv_norm_out)
         p.set_ptr("mul1_sqrt_scale", self.mul1_sqrt_scale)
+        if self.max_out > 1:
+            p.max_out = self.max_out
+            if self.amax is not None:
+                p.amax, p.amax_ld = self.amax.data_ptr(), self.amax.shape[-1]
         if self.flat and self.a.is_contiguous():
             p.a_flat = 2                      # dense tensor: the zero borders are made in shared memory
             assert self.stride == (1, 1) and len(self.seg_a_choff) == 1 and self.chunks_per_tap == 1 and self.n <= 64

@@ -44,11 +44,14 @@ class LayerPlan(PlanBase):
     def __init__(self, weight: Tensor, bias: Optional[Tensor], in_shape: Tuple[int, int, int, int], stride: int, pad: int,
                  b: float, linear_eps: bool, max_out: int = 1):
         nb, cin, h, w = in_shape
-        # MaxOut: the launch computes the plain linear map of all O*M units (scale mode NONE); the maximum over each group
-        # and the B-cos scale of the kept unit follow in bcosk_maxout_bcos_fwd
+        # MaxOut over 2 / 4 / 8 units runs INSIDE the conv launch's epilogue (include/bcosk.h `max_out`: adjacent-column
+        # maximum, scale of the kept unit, kept index).  Other group sizes (3: a group would straddle the 8-column register
+        # groups of the epilogue): the launch computes the plain linear map of all O*M units (scale mode NONE) and
+        # bcosk_maxout_bcos_fwd reduces and scales in a second pass.
         self.max_out, self.b_real = max_out, float(b)
+        self.mo_fused = max_out in (2, 4, 8)
         super().__init__(nb, planes=config.planes, dtype=config.dtype, device=weight.device, explain=True,
-                         b=b if max_out == 1 else 1.0)
+                         b=b if (max_out == 1 or self.mo_fused) else 1.0)
         self.cin, self.cp = cin, (cin + 7) // 8 * 8
         o, _, kh, kw = weight.shape
         self.x = Act(self._empty(nb, h, w, self.planes * self.cp), self.cp, self._empty(1, nb * h * w, dtype=torch.float32), 1)
@@ -57,7 +60,8 @@ class LayerPlan(PlanBase):
             wpad = torch.cat([wpad, wpad.new_zeros(o, self.cp - cin, kh, kw)], 1)
         self.y, self.rec = self._conv_fwd("module", self.x, wpad, stride, pad, pad, bn=None, relu=False, y_f32=True,
                                           want_sq=False, lin_bias=None if bias is None else bias.detach().float(),
-                                          sq_eps=(0.0, 1e-12) if linear_eps else (1e-6, 0.0))
+                                          sq_eps=(0.0, 1e-12) if linear_eps else (1e-6, 0.0),
+                                          max_out=max_out if self.mo_fused else 1)
         self.fwd_op = self.fwd_ops[-1]
         self._alloc_ghat(self.rec)
         dense = self.rec.stride > 1 and self.rec.k == 1
@@ -75,7 +79,7 @@ class LayerPlan(PlanBase):
             self.mo_inv = self._empty(self.mo_rows, dtype=torch.float32)
             eps_in, eps_out = (0.0, 1e-12) if linear_eps else (1e-6, 0.0)
             self.mo_norm = O.PatchNormOp("module.norm", self.x.sq, 1, nb, h, w, kh, stride, pad, eps_in, eps_out, self.mo_inv, oh, ow)
-            self.mo_y = self._empty(nb, oh, ow, self.mo_o, dtype=torch.float32)
+            self.mo_y = self.y.t if self.mo_fused else self._empty(nb, oh, ow, self.mo_o, dtype=torch.float32)
             self.mo_g16 = self._empty(self.mo_rows, self.planes * self.mo_o)
 
     # ---- forward: x NCHW fp32 -> y NCHW fp32 (and the gain tensor when an explanation backward may follow)
@@ -83,6 +87,15 @@ class LayerPlan(PlanBase):
         nb, _, h, w = x.shape
         L.nchw_to_nhwc16(x, self.x.t, self.cp, self.planes, self.dt_code, None, self.x.sq)
         o = self.rec.cout
+        if self.max_out > 1 and self.mo_fused:
+            gain = torch.empty(self.mo_rows, self.mo_o, dtype=torch.float32, device=x.device) if want_gain else None
+            amax = torch.empty(self.mo_rows, self.mo_o, dtype=torch.uint8, device=x.device) if want_gain else None
+            self.fwd_op.gain, self.fwd_op.amax = gain, amax
+            for op in self.fwd_ops:        # [stand-alone patch norm for large windows,] the fused conv + MaxOut launch
+                op.run()
+            out = torch.empty(nb, self.mo_o, *self.rec.out_hw, dtype=torch.float32, device=x.device)
+            L.nhwc_to_nchw_f32(self.y.t, nb, self.mo_o, self.rec.out_hw[0], self.rec.out_hw[1], 1, self.dt_code, out)
+            return out, (None if gain is None else (gain, amax))
         if self.max_out > 1:
             self.fwd_op.gain = None
             for op in self.fwd_ops:

@@ -164,6 +164,16 @@ typedef struct bcosk_igemm_params {
    *      sqrt(mul1 * mul1_sqrt_scale[row]).  Both are addressed like mul1 (dense row, or mapped row with side_mapped). */
   float* inv_norm_out;
   const float* mul1_sqrt_scale;
+  /* ---- MaxOut in the forward epilogue (BcosConv2d.forward_impl bcosconv2d.py:166-170, BcosLinear.forward
+   *      bcoslinear.py:107-110).  max_out = G > 1: the n GEMM columns are n/G groups of G ADJACENT units (unit c = o*G + k,
+   *      the reference's unflatten(dim=1, (O, G))).  The epilogue keeps the largest unit of every group (the first one on
+   *      ties, like torch.max), computes the B-cos scale from the kept unit and writes n/G columns per row: y (fp32 or
+   *      precision planes, row pitch y_ld), gain (the scale of the kept unit, row pitch gain_ld), amax (optional, uint8
+   *      [M][amax_ld]: k of the kept unit - the only unit the explanation gradient reaches), sq_out (sum of the kept
+   *      outputs squared).  G in {2, 4, 8}, n % G == 0; not combined with alpha / beta / res / relu / maskbits / a_flat.
+   *      0 and 1 both mean "no MaxOut". */
+  uint8_t* amax;
+  int32_t max_out, amax_ld;
 } bcosk_igemm_params;
 
 int bcosk_igemm(const bcosk_igemm_params* p, void* stream);

@@ -112,6 +112,14 @@ def run_igemm(op: O.IgemmOp) -> None:
             sp = torch.nn.functional.avg_pool2d(sq, k, stride=st, padding=pd, divisor_override=1)
             assert sp.shape[-2:] == (op.op, op.oq), (op.name, sp.shape, op.op, op.oq)
             inv_norm = (1.0 / ((sp + op.sq_eps[0]).sqrt() + op.sq_eps[1])).reshape(-1)
+        if op.max_out > 1:     # adjacent-column MaxOut: keep the largest unit of each group (first on ties), scale it
+            G = op.max_out
+            best, idx = D.view(M, n // G, G).max(dim=2)
+            # torch.max may return any index on exact ties; the kernel keeps the first
+            idx = (D.view(M, n // G, G) == best[..., None]).float().argmax(dim=2)
+            D, n = best, n // G
+            if op.amax is not None:
+                op.amax.copy_(idx.to(torch.uint8))
         alpha = op.alpha.float() if op.alpha is not None else torch.ones(n)
         beta = op.beta.float() if op.beta is not None else torch.zeros(n)
         if op.scale_mode == L.BCOSK_SCALE_B2:
@@ -147,7 +155,7 @@ def run_igemm(op: O.IgemmOp) -> None:
             # (fast path: sums of squares of the stored, i.e. rounded, values - same as the generic path)
             y2[rows] = tmp
         if op.sq_out is not None:
-            bn = op.resolved_block_n()
+            bn = op.resolved_block_n() // max(op.max_out, 1)     # stored columns per n tile
             for ti in range(op.sq_out.shape[0]):
                 op.sq_out[ti] = (stored[:, ti * bn:(ti + 1) * bn] ** 2).sum(1)
     else:

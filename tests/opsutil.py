@@ -10,7 +10,7 @@ from torch import Tensor
 from bcos_b200.engine import ops as O
 
 OUTPUT_FIELDS = {
-    O.IgemmOp: ["y", "gain", "maskbits", "sq_out", "out2"],
+    O.IgemmOp: ["y", "gain", "maskbits", "sq_out", "out2", "amax"],
     O.InputPrepOp: ["out", "sq"],
     O.PatchNormOp: ["inv_norm"],
     O.AvgPoolFwdOp: ["y", "sq"],
@@ -71,10 +71,11 @@ def compare(op_ref, op_dev, tol: float, fields: Iterable[str] | None = None) -> 
         planes = _planes_of(op_ref, name)
         if planes > 1 and r.dtype not in (torch.int32, torch.int64, torch.float32):
             r, d = _join(r.cpu(), planes), _join(d.cpu(), planes)
-        if r.dtype in (torch.int32, torch.int64):
+        if r.dtype in (torch.int32, torch.int64, torch.uint8):
             mism = (r.cpu() != d.cpu()).float().mean().item()
             errs[name] = mism
-            assert mism <= (2e-3 if name == "maskbits" else 0.0), (op_ref.name, name, mism)
+            # ReLU decisions / kept MaxOut units of values that tie to the last bit may fall the other way
+            assert mism <= (2e-3 if name in ("maskbits", "amax") else 0.0), (op_ref.name, name, mism)
         else:
             e = max_rel_err(d, r)
             errs[name] = e

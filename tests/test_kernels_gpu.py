@@ -108,6 +108,32 @@ def test_igemm_forward_general_b(bcosk_lib):
     print(_run_and_compare(plan.fwd_ops, tol32=2e-4))
 
 
+MAXOUT_CASES = [
+    # name, planes, G, cout (GEMM columns), k, b, bias, y_f32
+    ("mo2_1plane_16bit", 1, 2, 128, 3, 2.0, False, False),
+    ("mo4_1plane_f32_bias", 1, 4, 64, 1, 2.0, True, True),
+    ("mo2_hp3_f32", 3, 2, 64, 3, 2.0, False, True),
+    ("mo8_hp3_f32_b2p5_bias", 3, 8, 72, 1, 2.5, True, True),
+    ("mo2_hp2_planes_out", 2, 2, 128, 1, 2.0, False, False),
+]
+
+
+@pytest.mark.parametrize("case", MAXOUT_CASES, ids=[c[0] for c in MAXOUT_CASES])
+def test_igemm_forward_maxout_in_epilogue(bcosk_lib, case):
+    """include/bcosk.h `max_out`: adjacent-column maximum + scale of the kept unit + kept index inside the conv launch
+    (bcosconv2d.py:166-170), generic epilogue of the throughput kernel and of the parity-mode kernel."""
+    name, planes, G, cout, k, b, bias, y_f32 = case
+    g = torch.Generator().manual_seed(hash(name) % 2**31)
+    plan = _mini_plan(2, planes, b=b)
+    x = _rand_act(g, 2, 9, 9, 64, planes)
+    w = torch.randn(cout, 64, k, k, generator=g) / math.sqrt(64 * k * k)
+    lb = torch.randn(cout, generator=g) * 0.1 if bias else None
+    y, rec = plan._conv_fwd(name, x, w, 1, k // 2, k // 2, bn=None, relu=False, y_f32=y_f32, lin_bias=lb, max_out=G)
+    assert y.t.shape[-1] == (1 if y_f32 else planes) * cout // G and rec.gain.shape[-1] == cout // G and rec.amax.shape[-1] == cout // G
+    errs = _run_and_compare(plan.fwd_ops, tol16=BF16_TOL if planes == 1 else 2e-4, tol32=2e-4 if (planes > 1 or b != 2.0) else None)
+    print(name, errs)
+
+
 DGRAD_CASES = [
     # name, nb, h_in, cin, cout, k, stride, pad, planes
     ("d_1x1", 2, 12, 64, 128, 1, 1, 0, 1),
