@@ -253,6 +253,16 @@ def nchw_to_nhwc16(x, out, cp, planes, dtype, mul=None, sq=None) -> None:
                                       0 if mul is None else mul.shape[-1], _p(sq), _stream()), "bcosk_nchw_to_nhwc16")
 
 
+def seed_from_nchw(g, seed_scale, mul1, out1, mask2, mul2, out2, planes, dtype) -> None:
+    import torch
+    nb, c, h, w = g.shape
+    assert g.dtype == torch.float32 and g.is_contiguous()
+    check(load().bcosk_seed_from_nchw(_p(g), nb, c, h, w, C.c_float(seed_scale), _p(mul1),
+                                      int(mul1 is not None and mul1.dtype == torch.float32), _p(out1), _p(mask2), _p(mul2),
+                                      int(mul2 is not None and mul2.dtype == torch.float32), _p(out2), planes, dtype, _stream()),
+          "bcosk_seed_from_nchw")
+
+
 def nhwc_to_nchw_f32(y, nb, c, h, w, planes, dtype, out) -> None:
     import torch
     check(load().bcosk_nhwc_to_nchw_f32(_p(y), int(y.dtype == torch.float32), nb, c, h, w, y.shape[-1], planes, dtype, _p(out),

@@ -188,6 +188,119 @@ extern "C" int bcosk_channel_stats_nchw(const float* x, int32_t nb, int32_t c, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// Seed of a fused trunk's explanation pass from a gradient computed outside the plan (the attention-pool head of the CLIP
+// encoders runs on the module-level path): g NCHW fp32 -> the last block's two gradient tensors in NHWC 16-bit planes,
+//   out1 = g * seed_scale * mul1               (gradient x gain of the block's last conv: its `ghat`)
+//   out2 = g * seed_scale [* mul2], masked by the block's ReLU bits   (identity / downsample branch)
+// Thread = pixel, 8 channels per step (the same access pattern as nchw_to_nhwc16).
+// ------------------------------------------------------------------------------------------------
+namespace bcosk {
+
+template <typename T>
+__device__ __forceinline__ void load8_side(const void* base, bool f32, long long row, int ld, int ch0, float (&m)[8]) {
+  if (f32) {
+    const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + row * ld + ch0);
+    const float4 a = __ldg(q), b = __ldg(q + 1);
+    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+  } else {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(base) + row * ld + ch0));
+    float2 f;
+    f = Cvt<T>::unpack2(u.x); m[0] = f.x; m[1] = f.y;
+    f = Cvt<T>::unpack2(u.y); m[2] = f.x; m[3] = f.y;
+    f = Cvt<T>::unpack2(u.z); m[4] = f.x; m[5] = f.y;
+    f = Cvt<T>::unpack2(u.w); m[6] = f.x; m[7] = f.y;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void store8_planes(T* dst, int planes, int plane_stride, const float (&v)[8]) {
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = v[i];
+  for (int pl = 0; pl < planes; ++pl) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      w[k] = Cvt<T>::pack2(r[2 * k], r[2 * k + 1]);
+      const float2 q = Cvt<T>::unpack2(w[k]);
+      r[2 * k] -= q.x; r[2 * k + 1] -= q.y;
+    }
+    *reinterpret_cast<uint4*>(dst + (long long)pl * plane_stride) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+template <typename T>
+__global__ void seed_from_nchw_kernel(const float* __restrict__ g, int nb, int c, long long hw, float seed_scale,
+                                      const void* __restrict__ mul1, int mul1_f32, T* __restrict__ out1,
+                                      const uint32_t* __restrict__ mask2, const void* __restrict__ mul2, int mul2_f32,
+                                      T* __restrict__ out2, int planes) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)nb * hw) return;
+  const long long img = pix / hw, sp = pix - img * hw;
+  const float* src = g + img * c * hw + sp;
+  const int ld = planes * c;
+  for (int ch0 = 0; ch0 < c; ch0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(src + (long long)(ch0 + i) * hw) * seed_scale;
+    if (out1 != nullptr) {
+      float o[8];
+      if (mul1 != nullptr) {
+        float m[8];
+        load8_side<T>(mul1, mul1_f32 != 0, pix, c, ch0, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = v[i] * m[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = v[i];
+      }
+      store8_planes<T>(out1 + pix * ld + ch0, planes, c, o);
+    }
+    if (out2 != nullptr) {
+      float o[8];
+      if (mul2 != nullptr) {
+        float m[8];
+        load8_side<T>(mul2, mul2_f32 != 0, pix, c, ch0, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = v[i] * m[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = v[i];
+      }
+      if (mask2 != nullptr) {
+        const uint32_t mb = __ldg(mask2 + pix * ((c + 31) / 32) + (ch0 >> 5)) >> (ch0 & 31);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = ((mb >> i) & 1u) ? o[i] : 0.f;
+      }
+      store8_planes<T>(out2 + pix * ld + ch0, planes, c, o);
+    }
+  }
+}
+
+}  // namespace bcosk
+
+extern "C" int bcosk_seed_from_nchw(const float* g, int32_t nb, int32_t c, int32_t h, int32_t w, float seed_scale, const void* mul1,
+                                    int32_t mul1_f32, void* out1, const uint32_t* mask2, const void* mul2, int32_t mul2_f32,
+                                    void* out2, int32_t planes, int32_t dtype, void* stream) {
+  using namespace bcosk;
+  if (!g || (!out1 && !out2) || nb < 1 || c < 8 || c % 8 || planes < 1 || planes > 3)
+    return set_error(BCOSK_EINVAL, "seed_from_nchw: bad argument");
+  const long long hw = (long long)h * w, n = (long long)nb * hw;
+  if (dtype == BCOSK_DTYPE_BF16)
+    seed_from_nchw_kernel<__nv_bfloat16><<<nblocks(n, 128), 128, 0, S2(stream)>>>(
+        g, nb, c, hw, seed_scale, mul1, mul1_f32, reinterpret_cast<__nv_bfloat16*>(out1), mask2, mul2, mul2_f32,
+        reinterpret_cast<__nv_bfloat16*>(out2), planes);
+  else if (dtype == BCOSK_DTYPE_F16)
+    seed_from_nchw_kernel<__half><<<nblocks(n, 128), 128, 0, S2(stream)>>>(g, nb, c, hw, seed_scale, mul1, mul1_f32,
+                                                                         reinterpret_cast<__half*>(out1), mask2, mul2, mul2_f32,
+                                                                         reinterpret_cast<__half*>(out2), planes);
+  else
+    return set_error(BCOSK_EINVAL, "seed_from_nchw: dtype");
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // MaxOut for the module-level path (bcosconv2d.py:166-170, bcoslinear.py:107-110): the linear map has O*M units,
 // unit c = o*M + m; the output keeps the largest of the M candidates (first one on ties, like torch.max) and the
 // B-cos scale is computed from it.  The explanation gradient reaches only that unit.

@@ -1,3 +1,4 @@
 """Fused execution plans over the C-ABI kernels (CUDA only; no fallback)."""
 from .resnet import PRECISION_MODES, PipelinedExplainer, ResNetPlan  # noqa: F401
 from .train import ResNetTrainPlan  # noqa: F401
+from .clip_rn import CLIPResNetPlan  # noqa: F401

@@ -153,6 +153,16 @@ class PlanBase:
             return 256                    # experiment: 256-wide tiles for long K loops (off: wide_k_iters = 0)
         return 128
 
+    @staticmethod
+    def _even_taps(wt: Tensor, taps: List[Tuple[int, int]], kch: int) -> Tuple[Tensor, List[Tuple[int, int]]]:
+        """A pipeline stage is 64 K elements: with 32-channel chunks every segment needs an even number of (tap, chunk) pairs.
+        An odd count (3x3 over <= 32 channels) gets one more tap that re-reads the last tap's pixels against zero weights."""
+        cpt = (wt.shape[2] + kch - 1) // kch
+        if kch == 32 and (len(taps) * cpt) % 2 == 1:
+            wt = torch.cat([wt, wt.new_zeros(wt.shape[0], 1, wt.shape[2])], 1)
+            taps = list(taps) + [taps[-1]]
+        return wt, taps
+
     def _pack_b(self, wt: Tensor, planes: int, kch: int) -> Tuple[Tensor, int]:
         """[n, taps, c] fp32 -> (packed K-major device operand, chunks per tap).  The training plan overrides this to keep the
         operand refreshable from its fp32 master weights."""
@@ -206,7 +216,8 @@ class PlanBase:
             # left for the epilogues.
             w = w * alpha.sqrt().to(w.device).view(-1, 1, 1, 1)
             alpha = None
-        bmat, cpt = self._pack_b(P.fwd_weight_taps(w), self.planes, kch)
+        wt, taps = self._even_taps(P.fwd_weight_taps(w), P.conv_taps(kh, kw), kch)
+        bmat, cpt = self._pack_b(wt, self.planes, kch)
         block_n = self._block_n(o, bmat.shape[1] // 64)
         parts = (o + block_n - 1) // block_n
         yp = 1 if y_f32 else self.planes
@@ -241,7 +252,7 @@ class PlanBase:
         self.fwd_ops.append(O.IgemmOp(
             name=name, a=x.t, b=bmat, n=o, lo=(-pad_lo, -pad_lo),
             up=(pad_hi - (kw - 1), pad_hi - (kh - 1)), stride=(stride, stride), op=oh, oq=ow, kch=kch, chunks_per_tap=cpt,
-            taps=P.conv_taps(kh, kw), seg_a_choff=P.seg_a_offsets(self.planes, cin_phys), seg_b_plane=P.seg_b_planes(self.planes), dtype=self.dt_code,
+            taps=taps, seg_a_choff=P.seg_a_offsets(self.planes, cin_phys), seg_b_plane=P.seg_b_planes(self.planes), dtype=self.dt_code,
             mode=L.BCOSK_MODE_FWD, block_n=block_n, scale_mode=self.scale_mode, b_exp=self.b, relu=relu,
             inv_norm=inv_norm, sq_in=sq_in, sq_geom=sq_geom, sq_eps=sq_eps, alpha=alpha, beta=beta,
             lin_bias=None if lin_bias is None else self._dev(lin_bias),
@@ -295,10 +306,11 @@ class PlanBase:
         wt = P.dgrad_weight_taps(rec.w)                      # [c, taps, o]
         if wt.shape[0] < n:                                  # physical input channels beyond the logical ones
             wt = torch.cat([wt, wt.new_zeros(n - wt.shape[0], *wt.shape[1:])], 0)
+        wt, taps = self._even_taps(wt, P.conv_taps(k, k), kch)
         bmat, cpt = self._pack_b(wt, self.bplanes, kch)
         self.bwd_ops.append(O.IgemmOp(
             name=rec.name + ".dgrad", a=g, b=bmat, n=n, lo=(lo, lo), up=(up_w, up_h), stride=(1, 1),
-            op=oh, oq=ow, kch=kch, chunks_per_tap=cpt, taps=P.conv_taps(k, k),
+            op=oh, oq=ow, kch=kch, chunks_per_tap=cpt, taps=taps,
             seg_a_choff=P.seg_a_offsets(self.bplanes, rec.cout), seg_b_plane=P.seg_b_planes(self.bplanes), dtype=self.dt_code, mode=L.BCOSK_MODE_EXPLAIN,
             block_n=64 if (add is not None and add_stride == 1 and self.bplanes == 1 and n >= 64)
             else self._block_n(n, bmat.shape[1] // 64, hp=self.bwd_hp),   # dense extra gradient: 64-wide tiles stage it with TMA

@@ -386,6 +386,41 @@ class ExplanationImageOp:
         L.explanation_rgba(self.grad6, self.x, self.smooth, self.percentile, self.tmp, self.out)
 
 
+@dataclass
+class TrunkOutOp:
+    """Trunk output NHWC 16-bit planes -> NCHW fp32 (the layout the module-level head reads)."""
+    name: str
+    y: Tensor
+    nb: int
+    c: int
+    h: int
+    w: int
+    planes: int
+    dtype: int
+    out: Tensor
+
+    def run(self) -> None:
+        L.nhwc_to_nchw_f32(self.y, self.nb, self.c, self.h, self.w, self.planes, self.dtype, self.out)
+
+
+@dataclass
+class SeedFromNchwOp:
+    """include/bcosk.h bcosk_seed_from_nchw: external gradient (NCHW fp32) -> last block's ghat (x gain) and side (masked)."""
+    name: str
+    g: Tensor
+    seed_scale: float
+    mul1: Optional[Tensor]
+    out1: Tensor
+    mask2: Optional[Tensor]
+    mul2: Optional[Tensor]
+    out2: Optional[Tensor]
+    planes: int
+    dtype: int
+
+    def run(self) -> None:
+        L.seed_from_nchw(self.g, self.seed_scale, self.mul1, self.out1, self.mask2, self.mul2, self.out2, self.planes, self.dtype)
+
+
 def run_ops(ops) -> None:
     for o in ops:
         o.run()

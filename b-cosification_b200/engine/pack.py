@@ -81,19 +81,22 @@ def dgrad_weight_taps(w: Tensor) -> Tensor:
 
 def stem_s2d_weight(w7: Tensor, cp: int) -> Tensor:
     """7x7/2 pad-3 stem on [x,1-x] (6 ch) == 4x4/1 conv (pad 2 low, 1 high) on the 2x2 space-to-depth input:
-    W4[o, (dy*2+dx)*6 + c, tr, ts] = W7[o, c, 2*tr+dy-1, 2*ts+dx-1] (zero outside the 7x7 support)."""
+    W4[o, (dy*2+dx)*6 + c, tr, ts] = W7[o, c, 2*tr+dy-1, 2*ts+dx-1] (zero outside the 7x7 support).
+    The same identity turns the 3x3/2 pad-1 stem of the CLIP ResNets (CLIP/clip/model.py:109) into a 2x2/1 conv
+    (pad 1 low, 0 high): output pixel p reads rows 2p-1 .. 2p+1 = blocks p-1 (dy=1) and p (dy=0,1)."""
     o, c, kh, kw = w7.shape
-    assert (c, kh, kw) == (6, 7, 7)
-    w4 = torch.zeros(o, cp, 4, 4, dtype=w7.dtype, device=w7.device)
+    assert c == 6 and kh == kw and kh in (3, 7)
+    nt = (kh + 1) // 2
+    w4 = torch.zeros(o, cp, nt, nt, dtype=w7.dtype, device=w7.device)
     for dy in range(2):
         for dx in range(2):
-            for tr in range(4):
+            for tr in range(nt):
                 i = 2 * tr + dy - 1
-                if not 0 <= i < 7:
+                if not 0 <= i < kh:
                     continue
-                for ts in range(4):
+                for ts in range(nt):
                     j = 2 * ts + dx - 1
-                    if not 0 <= j < 7:
+                    if not 0 <= j < kw:
                         continue
                     base = (dy * 2 + dx) * 6
                     w4[:, base:base + 6, tr, ts] = w7[:, :, i, j]

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 from typing import Dict, Tuple
 
+from .engine.clip_rn import CLIPResNetPlan
 from .engine.resnet import RESNET_ARCH, ResNetPlan
 from .utils import synth
 
@@ -56,3 +57,42 @@ def synthetic_resnet_plan(arch: str, batch: int, **plan_kwargs) -> ResNetPlan:
     """Fused plan over the synthetic (random-init, BN-calibrated) checkpoint - the benchmark workload."""
     sd = synth.synthetic_checkpoint(arch, resnet_state_shapes(arch))
     return ResNetPlan(arch, sd, batch, **plan_kwargs)
+
+
+def clip_rn_state_shapes(layers=(3, 4, 6, 3), output_dim: int = 1024, width: int = 64) -> Dict[str, Tuple[int, ...]]:
+    """Keys/shapes of the B-cos CLIP ResNet image encoder: CLIP/clip/model.py:94-154 `ModifiedResNet` converted by
+    bcosify.py:74-113 (`clip_kd`), biases and positional embedding removed (clip_bcosification/model.py:15-23).  The named
+    ("-1", "0", "1") downsample Sequential becomes a positional BcosSequential: avg pool 0, conv 1, BN 2."""
+    shapes: Dict[str, Tuple[int, ...]] = {}
+
+    def bn(prefix, c):
+        shapes[prefix + ".weight"] = (c,)
+        shapes[prefix + ".running_mean"] = (c,)
+        shapes[prefix + ".running_var"] = (c,)
+        shapes[prefix + ".num_batches_tracked"] = ()
+
+    shapes["model.conv1.linear.weight"] = (width // 2, 6, 3, 3); bn("model.bn1", width // 2)
+    shapes["model.conv2.linear.weight"] = (width // 2, width // 2, 3, 3); bn("model.bn2", width // 2)
+    shapes["model.conv3.linear.weight"] = (width, width // 2, 3, 3); bn("model.bn3", width)
+    inpl = width
+    for li, (planes, nblocks) in enumerate(zip([width, width * 2, width * 4, width * 8], layers), start=1):
+        for bi in range(nblocks):
+            stride = 2 if (li > 1 and bi == 0) else 1
+            p = f"model.layer{li}.{bi}"
+            shapes[p + ".conv1.linear.weight"] = (planes, inpl, 1, 1); bn(p + ".bn1", planes)
+            shapes[p + ".conv2.linear.weight"] = (planes, planes, 3, 3); bn(p + ".bn2", planes)
+            shapes[p + ".conv3.linear.weight"] = (planes * 4, planes, 1, 1); bn(p + ".bn3", planes * 4)
+            if stride > 1 or inpl != planes * 4:
+                shapes[p + ".downsample.1.linear.weight"] = (planes * 4, inpl, 1, 1); bn(p + ".downsample.2", planes * 4)
+            inpl = planes * 4
+    e = width * 32
+    for nme in ("k_proj", "q_proj", "v_proj"):
+        shapes[f"model.attnpool.{nme}.weight"] = (e, e)
+    shapes["model.attnpool.c_proj.linear.weight"] = (output_dim, e)
+    return shapes
+
+
+def synthetic_clip_rn50_plan(batch: int, **plan_kwargs) -> CLIPResNetPlan:
+    """Fused CLIP RN50 plan over the synthetic (random-init, BN-calibrated) checkpoint - BASELINE config 4."""
+    sd = synth.synthetic_checkpoint("clip_rn50", clip_rn_state_shapes())
+    return CLIPResNetPlan(sd, batch, **plan_kwargs)

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Tuple
 
+import contextlib
 import weakref
 
 import torch
@@ -29,6 +30,18 @@ class config:
 
 def set_precision(mode: str) -> None:
     config.planes = {"parity": 3, "bf16x2": 2, "bf16": 1}[mode]
+
+
+@contextlib.contextmanager
+def precision(planes: int, dtype: str):
+    """Operand format of the module-level launches issued inside the block (a fused plan runs its module-level head in the
+    plan's own format).  LayerPlans are cached per format; a backward uses the plan its forward ran on."""
+    old = (config.planes, config.dtype)
+    config.planes, config.dtype = int(planes), dtype
+    try:
+        yield
+    finally:
+        config.planes, config.dtype = old
 
 
 def _require_cuda(x: Tensor, who: str) -> None:

@@ -401,6 +401,14 @@ int bcosk_nchw_to_nhwc16(const float* x, int32_t nb, int32_t c, int32_t h, int32
 /* NHWC (fp32, or 16-bit planes summed) -> NCHW fp32 */
 int bcosk_nhwc_to_nchw_f32(const void* y, int32_t y_f32, int32_t nb, int32_t c, int32_t h, int32_t w, int32_t ld,
                            int32_t planes, int32_t dtype, float* out, void* stream);
+/* Seed of a fused trunk's explanation pass from a gradient computed OUTSIDE the plan (CLIP encoders: the attention-pool head
+ * bcos/modules/bcosattnpool.py:34-59 runs on the module-level path and autograd hands back d target / d trunk output):
+ * g [nb, c, h, w] fp32 NCHW ->  out1[pix, pl*c + ch] = planes(g * seed_scale * mul1[pix, ch])  (mul1 = gain of the block's last conv)
+ *                               out2[pix, pl*c + ch] = planes(g * seed_scale [* mul2[pix, ch]]) where bit ch of mask2[pix] is set
+ * mul1 / mul2: [nb*h*w, c] 16-bit or fp32; mask2: [nb*h*w, ceil(c/32)] words (the block's ReLU bits); out1 / out2 may be NULL. */
+int bcosk_seed_from_nchw(const float* g, int32_t nb, int32_t c, int32_t h, int32_t w, float seed_scale, const void* mul1,
+                         int32_t mul1_f32, void* out1, const uint32_t* mask2, const void* mul2, int32_t mul2_f32, void* out2,
+                         int32_t planes, int32_t dtype, void* stream);
 /* out = relu?((x * alpha[c] + beta[c]) * smul + sadd) on NCHW fp32: batch_norm_uncentered_2d (eval / after statistics)
  * batchnorm_uncentered.py:45-58 and LogitLayer.forward logitlayer.py:22-27 (alpha = beta = NULL) */
 int bcosk_scale_bias_nchw(const float* x, int32_t nb, int32_t c, int64_t hw, const float* alpha, const float* beta, float smul,

@@ -651,7 +651,8 @@ class OracleCLIPResNet:
             norm = norm.detach()
         return t / norm
 
-    def forward(self, x6: Tensor, detach: bool = False) -> Tensor:
+    def trunk(self, x6: Tensor, detach: bool = False) -> Tensor:
+        """CLIP/clip/model.py:139-152: stem, avg pool, four stages (everything in front of the attention pool)."""
         x = normalize6(x6, self.mean, self.std)
         x = F.relu(self._bn("model.bn1", self._conv("model.conv1", x, 2, 1, detach), detach))
         x = F.relu(self._bn("model.bn2", self._conv("model.conv2", x, 1, 1, detach), detach))
@@ -660,6 +661,10 @@ class OracleCLIPResNet:
         for li, nb in enumerate(self.layers, start=1):
             for bi in range(nb):
                 x = self._block(f"model.layer{li}.{bi}", x, 2 if (li > 1 and bi == 0) else 1, detach)
+        return x
+
+    def forward(self, x6: Tensor, detach: bool = False) -> Tensor:
+        x = self.trunk(x6, detach)
         return self.attn_unpool(x, detach) if self.unpool else self.attnpool(x, detach)
 
     __call__ = forward

@@ -280,10 +280,28 @@ def run_explanation_image(op: O.ExplanationImageOp) -> None:
     op.out.copy_(R.gradient_to_image_batched(_x6(op.x), op.grad6, op.smooth, op.percentile))
 
 
+def run_trunk_out(op: O.TrunkOutOp) -> None:
+    op.out.copy_(_join(op.y, op.planes)[..., :op.c].permute(0, 3, 1, 2))
+
+
+def run_seed_from_nchw(op: O.SeedFromNchwOp) -> None:
+    nb, c, h, w = op.g.shape
+    g = op.g.float().permute(0, 2, 3, 1).reshape(nb * h * w, c) * op.seed_scale
+    if op.out1 is not None:
+        v = g * op.mul1.float().view(-1, c) if op.mul1 is not None else g
+        _split_store(op.out1, v.view(nb, h, w, c), op.planes)
+    if op.out2 is not None:
+        o = g * op.mul2.float().view(-1, c) if op.mul2 is not None else g
+        if op.mask2 is not None:
+            o = o * _mask_bits(op.mask2, c)
+        _split_store(op.out2, o.view(nb, h, w, c), op.planes)
+
+
 _DISPATCH = {
     O.IgemmOp: run_igemm, O.InputPrepOp: run_input_prep, O.PatchNormOp: run_patch_norm, O.AvgPoolFwdOp: run_avgpool_fwd,
     O.AvgPoolBwdMulOp: run_avgpool_bwd_mul, O.GapLogitsOp: run_gap_logits, O.FcSeedOp: run_fc_seed,
     O.ContribMapOp: run_contrib_map, O.ExplanationImageOp: run_explanation_image,
+    O.TrunkOutOp: run_trunk_out, O.SeedFromNchwOp: run_seed_from_nchw,
 }
 
 

@@ -19,6 +19,8 @@ OUTPUT_FIELDS = {
     O.FcSeedOp: ["out1", "out2"],
     O.ContribMapOp: ["cmap", "grad6"],
     O.ExplanationImageOp: ["out"],
+    O.TrunkOutOp: ["out"],
+    O.SeedFromNchwOp: ["out1", "out2"],
 }
 
 

@@ -99,3 +99,34 @@ def test_released_checkpoint_formats(tmp_path):
     plan = C.resnet_plan_from_checkpoint("resnet18", tmp_path / "last.ckpt", 1, device="cpu", image_size=64)
     ref = ResNetPlan("resnet18", sd, 1, device="cpu", image_size=64)
     assert len(plan.fwd_ops) == len(ref.fwd_ops) and plan.num_launches() == ref.num_launches()
+
+
+def test_clip_rn_trunk_plan_matches_oracle():
+    """engine/clip_rn.py: three-conv stem (3x3/2 as a 2x2 conv over the space-to-depth input, zero-tap padding of the 32-channel
+    3x3 convs), average pools inside the bottlenecks and in front of the downsample convs, external seed (the attention-pool
+    head is evaluated here by the oracle with autograd), contribution map - launch list run by the emulator vs the oracle."""
+    from bcos_b200.engine import CLIPResNetPlan
+    from bcos_b200.models import clip_rn_state_shapes
+    shapes = clip_rn_state_shapes(layers=(1, 2, 1, 1), width=16, output_dim=64)
+    assert shapes == OR.clip_rn_state_shapes(layers=(1, 2, 1, 1), width=16, output_dim=64)
+    sd = synth.synth_state_dict(shapes, 0)
+    x6 = synth.to_bcos_input(synth.synth_images_u8(2, 64, 1))
+    om = OR.OracleCLIPResNet(sd, layers=(1, 2, 1, 1), heads=4)
+    om.calibrate_bn(x6)
+    tvec = OR.clip_seed_direction(64, 0)
+    ref = OR.explain_cosine(om.forward, x6, tvec)
+    plan = CLIPResNetPlan(sd, 2, planes=3, device="cpu", image_size=64, layers=(1, 2, 1, 1), width=16, heads=4)
+    plan.x_in.copy_(x6)
+    E.run(plan.fwd_ops)
+    feat_ref = om.trunk(x6)
+    assert ((plan.feat - feat_ref).abs().max() / feat_ref.abs().max()).item() < 1e-4     # three bf16 planes
+    feat = plan.feat.clone().requires_grad_(True)
+    with torch.enable_grad():
+        emb = om.attnpool(feat, detach=True)
+        (g,) = torch.autograd.grad(torch.nn.functional.cosine_similarity(emb, tvec[None], dim=1).sum(), [feat])
+    plan.g_feat.copy_(g)
+    E.run(plan.bwd_ops)
+    assert ((emb.detach() - ref["embedding"]).abs().max() / ref["embedding"].abs().max()).item() < 1e-5
+    cm, rm = plan.cmap, ref["contribution_map"]
+    assert torch.nn.functional.cosine_similarity(cm.flatten(1), rm.flatten(1)).min().item() > 0.99999
+    assert ((cm - rm).abs().max() / rm.abs().max()).item() < 1e-3
