@@ -64,6 +64,8 @@ def parse_args():
                          "bf16 plane, the format BASELINE.json names - faster, does not meet the map tolerances")
     ap.add_argument("--no-throughput-record", action="store_true", help="skip the extra bf16 x1 measurement")
     ap.add_argument("--no-train-record", action="store_true", help="skip the fine-tuning-step measurement (BASELINE config 5)")
+    ap.add_argument("--no-clip-record", action="store_true", help="skip the CLIP RN50 measurement (BASELINE config 4)")
+    ap.add_argument("--clip-batch", type=int, default=512, help="images per GPU of the CLIP RN50 record (config 4: 512)")
     ap.add_argument("--train-batch", type=int, default=64, help="images per GPU of the fine-tuning step (reference recipe: 64)")
     ap.add_argument("--train-steps", type=int, default=8)
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline / reference-arm step (8 = the CPU's best)")
@@ -228,6 +230,11 @@ def main():
     if not args.no_train_record:
         train = measure_train_step(args, dev, rank, world, barrier, max_over_ranks)
 
+    # ---------------- extra record: BASELINE config 4, the B-cos CLIP RN50 image encoder (embedding + explanation, batch 512) ----
+    clip = None
+    if not args.no_clip_record:
+        clip = measure_clip_rn50(args, dev, world, barrier, max_over_ranks)
+
     plan = synthetic_resnet_plan(args.arch, B, mode=args.mode, device=dev, input_u8=True)
     prec = plan.precision
     plan.load_input(h_in)
@@ -347,6 +354,8 @@ def main():
         res["throughput_mode"] = thr
     if train is not None:
         res["train_step"] = train
+    if clip is not None:
+        res["clip_rn50"] = clip
     if args.layer_table:
         rows = []
         for o, t in zip(all_ops, per_op):
@@ -364,6 +373,45 @@ def main():
         res["cpu_baseline"] = {"value": c["value"], "unit": "img/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]}
     print(json.dumps(res), file=real_stdout, flush=True)
     D.shutdown()
+
+
+def measure_clip_rn50(args, dev, world, barrier, max_over_ranks):
+    """BASELINE config 4: B-cos CLIP RN50 image encoder, embedding + explanation of cos(embedding, text direction) on synthetic
+    images through the fused plan (engine/clip_rn.py; trunk as CUDA graphs, attention-pool head on the module-level kernels),
+    same operand format as the main record.  Device-resident inputs, CUDA events, max over ranks."""
+    import torch
+    from bcos_b200.models import synthetic_clip_rn50_plan
+    from bcos_b200.utils import synth
+    Bc, reps = args.clip_batch, 4
+    plan = synthetic_clip_rn50_plan(Bc, mode=args.mode, device=dev, input_u8=True)
+    x = torch.from_numpy(synth.synth_images_u8(32, 224, 5)).repeat((Bc + 31) // 32, 1, 1, 1)[:Bc].to(dev)
+    plan.load_input(x)
+    plan.capture()
+    g = torch.Generator().manual_seed(0)
+    t = torch.nn.functional.normalize(torch.randn(1024, generator=g), dim=0)
+    for _ in range(2):
+        plan.explain_direction(None, t)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    for _ in range(reps):
+        plan.embed(None)
+    ev[1].record()
+    for _ in range(reps):
+        out = plan.explain_direction(None, t)
+    ev[2].record()
+    barrier()
+    ms_e = max_over_ranks(ev[0].elapsed_time(ev[1])) / reps
+    ms_x = max_over_ranks(ev[1].elapsed_time(ev[2])) / reps
+    ok = bool(torch.isfinite(out["embedding"]).all() and torch.isfinite(out["contribution_map"]).all())
+    rec = {"workload": "B-cos CLIP RN50 image encoder (resnet_50_clip_b2_noBias) embedding + explanation throughput on synthetic images, batch 512 (BASELINE config 4)",
+           "batch_per_gpu": Bc, "n_gpus": world, "mode": args.mode, "embed_ms_per_step": ms_e, "embed_value": world * Bc / (ms_e * 1e-3),
+           "ms_per_step": ms_x, "value": world * Bc / (ms_x * 1e-3), "unit": "img/s",
+           "launches_per_step": plan.num_launches(), "finite": ok,
+           "parity": "tests/test_clip_gpu.py: embedding 1e-4 rel, map cosine 0.9999994, max-abs 8.7e-4 of range vs the reference golden (contract mode)"}
+    del plan
+    torch.cuda.empty_cache()
+    return rec
 
 
 def measure_train_step(args, dev, rank, world, barrier, max_over_ranks):
