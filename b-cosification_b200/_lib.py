@@ -253,6 +253,41 @@ def nchw_to_nhwc16(x, out, cp, planes, dtype, mul=None, sq=None) -> None:
                                       0 if mul is None else mul.shape[-1], _p(sq), _stream()), "bcosk_nchw_to_nhwc16")
 
 
+# ---- fused SimpleViT plan (csrc/bcosk_vit.cu)
+def vit_patchify(x, p, mean6, inv_std6, out, planes, dtype, sq) -> None:
+    nb, _, h, w = x.shape
+    fn = load().bcosk_vit_patchify_u8 if _is_u8(x) else load().bcosk_vit_patchify
+    check(fn(_p(x), nb, h, w, p, _f6(mean6), _f6(inv_std6), _p(out), planes, dtype, _p(sq), _stream()), "bcosk_vit_patchify")
+
+
+def vit_contrib_map(g, x, p, inv_std6, out_scale, cmap, grad6) -> None:
+    nb, _, h, w = x.shape
+    fn = load().bcosk_vit_contrib_map_u8 if _is_u8(x) else load().bcosk_vit_contrib_map
+    check(fn(_p(g), _p(x), nb, h, w, p, _f6(inv_std6), C.c_float(out_scale), _p(cmap), _p(grad6), _stream()), "bcosk_vit_contrib_map")
+
+
+def vit_ln_fwd(x, rows, d, planes, w, eps, y, rstd, sq, dtype) -> None:
+    check(load().bcosk_vit_ln_fwd(_p(x), C.c_int64(rows), d, planes, _p(w), C.c_float(eps), _p(y), _p(rstd), _p(sq), dtype, _stream()),
+          "bcosk_vit_ln_fwd")
+
+
+def vit_ln_bwd(g, G_in, rows, d, w, rstd, G_out, gain, ghat, dtype) -> None:
+    import torch
+    check(load().bcosk_vit_ln_bwd(_p(g), int(g.dtype == torch.float32), _p(G_in), C.c_int64(rows), d, _p(w), _p(rstd), _p(G_out), _p(gain),
+                                  int(gain is not None and gain.dtype == torch.float32), _p(ghat), dtype, _stream()), "bcosk_vit_ln_bwd")
+
+
+def vit_gelu_fwd(u, rows, d, planes, a, sq, gain, dtype) -> None:
+    import torch
+    check(load().bcosk_vit_gelu_fwd(_p(u), C.c_int64(rows), d, planes, _p(a), _p(sq), _p(gain),
+                                    int(gain is not None and gain.dtype == torch.float32), dtype, _stream()), "bcosk_vit_gelu_fwd")
+
+
+def vit_attention(qkv, planes, g, batch, n, heads, dim_head, scale, backward, out, dtype) -> None:
+    check(load().bcosk_vit_attention(_p(qkv), planes, _p(g), batch, n, heads, dim_head, C.c_float(scale), int(backward), _p(out), dtype,
+                                     _stream()), "bcosk_vit_attention")
+
+
 def seed_from_nchw(g, seed_scale, mul1, out1, mask2, mul2, out2, planes, dtype) -> None:
     import torch
     nb, c, h, w = g.shape

@@ -175,7 +175,7 @@ class PlanBase:
                   inv_norm: Optional[Tensor] = None, kch: int = 64, want_sq: bool = True,
                   sq_geom: Optional[Tuple[int, int, int, int, int]] = None, lin_bias: Optional[Tensor] = None,
                   sq_eps: Tuple[float, float] = (1e-6, 0.0), flat: bool = False, want_inv: bool = False,
-                  max_out: int = 1) -> Tuple[Act, ConvRec]:
+                  max_out: int = 1, scale_mode: Optional[int] = None, want_gain: bool = True) -> Tuple[Act, ConvRec]:
         """One fused launch: B-cos conv (+BN multiplier, +residual, +ReLU).  The patch norm comes from `x.sq`
         (per-pixel sums of squares written by x's producer) and is evaluated inside the kernel; `sq_geom`
         overrides its (h, w, k, stride, pad) when the GEMM geometry is not the convolution's (space-to-depth stem).
@@ -184,6 +184,7 @@ class PlanBase:
         nb = self.nb
         h, wd = x.hw
         o, c, kh, kw = w.shape
+        smode = self.scale_mode if scale_mode is None else scale_mode      # per-launch override (plain linear maps: NONE)
         oh = (h + pad_lo + pad_hi - kh) // stride + 1
         ow = (wd + pad_lo + pad_hi - kw) // stride + 1
         M = nb * oh * ow
@@ -196,7 +197,7 @@ class PlanBase:
         flat = flat or (self.flat_3x3 and max_out == 1 and self.planes == 1 and not self.hp_accum and stride == 1 and kh == kw and kh > 1
                         and cin_phys == 64 and kch == 64 and o <= 64 and res is None and not y_f32 and x.t.is_contiguous())
         sq_in = None
-        if inv_norm is None and self.scale_mode != L.BCOSK_SCALE_NONE:
+        if inv_norm is None and smode != L.BCOSK_SCALE_NONE:
             sq_in = x.sq
             if sq_geom is None:
                 assert pad_lo == pad_hi and kh == kw, "asymmetric convs must pass inv_norm or sq_geom"
@@ -209,7 +210,7 @@ class PlanBase:
                                                   sq_geom[3], sq_geom[4], sq_eps[0], sq_eps[1], inv_norm, oh, ow))
                 sq_in = None
         alpha, beta = self._bn_alpha(bn) if bn else (None, None)
-        if (alpha is not None and beta is None and self.fold_bn and self.scale_mode == L.BCOSK_SCALE_B2
+        if (alpha is not None and beta is None and self.fold_bn and smode == L.BCOSK_SCALE_B2
                 and bool((alpha > 0).all())):
             # y = a * lin * |lin| / n == lin' * |lin'| / n with lin' = sqrt(a) * lin: fold sqrt(a) into the weights.  The
             # explanation pass uses the same folded weights (d y / d x = (|lin'| / n) * W'), so nothing per channel is
@@ -228,7 +229,7 @@ class PlanBase:
         # (ReLU, no residual, BN multiplier folded, b = 2, throughput mode)
         lazy_gain = (self.with_explain and self.recompute_gain and max_out == 1 and self.planes == 1 and not self.hp_accum and relu
                      and res is None and alpha is None and beta is None and lin_bias is None and not y_f32
-                     and self.scale_mode == L.BCOSK_SCALE_B2)
+                     and smode == L.BCOSK_SCALE_B2)
         inv_out = None
         if lazy_gain:
             rec.gain_y = y.view(M, o)
@@ -238,11 +239,11 @@ class PlanBase:
             else:
                 rec.gain_inv = inv_norm
         if want_inv and not lazy_gain:        # training: 1/||patch|| is needed again by the backward of the scale
-            if inv_norm is None and self.scale_mode != L.BCOSK_SCALE_NONE:
+            if inv_norm is None and smode != L.BCOSK_SCALE_NONE:
                 inv_out = self._empty(M, dtype=torch.float32)
             rec.inv = inv_norm if inv_norm is not None else inv_out
         if self.with_explain:
-            if not lazy_gain:
+            if not lazy_gain and want_gain:
                 rec.gain = self._empty(M, oy, dtype=self.gain_dt)
             if max_out > 1:
                 rec.amax = torch.zeros(M, oy, dtype=torch.uint8, device=self.device)
@@ -253,7 +254,7 @@ class PlanBase:
             name=name, a=x.t, b=bmat, n=o, lo=(-pad_lo, -pad_lo),
             up=(pad_hi - (kw - 1), pad_hi - (kh - 1)), stride=(stride, stride), op=oh, oq=ow, kch=kch, chunks_per_tap=cpt,
             taps=taps, seg_a_choff=P.seg_a_offsets(self.planes, cin_phys), seg_b_plane=P.seg_b_planes(self.planes), dtype=self.dt_code,
-            mode=L.BCOSK_MODE_FWD, block_n=block_n, scale_mode=self.scale_mode, b_exp=self.b, relu=relu,
+            mode=L.BCOSK_MODE_FWD, block_n=block_n, scale_mode=smode, b_exp=self.b, relu=relu,
             inv_norm=inv_norm, sq_in=sq_in, sq_geom=sq_geom, sq_eps=sq_eps, alpha=alpha, beta=beta,
             lin_bias=None if lin_bias is None else self._dev(lin_bias),
             res=None if res is None else res.t, res_planes=self.planes,

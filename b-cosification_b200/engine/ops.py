@@ -421,6 +421,123 @@ class SeedFromNchwOp:
         L.seed_from_nchw(self.g, self.seed_scale, self.mul1, self.out1, self.mask2, self.mul2, self.out2, self.planes, self.dtype)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Fused SimpleViT plan (engine/vit.py; kernels: csrc/bcosk_vit.cu).  Token tensors: [nb, gh, gw, planes * d].
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class VitPatchifyOp:
+    name: str
+    x: Tensor            # [nb, 6, h, w] fp32 or uint8 RGB [nb, 3, h, w]
+    p: int
+    mean6: Tuple[float, ...]
+    inv_std6: Tuple[float, ...]
+    out: Tensor          # [nb, h/p, w/p, planes * p*p*6]
+    planes: int
+    dtype: int
+    sq: Optional[Tensor]  # [1, rows] fp32
+
+    def run(self) -> None:
+        L.vit_patchify(self.x, self.p, self.mean6, self.inv_std6, self.out, self.planes, self.dtype, self.sq)
+
+
+@dataclass
+class VitContribMapOp:
+    name: str
+    g: Tensor            # [nb, gh, gw, p*p*6] fp32 (patch-embedding data gradient)
+    x: Tensor
+    p: int
+    inv_std6: Tuple[float, ...]
+    out_scale: float
+    cmap: Tensor         # [nb, h, w] fp32
+    grad6: Optional[Tensor]
+
+    def run(self) -> None:
+        L.vit_contrib_map(self.g, self.x, self.p, self.inv_std6, self.out_scale, self.cmap, self.grad6)
+
+
+@dataclass
+class VitLnFwdOp:
+    name: str
+    x: Tensor            # [.., planes * d]
+    d: int
+    planes: int
+    w: Tensor            # [d] fp32
+    eps: float
+    y: Tensor
+    rstd: Tensor         # [rows] fp32
+    sq: Optional[Tensor]  # [1, rows] fp32: sum of the stored outputs squared
+    dtype: int
+
+    def run(self) -> None:
+        L.vit_ln_fwd(self.x, self.rstd.numel(), self.d, self.planes, self.w, self.eps, self.y, self.rstd, self.sq, self.dtype)
+
+
+@dataclass
+class VitLnBwdOp:
+    """G_out = G_in + rstd * (g w - mean(g w));  ghat = G_out * gain (one 16-bit plane)."""
+    name: str
+    g: Tensor            # [.., d] fp32 or 16-bit
+    G_in: Optional[Tensor]   # [.., d] fp32
+    d: int
+    w: Tensor
+    rstd: Tensor
+    G_out: Optional[Tensor]  # fp32
+    gain: Optional[Tensor]
+    ghat: Optional[Tensor]   # 16-bit
+    dtype: int
+
+    def run(self) -> None:
+        L.vit_ln_bwd(self.g, self.G_in, self.rstd.numel(), self.d, self.w, self.rstd, self.G_out, self.gain, self.ghat, self.dtype)
+
+
+@dataclass
+class VitGeluFwdOp:
+    name: str
+    u: Tensor            # [.., planes * d]
+    d: int
+    planes: int
+    a: Tensor
+    sq: Optional[Tensor]
+    gain: Optional[Tensor]   # [rows, d] multiplied in place by the gate
+    dtype: int
+
+    def run(self) -> None:
+        L.vit_gelu_fwd(self.u, self.u.numel() // self.u.shape[-1], self.d, self.planes, self.a, self.sq, self.gain, self.dtype)
+
+
+@dataclass
+class VitAttentionOp:
+    name: str
+    qkv: Tensor          # [nb, gh, gw, planes * 3*heads*dh]
+    planes: int
+    g: Optional[Tensor]  # backward: [nb, gh, gw, heads*dh] fp32
+    nb: int
+    n: int
+    heads: int
+    dh: int
+    scale: float
+    backward: bool
+    out: Tensor          # forward: planes * heads*dh; backward: heads*dh (one plane)
+    dtype: int
+
+    def run(self) -> None:
+        L.vit_attention(self.qkv, self.planes, self.g, self.nb, self.n, self.heads, self.dh, self.scale, self.backward, self.out, self.dtype)
+
+
+@dataclass
+class PixelSqsumOp:
+    """sq[row] = sum over the columns of a plane row (value = sum of planes) squared."""
+    name: str
+    x: Tensor            # [.., planes * c]
+    c: int
+    planes: int
+    dtype: int
+    sq: Tensor           # [1, rows]
+
+    def run(self) -> None:
+        L.pixel_sqsum(self.x, self.sq.numel(), self.c, self.planes, self.c, self.planes * self.c, self.dtype, self.sq)
+
+
 def run_ops(ops) -> None:
     for o in ops:
         o.run()

@@ -10,6 +10,7 @@ from typing import Dict, Tuple
 
 from .engine.clip_rn import CLIPResNetPlan
 from .engine.resnet import RESNET_ARCH, ResNetPlan
+from .engine.vit import VIT_ARCH, ViTPlan
 from .utils import synth
 
 
@@ -96,3 +97,26 @@ def synthetic_clip_rn50_plan(batch: int, **plan_kwargs) -> CLIPResNetPlan:
     """Fused CLIP RN50 plan over the synthetic (random-init, BN-calibrated) checkpoint - BASELINE config 4."""
     sd = synth.synthetic_checkpoint("clip_rn50", clip_rn_state_shapes())
     return CLIPResNetPlan(sd, batch, **plan_kwargs)
+
+
+def vit_state_shapes(arch: str, num_classes: int = 1000, patch: int = 16) -> Dict[str, Tuple[int, ...]]:
+    """Keys/shapes of the B-cosified SimpleViT (bcos/models/vit.py:253-339 converted by bcosify_vit.py:45-153, biases stripped by
+    the factories vit_bcosification/model.py:20-25)."""
+    dim, depth, heads, mlp = VIT_ARCH[arch]
+    s: Dict[str, Tuple[int, ...]] = {"model.to_patch_embedding.linear.linear.weight": (dim, patch * patch * 6)}
+    for i in range(depth):
+        p = f"model.transformer.encoder_{i}"
+        s[p + ".attn.norm.weight"] = (dim,)
+        s[p + ".attn.to_qkv.weight"] = (3 * dim, dim)
+        s[p + ".attn.to_out.linear.weight"] = (dim, dim)
+        s[p + ".ff.net.norm.weight"] = (dim,)
+        s[p + ".ff.net.linear1.linear.weight"] = (mlp, dim)
+        s[p + ".ff.net.linear2.linear.weight"] = (dim, mlp)
+    s["model.linear_head.norm.weight"] = (dim,)
+    s["model.linear_head.linear.linear.weight"] = (num_classes, dim)
+    return s
+
+
+def synthetic_vit_plan(arch: str, batch: int, **plan_kwargs) -> ViTPlan:
+    """Fused SimpleViT plan over the synthetic (random-init) checkpoint - BASELINE config 3."""
+    return ViTPlan(arch, synth.synth_state_dict(vit_state_shapes(arch), 0), batch, **plan_kwargs)

@@ -401,6 +401,43 @@ int bcosk_nchw_to_nhwc16(const float* x, int32_t nb, int32_t c, int32_t h, int32
 /* NHWC (fp32, or 16-bit planes summed) -> NCHW fp32 */
 int bcosk_nhwc_to_nchw_f32(const void* y, int32_t y_f32, int32_t nb, int32_t c, int32_t h, int32_t w, int32_t ld,
                            int32_t planes, int32_t dtype, float* out, void* stream);
+/* ---------------------------------------------------------------------------------------------
+ * Fused SimpleViT plan (engine/vit.py): token tensors are [rows = images * tokens][planes * d] 16-bit precision planes
+ * (plane pl at column pl * d), so the linear layers run as 1x1 bcosk_igemm launches with only these kernels in between.
+ * ------------------------------------------------------------------------------------------- */
+/* "b c (h p1) (w p2) -> b h w (p1 p2 c)" (bcos/models/vit.py:290-294) of the normalised [x, 1-x] input (bcosify_vit.py:79-82):
+ * x [nb,6,h,w] fp32 (or uint8 RGB [nb,3,h,w], inverse channels formed on the fly) -> out [nb*(h/p)*(w/p)][planes * p*p*6],
+ * column (p1*p + p2)*6 + c; sq [rows] = sum of the stored values squared (the patch-embedding B-cos linear's input norm). */
+int bcosk_vit_patchify(const float* x, int32_t nb, int32_t h, int32_t w, int32_t p, const float* mean6, const float* inv_std6,
+                       void* out, int32_t planes, int32_t dtype, float* sq, void* stream);
+int bcosk_vit_patchify_u8(const uint8_t* x, int32_t nb, int32_t h, int32_t w, int32_t p, const float* mean6, const float* inv_std6,
+                          void* out, int32_t planes, int32_t dtype, float* sq, void* stream);
+/* (x * grad).sum(1) (bcos/common.py:181) from the patch-embedding data gradient g [rows][p*p*6] fp32 (columns as above):
+ * cmap[img,y,x] = sum_c x6[c] * g[..] * inv_std6[c] * out_scale; grad6 [nb,6,h,w] (optional) receives the dynamic linear weights */
+int bcosk_vit_contrib_map(const float* g, const float* x, int32_t nb, int32_t h, int32_t w, int32_t p, const float* inv_std6,
+                          float out_scale, float* cmap, float* grad6, void* stream);
+int bcosk_vit_contrib_map_u8(const float* g, const uint8_t* x, int32_t nb, int32_t h, int32_t w, int32_t p, const float* inv_std6,
+                             float out_scale, float* cmap, float* grad6, void* stream);
+/* DetachableLayerNorm.forward (centered_norms.py:187-224, bias-free): y = (x - mean) / sqrt(var + eps) * w over d, plane rows in
+ * and out; rstd [rows] is kept for the explanation pass, sq [rows] (optional) = sum of the stored outputs squared. */
+int bcosk_vit_ln_fwd(const void* x, int64_t rows, int32_t d, int32_t planes, const float* w, float eps, void* y, float* rstd,
+                     float* sq, int32_t dtype, void* stream);
+/* Explanation backward of that LayerNorm (variance detached, mean in the graph) fused with the residual-stream add and the gain
+ * of the linear layer in front:  G_out = G_in + rstd * (g w - mean_d(g w));  ghat = G_out * gain.
+ * g [rows][d] fp32 or one 16-bit plane; G_in / G_out fp32 (G_in, G_out, gain optional); ghat one 16-bit plane (optional). */
+int bcosk_vit_ln_bwd(const void* g, int32_t g_f32, const float* G_in, int64_t rows, int32_t d, const float* w, const float* rstd,
+                     float* G_out, const void* gain, int32_t gain_f32, void* ghat, int32_t dtype, void* stream);
+/* MyGELU (bcosify_vit.py:27-32) on plane rows: a = u * Phi(u), sq [rows] = sum a^2 (optional); gain [rows][d] (optional, the
+ * saved gain of the B-cos linear that produced u, 16-bit or fp32) is multiplied in place by the detached gate Phi(u). */
+int bcosk_vit_gelu_fwd(const void* u, int64_t rows, int32_t d, int32_t planes, void* a, float* sq, void* gain, int32_t gain_f32,
+                       int32_t dtype, void* stream);
+/* Attention.forward (bcos/models/vit.py:143-158) on plane rows, one CTA per (image, head), dim_head = 64, n <= 208:
+ * qkv [batch*n][planes * 3*heads*64] (q | k | v blocks per plane).  backward = 0: out [batch*n][planes * heads*64] =
+ * softmax(q k^T scale) v.  backward = 1 (explanation mode: q, k frozen): out [batch*n][heads*64] one 16-bit plane = P^T g,
+ * g [batch*n][heads*64] fp32, P recomputed from q, k. */
+int bcosk_vit_attention(const void* qkv, int32_t planes, const float* g, int32_t batch, int32_t n, int32_t heads, int32_t dim_head,
+                        float scale, int32_t backward, void* out, int32_t dtype, void* stream);
+
 /* Seed of a fused trunk's explanation pass from a gradient computed OUTSIDE the plan (CLIP encoders: the attention-pool head
  * bcos/modules/bcosattnpool.py:34-59 runs on the module-level path and autograd hands back d target / d trunk output):
  * g [nb, c, h, w] fp32 NCHW ->  out1[pix, pl*c + ch] = planes(g * seed_scale * mul1[pix, ch])  (mul1 = gain of the block's last conv)

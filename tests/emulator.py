@@ -297,11 +297,89 @@ def run_seed_from_nchw(op: O.SeedFromNchwOp) -> None:
         _split_store(op.out2, o.view(nb, h, w, c), op.planes)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# fused SimpleViT plan (engine/vit.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_vit_patchify(op: O.VitPatchifyOp) -> None:
+    x = _x6(op.x)
+    nb, _, h, w = x.shape
+    p = op.p
+    xn = (x - torch.tensor(op.mean6).view(1, 6, 1, 1)) * torch.tensor(op.inv_std6).view(1, 6, 1, 1)
+    v = xn.view(nb, 6, h // p, p, w // p, p).permute(0, 2, 4, 3, 5, 1).reshape(nb, h // p, w // p, p * p * 6)
+    stored = _split_store(op.out, v.contiguous(), op.planes)
+    if op.sq is not None:
+        op.sq.view(-1)[:] = (stored ** 2).sum(-1).reshape(-1)
+
+
+def run_vit_contrib_map(op: O.VitContribMapOp) -> None:
+    nb, _, h, w = op.x.shape
+    p = op.p
+    g = op.g.view(nb, h // p, w // p, p, p, 6).permute(0, 5, 1, 3, 2, 4).reshape(nb, 6, h, w)
+    g6 = g * torch.tensor(op.inv_std6).view(1, 6, 1, 1) * op.out_scale
+    op.cmap.copy_((_x6(op.x) * g6).sum(1))
+    if op.grad6 is not None:
+        op.grad6.copy_(g6)
+
+
+def run_vit_ln_fwd(op: O.VitLnFwdOp) -> None:
+    x = _join(op.x, op.planes)
+    var, mean = torch.var_mean(x, dim=-1, unbiased=False, keepdim=True)
+    rstd = 1.0 / (var + op.eps).sqrt()
+    y = (x - mean) * rstd * op.w.float()
+    stored = _split_store(op.y, y, op.planes)
+    op.rstd.copy_(rstd.reshape(-1))
+    if op.sq is not None:
+        op.sq.view(-1)[:] = (stored ** 2).sum(-1).reshape(-1)
+
+
+def run_vit_ln_bwd(op: O.VitLnBwdOp) -> None:
+    gw = op.g.float() * op.w.float()
+    gx = op.rstd.float().view(*gw.shape[:-1], 1) * (gw - gw.mean(-1, keepdim=True))
+    if op.G_in is not None:
+        gx = gx + op.G_in
+    if op.G_out is not None:
+        op.G_out.copy_(gx)
+    if op.ghat is not None:
+        v = gx * op.gain.float().view(gx.shape) if op.gain is not None else gx
+        _split_store(op.ghat, v, 1)
+
+
+def run_vit_gelu_fwd(op: O.VitGeluFwdOp) -> None:
+    u = _join(op.u, op.planes)
+    gate = 0.5 * (1.0 + torch.erf(u / 2.0 ** 0.5))
+    stored = _split_store(op.a, u * gate, op.planes)
+    if op.sq is not None:
+        op.sq.view(-1)[:] = (stored ** 2).sum(-1).reshape(-1)
+    if op.gain is not None:
+        op.gain.copy_((op.gain.float() * gate.reshape(op.gain.shape)).to(op.gain.dtype))
+
+
+def run_vit_attention(op: O.VitAttentionOp) -> None:
+    hd = op.heads * op.dh
+    qkv = _join(op.qkv, op.planes).reshape(op.nb, op.n, 3, op.heads, op.dh)
+    q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))                 # [nb, heads, n, dh]
+    prob = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) * op.scale, dim=-1)
+    if not op.backward:
+        o = torch.matmul(prob, v).transpose(1, 2).reshape(op.nb, op.n, hd)
+        _split_store(op.out, o.reshape(op.out.shape[:-1] + (hd,)), op.planes)
+    else:
+        g = op.g.float().reshape(op.nb, op.n, op.heads, op.dh).transpose(1, 2)
+        gv = torch.matmul(prob.transpose(-1, -2), g).transpose(1, 2).reshape(op.nb, op.n, hd)
+        _split_store(op.out, gv.reshape(op.out.shape[:-1] + (hd,)), 1)
+
+
+def run_pixel_sqsum(op: O.PixelSqsumOp) -> None:
+    op.sq.view(-1)[:] = (_join(op.x, op.planes) ** 2).sum(-1).reshape(-1)
+
+
 _DISPATCH = {
     O.IgemmOp: run_igemm, O.InputPrepOp: run_input_prep, O.PatchNormOp: run_patch_norm, O.AvgPoolFwdOp: run_avgpool_fwd,
     O.AvgPoolBwdMulOp: run_avgpool_bwd_mul, O.GapLogitsOp: run_gap_logits, O.FcSeedOp: run_fc_seed,
     O.ContribMapOp: run_contrib_map, O.ExplanationImageOp: run_explanation_image,
     O.TrunkOutOp: run_trunk_out, O.SeedFromNchwOp: run_seed_from_nchw,
+    O.VitPatchifyOp: run_vit_patchify, O.VitContribMapOp: run_vit_contrib_map, O.VitLnFwdOp: run_vit_ln_fwd,
+    O.VitLnBwdOp: run_vit_ln_bwd, O.VitGeluFwdOp: run_vit_gelu_fwd, O.VitAttentionOp: run_vit_attention,
+    O.PixelSqsumOp: run_pixel_sqsum,
 }
 
 

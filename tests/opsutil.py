@@ -21,6 +21,13 @@ OUTPUT_FIELDS = {
     O.ExplanationImageOp: ["out"],
     O.TrunkOutOp: ["out"],
     O.SeedFromNchwOp: ["out1", "out2"],
+    O.VitPatchifyOp: ["out", "sq"],
+    O.VitContribMapOp: ["cmap", "grad6"],
+    O.VitLnFwdOp: ["y", "rstd", "sq"],
+    O.VitLnBwdOp: ["G_out", "ghat"],
+    O.VitGeluFwdOp: ["a", "sq", "gain"],
+    O.VitAttentionOp: ["out"],
+    O.PixelSqsumOp: ["sq"],
 }
 
 

@@ -130,3 +130,23 @@ def test_clip_rn_trunk_plan_matches_oracle():
     cm, rm = plan.cmap, ref["contribution_map"]
     assert torch.nn.functional.cosine_similarity(cm.flatten(1), rm.flatten(1)).min().item() > 0.99999
     assert ((cm - rm).abs().max() / rm.abs().max()).item() < 1e-3
+
+
+def test_vit_plan_matches_oracle():
+    """engine/vit.py: patchify, positional embedding through the residual input, LayerNorm / attention / GELU kernels between the
+    1x1 launches, explanation chain with the fp32 residual-stream gradient - launch list run by the emulator vs the oracle."""
+    from bcos_b200.engine import ViTPlan
+    from bcos_b200.models import vit_state_shapes
+    arch = "simple_vit_ti_patch16_224"
+    shapes = vit_state_shapes(arch)
+    assert shapes == OR.vit_state_shapes(arch)
+    sd = synth.synth_state_dict(shapes, 0)
+    x6 = synth.to_bcos_input(synth.synth_images_u8(2, 64, 1))
+    ref = OR.explain_batched(OR.OracleViT(arch, sd).forward, x6)
+    plan = ViTPlan(arch, sd, 2, planes=3, explain_planes=1, dtype="bf16", device="cpu", image_size=64, want_grad6=True)
+    plan.x_in.copy_(x6)
+    E.run(plan.fwd_ops)
+    E.run(plan.bwd_ops)
+    m = OR.parity_metrics(plan.logits, plan.cmap, ref["logits"], ref["contribution_map"])
+    print(m)
+    assert m["argmax_equal"] and m["logit_rel_err"] < 1e-4 and m["map_cos_min"] > 0.9999, m
