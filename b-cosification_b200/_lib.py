@@ -283,8 +283,9 @@ def vit_gelu_fwd(u, rows, d, planes, a, sq, gain, dtype) -> None:
                                     int(gain is not None and gain.dtype == torch.float32), dtype, _stream()), "bcosk_vit_gelu_fwd")
 
 
-def vit_attention(qkv, planes, g, batch, n, heads, dim_head, scale, backward, out, dtype) -> None:
-    check(load().bcosk_vit_attention(_p(qkv), planes, _p(g), batch, n, heads, dim_head, C.c_float(scale), int(backward), _p(out), dtype,
+def vit_attention(qkv, planes, g, batch, n, heads, dim_head, scale, backward, out, dtype, tc=True) -> None:
+    fn = load().bcosk_vit_attention_tc if tc else load().bcosk_vit_attention
+    check(fn(_p(qkv), planes, _p(g), batch, n, heads, dim_head, C.c_float(scale), int(backward), _p(out), dtype,
                                      _stream()), "bcosk_vit_attention")
 
 

@@ -519,9 +519,11 @@ class VitAttentionOp:
     backward: bool
     out: Tensor          # forward: planes * heads*dh; backward: heads*dh (one plane)
     dtype: int
+    tc: bool = True      # tensor-core kernel (bcosk_vit_attention_tc); False = the CUDA-core shared-memory kernel (n <= 208)
 
     def run(self) -> None:
-        L.vit_attention(self.qkv, self.planes, self.g, self.nb, self.n, self.heads, self.dh, self.scale, self.backward, self.out, self.dtype)
+        L.vit_attention(self.qkv, self.planes, self.g, self.nb, self.n, self.heads, self.dh, self.scale, self.backward, self.out, self.dtype,
+                        self.tc)
 
 
 @dataclass

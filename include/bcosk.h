@@ -438,6 +438,13 @@ int bcosk_vit_gelu_fwd(const void* u, int64_t rows, int32_t d, int32_t planes, v
 int bcosk_vit_attention(const void* qkv, int32_t planes, const float* g, int32_t batch, int32_t n, int32_t heads, int32_t dim_head,
                         float scale, int32_t backward, void* out, int32_t dtype, void* stream);
 
+/* The same attention on the tensor cores (csrc/bcosk_vit_attn.cu: TMA boxes, tcgen05.mma into TMEM for q k^T and for the
+ * probability-weighted sums, softmax by the TMEM-lane threads; V and, in the backward, the probabilities and g are fed as
+ * MN-major operands, so no transpose exists).  Same arguments and results as bcosk_vit_attention up to fp32 rounding;
+ * n <= 256, dim_head = 64.  The explanation pass rounds the probabilities and g / row-sum to ONE 16-bit plane (its format). */
+int bcosk_vit_attention_tc(const void* qkv, int32_t planes, const float* g, int32_t batch, int32_t n, int32_t heads, int32_t dim_head,
+                           float scale, int32_t backward, void* out, int32_t dtype, void* stream);
+
 /* Seed of a fused trunk's explanation pass from a gradient computed OUTSIDE the plan (CLIP encoders: the attention-pool head
  * bcos/modules/bcosattnpool.py:34-59 runs on the module-level path and autograd hands back d target / d trunk output):
  * g [nb, c, h, w] fp32 NCHW ->  out1[pix, pl*c + ch] = planes(g * seed_scale * mul1[pix, ch])  (mul1 = gain of the block's last conv)
