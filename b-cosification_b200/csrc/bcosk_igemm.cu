@@ -294,6 +294,7 @@ __device__ __forceinline__ void epilogue_fwd_fast(const bcosk_igemm_params& p, c
   const uint32_t a4 = smem_u32(s_alpha + j * 32), b4 = smem_u32(s_beta + j * 32);
   const float2 inv2 = make_float2(inv_norm, inv_norm);
   const uint32_t relu_off = p.relu ? 0u : 0xffffffffu;
+  const bool plain = p.scale_mode == BCOSK_SCALE_NONE;       // plain linear map (the ViT's to_qkv): the multiplier is alpha alone
   float2 sq2 = make_float2(0.f, 0.f);
   uint32_t mbits = 0;
 #pragma unroll
@@ -311,11 +312,12 @@ __device__ __forceinline__ void epilogue_fwd_fast(const bcosk_igemm_params& p, c
       if (AFFINE) {
         const float2 kk = __fmul2_rn(h ? make_float2(al.z, al.w) : make_float2(al.x, al.y), inv2);
         t = make_float2(fabsf(vv.x) * kk.x, fabsf(vv.y) * kk.y);                   // |lin| / ||patch|| * alpha
+        if (plain) t = h ? make_float2(al.z, al.w) : make_float2(al.x, al.y);
         y = __ffma2_rn(vv, t, h ? make_float2(be.z, be.w) : make_float2(be.x, be.y));
         y = __fadd2_rn(y, Cvt<T>::unpack2(rw[k]));
       } else {
         // the plan folded sqrt(BN multiplier) into the weights: nothing per channel is left
-        t = make_float2(fabsf(vv.x) * inv_norm, fabsf(vv.y) * inv_norm);
+        t = plain ? make_float2(1.f, 1.f) : make_float2(fabsf(vv.x) * inv_norm, fabsf(vv.y) * inv_norm);
         y = __ffma2_rn(vv, t, Cvt<T>::unpack2(rw[k]));
       }
       const uint32_t ywk = Cvt<T>::pack2(y.x, y.y);
@@ -438,7 +440,7 @@ template <int MODE>
 __device__ __forceinline__ bool epilogue_fast_ok(const bcosk_igemm_params& p) {
   if (MODE == BCOSK_MODE_FWD)
     return !p.y_f32 && p.y_planes == 1 && (p.gain == nullptr || !p.gain_f32) && (p.res == nullptr || p.res_planes == 1) &&
-           p.scale_mode == BCOSK_SCALE_B2 && p.lin_bias == nullptr && p.max_out <= 1;
+           (p.scale_mode == BCOSK_SCALE_B2 || p.scale_mode == BCOSK_SCALE_NONE) && p.lin_bias == nullptr && p.max_out <= 1;
   return (p.y_f32 || p.y_planes == 1) && (p.add == nullptr || p.add_planes == 1) && (p.mul1 == nullptr || !p.mul1_f32) &&
          (p.out2 == nullptr || p.out2_planes == 1) && (p.mul2 == nullptr || !p.mul2_f32);
 }

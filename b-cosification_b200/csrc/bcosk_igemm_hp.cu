@@ -129,7 +129,7 @@ template <typename T>
 __device__ __forceinline__ void hp_fwd_fast(const float (&acc)[32], float inv_norm, uint32_t ab /* smem: alpha[32] of this half, beta at +256 B */,
                                             uint32_t res0 /* plane-0 box or 0 */, uint32_t y0, uint32_t gbox /* fp32 gain box or 0 */,
                                             uint32_t g16 /* 16-bit gain box or 0 */, int row, int j, bool relu, float& sq_acc,
-                                            uint32_t& mbits) {
+                                            uint32_t& mbits, bool plain /* scale mode NONE: multiplier = alpha */) {
   using namespace hp;
   const float floor_v = relu ? 0.f : -FLT_MAX;
   const float2 inv2 = make_float2(inv_norm, inv_norm);
@@ -151,6 +151,7 @@ __device__ __forceinline__ void hp_fwd_fast(const float (&acc)[32], float inv_no
       const float2 vv = make_float2(acc[g * 8 + 2 * k], acc[g * 8 + 2 * k + 1]);
       const float2 kk = __fmul2_rn(pair4(a_lo, a_hi, k), inv2);
       float2 t = make_float2(fabsf(vv.x) * kk.x, fabsf(vv.y) * kk.y);
+      if (plain) t = pair4(a_lo, a_hi, k);
       float2 y = __ffma2_rn(vv, t, pair4(b_lo, b_hi, k));
       y = __fadd2_rn(y, Cvt<T>::unpack2(pick4(r0, k)));
       y = __fadd2_rn(y, Cvt<T>::unpack2(pick4(r1, k)));
@@ -586,7 +587,7 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           uint32_t mbits;
           hp_fwd_fast<T>(acc, inv_norm, smem_u32(s_alpha + j * 32), aux.in16_planes ? r_in16 : 0u, r_out1,
                          aux.out2_kind == 1 ? r_out2 + j * BOX_BYTES : 0u, aux.out2_kind == 3 ? r_out2 : 0u, row, j, p.relu != 0, sq_acc,
-                         mbits);
+                         mbits, p.scale_mode == BCOSK_SCALE_NONE);
           if (p.maskbits != nullptr) p.maskbits[(size_t)ri.m * p.mask_ld + (c0 >> 5)] = mbits;
         } else {
           hp_explain_fast<T>(acc, aux.in16_planes ? r_in16 : 0u, aux.in32 ? r_in32 + j * BOX_BYTES : 0u, r_out1,
@@ -935,7 +936,7 @@ static int launch_hp_mode(const bcosk_igemm_params& p, cudaStream_t st) {
   }
   // ---- the packed two-plane epilogue
   if (MODE == BCOSK_MODE_FWD)
-    aux.fast = p.scale_mode == BCOSK_SCALE_B2 && !p.lin_bias && !p.y_f32 && p.y_planes == 2 && aux.out1_planes == 2 &&
+    aux.fast = (p.scale_mode == BCOSK_SCALE_B2 || p.scale_mode == BCOSK_SCALE_NONE) && !p.lin_bias && !p.y_f32 && p.y_planes == 2 && aux.out1_planes == 2 &&
                (!p.res || aux.in16_planes == 2) && (!p.gain || aux.out2_kind == 1 || aux.out2_kind == 3);
   else
     aux.fast = !p.y_f32 && p.y_planes == 2 && aux.out1_planes == 2 && (!p.add || aux.in16_planes == 2) && (!p.mul1 || aux.in32) &&

@@ -134,7 +134,7 @@ def run_igemm(op: O.IgemmOp) -> None:
         # throughput path (single 16-bit plane): ReLU / mask are decided on the ROUNDED value (packed 16-bit compare) and
         # the sums of squares use the un-rounded fp32 value; the generic path decides on fp32 and squares what it stored
         fast = (not op.y_f32) and op.y_planes == 1 and (op.gain is None or op.gain.dtype != torch.float32) \
-            and op.res_planes == 1 and op.scale_mode == L.BCOSK_SCALE_B2 and op.lin_bias is None
+            and op.res_planes == 1 and op.scale_mode in (L.BCOSK_SCALE_B2, L.BCOSK_SCALE_NONE) and op.lin_bias is None
         pos = (v.to(op.y.dtype).float() > 0) if fast else (v > 0)
         if op.relu:
             v = torch.where(pos, v, torch.zeros_like(v))

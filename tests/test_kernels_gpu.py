@@ -108,6 +108,22 @@ def test_igemm_forward_general_b(bcosk_lib):
     print(_run_and_compare(plan.fwd_ops, tol32=2e-4))
 
 
+@pytest.mark.parametrize("planes", [1, 2])
+def test_igemm_forward_plain_linear(bcosk_lib, planes):
+    """scale mode NONE per launch (the ViT's to_qkv, bcos/models/vit.py:140): y = W x (+ residual), no gain, packed epilogue"""
+    g = torch.Generator().manual_seed(21)
+    plan = _mini_plan(2, planes)
+    x = _rand_act(g, 2, 6, 6, 128, planes)
+    w = torch.randn(192, 128, 1, 1, generator=g) / math.sqrt(128)
+    res = _rand_act(g, 2, 6, 6, 192, planes)
+    for r in (None, res):
+        plan.fwd_ops.clear()
+        y, rec = plan._conv_fwd("plain", x, w, 1, 0, 0, bn=None, relu=False, res=r, want_sq=False, scale_mode=L.BCOSK_SCALE_NONE,
+                                want_gain=False)
+        assert rec.gain is None
+        print(_run_and_compare(plan.fwd_ops, tol16=BF16_TOL if planes == 1 else 2e-4))
+
+
 MAXOUT_CASES = [
     # name, planes, G, cout (GEMM columns), k, b, bias, y_f32
     ("mo2_1plane_16bit", 1, 2, 128, 3, 2.0, False, False),
