@@ -64,6 +64,8 @@ def parse_args():
                          "bf16 plane, the format BASELINE.json names - faster, does not meet the map tolerances")
     ap.add_argument("--no-throughput-record", action="store_true", help="skip the extra bf16 x1 measurement")
     ap.add_argument("--no-train-record", action="store_true", help="skip the fine-tuning-step measurement (BASELINE config 5)")
+    ap.add_argument("--no-vit-record", action="store_true", help="skip the SimpleViT measurements (BASELINE config 3)")
+    ap.add_argument("--vit-batch", type=int, default=256, help="images per GPU of the SimpleViT records")
     ap.add_argument("--no-clip-record", action="store_true", help="skip the CLIP RN50 measurement (BASELINE config 4)")
     ap.add_argument("--clip-batch", type=int, default=512, help="images per GPU of the CLIP RN50 record (config 4: 512)")
     ap.add_argument("--train-batch", type=int, default=64, help="images per GPU of the fine-tuning step (reference recipe: 64)")
@@ -235,6 +237,11 @@ def main():
     if not args.no_clip_record:
         clip = measure_clip_rn50(args, dev, world, barrier, max_over_ranks)
 
+    # ---------------- extra record: BASELINE config 3, B-cosified SimpleViT-Ti/16 and ViT-B/16 forward + explanation at 224^2 ------
+    vit = None
+    if not args.no_vit_record:
+        vit = [measure_vit(args, arch, dev, world, barrier, max_over_ranks) for arch in ("simple_vit_ti_patch16_224", "simple_vit_b_patch16_224")]
+
     plan = synthetic_resnet_plan(args.arch, B, mode=args.mode, device=dev, input_u8=True)
     prec = plan.precision
     plan.load_input(h_in)
@@ -356,6 +363,8 @@ def main():
         res["train_step"] = train
     if clip is not None:
         res["clip_rn50"] = clip
+    if vit is not None:
+        res["vit"] = vit
     if args.layer_table:
         rows = []
         for o, t in zip(all_ops, per_op):
@@ -373,6 +382,43 @@ def main():
         res["cpu_baseline"] = {"value": c["value"], "unit": "img/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]}
     print(json.dumps(res), file=real_stdout, flush=True)
     D.shutdown()
+
+
+def measure_vit(args, arch, dev, world, barrier, max_over_ranks):
+    """BASELINE config 3: B-cosified SimpleViT (bcosify_vit simple_vit, BcosLinear attention / MLP) forward + explanation at 224^2
+    through the fused plan (engine/vit.py: 1x1 tcgen05 launches, tensor-core attention, CUDA graph), same operand format as the
+    main record.  Device-resident uint8 inputs, CUDA events, max over ranks."""
+    import torch
+    from bcos_b200.models import synthetic_vit_plan
+    from bcos_b200.utils import synth
+    Bv, reps = args.vit_batch, 5
+    plan = synthetic_vit_plan(arch, Bv, mode=args.mode, device=dev, input_u8=True)
+    x = torch.from_numpy(synth.synth_images_u8(32, 224, 7)).repeat((Bv + 31) // 32, 1, 1, 1)[:Bv].to(dev)
+    plan.load_input(x)
+    plan.capture()
+    for _ in range(3):
+        plan.replay_all()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    for _ in range(reps):
+        plan.replay_forward()
+    ev[1].record()
+    for _ in range(reps):
+        plan.replay_all()
+    ev[2].record()
+    barrier()
+    ms_f = max_over_ranks(ev[0].elapsed_time(ev[1])) / reps
+    ms_x = max_over_ranks(ev[1].elapsed_time(ev[2])) / reps
+    ok = bool(torch.isfinite(plan.logits).all() and torch.isfinite(plan.cmap).all())
+    rec = {"workload": f"B-cosified {arch} forward + explain at 224^2 (BASELINE config 3)", "arch": arch, "batch_per_gpu": Bv, "n_gpus": world,
+           "mode": args.mode, "forward_ms_per_step": ms_f, "forward_value": world * Bv / (ms_f * 1e-3), "ms_per_step": ms_x,
+           "value": world * Bv / (ms_x * 1e-3), "unit": "img/s", "launches_per_step": plan.num_launches(),
+           "executed_gemm_tflops_per_gpu": plan.gemm_flops() / (ms_x * 1e-3) / 1e12, "finite": ok,
+           "parity": "tests/test_vit_gpu.py: argmax equal, logits <= 1e-6 rel, map cosine 0.9999999, max-abs <= 3.8e-4 of range vs the reference goldens (contract mode)"}
+    del plan
+    torch.cuda.empty_cache()
+    return rec
 
 
 def measure_clip_rn50(args, dev, world, barrier, max_over_ranks):
