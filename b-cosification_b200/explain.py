@@ -44,11 +44,11 @@ class explanation_mode:
         return wrapped
 
 
-def gradient_to_image(image: Tensor, linear_mapping: Tensor, smooth: int = 15, alpha_percentile: float = 99.5) -> Tensor:
+def gradient_to_image(image: Tensor, linear_mapping: Tensor, smooth: int = 15, alpha_percentile: float = 99.5):
     """RGBA explanation [H, W, 4] from a 6-channel image and its dynamic linear weights (bcos/common.py:387-436), computed
-    by `bcosk_explanation_rgba` on the tensor's CUDA device (the reference converts to numpy for plotting; call
-    `.cpu().numpy()` on the result for that).  Batches: `gradient_to_image_batch`."""
-    return gradient_to_image_batch(image[None], linear_mapping[None], smooth, alpha_percentile)[0]
+    by `bcosk_explanation_rgba` on the tensor's CUDA device and returned as a NUMPY array like the reference's (so
+    `plt.imshow(model.explain(x)["explanation"])` works unchanged).  Device tensors / batches: `gradient_to_image_batch`."""
+    return gradient_to_image_batch(image[None], linear_mapping[None], smooth, alpha_percentile)[0].cpu().numpy()
 
 
 def gradient_to_image_batch(images: Tensor, linear_mappings: Tensor, smooth: int = 15,

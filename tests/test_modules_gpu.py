@@ -170,6 +170,7 @@ def test_module_level_resnet18_matches_golden(bcosk_lib, golden_dir):
     e = m.explain(x6[:1].clone().requires_grad_(True))
     assert e["prediction"] == int(gold["logits"][0].argmax())
     assert tuple(e["explanation"].shape) == (224, 224, 4)
+    assert isinstance(e["explanation"], np.ndarray)            # like the reference: plt.imshow(expl["explanation"]) works unchanged
 
 
 def test_module_level_densenet121_matches_golden(bcosk_lib, golden_dir):
