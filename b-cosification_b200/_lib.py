@@ -289,6 +289,29 @@ def vit_attention(qkv, planes, g, batch, n, heads, dim_head, scale, backward, ou
                                      _stream()), "bcosk_vit_attention")
 
 
+# ---- fused DenseNet plan (csrc/bcosk_dense.cu)
+def dense_bn_relu_fwd(x, rows, c, planes, x_ld, x_plane_stride, alpha, relu, y, sq, maskbits, dtype) -> None:
+    check(load().bcosk_dense_bn_relu_fwd(_p(x), C.c_int64(rows), c, planes, x_ld, x_plane_stride, _p(alpha), int(relu), _p(y), _p(sq),
+                                         _p(maskbits), dtype, _stream()), "bcosk_dense_bn_relu_fwd")
+
+
+def dense_bn_relu_bwd(g, rows, c, alpha, maskbits, G, g_ld, accumulate, dtype) -> None:
+    import torch
+    check(load().bcosk_dense_bn_relu_bwd(_p(g), int(g.dtype == torch.float32), C.c_int64(rows), c, _p(alpha), _p(maskbits), _p(G), g_ld,
+                                         int(accumulate), dtype, _stream()), "bcosk_dense_bn_relu_bwd")
+
+
+def dense_slice_cast(G, g_ld, col0, rows, c, gain, scale, out, dtype) -> None:
+    import torch
+    check(load().bcosk_dense_slice_cast(_p(G), g_ld, col0, C.c_int64(rows), c, _p(gain), int(gain is not None and gain.dtype == torch.float32),
+                                        C.c_float(scale), _p(out), dtype, _stream()), "bcosk_dense_slice_cast")
+
+
+def copy_rows_2d(dst_ptr, dst_pitch, src_ptr, src_pitch, width, rows) -> None:
+    check(load().bcosk_copy_rows_2d(C.c_void_p(dst_ptr), C.c_int64(dst_pitch), C.c_void_p(src_ptr), C.c_int64(src_pitch), C.c_int64(width),
+                                    C.c_int64(rows), _stream()), "bcosk_copy_rows_2d")
+
+
 def seed_from_nchw(g, seed_scale, mul1, out1, mask2, mul2, out2, planes, dtype) -> None:
     import torch
     nb, c, h, w = g.shape

@@ -1,0 +1,210 @@
+// bcosk_dense.cu -- bandwidth kernels of the fused DenseNet plan (engine/densenet.py) for sm_100a.
+//
+// A dense block keeps ONE feature tensor F [pixels][planes * C_total] (NHWC 16-bit precision planes); every layer's 3x3 conv
+// writes its `growth` new channels straight into its slice of F (bcosk_igemm with a column offset), so the torch.cat of the
+// reference (torchvision densenet.py _DenseLayer / _DenseBlock, B-cosified by bcosify.py:74-113) never copies anything.
+// Every consumer normalises the channels it reads with ITS OWN uncentred BN (batchnorm_uncentered.py:49-58, eval mode) + ReLU:
+//
+//   dense_bn_relu_fwd        t = relu(F[:, :c] * alpha) as dense plane rows + sum t^2 per pixel + ReLU bits
+//   dense_bn_relu_bwd        G[:, :c] (+)= g * alpha * mask   (explanation / plain backward; G: fp32 feature-gradient tensor)
+//   dense_slice_cast         ghat = G[:, col0 : col0 + c] (* gain) -> one 16-bit plane, the A operand of a data gradient
+//   copy_rows_2d             strided device copy (pool output -> the first channels of the next block's F)
+//
+// One warp per pixel row, 16-byte vectors, shuffle reductions, fp32 arithmetic.
+#include "../../include/bcosk.h"
+#include "bcosk_common.cuh"
+#include "bcosk_host.h"
+
+namespace bcosk {
+
+static inline cudaStream_t SD(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename T>
+__device__ __forceinline__ void d_unpack8(const uint4& u, float (&f)[8]) {
+  float2 q;
+  q = Cvt<T>::unpack2(u.x); f[0] = q.x; f[1] = q.y;
+  q = Cvt<T>::unpack2(u.y); f[2] = q.x; f[3] = q.y;
+  q = Cvt<T>::unpack2(u.z); f[4] = q.x; f[5] = q.y;
+  q = Cvt<T>::unpack2(u.w); f[6] = q.x; f[7] = q.y;
+}
+__device__ __forceinline__ void d_load8_f32(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// x rows: [rows][planes * x_pstride] (channels [0, c) of every plane are read); y rows: [rows][planes * c] dense.
+template <typename T>
+__global__ void dense_bn_relu_fwd_kernel(const T* __restrict__ x, long long rows, int c, int planes, int x_ld, int x_pstride,
+                                         const float* __restrict__ alpha, int relu, T* __restrict__ y, float* __restrict__ sq,
+                                         uint32_t* __restrict__ maskbits) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31, nvec = c >> 3;
+  const T* xr = x + row * (long long)x_ld;
+  T* yr = y + row * (long long)planes * c;
+  float sacc = 0.f;
+  for (int v0 = 0; v0 < nvec; v0 += 32) {        // whole warp iterates together (shuffles below)
+    const int v = v0 + lane;
+    uint32_t bits = 0;
+    if (v < nvec) {
+      float f[8];
+      d_unpack8<T>(__ldg(reinterpret_cast<const uint4*>(xr + v * 8)), f);
+      for (int pl = 1; pl < planes; ++pl) {
+        float g[8];
+        d_unpack8<T>(__ldg(reinterpret_cast<const uint4*>(xr + (size_t)pl * x_pstride + v * 8)), g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += g[i];
+      }
+      float a[8];
+      d_load8_f32(alpha + v * 8, a);
+      float r[8], acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float t = f[i] * a[i];
+        const bool pos = !relu || t > 0.f;
+        bits |= (pos ? 1u : 0u) << i;
+        r[i] = pos ? t : 0.f;
+        acc[i] = 0.f;
+      }
+      for (int pl = 0; pl < planes; ++pl) {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          w[k] = Cvt<T>::pack2(r[2 * k], r[2 * k + 1]);
+          const float2 q = Cvt<T>::unpack2(w[k]);
+          r[2 * k] -= q.x; r[2 * k + 1] -= q.y;
+          acc[2 * k] += q.x; acc[2 * k + 1] += q.y;
+        }
+        *reinterpret_cast<uint4*>(yr + (size_t)pl * c + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sacc = fmaf(acc[i], acc[i], sacc);
+    }
+    if (maskbits != nullptr) {
+      // lanes 4k .. 4k+3 hold the four 8-channel groups of mask word k of this 256-channel step
+      uint32_t wbits = bits << ((lane & 3) * 8);
+      wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
+      wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
+      const int word = (v0 >> 2) + (lane >> 2);
+      if ((lane & 3) == 0 && word < (c + 31) / 32) maskbits[row * ((c + 31) / 32) + word] = wbits;
+    }
+  }
+  sacc = warp_sum(sacc);
+  if (lane == 0 && sq != nullptr) sq[row] = sacc;
+}
+
+// G rows: [rows][g_ld] fp32, channels [0, c) updated: G = (accumulate ? G : 0) + g * alpha * mask.  g: [rows][c] fp32 or 16-bit.
+template <typename T>
+__global__ void dense_bn_relu_bwd_kernel(const void* __restrict__ g, int g_f32, long long rows, int c, const float* __restrict__ alpha,
+                                         const uint32_t* __restrict__ maskbits, float* __restrict__ G, int g_ld, int accumulate) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (row, 8-channel group)
+  const int nvec = c >> 3;
+  if (idx >= rows * nvec) return;
+  const long long row = idx / nvec;
+  const int v = (int)(idx - row * nvec);
+  float f[8];
+  if (g_f32) d_load8_f32(reinterpret_cast<const float*>(g) + row * c + v * 8, f);
+  else d_unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(g) + row * c + v * 8)), f);
+  float a[8];
+  d_load8_f32(alpha + v * 8, a);
+  uint32_t mb = 0xffu;
+  if (maskbits != nullptr) mb = (__ldg(maskbits + row * ((c + 31) / 32) + (v >> 2)) >> ((v & 3) * 8)) & 0xffu;
+  float* gp = G + row * (long long)g_ld + v * 8;
+  float o[8];
+  if (accumulate) {
+    const float4 p0 = *reinterpret_cast<const float4*>(gp), p1 = *reinterpret_cast<const float4*>(gp + 4);
+    o[0] = p0.x; o[1] = p0.y; o[2] = p0.z; o[3] = p0.w; o[4] = p1.x; o[5] = p1.y; o[6] = p1.z; o[7] = p1.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] += ((mb >> i) & 1u) ? f[i] * a[i] : 0.f;
+  reinterpret_cast<float4*>(gp)[0] = make_float4(o[0], o[1], o[2], o[3]);
+  reinterpret_cast<float4*>(gp)[1] = make_float4(o[4], o[5], o[6], o[7]);
+}
+
+// out [rows][c] one 16-bit plane = G[rows][col0 : col0 + c] (fp32, row pitch g_ld) * gain[rows][c] (optional, 16-bit or fp32) * scale
+template <typename T>
+__global__ void dense_slice_cast_kernel(const float* __restrict__ G, int g_ld, int col0, long long rows, int c, const void* __restrict__ gain,
+                                        int gain_f32, float scale, T* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nvec = c >> 3;
+  if (idx >= rows * nvec) return;
+  const long long row = idx / nvec;
+  const int v = (int)(idx - row * nvec);
+  float f[8];
+  d_load8_f32(G + row * (long long)g_ld + col0 + v * 8, f);
+  if (gain != nullptr) {
+    float gn[8];
+    if (gain_f32) d_load8_f32(reinterpret_cast<const float*>(gain) + row * c + v * 8, gn);
+    else d_unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(gain) + row * c + v * 8)), gn);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] *= gn[i];
+  }
+  uint32_t w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[k] = Cvt<T>::pack2(f[2 * k] * scale, f[2 * k + 1] * scale);
+  *reinterpret_cast<uint4*>(out + row * c + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+}  // namespace bcosk
+
+using namespace bcosk;
+
+extern "C" int bcosk_dense_bn_relu_fwd(const void* x, int64_t rows, int32_t c, int32_t planes, int32_t x_ld, int32_t x_plane_stride,
+                                       const float* alpha, int32_t relu, void* y, float* sq, uint32_t* maskbits, int32_t dtype, void* stream) {
+  if (!x || !y || !alpha || rows < 1 || c < 8 || c % 8 || planes < 1 || planes > 3 || x_ld % 8 || x_plane_stride % 8)
+    return set_error(BCOSK_EINVAL, "dense_bn_relu_fwd: bad argument");
+  if (maskbits && c % 32) return set_error(BCOSK_EINVAL, "dense_bn_relu_fwd: mask bits need c % 32 == 0");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (dtype == BCOSK_DTYPE_BF16)
+    dense_bn_relu_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, SD(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, c, planes, x_ld,
+                                                                        x_plane_stride, alpha, relu, reinterpret_cast<__nv_bfloat16*>(y), sq, maskbits);
+  else if (dtype == BCOSK_DTYPE_F16)
+    dense_bn_relu_fwd_kernel<__half><<<grid, 256, 0, SD(stream)>>>(reinterpret_cast<const __half*>(x), rows, c, planes, x_ld, x_plane_stride, alpha,
+                                                                 relu, reinterpret_cast<__half*>(y), sq, maskbits);
+  else
+    return set_error(BCOSK_EINVAL, "dense_bn_relu_fwd: dtype");
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_dense_bn_relu_bwd(const void* g, int32_t g_f32, int64_t rows, int32_t c, const float* alpha, const uint32_t* maskbits,
+                                       float* G, int32_t g_ld, int32_t accumulate, int32_t dtype, void* stream) {
+  if (!g || !G || !alpha || rows < 1 || c < 8 || c % 8 || g_ld % 4 || g_ld < c) return set_error(BCOSK_EINVAL, "dense_bn_relu_bwd: bad argument");
+  const long long n = rows * (c / 8);
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (dtype == BCOSK_DTYPE_BF16)
+    dense_bn_relu_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, SD(stream)>>>(g, g_f32, rows, c, alpha, maskbits, G, g_ld, accumulate);
+  else if (dtype == BCOSK_DTYPE_F16)
+    dense_bn_relu_bwd_kernel<__half><<<grid, 256, 0, SD(stream)>>>(g, g_f32, rows, c, alpha, maskbits, G, g_ld, accumulate);
+  else
+    return set_error(BCOSK_EINVAL, "dense_bn_relu_bwd: dtype");
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_dense_slice_cast(const float* G, int32_t g_ld, int32_t col0, int64_t rows, int32_t c, const void* gain, int32_t gain_f32,
+                                      float scale, void* out, int32_t dtype, void* stream) {
+  if (!G || !out || rows < 1 || c < 8 || c % 8 || col0 % 4 || g_ld % 4 || col0 + c > g_ld)
+    return set_error(BCOSK_EINVAL, "dense_slice_cast: bad argument");
+  const long long n = rows * (c / 8);
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (dtype == BCOSK_DTYPE_BF16)
+    dense_slice_cast_kernel<__nv_bfloat16><<<grid, 256, 0, SD(stream)>>>(G, g_ld, col0, rows, c, gain, gain_f32, scale, reinterpret_cast<__nv_bfloat16*>(out));
+  else if (dtype == BCOSK_DTYPE_F16)
+    dense_slice_cast_kernel<__half><<<grid, 256, 0, SD(stream)>>>(G, g_ld, col0, rows, c, gain, gain_f32, scale, reinterpret_cast<__half*>(out));
+  else
+    return set_error(BCOSK_EINVAL, "dense_slice_cast: dtype");
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_copy_rows_2d(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes, int64_t width_bytes,
+                                  int64_t rows, void* stream) {
+  if (!dst || !src || rows < 1 || width_bytes < 1) return set_error(BCOSK_EINVAL, "copy_rows_2d: bad argument");
+  BCOSK_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes, (size_t)rows,
+                                     cudaMemcpyDeviceToDevice, SD(stream)));
+  return BCOSK_OK;
+}

@@ -3,3 +3,4 @@ from .resnet import PRECISION_MODES, PipelinedExplainer, ResNetPlan  # noqa: F40
 from .train import ResNetTrainPlan  # noqa: F401
 from .clip_rn import CLIPResNetPlan  # noqa: F401
 from .vit import ViTPlan  # noqa: F401
+from .densenet import DenseNetPlan  # noqa: F401

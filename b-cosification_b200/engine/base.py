@@ -175,7 +175,8 @@ class PlanBase:
                   inv_norm: Optional[Tensor] = None, kch: int = 64, want_sq: bool = True,
                   sq_geom: Optional[Tuple[int, int, int, int, int]] = None, lin_bias: Optional[Tensor] = None,
                   sq_eps: Tuple[float, float] = (1e-6, 0.0), flat: bool = False, want_inv: bool = False,
-                  max_out: int = 1, scale_mode: Optional[int] = None, want_gain: bool = True) -> Tuple[Act, ConvRec]:
+                  max_out: int = 1, scale_mode: Optional[int] = None, want_gain: bool = True,
+                  y_buf: Optional[Tensor] = None, y_col: int = 0) -> Tuple[Act, ConvRec]:
         """One fused launch: B-cos conv (+BN multiplier, +residual, +ReLU).  The patch norm comes from `x.sq`
         (per-pixel sums of squares written by x's producer) and is evaluated inside the kernel; `sq_geom`
         overrides its (h, w, k, stride, pad) when the GEMM geometry is not the convolution's (space-to-depth stem).
@@ -223,7 +224,12 @@ class PlanBase:
         parts = (o + block_n - 1) // block_n
         yp = 1 if y_f32 else self.planes
         oy = o // max_out                 # columns that leave the epilogue
-        y = self._empty(nb, oh, ow, yp * oy, dtype=torch.float32 if y_f32 else self.dt)
+        if y_buf is not None:             # the launch writes columns [y_col, y_col + oy) of every plane of a wider tensor (DenseNet features)
+            assert tuple(y_buf.shape[:3]) == (nb, oh, ow) and not y_f32 and y_buf.shape[-1] % yp == 0 and y_col % 8 == 0
+            assert y_col + oy <= y_buf.shape[-1] // yp and not flat
+            y = y_buf
+        else:
+            y = self._empty(nb, oh, ow, yp * oy, dtype=torch.float32 if y_f32 else self.dt)
         rec = ConvRec(name, w, stride, pad_lo, pad_hi, (h, wd), (oh, ow), cin_phys)
         # y = lin |lin| / n, clamped at 0: the explanation gain |lin| / n is sqrt(y / n) - not stored where that holds
         # (ReLU, no residual, BN multiplier folded, b = 2, throughput mode)
@@ -259,7 +265,7 @@ class PlanBase:
             lin_bias=None if lin_bias is None else self._dev(lin_bias),
             res=None if res is None else res.t, res_planes=self.planes,
             gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32, hp_accum=self.hp_accum, hp_chunk=self.hp_chunk, flat=flat,
-            inv_norm_out=inv_out, max_out=max_out, amax=rec.amax,
+            inv_norm_out=inv_out, max_out=max_out, amax=rec.amax, y_col=y_col,
             algo_flops=2.0 * M * o * float((w != 0).sum().item()) / o))
         rec.algo_flops = self.fwd_ops[-1].algo_flops
         return Act(y, oy, sq, parts), rec

@@ -76,6 +76,8 @@ class IgemmOp:
     side_mapped: bool = False        # include/bcosk.h `side_mapped`: mul1 / out2 / ... follow the mapped output row
     inv_norm_out: Optional[Tensor] = None      # forward: [M] fp32, receives the 1/||patch|| the launch used
     mul1_sqrt_scale: Optional[Tensor] = None   # explain: mul1 holds the producer's ReLU output, gain = sqrt(mul1 * this[row])
+    y_col: int = 0                             # first column of the n-column slice of `y` this launch writes in every plane (DenseNet
+                                               # feature tensors: y = the whole block tensor, y_ld = its row pitch); 0 = y is the launch's own
     max_out: int = 1                           # include/bcosk.h `max_out`: groups of adjacent units reduced in the forward epilogue
     amax: Optional[Tensor] = None              # [M, n / max_out] uint8: index of the kept unit
 
@@ -101,7 +103,9 @@ class IgemmOp:
         a_pix = self.M if strided_1x1 else nb * h * w
         total = a_pix * ac * self.a.element_size() * self.a_dense_frac
         total += nbytes(self.b)
-        ydense = self.M * (self.y.shape[-1]) * self.y.element_size()      # rows actually written
+        ywidth = self.y.shape[-1] if (self.y_col == 0 and self.max_out == 1 and self.y.shape[-1] <= (1 if self.y_f32 else self.y_planes) * self.n) \
+            else (1 if self.y_f32 else self.y_planes) * (self.n // max(self.max_out, 1))
+        ydense = self.M * ywidth * self.y.element_size()      # rows actually written
         total += ydense
         if self.inv_norm is None and self.sq_in is not None:
             total += nbytes(self.sq_in)
@@ -181,7 +185,7 @@ class IgemmOp:
             p.maskbits = self.maskbits.data_ptr()
             p.mask_ld = self.maskbits.shape[-1]
         p.set_ptr("sq_out", self.sq_out)
-        p.y = self.y.data_ptr()
+        p.y = self.y.data_ptr() + self.y_col * self.y.element_size()
         p.y_ld = self.y.shape[-1]
         p.y_planes = self.y_planes
         p.y_plane_stride = self.y.shape[-1] // self.y_planes
@@ -538,6 +542,82 @@ class PixelSqsumOp:
 
     def run(self) -> None:
         L.pixel_sqsum(self.x, self.sq.numel(), self.c, self.planes, self.c, self.planes * self.c, self.dtype, self.sq)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Fused DenseNet plan (engine/densenet.py; kernels: csrc/bcosk_dense.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class DenseBnReluFwdOp:
+    """t = relu(F[:, :c] * alpha): dense plane rows + sum t^2 per pixel + ReLU bits."""
+    name: str
+    x: Tensor            # block feature tensor [nb, h, w, planes * c_total]
+    c: int
+    planes: int
+    alpha: Tensor        # [c] fp32
+    relu: bool
+    y: Tensor            # [nb, h, w, planes * c]
+    sq: Optional[Tensor]
+    maskbits: Optional[Tensor]   # [rows, c/32] int32
+    dtype: int
+
+    def run(self) -> None:
+        ld = self.x.shape[-1]
+        L.dense_bn_relu_fwd(self.x, self.y.numel() // self.y.shape[-1], self.c, self.planes, ld, ld // self.planes, self.alpha, self.relu,
+                            self.y, self.sq, self.maskbits, self.dtype)
+
+
+@dataclass
+class DenseBnReluBwdOp:
+    """G[:, :c] (+)= g * alpha * mask  (G: fp32 feature-gradient tensor of the block)."""
+    name: str
+    g: Tensor            # [nb, h, w, c] fp32 or 16-bit
+    c: int
+    alpha: Tensor
+    maskbits: Optional[Tensor]
+    G: Tensor            # [nb, h, w, c_total] fp32
+    accumulate: bool
+    dtype: int
+
+    def run(self) -> None:
+        L.dense_bn_relu_bwd(self.g, self.g.numel() // self.g.shape[-1], self.c, self.alpha, self.maskbits, self.G, self.G.shape[-1],
+                            self.accumulate, self.dtype)
+
+
+@dataclass
+class DenseSliceCastOp:
+    """out (one 16-bit plane) = G[:, col0 : col0 + c] * gain * scale."""
+    name: str
+    G: Tensor            # [nb, h, w, c_total] fp32
+    col0: int
+    c: int
+    gain: Optional[Tensor]   # [rows, c]
+    scale: float
+    out: Tensor          # [nb, h, w, c] 16-bit
+    dtype: int
+
+    def run(self) -> None:
+        L.dense_slice_cast(self.G, self.G.shape[-1], self.col0, self.out.numel() // self.out.shape[-1], self.c, self.gain, self.scale,
+                           self.out, self.dtype)
+
+
+@dataclass
+class CopyChannelsOp:
+    """dst[:, pl * dst_pstride + dst_col : ... + c] = src[:, pl * c : (pl + 1) * c] for every plane (strided device copies)."""
+    name: str
+    src: Tensor          # [.., planes * c] dense
+    c: int
+    planes: int
+    dst: Tensor          # [.., planes * c_total]
+    dst_col: int
+
+    def run(self) -> None:
+        rows = self.src.numel() // self.src.shape[-1]
+        es = self.src.element_size()
+        ld_s, ld_d = self.src.shape[-1], self.dst.shape[-1]
+        for pl in range(self.planes):
+            L.copy_rows_2d(self.dst.data_ptr() + (pl * (ld_d // self.planes) + self.dst_col) * es, ld_d * es,
+                           self.src.data_ptr() + pl * self.c * es, ld_s * es, self.c * es, rows)
 
 
 def run_ops(ops) -> None:

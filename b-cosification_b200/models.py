@@ -9,6 +9,7 @@ from __future__ import annotations
 from typing import Dict, Tuple
 
 from .engine.clip_rn import CLIPResNetPlan
+from .engine.densenet import DENSENET_ARCH, DenseNetPlan, dn_names
 from .engine.resnet import RESNET_ARCH, ResNetPlan
 from .engine.vit import VIT_ARCH, ViTPlan
 from .utils import synth
@@ -120,3 +121,42 @@ def vit_state_shapes(arch: str, num_classes: int = 1000, patch: int = 16) -> Dic
 def synthetic_vit_plan(arch: str, batch: int, **plan_kwargs) -> ViTPlan:
     """Fused SimpleViT plan over the synthetic (random-init) checkpoint - BASELINE config 3."""
     return ViTPlan(arch, synth.synth_state_dict(vit_state_shapes(arch), 0), batch, **plan_kwargs)
+
+
+def densenet_state_shapes(arch: str, num_classes: int = 1000, bn_size: int = 4) -> Dict[str, Tuple[int, ...]]:
+    """Keys/shapes of `BcosifyNetwork(DenseNetBcos(...))` (bcosify.py:22-113 over torchvision's DenseNet, classifier as a 1x1 B-cos
+    conv before the global average: bcos/models/standard_models.py:56-63), biases removed by the factories."""
+    growth, blocks, init = DENSENET_ARCH[arch]
+    shapes: Dict[str, Tuple[int, ...]] = {}
+
+    def bn(prefix, c):
+        shapes[prefix + ".weight"] = (c,)
+        shapes[prefix + ".running_mean"] = (c,)
+        shapes[prefix + ".running_var"] = (c,)
+        shapes[prefix + ".num_batches_tracked"] = ()
+
+    nm = dn_names(len(blocks))
+    shapes[nm["conv0"] + ".linear.weight"] = (init, 6, 7, 7)
+    bn(nm["norm0"], init)
+    c = init
+    for bi, nlayers in enumerate(blocks, start=1):
+        for li in range(1, nlayers + 1):
+            p = nm[f"denseblock{bi}"] + f".denselayer{li}"
+            bn(p + ".norm1", c)
+            shapes[p + ".conv1.linear.weight"] = (bn_size * growth, c, 1, 1)
+            bn(p + ".norm2", bn_size * growth)
+            shapes[p + ".conv2.linear.weight"] = (growth, bn_size * growth, 3, 3)
+            c += growth
+        if bi != len(blocks):
+            bn(nm[f"transition{bi}.norm"], c)
+            shapes[nm[f"transition{bi}.conv"] + ".linear.weight"] = (c // 2, c, 1, 1)
+            c //= 2
+    bn(nm["norm5"], c)
+    shapes["model.classifier.linear.weight"] = (num_classes, c, 1, 1)
+    return shapes
+
+
+def synthetic_densenet_plan(arch: str, batch: int, **plan_kwargs) -> DenseNetPlan:
+    """Fused DenseNet plan over the synthetic (random-init, BN-calibrated) checkpoint."""
+    sd = synth.synthetic_checkpoint(arch, densenet_state_shapes(arch))
+    return DenseNetPlan(arch, sd, batch, **plan_kwargs)

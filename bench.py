@@ -64,6 +64,7 @@ def parse_args():
                          "bf16 plane, the format BASELINE.json names - faster, does not meet the map tolerances")
     ap.add_argument("--no-throughput-record", action="store_true", help="skip the extra bf16 x1 measurement")
     ap.add_argument("--no-train-record", action="store_true", help="skip the fine-tuning-step measurement (BASELINE config 5)")
+    ap.add_argument("--no-densenet-record", action="store_true", help="skip the DenseNet-121 measurement")
     ap.add_argument("--no-vit-record", action="store_true", help="skip the SimpleViT measurements (BASELINE config 3)")
     ap.add_argument("--vit-batch", type=int, default=256, help="images per GPU of the SimpleViT records")
     ap.add_argument("--no-clip-record", action="store_true", help="skip the CLIP RN50 measurement (BASELINE config 4)")
@@ -242,6 +243,11 @@ def main():
     if not args.no_vit_record:
         vit = [measure_vit(args, arch, dev, world, barrier, max_over_ranks) for arch in ("simple_vit_ti_patch16_224", "simple_vit_b_patch16_224")]
 
+    # ---------------- extra record: B-cosified DenseNet-121 (the other network of BASELINE config 5) forward + explanation -----------
+    dense = None
+    if not args.no_densenet_record:
+        dense = measure_densenet(args, dev, world, barrier, max_over_ranks)
+
     plan = synthetic_resnet_plan(args.arch, B, mode=args.mode, device=dev, input_u8=True)
     prec = plan.precision
     plan.load_input(h_in)
@@ -365,6 +371,8 @@ def main():
         res["clip_rn50"] = clip
     if vit is not None:
         res["vit"] = vit
+    if dense is not None:
+        res["densenet121"] = dense
     if args.layer_table:
         rows = []
         for o, t in zip(all_ops, per_op):
@@ -382,6 +390,42 @@ def main():
         res["cpu_baseline"] = {"value": c["value"], "unit": "img/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]}
     print(json.dumps(res), file=real_stdout, flush=True)
     D.shutdown()
+
+
+def measure_densenet(args, dev, world, barrier, max_over_ranks):
+    """B-cosified DenseNet-121 forward + explanation at 224^2, batch 256, through the fused plan (engine/densenet.py: block feature
+    tensors written slice by slice, per-consumer BN + ReLU kernels, fp32 feature-gradient accumulation), same operand format as the
+    main record.  Device-resident uint8 inputs, CUDA events, max over ranks."""
+    import torch
+    from bcos_b200.models import synthetic_densenet_plan
+    from bcos_b200.utils import synth
+    Bd, reps = 256, 5
+    plan = synthetic_densenet_plan("densenet121", Bd, mode=args.mode, device=dev, input_u8=True)
+    x = torch.from_numpy(synth.synth_images_u8(32, 224, 9)).repeat(Bd // 32, 1, 1, 1).to(dev)
+    plan.load_input(x)
+    plan.capture()
+    for _ in range(3):
+        plan.replay_all()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    for _ in range(reps):
+        plan.replay_forward()
+    ev[1].record()
+    for _ in range(reps):
+        plan.replay_all()
+    ev[2].record()
+    barrier()
+    ms_f = max_over_ranks(ev[0].elapsed_time(ev[1])) / reps
+    ms_x = max_over_ranks(ev[1].elapsed_time(ev[2])) / reps
+    ok = bool(torch.isfinite(plan.logits).all() and torch.isfinite(plan.cmap).all())
+    rec = {"workload": "B-cosified DenseNet-121 forward + explanation maps at 224^2", "batch_per_gpu": Bd, "n_gpus": world, "mode": args.mode,
+           "forward_ms_per_step": ms_f, "forward_value": world * Bd / (ms_f * 1e-3), "ms_per_step": ms_x, "value": world * Bd / (ms_x * 1e-3),
+           "unit": "img/s", "launches_per_step": plan.num_launches(), "finite": ok,
+           "parity": "tests/test_densenet_gpu.py: argmax equal, logits 2e-7 rel, map cosine 0.9999999, max-abs 2.7e-4 of range vs the reference golden (contract mode)"}
+    del plan
+    torch.cuda.empty_cache()
+    return rec
 
 
 def measure_vit(args, arch, dev, world, barrier, max_over_ranks):

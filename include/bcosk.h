@@ -445,6 +445,28 @@ int bcosk_vit_attention(const void* qkv, int32_t planes, const float* g, int32_t
 int bcosk_vit_attention_tc(const void* qkv, int32_t planes, const float* g, int32_t batch, int32_t n, int32_t heads, int32_t dim_head,
                            float scale, int32_t backward, void* out, int32_t dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused DenseNet plan (engine/densenet.py).  A dense block keeps ONE feature tensor F [pixels][planes * C_total]; every layer's
+ * 3x3 launch writes its new channels into its slice of F (y pointer + column offset, y_ld = planes * C_total), so the
+ * torch.cat of torchvision's _DenseLayer never copies.  Every consumer applies ITS OWN eval-mode uncentred BN + ReLU
+ * (batchnorm_uncentered.py:49-58) to the channels it reads:
+ * ------------------------------------------------------------------------------------------- */
+/* y [rows][planes * c] = relu?(x[:, :c] * alpha[c]) (x rows [rows][x_ld], plane pl at column pl * x_plane_stride);
+ * sq [rows] = sum y^2 (optional), maskbits [rows][c/32] = ReLU bits (optional, c % 32 == 0). */
+int bcosk_dense_bn_relu_fwd(const void* x, int64_t rows, int32_t c, int32_t planes, int32_t x_ld, int32_t x_plane_stride,
+                            const float* alpha, int32_t relu, void* y, float* sq, uint32_t* maskbits, int32_t dtype, void* stream);
+/* Its (explanation / plain) backward into the fp32 feature-gradient tensor G [rows][g_ld]:
+ * G[:, :c] = (accumulate ? G[:, :c] : 0) + g * alpha * mask bit;  g [rows][c] fp32 or one 16-bit plane. */
+int bcosk_dense_bn_relu_bwd(const void* g, int32_t g_f32, int64_t rows, int32_t c, const float* alpha, const uint32_t* maskbits,
+                            float* G, int32_t g_ld, int32_t accumulate, int32_t dtype, void* stream);
+/* out [rows][c] (one 16-bit plane) = G[:, col0 : col0 + c] * gain[rows][c] (optional, 16-bit or fp32) * scale: the A operand of
+ * the data gradient of the layer that produced those channels. */
+int bcosk_dense_slice_cast(const float* G, int32_t g_ld, int32_t col0, int64_t rows, int32_t c, const void* gain, int32_t gain_f32,
+                           float scale, void* out, int32_t dtype, void* stream);
+/* Strided device-to-device copy (cudaMemcpy2DAsync): a pooled tensor into the first channels of the next block's F. */
+int bcosk_copy_rows_2d(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes, int64_t width_bytes,
+                       int64_t rows, void* stream);
+
 /* Seed of a fused trunk's explanation pass from a gradient computed OUTSIDE the plan (CLIP encoders: the attention-pool head
  * bcos/modules/bcosattnpool.py:34-59 runs on the module-level path and autograd hands back d target / d trunk output):
  * g [nb, c, h, w] fp32 NCHW ->  out1[pix, pl*c + ch] = planes(g * seed_scale * mul1[pix, ch])  (mul1 = gain of the block's last conv)

@@ -719,6 +719,20 @@ def calibration_file_clip(batch: int = 8, seed: int = 100):
     print(f"[calib] wrote {path} ({os.path.getsize(path)/1e3:.0f} kB)")
 
 
+def calibration_file_densenet(arch: str = "densenet121", batch: int = 8, seed: int = 100):
+    """The same for DenseNet-121 (fused DenseNet plan, scripts/exp_densenet_plan.py)."""
+    sd = synth.synth_state_dict(O.densenet_state_shapes(arch), 0)
+    x6 = synth.to_bcos_input(synth.synth_images_u8(batch, 224, seed))
+    om = O.OracleDenseNet(arch, sd)
+    om.calibrate_bn(x6)
+    keys = sorted(k for k in sd if k.endswith("running_var"))
+    path = os.path.join(ROOT, "b-cosification_b200", "utils", "calib", f"{arch}_bnvar.npz")
+    np.savez_compressed(path, bn_keys=np.array(keys), bn_sizes=np.array([sd[k].numel() for k in keys], dtype=np.int64),
+                        bn_var=torch.cat([sd[k].flatten() for k in keys]).numpy(), weights_seed=np.int64(0),
+                        images_seed=np.int64(seed), batch=np.int64(batch))
+    print(f"[calib] wrote {path} ({os.path.getsize(path)/1e3:.0f} kB)")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="modules,resnet18,resnet50")
@@ -755,3 +769,5 @@ if __name__ == "__main__":
         calibration_file("resnet50")
     if "calib_clip" in which:
         calibration_file_clip()
+    if "calib_densenet" in which:
+        calibration_file_densenet()

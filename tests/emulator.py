@@ -149,6 +149,13 @@ def run_igemm(op: O.IgemmOp) -> None:
         if op.y_f32:
             y2[rows] = v
             stored = v
+        elif op.y_col or op.y.shape[-1] != op.y_planes * v.shape[-1]:
+            # the launch writes an n-column slice of a wider tensor (DenseNet block features): plane pl at pl * (ld / planes) + y_col
+            tmp = torch.zeros(M, op.y_planes * v.shape[-1], dtype=op.y.dtype)
+            stored = _split_store(tmp, v, op.y_planes)
+            pst, nn = op.y.shape[-1] // op.y_planes, v.shape[-1]
+            for pl in range(op.y_planes):
+                y2[rows, pl * pst + op.y_col: pl * pst + op.y_col + nn] = tmp[:, pl * nn:(pl + 1) * nn]
         else:
             tmp = torch.zeros(M, op.y.shape[-1], dtype=op.y.dtype)
             stored = _split_store(tmp, v, op.y_planes)
@@ -372,6 +379,45 @@ def run_pixel_sqsum(op: O.PixelSqsumOp) -> None:
     op.sq.view(-1)[:] = (_join(op.x, op.planes) ** 2).sum(-1).reshape(-1)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# fused DenseNet plan (engine/densenet.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_dense_bn_relu_fwd(op: O.DenseBnReluFwdOp) -> None:
+    pst = op.x.shape[-1] // op.planes
+    x = sum(op.x[..., pl * pst: pl * pst + op.c].float() for pl in range(op.planes))
+    t = x * op.alpha.float()
+    pos = (t > 0) if op.relu else torch.ones_like(t, dtype=torch.bool)
+    t = torch.where(pos, t, torch.zeros_like(t))
+    stored = _split_store(op.y, t, op.planes)
+    if op.sq is not None:
+        op.sq.view(-1)[:] = (stored ** 2).sum(-1).reshape(-1)
+    if op.maskbits is not None:
+        op.maskbits.copy_(_pack_mask(pos.reshape(-1, op.c)))
+
+
+def run_dense_bn_relu_bwd(op: O.DenseBnReluBwdOp) -> None:
+    v = op.g.float() * op.alpha.float()
+    if op.maskbits is not None:
+        v = v * _mask_bits(op.maskbits, op.c).reshape(v.shape)
+    if op.accumulate:
+        op.G[..., :op.c] += v
+    else:
+        op.G[..., :op.c] = v
+
+
+def run_dense_slice_cast(op: O.DenseSliceCastOp) -> None:
+    v = op.G[..., op.col0: op.col0 + op.c].float()
+    if op.gain is not None:
+        v = v * op.gain.float().reshape(v.shape)
+    op.out.copy_((v * op.scale).to(op.out.dtype))
+
+
+def run_copy_channels(op: O.CopyChannelsOp) -> None:
+    pst = op.dst.shape[-1] // op.planes
+    for pl in range(op.planes):
+        op.dst[..., pl * pst + op.dst_col: pl * pst + op.dst_col + op.c] = op.src[..., pl * op.c:(pl + 1) * op.c]
+
+
 _DISPATCH = {
     O.IgemmOp: run_igemm, O.InputPrepOp: run_input_prep, O.PatchNormOp: run_patch_norm, O.AvgPoolFwdOp: run_avgpool_fwd,
     O.AvgPoolBwdMulOp: run_avgpool_bwd_mul, O.GapLogitsOp: run_gap_logits, O.FcSeedOp: run_fc_seed,
@@ -380,6 +426,8 @@ _DISPATCH = {
     O.VitPatchifyOp: run_vit_patchify, O.VitContribMapOp: run_vit_contrib_map, O.VitLnFwdOp: run_vit_ln_fwd,
     O.VitLnBwdOp: run_vit_ln_bwd, O.VitGeluFwdOp: run_vit_gelu_fwd, O.VitAttentionOp: run_vit_attention,
     O.PixelSqsumOp: run_pixel_sqsum,
+    O.DenseBnReluFwdOp: run_dense_bn_relu_fwd, O.DenseBnReluBwdOp: run_dense_bn_relu_bwd, O.DenseSliceCastOp: run_dense_slice_cast,
+    O.CopyChannelsOp: run_copy_channels,
 }
 
 

@@ -28,6 +28,10 @@ OUTPUT_FIELDS = {
     O.VitGeluFwdOp: ["a", "sq", "gain"],
     O.VitAttentionOp: ["out"],
     O.PixelSqsumOp: ["sq"],
+    O.DenseBnReluFwdOp: ["y", "sq", "maskbits"],
+    O.DenseBnReluBwdOp: ["G"],
+    O.DenseSliceCastOp: ["out"],
+    O.CopyChannelsOp: ["dst"],
 }
 
 

@@ -150,3 +150,22 @@ def test_vit_plan_matches_oracle():
     m = OR.parity_metrics(plan.logits, plan.cmap, ref["logits"], ref["contribution_map"])
     print(m)
     assert m["argmax_equal"] and m["logit_rel_err"] < 1e-4 and m["map_cos_min"] > 0.9999, m
+
+
+def test_densenet_plan_matches_oracle():
+    """engine/densenet.py: block feature tensors written slice by slice (no concatenation copies), per-consumer BN + ReLU kernels,
+    fp32 feature-gradient accumulation in the explanation pass - launch list run by the emulator vs the oracle."""
+    from bcos_b200.engine import DenseNetPlan
+    arch = "densenet121"
+    sd = synth.synth_state_dict(OR.densenet_state_shapes(arch), 0)
+    x6 = synth.to_bcos_input(synth.synth_images_u8(2, 64, 1))
+    om = OR.OracleDenseNet(arch, sd)
+    om.calibrate_bn(x6)
+    ref = OR.explain_batched(om.forward, x6)
+    plan = DenseNetPlan(arch, sd, 2, planes=3, explain_planes=1, dtype="bf16", device="cpu", image_size=64, want_grad6=True)
+    plan.x_in.copy_(x6)
+    E.run(plan.fwd_ops)
+    E.run(plan.bwd_ops)
+    m = OR.parity_metrics(plan.logits, plan.cmap, ref["logits"], ref["contribution_map"])
+    print(m)
+    assert m["argmax_equal"] and m["logit_rel_err"] < 1e-4 and m["map_cos_min"] > 0.999, m
