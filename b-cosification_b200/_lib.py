@@ -312,6 +312,29 @@ def copy_rows_2d(dst_ptr, dst_pitch, src_ptr, src_pitch, width, rows) -> None:
                                     C.c_int64(rows), _stream()), "bcosk_copy_rows_2d")
 
 
+# ---- attention-pool head inside the fused CLIP plan (csrc/bcosk_head.cu)
+def sgemm_batched(trans_a, trans_b, m, n, k, a_ptr, lda, stride_a, b_ptr, ldb, stride_b, c_ptr, ldc, stride_c, batch, alpha) -> None:
+    check(load().bcosk_sgemm_batched(int(trans_a), int(trans_b), m, n, k, C.c_void_p(a_ptr), C.c_int64(lda), C.c_int64(stride_a),
+                                     C.c_void_p(b_ptr), C.c_int64(ldb), C.c_int64(stride_b), C.c_void_p(c_ptr), C.c_int64(ldc),
+                                     C.c_int64(stride_c), batch, C.c_float(alpha), _stream()), "bcosk_sgemm_batched")
+
+
+def head_tokens(x, nb, npix, c, planes, dtype, tokens) -> None:
+    check(load().bcosk_head_tokens(_p(x), nb, npix, c, planes, dtype, _p(tokens), _stream()), "bcosk_head_tokens")
+
+
+def row_softmax(s, rows, n) -> None:
+    check(load().bcosk_row_softmax(_p(s), C.c_int64(rows), n, _stream()), "bcosk_row_softmax")
+
+
+def seed_from_tokens(g_tokens, nb, npix, c, scale, mul1, out1, mask2, mul2, out2, planes, dtype) -> None:
+    import torch
+    check(load().bcosk_seed_from_tokens(_p(g_tokens), nb, npix, c, C.c_float(scale), _p(mul1),
+                                        int(mul1 is not None and mul1.dtype == torch.float32), _p(out1), _p(mask2), _p(mul2),
+                                        int(mul2 is not None and mul2.dtype == torch.float32), _p(out2), planes, dtype, _stream()),
+          "bcosk_seed_from_tokens")
+
+
 def seed_from_nchw(g, seed_scale, mul1, out1, mask2, mul2, out2, planes, dtype) -> None:
     import torch
     nb, c, h, w = g.shape

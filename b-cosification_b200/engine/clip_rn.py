@@ -11,10 +11,13 @@ pass is the chain of explain-dgrad launches whose epilogues multiply by the prod
 stem conv runs as a 2x2/1 conv over the 2x2 space-to-depth input (engine/pack.py stem_s2d_weight), so the input-prep and
 contribution-map kernels of the ResNet plan serve here too.
 
-The attention-pool head (50 tokens per image) stays on the module-level path
-(modules/bcosattnpool.py: packed q|k|v projection, frozen-probability attention kernel, output projection - all libbcosk
-kernels): `embed()` converts the trunk output to NCHW fp32 once, `explain_direction()` lets autograd hand back
-d target / d trunk-output, and `bcosk_seed_from_nchw` turns that into the last block's gradient tensors.
+The attention-pool head is part of the plan (`fused_head=True`, csrc/bcosk_head.cu): only the mean token's output is kept
+(bcosattnpool.py:52-58), so the projections commute with the pooling - scores s_j = (W_k,h^T q_h) . x_j, output
+o_h = W_v,h (sum_j p_j x_j): three token-equivalents of 2048 x 2048 projections per image instead of 150, done in fp32 by a
+strided-batched SGEMM; the explanation backward (q, k frozen: p constant) is three more SGEMM calls and `bcosk_seed_from_tokens`
+turns the token gradient into the last block's gradient tensors.  The only torch code left is the user's target function on the
+[batch, 1024] embedding.  `fused_head=False` keeps the module-level head (modules/bcosattnpool.py, q|k|v of all 50 tokens through
+the tcgen05 linear kernel + autograd) for comparison.
 """
 from __future__ import annotations
 
@@ -51,7 +54,7 @@ class CLIPResNetPlan(PlanBase):
                  dtype: Optional[str] = None, device="cuda", image_size: int = 224, layers=(3, 4, 6, 3), width: int = 64,
                  heads: int = 32, explain: bool = True, b: float = 2.0, bn_eps: float = 1e-5, mean=CLIP_MEAN_ADDINVERSE,
                  std=CLIP_STD_ADDINVERSE, seed_scale: Optional[float] = None, input_u8: bool = False,
-                 explain_planes: Optional[int] = None, want_grad6: bool = False):
+                 explain_planes: Optional[int] = None, want_grad6: bool = False, fused_head: bool = True):
         cfg = resolve_precision(mode, planes, dtype, explain_planes, seed_scale)
         self.precision = cfg
         super().__init__(batch, planes=cfg["planes"], dtype=cfg["dtype"], device=device, explain=explain, b=b, bn_eps=bn_eps,
@@ -62,6 +65,7 @@ class CLIPResNetPlan(PlanBase):
         self.seed_scale = float(cfg["seed_scale"])
         self.size, self.input_u8 = image_size, input_u8
         self.stem_cp = 32
+        self.fused_head = fused_head
         self.blocks: List[ClipBlock] = []
         self._head = None
         self._build_forward()
@@ -119,8 +123,42 @@ class CLIPResNetPlan(PlanBase):
                 inpl = planes_ * 4
         self.trunk_out = x
         self.c_out = x.c
-        self.feat = self._empty(nb, x.c, x.hw[0], x.hw[1], dtype=torch.float32)      # NCHW fp32 for the attention-pool head
-        self.fwd_ops.append(O.TrunkOutOp("trunk_out", x.t, nb, x.c, x.hw[0], x.hw[1], pl, self.dt_code, self.feat))
+        if self.fused_head:
+            self._build_head_forward()
+        else:
+            self.feat = self._empty(nb, x.c, x.hw[0], x.hw[1], dtype=torch.float32)      # NCHW fp32 for the module-level head
+            self.fwd_ops.append(O.TrunkOutOp("trunk_out", x.t, nb, x.c, x.hw[0], x.hw[1], pl, self.dt_code, self.feat))
+
+    def _build_head_forward(self) -> None:
+        """bcosattnpool.py:34-59 with the projections commuted past the pooling (module docstring); fp32 SGEMM launches."""
+        nb, c, H = self.nb, self.c_out, self.heads
+        dh = c // H
+        T = self.trunk_out.hw[0] * self.trunk_out.hw[1] + 1
+        f32 = torch.float32
+        sd = self.sd
+        self.wq, self.wk, self.wv = (self._dev(sd[f"model.attnpool.{n}.weight"]) for n in ("q_proj", "k_proj", "v_proj"))
+        self.wc = self._dev(sd["model.attnpool.c_proj.linear.weight"])
+        od = self.wc.shape[0]
+        self.tokens = self._empty(nb, T, c, dtype=f32)
+        self.h_q = self._empty(nb, c, dtype=f32)
+        self.h_qt = self._empty(nb, H, c, dtype=f32)
+        self.h_p = self._empty(nb, H, T, dtype=f32)
+        self.h_xbar = self._empty(nb, H, c, dtype=f32)
+        self.h_o = self._empty(nb, c, dtype=f32)
+        self.emb = self._empty(nb, od, dtype=f32)
+        ops = self.fwd_ops
+        ops.append(O.HeadTokensOp("attnpool.tokens", self.trunk_out.t, c, self.planes, self.dt_code, self.tokens))
+        # q = W_q x_0 / sqrt(dh)  (x_0 = mean token)
+        ops.append(O.SgemmOp("attnpool.q", False, True, nb, c, c, self.tokens, 0, T * c, 0, self.wq, 0, c, 0, self.h_q, 0, c, 0, 1, dh ** -0.5))
+        # qt_h = W_k,h^T q_h
+        ops.append(O.SgemmOp("attnpool.qk", False, False, nb, c, dh, self.h_q, 0, c, dh, self.wk, 0, c, dh * c, self.h_qt, 0, H * c, c, H))
+        # s[b, h, j] = qt[b, h] . x[b, j];  p = softmax_j
+        ops.append(O.SgemmOp("attnpool.scores", False, True, H, T, c, self.h_qt, 0, c, H * c, self.tokens, 0, c, T * c, self.h_p, 0, T, H * T, nb))
+        ops.append(O.RowSoftmaxOp("attnpool.softmax", self.h_p))
+        # xbar[b, h] = sum_j p[b, h, j] x[b, j];  o_h = W_v,h xbar_h;  emb = W_c o
+        ops.append(O.SgemmOp("attnpool.pool", False, False, H, c, T, self.h_p, 0, T, H * T, self.tokens, 0, c, T * c, self.h_xbar, 0, c, H * c, nb))
+        ops.append(O.SgemmOp("attnpool.v", False, True, nb, dh, c, self.h_xbar, 0, H * c, c, self.wv, 0, c, dh * c, self.h_o, 0, c, dh, H))
+        ops.append(O.SgemmOp("attnpool.c_proj", False, True, nb, od, c, self.h_o, 0, c, 0, self.wc, 0, c, 0, self.emb, 0, od, 0, 1))
 
     # ------------------------------------------------------------------ explanation pass
     def _build_explain(self, want_grad6: bool) -> None:
@@ -136,11 +174,29 @@ class CLIPResNetPlan(PlanBase):
         for r in self.stem:
             self._alloc_ghat(r)
         last = self.blocks[-1]
-        # ---- seed: d target / d trunk output (NCHW fp32, computed by the head through autograd) -> last block's gradients
-        self.g_feat = self._zeros(nb, self.c_out, last.y.hw[0], last.y.hw[1], dtype=torch.float32)
         # (the seed scale that keeps fp16 gradients in range is applied to the target itself, in front of the head's backward)
-        self.bwd_ops.append(O.SeedFromNchwOp("head.seed", self.g_feat, 1.0, last.convs[-1].gain, last.convs[-1].ghat,
-                                           last.mask, None if last.ds is None else last.ds.gain, last.side, pl, self.dt_code))
+        if self.fused_head:
+            # ---- head backward in explanation mode (q, k frozen: p is a constant): g_o = W_c^T g_emb, g_xbar_h = W_v,h^T g_o,h,
+            #      g_x[b, j] = sum_h p[b, h, j] g_xbar[b, h]; the mean token's share is spread over the pixels by the seed kernel
+            c, H = self.c_out, self.heads
+            dh, T, od = c // H, self.tokens.shape[1], self.wc.shape[0]
+            f32 = torch.float32
+            self.g_emb = self._zeros(nb, od, dtype=f32)
+            self.g_o = self._empty(nb, c, dtype=f32)
+            self.g_xbar = self._empty(nb, H, c, dtype=f32)
+            self.g_tokens = self._empty(nb, T, c, dtype=f32)
+            ops = self.bwd_ops
+            ops.append(O.SgemmOp("attnpool.c_proj.bwd", False, False, nb, c, od, self.g_emb, 0, od, 0, self.wc, 0, c, 0, self.g_o, 0, c, 0, 1))
+            ops.append(O.SgemmOp("attnpool.v.bwd", False, False, nb, c, dh, self.g_o, 0, c, dh, self.wv, 0, c, dh * c, self.g_xbar, 0, H * c, c, H))
+            ops.append(O.SgemmOp("attnpool.pool.bwd", True, False, T, c, H, self.h_p, 0, T, H * T, self.g_xbar, 0, c, H * c, self.g_tokens, 0, c,
+                                 T * c, nb))
+            ops.append(O.SeedFromTokensOp("head.seed", self.g_tokens, 1.0, last.convs[-1].gain, last.convs[-1].ghat, last.mask,
+                                          None if last.ds is None else last.ds.gain, last.side, pl, self.dt_code))
+        else:
+            # ---- seed: d target / d trunk output (NCHW fp32, computed by the module-level head through autograd)
+            self.g_feat = self._zeros(nb, self.c_out, last.y.hw[0], last.y.hw[1], dtype=torch.float32)
+            self.bwd_ops.append(O.SeedFromNchwOp("head.seed", self.g_feat, 1.0, last.convs[-1].gain, last.convs[-1].ghat,
+                                               last.mask, None if last.ds is None else last.ds.gain, last.side, pl, self.dt_code))
         self.g_pool = self._zeros(nb, self.pool_out.hw[0], self.pool_out.hw[1], pl * self.pool_out.c)
         for bi in range(len(self.blocks) - 1, -1, -1):
             blk = self.blocks[bi]
@@ -212,6 +268,8 @@ class CLIPResNetPlan(PlanBase):
         if x6 is not None:
             self.load_input(x6)
         self.replay_forward()
+        if self.fused_head:
+            return self.emb
         from ..modules import _runtime as R
         with torch.no_grad(), R.precision(self.planes, self.precision["dtype"]):
             return self.head()(self.feat)
@@ -224,6 +282,16 @@ class CLIPResNetPlan(PlanBase):
         if x6 is not None:
             self.load_input(x6)
         self.replay_forward()
+        if self.fused_head:
+            emb = self.emb.detach().clone().requires_grad_(True)
+            with torch.enable_grad():
+                (g,) = torch.autograd.grad(target_fn(emb).sum() * self.seed_scale, [emb])     # the user's target on [batch, dim]
+            self.g_emb.copy_(g)
+            self.replay_explain()
+            out = {"embedding": emb.detach(), "contribution_map": self.cmap}
+            if self.grad6 is not None:
+                out["dynamic_linear_weights"] = self.grad6
+            return out
         head = self.head()
         feat = self.feat.detach().requires_grad_(True)
         head.set_explanation_mode(True)

@@ -620,6 +620,80 @@ class CopyChannelsOp:
                            self.src.data_ptr() + pl * self.c * es, ld_s * es, self.c * es, rows)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Attention-pool head inside the fused CLIP plan (kernels: csrc/bcosk_head.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class SgemmOp:
+    """C[i] = alpha * op(A[i]) op(B[i]), i < batch: fp32 row-major operands addressed as (tensor, element offset, row pitch, batch stride)."""
+    name: str
+    trans_a: bool
+    trans_b: bool
+    m: int
+    n: int
+    k: int
+    a: Tensor
+    a_off: int
+    lda: int
+    stride_a: int
+    b: Tensor
+    b_off: int
+    ldb: int
+    stride_b: int
+    c: Tensor
+    c_off: int
+    ldc: int
+    stride_c: int
+    batch: int
+    alpha: float = 1.0
+
+    def run(self) -> None:
+        L.sgemm_batched(self.trans_a, self.trans_b, self.m, self.n, self.k, self.a.data_ptr() + 4 * self.a_off, self.lda, self.stride_a,
+                        self.b.data_ptr() + 4 * self.b_off, self.ldb, self.stride_b, self.c.data_ptr() + 4 * self.c_off, self.ldc,
+                        self.stride_c, self.batch, self.alpha)
+
+
+@dataclass
+class HeadTokensOp:
+    name: str
+    x: Tensor            # [nb, h, w, planes * c]
+    c: int
+    planes: int
+    dtype: int
+    tokens: Tensor       # [nb, h*w + 1, c] fp32
+
+    def run(self) -> None:
+        nb, h, w, _ = self.x.shape
+        L.head_tokens(self.x, nb, h * w, self.c, self.planes, self.dtype, self.tokens)
+
+
+@dataclass
+class RowSoftmaxOp:
+    name: str
+    s: Tensor            # [..., n] fp32, in place
+
+    def run(self) -> None:
+        L.row_softmax(self.s, self.s.numel() // self.s.shape[-1], self.s.shape[-1])
+
+
+@dataclass
+class SeedFromTokensOp:
+    name: str
+    g_tokens: Tensor     # [nb, npix + 1, c] fp32
+    scale: float
+    mul1: Optional[Tensor]
+    out1: Tensor         # [nb, h, w, planes * c]
+    mask2: Optional[Tensor]
+    mul2: Optional[Tensor]
+    out2: Optional[Tensor]
+    planes: int
+    dtype: int
+
+    def run(self) -> None:
+        nb, t, c = self.g_tokens.shape
+        L.seed_from_tokens(self.g_tokens, nb, t - 1, c, self.scale, self.mul1, self.out1, self.mask2, self.mul2, self.out2, self.planes, self.dtype)
+
+
 def run_ops(ops) -> None:
     for o in ops:
         o.run()

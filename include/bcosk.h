@@ -467,6 +467,28 @@ int bcosk_dense_slice_cast(const float* G, int32_t g_ld, int32_t col0, int64_t r
 int bcosk_copy_rows_2d(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes, int64_t width_bytes,
                        int64_t rows, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Attention-pool head of the CLIP ResNet encoders inside the fused plan (BcosAttentionPool2d.forward bcosattnpool.py:34-59, pooled
+ * mode; csrc/bcosk_head.cu).  Only the mean token's output is kept, so projections commute with the pooling: scores
+ * s_j = (W_k,h^T q_h) . x_j, output o_h = W_v,h (sum_j p_j x_j) - three token-equivalents of projections per image instead of 150.
+ * fp32 on the CUDA cores (small: 32 GFLOP per 512 images).
+ * ------------------------------------------------------------------------------------------- */
+/* C[i] (m x n, row pitch ldc) = alpha * op(A[i]) (m x k) * op(B[i]) (k x n) for i < batch; row-major, operand i at base + i * stride;
+ * trans_a: A is stored k x m; trans_b: B is stored n x k. */
+int bcosk_sgemm_batched(int32_t trans_a, int32_t trans_b, int32_t m, int32_t n, int32_t k, const float* a, int64_t lda, int64_t stride_a,
+                        const float* b, int64_t ldb, int64_t stride_b, float* c, int64_t ldc, int64_t stride_c, int32_t batch, float alpha,
+                        void* stream);
+/* tokens [nb][npix + 1][c] fp32 from the trunk output planes x [nb][npix][planes * c]: token 0 = mean over the pixels
+ * (bcosattnpool.py:37-38: cat([x.mean(0), x])), token j + 1 = pixel j. */
+int bcosk_head_tokens(const void* x, int32_t nb, int32_t npix, int32_t c, int32_t planes, int32_t dtype, float* tokens, void* stream);
+/* in-place softmax over rows of n fp32 values */
+int bcosk_row_softmax(float* s, int64_t rows, int32_t n, void* stream);
+/* Gradient wrt the tokens g_tokens [nb][npix + 1][c] fp32 -> the last trunk block's gradient tensors (see bcosk_seed_from_nchw):
+ * g[pix] = g_tokens[pix + 1] + g_tokens[0] / npix;  out1 = planes(g * scale * mul1), out2 = planes(g * scale [* mul2]) under mask2. */
+int bcosk_seed_from_tokens(const float* g_tokens, int32_t nb, int32_t npix, int32_t c, float scale, const void* mul1, int32_t mul1_f32,
+                           void* out1, const uint32_t* mask2, const void* mul2, int32_t mul2_f32, void* out2, int32_t planes,
+                           int32_t dtype, void* stream);
+
 /* Seed of a fused trunk's explanation pass from a gradient computed OUTSIDE the plan (CLIP encoders: the attention-pool head
  * bcos/modules/bcosattnpool.py:34-59 runs on the module-level path and autograd hands back d target / d trunk output):
  * g [nb, c, h, w] fp32 NCHW ->  out1[pix, pl*c + ch] = planes(g * seed_scale * mul1[pix, ch])  (mul1 = gain of the block's last conv)

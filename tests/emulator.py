@@ -418,6 +418,44 @@ def run_copy_channels(op: O.CopyChannelsOp) -> None:
         op.dst[..., pl * pst + op.dst_col: pl * pst + op.dst_col + op.c] = op.src[..., pl * op.c:(pl + 1) * op.c]
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# attention-pool head inside the fused CLIP plan
+# ---------------------------------------------------------------------------------------------------------------------
+def run_sgemm(op: O.SgemmOp) -> None:
+    def view(t, off, rows, cols, ld, stride, trans):
+        r, c = (cols, rows) if trans else (rows, cols)             # stored shape
+        v = torch.as_strided(t.reshape(-1), (op.batch, r, c), (stride, ld, 1), off)
+        return v.transpose(1, 2) if trans else v
+    a = view(op.a, op.a_off, op.m, op.k, op.lda, op.stride_a, op.trans_a)
+    b = view(op.b, op.b_off, op.k, op.n, op.ldb, op.stride_b, op.trans_b)
+    c = torch.as_strided(op.c.reshape(-1), (op.batch, op.m, op.n), (op.stride_c, op.ldc, 1), op.c_off)
+    c.copy_(op.alpha * torch.matmul(a, b))
+
+
+def run_head_tokens(op: O.HeadTokensOp) -> None:
+    nb, h, w, _ = op.x.shape
+    x = _join(op.x, op.planes).reshape(nb, h * w, op.c)
+    op.tokens[:, 1:] = x
+    op.tokens[:, 0] = x.sum(1) / (h * w)
+
+
+def run_row_softmax(op: O.RowSoftmaxOp) -> None:
+    op.s.copy_(torch.softmax(op.s, dim=-1))
+
+
+def run_seed_from_tokens(op: O.SeedFromTokensOp) -> None:
+    nb, t, c = op.g_tokens.shape
+    g = ((op.g_tokens[:, 1:] + op.g_tokens[:, :1] / (t - 1)) * op.scale).reshape(nb * (t - 1), c)
+    if op.out1 is not None:
+        v = g * op.mul1.float().view(-1, c) if op.mul1 is not None else g
+        _split_store(op.out1, v.view(op.out1.shape[0], op.out1.shape[1], op.out1.shape[2], c), op.planes)
+    if op.out2 is not None:
+        o = g * op.mul2.float().view(-1, c) if op.mul2 is not None else g
+        if op.mask2 is not None:
+            o = o * _mask_bits(op.mask2, c)
+        _split_store(op.out2, o.view(op.out2.shape[0], op.out2.shape[1], op.out2.shape[2], c), op.planes)
+
+
 _DISPATCH = {
     O.IgemmOp: run_igemm, O.InputPrepOp: run_input_prep, O.PatchNormOp: run_patch_norm, O.AvgPoolFwdOp: run_avgpool_fwd,
     O.AvgPoolBwdMulOp: run_avgpool_bwd_mul, O.GapLogitsOp: run_gap_logits, O.FcSeedOp: run_fc_seed,
@@ -428,6 +466,7 @@ _DISPATCH = {
     O.PixelSqsumOp: run_pixel_sqsum,
     O.DenseBnReluFwdOp: run_dense_bn_relu_fwd, O.DenseBnReluBwdOp: run_dense_bn_relu_bwd, O.DenseSliceCastOp: run_dense_slice_cast,
     O.CopyChannelsOp: run_copy_channels,
+    O.SgemmOp: run_sgemm, O.HeadTokensOp: run_head_tokens, O.RowSoftmaxOp: run_row_softmax, O.SeedFromTokensOp: run_seed_from_tokens,
 }
 
 

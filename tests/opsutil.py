@@ -32,6 +32,10 @@ OUTPUT_FIELDS = {
     O.DenseBnReluBwdOp: ["G"],
     O.DenseSliceCastOp: ["out"],
     O.CopyChannelsOp: ["dst"],
+    O.SgemmOp: ["c"],
+    O.HeadTokensOp: ["tokens"],
+    O.RowSoftmaxOp: ["s"],
+    O.SeedFromTokensOp: ["out1", "out2"],
 }
 
 

@@ -63,6 +63,56 @@ def test_seed_from_nchw_kernel(bcosk_lib):
         print(U.compare(op, dev, 1e-3 if planes == 1 else 2e-5, ["out1", "out2"]))
 
 
+def test_head_kernels(bcosk_lib):
+    """csrc/bcosk_head.cu: strided-batched SGEMM (all four transpose forms, ragged sizes, per-head and per-image batching), the token
+    gather with the mean token, the row softmax and the token-gradient seed, each against its torch restatement."""
+    from bcos_b200 import _lib as L
+    g = torch.Generator().manual_seed(23)
+
+    def chk(op, tol16=2e-3, tol32=2e-5):
+        dev = U.to_device(op, "cuda", {})
+        E.run([op])
+        dev.run()
+        torch.cuda.synchronize()
+        return {n: U.compare(op, dev, tol32 if getattr(op, n).dtype == torch.float32 else tol16, [n])[n]
+                for n in U.OUTPUT_FIELDS[type(op)] if getattr(op, n) is not None}
+
+    m, n, k, bt = 70, 45, 37, 3
+    for ta in (False, True):
+        for tb in (False, True):
+            a = torch.randn(bt, *((k, m) if ta else (m, k)), generator=g)
+            b = torch.randn(bt, *((n, k) if tb else (k, n)), generator=g)
+            op = O.SgemmOp(f"sgemm_{int(ta)}{int(tb)}", ta, tb, m, n, k, a, 0, a.shape[-1], a[0].numel(), b, 0, b.shape[-1], b[0].numel(),
+                           torch.zeros(bt, m, n), 0, n, m * n, bt, 0.5)
+            print(op.name, chk(op))
+    # per-head batching with strides inside one matrix (q[:, h-block] x W[h-block rows, :] -> out[:, h, :])
+    B_, H, dh, c = 5, 4, 16, 64
+    q, w = torch.randn(B_, c, generator=g), torch.randn(c, c, generator=g)
+    op = O.SgemmOp("per_head", False, False, B_, c, dh, q, 0, c, dh, w, 0, c, dh * c, torch.zeros(B_, H, c), 0, H * c, c, H)
+    print(op.name, chk(op))
+    x = torch.zeros(3, 4, 4, 2 * 64, dtype=torch.float16)
+    E._split_store(x, torch.randn(3, 4, 4, 64, generator=g), 2)
+    print("tokens", chk(O.HeadTokensOp("tokens", x, 64, 2, L.DTYPE_CODE["fp16"], torch.zeros(3, 17, 64))))
+    print("softmax", chk(O.RowSoftmaxOp("softmax", torch.randn(6, 8, 50, generator=g) * 3)))
+    mask = torch.randint(-2**31, 2**31 - 1, (3 * 16, 2), generator=g, dtype=torch.int64).to(torch.int32)
+    op = O.SeedFromTokensOp("seed", torch.randn(3, 17, 64, generator=g), 4096.0, torch.rand(48, 64, generator=g).half(),
+                            torch.zeros(3, 4, 4, 64, dtype=torch.float16), mask, None, torch.zeros(3, 4, 4, 64, dtype=torch.float16), 1,
+                            L.DTYPE_CODE["fp16"])
+    print("seed_from_tokens", chk(op))
+
+
+def test_clip_rn50_module_level_head_path(bcosk_lib, golden_dir):
+    """fused_head=False: trunk as fused launches, attention pool on the module-level kernels through autograd (the hand-over path)."""
+    gold, sd = _golden(golden_dir)
+    x6 = synth.to_bcos_input(gold["images_u8"]).cuda()
+    plan = CLIPResNetPlan(sd, 2, mode="parity", device="cuda", fused_head=False)
+    out = plan.explain_direction(x6, OR.clip_seed_direction(1024, int(gold["seed"])))
+    torch.cuda.synchronize()
+    m = _metrics(out, gold)
+    print("fused trunk + module-level head vs reference golden:", m)
+    assert m["emb_rel"] <= 2e-3 and m["cos"] >= 0.999 and min(m["mar"], m["mar64"]) <= 1e-3, m
+
+
 @pytest.mark.parametrize("mode", ["parity", "throughput_fp16"])
 def test_clip_rn50_fused_plan_matches_golden(bcosk_lib, golden_dir, mode):
     gold, sd = _golden(golden_dir)

@@ -115,7 +115,20 @@ def test_clip_rn_trunk_plan_matches_oracle():
     om.calibrate_bn(x6)
     tvec = OR.clip_seed_direction(64, 0)
     ref = OR.explain_cosine(om.forward, x6, tvec)
-    plan = CLIPResNetPlan(sd, 2, planes=3, device="cpu", image_size=64, layers=(1, 2, 1, 1), width=16, heads=4)
+    # (a) the whole plan incl. the fused attention-pool head (pool-before-project SGEMM chain) and its explanation backward
+    full = CLIPResNetPlan(sd, 2, planes=3, device="cpu", image_size=64, layers=(1, 2, 1, 1), width=16, heads=4)
+    full.x_in.copy_(x6)
+    E.run(full.fwd_ops)
+    assert ((full.emb - ref["embedding"]).abs().max() / ref["embedding"].abs().max()).item() < 1e-4
+    e = full.emb.clone().requires_grad_(True)
+    with torch.enable_grad():
+        (ge,) = torch.autograd.grad(torch.nn.functional.cosine_similarity(e, tvec[None], dim=1).sum() * full.seed_scale, [e])
+    full.g_emb.copy_(ge)
+    E.run(full.bwd_ops)
+    assert torch.nn.functional.cosine_similarity(full.cmap.flatten(1), ref["contribution_map"].flatten(1)).min().item() > 0.99999
+    assert ((full.cmap - ref["contribution_map"]).abs().max() / ref["contribution_map"].abs().max()).item() < 1e-3
+    # (b) the trunk with an external head (the oracle's attention pool + autograd): the module-level hand-over path
+    plan = CLIPResNetPlan(sd, 2, planes=3, device="cpu", image_size=64, layers=(1, 2, 1, 1), width=16, heads=4, fused_head=False)
     plan.x_in.copy_(x6)
     E.run(plan.fwd_ops)
     feat_ref = om.trunk(x6)
