@@ -335,6 +335,12 @@ def seed_from_tokens(g_tokens, nb, npix, c, scale, mul1, out1, mask2, mul2, out2
           "bcosk_seed_from_tokens")
 
 
+def stem_im2col_u8(x, k, stride, pad, mean6, inv_std6, a_scale, out, kp, inv_norm, dtype) -> None:
+    nb, _, h, w = x.shape
+    check(load().bcosk_stem_im2col_u8(_p(x), nb, h, w, k, stride, pad, _f6(mean6), _f6(inv_std6), C.c_float(a_scale), _p(out), kp, _p(inv_norm),
+                                      dtype, _stream()), "bcosk_stem_im2col_u8")
+
+
 def seed_from_nchw(g, seed_scale, mul1, out1, mask2, mul2, out2, planes, dtype) -> None:
     import torch
     nb, c, h, w = g.shape

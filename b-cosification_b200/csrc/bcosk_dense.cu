@@ -148,9 +148,128 @@ __global__ void dense_slice_cast_kernel(const float* __restrict__ G, int g_ld, i
   *reinterpret_cast<uint4*>(out + row * c + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stem patch matrix for the contract-mode plans with uint8 input (engine/base.py _stem_fwd_im2col): the k x k / stride conv over the
+// 6-channel normalised [x, 1-x] input is LINEAR in the raw byte v of every colour: xn_c = v/255/std_c - mean_c/std_c and
+// xn_{c+3} = -v/255/std_{c+3} + (1 - mean_{c+3})/std_{c+3}.  So the conv equals a GEMM over rows of (v_R, v_G, v_B, 1) per tap with
+// folded weights - the bytes are EXACT in one 16-bit plane (only the weights need precision planes: 2 plane products instead of 3),
+// the "1" column carries the constant term exactly where the tap lies inside the image (zero padding applies to xn, not to v), and
+// the 49-tap window is gathered once here instead of 16 x 3 times by the implicit GEMM (the stem was L2-bandwidth bound).
+//   out  [pixels][kp]: column tap*4 + {0,1,2} = v * a_scale, tap*4 + 3 = 1 for in-image taps, zeros elsewhere (kp % 64 == 0)
+//   inv_norm [pixels] = 1 / sqrt(sum over in-image taps and the 6 channels of xn^2 + 1e-6)      (calc_patch_norms bcosconv2d.py:196-231)
+// One warp per output pixel, lane = 16-byte vector (two taps).
+// ------------------------------------------------------------------------------------------------
+struct SF6 { float v[6]; };
+
+// One CTA per (image, output row): the k input rows of the three colour planes are staged in shared memory (bytes) together with
+// the per-pixel sum of the six normalised channels squared; every thread then assembles 16-byte output vectors (two taps) from
+// shared memory - the 512-byte rows of the patch matrix leave fully coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_im2col_u8_kernel(const uint8_t* __restrict__ x, int H, int W, int k, int stride, int pad, int op, int oq, SF6 mean, SF6 istd,
+                      float a_scale, T* __restrict__ out, int kp, float* __restrict__ inv_norm) {
+  extern __shared__ uint8_t sm_raw[];
+  const int img = blockIdx.y, p = blockIdx.x;
+  uint8_t* sb = sm_raw;                                              // [k][3][W] bytes
+  float* sq = reinterpret_cast<float*>(sm_raw + ((k * 3 * W + 15) / 16) * 16);   // [k][W] sum_c xn^2 (0 for rows outside the image)
+  const uint8_t* xi = x + (size_t)img * 3 * H * W;
+  const int iy0 = p * stride - pad;
+  for (int e = threadIdx.x; e < k * 3 * W; e += blockDim.x) {
+    const int dy = e / (3 * W), r = e - dy * 3 * W, c = r / W, ix = r - c * W;
+    const int iy = iy0 + dy;
+    sb[e] = (iy >= 0 && iy < H) ? xi[((size_t)c * H + iy) * W + ix] : (uint8_t)0;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < k * W; e += blockDim.x) {
+    const int dy = e / W, ix = e - dy * W;
+    const int iy = iy0 + dy;
+    float acc = 0.f;
+    if (iy >= 0 && iy < H) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float xv = (float)sb[(dy * 3 + c) * W + ix] * (1.0f / 255.0f);
+        const float a = (xv - mean.v[c]) * istd.v[c], b = ((1.0f - xv) - mean.v[c + 3]) * istd.v[c + 3];
+        acc = fmaf(a, a, acc);
+        acc = fmaf(b, b, acc);
+      }
+    }
+    sq[e] = acc;
+  }
+  __syncthreads();
+  const int nvec = kp >> 3, ntap = k * k;
+  const long long row0 = ((long long)img * op + p) * oq;
+  {
+    // blockDim % nvec == 0: every thread owns ONE vector position (two taps) for all the pixels it writes - the tap arithmetic
+    // (runtime divisions) is done once per thread, not once per vector
+    const int v0 = threadIdx.x % nvec, qstep = blockDim.x / nvec;
+    int off[2][3], dxs[2];
+    bool live[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int t = v0 * 2 + h;
+      const int dy = t / k, dx = t - dy * k;
+      const int iy = iy0 + dy;
+      live[h] = t < ntap && iy >= 0 && iy < H;
+      dxs[h] = dx - pad;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) off[h][c] = (dy * 3 + c) * W;
+    }
+    for (int q = threadIdx.x / nvec; q < oq; q += qstep) {
+      float f[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ix = q * stride + dxs[h];
+        float r = 0.f, g = 0.f, b = 0.f, one = 0.f;
+        if (live[h] && ix >= 0 && ix < W) {
+          r = (float)sb[off[h][0] + ix]; g = (float)sb[off[h][1] + ix]; b = (float)sb[off[h][2] + ix];
+          one = 1.f;
+        }
+        f[h * 4 + 0] = r * a_scale; f[h * 4 + 1] = g * a_scale; f[h * 4 + 2] = b * a_scale; f[h * 4 + 3] = one;
+      }
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = Cvt<T>::pack2(f[2 * i], f[2 * i + 1]);
+      *reinterpret_cast<uint4*>(out + (row0 + q) * (long long)kp + v0 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  if (inv_norm != nullptr) {
+    for (int q = threadIdx.x; q < oq; q += blockDim.x) {
+      float acc = 0.f;
+      for (int dy = 0; dy < k; ++dy)
+        for (int dx = 0; dx < k; ++dx) {
+          const int ix = q * stride - pad + dx;
+          if (ix >= 0 && ix < W) acc += sq[dy * W + ix];
+        }
+      inv_norm[row0 + q] = 1.0f / sqrtf(acc + 1e-6f);
+    }
+  }
+}
+
 }  // namespace bcosk
 
 using namespace bcosk;
+
+extern "C" int bcosk_stem_im2col_u8(const uint8_t* x, int32_t nb, int32_t h, int32_t w, int32_t k, int32_t stride, int32_t pad, const float* mean6,
+                                    const float* inv_std6, float a_scale, void* out, int32_t kp, float* inv_norm, int32_t dtype, void* stream) {
+  if (!x || !out || !mean6 || !inv_std6 || nb < 1 || k < 1 || stride < 1 || kp % 64 || kp < k * k * 4 || 256 % (kp / 8) != 0)
+    return set_error(BCOSK_EINVAL, "stem_im2col_u8: bad argument (kp must be 64, 128 or 256 and >= 4 k^2)");
+  const int op = (h + 2 * pad - k) / stride + 1, oq = (w + 2 * pad - k) / stride + 1;
+  if (nb > 65535) return set_error(BCOSK_EUNSUPPORTED, "stem_im2col_u8: batch too large for the grid");
+  SF6 m, s;
+  for (int i = 0; i < 6; ++i) { m.v[i] = mean6[i]; s.v[i] = inv_std6[i]; }
+  const size_t smem = (size_t)((k * 3 * w + 15) / 16) * 16 + (size_t)k * w * sizeof(float);
+  if (smem > 48 * 1024) return set_error(BCOSK_EUNSUPPORTED, "stem_im2col_u8: image too wide for the shared-memory rows");
+  dim3 grid(op, nb);
+  if (dtype == BCOSK_DTYPE_BF16)
+    stem_im2col_u8_kernel<__nv_bfloat16><<<grid, 256, smem, SD(stream)>>>(x, h, w, k, stride, pad, op, oq, m, s, a_scale, reinterpret_cast<__nv_bfloat16*>(out), kp, inv_norm);
+  else if (dtype == BCOSK_DTYPE_F16)
+    stem_im2col_u8_kernel<__half><<<grid, 256, smem, SD(stream)>>>(x, h, w, k, stride, pad, op, oq, m, s, a_scale, reinterpret_cast<__half*>(out), kp, inv_norm);
+  else
+    return set_error(BCOSK_EINVAL, "stem_im2col_u8: dtype");
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
 
 extern "C" int bcosk_dense_bn_relu_fwd(const void* x, int64_t rows, int32_t c, int32_t planes, int32_t x_ld, int32_t x_plane_stride,
                                        const float* alpha, int32_t relu, void* y, float* sq, uint32_t* maskbits, int32_t dtype, void* stream) {

@@ -270,6 +270,53 @@ class PlanBase:
         rec.algo_flops = self.fwd_ops[-1].algo_flops
         return Act(y, oy, sq, parts), rec
 
+    # ------------------------------------------------------------------ stem of the contract-mode plans with uint8 input
+    stem_im2col = True     # parity-mode plans with uint8 input: stem as a GEMM over an exact byte patch matrix (see _stem_fwd_im2col)
+
+    def _stem_fwd_im2col(self, name: str, x_u8: Tensor, w: Tensor, w_s2d: Tensor, k: int, stride: int, pad: int, *, bn: Optional[str],
+                         mean6, inv_std6, s2d_pad: Tuple[int, int], stem_cp: int, want_sq: bool = False) -> Tuple[Act, ConvRec]:
+        """The k x k / stride stem conv + BN + ReLU of a plan whose input is uint8 RGB, in the contract (precision-plane) modes.
+
+        The conv over the normalised [x, 1-x] input is linear in the raw bytes, so it runs as ONE 1x1 launch over the patch matrix
+        `bcosk_stem_im2col_u8` writes (rows of (v_R, v_G, v_B, 1) per tap): the bytes are exact in one 16-bit plane, only the
+        (folded) weights carry precision planes - `planes` plane products instead of 3 / 6, K = 256 per product instead of 512 - and
+        the window is gathered once (the implicit-GEMM stem re-read its input 16 taps x 3 segments from L2: 1.95 of the 22.2 ms of
+        a ResNet-50 step).  The ConvRec describes the SAME convolution in its space-to-depth form (`w_s2d`), which is what the
+        explanation pass differentiates (its data gradient is unchanged)."""
+        nb = self.nb
+        _, _, S, _ = x_u8.shape
+        o = w.shape[0]
+        oh = (S + 2 * pad - k) // stride + 1
+        M = nb * oh * oh
+        kp = (4 * k * k + 63) // 64 * 64
+        a_scale = 2.0 ** -6                       # bytes 0..255 -> 0..3.98 (exact): keeps the folded weights at the magnitude of W
+        A = self._empty(nb, oh, oh, kp)
+        inv = self._empty(M, dtype=torch.float32)
+        self.fwd_ops.append(O.StemIm2colOp(name + ".im2col", x_u8, k, stride, pad, tuple(mean6), tuple(inv_std6), a_scale, A, inv, self.dt_code))
+        alpha, beta = self._bn_alpha(bn) if bn else (None, None)
+        if (alpha is not None and beta is None and self.fold_bn and self.scale_mode == L.BCOSK_SCALE_B2 and bool((alpha > 0).all())):
+            sa = alpha.sqrt().to(w.device).view(-1, 1, 1, 1)          # same folding as _conv_fwd: lin' = sqrt(a) lin
+            w, w_s2d = w * sa, w_s2d * sa
+            alpha = None
+        wf = P.stem_im2col_weight(w, mean6, inv_std6, a_scale, kp)                       # [o, kp] fp32
+        planes_b = P.split_planes(wf, self.planes, self.dt)
+        bmat = self._dev(torch.cat(planes_b, dim=1), self.dt)                             # [o, planes * kp]: segment s = (a plane 0, b plane s)
+        y = self._empty(nb, oh, oh, self.planes * o)
+        rec = ConvRec(name, w_s2d, 1, s2d_pad[0], s2d_pad[1], (oh, oh), (oh, oh), stem_cp)
+        if self.with_explain:
+            rec.gain = self._empty(M, o, dtype=self.gain_dt)
+        block_n = self._block_n(o, self.planes * kp // 64)
+        parts = (o + block_n - 1) // block_n
+        sq = self._empty(parts, M, dtype=torch.float32) if want_sq else None
+        self.fwd_ops.append(O.IgemmOp(
+            name=name, a=A, b=bmat, n=o, lo=(0, 0), up=(0, 0), stride=(1, 1), op=oh, oq=oh, kch=64, chunks_per_tap=kp // 64, taps=[(0, 0)],
+            seg_a_choff=[0] * self.planes, seg_b_plane=list(range(self.planes)), dtype=self.dt_code, mode=L.BCOSK_MODE_FWD, block_n=block_n,
+            scale_mode=self.scale_mode, b_exp=self.b, relu=True, inv_norm=inv, alpha=alpha, beta=beta, gain=rec.gain, sq_out=sq, y=y,
+            y_planes=self.planes, hp_accum=self.hp_accum, hp_chunk=self.hp_chunk,
+            algo_flops=2.0 * M * float((w != 0).sum().item())))
+        rec.algo_flops = self.fwd_ops[-1].algo_flops
+        return Act(y, o, sq, parts), rec
+
     # ------------------------------------------------------------------ explanation emission
     @staticmethod
     def _gain_of(rec: ConvRec):

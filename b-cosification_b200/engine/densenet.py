@@ -115,12 +115,16 @@ class DenseNetPlan(PlanBase):
         self.x_in = self._empty(nb, 3, S, S, dtype=torch.uint8) if self.input_u8 else self._empty(nb, 6, S, S, dtype=torch.float32)
         # ---- stem: normalise + space-to-depth, 7x7/2 conv as a 4x4/1 conv, BN, ReLU (same launches as the ResNet plan)
         h2 = S // 2
-        a0 = self._empty(nb, h2, h2, pl * self.stem_cp)
-        sq0 = self._empty(1, nb * S * S, dtype=torch.float32)
-        self.fwd_ops.append(O.InputPrepOp("input_prep", self.x_in, self.mean, self.inv_std, a0, self.stem_cp, pl, self.dt_code, sq0))
         w4 = P.stem_s2d_weight(sd[nm["conv0"] + ".linear.weight"], self.stem_cp)
-        y1, self.stem = self._conv_fwd("stem", Act(a0, self.stem_cp, sq0, 1), w4, 1, 2, 1, bn=nm["norm0"], relu=True, kch=self.stem_kch,
-                                       want_sq=False, sq_geom=(S, S, 7, 2, 3))
+        if self.hp_accum and self.input_u8 and self.stem_im2col:
+            y1, self.stem = self._stem_fwd_im2col("stem", self.x_in, sd[nm["conv0"] + ".linear.weight"], w4, 7, 2, 3, bn=nm["norm0"],
+                                                  mean6=self.mean, inv_std6=self.inv_std, s2d_pad=(2, 1), stem_cp=self.stem_cp)
+        else:
+            a0 = self._empty(nb, h2, h2, pl * self.stem_cp)
+            sq0 = self._empty(1, nb * S * S, dtype=torch.float32)
+            self.fwd_ops.append(O.InputPrepOp("input_prep", self.x_in, self.mean, self.inv_std, a0, self.stem_cp, pl, self.dt_code, sq0))
+            y1, self.stem = self._conv_fwd("stem", Act(a0, self.stem_cp, sq0, 1), w4, 1, 2, 1, bn=nm["norm0"], relu=True, kch=self.stem_kch,
+                                           want_sq=False, sq_geom=(S, S, 7, 2, 3))
         hp = (h2 + 2 - 3) // 2 + 1
         pooled = self._empty(nb, hp, hp, pl * self.init_c)
         self.fwd_ops.append(O.AvgPoolFwdOp("pool", y1.t, self.init_c, pl, 3, 2, 1, pooled, self.dt_code, None))

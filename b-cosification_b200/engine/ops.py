@@ -694,6 +694,26 @@ class SeedFromTokensOp:
         L.seed_from_tokens(self.g_tokens, nb, t - 1, c, self.scale, self.mul1, self.out1, self.mask2, self.mul2, self.out2, self.planes, self.dtype)
 
 
+@dataclass
+class StemIm2colOp:
+    """include/bcosk.h bcosk_stem_im2col_u8: uint8 image -> stem patch matrix (v_R, v_G, v_B, 1 per tap) + 1/||patch||."""
+    name: str
+    x: Tensor            # [nb, 3, h, w] uint8
+    k: int
+    stride: int
+    pad: int
+    mean6: Tuple[float, ...]
+    inv_std6: Tuple[float, ...]
+    a_scale: float
+    out: Tensor          # [nb, op, oq, kp] 16-bit, one plane
+    inv_norm: Tensor     # [nb*op*oq] fp32
+    dtype: int
+
+    def run(self) -> None:
+        L.stem_im2col_u8(self.x, self.k, self.stride, self.pad, self.mean6, self.inv_std6, self.a_scale, self.out, self.out.shape[-1],
+                         self.inv_norm, self.dtype)
+
+
 def run_ops(ops) -> None:
     for o in ops:
         o.run()

@@ -101,3 +101,22 @@ def stem_s2d_weight(w7: Tensor, cp: int) -> Tensor:
                     base = (dy * 2 + dx) * 6
                     w4[:, base:base + 6, tr, ts] = w7[:, :, i, j]
     return w4
+
+
+def stem_im2col_weight(w: Tensor, mean6: Sequence[float], inv_std6: Sequence[float], a_scale: float, kp: int) -> Tensor:
+    """W [o, 6, k, k] (stem conv over the normalised [x, 1-x] input) -> [o, kp] for the patch matrix of bcosk_stem_im2col_u8:
+    column tap*4 + c multiplies the raw byte v_c * a_scale, column tap*4 + 3 the in-image indicator.  With
+    xn_c = v/255 * istd_c - mean_c * istd_c and xn_{c+3} = -v/255 * istd_{c+3} + (1 - mean_{c+3}) * istd_{c+3}:
+        W'[tap, c] = (W[c] istd_c - W[c+3] istd_{c+3}) / (255 a_scale),   W'[tap, 3] = sum_c (-W[c] mean_c istd_c + W[c+3] (1 - mean_{c+3}) istd_{c+3}).
+    Folded in fp64."""
+    o, c, kh, kw = w.shape
+    assert c == 6 and kp >= 4 * kh * kw
+    w64 = w.to(torch.float64).permute(0, 2, 3, 1).reshape(o, kh * kw, 6)            # [o, tap, c]
+    m = torch.tensor(list(mean6), dtype=torch.float64)
+    s = torch.tensor(list(inv_std6), dtype=torch.float64)
+    out = torch.zeros(o, kp, dtype=torch.float64)
+    col = (w64[:, :, :3] * s[:3] - w64[:, :, 3:] * s[3:]) / (255.0 * a_scale)     # [o, tap, 3]
+    one = (-w64[:, :, :3] * (m[:3] * s[:3]) + w64[:, :, 3:] * ((1.0 - m[3:]) * s[3:])).sum(-1)
+    blk = torch.cat([col, one[..., None]], -1).reshape(o, kh * kw * 4)
+    out[:, :kh * kw * 4] = blk
+    return out.to(torch.float32)

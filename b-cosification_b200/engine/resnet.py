@@ -106,14 +106,19 @@ class ResNetPlan(PlanBase):
         h2 = S // 2
         # throughput mode: the stem reads a zero-bordered buffer (pad 2 before / 1 after) through one window per tile
         self.stem_flat = self.flat_stem and pl == 1 and not self.hp_accum
-        a0 = self._padded(nb, h2, h2, self.stem_cp, 2, 1) if self.stem_flat else self._empty(nb, h2, h2, pl * self.stem_cp)
-        sq0 = self._empty(1, nb * S * S, dtype=torch.float32)
-        self.fwd_ops.append(O.InputPrepOp("input_prep", self.x_in, self.mean, self.inv_std, a0, self.stem_cp, pl,
-                                          self.dt_code, sq0))
         w4 = P.stem_s2d_weight(sd["model.conv1.linear.weight"], self.stem_cp)
-        # the patch norm is the ORIGINAL 7x7/2 pad-3 window over the full-resolution sums of squares
-        y1, self.stem = self._conv_fwd("stem", Act(a0, self.stem_cp, sq0, 1), w4, 1, 2, 1, bn="model.bn1", relu=True,
-                                       kch=self.stem_kch, want_sq=False, sq_geom=(S, S, 7, 2, 3), flat=self.stem_flat)
+        if self.hp_accum and self.input_u8 and self.stem_im2col:
+            # contract modes with uint8 input: GEMM over the exact byte patch matrix (base.py _stem_fwd_im2col)
+            y1, self.stem = self._stem_fwd_im2col("stem", self.x_in, sd["model.conv1.linear.weight"], w4, 7, 2, 3, bn="model.bn1",
+                                                  mean6=self.mean, inv_std6=self.inv_std, s2d_pad=(2, 1), stem_cp=self.stem_cp)
+        else:
+            a0 = self._padded(nb, h2, h2, self.stem_cp, 2, 1) if self.stem_flat else self._empty(nb, h2, h2, pl * self.stem_cp)
+            sq0 = self._empty(1, nb * S * S, dtype=torch.float32)
+            self.fwd_ops.append(O.InputPrepOp("input_prep", self.x_in, self.mean, self.inv_std, a0, self.stem_cp, pl,
+                                              self.dt_code, sq0))
+            # the patch norm is the ORIGINAL 7x7/2 pad-3 window over the full-resolution sums of squares
+            y1, self.stem = self._conv_fwd("stem", Act(a0, self.stem_cp, sq0, 1), w4, 1, 2, 1, bn="model.bn1", relu=True,
+                                           kch=self.stem_kch, want_sq=False, sq_geom=(S, S, 7, 2, 3), flat=self.stem_flat)
         # ---- AvgPool2d(3, 2, 1) (replaces maxpool)
         hp = (h2 + 2 - 3) // 2 + 1
         p1 = self._empty(nb, hp, hp, pl * 64)

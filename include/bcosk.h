@@ -489,6 +489,15 @@ int bcosk_seed_from_tokens(const float* g_tokens, int32_t nb, int32_t npix, int3
                            void* out1, const uint32_t* mask2, const void* mul2, int32_t mul2_f32, void* out2, int32_t planes,
                            int32_t dtype, void* stream);
 
+/* Stem patch matrix for the contract-mode plans with uint8 input.  The k x k / stride stem conv over the normalised [x, 1-x] input
+ * (BcosifyNetwork.forward bcosify.py:50-53 + BcosifyConv2d) is linear in the raw byte v of every colour, so it equals a GEMM over
+ * rows of (v_R, v_G, v_B, 1) per tap with folded weights (engine/pack.py stem_im2col_weight): the bytes are exact in ONE 16-bit plane
+ * and the window is gathered once.  out [nb*op*oq][kp] (kp % 64 == 0, kp >= 4 k^2): column tap*4 + c = v_c * a_scale, tap*4 + 3 = 1
+ * for in-image taps, zeros elsewhere; inv_norm [nb*op*oq] = 1/sqrt(sum over the window of the 6 normalised channels squared + 1e-6)
+ * (calc_patch_norms bcosconv2d.py:196-231). */
+int bcosk_stem_im2col_u8(const uint8_t* x, int32_t nb, int32_t h, int32_t w, int32_t k, int32_t stride, int32_t pad, const float* mean6,
+                         const float* inv_std6, float a_scale, void* out, int32_t kp, float* inv_norm, int32_t dtype, void* stream);
+
 /* Seed of a fused trunk's explanation pass from a gradient computed OUTSIDE the plan (CLIP encoders: the attention-pool head
  * bcos/modules/bcosattnpool.py:34-59 runs on the module-level path and autograd hands back d target / d trunk output):
  * g [nb, c, h, w] fp32 NCHW ->  out1[pix, pl*c + ch] = planes(g * seed_scale * mul1[pix, ch])  (mul1 = gain of the block's last conv)

@@ -456,6 +456,23 @@ def run_seed_from_tokens(op: O.SeedFromTokensOp) -> None:
         _split_store(op.out2, o.view(op.out2.shape[0], op.out2.shape[1], op.out2.shape[2], c), op.planes)
 
 
+def run_stem_im2col(op: O.StemIm2colOp) -> None:
+    nb, _, h, w = op.x.shape
+    k, st, pd = op.k, op.stride, op.pad
+    v = op.x.float()
+    v4 = torch.cat([v * op.a_scale, torch.ones(nb, 1, h, w)], 1)                                  # [nb, 4, h, w]
+    cols = torch.nn.functional.unfold(v4, k, padding=pd, stride=st)                               # [nb, 4*k*k, L] channel-major (c, tap)
+    L_ = cols.shape[-1]
+    cols = cols.view(nb, 4, k * k, L_).permute(0, 3, 2, 1).reshape(nb, L_, k * k * 4)             # (tap, c)
+    out = torch.zeros(nb * L_, op.out.shape[-1])
+    out[:, :k * k * 4] = cols.reshape(nb * L_, -1)
+    op.out.copy_(out.view(op.out.shape).to(op.out.dtype))
+    x6 = _x6(op.x)
+    xn = (x6 - torch.tensor(op.mean6).view(1, 6, 1, 1)) * torch.tensor(op.inv_std6).view(1, 6, 1, 1)
+    sq = torch.nn.functional.avg_pool2d((xn ** 2).sum(1, keepdim=True), k, stride=st, padding=pd, divisor_override=1)
+    op.inv_norm.copy_((1.0 / (sq + 1e-6).sqrt()).reshape(-1))
+
+
 _DISPATCH = {
     O.IgemmOp: run_igemm, O.InputPrepOp: run_input_prep, O.PatchNormOp: run_patch_norm, O.AvgPoolFwdOp: run_avgpool_fwd,
     O.AvgPoolBwdMulOp: run_avgpool_bwd_mul, O.GapLogitsOp: run_gap_logits, O.FcSeedOp: run_fc_seed,
@@ -466,7 +483,7 @@ _DISPATCH = {
     O.PixelSqsumOp: run_pixel_sqsum,
     O.DenseBnReluFwdOp: run_dense_bn_relu_fwd, O.DenseBnReluBwdOp: run_dense_bn_relu_bwd, O.DenseSliceCastOp: run_dense_slice_cast,
     O.CopyChannelsOp: run_copy_channels,
-    O.SgemmOp: run_sgemm, O.HeadTokensOp: run_head_tokens, O.RowSoftmaxOp: run_row_softmax, O.SeedFromTokensOp: run_seed_from_tokens,
+    O.StemIm2colOp: run_stem_im2col, O.SgemmOp: run_sgemm, O.HeadTokensOp: run_head_tokens, O.RowSoftmaxOp: run_row_softmax, O.SeedFromTokensOp: run_seed_from_tokens,
 }
 
 

@@ -32,6 +32,7 @@ OUTPUT_FIELDS = {
     O.DenseBnReluBwdOp: ["G"],
     O.DenseSliceCastOp: ["out"],
     O.CopyChannelsOp: ["dst"],
+    O.StemIm2colOp: ["out", "inv_norm"],
     O.SgemmOp: ["c"],
     O.HeadTokensOp: ["tokens"],
     O.RowSoftmaxOp: ["s"],

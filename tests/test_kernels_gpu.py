@@ -124,6 +124,26 @@ def test_igemm_forward_plain_linear(bcosk_lib, planes):
         print(_run_and_compare(plan.fwd_ops, tol16=BF16_TOL if planes == 1 else 2e-4))
 
 
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+def test_stem_im2col_u8(bcosk_lib, dt):
+    """bcosk_stem_im2col_u8: byte patch matrix (v_R, v_G, v_B, 1 per in-image tap) and 1/||patch|| of the normalised window"""
+    g = torch.Generator().manual_seed(31)
+    x = torch.randint(0, 256, (2, 3, 40, 40), generator=g, dtype=torch.uint8)
+    mean6, istd6 = (0.485, 0.456, 0.406, 0.515, 0.544, 0.594), tuple(1 / s for s in (0.229, 0.224, 0.225, 0.229, 0.224, 0.225))
+    tdt = torch.float16 if dt == "fp16" else torch.bfloat16
+    for k, st, pd in ((7, 2, 3), (3, 2, 1)):
+        op_ = (40 + 2 * pd - k) // st + 1
+        kp = (4 * k * k + 63) // 64 * 64
+        op = O.StemIm2colOp("im2col", x, k, st, pd, mean6, istd6, 2.0 ** -6, torch.zeros(2, op_, op_, kp, dtype=tdt), torch.zeros(2 * op_ * op_),
+                            L.DTYPE_CODE[dt])
+        dev = U.to_device(op, "cuda", {})
+        E.run([op])
+        dev.run()
+        torch.cuda.synchronize()
+        assert torch.equal(dev.out.cpu(), op.out)                                   # bytes and indicators are exact
+        assert U.max_rel_err(dev.inv_norm, op.inv_norm) < 2e-6
+
+
 MAXOUT_CASES = [
     # name, planes, G, cout (GEMM columns), k, b, bias, y_f32
     ("mo2_1plane_16bit", 1, 2, 128, 3, 2.0, False, False),

@@ -182,3 +182,32 @@ def test_densenet_plan_matches_oracle():
     m = OR.parity_metrics(plan.logits, plan.cmap, ref["logits"], ref["contribution_map"])
     print(m)
     assert m["argmax_equal"] and m["logit_rel_err"] < 1e-4 and m["map_cos_min"] > 0.999, m
+
+
+def test_uint8_stem_patch_matrix_path_matches_the_implicit_gemm_stem():
+    """Contract-mode plans with uint8 input run the stem as a GEMM over the exact byte patch matrix (base.py _stem_fwd_im2col:
+    folded weights, in-image indicator column, patch norm from the window): same network function as the space-to-depth stem."""
+    arch, size, nb = "resnet18", 64, 2
+    sd = synth.synth_state_dict(resnet_state_shapes(arch), 0)
+    u8 = torch.from_numpy(synth.synth_images_u8(nb, size, 3))
+    x6 = synth.to_bcos_input(u8)
+    om = OR.OracleResNet(arch, sd)
+    om.calibrate_bn(x6)
+    ref = OR.explain_batched(om.forward, x6)
+    a = ResNetPlan(arch, sd, nb, planes=2, dtype="fp16", explain_planes=1, seed_scale=4096.0, device="cpu", image_size=size, input_u8=True)
+    assert any(isinstance(o, O.StemIm2colOp) for o in a.fwd_ops) and not any(isinstance(o, O.InputPrepOp) for o in a.fwd_ops)
+    a.x_in.copy_(u8)
+    E.run(a.fwd_ops)
+    E.run(a.bwd_ops)
+    m = OR.parity_metrics(a.logits, a.cmap, ref["logits"], ref["contribution_map"])
+    assert m["argmax_equal"] and m["logit_rel_err"] < 1e-4 and m["map_cos_min"] > 0.9999 and m["map_maxabs_over_range"] < 2e-3, m
+    b = ResNetPlan(arch, sd, nb, planes=2, dtype="fp16", explain_planes=1, seed_scale=4096.0, device="cpu", image_size=size, input_u8=True)
+    b.stem_im2col = False
+    b.fwd_ops.clear(); b.bwd_ops.clear(); b.blocks.clear()
+    b._build_forward(); b._build_explain(False)
+    assert any(isinstance(o, O.InputPrepOp) for o in b.fwd_ops)
+    b.x_in.copy_(u8)
+    E.run(b.fwd_ops)
+    E.run(b.bwd_ops)
+    assert ((a.logits - b.logits).abs().max() / b.logits.abs().max()).item() < 1e-4
+    assert torch.nn.functional.cosine_similarity(a.cmap.flatten(1), b.cmap.flatten(1)).min().item() > 0.9999
