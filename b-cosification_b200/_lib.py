@@ -471,6 +471,21 @@ def gather_cast(src, idx, n, out, dtype) -> None:
     check(load().bcosk_gather_cast(_p(src), _p(idx), C.c_int64(n), _p(out), dtype, _stream()), "bcosk_gather_cast")
 
 
+def adam_state_step(state, beta1, beta2) -> None:
+    check(load().bcosk_adam_state_step(_p(state), C.c_float(beta1), C.c_float(beta2), _stream()), "bcosk_adam_state_step")
+
+
+def agc_adamw_multi(w, g, gidx, m, v, unit_off, unit_cols, units, grad_scale, lr, beta1, beta2, eps, weight_decay, clip_factor, agc_eps,
+                    adam_state) -> None:
+    check(load().bcosk_agc_adamw_multi(_p(w), _p(g), _p(gidx), _p(m), _p(v), _p(unit_off), _p(unit_cols), units, C.c_float(grad_scale),
+                                       C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay),
+                                       C.c_float(clip_factor), C.c_float(agc_eps), _p(adam_state), _stream()), "bcosk_agc_adamw_multi")
+
+
+def gather_cast_multi(src, table, npacks, max_n, dtype) -> None:
+    check(load().bcosk_gather_cast_multi(_p(src), _p(table), npacks, C.c_int64(max_n), dtype, _stream()), "bcosk_gather_cast_multi")
+
+
 def agc_adamw(w, g, gidx, m, v, units, cols, grad_scale, lr, beta1, beta2, eps, weight_decay, clip_factor, agc_eps, step) -> None:
     check(load().bcosk_agc_adamw(_p(w), _p(g), _p(gidx), _p(m), _p(v), units, cols, C.c_float(grad_scale), C.c_float(lr),
                                  C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_float(clip_factor),

@@ -399,6 +399,73 @@ __global__ void __launch_bounds__(256) agc_adamw_kernel(float* __restrict__ w, c
   }
 }
 
+// ---- whole-model variants (one launch each; CUDA-graph friendly: the step counter lives in device memory) ----------------------
+// adam state [3] = {step, 1 - beta1^step, 1 - beta2^step}: advanced on the device so that a captured graph can be replayed
+__global__ void adam_state_step_kernel(float* __restrict__ st, float beta1, float beta2) {
+  const float step = st[0] + 1.f;
+  st[0] = step;
+  st[1] = 1.f - powf(beta1, step);
+  st[2] = 1.f - powf(beta2, step);
+}
+
+// unit u of the whole model: cols[u] consecutive master weights starting at off[u] (one block per unit)
+__global__ void __launch_bounds__(256) agc_adamw_multi_kernel(float* __restrict__ w, const float* __restrict__ g, const int32_t* __restrict__ gidx,
+                                                              float* __restrict__ m, float* __restrict__ v, const long long* __restrict__ off,
+                                                              const int32_t* __restrict__ ncols, float gscale, float lr, float beta1,
+                                                              float beta2, float eps, float wd, float clip, float agc_eps,
+                                                              const float* __restrict__ st) {
+  __shared__ float red[2][8];
+  const size_t base = (size_t)off[blockIdx.x];
+  const int cols = ncols[blockIdx.x];
+  const float bc1 = st[1], bc2 = st[2];
+  float sw = 0.f, sg = 0.f;
+  for (int i = threadIdx.x; i < cols; i += 256) {
+    const float ww = w[base + i];
+    const float gg = g[(size_t)gidx[base + i]] * gscale;
+    sw = fmaf(ww, ww, sw);
+    sg = fmaf(gg, gg, sg);
+  }
+  sw = warp_sum(sw);
+  sg = warp_sum(sg);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sw; red[1][threadIdx.x >> 5] = sg; }
+  __syncthreads();
+  float nw = 0.f, ng = 0.f;
+  for (int i = 0; i < 8; ++i) { nw += red[0][i]; ng += red[1][i]; }
+  nw = sqrtf(nw);
+  ng = sqrtf(ng);
+  float factor = 1.f;
+  if (clip > 0.f) {
+    const float max_norm = fmaxf(nw, agc_eps) * clip;
+    if (!(ng < max_norm)) factor = max_norm / fmaxf(ng, 1e-6f);
+  }
+  for (int i = threadIdx.x; i < cols; i += 256) {
+    const float gg = g[(size_t)gidx[base + i]] * gscale * factor;
+    float ww = w[base + i];
+    const float mm = beta1 * m[base + i] + (1.f - beta1) * gg;
+    const float vv = beta2 * v[base + i] + (1.f - beta2) * gg * gg;
+    m[base + i] = mm;
+    v[base + i] = vv;
+    ww -= lr * wd * ww;
+    ww -= lr * (mm / bc1) / (sqrtf(vv / bc2) + eps);
+    w[base + i] = ww;
+  }
+}
+
+// table[p] = {index pointer, output pointer, n}: every packed operand of the model refreshed in one launch (blockIdx.y = pack)
+template <typename T>
+__global__ void gather_cast_multi_kernel(const float* __restrict__ src, const long long* __restrict__ table) {
+  const long long* e = table + 3 * (long long)blockIdx.y;
+  const int32_t* idx = reinterpret_cast<const int32_t*>(e[0]);
+  T* out = reinterpret_cast<T*>(e[1]);
+  const long long n = e[2];
+  for (long long i2 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i2 < n; i2 += (long long)gridDim.x * blockDim.x * 2) {
+    const int32_t a = idx[i2], b = (i2 + 1 < n) ? idx[i2 + 1] : -1;
+    const float fa = a >= 0 ? __ldg(src + a) : 0.f, fb = b >= 0 ? __ldg(src + b) : 0.f;
+    if (i2 + 1 < n) *reinterpret_cast<uint32_t*>(out + i2) = Cvt<T>::pack2(fa, fb);
+    else out[i2] = (T)fa;
+  }
+}
+
 inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline unsigned grid_for(long long items, int per_block, unsigned cap = 0x7fffffffu) {
   long long b = (items + per_block - 1) / per_block;
@@ -544,6 +611,32 @@ extern "C" int bcosk_agc_adamw(float* w, const float* g, const int32_t* gidx, fl
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   agc_adamw_kernel<<<units, 256, 0, S_(stream)>>>(w, g, gidx, m, v, cols, grad_scale, lr, beta1, beta2, eps, weight_decay, clip_factor,
                                                  agc_eps, bc1, bc2);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_adam_state_step(float* state, float beta1, float beta2, void* stream) {
+  if (!state) return set_error(BCOSK_EINVAL, "adam_state_step: null pointer");
+  adam_state_step_kernel<<<1, 1, 0, S_(stream)>>>(state, beta1, beta2);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_agc_adamw_multi(float* w, const float* g, const int32_t* gidx, float* m, float* v, const int64_t* unit_off,
+                                     const int32_t* unit_cols, int32_t units, float grad_scale, float lr, float beta1, float beta2, float eps,
+                                     float weight_decay, float clip_factor, float agc_eps, const float* adam_state, void* stream) {
+  if (!w || !g || !gidx || !m || !v || !unit_off || !unit_cols || !adam_state || units < 1)
+    return set_error(BCOSK_EINVAL, "agc_adamw_multi: bad argument");
+  agc_adamw_multi_kernel<<<units, 256, 0, S_(stream)>>>(w, g, gidx, m, v, reinterpret_cast<const long long*>(unit_off), unit_cols, grad_scale, lr,
+                                                       beta1, beta2, eps, weight_decay, clip_factor, agc_eps, adam_state);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_gather_cast_multi(const float* src, const int64_t* table, int32_t npacks, int64_t max_n, int32_t dtype, void* stream) {
+  if (!src || !table || npacks < 1 || npacks > 65535 || max_n < 1) return set_error(BCOSK_EINVAL, "gather_cast_multi: bad argument");
+  dim3 grid(grid_for((max_n + 1) / 2, 256, 1024), npacks);
+  BCOSK_T_SWITCH(dtype, gather_cast_multi_kernel<T><<<grid, 256, 0, S_(stream)>>>(src, reinterpret_cast<const long long*>(table));)
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }

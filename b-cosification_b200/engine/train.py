@@ -406,12 +406,27 @@ class ResNetTrainPlan(PlanBase):
                 gidx[lay.bnw_off:lay.bnw_off + o] = lay.gbn_off + torch.arange(o)
         assert int((gidx < 0).sum()) == 0, "a master weight without a gradient slot"
         self.gidx = gidx.to(torch.int32).to(self.device)
+        # ---- AGC + AdamW of the WHOLE model in one launch: one unit = one output row of a conv / the whole BN weight vector
+        #      (agc.py:28-42 clips unit-wise); the Adam step counter lives on the device so that the step can be a CUDA graph
+        u_off, u_cols = [], []
         for lay in self.layers:
             o = lay.fwd.n
             cols = lay.w_numel // o
-            self.opt_ops.append(FnOp(lay.name + ".opt", lambda l=lay, o=o, cols=cols: self._opt(l.w_off, o, cols)))
+            u_off += [lay.w_off + i * cols for i in range(o)]
+            u_cols += [cols] * o
             if lay.bn is not None:
-                self.opt_ops.append(FnOp(lay.name + ".bn.opt", lambda l=lay, o=o: self._opt(l.bnw_off, 1, o)))
+                u_off.append(lay.bnw_off)
+                u_cols.append(o)
+        self.unit_off = torch.tensor(u_off, dtype=torch.int64, device=self.device)
+        self.unit_cols = torch.tensor(u_cols, dtype=torch.int32, device=self.device)
+        self.adam_state = self._zeros(3, dtype=torch.float32)          # {step, 1 - beta1^step, 1 - beta2^step}
+        self.opt_ops.append(FnOp("adam.step", lambda: L.adam_state_step(self.adam_state, self.hyper["beta1"], self.hyper["beta2"])))
+        self.opt_ops.append(FnOp("agc_adamw", self._opt_all))
+        # ---- every packed 16-bit operand refreshed from the fp32 master weights in one launch
+        tab = [[idx.data_ptr(), buf.data_ptr(), idx.numel()] for buf, idx in self.packs]
+        self.pack_table = torch.tensor(tab, dtype=torch.int64, device=self.device)
+        self.pack_max_n = max(idx.numel() for _, idx in self.packs)
+        self._graph = None
 
     def _norm_vec(self, lay: TrainLayer) -> Tensor:
         """Patch-norm vector of `lay` at its INPUT resolution (a fresh buffer; 1x1 stride-1 layers use gnT directly)."""
@@ -428,19 +443,17 @@ class ResNetTrainPlan(PlanBase):
                 return buf, idx
         raise KeyError(lay.name)
 
-    def _opt(self, off: int, units: int, cols: int) -> None:
+    def _opt_all(self) -> None:
         h = self.hyper
-        n = units * cols
-        L.agc_adamw(self.w_flat[off:off + n], self.g_flat, self.gidx[off:off + n], self.m_flat[off:off + n], self.v_flat[off:off + n],
-                    units, cols, 1.0 / (self.world * self.loss_scale), h["lr"], h["beta1"], h["beta2"], h["eps"], h["wd"], h["clip"], h["agc_eps"],
-                    self.step_count)
+        L.agc_adamw_multi(self.w_flat, self.g_flat, self.gidx, self.m_flat, self.v_flat, self.unit_off, self.unit_cols, self.unit_off.numel(),
+                          1.0 / (self.world * self.loss_scale), h["lr"], h["beta1"], h["beta2"], h["eps"], h["wd"], h["clip"], h["agc_eps"],
+                          self.adam_state)
 
     # ------------------------------------------------------------------ execution
     def refresh_operands(self) -> None:
         """fp32 master weights -> every packed 16-bit operand (forward, data-gradient and parity-class launches)."""
         self._require_gpu()
-        for buf, idx in self.packs:
-            L.gather_cast(self.w_flat, idx, idx.numel(), buf, self.dt_code)
+        L.gather_cast_multi(self.w_flat, self.pack_table, len(self.packs), self.pack_max_n, self.dt_code)
 
     def load_batch(self, images: Tensor, labels: Tensor) -> None:
         self.x_in.copy_(images, non_blocking=True)
@@ -462,9 +475,59 @@ class ResNetTrainPlan(PlanBase):
         """One step: forward (train mode), loss, backward, gradient all-reduce, AGC + AdamW.  Returns the loss tensor (device)."""
         if images is not None:
             self.load_batch(images, labels)
+        if self._graph is not None:
+            self.step_count += 1
+            self._graph.replay()
+            return self.loss
         self.forward_backward()
         self.optimizer_step()
         return self.loss
+
+    def capture(self) -> bool:
+        """Capture the whole step (forward, loss, backward with the bucketed all-reduce on its side stream, AGC + AdamW, operand
+        refresh: ~640 launches) as ONE CUDA graph; `train_step` replays it.  The training state (weights, moments, step counter,
+        BN running variances) is saved around the warm-up steps the capture needs, so capturing does not advance training.
+        Single-rank plans only: returns False (and the step stays eager) when world_size > 1."""
+        self._require_gpu()
+        if self.world > 1:
+            # a captured graph with the NCCL all-reduce on its side stream hung on this stack (torch 2.11, NCCL 2.28.9, two B200s):
+            # multi-rank steps stay eager (the whole-model optimizer / refresh launches still apply)
+            return False
+        state = [self.w_flat, self.m_flat, self.v_flat, self.adam_state] + list(self.running_var.values())
+        keep = [t.clone() for t in state]
+        steps = self.step_count
+
+        def restore():
+            for dst, src in zip(state, keep):
+                dst.copy_(src)
+            self.step_count = steps
+            self.refresh_operands()
+
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.forward_backward()
+                self.optimizer_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        restore()
+        g = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(g):
+                self.forward_backward()
+                O.run_ops(self.opt_ops)
+                self.refresh_operands()
+        except Exception as e:  # noqa: BLE001
+            import warnings
+            warnings.warn(f"bcos_b200: training step not captured ({type(e).__name__}: {e}); running eagerly")
+            torch.cuda.synchronize()
+            restore()
+            return False
+        torch.cuda.synchronize()
+        restore()
+        self._graph = g
+        return True
 
     # ------------------------------------------------------------------ inspection (tests, checkpoints)
     def gradients(self) -> Dict[str, Tensor]:
@@ -483,7 +546,7 @@ class ResNetTrainPlan(PlanBase):
         return out
 
     def num_train_launches(self) -> int:
-        return len(self.fwd_ops) + len(self.bwd_ops) + len(self.opt_ops) + len(self.packs)
+        return len(self.fwd_ops) + len(self.bwd_ops) + len(self.opt_ops) + 1
 
     def train_flops(self) -> float:
         """2*MAC of forward + data gradient + weight gradient (the data gradient of the stem is not needed)."""

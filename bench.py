@@ -517,6 +517,7 @@ def measure_train_step(args, dev, rank, world, barrier, max_over_ranks):
     imgs = torch.from_numpy(synth.synth_images_u8(Bt, 224, 2000 + rank)).to(dev)
     labels = (torch.arange(Bt) * 37 + rank) % 1000
     plan.load_batch(imgs, labels.to(dev))
+    captured = plan.capture()            # the whole step (incl. the bucketed all-reduce on its side stream) as one CUDA graph
     losses = []
     for _ in range(3):
         losses.append(float(plan.train_step()))
@@ -532,7 +533,7 @@ def measure_train_step(args, dev, rank, world, barrier, max_over_ranks):
     rec = {"workload": "B-cosification fine-tuning step of ResNet-50, batch-sharded backward, NCCL gradient all-reduce (BASELINE config 5)",
            "batch_per_gpu": Bt, "n_gpus": world, "steps": Kt, "ms_per_step": ms, "value": world * Bt / (ms * 1e-3), "unit": "img/s",
            "dtype": "bf16 operands, fp32 accumulate / master weights / optimizer state",
-           "tflops_per_gpu": plan.train_flops() / (ms * 1e-3) / 1e12, "launches_per_step": plan.num_train_launches(),
+           "tflops_per_gpu": plan.train_flops() / (ms * 1e-3) / 1e12, "launches_per_step": plan.num_train_launches(), "cuda_graph": bool(captured),
            "collective": None if world == 1 else f"NCCL all_reduce(sum) of {len(plan.buckets)} fp32 gradient buckets on a side stream, overlapped with the backward pass",
            "allreduce_bytes_per_step": 0 if world == 1 else int(plan.g_flat.numel() * 4),
            "loss_first_steps": losses[:3], "loss_last": losses[-1], "loss_decreases_on_fixed_batch": bool(losses[-1] < losses[0])}

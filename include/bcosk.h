@@ -289,6 +289,16 @@ int bcosk_gather_cast(const float* src, const int32_t* idx, int64_t n, void* out
 int bcosk_agc_adamw(float* w, const float* g, const int32_t* gidx, float* m, float* v, int32_t units, int32_t cols,
                     float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay, float clip_factor,
                     float agc_eps, int32_t step, void* stream);
+/* Whole-model variants, one launch each and CUDA-graph friendly.  adam_state [3] fp32 on the device = {step, 1 - beta1^step,
+ * 1 - beta2^step}: bcosk_adam_state_step advances it (so a captured training-step graph can be replayed), bcosk_agc_adamw_multi
+ * runs AGC + AdamW for EVERY unit of the model (unit u = unit_cols[u] consecutive master weights at unit_off[u]; gidx maps every
+ * master element to its gradient slot), bcosk_gather_cast_multi refreshes every packed operand (table[p] = {int32 index pointer,
+ * 16-bit output pointer, n} as int64). */
+int bcosk_adam_state_step(float* state, float beta1, float beta2, void* stream);
+int bcosk_agc_adamw_multi(float* w, const float* g, const int32_t* gidx, float* m, float* v, const int64_t* unit_off,
+                          const int32_t* unit_cols, int32_t units, float grad_scale, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, float clip_factor, float agc_eps, const float* adam_state, void* stream);
+int bcosk_gather_cast_multi(const float* src, const int64_t* table, int32_t npacks, int64_t max_n, int32_t dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Bandwidth kernels (coalesced, 16-byte vectorised, warp-shuffle reductions)

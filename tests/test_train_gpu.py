@@ -218,6 +218,29 @@ def test_resnet18_train_step_matches_oracle(bcosk_lib, dtype, loss_scale, min_co
     assert math.isfinite(loss2)
 
 
+def test_captured_train_step_equals_eager(bcosk_lib):
+    """ResNetTrainPlan.capture(): the whole step as one CUDA graph (whole-model AGC + AdamW launch, device-side Adam step counter,
+    one operand-refresh launch) gives the same weights as the eager step; capturing does not advance the training state."""
+    arch, S, nb = "resnet18", 64, 8
+    sd = synth.synth_state_dict(OR.resnet_state_shapes(arch), 0)
+    imgs = torch.from_numpy(synth.synth_images_u8(nb, S, 1))
+    labels = torch.arange(nb) * 37 % 1000
+    a = ResNetTrainPlan(arch, sd, nb, dtype="bf16", device="cuda", image_size=S)
+    b = ResNetTrainPlan(arch, sd, nb, dtype="bf16", device="cuda", image_size=S)
+    b.load_batch(imgs, labels)
+    w0 = b.w_flat.clone()
+    assert b.capture() and torch.equal(b.w_flat, w0) and float(b.adam_state[0]) == 0.0
+    la, lb = [], []
+    for _ in range(3):
+        la.append(float(a.train_step(imgs, labels)))
+        lb.append(float(b.train_step(imgs, labels)))
+    torch.cuda.synchronize()
+    assert float(b.adam_state[0]) == 3.0 and b.step_count == 3
+    assert max(abs(x - y) / abs(x) for x, y in zip(la, lb)) < 1e-4, (la, lb)
+    # split-K weight gradients add with fp32 atomics (order-dependent in the last bits), everything else is fixed-order
+    assert _rel(b.w_flat, a.w_flat) < 1e-4
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NCCL all-reduce of the gradient buckets)")
 def test_two_rank_nccl_allreduce_matches_manual_sum():
     """scripts/exp_train_ddp.py under torchrun: the bucketed side-stream all-reduce equals all_reduce of the ranks' local
