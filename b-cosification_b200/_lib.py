@@ -341,6 +341,22 @@ def stem_im2col_u8(x, k, stride, pad, mean6, inv_std6, a_scale, out, kp, inv_nor
                                       dtype, _stream()), "bcosk_stem_im2col_u8")
 
 
+def zero_insert_nhwc(src, dst, stride) -> None:
+    nb, oh, ow, e = src.shape
+    check(load().bcosk_zero_insert_nhwc(_p(src), nb, oh, ow, e, _p(dst), dst.shape[1], dst.shape[2], stride, _stream()), "bcosk_zero_insert_nhwc")
+
+
+def nhwc_scatter_nchw_f32(y, nb, c, oh, ow, planes, dtype, out, stride) -> None:
+    import torch
+    check(load().bcosk_nhwc_scatter_nchw_f32(_p(y), int(y.dtype == torch.float32), nb, c, oh, ow, y.shape[-1], planes, dtype, _p(out),
+                                             out.shape[2], out.shape[3], stride, _stream()), "bcosk_nhwc_scatter_nchw_f32")
+
+
+def pixel_sqsum_nchw_f32(x, sq) -> None:
+    nb, c, h, w = x.shape
+    check(load().bcosk_pixel_sqsum_nchw_f32(_p(x), nb, c, C.c_int64(h * w), _p(sq), _stream()), "bcosk_pixel_sqsum_nchw_f32")
+
+
 def seed_from_nchw(g, seed_scale, mul1, out1, mask2, mul2, out2, planes, dtype) -> None:
     import torch
     nb, c, h, w = g.shape

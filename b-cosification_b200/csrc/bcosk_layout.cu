@@ -188,6 +188,99 @@ extern "C" int bcosk_channel_stats_nchw(const float* x, int32_t nb, int32_t c, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small strided movers of the module-level path (no eager torch indexing on the path):
+//   zero_insert_nhwc      dst[img, s*p, s*q, :] = src[img, p, q, :]      (the zero-inserted gradient of a strided k x k conv; the
+//                         other positions of dst are zero from allocation and never written)
+//   nhwc_scatter_nchw_f32 out[img, ch, s*p, s*q] = y[img, p, q, ch]      (data gradient of a strided 1x1 conv: it lives on the sampled
+//                         input positions only; out is zero elsewhere)
+//   pixel_sqsum_nchw_f32  sq[img, pix] = sum_ch x[img, ch, pix]^2        (calc_patch_norms' first step on the reference's own layout)
+// ------------------------------------------------------------------------------------------------
+namespace bcosk {
+
+__global__ void zero_insert_nhwc_kernel(const uint4* __restrict__ src, int oh, int ow, int vec_per_pix, uint4* __restrict__ dst, int h, int w,
+                                        int stride, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long pix = idx / vec_per_pix;
+  const int v = (int)(idx - pix * vec_per_pix);
+  const long long img = pix / ((long long)oh * ow);
+  const int r = (int)(pix - img * oh * ow);
+  const int p = r / ow, q = r - p * ow;
+  dst[((img * h + (long long)p * stride) * w + (long long)q * stride) * vec_per_pix + v] = src[idx];
+}
+
+template <typename T>
+__global__ void nhwc_scatter_nchw_f32_kernel(const void* __restrict__ y, int y_f32, int nb, int c, int oh, int ow, int ld, int planes,
+                                             float* __restrict__ out, int H, int W, int stride) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ohw = (long long)oh * ow;
+  if (pix >= (long long)nb * ohw) return;
+  const long long img = pix / ohw;
+  const int r = (int)(pix - img * ohw);
+  const int p = r / ow, q = r - p * ow;
+  float* dst = out + img * c * (long long)H * W + (long long)p * stride * W + (long long)q * stride;
+  const int cpl = ld / (y_f32 ? 1 : planes);
+  for (int ch = 0; ch < c; ++ch) {
+    float f = 0.f;
+    if (y_f32) f = __ldg(reinterpret_cast<const float*>(y) + pix * ld + ch);
+    else
+      for (int pl = 0; pl < planes; ++pl) f += (float)reinterpret_cast<const T*>(y)[pix * ld + (long long)pl * cpl + ch];
+    dst[(long long)ch * H * W] = f;
+  }
+}
+
+__global__ void pixel_sqsum_nchw_f32_kernel(const float* __restrict__ x, int c, long long hw, long long total, float* __restrict__ sq) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const long long img = pix / hw, sp = pix - img * hw;
+  const float* src = x + img * c * hw + sp;
+  float acc = 0.f;
+  for (int ch = 0; ch < c; ++ch) {
+    const float v = __ldg(src + (long long)ch * hw);
+    acc = fmaf(v, v, acc);
+  }
+  sq[pix] = acc;
+}
+
+}  // namespace bcosk
+
+extern "C" int bcosk_zero_insert_nhwc(const void* src, int32_t nb, int32_t oh, int32_t ow, int32_t row_elems, void* dst, int32_t h, int32_t w,
+                                      int32_t stride, void* stream) {
+  using namespace bcosk;
+  if (!src || !dst || nb < 1 || row_elems % 8 || stride < 1 || (oh - 1) * stride >= h || (ow - 1) * stride >= w)
+    return set_error(BCOSK_EINVAL, "zero_insert_nhwc: bad argument");
+  const int vpp = row_elems / 8;
+  const long long total = (long long)nb * oh * ow * vpp;
+  zero_insert_nhwc_kernel<<<nblocks(total, 256), 256, 0, S2(stream)>>>(reinterpret_cast<const uint4*>(src), oh, ow, vpp, reinterpret_cast<uint4*>(dst), h,
+                                                                      w, stride, total);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_nhwc_scatter_nchw_f32(const void* y, int32_t y_f32, int32_t nb, int32_t c, int32_t oh, int32_t ow, int32_t ld,
+                                           int32_t planes, int32_t dtype, float* out, int32_t h, int32_t w, int32_t stride, void* stream) {
+  using namespace bcosk;
+  if (!y || !out || nb < 1 || c < 1 || stride < 1 || (oh - 1) * stride >= h || (ow - 1) * stride >= w)
+    return set_error(BCOSK_EINVAL, "nhwc_scatter_nchw_f32: bad argument");
+  const long long n = (long long)nb * oh * ow;
+  if (dtype == BCOSK_DTYPE_F16)
+    nhwc_scatter_nchw_f32_kernel<__half><<<nblocks(n, 128), 128, 0, S2(stream)>>>(y, y_f32, nb, c, oh, ow, ld, planes, out, h, w, stride);
+  else
+    nhwc_scatter_nchw_f32_kernel<__nv_bfloat16><<<nblocks(n, 128), 128, 0, S2(stream)>>>(y, y_f32, nb, c, oh, ow, ld, planes, out, h, w, stride);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_pixel_sqsum_nchw_f32(const float* x, int32_t nb, int32_t c, int64_t hw, float* sq, void* stream) {
+  using namespace bcosk;
+  if (!x || !sq || nb < 1 || c < 1 || hw < 1) return set_error(BCOSK_EINVAL, "pixel_sqsum_nchw_f32: bad argument");
+  const long long total = (long long)nb * hw;
+  pixel_sqsum_nchw_f32_kernel<<<nblocks(total, 256), 256, 0, S2(stream)>>>(x, c, hw, total, sq);
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Seed of a fused trunk's explanation pass from a gradient computed outside the plan (the attention-pool head of the CLIP
 // encoders runs on the module-level path): g NCHW fp32 -> the last block's two gradient tensors in NHWC 16-bit planes,
 //   out1 = g * seed_scale * mul1               (gradient x gain of the block's last conv: its `ghat`)

@@ -140,16 +140,12 @@ class LayerPlan(PlanBase):
         else:
             L.nchw_to_nhwc16(gy.contiguous(), self.ghat_dense, o, self.planes, self.dt_code, gain.float() if gain.dtype != torch.float32 else gain, None)
         if self.rec.ghat_map is not None:          # strided k>1 conv: zero-inserted gradient at input resolution
-            s = self.rec.stride
-            self.rec.ghat[:, ::s, ::s][:, :oh, :ow] = self.ghat_dense
+            L.zero_insert_nhwc(self.ghat_dense, self.rec.ghat, self.rec.stride)
         self.bwd_op.run()
         h, w = self.rec.in_hw
         if self.dense_dgrad:                       # 1x1 strided conv: gradient lives on the sampled positions only
-            s = self.rec.stride
-            small = torch.empty(nb, self.cin, oh, ow, dtype=torch.float32, device=gy.device)
-            L.nhwc_to_nchw_f32(self.gx, nb, self.cin, oh, ow, 1, self.dt_code, small)
             gx = torch.zeros(nb, self.cin, h, w, dtype=torch.float32, device=gy.device)
-            gx[:, :, ::s, ::s][:, :, :oh, :ow] = small
+            L.nhwc_scatter_nchw_f32(self.gx, nb, self.cin, oh, ow, 1, self.dt_code, gx, self.rec.stride)
             return gx
         gx = torch.empty(nb, self.cin, h, w, dtype=torch.float32, device=gy.device)
         L.nhwc_to_nchw_f32(self.gx, nb, self.cin, h, w, 1, self.dt_code, gx)
@@ -164,8 +160,11 @@ class _PlanCache:
         self.stamp = None
 
     def get(self, weight: Tensor, bias: Optional[Tensor], eff_weight_fn, in_shape, stride, pad, b, linear_eps,
-            max_out: int = 1) -> LayerPlan:
-        stamp = (weight.data_ptr(), weight._version, None if bias is None else (bias.data_ptr(), bias._version), str(weight.device))
+            max_out: int = 1, extra: tuple = ()) -> LayerPlan:
+        # everything the packed (effective) weight is made of: further tensors (weight-norm scale, the q / k / v matrices of a packed
+        # projection) and flags come in through `extra`
+        stamp = (weight.data_ptr(), weight._version, None if bias is None else (bias.data_ptr(), bias._version), str(weight.device),
+                 tuple((e.data_ptr(), e._version) if isinstance(e, Tensor) else e for e in extra))
         if stamp != self.stamp:
             self.plans.clear()
             self.stamp = stamp
@@ -275,11 +274,11 @@ def _is_fake(x: Tensor) -> bool:
 
 
 def bcos_map(x: Tensor, cache: _PlanCache, weight: Tensor, bias: Optional[Tensor], eff_weight_fn, stride: int, pad: int,
-             b: float, detach: bool, linear_eps: bool = False, max_out: int = 1) -> Tensor:
+             b: float, detach: bool, linear_eps: bool = False, max_out: int = 1, extra: tuple = ()) -> Tensor:
     if not _is_fake(x):
         _require_cuda(x, "B-cos module")
     x32 = x.float().contiguous()
-    lp = cache.get(weight, bias, eff_weight_fn, tuple(x32.shape), stride, pad, b, linear_eps, max_out)
+    lp = cache.get(weight, bias, eff_weight_fn, tuple(x32.shape), stride, pad, b, linear_eps, max_out, extra)
     want_grad = torch.is_grad_enabled() and x.requires_grad
     y = torch.ops.bcos_b200.bcos_map(x32, _handle_of(lp), bool(detach), bool(want_grad))[0]
     return y if x.dtype == torch.float32 else y.to(x.dtype)

@@ -37,25 +37,25 @@ class BcosAttentionPool2d(DetachableModule):
         return new
 
     @staticmethod
-    def _plain(x: Tensor, cache, weight: Tensor, key_tensor: Tensor) -> Tensor:
+    def _plain(x: Tensor, cache, weight: Tensor, key_tensor: Tensor, extra: tuple = ()) -> Tensor:
         lead = x.shape[:-1]
-        y = R.bcos_map(x.reshape(-1, x.shape[-1], 1, 1), cache, key_tensor, None, lambda: weight[:, :, None, None], 1, 0, 1.0, True)
+        y = R.bcos_map(x.reshape(-1, x.shape[-1], 1, 1), cache, key_tensor, None, lambda: weight[:, :, None, None], 1, 0, 1.0, True,
+                       extra=extra)
         return y.reshape(*lead, weight.shape[0])
 
     def forward(self, x):
         if self.attn_unpool:
             return self._forward_unpool(x)
-        for lin in (self.q_proj, self.k_proj, self.v_proj, self.c_proj):
-            if getattr(lin, "bias", None) is not None:
-                raise NotImplementedError("bcos_b200: attention pooling is built bias-free (all registered configs strip biases)")
+        # like the reference's pooled path (bcosattnpool.py:40-58: in_proj_bias=None, out_proj_bias=None) the projections' biases,
+        # if any, are NOT used here
         n, c = x.shape[0], x.shape[1]
         t = x.flatten(start_dim=2).permute(0, 2, 1)                        # N (HW) C
         t = torch.cat([t.mean(dim=1, keepdim=True), t], dim=1)             # N (HW+1) C ; no positional embedding (:33-34)
         wqkv = torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], 0)
-        qkv = self._plain(t, self._qkv_cache, wqkv, self.v_proj.weight)
+        qkv = self._plain(t, self._qkv_cache, wqkv, self.v_proj.weight, extra=(self.q_proj.weight, self.k_proj.weight))
         dh = c // self.num_heads
         # every token attends, only the query of the mean token (index 0) is used; q, k frozen in explanation mode
-        o = frozen_attention(qkv, self.num_heads, dh ** -0.5, True)[:, 0]
+        o = frozen_attention(qkv, self.num_heads, dh ** -0.5, self.detach)[:, 0]      # backward outside explanation mode raises
         cw = self.c_proj.weight if isinstance(self.c_proj, nn.Linear) else self.c_proj.linear.weight
         return self._plain(o, self._out_cache, cw, cw)                     # c_proj acts as a plain linear (:56)
 

@@ -111,6 +111,7 @@ class BcosConv2d(DetachableModule):
             raise NotImplementedError("bcos_b200: MaxOut needs out_channels % 8 == 0")
         b = float(self.b.detach()) if isinstance(self.b, torch.Tensor) else float(self.b)
         lin = self.linear
+        extra = (getattr(lin, "scale", None), getattr(lin, "use_weight_norm", None))     # what else the effective weight depends on
         k, st, pd = _single(self.kernel_size), _single(self.stride), _single(self.padding)
         if k == st and pd == 0 and k * k > 64:
             # patch-embedding convolution (CLIP ViT conv1: 16x16 / 32x32 non-overlapping patches): the same B-cos transform is
@@ -121,9 +122,9 @@ class BcosConv2d(DetachableModule):
             xp = in_tensor.reshape(n, c, h // k, k, w // k, k).permute(0, 1, 3, 5, 2, 4).reshape(n, c * k * k, h // k, w // k)
             return R.bcos_map(xp, self._cache, lin.weight, getattr(lin, "bias", None),
                               lambda: self._effective_weight().reshape(lin.weight.shape[0], c * k * k, 1, 1), 1, 0, b, self.detach,
-                              max_out=self.max_out)
+                              max_out=self.max_out, extra=extra)
         return R.bcos_map(in_tensor, self._cache, lin.weight, getattr(lin, "bias", None), self._effective_weight,
-                          st, pd, b, self.detach, max_out=self.max_out)
+                          st, pd, b, self.detach, max_out=self.max_out, extra=extra)
 
     def calc_patch_norms(self, in_tensor: Tensor) -> Tensor:
         """||patch|| per output position, [N,1,Ho,Wo] (bcosconv2d.py:196-231) through bcosk_patch_inv_norm."""
@@ -132,12 +133,8 @@ class BcosConv2d(DetachableModule):
         x = in_tensor.float().contiguous()
         nb, c, h, w = x.shape
         k, s, p = _single(self.kernel_size), _single(self.stride), _single(self.padding)
-        cp = (c + 7) // 8 * 8
-        buf = torch.empty(nb, h, w, cp, dtype=torch.bfloat16, device=x.device)
         sq = torch.empty(nb * h * w, dtype=torch.float32, device=x.device)
-        L.nchw_to_nhwc16(x, buf, cp, 1, 1, None, sq)
-        # exact fp32 sums of squares (the bridge squares what it stored): recompute from x for the public helper
-        sq = (x * x).sum(1).reshape(-1).contiguous()
+        L.pixel_sqsum_nchw_f32(x, sq)            # exact fp32 sums of squares per pixel
         oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
         inv = torch.empty(nb * oh * ow, dtype=torch.float32, device=x.device)
         L.patch_inv_norm(sq, 1, nb, h, w, k, k, s, p, 1e-6, 0.0, inv, oh, ow)

@@ -516,6 +516,16 @@ int bcosk_stem_im2col_u8(const uint8_t* x, int32_t nb, int32_t h, int32_t w, int
 int bcosk_seed_from_nchw(const float* g, int32_t nb, int32_t c, int32_t h, int32_t w, float seed_scale, const void* mul1,
                          int32_t mul1_f32, void* out1, const uint32_t* mask2, const void* mul2, int32_t mul2_f32, void* out2,
                          int32_t planes, int32_t dtype, void* stream);
+/* Strided movers of the module-level path.  zero_insert: dst[img, s*p, s*q, :] = src[img, p, q, :] (row_elems 16-bit elements per pixel,
+ * a multiple of 8; dst [nb, h, w, row_elems] is zero elsewhere and stays so): the zero-inserted gradient of a strided k x k conv.
+ * nhwc_scatter_nchw_f32: out[img, ch, s*p, s*q] = y[img, p, q, ch] (y as in bcosk_nhwc_to_nchw_f32; out [nb, c, h, w] zero elsewhere):
+ * the data gradient of a strided 1x1 conv.  pixel_sqsum_nchw_f32: sq[img, pix] = sum_ch x[img, ch, pix]^2 (calc_patch_norms
+ * bcosconv2d.py:196-231 on the reference's own NCHW fp32 layout). */
+int bcosk_zero_insert_nhwc(const void* src, int32_t nb, int32_t oh, int32_t ow, int32_t row_elems, void* dst, int32_t h, int32_t w,
+                           int32_t stride, void* stream);
+int bcosk_nhwc_scatter_nchw_f32(const void* y, int32_t y_f32, int32_t nb, int32_t c, int32_t oh, int32_t ow, int32_t ld, int32_t planes,
+                                int32_t dtype, float* out, int32_t h, int32_t w, int32_t stride, void* stream);
+int bcosk_pixel_sqsum_nchw_f32(const float* x, int32_t nb, int32_t c, int64_t hw, float* sq, void* stream);
 /* out = relu?((x * alpha[c] + beta[c]) * smul + sadd) on NCHW fp32: batch_norm_uncentered_2d (eval / after statistics)
  * batchnorm_uncentered.py:45-58 and LogitLayer.forward logitlayer.py:22-27 (alpha = beta = NULL) */
 int bcosk_scale_bias_nchw(const float* x, int32_t nb, int32_t c, int64_t hw, const float* alpha, const float* beta, float smul,
