@@ -266,8 +266,8 @@ def vit_contrib_map(g, x, p, inv_std6, out_scale, cmap, grad6) -> None:
     check(fn(_p(g), _p(x), nb, h, w, p, _f6(inv_std6), C.c_float(out_scale), _p(cmap), _p(grad6), _stream()), "bcosk_vit_contrib_map")
 
 
-def vit_ln_fwd(x, rows, d, planes, w, eps, y, rstd, sq, dtype) -> None:
-    check(load().bcosk_vit_ln_fwd(_p(x), C.c_int64(rows), d, planes, _p(w), C.c_float(eps), _p(y), _p(rstd), _p(sq), dtype, _stream()),
+def vit_ln_fwd(x, rows, d, planes, w, eps, y, rstd, sq, dtype, out_planes=0) -> None:
+    check(load().bcosk_vit_ln_fwd(_p(x), C.c_int64(rows), d, planes, out_planes, _p(w), C.c_float(eps), _p(y), _p(rstd), _p(sq), dtype, _stream()),
           "bcosk_vit_ln_fwd")
 
 

@@ -161,8 +161,8 @@ __global__ void vit_contrib_map_kernel(const float* __restrict__ g, const X* __r
 // ------------------------------------------------------------------------------------------------ LayerNorm forward
 constexpr int LN_MAXV = 4;   // 8-column vectors per lane: d <= 1024
 template <typename T>
-__global__ void vit_ln_fwd_kernel(const T* __restrict__ x, long long rows, int d, int planes, const float* __restrict__ w, float eps,
-                                  T* __restrict__ y, float* __restrict__ rstd_out, float* __restrict__ sq) {
+__global__ void vit_ln_fwd_kernel(const T* __restrict__ x, long long rows, int d, int planes, int out_planes, const float* __restrict__ w,
+                                  float eps, T* __restrict__ y, float* __restrict__ rstd_out, float* __restrict__ sq) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31, nvec = d >> 3;
@@ -190,7 +190,7 @@ __global__ void vit_ln_fwd_kernel(const T* __restrict__ x, long long rows, int d
   }
   const float var = warp_sum(q) / (float)d;            // biased, like F.layer_norm
   const float rstd = 1.0f / sqrtf(var + eps);
-  T* yr = y + row * (long long)planes * d;
+  T* yr = y + row * (long long)out_planes * d;
   float sacc = 0.f;
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i) {
@@ -201,7 +201,7 @@ __global__ void vit_ln_fwd_kernel(const T* __restrict__ x, long long rows, int d
       float o[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] = f[i][k] * rstd * wv[k];
-      store8_row<T>(yr, planes, d, v * 8, o);
+      store8_row<T>(yr, out_planes, d, v * 8, o);
 #pragma unroll
       for (int k = 0; k < 8; ++k) sacc = fmaf(o[k], o[k], sacc);
     }
@@ -452,15 +452,16 @@ extern "C" int bcosk_vit_contrib_map_u8(const float* g, const uint8_t* x, int32_
   return vit_contrib_impl<uint8_t>(g, x, nb, h, w, p, inv_std6, out_scale, cmap, grad6, stream);
 }
 
-extern "C" int bcosk_vit_ln_fwd(const void* x, int64_t rows, int32_t d, int32_t planes, const float* w, float eps, void* y, float* rstd,
-                                float* sq, int32_t dtype, void* stream) {
-  if (!x || !y || !w || !rstd || rows < 1 || d % 8 || d > 256 * LN_MAXV || planes < 1 || planes > 3)
+extern "C" int bcosk_vit_ln_fwd(const void* x, int64_t rows, int32_t d, int32_t planes, int32_t out_planes, const float* w, float eps, void* y,
+                                float* rstd, float* sq, int32_t dtype, void* stream) {
+  if (out_planes == 0) out_planes = planes;
+  if (!x || !y || !w || !rstd || rows < 1 || d % 8 || d > 256 * LN_MAXV || planes < 1 || planes > 3 || out_planes < 1 || out_planes > 3)
     return set_error(BCOSK_EINVAL, "vit_ln_fwd: bad argument (d must be a multiple of 8, <= 1024)");
   const unsigned grid = (unsigned)((rows + 7) / 8);
   VIT_DISPATCH(dtype,
-               (vit_ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, SV(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, d, planes, w, eps,
+               (vit_ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, SV(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, d, planes, out_planes, w, eps,
                                                                              reinterpret_cast<__nv_bfloat16*>(y), rstd, sq)),
-               (vit_ln_fwd_kernel<__half><<<grid, 256, 0, SV(stream)>>>(reinterpret_cast<const __half*>(x), rows, d, planes, w, eps,
+               (vit_ln_fwd_kernel<__half><<<grid, 256, 0, SV(stream)>>>(reinterpret_cast<const __half*>(x), rows, d, planes, out_planes, w, eps,
                                                                       reinterpret_cast<__half*>(y), rstd, sq)))
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;

@@ -176,12 +176,16 @@ class PlanBase:
                   sq_geom: Optional[Tuple[int, int, int, int, int]] = None, lin_bias: Optional[Tensor] = None,
                   sq_eps: Tuple[float, float] = (1e-6, 0.0), flat: bool = False, want_inv: bool = False,
                   max_out: int = 1, scale_mode: Optional[int] = None, want_gain: bool = True,
-                  y_buf: Optional[Tensor] = None, y_col: int = 0) -> Tuple[Act, ConvRec]:
+                  y_buf: Optional[Tensor] = None, y_col: int = 0, a_planes: Optional[int] = None, w_planes: Optional[int] = None,
+                  y_planes: Optional[int] = None, res_planes: Optional[int] = None, hp: Optional[bool] = None) -> Tuple[Act, ConvRec]:
         """One fused launch: B-cos conv (+BN multiplier, +residual, +ReLU).  The patch norm comes from `x.sq`
         (per-pixel sums of squares written by x's producer) and is evaluated inside the kernel; `sq_geom`
         overrides its (h, w, k, stride, pad) when the GEMM geometry is not the convolution's (space-to-depth stem).
         `max_out` = G > 1: the o GEMM columns are o/G groups of G adjacent units; the epilogue keeps the largest unit of each
-        group, scales it and writes o/G columns (y, gain) plus the kept index (`rec.amax`), bcosconv2d.py:166-170."""
+        group, scales it and writes o/G columns (y, gain) plus the kept index (`rec.amax`), bcosconv2d.py:166-170.
+        `a_planes` / `w_planes` / `y_planes` / `res_planes` (default: the plan's `planes`) give the precision planes of the input, the
+        weights, the output and the residual of THIS launch (mixed formats: e.g. a one-plane branch added to a two-plane residual
+        stream); `hp` overrides the choice of the fp32-faithful (plane-aware) kernel."""
         nb = self.nb
         h, wd = x.hw
         o, c, kh, kw = w.shape
@@ -189,13 +193,17 @@ class PlanBase:
         oh = (h + pad_lo + pad_hi - kh) // stride + 1
         ow = (wd + pad_lo + pad_hi - kw) // stride + 1
         M = nb * oh * ow
-        cin_phys = x.t.shape[-1] // self.planes
+        pa = self.planes if a_planes is None else a_planes
+        pw = self.planes if w_planes is None else w_planes
+        segs = P.segments(pa, pw)
+        hp_launch = (self.hp_accum if hp is None else hp)
+        cin_phys = x.t.shape[-1] // pa
         assert c <= cin_phys
         # stride-1 k x k convs over 64 channels with <= 64 outputs (ResNet layer1 conv2): flat-window gather, the zero
         # borders are produced in shared memory by the TMA box (include/bcosk.h a_flat = 2)
         if max_out > 1:
             assert max_out in (2, 4, 8) and o % max_out == 0 and bn is None and not relu and res is None and not want_mask and not flat
-        flat = flat or (self.flat_3x3 and max_out == 1 and self.planes == 1 and not self.hp_accum and stride == 1 and kh == kw and kh > 1
+        flat = flat or (self.flat_3x3 and max_out == 1 and self.planes == 1 and pa == 1 and pw == 1 and not hp_launch and stride == 1 and kh == kw and kh > 1
                         and cin_phys == 64 and kch == 64 and o <= 64 and res is None and not y_f32 and x.t.is_contiguous())
         sq_in = None
         if inv_norm is None and smode != L.BCOSK_SCALE_NONE:
@@ -219,10 +227,14 @@ class PlanBase:
             w = w * alpha.sqrt().to(w.device).view(-1, 1, 1, 1)
             alpha = None
         wt, taps = self._even_taps(P.fwd_weight_taps(w), P.conv_taps(kh, kw), kch)
-        bmat, cpt = self._pack_b(wt, self.planes, kch)
-        block_n = self._block_n(o, bmat.shape[1] // 64)
+        if (pa, pw) == (self.planes, self.planes):
+            bmat, cpt = self._pack_b(wt, self.planes, kch)
+        else:
+            bm, cpt = P.pack_b(wt, pw, kch, self.dt, segs)
+            bmat = self._dev(bm, self.dt)
+        block_n = self._block_n(o, bmat.shape[1] // 64, hp=hp_launch)
         parts = (o + block_n - 1) // block_n
-        yp = 1 if y_f32 else self.planes
+        yp = 1 if y_f32 else (self.planes if y_planes is None else y_planes)
         oy = o // max_out                 # columns that leave the epilogue
         if y_buf is not None:             # the launch writes columns [y_col, y_col + oy) of every plane of a wider tensor (DenseNet features)
             assert tuple(y_buf.shape[:3]) == (nb, oh, ow) and not y_f32 and y_buf.shape[-1] % yp == 0 and y_col % 8 == 0
@@ -259,12 +271,12 @@ class PlanBase:
         self.fwd_ops.append(O.IgemmOp(
             name=name, a=x.t, b=bmat, n=o, lo=(-pad_lo, -pad_lo),
             up=(pad_hi - (kw - 1), pad_hi - (kh - 1)), stride=(stride, stride), op=oh, oq=ow, kch=kch, chunks_per_tap=cpt,
-            taps=taps, seg_a_choff=P.seg_a_offsets(self.planes, cin_phys), seg_b_plane=P.seg_b_planes(self.planes), dtype=self.dt_code,
+            taps=taps, seg_a_choff=[a * cin_phys for a, _ in segs], seg_b_plane=[b for _, b in segs], dtype=self.dt_code,
             mode=L.BCOSK_MODE_FWD, block_n=block_n, scale_mode=smode, b_exp=self.b, relu=relu,
             inv_norm=inv_norm, sq_in=sq_in, sq_geom=sq_geom, sq_eps=sq_eps, alpha=alpha, beta=beta,
             lin_bias=None if lin_bias is None else self._dev(lin_bias),
-            res=None if res is None else res.t, res_planes=self.planes,
-            gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32, hp_accum=self.hp_accum, hp_chunk=self.hp_chunk, flat=flat,
+            res=None if res is None else res.t, res_planes=self.planes if res_planes is None else res_planes,
+            gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32, hp_accum=hp_launch, hp_chunk=self.hp_chunk, flat=flat,
             inv_norm_out=inv_out, max_out=max_out, amax=rec.amax, y_col=y_col,
             algo_flops=2.0 * M * o * float((w != 0).sum().item()) / o))
         rec.algo_flops = self.fwd_ops[-1].algo_flops

@@ -471,9 +471,10 @@ class VitLnFwdOp:
     rstd: Tensor         # [rows] fp32
     sq: Optional[Tensor]  # [1, rows] fp32: sum of the stored outputs squared
     dtype: int
+    out_planes: int = 0  # planes of y (0 = `planes`)
 
     def run(self) -> None:
-        L.vit_ln_fwd(self.x, self.rstd.numel(), self.d, self.planes, self.w, self.eps, self.y, self.rstd, self.sq, self.dtype)
+        L.vit_ln_fwd(self.x, self.rstd.numel(), self.d, self.planes, self.w, self.eps, self.y, self.rstd, self.sq, self.dtype, self.out_planes)
 
 
 @dataclass

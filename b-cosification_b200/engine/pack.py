@@ -40,12 +40,19 @@ def join_planes(t: Tensor, planes: int) -> Tensor:
     return acc
 
 
-def pack_b(wt: Tensor, planes: int, kch: int, dtype: torch.dtype) -> Tuple[Tensor, int]:
-    """wt [n, taps, c] fp32 (one [n, c] matrix per tap) -> (B [n, segs*taps*cpt*kch], chunks_per_tap)."""
+def segments(a_planes: int, b_planes: int) -> List[Tuple[int, int]]:
+    """Plane products kept for operands with a_planes x b_planes precision planes: the canonical list of max(a, b) planes restricted
+    to the planes that exist (1 x 1: a0 b0; 2 x 1: a0 b0 + a1 b0; 1 x 2: a0 b0 + a0 b1; 2 x 2: a0 b0 + a0 b1 + a1 b0; ...)."""
+    return [(a, b) for a, b in SEGMENTS[max(a_planes, b_planes)] if a < a_planes and b < b_planes]
+
+
+def pack_b(wt: Tensor, planes: int, kch: int, dtype: torch.dtype, segs: Sequence[Tuple[int, int]] = None) -> Tuple[Tensor, int]:
+    """wt [n, taps, c] fp32 (one [n, c] matrix per tap) -> (B [n, segs*taps*cpt*kch], chunks_per_tap).  `planes` = precision planes
+    of the weights; `segs` (default SEGMENTS[planes]) = the (a plane, b plane) products the launch walks."""
     n, taps, c = wt.shape
     cpt = (c + kch - 1) // kch
     pl = split_planes(wt, planes, dtype)
-    segs = SEGMENTS[planes]
+    segs = SEGMENTS[planes] if segs is None else list(segs)
     out = torch.zeros(n, len(segs), taps, cpt * kch, dtype=dtype, device=wt.device)
     for s, (_, bp) in enumerate(segs):
         out[:, s, :, :c] = pl[bp]

@@ -429,9 +429,10 @@ int bcosk_vit_contrib_map(const float* g, const float* x, int32_t nb, int32_t h,
 int bcosk_vit_contrib_map_u8(const float* g, const uint8_t* x, int32_t nb, int32_t h, int32_t w, int32_t p, const float* inv_std6,
                              float out_scale, float* cmap, float* grad6, void* stream);
 /* DetachableLayerNorm.forward (centered_norms.py:187-224, bias-free): y = (x - mean) / sqrt(var + eps) * w over d, plane rows in
- * and out; rstd [rows] is kept for the explanation pass, sq [rows] (optional) = sum of the stored outputs squared. */
-int bcosk_vit_ln_fwd(const void* x, int64_t rows, int32_t d, int32_t planes, const float* w, float eps, void* y, float* rstd,
-                     float* sq, int32_t dtype, void* stream);
+ * (`planes`) and out (`out_planes`, 0 = the same: a two-plane residual stream may feed one-plane branch operands); rstd [rows] is
+ * kept for the explanation pass, sq [rows] (optional) = sum of the stored outputs squared. */
+int bcosk_vit_ln_fwd(const void* x, int64_t rows, int32_t d, int32_t planes, int32_t out_planes, const float* w, float eps, void* y,
+                     float* rstd, float* sq, int32_t dtype, void* stream);
 /* Explanation backward of that LayerNorm (variance detached, mean in the graph) fused with the residual-stream add and the gain
  * of the linear layer in front:  G_out = G_in + rstd * (g w - mean_d(g w));  ghat = G_out * gain.
  * g [rows][d] fp32 or one 16-bit plane; G_in / G_out fp32 (G_in, G_out, gain optional); ghat one 16-bit plane (optional). */

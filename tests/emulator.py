@@ -333,7 +333,7 @@ def run_vit_ln_fwd(op: O.VitLnFwdOp) -> None:
     var, mean = torch.var_mean(x, dim=-1, unbiased=False, keepdim=True)
     rstd = 1.0 / (var + op.eps).sqrt()
     y = (x - mean) * rstd * op.w.float()
-    stored = _split_store(op.y, y, op.planes)
+    stored = _split_store(op.y, y, op.out_planes or op.planes)
     op.rstd.copy_(rstd.reshape(-1))
     if op.sq is not None:
         op.sq.view(-1)[:] = (stored ** 2).sum(-1).reshape(-1)

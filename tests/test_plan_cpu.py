@@ -163,6 +163,14 @@ def test_vit_plan_matches_oracle():
     m = OR.parity_metrics(plan.logits, plan.cmap, ref["logits"], ref["contribution_map"])
     print(m)
     assert m["argmax_equal"] and m["logit_rel_err"] < 1e-4 and m["map_cos_min"] > 0.9999, m
+    # mixed operand format: two-plane residual stream, one-plane branch operands (engine/vit.py `branch_planes`)
+    mixed = ViTPlan(arch, sd, 2, planes=2, explain_planes=1, dtype="fp16", seed_scale=4096.0, device="cpu", image_size=64, branch_planes=1)
+    mixed.x_in.copy_(x6)
+    E.run(mixed.fwd_ops)
+    E.run(mixed.bwd_ops)
+    mm = OR.parity_metrics(mixed.logits, mixed.cmap, ref["logits"], ref["contribution_map"])
+    print("mixed", mm)
+    assert mm["argmax_equal"] and mm["logit_rel_err"] < 2e-3 and mm["map_cos_min"] > 0.999, mm
 
 
 def test_densenet_plan_matches_oracle():

@@ -3,8 +3,8 @@ against its torch restatement (tests/emulator.py) on seeded inputs, and the whol
 the reference (tests/golden/simple_vit_{ti,b}_patch16_224_b2.npz).
 
 Tolerances (BASELINE.json north_star): argmax identical, logits <= 2e-3 relative, contribution maps cosine >= 0.999 and
-max-abs <= 1e-3 of the map range - asserted for the contract mode ("parity": two fp16 planes forward, one fp16 plane in the
-linear explanation pass)."""
+max-abs <= 1e-3 of the map range - asserted for the contract modes ("parity": two-plane fp16 residual stream with one-plane
+branch operands, the default; "parity_full": two fp16 planes everywhere; one fp16 plane in the linear explanation pass)."""
 import os
 
 import numpy as np
@@ -97,14 +97,15 @@ def test_vit_fused_plan_matches_golden(bcosk_lib, golden_dir, arch):
     gold = np.load(os.path.join(golden_dir, f"{arch}_b2.npz"))
     sd = synth.synth_state_dict(vit_state_shapes(arch), int(gold["seed"]))
     x6 = synth.to_bcos_input(gold["images_u8"]).cuda()
-    for mode in ("parity", "throughput_fp16", "throughput"):
+    for mode in ("parity", "parity_full", "throughput_fp16", "throughput"):
         plan = ViTPlan(arch, sd, 2, mode=mode, device="cuda")
+        assert plan.bp == (1 if mode != "parity_full" else 2) and plan.sp == (2 if mode.startswith("parity") else 1)
         out = plan.explain(x6)
         torch.cuda.synchronize()
         m = OR.parity_metrics(out["logits"].float().cpu(), out["contribution_map"].float().cpu(), torch.from_numpy(gold["logits"]),
                               torch.from_numpy(gold["contribution_map"]))
         print(f"fused {arch} plan ({mode}) vs reference golden:", m)
-        if mode == "parity":
+        if mode.startswith("parity"):     # "parity": two-plane residual stream + one-plane branches (default); "parity_full": all two planes
             assert m["argmax_equal"] and m["logit_rel_err"] <= 2e-3 and m["map_cos_min"] >= 0.999 and m["map_maxabs_over_range"] <= 1e-3, m
         else:
             assert m["map_cos_min"] >= 0.9, m
