@@ -194,7 +194,7 @@ class PlanBase:
         ow = (wd + pad_lo + pad_hi - kw) // stride + 1
         M = nb * oh * ow
         pa = self.planes if a_planes is None else a_planes
-        pw = self.planes if w_planes is None else w_planes
+        pw = (self.fwd_w_planes or self.planes) if w_planes is None else w_planes
         segs = P.segments(pa, pw)
         hp_launch = (self.hp_accum if hp is None else hp)
         cin_phys = x.t.shape[-1] // pa
@@ -283,6 +283,7 @@ class PlanBase:
         return Act(y, oy, sq, parts), rec
 
     # ------------------------------------------------------------------ stem of the contract-mode plans with uint8 input
+    fwd_w_planes = None    # experiment knob: precision planes of the forward weights (None = the plan's planes); see scripts/exp_w_planes.py
     stem_im2col = True     # parity-mode plans with uint8 input: stem as a GEMM over an exact byte patch matrix (see _stem_fwd_im2col)
 
     def _stem_fwd_im2col(self, name: str, x_u8: Tensor, w: Tensor, w_s2d: Tensor, k: int, stride: int, pad: int, *, bn: Optional[str],
