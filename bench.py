@@ -215,6 +215,19 @@ def main():
     sampler = ClockSampler(local_rank)
     windows = []
 
+    def guarded(what, fn):
+        """The extra records must never cost the headline line: a failure in one of them is recorded (single-rank run) instead of
+        ending the run.  With several ranks the exception propagates - a rank that silently skipped a barrier would hang the others."""
+        try:
+            return fn()
+        except Exception as e:  # noqa: BLE001
+            if world > 1:
+                raise
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+            print(f"[bench] extra record `{what}` failed: {type(e).__name__}: {e}", file=sys.stderr)
+            return {"error": f"{type(e).__name__}: {e}"}
+
     # ---------------- optional extra record: the opt-in bf16 x1 throughput mode (BASELINE's named format), device resident -------
     thr = None
     if args.mode != "throughput" and not args.no_throughput_record:
@@ -231,22 +244,23 @@ def main():
     # ---------------- extra record: the fine-tuning step (config 5), batch sharded, gradients all-reduced over NCCL ----------------
     train = None
     if not args.no_train_record:
-        train = measure_train_step(args, dev, rank, world, barrier, max_over_ranks)
+        train = guarded("train_step", lambda: measure_train_step(args, dev, rank, world, barrier, max_over_ranks))
 
     # ---------------- extra record: BASELINE config 4, the B-cos CLIP RN50 image encoder (embedding + explanation, batch 512) ----
     clip = None
     if not args.no_clip_record:
-        clip = measure_clip_rn50(args, dev, world, barrier, max_over_ranks)
+        clip = guarded("clip_rn50", lambda: measure_clip_rn50(args, dev, world, barrier, max_over_ranks))
 
     # ---------------- extra record: BASELINE config 3, B-cosified SimpleViT-Ti/16 and ViT-B/16 forward + explanation at 224^2 ------
     vit = None
     if not args.no_vit_record:
-        vit = [measure_vit(args, arch, dev, world, barrier, max_over_ranks) for arch in ("simple_vit_ti_patch16_224", "simple_vit_b_patch16_224")]
+        vit = [guarded("vit", lambda a=arch: measure_vit(args, a, dev, world, barrier, max_over_ranks))
+               for arch in ("simple_vit_ti_patch16_224", "simple_vit_b_patch16_224")]
 
     # ---------------- extra record: B-cosified DenseNet-121 (the other network of BASELINE config 5) forward + explanation -----------
     dense = None
     if not args.no_densenet_record:
-        dense = measure_densenet(args, dev, world, barrier, max_over_ranks)
+        dense = guarded("densenet121", lambda: measure_densenet(args, dev, world, barrier, max_over_ranks))
 
     plan = synthetic_resnet_plan(args.arch, B, mode=args.mode, device=dev, input_u8=True)
     prec = plan.precision
