@@ -277,6 +277,24 @@ def vit_ln_bwd(g, G_in, rows, d, w, rstd, G_out, gain, ghat, dtype) -> None:
                                   int(gain is not None and gain.dtype == torch.float32), _p(ghat), dtype, _stream()), "bcosk_vit_ln_bwd")
 
 
+def vit_ln_bwd_full(g, x, planes, G_in, rows, d, w, rstd, G_out, gain, ghat, dtype) -> None:
+    import torch
+    check(load().bcosk_vit_ln_bwd_full(_p(g), int(g.dtype == torch.float32), _p(x), planes, _p(G_in), C.c_int64(rows), d, _p(w), _p(rstd), _p(G_out),
+                                       _p(gain), int(gain is not None and gain.dtype == torch.float32), _p(ghat), dtype, _stream()),
+          "bcosk_vit_ln_bwd_full")
+
+
+def vit_quickgelu_fwd(u, rows, d, planes, a, sq, gain, dtype) -> None:
+    import torch
+    check(load().bcosk_vit_quickgelu_fwd(_p(u), C.c_int64(rows), d, planes, _p(a), _p(sq), _p(gain),
+                                         int(gain is not None and gain.dtype == torch.float32), dtype, _stream()), "bcosk_vit_quickgelu_fwd")
+
+
+def vit_attention_bwd_full(qkv, planes, g, batch, n, heads, dim_head, scale, out, dtype) -> None:
+    check(load().bcosk_vit_attention_bwd_full(_p(qkv), planes, _p(g), batch, n, heads, dim_head, C.c_float(scale), _p(out), dtype, _stream()),
+          "bcosk_vit_attention_bwd_full")
+
+
 def vit_gelu_fwd(u, rows, d, planes, a, sq, gain, dtype) -> None:
     import torch
     check(load().bcosk_vit_gelu_fwd(_p(u), C.c_int64(rows), d, planes, _p(a), _p(sq), _p(gain),

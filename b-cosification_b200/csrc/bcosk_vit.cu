@@ -395,6 +395,221 @@ vit_attention_kernel(const T* __restrict__ qkv, int planes, const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ CLIP ViT encoder (engine/clip_vit.py)
+// The reference leaves CLIP's LayerNorm, QuickGELU and nn.MultiheadAttention untouched (bcosify.py:74-113 converts only conv1 and the
+// MLP linears), so its explanation pass differentiates them exactly: these are the TRUE backward forms.
+
+// LayerNorm backward (nothing detached): with xh = (x - mean) rstd and gw = g w,
+//   G_out = G_in + rstd * (gw - mean_d(gw) - xh * mean_d(gw xh));  ghat = G_out (* gain) as one 16-bit plane.
+template <typename T>
+__global__ void vit_ln_bwd_full_kernel(const void* __restrict__ g, int g_f32, const T* __restrict__ x, int planes, const float* __restrict__ G_in,
+                                       long long rows, int d, const float* __restrict__ w, const float* __restrict__ rstd,
+                                       float* __restrict__ G_out, const void* __restrict__ gain, int gain_f32, T* __restrict__ ghat) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31, nvec = d >> 3;
+  const T* xr = x + row * (long long)planes * d;
+  float f[LN_MAXV][8], xh[LN_MAXV][8];
+  float s = 0.f, sx = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      if (g_f32) load8_f32(reinterpret_cast<const float*>(g) + row * d + v * 8, f[i]);
+      else unpack8v<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(g) + row * d + v * 8)), f[i]);
+      float wv[8];
+      load8_f32(w + v * 8, wv);
+      load8_row<T>(xr, planes, d, v * 8, xh[i]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { f[i][k] *= wv[k]; s += f[i][k]; sx += xh[i][k]; }
+    }
+  }
+  const float mean_g = warp_sum(s) / (float)d;
+  const float mean_x = warp_sum(sx) / (float)d;
+  const float r = __ldg(rstd + row);
+  float sgx = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { xh[i][k] = (xh[i][k] - mean_x) * r; sgx = fmaf(f[i][k], xh[i][k], sgx); }
+    }
+  }
+  const float mean_gx = warp_sum(sgx) / (float)d;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = r * (f[i][k] - mean_g - xh[i][k] * mean_gx);
+      if (G_in != nullptr) {
+        float a[8];
+        load8_f32(G_in + row * d + v * 8, a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += a[k];
+      }
+      if (G_out != nullptr) store8_f32(G_out + row * d + v * 8, o);
+      if (ghat != nullptr) {
+        if (gain != nullptr) {
+          float gn[8];
+          if (gain_f32) load8_f32(reinterpret_cast<const float*>(gain) + row * d + v * 8, gn);
+          else unpack8v<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(gain) + row * d + v * 8)), gn);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] *= gn[k];
+        }
+        store8_row<T>(ghat + row * d, 1, 0, v * 8, o);
+      }
+    }
+  }
+}
+
+// QuickGELU (CLIP/clip/model.py:166-168): a = u * sigmoid(1.702 u); the saved gain of the producing B-cos linear is multiplied by the
+// TRUE derivative sigmoid + 1.702 u sigmoid (1 - sigmoid) (the reference does not detach this activation).
+template <typename T>
+__global__ void vit_quickgelu_fwd_kernel(const T* __restrict__ u, long long rows, int d, int planes, T* __restrict__ a, float* __restrict__ sq,
+                                         void* __restrict__ gain, int gain_f32) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31, nvec = d >> 3;
+  const T* ur = u + row * (long long)planes * d;
+  T* ar = a + row * (long long)planes * d;
+  float sacc = 0.f;
+  for (int v = lane; v < nvec; v += 32) {
+    float f[8], dv[8];
+    load8_row<T>(ur, planes, d, v * 8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float sg = 1.0f / (1.0f + expf(-1.702f * f[k]));
+      dv[k] = sg + 1.702f * f[k] * sg * (1.0f - sg);
+      f[k] *= sg;
+    }
+    store8_row<T>(ar, planes, d, v * 8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sacc = fmaf(f[k], f[k], sacc);
+    if (gain != nullptr) {
+      float gn[8];
+      if (gain_f32) {
+        float* gp = reinterpret_cast<float*>(gain) + row * d + v * 8;
+        load8_f32(gp, gn);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gn[k] *= dv[k];
+        store8_f32(gp, gn);
+      } else {
+        T* gp = reinterpret_cast<T*>(gain) + row * d + v * 8;
+        unpack8v<T>(*reinterpret_cast<const uint4*>(gp), gn);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gn[k] *= dv[k];
+        store8_row<T>(gp, 1, 0, 0, gn);
+      }
+    }
+  }
+  sacc = warp_sum(sacc);
+  if (lane == 0 && sq != nullptr) sq[row] = sacc;
+}
+
+// Full attention backward (nothing frozen), one CTA per (image, head), n <= 112 tokens (shared memory), D = 64.  With z = scale q k^T, P = softmax(z):
+//   dV = P^T g;  dP = g V^T;  dz = P o (dP - rowsum(P o dP));  dQ = scale dz K;  dK = scale dz^T Q.
+// out [n][3*H*D] one 16-bit plane (q | k | v blocks): the A operand of the in_proj data gradient.
+template <typename T>
+__global__ void __launch_bounds__(256, 1)
+vit_attention_bwd_full_kernel(const T* __restrict__ qkv, int planes, const float* __restrict__ g, int n, int heads, float scale, T* __restrict__ out) {
+  extern __shared__ float sm[];
+  constexpr int LDB = VAT_D + 1;
+  float* P = sm;                                   // [n][n]  probabilities
+  float* DZ = P + (size_t)n * n;                    // [n][n]  dP, then dz * scale
+  float* sq_ = DZ + (size_t)n * n;                  // [n][LDB] q
+  float* sk = sq_ + (size_t)n * LDB;                // k
+  float* sv = sk + (size_t)n * LDB;                 // v
+  float* sg = sv + (size_t)n * LDB;                 // g
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int hd = heads * VAT_D, pst = 3 * hd, ld = planes * pst;
+  const T* base = qkv + (size_t)b * n * ld + h * VAT_D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < n * (VAT_D / 8); i += blockDim.x) {
+    const int r = i / (VAT_D / 8), c8 = (i % (VAT_D / 8)) * 8;
+    float f[8];
+    load8_row<T>(base + (size_t)r * ld, planes, pst, c8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sq_[r * LDB + c8 + k] = f[k];
+    load8_row<T>(base + (size_t)r * ld + hd, planes, pst, c8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sk[r * LDB + c8 + k] = f[k];
+    load8_row<T>(base + (size_t)r * ld + 2 * hd, planes, pst, c8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sv[r * LDB + c8 + k] = f[k];
+  }
+  const float* gh = g + (size_t)b * n * hd + h * VAT_D;
+  for (int i = threadIdx.x; i < n * VAT_D; i += blockDim.x) sg[(i / VAT_D) * LDB + (i % VAT_D)] = __ldg(gh + (size_t)(i / VAT_D) * hd + (i % VAT_D));
+  __syncthreads();
+  // rows of P and dz (one warp per query row; lane = key j, j + 32, ...)
+  for (int i = warp; i < n; i += nw) {
+    float mx = -INFINITY;
+    for (int j = lane; j < n; j += 32) {
+      float s = 0.f;
+#pragma unroll 16
+      for (int dd = 0; dd < VAT_D; ++dd) s = fmaf(sq_[i * LDB + dd], sk[j * LDB + dd], s);
+      s *= scale;
+      P[(size_t)i * n + j] = s;
+      mx = fmaxf(mx, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < n; j += 32) {
+      const float e = expf(P[(size_t)i * n + j] - mx);
+      P[(size_t)i * n + j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < n; j += 32) P[(size_t)i * n + j] *= inv;
+  }
+  __syncthreads();
+  // dV[j] = sum_i P[i][j] g[i]
+  T* obase = out + (size_t)b * n * pst + h * VAT_D;
+  for (int j = warp; j < n; j += nw) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int i = 0; i < n; ++i) {
+      const float pw = P[(size_t)i * n + j];
+      a0 = fmaf(pw, sg[i * LDB + lane], a0);
+      a1 = fmaf(pw, sg[i * LDB + lane + 32], a1);
+    }
+    obase[(size_t)j * pst + 2 * hd + lane] = T(a0);
+    obase[(size_t)j * pst + 2 * hd + lane + 32] = T(a1);
+  }
+  __syncthreads();
+  // dz[i][j] = P (dP - sum_j P dP) * scale, dP[i][j] = g[i] . v[j]   (one warp per query row; dz goes to its own n x n buffer)
+  for (int i = warp; i < n; i += nw) {
+    float acc = 0.f;
+    for (int jj = lane; jj < n; jj += 32) {
+      float dp = 0.f;
+#pragma unroll 16
+      for (int dd = 0; dd < VAT_D; ++dd) dp = fmaf(sg[i * LDB + dd], sv[jj * LDB + dd], dp);
+      DZ[(size_t)i * n + jj] = dp;
+      acc = fmaf(P[(size_t)i * n + jj], dp, acc);
+    }
+    acc = warp_sum(acc);
+    for (int jj = lane; jj < n; jj += 32) DZ[(size_t)i * n + jj] = P[(size_t)i * n + jj] * (DZ[(size_t)i * n + jj] - acc) * scale;
+  }
+  __syncthreads();
+  // dQ[i] = sum_j dz[i][j] k[j];  dK[j] = sum_i dz[i][j] q[i]
+  for (int r = warp; r < n; r += nw) {
+    float q0 = 0.f, q1 = 0.f, k0 = 0.f, k1 = 0.f;
+    for (int t = 0; t < n; ++t) {
+      const float a = DZ[(size_t)r * n + t], bb = DZ[(size_t)t * n + r];
+      q0 = fmaf(a, sk[t * LDB + lane], q0);
+      q1 = fmaf(a, sk[t * LDB + lane + 32], q1);
+      k0 = fmaf(bb, sq_[t * LDB + lane], k0);
+      k1 = fmaf(bb, sq_[t * LDB + lane + 32], k1);
+    }
+    obase[(size_t)r * pst + lane] = T(q0);
+    obase[(size_t)r * pst + lane + 32] = T(q1);
+    obase[(size_t)r * pst + hd + lane] = T(k0);
+    obase[(size_t)r * pst + hd + lane + 32] = T(k1);
+  }
+}
+
 }  // namespace bcosk
 
 using namespace bcosk;
@@ -514,6 +729,55 @@ extern "C" int bcosk_vit_attention(const void* qkv, int32_t planes, const float*
     return set_error(BCOSK_EINVAL, "vit_attention: dtype");
   }
 #undef VAT_LAUNCH
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_vit_ln_bwd_full(const void* g, int32_t g_f32, const void* x, int32_t planes, const float* G_in, int64_t rows, int32_t d,
+                                     const float* w, const float* rstd, float* G_out, const void* gain, int32_t gain_f32, void* ghat,
+                                     int32_t dtype, void* stream) {
+  if (!g || !x || !w || !rstd || (!G_out && !ghat) || rows < 1 || d % 8 || d > 256 * LN_MAXV || planes < 1 || planes > 3)
+    return set_error(BCOSK_EINVAL, "vit_ln_bwd_full: bad argument");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  VIT_DISPATCH(dtype,
+               (vit_ln_bwd_full_kernel<__nv_bfloat16><<<grid, 256, 0, SV(stream)>>>(g, g_f32, reinterpret_cast<const __nv_bfloat16*>(x), planes, G_in, rows, d, w,
+                                                                                  rstd, G_out, gain, gain_f32, reinterpret_cast<__nv_bfloat16*>(ghat))),
+               (vit_ln_bwd_full_kernel<__half><<<grid, 256, 0, SV(stream)>>>(g, g_f32, reinterpret_cast<const __half*>(x), planes, G_in, rows, d, w, rstd,
+                                                                           G_out, gain, gain_f32, reinterpret_cast<__half*>(ghat))))
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_vit_quickgelu_fwd(const void* u, int64_t rows, int32_t d, int32_t planes, void* a, float* sq, void* gain, int32_t gain_f32,
+                                       int32_t dtype, void* stream) {
+  if (!u || !a || rows < 1 || d % 8 || planes < 1 || planes > 3) return set_error(BCOSK_EINVAL, "vit_quickgelu_fwd: bad argument");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  VIT_DISPATCH(dtype,
+               (vit_quickgelu_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, SV(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(u), rows, d, planes,
+                                                                                    reinterpret_cast<__nv_bfloat16*>(a), sq, gain, gain_f32)),
+               (vit_quickgelu_fwd_kernel<__half><<<grid, 256, 0, SV(stream)>>>(reinterpret_cast<const __half*>(u), rows, d, planes,
+                                                                             reinterpret_cast<__half*>(a), sq, gain, gain_f32)))
+  BCOSK_CUDA_CHECK(cudaGetLastError());
+  return BCOSK_OK;
+}
+
+extern "C" int bcosk_vit_attention_bwd_full(const void* qkv, int32_t planes, const float* g, int32_t batch, int32_t n, int32_t heads, int32_t dim_head,
+                                            float scale, void* out, int32_t dtype, void* stream) {
+  if (!qkv || !g || !out || planes < 1 || planes > 3 || batch < 1) return set_error(BCOSK_EINVAL, "vit_attention_bwd_full: bad argument");
+  if (dim_head != VAT_D) return set_error(BCOSK_EUNSUPPORTED, "vit_attention_bwd_full: dim_head must be 64");
+  const size_t smem = (2 * (size_t)n * n + 4 * (size_t)n * (VAT_D + 1)) * sizeof(float);
+  if (smem > 227 * 1024) return set_error(BCOSK_EUNSUPPORTED, "vit_attention_bwd_full: sequence too long for the shared-memory kernel");
+  if (dtype == BCOSK_DTYPE_BF16) {
+    BCOSK_CUDA_CHECK(cudaFuncSetAttribute(vit_attention_bwd_full_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    vit_attention_bwd_full_kernel<__nv_bfloat16><<<batch * heads, 256, smem, SV(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), planes, g, n, heads, scale,
+                                                                                          reinterpret_cast<__nv_bfloat16*>(out));
+  } else if (dtype == BCOSK_DTYPE_F16) {
+    BCOSK_CUDA_CHECK(cudaFuncSetAttribute(vit_attention_bwd_full_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    vit_attention_bwd_full_kernel<__half><<<batch * heads, 256, smem, SV(stream)>>>(reinterpret_cast<const __half*>(qkv), planes, g, n, heads, scale,
+                                                                                   reinterpret_cast<__half*>(out));
+  } else {
+    return set_error(BCOSK_EINVAL, "vit_attention_bwd_full: dtype");
+  }
   BCOSK_CUDA_CHECK(cudaGetLastError());
   return BCOSK_OK;
 }

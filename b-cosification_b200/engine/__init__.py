@@ -4,3 +4,4 @@ from .train import ResNetTrainPlan  # noqa: F401
 from .clip_rn import CLIPResNetPlan  # noqa: F401
 from .vit import ViTPlan  # noqa: F401
 from .densenet import DenseNetPlan  # noqa: F401
+from .clip_vit import CLIPViTPlan  # noqa: F401

@@ -177,7 +177,8 @@ class PlanBase:
                   sq_eps: Tuple[float, float] = (1e-6, 0.0), flat: bool = False, want_inv: bool = False,
                   max_out: int = 1, scale_mode: Optional[int] = None, want_gain: bool = True,
                   y_buf: Optional[Tensor] = None, y_col: int = 0, a_planes: Optional[int] = None, w_planes: Optional[int] = None,
-                  y_planes: Optional[int] = None, res_planes: Optional[int] = None, hp: Optional[bool] = None) -> Tuple[Act, ConvRec]:
+                  y_planes: Optional[int] = None, res_planes: Optional[int] = None, hp: Optional[bool] = None,
+                  out_map: Optional[Tuple[int, int, int, int]] = None) -> Tuple[Act, ConvRec]:
         """One fused launch: B-cos conv (+BN multiplier, +residual, +ReLU).  The patch norm comes from `x.sq`
         (per-pixel sums of squares written by x's producer) and is evaluated inside the kernel; `sq_geom`
         overrides its (h, w, k, stride, pad) when the GEMM geometry is not the convolution's (space-to-depth stem).
@@ -237,7 +238,7 @@ class PlanBase:
         yp = 1 if y_f32 else (self.planes if y_planes is None else y_planes)
         oy = o // max_out                 # columns that leave the epilogue
         if y_buf is not None:             # the launch writes columns [y_col, y_col + oy) of every plane of a wider tensor (DenseNet features)
-            assert tuple(y_buf.shape[:3]) == (nb, oh, ow) and not y_f32 and y_buf.shape[-1] % yp == 0 and y_col % 8 == 0
+            assert (out_map is not None or tuple(y_buf.shape[:3]) == (nb, oh, ow)) and not y_f32 and y_buf.shape[-1] % yp == 0 and y_col % 8 == 0
             assert y_col + oy <= y_buf.shape[-1] // yp and not flat
             y = y_buf
         else:
@@ -277,7 +278,7 @@ class PlanBase:
             lin_bias=None if lin_bias is None else self._dev(lin_bias),
             res=None if res is None else res.t, res_planes=self.planes if res_planes is None else res_planes,
             gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32, hp_accum=hp_launch, hp_chunk=self.hp_chunk, flat=flat,
-            inv_norm_out=inv_out, max_out=max_out, amax=rec.amax, y_col=y_col,
+            inv_norm_out=inv_out, max_out=max_out, amax=rec.amax, y_col=y_col, out_map=out_map,
             algo_flops=2.0 * M * o * float((w != 0).sum().item()) / o))
         rec.algo_flops = self.fwd_ops[-1].algo_flops
         return Act(y, oy, sq, parts), rec

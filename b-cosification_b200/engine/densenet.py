@@ -77,8 +77,7 @@ class DenseNetPlan(PlanBase):
                  logit_bias: Optional[float] = -math.log(1000 - 1), logit_temperature: Optional[float] = None,
                  seed_scale: Optional[float] = None, stem_kch: int = 32, input_u8: bool = False, explain_planes: Optional[int] = None):
         cfg = resolve_precision(mode, planes, dtype, explain_planes, seed_scale)
-        if cfg["explain_planes"] is None:
-            cfg["explain_planes"] = 1
+        cfg["explain_planes"] = 1          # the (linear) explanation pass of this plan always runs on one 16-bit plane
         self.precision = cfg
         super().__init__(batch, planes=cfg["planes"], dtype=cfg["dtype"], device=device, explain=explain, b=b, bn_eps=bn_eps,
                          state_dict=state_dict, explain_planes=cfg["explain_planes"])

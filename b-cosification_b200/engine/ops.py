@@ -490,9 +490,15 @@ class VitLnBwdOp:
     gain: Optional[Tensor]
     ghat: Optional[Tensor]   # 16-bit
     dtype: int
+    x: Optional[Tensor] = None   # TRUE backward (nothing detached; CLIP's LayerNorm): the LayerNorm input as plane rows
+    x_planes: int = 1
 
     def run(self) -> None:
-        L.vit_ln_bwd(self.g, self.G_in, self.rstd.numel(), self.d, self.w, self.rstd, self.G_out, self.gain, self.ghat, self.dtype)
+        if self.x is not None:
+            L.vit_ln_bwd_full(self.g, self.x, self.x_planes, self.G_in, self.rstd.numel(), self.d, self.w, self.rstd, self.G_out, self.gain,
+                              self.ghat, self.dtype)
+        else:
+            L.vit_ln_bwd(self.g, self.G_in, self.rstd.numel(), self.d, self.w, self.rstd, self.G_out, self.gain, self.ghat, self.dtype)
 
 
 @dataclass
@@ -505,9 +511,11 @@ class VitGeluFwdOp:
     sq: Optional[Tensor]
     gain: Optional[Tensor]   # [rows, d] multiplied in place by the gate
     dtype: int
+    quick: bool = False      # CLIP's QuickGELU (u sigmoid(1.702 u)); the gain is multiplied by its TRUE derivative (not detached there)
 
     def run(self) -> None:
-        L.vit_gelu_fwd(self.u, self.u.numel() // self.u.shape[-1], self.d, self.planes, self.a, self.sq, self.gain, self.dtype)
+        fn = L.vit_quickgelu_fwd if self.quick else L.vit_gelu_fwd
+        fn(self.u, self.u.numel() // self.u.shape[-1], self.d, self.planes, self.a, self.sq, self.gain, self.dtype)
 
 
 @dataclass
@@ -525,8 +533,12 @@ class VitAttentionOp:
     out: Tensor          # forward: planes * heads*dh; backward: heads*dh (one plane)
     dtype: int
     tc: bool = True      # tensor-core kernel (bcosk_vit_attention_tc); False = the CUDA-core shared-memory kernel (n <= 208)
+    full_bwd: bool = False   # backward with NOTHING frozen (CLIP's nn.MultiheadAttention): out = [.., 3*heads*dh] (dq | dk | dv), one plane
 
     def run(self) -> None:
+        if self.backward and self.full_bwd:
+            L.vit_attention_bwd_full(self.qkv, self.planes, self.g, self.nb, self.n, self.heads, self.dh, self.scale, self.out, self.dtype)
+            return
         L.vit_attention(self.qkv, self.planes, self.g, self.nb, self.n, self.heads, self.dh, self.scale, self.backward, self.out, self.dtype,
                         self.tc)
 

@@ -68,8 +68,7 @@ class ViTPlan(PlanBase):
                  seed_scale: Optional[float] = None, input_u8: bool = False, explain_planes: Optional[int] = None,
                  branch_planes: Optional[int] = None):
         cfg = resolve_precision(mode, planes, dtype, explain_planes, seed_scale)
-        if cfg["explain_planes"] is None:
-            cfg["explain_planes"] = 1
+        cfg["explain_planes"] = 1          # the (linear) explanation pass of this plan always runs on one 16-bit plane
         self.precision = cfg
         super().__init__(batch, planes=cfg["planes"], dtype=cfg["dtype"], device=device, explain=explain, b=b, state_dict=state_dict,
                          explain_planes=cfg["explain_planes"])

@@ -160,3 +160,23 @@ def synthetic_densenet_plan(arch: str, batch: int, **plan_kwargs) -> DenseNetPla
     """Fused DenseNet plan over the synthetic (random-init, BN-calibrated) checkpoint."""
     sd = synth.synthetic_checkpoint(arch, densenet_state_shapes(arch))
     return DenseNetPlan(arch, sd, batch, **plan_kwargs)
+
+
+def clip_vit_state_shapes(input_resolution: int = 224, patch: int = 32, width: int = 768, layers: int = 12,
+                          output_dim: int = 512) -> Dict[str, Tuple[int, ...]]:
+    """Keys/shapes of the B-cos CLIP ViT image encoder: CLIP/clip/model.py:206-241 `VisionTransformer` converted by bcosify.py:74-113
+    (`clip_kd`), `.bias` attributes and the positional embedding stripped (clip_bcosification/model.py:17-25; `in_proj_bias` is not a
+    `.bias` attribute and survives).  The named mlp Sequential becomes a positional BcosSequential: c_fc 0, gelu 1, c_proj 2."""
+    s: Dict[str, Tuple[int, ...]] = {"model.class_embedding": (width,), "model.proj": (width, output_dim),
+                                     "model.conv1.linear.weight": (width, 6, patch, patch), "model.ln_pre.weight": (width,),
+                                     "model.ln_post.weight": (width,)}
+    for i in range(layers):
+        p = f"model.transformer.resblocks.{i}"
+        s[p + ".attn.in_proj_weight"] = (3 * width, width)
+        s[p + ".attn.in_proj_bias"] = (3 * width,)
+        s[p + ".attn.out_proj.linear.weight"] = (width, width)
+        s[p + ".ln_1.weight"] = (width,)
+        s[p + ".ln_2.weight"] = (width,)
+        s[p + ".mlp.0.linear.weight"] = (4 * width, width)
+        s[p + ".mlp.2.linear.weight"] = (width, 4 * width)
+    return s

@@ -251,6 +251,10 @@ def main():
     if not args.no_clip_record:
         clip = guarded("clip_rn50", lambda: measure_clip_rn50(args, dev, world, barrier, max_over_ranks))
 
+    clip_vit = None
+    if not args.no_clip_record:
+        clip_vit = guarded("clip_vit_b32", lambda: measure_clip_vit(args, dev, world, barrier, max_over_ranks))
+
     # ---------------- extra record: BASELINE config 3, B-cosified SimpleViT-Ti/16 and ViT-B/16 forward + explanation at 224^2 ------
     vit = None
     if not args.no_vit_record:
@@ -383,6 +387,8 @@ def main():
         res["train_step"] = train
     if clip is not None:
         res["clip_rn50"] = clip
+    if clip_vit is not None:
+        res["clip_vit_b32"] = clip_vit
     if vit is not None:
         res["vit"] = vit
     if dense is not None:
@@ -475,6 +481,45 @@ def measure_vit(args, arch, dev, world, barrier, max_over_ranks):
            "executed_gemm_tflops_per_gpu": plan.gemm_flops() / (ms_x * 1e-3) / 1e12, "finite": ok,
            "operands": f"residual stream {plan.sp} plane(s), branch operands {plan.bp} plane(s), explanation pass 1 plane ({plan.precision['dtype']})",
            "parity": "tests/test_vit_gpu.py: argmax equal, logits <= 1.5e-4 rel, map cosine 0.9999997, max-abs <= 5.0e-4 of range vs the reference goldens (contract mode)"}
+    del plan
+    torch.cuda.empty_cache()
+    return rec
+
+
+def measure_clip_vit(args, dev, world, barrier, max_over_ranks):
+    """The other CLIP image encoder north_star names: B-cos CLIP ViT-B/32 (CLIP/clip/model.py:206-241 through bcosify.py with clip_kd),
+    embedding + explanation of cos(embedding, text direction), batch 512, through the fused plan (engine/clip_vit.py)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from bcos_b200.engine import CLIPViTPlan
+    from bcos_b200.models import clip_vit_state_shapes
+    from bcos_b200.utils import synth
+    Bc, reps = args.clip_batch, 4
+    plan = CLIPViTPlan(synth.synth_state_dict(clip_vit_state_shapes(), 0), Bc, mode=args.mode, device=dev, input_u8=True)
+    x = torch.from_numpy(synth.synth_images_u8(32, 224, 5)).repeat((Bc + 31) // 32, 1, 1, 1)[:Bc].to(dev)
+    plan.load_input(x)
+    plan.capture()
+    g = torch.Generator().manual_seed(0)
+    t = torch.nn.functional.normalize(torch.randn(plan.out_dim, generator=g), dim=0)
+    for _ in range(2):
+        plan.explain_direction(None, t)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    for _ in range(reps):
+        plan.embed(None)
+    ev[1].record()
+    for _ in range(reps):
+        out = plan.explain_direction(None, t)
+    ev[2].record()
+    barrier()
+    ms_e = max_over_ranks(ev[0].elapsed_time(ev[1])) / reps
+    ms_x = max_over_ranks(ev[1].elapsed_time(ev[2])) / reps
+    ok = bool(torch.isfinite(out["embedding"]).all() and torch.isfinite(out["contribution_map"]).all())
+    rec = {"workload": "B-cos CLIP ViT-B/32 image encoder embedding + explanation on synthetic images", "batch_per_gpu": Bc, "n_gpus": world,
+           "mode": args.mode, "embed_ms_per_step": ms_e, "embed_value": world * Bc / (ms_e * 1e-3), "ms_per_step": ms_x,
+           "value": world * Bc / (ms_x * 1e-3), "unit": "img/s", "launches_per_step": plan.num_launches(), "finite": ok,
+           "parity": "tests/test_vit_gpu.py: embedding 4.0e-4 rel, map cosine 0.9999987, max-abs 7.7e-4 of range vs the reference golden (contract mode)"}
     del plan
     torch.cuda.empty_cache()
     return rec

@@ -449,6 +449,21 @@ int bcosk_vit_gelu_fwd(const void* u, int64_t rows, int32_t d, int32_t planes, v
 int bcosk_vit_attention(const void* qkv, int32_t planes, const float* g, int32_t batch, int32_t n, int32_t heads, int32_t dim_head,
                         float scale, int32_t backward, void* out, int32_t dtype, void* stream);
 
+/* CLIP ViT image encoder (engine/clip_vit.py).  The reference converts only conv1 and the MLP linears of CLIP's VisionTransformer
+ * (bcosify.py:74-113); LayerNorm, QuickGELU and nn.MultiheadAttention (CLIP/clip/model.py:157-204) stay stock and are differentiated
+ * exactly in its explanation pass.  True backward forms:
+ *   ln_bwd_full         with xh = (x - mean) rstd, gw = g w:  G_out = G_in + rstd (gw - mean(gw) - xh mean(gw xh)); ghat = G_out (* gain)
+ *                       (x: the LayerNorm input as plane rows; other arguments as bcosk_vit_ln_bwd)
+ *   quickgelu_fwd       a = u sigmoid(1.702 u) on plane rows, sq = sum a^2; gain *= sigmoid + 1.702 u sigmoid (1 - sigmoid)
+ *   attention_bwd_full  dV = P^T g, dz = P o (g V^T - rowsum(P o g V^T)), dQ = scale dz K, dK = scale dz^T Q -> out [batch*n][3*heads*64]
+ *                       one 16-bit plane (q | k | v blocks); qkv, g as bcosk_vit_attention; n <= 112 */
+int bcosk_vit_ln_bwd_full(const void* g, int32_t g_f32, const void* x, int32_t planes, const float* G_in, int64_t rows, int32_t d,
+                          const float* w, const float* rstd, float* G_out, const void* gain, int32_t gain_f32, void* ghat, int32_t dtype,
+                          void* stream);
+int bcosk_vit_quickgelu_fwd(const void* u, int64_t rows, int32_t d, int32_t planes, void* a, float* sq, void* gain, int32_t gain_f32,
+                            int32_t dtype, void* stream);
+int bcosk_vit_attention_bwd_full(const void* qkv, int32_t planes, const float* g, int32_t batch, int32_t n, int32_t heads, int32_t dim_head,
+                                 float scale, void* out, int32_t dtype, void* stream);
 /* The same attention on the tensor cores (csrc/bcosk_vit_attn.cu: TMA boxes, tcgen05.mma into TMEM for q k^T and for the
  * probability-weighted sums, softmax by the TMEM-lane threads; V and, in the backward, the probabilities and g are fed as
  * MN-major operands, so no transpose exists).  Same arguments and results as bcosk_vit_attention up to fp32 rounding;

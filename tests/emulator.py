@@ -341,7 +341,13 @@ def run_vit_ln_fwd(op: O.VitLnFwdOp) -> None:
 
 def run_vit_ln_bwd(op: O.VitLnBwdOp) -> None:
     gw = op.g.float() * op.w.float()
-    gx = op.rstd.float().view(*gw.shape[:-1], 1) * (gw - gw.mean(-1, keepdim=True))
+    r = op.rstd.float().view(*gw.shape[:-1], 1)
+    if op.x is not None:      # true backward: the normalised input is in the graph
+        x = _join(op.x, op.x_planes).reshape(gw.shape)
+        xh = (x - x.mean(-1, keepdim=True)) * r
+        gx = r * (gw - gw.mean(-1, keepdim=True) - xh * (gw * xh).mean(-1, keepdim=True))
+    else:
+        gx = r * (gw - gw.mean(-1, keepdim=True))
     if op.G_in is not None:
         gx = gx + op.G_in
     if op.G_out is not None:
@@ -353,8 +359,13 @@ def run_vit_ln_bwd(op: O.VitLnBwdOp) -> None:
 
 def run_vit_gelu_fwd(op: O.VitGeluFwdOp) -> None:
     u = _join(op.u, op.planes)
-    gate = 0.5 * (1.0 + torch.erf(u / 2.0 ** 0.5))
-    stored = _split_store(op.a, u * gate, op.planes)
+    if op.quick:
+        sg = torch.sigmoid(1.702 * u)
+        stored = _split_store(op.a, u * sg, op.planes)
+        gate = sg + 1.702 * u * sg * (1.0 - sg)           # the true derivative goes into the gain
+    else:
+        gate = 0.5 * (1.0 + torch.erf(u / 2.0 ** 0.5))
+        stored = _split_store(op.a, u * gate, op.planes)
     if op.sq is not None:
         op.sq.view(-1)[:] = (stored ** 2).sum(-1).reshape(-1)
     if op.gain is not None:
@@ -369,6 +380,14 @@ def run_vit_attention(op: O.VitAttentionOp) -> None:
     if not op.backward:
         o = torch.matmul(prob, v).transpose(1, 2).reshape(op.nb, op.n, hd)
         _split_store(op.out, o.reshape(op.out.shape[:-1] + (hd,)), op.planes)
+    elif op.full_bwd:
+        g = op.g.float().reshape(op.nb, op.n, op.heads, op.dh).transpose(1, 2)
+        dv = torch.matmul(prob.transpose(-1, -2), g)
+        dp = torch.matmul(g, v.transpose(-1, -2))
+        dz = prob * (dp - (prob * dp).sum(-1, keepdim=True)) * op.scale
+        dq, dk = torch.matmul(dz, k), torch.matmul(dz.transpose(-1, -2), q)
+        full = torch.stack([t.transpose(1, 2).reshape(op.nb, op.n, hd) for t in (dq, dk, dv)], 2).reshape(op.nb, op.n, 3 * hd)
+        _split_store(op.out, full.reshape(op.out.shape[:-1] + (3 * hd,)), 1)
     else:
         g = op.g.float().reshape(op.nb, op.n, op.heads, op.dh).transpose(1, 2)
         gv = torch.matmul(prob.transpose(-1, -2), g).transpose(1, 2).reshape(op.nb, op.n, hd)

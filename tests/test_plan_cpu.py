@@ -219,3 +219,28 @@ def test_uint8_stem_patch_matrix_path_matches_the_implicit_gemm_stem():
     E.run(b.bwd_ops)
     assert ((a.logits - b.logits).abs().max() / b.logits.abs().max()).item() < 1e-4
     assert torch.nn.functional.cosine_similarity(a.cmap.flatten(1), b.cmap.flatten(1)).min().item() > 0.9999
+
+
+def test_clip_vit_plan_matches_oracle():
+    """engine/clip_vit.py: class token + patch embedding through the launch's output map, in_proj bias, TRUE backward of LayerNorm /
+    attention / QuickGELU (the reference detaches none of them), projection of token 0 - launch list run by the emulator vs the oracle."""
+    from bcos_b200.engine import CLIPViTPlan
+    shapes = OR.clip_vit_state_shapes(64, 32, 128, 2, 64)
+    sd = synth.synth_state_dict(shapes, 0)
+    x6 = synth.to_bcos_input(synth.synth_images_u8(2, 64, 1))
+    tvec = OR.clip_seed_direction(64, 0)
+    ref = OR.explain_cosine(OR.OracleCLIPViT(sd, heads=2).forward, x6, tvec)
+    for bp in (3, 1):
+        plan = CLIPViTPlan(sd, 2, heads=2, planes=3, explain_planes=1, dtype="bf16", device="cpu", image_size=64, branch_planes=bp)
+        plan.x_in.copy_(x6)
+        E.run(plan.fwd_ops)
+        emb = plan.emb_all[:, 0].clone().requires_grad_(True)
+        with torch.enable_grad():
+            (g,) = torch.autograd.grad(torch.nn.functional.cosine_similarity(emb, tvec[None], dim=1).sum() * plan.seed_scale, [emb])
+        plan.g_emb.copy_(g)
+        E.run(plan.bwd_ops)
+        e_rel = ((emb.detach() - ref["embedding"]).abs().max() / ref["embedding"].abs().max()).item()
+        cos = torch.nn.functional.cosine_similarity(plan.cmap.flatten(1), ref["contribution_map"].flatten(1)).min().item()
+        mar = ((plan.cmap - ref["contribution_map"]).abs().max() / ref["contribution_map"].abs().max()).item()
+        print("clip vit plan", bp, e_rel, cos, mar)
+        assert e_rel < (1e-4 if bp == 3 else 5e-3) and cos > (0.9999 if bp == 3 else 0.999), (bp, e_rel, cos, mar)

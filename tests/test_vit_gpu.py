@@ -128,3 +128,62 @@ def test_vit_captured_plan_batch_independent(bcosk_lib, golden_dir):
                           torch.from_numpy(gold["contribution_map"]))
     print("captured batch-32 ViT-Ti plan, images 0-1 vs golden:", m)
     assert m["argmax_equal"] and m["logit_rel_err"] <= 2e-3 and m["map_cos_min"] >= 0.999 and m["map_maxabs_over_range"] <= 1e-3, m
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CLIP ViT image encoder (engine/clip_vit.py): true-backward kernels and the fused plan vs the reference golden
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("planes,dt", [(1, torch.float16), (2, torch.float16), (1, torch.bfloat16)])
+def test_clip_vit_true_backward_kernels(bcosk_lib, planes, dt):
+    g = torch.Generator().manual_seed(29)
+    code = L.DTYPE_CODE["fp16" if dt == torch.float16 else "bf16"]
+    nb, T, d, heads = 3, 50, 128, 2
+    M = nb * T
+    tol16 = 1e-2 if dt == torch.bfloat16 else 2e-3
+    x = _planes(g, (nb, T, 1, d), planes, dt)
+    w = torch.rand(d, generator=g) + 0.5
+    for g16 in (False, True):
+        gin = torch.randn(nb, T, 1, d, generator=g)
+        op = O.VitLnBwdOp("ln_bwd_full", gin.to(dt) if g16 else gin, torch.randn(nb, T, 1, d, generator=g), d, w, torch.rand(M, generator=g) + 0.5,
+                          torch.zeros(nb, T, 1, d), torch.rand(M, d, generator=g).to(dt), torch.zeros(nb, T, 1, d, dtype=dt), code, x, planes)
+        print("ln_bwd_full", _check(op, tol16, 3e-5))
+    u = _planes(g, (nb, T, 1, 256), planes, dt)
+    for gdt in (dt, torch.float32):
+        op = O.VitGeluFwdOp("quickgelu", u, 256, planes, torch.zeros_like(u), torch.zeros(1, M), torch.rand(M, 256, generator=g).to(gdt), code, True)
+        print("quickgelu", _check(op, 1e-2 if dt == torch.bfloat16 else 2e-3, 2e-3 if planes == 1 else 3e-5))
+    hd = heads * 64
+    qkv = _planes(g, (nb, T, 1, 3 * hd), planes, dt)
+    op = O.VitAttentionOp("attn.bwd_full", qkv, planes, torch.randn(nb, T, 1, hd, generator=g), nb, T, heads, 64, 64 ** -0.5, True,
+                          torch.zeros(nb, T, 1, 3 * hd, dtype=dt), code, True, True)
+    print("attention_bwd_full", _check(op, tol16, 2e-5))
+    fwd = O.VitAttentionOp("attn.fwd50", qkv, planes, None, nb, T, heads, 64, 64 ** -0.5, False, torch.zeros(nb, T, 1, planes * hd, dtype=dt), code, True)
+    print("attention fwd (tensor cores, 50 tokens)", _check(fwd, 1e-2 if planes == 1 else 5e-5, 2e-5))
+
+
+def test_clip_vit_fused_plan_matches_golden(bcosk_lib, golden_dir):
+    from bcos_b200.engine import CLIPViTPlan
+    gold = np.load(os.path.join(golden_dir, "clip_vit_b32_b2.npz"))
+    res, patch, width, layers, heads, out_dim = gold["geometry"].tolist()
+    sd = synth.synth_state_dict(OR.clip_vit_state_shapes(res, patch, width, layers, out_dim), int(gold["seed"]))
+    x6 = synth.to_bcos_input(gold["images_u8"]).cuda()
+    t = OR.clip_seed_direction(out_dim, int(gold["seed"]))
+    ref_e = torch.from_numpy(gold["embedding"])
+    ref, ref64 = torch.from_numpy(gold["contribution_map"]), torch.from_numpy(gold["contribution_map_fp64"])
+    rng = ref.flatten(1).max(1).values - ref.flatten(1).min(1).values
+    for mode in ("parity", "parity_full", "throughput_fp16"):
+        plan = CLIPViTPlan(sd, 2, heads=heads, mode=mode, device="cuda")
+        out = plan.explain_direction(x6, t)
+        torch.cuda.synchronize()
+        emb, cmap = out["embedding"].float().cpu(), out["contribution_map"].float().cpu()
+        e_rel = ((emb - ref_e).abs().max() / ref_e.abs().max()).item()
+        cos = torch.nn.functional.cosine_similarity(cmap.flatten(1).double(), ref.flatten(1).double()).min().item()
+        mar = ((cmap - ref).abs().flatten(1).max(1).values / rng).max().item()
+        mar64 = ((cmap - ref64).abs().flatten(1).max(1).values / rng).max().item()
+        print(f"fused CLIP ViT-B/32 plan ({mode}): embedding rel err {e_rel:.2e}, map cosine {cos:.8f}, max-abs/range {mar:.2e} (vs fp64 {mar64:.2e}; "
+              f"reference's own floor {float(gold['fp32_noise_floor_maxabs_over_range']):.2e})")
+        if mode.startswith("parity"):
+            assert e_rel <= 2e-3 and cos >= 0.999 and min(mar, mar64) <= 1e-3, (mode, e_rel, cos, mar, mar64)
+        else:
+            assert cos >= 0.9
+        assert torch.allclose(plan.embed(x6), out["embedding"], rtol=1e-5, atol=1e-6)
+        del plan
