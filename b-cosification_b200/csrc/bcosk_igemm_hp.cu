@@ -332,11 +332,12 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         for (int it = 0; it < num_iters; ++it) {
           uint8_t* slot = smem + stage * PAIR_BYTES;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], PAIR_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], aux.paired == 2 ? PAIR_BYTES - A_BYTES : PAIR_BYTES);
           tma_load_im2col_4d(slot, &tmap_a, &full_bar[stage], p.seg_a_choff[0] + kc * p.kch, base_w, base_h, img, p.tap_off_w[tap],
                              p.tap_off_h[tap]);
-          tma_load_im2col_4d(slot + A_BYTES, &tmap_a, &full_bar[stage], p.seg_a_choff[2] + kc * p.kch, base_w, base_h, img,
-                             p.tap_off_w[tap], p.tap_off_h[tap]);
+          if (aux.paired != 2)
+            tma_load_im2col_4d(slot + A_BYTES, &tmap_a, &full_bar[stage], p.seg_a_choff[2] + kc * p.kch, base_w, base_h, img,
+                               p.tap_off_w[tap], p.tap_off_h[tap]);
           tma_load_2d(slot + 2 * A_BYTES, &tmap_b, &full_bar[stage], it * p.kch, n0);
           tma_load_2d(slot + 2 * A_BYTES + B_BYTES, &tmap_b, &full_bar[stage], seg_cols + it * p.kch, n0);
           if (++kc == p.chunks_per_tap) { kc = 0; ++tap; }
@@ -410,10 +411,12 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           umma_f16(tmem_x, da0 + 2, db1 + 2, idesc, 1);
           umma_f16(tmem_x, da0 + 4, db1 + 4, idesc, 1);
           umma_f16(tmem_x, da0 + 6, db1 + 6, idesc, 1);
-          umma_f16(tmem_x, da1, db0, idesc, 1);
-          umma_f16(tmem_x, da1 + 2, db0 + 2, idesc, 1);
-          umma_f16(tmem_x, da1 + 4, db0 + 4, idesc, 1);
-          umma_f16(tmem_x, da1 + 6, db0 + 6, idesc, 1);
+          if (aux.paired != 2) {
+            umma_f16(tmem_x, da1, db0, idesc, 1);
+            umma_f16(tmem_x, da1 + 2, db0 + 2, idesc, 1);
+            umma_f16(tmem_x, da1 + 4, db0 + 4, idesc, 1);
+            umma_f16(tmem_x, da1 + 6, db0 + 6, idesc, 1);
+          }
           umma_commit(&empty_bar[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -881,6 +884,11 @@ static int launch_hp_mode(const bcosk_igemm_params& p, cudaStream_t st) {
   // two-plane operands in the canonical segment order {a0 b0, a0 b1, a1 b0}: paired stages (a0 fetched once)
   aux.paired = (g_hp_stage_boxes & 4) == 0 && p.kch == 64 && p.num_segs == 3 && p.seg_b_plane[0] == 0 && p.seg_b_plane[1] == 1 &&
                p.seg_b_plane[2] == 0 && p.seg_a_choff[0] == p.seg_a_choff[1] && p.seg_a_choff[2] != p.seg_a_choff[0];
+  // one-plane input against two-plane weights {a0 b0, a0 b1} (exact byte patch matrix of the stem, one-plane branch operands added into a
+  // two-plane residual stream): the same paired stage without the a1 box and without the a1 b0 product
+  if (!aux.paired && (g_hp_stage_boxes & 4) == 0 && p.kch == 64 && p.num_segs == 2 && p.seg_b_plane[0] == 0 && p.seg_b_plane[1] == 1 &&
+      p.seg_a_choff[0] == p.seg_a_choff[1])
+    aux.paired = 2;
   const int slot_b = aux.paired ? PAIR_BYTES : SLOT_BYTES;
   const int max_ring = aux.paired ? 2 : 4;        // ring slots that fit two CTAs per SM
   const int iters = aux.paired ? p.num_taps * p.chunks_per_tap : p.num_segs * p.num_taps * p.chunks_per_tap / (STAGE_K / p.kch);

@@ -144,6 +144,27 @@ def test_stem_im2col_u8(bcosk_lib, dt):
         assert U.max_rel_err(dev.inv_norm, op.inv_norm) < 2e-6
 
 
+@pytest.mark.parametrize("k,res", [(1, True), (3, False), (1, False)])
+def test_igemm_forward_mixed_planes(bcosk_lib, k, res):
+    """one-plane input x two-plane weights -> two-plane output (+ two-plane residual) through the plane-aware kernel: the launch format of
+    the ViT plans' adds into the residual stream (segments a0 b0 + a0 b1; paired stages without the a1 box)"""
+    g = torch.Generator().manual_seed(41 + k)
+    plan = PlanBase(2, planes=2, dtype="fp16", device="cpu", explain=True)
+    plan.flat_3x3 = False
+    x = _rand_act(g, 2, 9, 9, 192, 1, dt=torch.float16)
+    w = torch.randn(128, 192, k, k, generator=g) / math.sqrt(192 * k * k)
+    r = _rand_act(g, 2, 9, 9, 128, 2, dt=torch.float16) if res else None
+    plan._conv_fwd("mixed", x, w, 1, k // 2, k // 2, bn=None, relu=False, res=r, want_sq=True, a_planes=1, w_planes=2, y_planes=2,
+                   res_planes=2, hp=True)
+    op = plan.fwd_ops[-1]
+    assert len(op.seg_a_choff) == 2 and op.seg_a_choff == [0, 0] and op.seg_b_plane == [0, 1] and op.y_planes == 2
+    print(_run_and_compare(plan.fwd_ops, tol16=2e-5, tol32=2e-5))
+    # and the all-one-plane branch format on the throughput kernel
+    plan.fwd_ops.clear()
+    plan._conv_fwd("branch", x, w, 1, k // 2, k // 2, bn=None, relu=False, want_sq=True, a_planes=1, w_planes=1, y_planes=1, hp=False)
+    print(_run_and_compare(plan.fwd_ops, tol16=2e-3, tol32=2e-3))
+
+
 MAXOUT_CASES = [
     # name, planes, G, cout (GEMM columns), k, b, bias, y_f32
     ("mo2_1plane_16bit", 1, 2, 128, 3, 2.0, False, False),
