@@ -18,32 +18,33 @@ static inline cudaStream_t SH(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 // C[b] (M x N, row pitch ldc) = alpha * op(A[b]) (M x K) * op(B[b]) (K x N); row-major storage, op = transpose when the flag is set
 // (A stored K x M / B stored N x K).  64 x 64 x 16 tiles, 256 threads, 4 x 4 outputs per thread.
-template <bool TA, bool TB>
+template <bool TA, bool TB, int TM>
 __global__ void __launch_bounds__(256)
 sgemm_batched_kernel(int M, int N, int K, const float* __restrict__ A, long long lda, long long sA, const float* __restrict__ B, long long ldb,
                      long long sB, float* __restrict__ C, long long ldc, long long sC, float alpha) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Bs[16][64 + 4];
+  constexpr int R = TM / 16;                       // outputs per thread and dimension (4 for 64 x 64 tiles, 2 for 32 x 32)
+  __shared__ float As[16][TM + 4];
+  __shared__ float Bs[16][TM + 4];
   const int bz = blockIdx.z;
   A += (size_t)bz * sA;
   B += (size_t)bz * sB;
   C += (size_t)bz * sC;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TM;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][4];
+  float acc[R][R];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < R; ++j) acc[i][j] = 0.f;
   for (int k0 = 0; k0 < K; k0 += 16) {
-    // 1024 elements per tile, 4 per thread; the fast index of the load follows the contiguous axis of the operand
-    for (int e = threadIdx.x; e < 1024; e += 256) {
+    // 16 * TM elements per tile; the fast index of the load follows the contiguous axis of the operand
+    for (int e = threadIdx.x; e < 16 * TM; e += 256) {
       int kk, mm;
-      if (TA) { mm = e & 63; kk = e >> 6; } else { kk = e & 15; mm = e >> 4; }
+      if (TA) { mm = e % TM; kk = e / TM; } else { kk = e & 15; mm = e >> 4; }
       const int m = m0 + mm, k = k0 + kk;
       As[kk][mm] = (m < M && k < K) ? __ldg(TA ? A + (size_t)k * lda + m : A + (size_t)m * lda + k) : 0.f;
       int nn;
-      if (TB) { kk = e & 15; nn = e >> 4; } else { nn = e & 63; kk = e >> 6; }
+      if (TB) { kk = e & 15; nn = e >> 4; } else { nn = e % TM; kk = e / TM; }
       const int n = n0 + nn;
       const int k2 = k0 + kk;
       Bs[kk][nn] = (n < N && k2 < K) ? __ldg(TB ? B + (size_t)n * ldb + k2 : B + (size_t)k2 * ldb + n) : 0.f;
@@ -51,25 +52,25 @@ sgemm_batched_kernel(int M, int N, int K, const float* __restrict__ A, long long
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      float a[4], b[4];
+      float a[R], b[R];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < R; ++i) a[i] = As[kk][ty * R + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+      for (int j = 0; j < R; ++j) b[j] = Bs[kk][tx * R + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < R; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < R; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < R; ++i) {
+    const int m = m0 + ty * R + i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < R; ++j) {
+      const int n = n0 + tx * R + j;
       if (n < N) C[(size_t)m * ldc + n] = alpha * acc[i][j];
     }
   }
@@ -198,9 +199,16 @@ extern "C" int bcosk_sgemm_batched(int32_t trans_a, int32_t trans_b, int32_t m, 
                                    int64_t stride_a, const float* b, int64_t ldb, int64_t stride_b, float* c, int64_t ldc, int64_t stride_c,
                                    int32_t batch, float alpha, void* stream) {
   if (!a || !b || !c || m < 1 || n < 1 || k < 1 || batch < 1 || batch > 65535) return set_error(BCOSK_EINVAL, "sgemm_batched: bad argument");
-  dim3 grid((n + 63) / 64, (m + 63) / 64, batch);
+  // few 64 x 64 tiles (the projections of 512 mean tokens: 128-256 CTAs looping over K = 2048) leave SMs idle: 32 x 32 tiles then
+  const long long tiles64 = (long long)((n + 63) / 64) * ((m + 63) / 64) * batch;
+  const int tm = tiles64 < 2 * 148 ? 32 : 64;
+  dim3 grid((n + tm - 1) / tm, (m + tm - 1) / tm, batch);
   if (grid.y > 65535) return set_error(BCOSK_EUNSUPPORTED, "sgemm_batched: m too large for the grid");
-#define SG(TA_, TB_) sgemm_batched_kernel<TA_, TB_><<<grid, 256, 0, SH(stream)>>>(m, n, k, a, lda, stride_a, b, ldb, stride_b, c, ldc, stride_c, alpha)
+#define SG(TA_, TB_)                                                                                                                   \
+  do {                                                                                                                                 \
+    if (tm == 32) sgemm_batched_kernel<TA_, TB_, 32><<<grid, 256, 0, SH(stream)>>>(m, n, k, a, lda, stride_a, b, ldb, stride_b, c, ldc, stride_c, alpha); \
+    else sgemm_batched_kernel<TA_, TB_, 64><<<grid, 256, 0, SH(stream)>>>(m, n, k, a, lda, stride_a, b, ldb, stride_b, c, ldc, stride_c, alpha);          \
+  } while (0)
   if (trans_a) { if (trans_b) SG(true, true); else SG(true, false); }
   else { if (trans_b) SG(false, true); else SG(false, false); }
 #undef SG

@@ -77,8 +77,8 @@ def test_head_kernels(bcosk_lib):
         return {n: U.compare(op, dev, tol32 if getattr(op, n).dtype == torch.float32 else tol16, [n])[n]
                 for n in U.OUTPUT_FIELDS[type(op)] if getattr(op, n) is not None}
 
-    m, n, k, bt = 70, 45, 37, 3
-    for ta in (False, True):
+    for (m, n, k, bt) in ((70, 45, 37, 3), (300, 520, 37, 8)):       # few tiles -> 32 x 32 tiles; many -> 64 x 64
+      for ta in (False, True):
         for tb in (False, True):
             a = torch.randn(bt, *((k, m) if ta else (m, k)), generator=g)
             b = torch.randn(bt, *((n, k) if tb else (k, n)), generator=g)
