@@ -43,15 +43,22 @@ __global__ void dense_bn_relu_fwd_kernel(const T* __restrict__ x, long long rows
   const T* xr = x + row * (long long)x_ld;
   T* yr = y + row * (long long)planes * c;
   float sacc = 0.f;
+#pragma unroll 2
   for (int v0 = 0; v0 < nvec; v0 += 32) {        // whole warp iterates together (shuffles below)
     const int v = v0 + lane;
     uint32_t bits = 0;
     if (v < nvec) {
       float f[8];
-      d_unpack8<T>(__ldg(reinterpret_cast<const uint4*>(xr + v * 8)), f);
-      for (int pl = 1; pl < planes; ++pl) {
+      uint4 u[3];                                  // all plane loads in flight before the first use
+      u[0] = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+#pragma unroll
+      for (int pl = 1; pl < 3; ++pl)
+        u[pl] = pl < planes ? __ldg(reinterpret_cast<const uint4*>(xr + (size_t)pl * x_pstride + v * 8)) : make_uint4(0u, 0u, 0u, 0u);
+      d_unpack8<T>(u[0], f);
+#pragma unroll
+      for (int pl = 1; pl < 3; ++pl) {
         float g[8];
-        d_unpack8<T>(__ldg(reinterpret_cast<const uint4*>(xr + (size_t)pl * x_pstride + v * 8)), g);
+        d_unpack8<T>(u[pl], g);
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] += g[i];
       }

@@ -35,10 +35,17 @@ __device__ __forceinline__ void unpack8v(const uint4& u, float (&f)[8]) {
 // 8 columns of a plane row -> fp32 (sum of planes)
 template <typename T>
 __device__ __forceinline__ void load8_row(const T* row, int planes, int plane_stride, int col, float (&f)[8]) {
-  unpack8v<T>(__ldg(reinterpret_cast<const uint4*>(row + col)), f);
-  for (int pl = 1; pl < planes; ++pl) {
+  // all plane loads are issued before the first use (at most three planes; a runtime loop would serialise them)
+  uint4 u[3];
+  u[0] = __ldg(reinterpret_cast<const uint4*>(row + col));
+#pragma unroll
+  for (int pl = 1; pl < 3; ++pl)
+    u[pl] = pl < planes ? __ldg(reinterpret_cast<const uint4*>(row + (size_t)pl * plane_stride + col)) : make_uint4(0u, 0u, 0u, 0u);
+  unpack8v<T>(u[0], f);
+#pragma unroll
+  for (int pl = 1; pl < 3; ++pl) {
     float g[8];
-    unpack8v<T>(__ldg(reinterpret_cast<const uint4*>(row + (size_t)pl * plane_stride + col)), g);
+    unpack8v<T>(u[pl], g);        // zero words unpack to +0.0 for both 16-bit formats
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] += g[i];
   }
