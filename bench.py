@@ -136,27 +136,43 @@ class ClockSampler:
 
 
 def cpu_reference_arm(args, steps, warmup):
-    """The reference's own arithmetic on the host cores: the oracle port (the reference is pure Python on ATen and
-    cannot travel to the GPU box; oracle/bcos_oracle.py is pinned bit-exactly against it by oracle/make_golden.py)."""
+    """The reference's own CPU implementation of the path on the host cores.  shrebox/B-cosification is pure Python on ATen;
+    its unmodified hot-path modules travel to the GPU box as the build artefact oracle/_ref/bcos_reference.zip (recipe:
+    oracle/stage_ref.py) and are run through the reference's own BcosifyNetwork / explanation_mode (kind "reference").
+    Without the archive (and without /root/reference) the oracle port runs instead (kind "port"; pinned bit-exactly against
+    the reference by oracle/make_golden.py)."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import bcos_oracle as OR
+    import refload
     from bcos_b200.models import resnet_state_shapes
     from bcos_b200.utils import synth
     if torch.get_num_threads() < _host_threads():
         torch.set_num_threads(_host_threads())
     sd = synth.synthetic_checkpoint(args.arch, resnet_state_shapes(args.arch))
     x6 = synth.to_bcos_input(synth.synth_images_u8(args.cpu_batch, 224, 7))
-    model = OR.OracleResNet(args.arch, sd)
+    kind = "port"
+    if refload.available() and not os.environ.get("BCOS_BENCH_CPU_PORT"):
+        import make_golden as G
+        model = G.build_reference_resnet(args.arch)                  # the reference's bcosify.BcosifyNetwork over its ResNetBcos
+        model.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+        model.eval()
+        step = lambda: G.reference_explain_batched(model, x6)        # noqa: E731
+        kind = "reference"
+        what = f"the reference's own modules ({refload.source()})"
+    else:
+        oracle_model = OR.OracleResNet(args.arch, sd)
+        step = lambda: OR.explain_batched(oracle_model.forward, x6)  # noqa: E731
+        what = "oracle port"
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        OR.explain_batched(model.forward, x6)
+        step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    return dict(value=args.cpu_batch * len(times) / total, ms_per_step=1e3 * total / len(times), cores=torch.get_num_threads(),
-                sample=f"{len(times)} steps x {args.cpu_batch} images (forward + batched explanation), fp32, torch CPU")
+    return dict(value=args.cpu_batch * len(times) / total, ms_per_step=1e3 * total / len(times), cores=torch.get_num_threads(), kind=kind,
+                sample=f"{len(times)} steps x {args.cpu_batch} images (forward + batched explanation), fp32, torch CPU, {what}")
 
 
 def main():
@@ -175,7 +191,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "arch": args.arch, "image": 224, "batch_per_step": args.cpu_batch,
                        "note": "bounded sample of the workload: the CPU's best step size (8 images; 32-image steps are ~1.5x slower per image)"},
-            "cpu_baseline": {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "cpu_baseline": {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }), file=real_stdout, flush=True)
         return
@@ -407,7 +423,7 @@ def main():
             json.dump({"batch": B, "arch": args.arch, "mode": args.mode, "step_ms_eager": step_ms_eager, "rows": rows}, fh, indent=1)
     if world == 1 and not args.no_cpu_baseline:
         c = cpu_reference_arm(args, args.cpu_steps, 2)
-        res["cpu_baseline"] = {"value": c["value"], "unit": "img/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]}
+        res["cpu_baseline"] = {"value": c["value"], "unit": "img/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"]}
     print(json.dumps(res), file=real_stdout, flush=True)
     D.shutdown()
 

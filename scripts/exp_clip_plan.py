@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--batches", default="256,512")
     ap.add_argument("--modes", default="parity,throughput")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--layers", default=None, help="write per-launch timings (eager, CUDA events) of the last configuration here")
     a = ap.parse_args()
     g = torch.Generator().manual_seed(0)
     t = torch.nn.functional.normalize(torch.randn(1024, generator=g), dim=0)
@@ -51,6 +52,21 @@ def main():
                               "embed_explain_ms": round(full, 3), "embed_img_s": round(B / emb * 1e3, 1),
                               "embed_explain_img_s": round(B / full * 1e3, 1), "launches_fwd": len(plan.fwd_ops),
                               "launches_bwd": len(plan.bwd_ops)}), flush=True)
+            if a.layers:
+                rows = []
+                for op in plan.fwd_ops + plan.bwd_ops:
+                    op.run()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(3):
+                        op.run()
+                    e1.record()
+                    e1.synchronize()
+                    row = {"name": op.name, "kind": type(op).__name__, "ms": round(e0.elapsed_time(e1) / 3, 4)}
+                    if hasattr(op, "ktot"):
+                        row.update(M=op.M, N=op.n, K=op.ktot, hp=bool(getattr(op, "hp", False)))
+                    rows.append(row)
+                json.dump({"mode": mode, "batch": B, "rows": rows}, open(a.layers, "w"), indent=1)
             del plan
             torch.cuda.empty_cache()
 

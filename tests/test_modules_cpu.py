@@ -92,7 +92,7 @@ def test_clip_vit_mirror_has_the_reference_state_dict_layout():
     assert m.model.positional_embedding is None and blk.mlp[0].linear.bias is None
 
 
-@pytest.mark.skipif(not refload.available(), reason="reference checkout not present (GPU box)")
+@pytest.mark.skipif(not refload.live(), reason="reference checkout not present (GPU box)")
 def test_reference_bcosify_runs_unchanged_on_our_modules():
     """The reference's bcosify.py + bcos/models/standard_models.py, imported unmodified, build the network out of OUR
     modules (registered under the reference's import paths) with the reference's state-dict layout."""

@@ -154,7 +154,7 @@ def test_batched_explain_equals_per_sample(golden_dir):
         assert torch.allclose(ei["contribution_map"][0], eb["contribution_map"][i], rtol=1e-3, atol=1e-9)
 
 
-@pytest.mark.skipif(not refload.available(), reason="reference checkout not present (GPU box)")
+@pytest.mark.skipif(not refload.live(), reason="reference checkout not present (GPU box)")
 def test_oracle_pinned_to_live_reference():
     refload.load()
     from bcos.modules.bcosifyconv2d import BcosifyConv2d
@@ -254,7 +254,7 @@ def test_gradient_to_image_known_answers(golden_dir):
         smooth, pct = kat[name + ".args"].tolist()
         out = OR.gradient_to_image_batched(x6, grad6, int(smooth), float(pct))
         assert torch.equal(out, _t(kat[name + ".rgba"])), name
-        if refload.available():
+        if refload.live():
             refload.load()
             import bcos.common as BC
             ref = np.stack([BC.gradient_to_image(x6[i], grad6[i], smooth=int(smooth), alpha_percentile=float(pct))
@@ -299,7 +299,7 @@ def test_clip_unpool_text_localisation_golden(golden_dir):
         assert ((cmap - ref).abs().max() / ref.abs().max()).item() < 1e-4, p
 
 
-@pytest.mark.skipif(not refload.available(), reason="reference checkout not present (GPU box)")
+@pytest.mark.skipif(not refload.live(), reason="reference checkout not present (GPU box)")
 def test_oracle_train_step_pinned_to_live_reference():
     """the oracle's fine-tuning step (train-mode forward, UniformOffLabelsBCE, autograd, AGC, first AdamW step)
     against the reference's own modules, loss and AGC code on the same weights and batch."""
@@ -340,3 +340,46 @@ def test_oracle_train_step_pinned_to_live_reference():
     for k, v in m.state_dict().items():
         if k.endswith("running_var"):
             assert torch.allclose(v, ref["running_var"][k], rtol=1e-5, atol=1e-8), k
+
+
+@pytest.mark.skipif(not refload.live(), reason="reference checkout not present (GPU box)")
+def test_staged_reference_archive_is_the_reference_and_runs():
+    """oracle/stage_ref.py: the archive the GPU box's CPU legs import holds the checkout's files byte for byte, and the model the
+    reference builds out of it (no checkout in sight) agrees with the oracle port on a small case."""
+    import hashlib
+    import json
+    import subprocess
+    import sys as _sys
+    import zipfile
+    import stage_ref
+    stage_ref.stage(quiet=True)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    man = json.load(open(stage_ref.MANIFEST))
+    assert man["count"] >= 20 and "bcos/modules/bcosconv2d.py" in man["files"] and "bcosify.py" in man["files"]
+    with zipfile.ZipFile(stage_ref.ARCHIVE) as z:
+        assert sorted(z.namelist()) == sorted(man["files"])
+        for rel, digest in man["files"].items():
+            data = z.read(rel)
+            assert hashlib.sha256(data).hexdigest() == digest
+            assert data == open(os.path.join(refload.LIVE, rel), "rb").read(), rel
+    code = """
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import torch, refload
+assert refload.source() == "archive", refload.source()
+import make_golden as G, bcos_oracle as OR
+from bcos_b200.utils import synth
+m = G.build_reference_resnet("resnet18")
+assert ".zip" in sys.modules["bcos.modules.bcosconv2d"].__file__
+sd = synth.synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 3)
+m.load_state_dict(sd, strict=True); m.eval()
+x6 = synth.to_bcos_input(synth.synth_images_u8(2, 64, 5))
+out, grad, cmap = G.reference_explain_batched(m, x6)
+oe = OR.explain_batched(OR.OracleResNet("resnet18", sd).forward, x6)
+pm = OR.parity_metrics(oe["logits"], oe["contribution_map"], out, cmap)
+assert pm["argmax_equal"] and pm["logit_rel_err"] < 1e-5 and pm["map_cos_min"] > 0.99999, pm
+print("ok")
+""" % (root, os.path.join(root, "oracle"))
+    env = dict(os.environ, BCOS_REFERENCE_ROOT="/nonexistent")
+    r = subprocess.run([_sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
