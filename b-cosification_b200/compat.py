@@ -23,6 +23,11 @@ def _find_reference_root(explicit: Optional[str]) -> Optional[str]:
     for c in cands:
         if c and os.path.isfile(os.path.join(c, "bcos", "modules", "bcosconv2d.py")):
             return os.path.abspath(c)
+        if c and c.endswith(".zip") and os.path.isfile(c):        # an archive of the checkout (zipimport resolves archive/sub/dir paths)
+            import zipfile
+            with zipfile.ZipFile(c) as z:
+                if "bcos/modules/bcosconv2d.py" in z.namelist():
+                    return os.path.abspath(c)
     return None
 
 
@@ -40,7 +45,8 @@ def install_as_bcos(reference_root: Optional[str] = None) -> Optional[str]:
     Only `bcos.modules[.*]` and `bcos.common` are replaced.  A real `bcos` package that is already imported stays in place
     (its other subpackages - bcos.models, bcos.data, bcos.experiments, bcos.training - keep working); when none is imported,
     `bcos` becomes a path-only package over the reference checkout (argument, $BCOS_REFERENCE_ROOT, or a sys.path entry that
-    holds bcos/modules/bcosconv2d.py), so `import bcos.models.resnet` etc. resolve to the reference's own files.
+    holds bcos/modules/bcosconv2d.py; a .zip archive of the checkout works too), so `import bcos.models.resnet` etc. resolve to
+    the reference's own files.
     Returns the reference root in use (None: no checkout found, only the replaced modules are importable)."""
     from . import explain, modules
     from .modules import bcosconv2d, bcoslinear, common, logitlayer, norms

@@ -733,6 +733,41 @@ def calibration_file_densenet(arch: str = "densenet121", batch: int = 8, seed: i
     print(f"[calib] wrote {path} ({os.path.getsize(path)/1e3:.0f} kB)")
 
 
+def golden_native(seed: int = 0):
+    """Native B-cos-v2 variants of the reference's model zoo (tests/native_variants.py), run by the reference itself."""
+    refload.load()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import native_variants as V
+    u8 = synth.synth_images_u8(V.BATCH, V.IMAGE, seed + 21)
+    x6 = synth.to_bcos_input(u8)
+    for name in V.VARIANTS:
+        t0 = time.time()
+        torch.manual_seed(0)
+        m = V.build(name)
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(synth.synth_state_dict(shapes, seed), strict=True)
+        if any(isinstance(b, nn.BatchNorm2d) for b in m.modules()):
+            reference_calibrate(m, x6)
+        m.eval()
+        logits, cmap = V.explain_batched(m, x6)
+        m64 = V.build(name)
+        m64.load_state_dict(m.state_dict(), strict=True)
+        m64 = m64.double().eval()
+        l64, c64 = V.explain_batched(m64, x6.double())
+        floor = O.parity_metrics(logits, cmap, l64.float(), c64.float())
+        cal = {k: v for k, v in m.state_dict().items() if k.endswith("running_var")}
+        keys = sorted(cal)
+        out = dict(images_u8=u8, logits=logits.numpy(), contribution_map=cmap.numpy(), logits_fp64=l64.numpy(),
+                   contribution_map_fp64=c64.float().numpy(), seed=np.int64(seed), num_params=np.int64(sum(v.numel() for v in m.state_dict().values())),
+                   fp32_noise_floor_maxabs_over_range=np.float64(floor["map_maxabs_over_range"]),
+                   bn_keys=np.array(keys), bn_sizes=np.array([cal[k].numel() for k in keys], dtype=np.int64),
+                   bn_var=(torch.cat([cal[k].flatten() for k in keys]).numpy() if keys else np.zeros(0, np.float32)))
+        path = os.path.join(GOLD, f"native_{name}.npz")
+        np.savez_compressed(path, **out)
+        print(f"[native {name}] wrote {path} ({os.path.getsize(path)/1e3:.1f} kB) in {time.time()-t0:.1f}s; logits std {logits.std():.4f} "
+              f"pred {logits.argmax(1).tolist()} map range {float(cmap.max()-cmap.min()):.3e}; fp32 vs fp64: {floor}")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="modules,resnet18,resnet50")
@@ -771,3 +806,5 @@ if __name__ == "__main__":
         calibration_file_clip()
     if "calib_densenet" in which:
         calibration_file_densenet()
+    if "native" in which:
+        golden_native()
