@@ -54,6 +54,19 @@ def _single(v) -> int:
     return int(a)
 
 
+def _patch_norms(in_tensor: Tensor, k: int, s: int, p: int) -> Tensor:
+    """sqrt(sum-pool_{k,s,p}(sum_c x^2) + 1e-6), [N,1,Ho,Wo]: exact fp32 per-pixel sums of squares, then bcosk_patch_inv_norm."""
+    from .. import _lib as L
+    x = in_tensor.float().contiguous()
+    nb, c, h, w = x.shape
+    sq = torch.empty(nb * h * w, dtype=torch.float32, device=x.device)
+    L.pixel_sqsum_nchw_f32(x, sq)
+    oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    inv = torch.empty(nb * oh * ow, dtype=torch.float32, device=x.device)
+    L.patch_inv_norm(sq, 1, nb, h, w, k, k, s, p, 1e-6, 0.0, inv, oh, ow)
+    return (1.0 / inv).view(nb, 1, oh, ow)
+
+
 class BcosConv2d(DetachableModule):
     """`out = (w_hat . x) * |cos(x, w_hat)|^(B-1)` (bcosconv2d.py:43-262)."""
 
@@ -94,6 +107,8 @@ class BcosConv2d(DetachableModule):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
+            if k in ("_group_caches", "_group_bias"):
+                continue
             setattr(new, k, R._PlanCache() if k == "_cache" else copy.deepcopy(v, memo))
         return new
 
@@ -104,13 +119,17 @@ class BcosConv2d(DetachableModule):
         return self.forward_impl(in_tensor)
 
     def forward_impl(self, in_tensor: Tensor) -> Tensor:
-        if self.groups != 1 or any(d > 1 for d in self.dilation) or self.padding_mode != "zeros":
-            raise NotImplementedError("bcos_b200: groups > 1, dilation > 1 and non-zero padding modes are not "
-                                      "built (no registered B-cosification config uses them)")
-        if self.max_out > 1 and self.out_channels % 8 != 0:
-            raise NotImplementedError("bcos_b200: MaxOut needs out_channels % 8 == 0")
+        if any(d > 1 for d in self.dilation) or self.padding_mode != "zeros":
+            # the reference's own patch norm (calc_patch_norms, bcosconv2d.py:196-231: a zero-padded, undilated sum pool) does not
+            # cover these either: its output shape / border values disagree with the convolution's
+            raise NotImplementedError("bcos_b200: dilation > 1 and non-zero padding modes are not built (the reference's "
+                                      "calc_patch_norms does not support them; no registered config uses them)")
+        if self.max_out > 1 and (self.out_channels // self.groups) % 8 != 0:
+            raise NotImplementedError("bcos_b200: MaxOut needs (out_channels / groups) % 8 == 0")
         b = float(self.b.detach()) if isinstance(self.b, torch.Tensor) else float(self.b)
         lin = self.linear
+        if self.groups > 1:
+            return self._forward_groups(in_tensor, b)
         extra = (getattr(lin, "scale", None), getattr(lin, "use_weight_norm", None))     # what else the effective weight depends on
         k, st, pd = _single(self.kernel_size), _single(self.stride), _single(self.padding)
         if k == st and pd == 0 and k * k > 64:
@@ -126,19 +145,53 @@ class BcosConv2d(DetachableModule):
         return R.bcos_map(in_tensor, self._cache, lin.weight, getattr(lin, "bias", None), self._effective_weight,
                           st, pd, b, self.detach, max_out=self.max_out, extra=extra)
 
+    def _forward_groups(self, in_tensor: Tensor, b: float) -> Tensor:
+        """groups > 1 (bcosconv2d.py:201-209, 224-229): every group is its own B-cos map -- its filters see only the group's input
+        channels and the patch norm is the group's -- so each runs as one launch plan over a channel slice (own plan cache)."""
+        G, lin = self.groups, self.linear
+        assert self.in_channels % G == 0 and self.out_channels % G == 0
+        if not hasattr(self, "_group_caches") or len(self._group_caches) != G:
+            self._group_caches = [R._PlanCache() for _ in range(G)]
+        cg, og = self.in_channels // G, self.out_channels * self.max_out // G
+        st, pd = _single(self.stride), _single(self.padding)
+        bias = getattr(lin, "bias", None)
+        pad_rows = (-og) % 8                      # launches write a multiple of 8 output columns: zero filters, sliced off again
+        assert pad_rows == 0 or self.max_out == 1
+        outs = []
+        for g in range(G):
+            rows = slice(g * og, (g + 1) * og)
+            extra = (getattr(lin, "scale", None), getattr(lin, "use_weight_norm", None), g)
+
+            def eff(rows=rows):
+                w = self._effective_weight()[rows]
+                return w if pad_rows == 0 else torch.cat([w, w.new_zeros((pad_rows,) + tuple(w.shape[1:]))], 0)
+
+            bg = None
+            if bias is not None and pad_rows == 0:
+                bg = bias[rows]
+            elif bias is not None:              # padded copy kept per (group, bias version): a fresh tensor per call would defeat the plan cache
+                key = (g, bias.data_ptr(), bias._version)
+                store = self.__dict__.setdefault("_group_bias", {})
+                if key not in store:
+                    for old in [k_ for k_ in store if k_[0] == g]:
+                        del store[old]
+                    store[key] = torch.cat([bias.detach()[rows], bias.new_zeros(pad_rows)], 0)
+                bg = store[key]
+            y = R.bcos_map(in_tensor[:, g * cg:(g + 1) * cg], self._group_caches[g], lin.weight, bg, eff, st, pd, b, self.detach,
+                           max_out=self.max_out, extra=extra + ((bias.data_ptr(), bias._version) if bias is not None else ()))
+            outs.append(y if pad_rows == 0 else y[:, :og])
+        return torch.cat(outs, 1)
+
     def calc_patch_norms(self, in_tensor: Tensor) -> Tensor:
-        """||patch|| per output position, [N,1,Ho,Wo] (bcosconv2d.py:196-231) through bcosk_patch_inv_norm."""
+        """||patch|| per output position, [N,1,Ho,Wo] (bcosconv2d.py:196-231) through bcosk_patch_inv_norm; groups > 1: [N,O,Ho,Wo] with
+        the norm of every output channel's own group, like the reference's repeat_interleave."""
         R._require_cuda(in_tensor, "calc_patch_norms")
-        from .. import _lib as L
-        x = in_tensor.float().contiguous()
-        nb, c, h, w = x.shape
         k, s, p = _single(self.kernel_size), _single(self.stride), _single(self.padding)
-        sq = torch.empty(nb * h * w, dtype=torch.float32, device=x.device)
-        L.pixel_sqsum_nchw_f32(x, sq)            # exact fp32 sums of squares per pixel
-        oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
-        inv = torch.empty(nb * oh * ow, dtype=torch.float32, device=x.device)
-        L.patch_inv_norm(sq, 1, nb, h, w, k, k, s, p, 1e-6, 0.0, inv, oh, ow)
-        return (1.0 / inv).view(nb, 1, oh, ow)
+        if self.groups > 1:
+            G, cg = self.groups, self.in_channels // self.groups
+            per = [_patch_norms(in_tensor[:, g * cg:(g + 1) * cg], k, s, p) for g in range(G)]
+            return torch.repeat_interleave(torch.cat(per, 1), self.out_channels // G, dim=1)
+        return _patch_norms(in_tensor, k, s, p)
 
     def extra_repr(self) -> str:
         s = "B={b}"

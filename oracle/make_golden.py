@@ -733,6 +733,40 @@ def calibration_file_densenet(arch: str = "densenet121", batch: int = 8, seed: i
     print(f"[calib] wrote {path} ({os.path.getsize(path)/1e3:.0f} kB)")
 
 
+def golden_groups(seed: int = 5):
+    """Known-answer vectors of grouped B-cos convolutions (bcosconv2d.py:201-209, 224-229: per-group patch norms), by the reference classes."""
+    refload.load()
+    from bcos.modules.bcosconv2d import BcosConv2d
+    from bcos.modules.bcosifyconv2d import BcosifyConv2d
+    g = torch.Generator().manual_seed(4321 + seed)
+    out = {}
+    cases = [
+        # name, cls, cin, cout, k, s, p, b, max_out, groups, H
+        ("conv_bcos_g4", BcosConv2d, 32, 64, 3, 1, 1, 2, 1, 4, 10),
+        ("conv_bcosify_g2_s2", BcosifyConv2d, 16, 32, 3, 2, 1, 2, 1, 2, 13),
+        ("conv_bcos_g2_b1p5_mo2", BcosConv2d, 16, 32, 3, 1, 1, 1.5, 2, 2, 9),
+        ("conv_bcos_depthwise", BcosConv2d, 8, 8, 3, 1, 1, 2, 1, 8, 8),
+        ("conv_bcosify_g4_1x1", BcosifyConv2d, 64, 32, 1, 1, 0, 2, 1, 4, 7),
+    ]
+    for name, cls, cin, cout, k, s, p, b, mo, G, H in cases:
+        mod = cls(cin, cout, kernel_size=k, stride=s, padding=p, b=b, max_out=mo, groups=G)
+        w = torch.randn(mod.linear.weight.shape, generator=g) * 0.2
+        mod.linear.weight.data = w.clone()
+        x = torch.randn(2, cin, H, H, generator=g)
+        y = mod(x)
+        seedg = torch.randn(y.shape, generator=g)
+        mod.set_explanation_mode(True)
+        xg = x.clone().requires_grad_(True)
+        (gx,) = torch.autograd.grad((mod(xg) * seedg).sum(), [xg])
+        norm = mod.calc_patch_norms(x)
+        assert norm.shape[1] == cout
+        out.update({f"{name}.w": w, f"{name}.x": x, f"{name}.y": y.detach(), f"{name}.seed": seedg, f"{name}.gx": gx, f"{name}.norm": norm.detach(),
+                    f"{name}.meta": torch.tensor([cin, cout, k, s, p, b, mo, float(cls is BcosConv2d), G], dtype=torch.float64)})
+    path = os.path.join(GOLD, "modules_groups_kat.npz")
+    np.savez_compressed(path, **{k: v.numpy() for k, v in out.items()})
+    print(f"[groups] wrote {path} ({os.path.getsize(path)/1e3:.1f} kB), {len(cases)} cases")
+
+
 def golden_native(seed: int = 0):
     """Native B-cos-v2 variants of the reference's model zoo (tests/native_variants.py), run by the reference itself."""
     refload.load()
@@ -808,3 +842,5 @@ if __name__ == "__main__":
         calibration_file_densenet()
     if "native" in which:
         golden_native()
+    if "groups" in which:
+        golden_groups()

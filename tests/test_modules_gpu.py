@@ -53,6 +53,27 @@ def test_conv_modules_match_reference(bcosk_lib, kat, name):
         assert _rel(mod.calc_patch_norms(x), _t(kat[name + ".norm"])[:, :1]) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["conv_bcos_g4", "conv_bcosify_g2_s2", "conv_bcos_g2_b1p5_mo2", "conv_bcos_depthwise", "conv_bcosify_g4_1x1"])
+def test_grouped_conv_modules_match_reference(bcosk_lib, golden_dir, name):
+    """groups > 1 (bcosconv2d.py:201-209, 224-229): per-group filters and per-group patch norms, vs the reference's own classes"""
+    kat = np.load(os.path.join(golden_dir, "modules_groups_kat.npz"))
+    cin, cout, k, s, p, b, mo, normed, G = kat[name + ".meta"].tolist()
+    cls = M.BcosConv2d if normed else M.BcosifyConv2d
+    mod = cls(int(cin), int(cout), kernel_size=int(k), stride=int(s), padding=int(p), b=b, max_out=int(mo), groups=int(G)).cuda()
+    assert tuple(mod.linear.weight.shape) == kat[name + ".w"].shape
+    mod.linear.weight.data = _t(kat[name + ".w"])
+    x = _t(kat[name + ".x"])
+    with torch.inference_mode():
+        y = mod(x)
+    tol = 2e-5 if b == 2 else 2e-4
+    assert _rel(y, _t(kat[name + ".y"])) < tol, (name, _rel(y, _t(kat[name + ".y"])))
+    mod.set_explanation_mode(True)
+    xg = x.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad((mod(xg) * _t(kat[name + ".seed"])).sum(), [xg])
+    assert _rel(gx, _t(kat[name + ".gx"])) < tol, (name, _rel(gx, _t(kat[name + ".gx"])))
+    assert _rel(mod.calc_patch_norms(x), _t(kat[name + ".norm"])) < 1e-5
+
+
 @pytest.mark.parametrize("name", ["lin_bcosify", "lin_bcos_normed", "lin_bcos_b1p5_mo2"])
 def test_linear_modules_match_reference(bcosk_lib, kat, name):
     fin, fout, b, mo, normed = kat[name + ".meta"].tolist()
