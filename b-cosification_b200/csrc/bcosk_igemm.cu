@@ -279,7 +279,7 @@ __device__ __forceinline__ void global_store_words(void* ptr, int ncols, const u
 
 // Forward, B=2 scale: branch-free over the 16 column pairs so the compiler can interleave them (all launch-uniform
 // options are folded into data: a zero residual word, an all-ones ReLU mask, ...).
-template <typename T, bool MASK, bool AFFINE>
+template <typename T, bool MASK, bool AFFINE, int ACT = 0>
 __device__ __forceinline__ void epilogue_fwd_fast(const bcosk_igemm_params& p, const RowInfo& ri, int64_t yrow,
                                                   float inv_norm, const float* s_alpha, const float* s_beta, int j, int c0,
                                                   int ncols, const float (&v)[32], float& sq_acc, const EpiTiles& tl, int row) {
@@ -319,6 +319,16 @@ __device__ __forceinline__ void epilogue_fwd_fast(const bcosk_igemm_params& p, c
         // the plan folded sqrt(BN multiplier) into the weights: nothing per channel is left
         t = plain ? make_float2(1.f, 1.f) : make_float2(fabsf(vv.x) * inv_norm, fabsf(vv.y) * inv_norm);
         y = __ffma2_rn(vv, t, Cvt<T>::unpack2(rw[k]));
+      }
+      if (ACT == 1) {      // MyGELU behind the transform: gate = Phi(y), detached in the explanation pass (folded into the gain)
+        const float2 gate = make_float2(0.5f * (1.0f + erff(y.x * 0.70710678118654752440f)),
+                                        0.5f * (1.0f + erff(y.y * 0.70710678118654752440f)));
+        y = __fmul2_rn(y, gate);
+        t = __fmul2_rn(t, gate);
+      } else if (ACT == 2) {   // QuickGELU y sigmoid(1.702 y), NOT detached (CLIP/clip/model.py:166-168): the gain takes its derivative
+        const float2 sg = make_float2(1.0f / (1.0f + expf(-1.702f * y.x)), 1.0f / (1.0f + expf(-1.702f * y.y)));
+        t = __fmul2_rn(t, make_float2(sg.x + 1.702f * y.x * sg.x * (1.0f - sg.x), sg.y + 1.702f * y.y * sg.y * (1.0f - sg.y)));
+        y = __fmul2_rn(y, sg);
       }
       const uint32_t ywk = Cvt<T>::pack2(y.x, y.y);
       const uint32_t m = Pk<T>::gt0_mask(ywk) | relu_off;                          // 0xFFFF per kept half
@@ -414,7 +424,13 @@ __device__ __forceinline__ void epilogue_chunk_fast(const bcosk_igemm_params& p,
                                                     float& sq_acc, const EpiTiles& tl, int row, uint32_t mb) {
   if (MODE == BCOSK_MODE_FWD) {
     const bool affine = p.alpha != nullptr || p.beta != nullptr;
-    if (p.maskbits != nullptr) {
+    if (p.act == 1) {          // (validated: no mask bits, no ReLU)
+      if (affine) epilogue_fwd_fast<T, false, true, 1>(p, ri, yrow, inv_norm, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
+      else epilogue_fwd_fast<T, false, false, 1>(p, ri, yrow, inv_norm, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
+    } else if (p.act == 2) {
+      if (affine) epilogue_fwd_fast<T, false, true, 2>(p, ri, yrow, inv_norm, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
+      else epilogue_fwd_fast<T, false, false, 2>(p, ri, yrow, inv_norm, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
+    } else if (p.maskbits != nullptr) {
       if (affine) epilogue_fwd_fast<T, true, true>(p, ri, yrow, inv_norm, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
       else epilogue_fwd_fast<T, true, false>(p, ri, yrow, inv_norm, s_alpha, s_beta, j, c0, ncols, v, sq_acc, tl, row);
     } else {
@@ -1933,6 +1949,12 @@ static int validate(const bcosk_igemm_params& p) {
   if (p.inv_norm_out && p.mode != BCOSK_MODE_FWD) return set_error(BCOSK_EINVAL, "igemm: inv_norm_out is a forward output");
   if (p.side_mapped && (p.mode != BCOSK_MODE_EXPLAIN || p.add != nullptr))
     return set_error(BCOSK_EINVAL, "igemm: side_mapped needs explain mode without an extra gradient");
+  if (p.act != 0) {
+    if (p.act != 1 && p.act != 2) return set_error(BCOSK_EINVAL, "igemm: act must be 0 (none), 1 (GELU, detached gate) or 2 (QuickGELU)");
+    if (p.mode != BCOSK_MODE_FWD || p.hp_accum || p.y_f32 || p.y_planes != 1 || (p.gain && p.gain_f32) || (p.res && p.res_planes != 1) ||
+        (p.scale_mode != BCOSK_SCALE_B2 && p.scale_mode != BCOSK_SCALE_NONE) || p.lin_bias || p.max_out > 1 || p.relu || p.maskbits)
+      return set_error(BCOSK_EUNSUPPORTED, "igemm: act belongs to a one-plane 16-bit forward launch without ReLU / mask bits / MaxOut / bias");
+  }
   if (p.max_out > 1) {
     if (p.mode != BCOSK_MODE_FWD || (p.max_out != 2 && p.max_out != 4 && p.max_out != 8) || p.n % p.max_out != 0)
       return set_error(BCOSK_EINVAL, "igemm: max_out must be 2, 4 or 8, divide n, and belongs to a forward launch");

@@ -178,7 +178,7 @@ class PlanBase:
                   max_out: int = 1, scale_mode: Optional[int] = None, want_gain: bool = True,
                   y_buf: Optional[Tensor] = None, y_col: int = 0, a_planes: Optional[int] = None, w_planes: Optional[int] = None,
                   y_planes: Optional[int] = None, res_planes: Optional[int] = None, hp: Optional[bool] = None,
-                  out_map: Optional[Tuple[int, int, int, int]] = None) -> Tuple[Act, ConvRec]:
+                  out_map: Optional[Tuple[int, int, int, int]] = None, act: int = 0) -> Tuple[Act, ConvRec]:
         """One fused launch: B-cos conv (+BN multiplier, +residual, +ReLU).  The patch norm comes from `x.sq`
         (per-pixel sums of squares written by x's producer) and is evaluated inside the kernel; `sq_geom`
         overrides its (h, w, k, stride, pad) when the GEMM geometry is not the convolution's (space-to-depth stem).
@@ -278,7 +278,7 @@ class PlanBase:
             lin_bias=None if lin_bias is None else self._dev(lin_bias),
             res=None if res is None else res.t, res_planes=self.planes if res_planes is None else res_planes,
             gain=rec.gain, maskbits=rec.mask, sq_out=sq, y=y, y_planes=yp, y_f32=y_f32, hp_accum=hp_launch, hp_chunk=self.hp_chunk, flat=flat,
-            inv_norm_out=inv_out, max_out=max_out, amax=rec.amax, y_col=y_col, out_map=out_map,
+            inv_norm_out=inv_out, max_out=max_out, amax=rec.amax, y_col=y_col, out_map=out_map, act=act,
             algo_flops=2.0 * M * o * float((w != 0).sum().item()) / o))
         rec.algo_flops = self.fwd_ops[-1].algo_flops
         return Act(y, oy, sq, parts), rec

@@ -46,6 +46,8 @@ class ClipBlockRec:
 
 
 class CLIPViTPlan(PlanBase):
+    fuse_gelu = True     # one-plane branches: QuickGELU inside c_fc's epilogue; False keeps the separate pass
+
     def __init__(self, state_dict: Dict[str, Tensor], batch: int, *, heads: int = 12, mode: Optional[str] = None, planes: Optional[int] = None,
                  dtype: Optional[str] = None, device="cuda", image_size: int = 224, explain: bool = True, want_grad6: bool = False,
                  b: float = 2.0, ln_eps: float = 1e-5, mean=CLIP_MEAN_ADDINVERSE, std=CLIP_STD_ADDINVERSE, seed_scale: Optional[float] = None,
@@ -130,13 +132,19 @@ class CLIPViTPlan(PlanBase):
             x1, r_out = self._conv_fwd(pfx + ".attn.out_proj", Act(o, d), sd[pfx + ".attn.out_proj.linear.weight"][:, :, None, None], 1, 0, 0,
                                        bn=None, relu=False, want_sq=False, scale_mode=NONE, want_gain=False, res=Act(x, d), **self._into_stream())
             y2, rstd2, w2 = self._ln(pfx + ".ln_2", x1.t, pfx + ".ln_2.weight", True, self.bp)
-            u, r_fc = self._conv_fwd(pfx + ".mlp.c_fc", y2, sd[pfx + ".mlp.0.linear.weight"][:, :, None, None], 1, 0, 0, bn=None, relu=False,
-                                     want_sq=False, sq_eps=(0.0, 1e-12), **self._branch())
-            hid = u.c
-            a = self._tok(hid, self.bp)
-            sqa = self._rows()
-            self.fwd_ops.append(O.VitGeluFwdOp(pfx + ".mlp.gelu", u.t, hid, self.bp, a, sqa, r_fc.gain, self.dt_code, True))
-            x2, r_pr = self._conv_fwd(pfx + ".mlp.c_proj", Act(a, hid, sqa, 1), sd[pfx + ".mlp.2.linear.weight"][:, :, None, None], 1, 0, 0,
+            if self.bp == 1 and self.fuse_gelu:
+                # QuickGELU inside c_fc's epilogue (include/bcosk.h `act` = 2): activation, its sums of squares and the gain x QuickGELU'
+                act_in, r_fc = self._conv_fwd(pfx + ".mlp.c_fc", y2, sd[pfx + ".mlp.0.linear.weight"][:, :, None, None], 1, 0, 0, bn=None,
+                                              relu=False, want_sq=True, sq_eps=(0.0, 1e-12), act=2, **self._branch())
+            else:
+                u, r_fc = self._conv_fwd(pfx + ".mlp.c_fc", y2, sd[pfx + ".mlp.0.linear.weight"][:, :, None, None], 1, 0, 0, bn=None, relu=False,
+                                         want_sq=False, sq_eps=(0.0, 1e-12), **self._branch())
+                hid = u.c
+                a = self._tok(hid, self.bp)
+                sqa = self._rows()
+                self.fwd_ops.append(O.VitGeluFwdOp(pfx + ".mlp.gelu", u.t, hid, self.bp, a, sqa, r_fc.gain, self.dt_code, True))
+                act_in = Act(a, hid, sqa, 1)
+            x2, r_pr = self._conv_fwd(pfx + ".mlp.c_proj", act_in, sd[pfx + ".mlp.2.linear.weight"][:, :, None, None], 1, 0, 0,
                                       bn=None, relu=False, want_sq=False, sq_eps=(0.0, 1e-12), res=x1, **self._into_stream())
             self.blocks.append(ClipBlockRec(pfx, x, x1.t, qkv.t, rstd1, rstd2, w1, w2, r_in, r_out, r_fc, r_pr))
             x = x2.t

@@ -80,6 +80,7 @@ class IgemmOp:
                                                # feature tensors: y = the whole block tensor, y_ld = its row pitch); 0 = y is the launch's own
     max_out: int = 1                           # include/bcosk.h `max_out`: groups of adjacent units reduced in the forward epilogue
     amax: Optional[Tensor] = None              # [M, n / max_out] uint8: index of the kept unit
+    act: int = 0                               # include/bcosk.h `act`: 1 = MyGELU, 2 = QuickGELU behind the transform (folded into y and the gain)
 
     # ---- derived ----
     @property
@@ -223,6 +224,7 @@ class IgemmOp:
         p.side_mapped = int(self.side_mapped)
         p.set_ptr("inv_norm_out", self.inv_norm_out)
         p.set_ptr("mul1_sqrt_scale", self.mul1_sqrt_scale)
+        p.act = int(self.act)
         if self.max_out > 1:
             p.max_out = self.max_out
             if self.amax is not None:

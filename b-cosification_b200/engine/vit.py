@@ -61,6 +61,8 @@ class EncoderRec:
 
 
 class ViTPlan(PlanBase):
+    fuse_gelu = True     # one-plane branches: MyGELU inside linear1's epilogue (include/bcosk.h `act`); False keeps the separate pass
+
     def __init__(self, arch: str, state_dict: Dict[str, Tensor], batch: int, *, mode: Optional[str] = None, planes: Optional[int] = None,
                  dtype: Optional[str] = None, device="cuda", image_size: int = 224, patch: int = 16, explain: bool = True,
                  want_grad6: bool = False, b: float = 2.0, ln_eps: float = 1e-5, mean=IMAGENET_MEAN_ADDINVERSE,
@@ -120,9 +122,9 @@ class ViTPlan(PlanBase):
         self.fwd_ops.append(O.VitLnFwdOp(name, x.t, x.c, self.sp, w, self.ln_eps, y, rstd, sq, self.dt_code, self.bp))
         return Act(y, x.c, sq, 1 if want_sq else 0), rstd, w
 
-    def _lin(self, name: str, x: Act, w2d: Tensor, **kw):
+    def _lin(self, name: str, x: Act, w2d: Tensor, want_sq: bool = False, **kw):
         """B-cos linear (bcosifylinear.py:42-95: scale from ||x|| + 1e-12) as a 1x1 launch."""
-        return self._conv_fwd(name, x, w2d[:, :, None, None], 1, 0, 0, bn=None, relu=False, sq_eps=(0.0, 1e-12), want_sq=False, **kw)
+        return self._conv_fwd(name, x, w2d[:, :, None, None], 1, 0, 0, bn=None, relu=False, sq_eps=(0.0, 1e-12), want_sq=want_sq, **kw)
 
     def _branch(self) -> Dict[str, object]:
         """launch format of a branch-internal linear map: `bp` planes in, out and in the weights"""
@@ -161,11 +163,18 @@ class ViTPlan(PlanBase):
             self.fwd_ops.append(O.PixelSqsumOp(pfx + ".attn.core.sq", o, d, bp, self.dt_code, sqo))
             x1, r_out = self._lin(pfx + ".attn.to_out", Act(o, d, sqo, 1), sd[pfx + ".attn.to_out.linear.weight"], res=x, **self._into_stream())
             h2, rstd2, w2 = self._ln(pfx + ".ff.net.norm", x1, pfx + ".ff.net.norm.weight", want_sq=True)
-            u, r1 = self._lin(pfx + ".ff.net.linear1", h2, sd[pfx + ".ff.net.linear1.linear.weight"], **self._branch())
-            a = self._tok(self.mlp, bp)
-            sqa = self._rows()
-            self.fwd_ops.append(O.VitGeluFwdOp(pfx + ".ff.net.act", u.t, self.mlp, bp, a, sqa, r1.gain, self.dt_code))
-            x2, r2 = self._lin(pfx + ".ff.net.linear2", Act(a, self.mlp, sqa, 1), sd[pfx + ".ff.net.linear2.linear.weight"], res=x1,
+            if bp == 1 and self.fuse_gelu:
+                # MyGELU (vit.py:89-113) inside linear1's epilogue: the launch writes the activation, its per-tile sums of squares and
+                # the gain with the (detached) gate folded in - no pass over the [tokens, mlp] tensor in between
+                act_in, r1 = self._lin(pfx + ".ff.net.linear1", h2, sd[pfx + ".ff.net.linear1.linear.weight"], want_sq=True, act=1,
+                                       **self._branch())
+            else:
+                u, r1 = self._lin(pfx + ".ff.net.linear1", h2, sd[pfx + ".ff.net.linear1.linear.weight"], **self._branch())
+                a = self._tok(self.mlp, bp)
+                sqa = self._rows()
+                self.fwd_ops.append(O.VitGeluFwdOp(pfx + ".ff.net.act", u.t, self.mlp, bp, a, sqa, r1.gain, self.dt_code))
+                act_in = Act(a, self.mlp, sqa, 1)
+            x2, r2 = self._lin(pfx + ".ff.net.linear2", act_in, sd[pfx + ".ff.net.linear2.linear.weight"], res=x1,
                                **self._into_stream())
             self.encoders.append(EncoderRec(pfx, qkv.t, rstd1, rstd2, w1, w2, r_out, r1, r2, wqkv[2 * d:3 * d, :, None, None].contiguous()))
             x = x2

@@ -174,6 +174,14 @@ typedef struct bcosk_igemm_params {
    *      0 and 1 both mean "no MaxOut". */
   uint8_t* amax;
   int32_t max_out, amax_ld;
+  /* ---- activation fused behind the B-cos transform (forward launches of the one-plane 16-bit path only).
+   *      act = 1: MyGELU of the ViT MLP (bcos/models/vit.py:89-113: x * Phi(x), the gate Phi(x) = (1 + erf(x / sqrt 2)) / 2
+   *      detached in explanation mode): y <- y * Phi(y) and gain <- gain * Phi(y) before rounding, so y is the activation the next
+   *      linear map reads (sq_out: its sums of squares) and gain is d y / d lin under the detached scale and gate.
+   *      act = 2: QuickGELU of the CLIP ViT MLP (CLIP/clip/model.py:166-168: x * sigmoid(1.702 x), an ordinary torch op that is NOT
+   *      detached in the explanation pass): y <- y * s, gain <- gain * (s + 1.702 y s (1 - s)), s = sigmoid(1.702 y).
+   *      Not combined with relu / maskbits / max_out / lin_bias / fp32 or multi-plane outputs / hp_accum.  0 = none. */
+  int32_t act, act_reserved;
 } bcosk_igemm_params;
 
 int bcosk_igemm(const bcosk_igemm_params* p, void* stream);

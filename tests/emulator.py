@@ -131,6 +131,12 @@ def run_igemm(op: O.IgemmOp) -> None:
         v = D * t + beta
         if op.res is not None:
             v = v + _join(op.res.reshape(M, -1), op.res_planes)
+        if op.act == 1:        # MyGELU behind the transform: gate on the fp32 value, folded into y and the gain before rounding
+            gate = 0.5 * (1.0 + torch.erf(v * 0.70710678118654752440))
+            v, t = v * gate, t * gate
+        elif op.act == 2:      # QuickGELU (not detached): the gain takes the derivative
+            sg = 1.0 / (1.0 + torch.exp(-1.702 * v))
+            v, t = v * sg, t * (sg + 1.702 * v * sg * (1.0 - sg))
         # throughput path (single 16-bit plane): ReLU / mask are decided on the ROUNDED value (packed 16-bit compare) and
         # the sums of squares use the un-rounded fp32 value; the generic path decides on fp32 and squares what it stored
         fast = (not op.y_f32) and op.y_planes == 1 and (op.gain is None or op.gain.dtype != torch.float32) \

@@ -124,6 +124,29 @@ def test_igemm_forward_plain_linear(bcosk_lib, planes):
         print(_run_and_compare(plan.fwd_ops, tol16=BF16_TOL if planes == 1 else 2e-4))
 
 
+@pytest.mark.parametrize("act", [1, 2])
+@pytest.mark.parametrize("dt,n", [("fp16", 384), ("bf16", 128), ("fp16", 64)])
+def test_igemm_forward_fused_gelu(bcosk_lib, dt, n, act):
+    """include/bcosk.h `act` = 1: MyGELU (bcos/models/vit.py:89-113) behind the B-cos transform of a one-plane linear launch - y is the
+    activation, sq_out its per-tile sums of squares, the gain carries the detached gate (the ViT MLP's linear1); `act` = 2: QuickGELU
+    of the CLIP ViT MLP (CLIP/clip/model.py:166-168), whose derivative goes into the gain"""
+    g = torch.Generator().manual_seed(51)
+    tdt = torch.float16 if dt == "fp16" else torch.bfloat16
+    plan = PlanBase(2, planes=1, dtype=dt, device="cpu", explain=True)
+    x = _rand_act(g, 2, 7, 9, 192, 1, dt=tdt)
+    w = torch.randn(n, 192, 1, 1, generator=g) * (3.0 / math.sqrt(192))          # outputs on both sides of the gate's knee
+    y, rec = plan._conv_fwd("gelu", x, w, 1, 0, 0, bn=None, relu=False, sq_eps=(0.0, 1e-12), want_sq=True, act=act)
+    assert plan.fwd_ops[-1].act == act and rec.gain is not None and y.sq is not None
+    print(_run_and_compare(plan.fwd_ops, tol16=BF16_TOL if dt == "bf16" else 2e-3))
+    # against the two-step form (transform, then GELU on the fp32 value): same numbers by construction of the emulator; and the
+    # library refuses the combinations the packed epilogue does not implement
+    bad = plan.fwd_ops[-1]
+    dev = U.to_device(bad, "cuda", {})
+    dev.relu = True
+    with pytest.raises(L.BcoskError):
+        dev.run()
+
+
 @pytest.mark.parametrize("dt", ["fp16", "bf16"])
 def test_stem_im2col_u8(bcosk_lib, dt):
     """bcosk_stem_im2col_u8: byte patch matrix (v_R, v_G, v_B, 1 per in-image tap) and 1/||patch|| of the normalised window"""
