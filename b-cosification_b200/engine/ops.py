@@ -94,6 +94,21 @@ class IgemmOp:
     def flops(self) -> float:
         return 2.0 * self.M * self.n * self.ktot
 
+    def smem_fill_bytes(self) -> float:
+        """Operand bytes the launch's TMA loads move from L2 into shared memory over its K loops, per-tile schedule: every (m tile, n tile)
+        pair fetches its A boxes (once per distinct a-plane in the paired stages of the plane-aware kernel, else once per segment) and its
+        B boxes (once per segment).  The L2 -> SM path (LTS cap, B300_MICROARCH.md) is what bounds the K >= 1024 contract-mode launches."""
+        bn = self.resolved_block_n()
+        m_tiles, n_tiles = (self.M + 127) // 128, (self.n + bn - 1) // bn
+        k_seg = len(self.taps) * self.chunks_per_tap * self.kch
+        segs = len(self.seg_a_choff)
+        sb = list(self.seg_b_plane or [0])
+        paired = (self.hp_accum and self.kch == 64 and segs >= 2 and sb[:2] == [0, 1] and self.seg_a_choff[0] == self.seg_a_choff[1]
+                  and (segs == 2 or (segs == 3 and sb[2] == 0 and self.seg_a_choff[2] != self.seg_a_choff[0])))
+        a_loads = len(set(self.seg_a_choff)) if paired else segs
+        b_loads = 2 if paired else segs
+        return float(m_tiles) * n_tiles * (a_loads * 128 + b_loads * bn) * k_seg * 2.0
+
     def algo_bytes(self) -> float:
         """Algorithmic HBM bytes of this launch: every operand / result tensor moved exactly once
         (x, W, y, gain, mask, sq, residual | g_out, W, g_in, gains, masks, extra gradient)."""

@@ -340,6 +340,7 @@ def main():
     # tensor-class launches: the ones SURVEY 8(d) marks tensor bound (3x3 at <= 28^2, K >= 1024 1x1, fc)
     tc = [(o, t) for o, t in ig if (len(o.taps) > 1 and o.op <= 28 and o.n >= 128) or (len(o.taps) == 1 and o.ktot // len(o.seg_a_choff) >= 1024)]
     tc_ms, tc_flops = sum(t for _, t in tc), sum(o.algo_flops for o, _ in tc)
+    tc_exec_flops, tc_fill = sum(o.flops() for o, _ in tc), sum(o.smem_fill_bytes() for o, _ in tc)
 
     if rank != 0:
         D.shutdown()
@@ -394,9 +395,20 @@ def main():
                             "executed_tflops": ig_exec_flops / (ig_ms * 1e-3) / 1e12, "peak_source": pk["source"] + " burst",
                             "tensor_class_launches": {"count": len(tc), "ms": tc_ms, "algorithmic_tflops": tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else None,
                                                       "frac_of_burst_peak": tc_flops / (tc_ms * 1e-3) / 1e12 / pk["bf16_tflops"] if tc_ms else None,
+                                                      "executed_tflops": tc_exec_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else None,
+                                                      "executed_frac_of_burst_peak": tc_exec_flops / (tc_ms * 1e-3) / 1e12 / pk["bf16_tflops"] if tc_ms else None,
                                                       "what": "3x3 at <= 28^2 and K >= 1024 1x1 launches (SURVEY 8d tensor-bound rows)"}},
         "clocks": sampler.summary(windows),
     }
+    # third roofline of the same tensor-class launches: operand bytes their TMA loads pull from L2 into shared memory (one 128 x 64 tile
+    # of the contract mode fetches 48 KB per 3.1 MFLOP executed) against the L2 slice throughput cap of the guide (B300_MICROARCH.md:
+    # ~6300 B / cycle full chip, path independent) at the SM clock sampled during the run
+    sm_mhz = res["clocks"].get("sm_mhz") or res["clocks"].get("sm_max_mhz") or 1965.0
+    l2_cap = 6300.0 * sm_mhz * 1e6 / 1e9
+    res["roofline_l2"] = {"bound": "l2", "achieved": tc_fill / (tc_ms * 1e-3) / 1e9 if tc_ms else None, "peak": l2_cap, "unit": "GB/s",
+                          "frac": tc_fill / (tc_ms * 1e-3) / 1e9 / l2_cap if tc_ms else None, "fill_bytes_per_step": tc_fill,
+                          "kernel": "tensor-class launches (roofline_tensor.tensor_class_launches)",
+                          "peak_source": "guide figure: L2 (LTS) throughput cap ~6300 B/cycle (B300_MICROARCH.md, measured on B300) x sampled SM clock"}
     if thr is not None:
         res["throughput_mode"] = thr
     if train is not None:
