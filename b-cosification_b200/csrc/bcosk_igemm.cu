@@ -2015,7 +2015,7 @@ extern "C" int bcosk_igemm(const bcosk_igemm_params* pp, void* stream) {
   int bn = p.block_n;
   if (bn == 0) bn = p.n <= 32 ? 32 : ((p.n <= 64 || p.hp_accum) ? 64 : 128);
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return set_error(BCOSK_EINVAL, "igemm: block_n");
-  if (p.hp_accum && bn > 64) return set_error(BCOSK_EINVAL, "igemm: hp_accum needs block_n <= 64");
+  if (p.hp_accum && bn > 128) return set_error(BCOSK_EINVAL, "igemm: hp_accum needs block_n <= 128");
   p.block_n = bn;
   if (p.max_out > 1) p.sched = 1;        // MaxOut: the per-tile kernel (generic epilogue, per-row stores)
   if (p.a_flat) return launch_flat(p, reinterpret_cast<cudaStream_t>(stream));

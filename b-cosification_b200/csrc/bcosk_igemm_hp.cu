@@ -35,18 +35,31 @@ namespace bcosk {
 
 namespace hp {
 constexpr int BM = 128;
-constexpr int BN = 64;
 constexpr int STAGE_K = 64;
 constexpr int A_BYTES = BM * STAGE_K * 2;      // 16 KB
-constexpr int B_BYTES = BN * STAGE_K * 2;      // 8 KB
-constexpr int SLOT_BYTES = A_BYTES + B_BYTES;  // 24 KB
 constexpr int BOX_BYTES = BM * 128;            // one [128 rows][128 bytes] swizzled box
 constexpr int THREADS = 320;
 constexpr int MAX_STAGES = 8;
-constexpr int TMEM_COLS = 4 * BN;             // two ping-pong partial accumulators + the cross-term accumulator (power of two)
-constexpr int PAIR_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // paired stage: [A plane 0 | A plane 1 | B plane 0 | B plane 1] = 48 KB
-constexpr int TAIL_BYTES = 256 + 2 * BN * 4 + BM * 4;   // barriers | alpha, beta | sum-of-squares exchange
-constexpr int MAX_SMEM = 115712;               // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
+// Tile width.  64: two CTAs per SM (<= 113 KB of shared memory, 256 TMEM columns each).  128 (forward launches with the packed
+// epilogue only): one CTA per SM, 64 KB paired stages - 98 instead of 65 FLOP per byte of L2 -> shared-memory fill, which is what
+// bounds the K >= 1024 launches; every epilogue warp then owns two 32-column groups.
+template <int BN_>
+struct Cfg {
+  static constexpr int BN = BN_;
+  static constexpr int NB = BN_ / 64;                       // 64-column boxes per plane of a 16-bit tensor
+  static constexpr int NG = BN_ / 64;                       // 32-column groups per epilogue warp (group jj = j + 2 h)
+  static constexpr int B_BYTES = BN_ * STAGE_K * 2;         // 8 / 16 KB
+  static constexpr int SLOT_BYTES = A_BYTES + B_BYTES;      // 24 / 32 KB
+  static constexpr int PAIR_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // paired stage: [A plane 0 | A plane 1 | B plane 0 | B plane 1] = 48 / 64 KB
+  static constexpr int PLANE_BYTES = NB * BOX_BYTES;        // boxes of one plane lie back to back
+  static constexpr int TMEM_COLS = 4 * BN_;                 // two ping-pong partial accumulators + the cross-term accumulator (power of two)
+  static constexpr int TAIL_BYTES = 256 + 2 * BN_ * 4 + BM * 4;   // barriers | alpha, beta | sum-of-squares exchange
+  static constexpr int MAX_SMEM = BN_ == 64 ? 115712 : 230400;    // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2; one: 225 KB
+  static constexpr int MIN_SMEM = BN_ == 64 ? 0 : 118784;   // wide tiles allocate all of TMEM: keep a second CTA off the SM
+  static constexpr int MIN_BLOCKS = BN_ == 64 ? 2 : 1;
+  static constexpr int MAX_RING_PAIRED = BN_ == 64 ? 2 : 3;
+  static constexpr int MAX_RING = BN_ == 64 ? 4 : 6;
+};
 }  // namespace hp
 
 struct HpAux {
@@ -126,10 +139,11 @@ __device__ __forceinline__ void split_pair(const float2 y, uint32_t& w0, uint32_
 // Packed forward epilogue of one row x 32 columns (two planes, B = 2 scale, everything boxed).
 //   t = |lin| * inv_norm * alpha;  y = lin * t + beta + res;  ReLU;  y -> two planes, gain = t (0 where clamped), sum y^2
 template <typename T>
-__device__ __forceinline__ void hp_fwd_fast(const float (&acc)[32], float inv_norm, uint32_t ab /* smem: alpha[32] of this half, beta at +256 B */,
+__device__ __forceinline__ void hp_fwd_fast(const float (&acc)[32], float inv_norm, uint32_t ab /* smem: alpha[32] of this group, beta at + 4 BN bytes */,
                                             uint32_t res0 /* plane-0 box or 0 */, uint32_t y0, uint32_t gbox /* fp32 gain box or 0 */,
                                             uint32_t g16 /* 16-bit gain box or 0 */, int row, int j, bool relu, float& sq_acc,
-                                            uint32_t& mbits, bool plain /* scale mode NONE: multiplier = alpha */) {
+                                            uint32_t& mbits, bool plain /* scale mode NONE: multiplier = alpha */,
+                                            uint32_t pstep /* bytes from plane 0 to plane 1 of a boxed tensor */, uint32_t beta_off) {
   using namespace hp;
   const float floor_v = relu ? 0.f : -FLT_MAX;
   const float2 inv2 = make_float2(inv_norm, inv_norm);
@@ -138,11 +152,11 @@ __device__ __forceinline__ void hp_fwd_fast(const float (&acc)[32], float inv_no
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const float4 a_lo = lds_f4(ab + g * 32), a_hi = lds_f4(ab + g * 32 + 16);
-    const float4 b_lo = lds_f4(ab + 256 + g * 32), b_hi = lds_f4(ab + 256 + g * 32 + 16);
+    const float4 b_lo = lds_f4(ab + beta_off + g * 32), b_hi = lds_f4(ab + beta_off + g * 32 + 16);
     uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
     if (res0 != 0) {
       r0 = lds128(tile_ptr(res0, row, j, g));
-      r1 = lds128(tile_ptr(res0 + BOX_BYTES, row, j, g));
+      r1 = lds128(tile_ptr(res0 + pstep, row, j, g));
     }
     uint32_t w0[4], w1[4];
     float tt[8];
@@ -174,7 +188,7 @@ __device__ __forceinline__ void hp_fwd_fast(const float (&acc)[32], float inv_no
                                                   Cvt<T>::pack2(tt[6], tt[7])));
     }
     sts128(tile_ptr(y0, row, j, g), make_uint4(w0[0], w0[1], w0[2], w0[3]));
-    sts128(tile_ptr(y0 + BOX_BYTES, row, j, g), make_uint4(w1[0], w1[1], w1[2], w1[3]));
+    sts128(tile_ptr(y0 + pstep, row, j, g), make_uint4(w1[0], w1[1], w1[2], w1[3]));
   }
   sq_acc += sq2.x + sq2.y;
   mbits = mb;
@@ -185,14 +199,14 @@ __device__ __forceinline__ void hp_fwd_fast(const float (&acc)[32], float inv_no
 template <typename T>
 __device__ __forceinline__ void hp_explain_fast(const float (&acc)[32], uint32_t add0 /* plane-0 box or 0 */, uint32_t gbox /* fp32 mul1 box or 0 */,
                                                 uint32_t y0, uint32_t o20 /* out2 plane-0 box or 0 */, const float* mul2_row /* global or null */,
-                                                uint32_t mb2, int row, int j) {
+                                                uint32_t mb2, int row, int j, uint32_t pstep) {
   using namespace hp;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
     if (add0 != 0) {
       a0 = lds128(tile_ptr(add0, row, j, g));
-      a1 = lds128(tile_ptr(add0 + BOX_BYTES, row, j, g));
+      a1 = lds128(tile_ptr(add0 + pstep, row, j, g));
     }
     float4 g_lo = make_float4(1.f, 1.f, 1.f, 1.f), g_hi = g_lo;
     if (gbox != 0) {
@@ -221,20 +235,24 @@ __device__ __forceinline__ void hp_explain_fast(const float (&acc)[32], uint32_t
     }
     if (o20 != 0) {
       sts128(tile_ptr(o20, row, j, g), make_uint4(ow0[0], ow0[1], ow0[2], ow0[3]));
-      sts128(tile_ptr(o20 + BOX_BYTES, row, j, g), make_uint4(ow1[0], ow1[1], ow1[2], ow1[3]));
+      sts128(tile_ptr(o20 + pstep, row, j, g), make_uint4(ow1[0], ow1[1], ow1[2], ow1[3]));
     }
     sts128(tile_ptr(y0, row, j, g), make_uint4(yw0[0], yw0[1], yw0[2], yw0[3]));
-    sts128(tile_ptr(y0 + BOX_BYTES, row, j, g), make_uint4(yw1[0], yw1[1], yw1[2], yw1[3]));
+    sts128(tile_ptr(y0 + pstep, row, j, g), make_uint4(yw1[0], yw1[1], yw1[2], yw1[3]));
   }
 }
 
-template <int MODE, typename T>
-__global__ void __launch_bounds__(hp::THREADS, 2)
+template <int MODE, typename T, int BN_>
+__global__ void __launch_bounds__(hp::THREADS, hp::Cfg<BN_>::MIN_BLOCKS)
 bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_in16, const __grid_constant__ CUtensorMap tmap_in32,
                       const __grid_constant__ CUtensorMap tmap_out1, const __grid_constant__ CUtensorMap tmap_out2,
                       const __grid_constant__ bcosk_igemm_params p, const HpAux aux) {
   using namespace hp;
+  using C = Cfg<BN_>;
+  constexpr int BN = C::BN, NB = C::NB, NG = C::NG;
+  constexpr int B_BYTES = C::B_BYTES, SLOT_BYTES = C::SLOT_BYTES, PAIR_BYTES = C::PAIR_BYTES, PLANE_BYTES = C::PLANE_BYTES;
+  constexpr int TMEM_COLS = C::TMEM_COLS;
   extern __shared__ __align__(1024) uint8_t smem[];   // no static shared memory: the dynamic window starts 1024-byte aligned
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int stages = aux.stages;
@@ -263,7 +281,8 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   const int num_iters = aux.paired ? seg_iters : p.num_segs * seg_iters;    // paired: one stage per (tap, chunk), both planes
   const int main_drains = (seg_iters + aux.chunk - 1) / aux.chunk;
   const int num_drains = aux.paired ? main_drains : main_drains + (num_iters - seg_iters + aux.xchunk - 1) / aux.xchunk;
-  const int boxes32 = min(2, (p.n - n0 + 31) >> 5);                              // fp32 boxes of this tile inside the tensor
+  const int boxes32 = min(BN / 32, (p.n - n0 + 31) >> 5);                        // fp32 boxes of this tile inside the tensor
+  const int boxes16 = min(NB, (p.n - n0 + 63) >> 6);                             // 64-column boxes per plane inside the tensor
   const bool any_in = aux.in16_planes != 0 || aux.in32 != 0;
 
   if (warp == 0 && lane == 0) {
@@ -298,9 +317,10 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (lane == 0) {
       const int ps16 = MODE == BCOSK_MODE_FWD ? p.res_plane_stride : p.add_plane_stride;
       auto load_inputs = [&]() {
-        mbar_arrive_expect_tx(in_bar, (uint32_t)(aux.in16_planes * BOX_BYTES + (aux.in32 ? boxes32 * BOX_BYTES : 0)));
+        mbar_arrive_expect_tx(in_bar, (uint32_t)(aux.in16_planes * boxes16 * BOX_BYTES + (aux.in32 ? boxes32 * BOX_BYTES : 0)));
         for (int pl = 0; pl < aux.in16_planes; ++pl)
-          tma_load_2d(smem + aux.off_in16 + pl * BOX_BYTES, &tmap_in16, in_bar, pl * ps16 + n0, m0);
+          for (int b = 0; b < boxes16; ++b)
+            tma_load_2d(smem + aux.off_in16 + pl * PLANE_BYTES + b * BOX_BYTES, &tmap_in16, in_bar, pl * ps16 + n0 + b * 64, m0);
         if (aux.in32)
           for (int b = 0; b < boxes32; ++b) tma_load_2d(smem + aux.off_in32 + b * BOX_BYTES, &tmap_in32, in_bar, n0 + b * 32, m0);
       };
@@ -309,7 +329,8 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           load_inputs();                 // their boxes are not part of the ring
         } else {
           // pull the lines into L2 while the K loop runs; the boxes are fetched into the ring after it
-          for (int pl = 0; pl < aux.in16_planes; ++pl) tma_prefetch_2d(&tmap_in16, pl * ps16 + n0, m0);
+          for (int pl = 0; pl < aux.in16_planes; ++pl)
+            for (int b = 0; b < boxes16; ++b) tma_prefetch_2d(&tmap_in16, pl * ps16 + n0 + b * 64, m0);
           if (aux.in32)
             for (int b = 0; b < boxes32; ++b) tma_prefetch_2d(&tmap_in32, n0 + b * 32, m0);
         }
@@ -469,11 +490,9 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int j = (warp - 2) >> 2;             // 32-column half of the tile
+    const int j = (warp - 2) >> 2;             // this warp owns the 32-column groups jj = j + 2 h, h < NG (warp-uniform)
     const int row = quad * 32 + lane;
     const int et = threadIdx.x - 64;           // 0..255
-    const int c0 = n0 + j * 32;
-    const bool cols_ok = c0 < p.n;             // warp-uniform
     if (MODE == BCOSK_MODE_FWD) {
       if (et < BN) {
         const int c = n0 + et;
@@ -523,10 +542,18 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if (ri.p % s == 0 && ri.q % s == 0 && ri.p / s < p.add_p && ri.q / s < p.add_q)
         add_row = ((int64_t)ri.img * p.add_p + ri.p / s) * p.add_q + ri.q / s;
     }
-    uint32_t mb2 = 0xffffffffu;
-    if (MODE == BCOSK_MODE_EXPLAIN && p.mask2 != nullptr && ri.valid && cols_ok) mb2 = __ldg(p.mask2 + (size_t)ri.m * p.mask2_ld + (c0 >> 5));
+    uint32_t mb2s[NG];
+#pragma unroll
+    for (int h = 0; h < NG; ++h) {
+      const int c0 = n0 + (j + 2 * h) * 32;
+      mb2s[h] = 0xffffffffu;
+      if (MODE == BCOSK_MODE_EXPLAIN && p.mask2 != nullptr && ri.valid && c0 < p.n) mb2s[h] = __ldg(p.mask2 + (size_t)ri.m * p.mask2_ld + (c0 >> 5));
+    }
     // side tensors read with per-row loads after the last drain: pull their lines into L2 now
-    if (ri.valid && cols_ok) {
+#pragma unroll
+    for (int h = 0; h < NG; ++h) {
+      const int c0 = n0 + (j + 2 * h) * 32;
+      if (!(ri.valid && c0 < p.n)) continue;
       const int ncols_pf = min(32, p.n - c0);
       auto prefetch_row = [&](const void* base, size_t elem_off, int elem_bytes) {
         const char* b = reinterpret_cast<const char*>(base) + elem_off * (size_t)elem_bytes;
@@ -546,33 +573,41 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       }
     }
 
-    // ---- sum the partial accumulators of this thread's 32 columns (round-to-nearest fp32 adds)
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * 32);
-    float acc[32];
+    // ---- sum the partial accumulators of this thread's 32-column groups (round-to-nearest fp32 adds)
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * 32);     // group h: + 64 h columns
+    float acc[NG][32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int h = 0; h < NG; ++h)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[h][i] = 0.f;
     for (int d = 0; d < num_drains; ++d) {
       const uint32_t buf = (uint32_t)d & 1u;
       mbar_wait(&acc_full_bar[buf], ((uint32_t)d >> 1) & 1u);
       tc_fence_after();
-      uint32_t raw[32];
-      tmem_ld_32x32(taddr + buf * BN, raw);
+      uint32_t raw[NG][32];
+#pragma unroll
+      for (int h = 0; h < NG; ++h) tmem_ld_32x32(taddr + buf * BN + h * 64, raw[h]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty_bar[buf]);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(raw[i]);
+      for (int h = 0; h < NG; ++h)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[h][i] += __uint_as_float(raw[h][i]);
     }
     if (aux.paired) {
       mbar_wait(&acc_full_bar[2], 0);
       tc_fence_after();
-      uint32_t raw[32];
-      tmem_ld_32x32(taddr + 2 * BN, raw);
+      uint32_t raw[NG][32];
+#pragma unroll
+      for (int h = 0; h < NG; ++h) tmem_ld_32x32(taddr + 2 * BN + h * 64, raw[h]);
       tmem_ld_wait();
       tc_fence_before();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(raw[i]);
+      for (int h = 0; h < NG; ++h)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[h][i] += __uint_as_float(raw[h][i]);
     }
     if (any_in) mbar_wait(in_bar, 0);
 
@@ -583,19 +618,25 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     float* y32 = reinterpret_cast<float*>(p.y);
     float sq_acc = 0.f;
 
-    if (ri.valid && cols_ok) {
+#pragma unroll
+    for (int h = 0; h < NG; ++h) {
+      const int jj = j + 2 * h;                // 32-column group of the tile
+      const int c0 = n0 + jj * 32;
+      if (!(ri.valid && c0 < p.n)) continue;
       const int ncols = min(32, p.n - c0);
+      const float (&accv)[32] = acc[h];
+      const uint32_t mb2 = mb2s[h];
       if (aux.fast) {
         if (MODE == BCOSK_MODE_FWD) {
           uint32_t mbits;
-          hp_fwd_fast<T>(acc, inv_norm, smem_u32(s_alpha + j * 32), aux.in16_planes ? r_in16 : 0u, r_out1,
-                         aux.out2_kind == 1 ? r_out2 + j * BOX_BYTES : 0u, aux.out2_kind == 3 ? r_out2 : 0u, row, j, p.relu != 0, sq_acc,
-                         mbits, p.scale_mode == BCOSK_SCALE_NONE);
+          hp_fwd_fast<T>(accv, inv_norm, smem_u32(s_alpha + jj * 32), aux.in16_planes ? r_in16 : 0u, r_out1,
+                         aux.out2_kind == 1 ? r_out2 + jj * BOX_BYTES : 0u, aux.out2_kind == 3 ? r_out2 : 0u, row, jj, p.relu != 0, sq_acc,
+                         mbits, p.scale_mode == BCOSK_SCALE_NONE, (uint32_t)PLANE_BYTES, (uint32_t)(BN * 4));
           if (p.maskbits != nullptr) p.maskbits[(size_t)ri.m * p.mask_ld + (c0 >> 5)] = mbits;
         } else {
-          hp_explain_fast<T>(acc, aux.in16_planes ? r_in16 : 0u, aux.in32 ? r_in32 + j * BOX_BYTES : 0u, r_out1,
+          hp_explain_fast<T>(accv, aux.in16_planes ? r_in16 : 0u, aux.in32 ? r_in32 + jj * BOX_BYTES : 0u, r_out1,
                              aux.out2_kind == 2 ? r_out2 : 0u,
-                             p.mul2 != nullptr ? reinterpret_cast<const float*>(p.mul2) + (size_t)ri.m * p.mul2_ld + c0 : nullptr, mb2, row, j);
+                             p.mul2 != nullptr ? reinterpret_cast<const float*>(p.mul2) + (size_t)ri.m * p.mul2_ld + c0 : nullptr, mb2, row, jj, (uint32_t)PLANE_BYTES);
         }
       } else {
         uint32_t mbits = 0;
@@ -605,7 +646,7 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const int cg = c0 + g * 8;
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = acc[g * 8 + i];
+            for (int i = 0; i < 8; ++i) v[i] = accv[g * 8 + i];
             uint4 w[3];
             if (MODE == BCOSK_MODE_FWD) {
               // ---------------- forward: scale, BN multiplier, residual, ReLU; writes y planes, gain, mask, sum y^2
@@ -618,8 +659,8 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 continue;
               }
               float t[8];
-              const float4 a0 = *reinterpret_cast<const float4*>(s_alpha + j * 32 + g * 8);
-              const float4 a1 = *reinterpret_cast<const float4*>(s_alpha + j * 32 + g * 8 + 4);
+              const float4 a0 = *reinterpret_cast<const float4*>(s_alpha + jj * 32 + g * 8);
+              const float4 a1 = *reinterpret_cast<const float4*>(s_alpha + jj * 32 + g * 8 + 4);
               const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
               if (p.scale_mode == BCOSK_SCALE_B2) {
 #pragma unroll
@@ -632,8 +673,8 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
                 for (int i = 0; i < 8; ++i) t[i] = al[i];
               }
-              const float4 b0 = *reinterpret_cast<const float4*>(s_beta + j * 32 + g * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(s_beta + j * 32 + g * 8 + 4);
+              const float4 b0 = *reinterpret_cast<const float4*>(s_beta + jj * 32 + g * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_beta + jj * 32 + g * 8 + 4);
               const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], t[i], be[i]);
@@ -642,7 +683,7 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
                 for (int i = 0; i < 8; ++i) r[i] = 0.f;
                 if (aux.in16_planes) {
-                  for (int pl = 0; pl < aux.in16_planes; ++pl) add8<T>(lds128(tile_ptr(r_in16 + pl * BOX_BYTES, row, j, g)), r);
+                  for (int pl = 0; pl < aux.in16_planes; ++pl) add8<T>(lds128(tile_ptr(r_in16 + pl * PLANE_BYTES, row, jj, g)), r);
                 } else {
                   const T* rp = reinterpret_cast<const T*>(p.res) + (size_t)ri.m * p.res_ld + cg;
                   for (int pl = 0; pl < p.res_planes; ++pl)
@@ -664,13 +705,13 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
               }
               if (p.gain != nullptr) {
                 if (aux.out2_kind == 1) {
-                  sts128(box_unit(r_out2 + j * BOX_BYTES, row, 2 * g), make_uint4(__float_as_uint(t[0]), __float_as_uint(t[1]),
+                  sts128(box_unit(r_out2 + jj * BOX_BYTES, row, 2 * g), make_uint4(__float_as_uint(t[0]), __float_as_uint(t[1]),
                                                                                  __float_as_uint(t[2]), __float_as_uint(t[3])));
-                  sts128(box_unit(r_out2 + j * BOX_BYTES, row, 2 * g + 1), make_uint4(__float_as_uint(t[4]), __float_as_uint(t[5]),
+                  sts128(box_unit(r_out2 + jj * BOX_BYTES, row, 2 * g + 1), make_uint4(__float_as_uint(t[4]), __float_as_uint(t[5]),
                                                                                      __float_as_uint(t[6]), __float_as_uint(t[7])));
                 } else if (aux.out2_kind == 3) {
                   split8<T>(t, 1, w);
-                  sts128(tile_ptr(r_out2, row, j, g), w[0]);
+                  sts128(tile_ptr(r_out2, row, jj, g), w[0]);
                 } else if (p.gain_f32) {
                   float4* gp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.gain) + (size_t)ri.m * p.gain_ld + cg);
                   gp[0] = make_float4(t[0], t[1], t[2], t[3]);
@@ -689,7 +730,7 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 if (aux.out1_planes) {
 #pragma unroll
                   for (int pl = 0; pl < 3; ++pl)
-                    if (pl < aux.out1_planes) sts128(tile_ptr(r_out1 + pl * BOX_BYTES, row, j, g), w[pl]);
+                    if (pl < aux.out1_planes) sts128(tile_ptr(r_out1 + pl * PLANE_BYTES, row, jj, g), w[pl]);
                 } else {
                   T* yp = y16 + (size_t)yrow * p.y_ld + cg;
 #pragma unroll
@@ -705,7 +746,7 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
               // ---------------- explain: tot = D + add;  out2 = tot * mul2 * mask2;  y = tot * mul1
               if (add_row >= 0) {
                 if (aux.in16_planes) {
-                  for (int pl = 0; pl < aux.in16_planes; ++pl) add8<T>(lds128(tile_ptr(r_in16 + pl * BOX_BYTES, row, j, g)), v);
+                  for (int pl = 0; pl < aux.in16_planes; ++pl) add8<T>(lds128(tile_ptr(r_in16 + pl * PLANE_BYTES, row, jj, g)), v);
                 } else {
                   const T* ap = reinterpret_cast<const T*>(p.add) + (size_t)add_row * p.add_ld + cg;
                   for (int pl = 0; pl < p.add_planes; ++pl)
@@ -736,7 +777,7 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 if (aux.out2_kind == 2) {
 #pragma unroll
                   for (int pl = 0; pl < 3; ++pl)
-                    if (pl < aux.out2_planes) sts128(tile_ptr(r_out2 + pl * BOX_BYTES, row, j, g), w[pl]);
+                    if (pl < aux.out2_planes) sts128(tile_ptr(r_out2 + pl * PLANE_BYTES, row, jj, g), w[pl]);
                 } else {
                   T* op = reinterpret_cast<T*>(p.out2) + (size_t)ri.m * p.out2_ld + cg;
 #pragma unroll
@@ -747,8 +788,8 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
               if (p.mul1 != nullptr) {
                 float gq[8];
                 if (aux.in32) {
-                  const float4 g0 = lds_f4(box_unit(r_in32 + j * BOX_BYTES, row, 2 * g));
-                  const float4 g1 = lds_f4(box_unit(r_in32 + j * BOX_BYTES, row, 2 * g + 1));
+                  const float4 g0 = lds_f4(box_unit(r_in32 + jj * BOX_BYTES, row, 2 * g));
+                  const float4 g1 = lds_f4(box_unit(r_in32 + jj * BOX_BYTES, row, 2 * g + 1));
                   gq[0] = g0.x; gq[1] = g0.y; gq[2] = g0.z; gq[3] = g0.w; gq[4] = g1.x; gq[5] = g1.y; gq[6] = g1.z; gq[7] = g1.w;
                 } else if (p.mul1_f32) {
                   const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.mul1) + (size_t)ri.m * p.mul1_ld + cg);
@@ -771,7 +812,7 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 if (aux.out1_planes) {
 #pragma unroll
                   for (int pl = 0; pl < 3; ++pl)
-                    if (pl < aux.out1_planes) sts128(tile_ptr(r_out1 + pl * BOX_BYTES, row, j, g), w[pl]);
+                    if (pl < aux.out1_planes) sts128(tile_ptr(r_out1 + pl * PLANE_BYTES, row, jj, g), w[pl]);
                 } else {
                   T* yp = y16 + (size_t)yrow * p.y_ld + cg;
 #pragma unroll
@@ -791,14 +832,17 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (aux.out1_planes != 0 || aux.out2_kind != 0) fence_proxy_async_smem();
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if ((aux.out1_planes != 0 || aux.out2_kind != 0) && et == 0) {
-      for (int pl = 0; pl < aux.out1_planes; ++pl) tma_store_2d_addr(&tmap_out1, r_out1 + pl * BOX_BYTES, pl * p.y_plane_stride + n0, m0);
+      for (int pl = 0; pl < aux.out1_planes; ++pl)
+        for (int b = 0; b < boxes16; ++b)
+          tma_store_2d_addr(&tmap_out1, r_out1 + pl * PLANE_BYTES + b * BOX_BYTES, pl * p.y_plane_stride + n0 + b * 64, m0);
       if (aux.out2_kind == 1) {
         for (int b = 0; b < boxes32; ++b) tma_store_2d_addr(&tmap_out2, r_out2 + b * BOX_BYTES, n0 + b * 32, m0);
       } else if (aux.out2_kind == 2) {
         for (int pl = 0; pl < aux.out2_planes; ++pl)
-          tma_store_2d_addr(&tmap_out2, r_out2 + pl * BOX_BYTES, pl * p.out2_plane_stride + n0, m0);
+          for (int b = 0; b < boxes16; ++b)
+            tma_store_2d_addr(&tmap_out2, r_out2 + pl * PLANE_BYTES + b * BOX_BYTES, pl * p.out2_plane_stride + n0 + b * 64, m0);
       } else if (aux.out2_kind == 3) {
-        tma_store_2d_addr(&tmap_out2, r_out2, n0, m0);
+        for (int b = 0; b < boxes16; ++b) tma_store_2d_addr(&tmap_out2, r_out2 + b * BOX_BYTES, n0 + b * 64, m0);
       }
       tma_store_commit_and_wait_read();
     }
@@ -812,7 +856,7 @@ bcosk_igemm_hp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, hp::TMEM_COLS);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -824,9 +868,13 @@ static int g_hp_xchunk = 0;      // experiment override of the cross-term accumu
 static int g_hp_stage_boxes = 1; // 0 = per-row epilogue I/O everywhere (A/B measurements)
 static int g_hp_early_iters = 4; // K loops of at most this many stages fetch their input boxes at kernel start
 
-template <int MODE>
+template <int MODE, int BN_>
 static int launch_hp_mode(const bcosk_igemm_params& p, cudaStream_t st) {
   using namespace hp;
+  using C = Cfg<BN_>;
+  constexpr int BN = C::BN;
+  constexpr int SLOT_BYTES = C::SLOT_BYTES, PAIR_BYTES = C::PAIR_BYTES, PLANE_BYTES = C::PLANE_BYTES, TAIL_BYTES = C::TAIL_BYTES;
+  constexpr int MAX_SMEM = C::MAX_SMEM;
   CUtensorMap ma, mb, min16, min32, mout1, mout2;
   memset(&min16, 0, sizeof(min16));
   memset(&min32, 0, sizeof(min32));
@@ -890,15 +938,15 @@ static int launch_hp_mode(const bcosk_igemm_params& p, cudaStream_t st) {
       p.seg_a_choff[0] == p.seg_a_choff[1])
     aux.paired = 2;
   const int slot_b = aux.paired ? PAIR_BYTES : SLOT_BYTES;
-  const int max_ring = aux.paired ? 2 : 4;        // ring slots that fit two CTAs per SM
+  const int max_ring = aux.paired ? C::MAX_RING_PAIRED : C::MAX_RING;        // ring slots that fit the CTAs of one SM
   const int iters = aux.paired ? p.num_taps * p.chunks_per_tap : p.num_segs * p.num_taps * p.chunks_per_tap / (STAGE_K / p.kch);
   const int early_iters = aux.paired ? (g_hp_early_iters + 2) / 3 : g_hp_early_iters;
   int stages = 0, extra = 0;
   auto place = [&]() -> bool {
-    const int in16_b = aux.in16_planes * BOX_BYTES, in32_b = aux.in32 ? 2 * BOX_BYTES : 0;
-    const int out1_b = aux.out1_planes * BOX_BYTES;
-    const int out2_b = aux.out2_kind == 1 ? 2 * BOX_BYTES
-                                          : (aux.out2_kind == 2 ? aux.out2_planes * BOX_BYTES : (aux.out2_kind == 3 ? BOX_BYTES : 0));
+    const int in16_b = aux.in16_planes * PLANE_BYTES, in32_b = aux.in32 ? (BN / 32) * BOX_BYTES : 0;
+    const int out1_b = aux.out1_planes * PLANE_BYTES;
+    const int out2_b = aux.out2_kind == 1 ? (BN / 32) * BOX_BYTES
+                                          : (aux.out2_kind == 2 ? aux.out2_planes * PLANE_BYTES : (aux.out2_kind == 3 ? PLANE_BYTES : 0));
     aux.early_in = 0;
     extra = 0;
     if ((in16_b || in32_b) && iters <= early_iters) {
@@ -952,9 +1000,12 @@ static int launch_hp_mode(const bcosk_igemm_params& p, cudaStream_t st) {
   if (g_hp_stage_boxes & 2) aux.fast = 0;      // A/B: generic epilogue arithmetic over the same boxes
   aux.stages = stages;
   aux.tail = (uint32_t)(stages * slot_b + extra);
-  const int smem = (int)aux.tail + tail_bytes;
-  auto kern = bcosk_igemm_hp_kernel<MODE, __nv_bfloat16>;
-  auto kern_h = bcosk_igemm_hp_kernel<MODE, __half>;
+  if (BN_ > 64 && !aux.fast)
+    return set_error(BCOSK_EUNSUPPORTED, "igemm(hp): 128-wide tiles need the packed two-plane epilogue (two boxed planes, B = 2 or plain scale)");
+  int smem = (int)aux.tail + tail_bytes;
+  if (smem < C::MIN_SMEM) smem = C::MIN_SMEM;
+  auto kern = bcosk_igemm_hp_kernel<MODE, __nv_bfloat16, BN_>;
+  auto kern_h = bcosk_igemm_hp_kernel<MODE, __half, BN_>;
   const void* fn = (p.dtype == BCOSK_DTYPE_BF16) ? (const void*)kern : (const void*)kern_h;
   BCOSK_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
   BCOSK_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -976,7 +1027,11 @@ int launch_hp(const bcosk_igemm_params& p, cudaStream_t st) {
     return set_error(BCOSK_EINVAL, "igemm(hp): a segment must be a whole number of K stages");
   if (p.hp_chunk < 0) return set_error(BCOSK_EINVAL, "igemm(hp): hp_chunk < 0");
   if (p.mul1_sqrt_scale) return set_error(BCOSK_EUNSUPPORTED, "igemm(hp): recomputed gains (mul1_sqrt_scale) are a throughput-mode option");
-  return p.mode == BCOSK_MODE_FWD ? launch_hp_mode<BCOSK_MODE_FWD>(p, st) : launch_hp_mode<BCOSK_MODE_EXPLAIN>(p, st);
+  if (p.block_n == 128) {
+    if (p.mode != BCOSK_MODE_FWD) return set_error(BCOSK_EUNSUPPORTED, "igemm(hp): 128-wide tiles are a forward-launch option");
+    return launch_hp_mode<BCOSK_MODE_FWD, 128>(p, st);
+  }
+  return p.mode == BCOSK_MODE_FWD ? launch_hp_mode<BCOSK_MODE_FWD, 64>(p, st) : launch_hp_mode<BCOSK_MODE_EXPLAIN, 64>(p, st);
 }
 
 }  // namespace bcosk

@@ -140,6 +140,8 @@ class PlanBase:
     flat_3x3 = True                  # 64 -> <=64 channel stride-1 k x k convs and their data gradients as flat-window launches
     flat_stem = True                 # stem and its data gradient as flat-window launches (throughput mode only)
     autotune_default = True          # capture() measures the per-launch schedule first (see autotune)
+    hp_wide_stages = 18  # parity-mode forward launches with at least this many (paired) K stages run 128-wide tiles (0 = never; measured: shorter
+                         # K loops lose more to the exposed epilogue of the one-CTA-per-SM kernel than they gain from the smaller operand fill)
     hp_chunk = 0     # parity-mode launches: K stages per TMEM accumulation of the leading segment (0 = library default)
     fold_bn = True   # fold sqrt(BN multiplier) into the conv weights when every multiplier is positive and there is no bias
 
@@ -234,8 +236,16 @@ class PlanBase:
             bm, cpt = P.pack_b(wt, pw, kch, self.dt, segs)
             bmat = self._dev(bm, self.dt)
         block_n = self._block_n(o, bmat.shape[1] // 64, hp=hp_launch)
-        parts = (o + block_n - 1) // block_n
         yp = 1 if y_f32 else (self.planes if y_planes is None else y_planes)
+        # long K loops of the plane-aware kernel are bound by the L2 -> shared-memory operand fill: 128-wide tiles fetch the
+        # A boxes once per 128 output columns (98 instead of 65 FLOP per fill byte).  Needs the packed two-plane epilogue.
+        k_stages = len(taps) * cpt * kch // 64
+        if (hp_launch and self.hp_wide_stages and k_stages >= self.hp_wide_stages and o % 128 == 0 and kch == 64 and yp == 2 and not y_f32
+                and max_out == 1 and lin_bias is None and smode in (L.BCOSK_SCALE_B2, L.BCOSK_SCALE_NONE) and y_buf is None and out_map is None
+                and (res is None or (self.planes if res_planes is None else res_planes) == 2) and segs in (P.segments(2, 2), P.segments(1, 2))
+                and (not self.with_explain or not want_gain or self.gain_dt != torch.float32)):
+            block_n = 128
+        parts = (o + block_n - 1) // block_n
         oy = o // max_out                 # columns that leave the epilogue
         if y_buf is not None:             # the launch writes columns [y_col, y_col + oy) of every plane of a wider tensor (DenseNet features)
             assert (out_map is not None or tuple(y_buf.shape[:3]) == (nb, oh, ow)) and not y_f32 and y_buf.shape[-1] % yp == 0 and y_col % 8 == 0

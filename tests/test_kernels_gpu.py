@@ -124,6 +124,35 @@ def test_igemm_forward_plain_linear(bcosk_lib, planes):
         print(_run_and_compare(plan.fwd_ops, tol16=BF16_TOL if planes == 1 else 2e-4))
 
 
+@pytest.mark.parametrize("k,cin,n,res,relu,pa", [(3, 128, 256, False, True, 2), (1, 1024, 256, True, True, 2), (1, 512, 384, True, False, 1),
+                                                 (3, 64, 128, False, True, 2)])
+def test_igemm_hp_wide_tiles(bcosk_lib, k, cin, n, res, relu, pa):
+    """128-wide tiles of the plane-aware kernel (long K loops: 64 KB paired stages, one CTA per SM, two column groups per epilogue
+    warp): same numbers as the 64-wide launch of the same convolution, and both against the emulator"""
+    g = torch.Generator().manual_seed(61 + k + n)
+    outs = {}
+    for wide in (8, 0):
+        plan = PlanBase(2, planes=2, dtype="fp16", device="cpu", explain=True, explain_planes=1)
+        plan.flat_3x3 = False
+        plan.hp_wide_stages = wide
+        gg = torch.Generator().manual_seed(61 + k + n)
+        x = _rand_act(gg, 2, 10, 10, cin, pa, dt=torch.float16)
+        w = torch.randn(n, cin, k, k, generator=gg) / math.sqrt(cin * k * k)
+        r = _rand_act(gg, 2, 10, 10, n, 2, dt=torch.float16) if res else None
+        kw = dict(a_planes=1, w_planes=2, y_planes=2, res_planes=2, hp=True) if pa == 1 else {}
+        y, rec = plan._conv_fwd("wide", x, w, 1, k // 2, k // 2, bn=None, relu=relu, res=r, want_sq=True, want_mask=relu, **kw)
+        op = plan.fwd_ops[-1]
+        assert op.hp_accum and op.resolved_block_n() == (128 if wide else 64), op.resolved_block_n()
+        print(_run_and_compare(plan.fwd_ops, tol16=6e-4))           # (the one-plane fp16 gain: 2^-11)
+        dev = U.to_device(op, "cuda", {})
+        dev.run()
+        torch.cuda.synchronize()
+        outs[wide] = (dev.y.clone(), dev.gain.clone(), dev.sq_out.sum(0).clone(), None if dev.maskbits is None else dev.maskbits.clone())
+    assert torch.equal(outs[8][0], outs[0][0]) and torch.equal(outs[8][1], outs[0][1])          # y planes and gains: bit-identical
+    assert outs[8][3] is None or torch.equal(outs[8][3], outs[0][3])
+    assert U.max_rel_err(outs[8][2], outs[0][2]) < 1e-6                                         # per-tile partials regroup the same squares
+
+
 @pytest.mark.parametrize("act", [1, 2])
 @pytest.mark.parametrize("dt,n", [("fp16", 384), ("bf16", 128), ("fp16", 64)])
 def test_igemm_forward_fused_gelu(bcosk_lib, dt, n, act):
