@@ -156,6 +156,29 @@ class PlanBase:
         return 128
 
     @staticmethod
+    def _flat_fits(width: int, k: int, ntaps: int, bn: int, dense: bool, kch: int = 64) -> bool:
+        """Does a flat-window launch (include/bcosk.h `a_flat`) over rows of `width` pixels (dense: the tensor's width; padded: the
+        bordered buffer's pitch) fit the shared memory / TMA boxes of bcosk_igemm_flat?  Mirrors launch_flat_bn (csrc/bcosk_igemm.cu):
+        wide feature maps (448^2 inputs) fall back to the im2col launches."""
+        up = lambda v, a: (v + a - 1) // a * a        # noqa: E731
+        row_bytes = kch * 2
+        if dense:
+            pitch = up(width + k - 1, 8)
+            nrows = ((0 if 128 % pitch == 0 else pitch - 1) + 127) // pitch + k
+            if nrows > 256 or pitch > 256:
+                return False
+            win = up(nrows * pitch * row_bytes, 1024)
+        else:
+            need = 128 + (k - 1) * width + (k - 1)
+            nbox = 1 if need <= 256 else 2
+            box_rows = up((need + nbox - 1) // nbox, 8)
+            if box_rows > 256:
+                return False
+            win = up(nbox * box_rows * row_bytes, 1024)
+        smem = up(ntaps * bn * row_bytes, 1024) + 2 * win + 4 * 128 * bn * 2 + 128 + 2 * bn * 4 + 2 * (bn // 32) * 128 * 4 + 64 * 4
+        return smem <= 227 * 1024
+
+    @staticmethod
     def _even_taps(wt: Tensor, taps: List[Tuple[int, int]], kch: int) -> Tuple[Tensor, List[Tuple[int, int]]]:
         """A pipeline stage is 64 K elements: with 32-channel chunks every segment needs an even number of (tap, chunk) pairs.
         An odd count (3x3 over <= 32 channels) gets one more tap that re-reads the last tap's pixels against zero weights."""
@@ -207,7 +230,8 @@ class PlanBase:
         if max_out > 1:
             assert max_out in (2, 4, 8) and o % max_out == 0 and bn is None and not relu and res is None and not want_mask and not flat
         flat = flat or (self.flat_3x3 and max_out == 1 and self.planes == 1 and pa == 1 and pw == 1 and not hp_launch and stride == 1 and kh == kw and kh > 1
-                        and cin_phys == 64 and kch == 64 and o <= 64 and res is None and not y_f32 and x.t.is_contiguous())
+                        and cin_phys == 64 and kch == 64 and o <= 64 and res is None and not y_f32 and x.t.is_contiguous()
+                        and self._flat_fits(wd, kh, kh * kw, 32 if o <= 32 else 64, True))
         sq_in = None
         if inv_norm is None and smode != L.BCOSK_SCALE_NONE:
             sq_in = x.sq
@@ -376,7 +400,8 @@ class PlanBase:
             oh, ow = rec.in_hw
         flat = flat or (self.flat_3x3 and self.bplanes == 1 and not self.bwd_hp and rec.stride == 1 and k > 1
                         and rec.cout == 64 and kch == 64 and rec.cin_phys <= 64 and add is None and out2 is None
-                        and y_map is None and not y_f32 and g.is_contiguous())
+                        and y_map is None and not y_f32 and g.is_contiguous()
+                        and self._flat_fits(g.shape[2], k, k * k, 32 if rec.cin_phys <= 32 else 64, True))
         lo = rec.pad_lo - (k - 1)
         up_h = oh - g.shape[1] + lo
         up_w = ow - g.shape[2] + lo

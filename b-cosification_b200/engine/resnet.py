@@ -105,7 +105,8 @@ class ResNetPlan(PlanBase):
         # ---- stem: normalise + space-to-depth, 7x7/2 conv as a 4x4/1 conv, BN, ReLU
         h2 = S // 2
         # throughput mode: the stem reads a zero-bordered buffer (pad 2 before / 1 after) through one window per tile
-        self.stem_flat = self.flat_stem and pl == 1 and not self.hp_accum
+        # (the flat window of the 4x4 space-to-depth stem spans 3 padded rows + 128 pixels: it fits two TMA boxes up to ~256^2 inputs)
+        self.stem_flat = self.flat_stem and pl == 1 and not self.hp_accum and self._flat_fits(h2 + 3, 4, 16, 64, False, self.stem_kch)
         w4 = P.stem_s2d_weight(sd["model.conv1.linear.weight"], self.stem_cp)
         if self.hp_accum and self.input_u8 and self.stem_im2col:
             # contract modes with uint8 input: GEMM over the exact byte patch matrix (base.py _stem_fwd_im2col)
@@ -179,7 +180,8 @@ class ResNetPlan(PlanBase):
             else:
                 blk.side = self._zeros(nb, blk.y.hw[0], blk.y.hw[1], pl * blk.y.c)
         self._alloc_ghat(self.stem)
-        self.stem_flat_bwd = self.flat_stem and pl == 1 and not self.bwd_hp
+        self.stem_flat_bwd = (self.flat_stem and pl == 1 and not self.bwd_hp
+                              and self._flat_fits(self.stem.out_hw[1] + 3, 4, 16, 32, False))
         if self.stem_flat_bwd:     # the transposed 4x4 gather pads 1 before / 2 after
             self.stem.ghat = self._padded(nb, self.stem.out_hw[0], self.stem.out_hw[1], self.stem.cout, 1, 2)
         last = self.blocks[-1]

@@ -305,3 +305,45 @@ def test_plan_from_released_checkpoint_matches_golden(bcosk_lib, golden_dir, tmp
     out_ema = plan_ema.explain(synth.to_bcos_input(gold["images_u8"]))
     torch.cuda.synchronize()
     assert not torch.allclose(out_ema["logits"], out["logits"])
+
+
+def test_grid_images_448_default_mode(bcosk_lib):
+    """The localisation metric's inputs (interpretability/analyses/localisation.py:313-398: 2x2 grids of 224^2 images = 448^2, one
+    explanation per grid cell's class): the default (contract) plan at 448^2 with uint8 input, several targets from one forward,
+    against the oracle - larger feature maps than any golden (M = 100 352 stem rows per image, ragged last tiles in layer4)."""
+    arch, S, nb = "resnet18", 448, 2
+    sd = synth.synth_state_dict(OR.resnet_state_shapes(arch), 0)
+    u8 = synth.synth_images_u8(nb, S, 3)
+    x6 = synth.to_bcos_input(u8)
+    om = OR.OracleResNet(arch, sd)
+    om.calibrate_bn(x6)
+    plan = ResNetPlan(arch, sd, nb, image_size=S, input_u8=True, device="cuda")
+    plan.capture()
+    targets = torch.tensor([[3, 7], [500, 999]], dtype=torch.int32)
+    out = plan.explain_targets(torch.from_numpy(u8), targets)
+    torch.cuda.synchronize()
+    # (like the golden tests: distance to the nearer of the reference arithmetic in fp32 and its fp64 evaluation - on these random-init
+    # nets the two differ by ~1e-3 of the map range themselves)
+    om64 = OR.OracleResNet(arch, {k: (v.double() if v.is_floating_point() else v) for k, v in om.sd.items()}) if hasattr(om, "sd") else None
+    for t in range(targets.shape[0]):
+        ref = OR.explain_batched(om.forward, x6, idx=targets[t].long())
+        m = OR.parity_metrics(out["logits"], out["contribution_map"][t], ref["logits"], ref["contribution_map"])
+        best = m["map_maxabs_over_range"]
+        if om64 is not None:
+            r64 = OR.explain_batched(om64.forward, x6.double(), idx=targets[t].long())
+            m64 = OR.parity_metrics(out["logits"], out["contribution_map"][t], r64["logits"].float(), r64["contribution_map"].float())
+            floor = OR.parity_metrics(ref["logits"], ref["contribution_map"], r64["logits"].float(), r64["contribution_map"].float())
+            print("448^2 target set", t, "vs fp64:", m64["map_maxabs_over_range"], "reference fp32 vs fp64:", floor["map_maxabs_over_range"])
+            best = min(best, m64["map_maxabs_over_range"])
+        print("448^2 target set", t, m)
+        assert m["argmax_equal"] and m["logit_rel_err"] <= 2e-3 and m["map_cos_min"] >= 0.999 and best <= 1e-3, (m, best)
+    # the one-plane throughput mode at this size: its flat-window launches (layer1 3x3, stem) do not fit 112- / 227-pixel rows and the
+    # plan falls back to the im2col launches (PlanBase._flat_fits)
+    thr = ResNetPlan(arch, sd, nb, image_size=S, input_u8=True, device="cuda", mode="throughput")
+    assert not thr.stem_flat and not any(getattr(o, "flat", False) for o in thr.fwd_ops + thr.bwd_ops)
+    o2 = thr.explain(torch.from_numpy(u8))
+    torch.cuda.synchronize()
+    ref = OR.explain_batched(om.forward, x6)
+    m = OR.parity_metrics(o2["logits"], o2["contribution_map"], ref["logits"], ref["contribution_map"])
+    print("448^2 throughput mode", m)
+    assert m["map_cos_min"] >= 0.97 and m["logit_rel_err"] <= 5e-2, m
