@@ -705,18 +705,21 @@ extern "C" int bcosk_pixel_sqsum(const void* x, int64_t rows, int32_t c, int32_t
   return BCOSK_OK;
 }
 
+// lanes that share one pixel in the direct pooling kernels: the largest power of two <= min(32, c / 8); every lane walks the 8-channel
+// groups g = lane, lane + lanes, ... < c / 8 (any channel count that is a multiple of 8: DenseNet-169 / -201 transitions have 320 / 448)
 static int lanes_per_pixel(int c) {
   const int g = c / 8;
-  if (c % 8) return 0;
-  if (g >= 32) return (g % 32 == 0) ? 32 : 0;
-  return (g & (g - 1)) == 0 ? g : 0;
+  if (c % 8 || g < 1) return 0;
+  int l = 1;
+  while (l * 2 <= g && l * 2 <= 32) l *= 2;
+  return l;
 }
 
 extern "C" int bcosk_avgpool_fwd(const void* x, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t planes, int32_t k,
                                  int32_t stride, int32_t pad, void* y, int32_t op, int32_t oq, int32_t dtype, float* sq,
                                  void* stream) {
   const int lpp = lanes_per_pixel(c);
-  if (!x || !y || lpp == 0) return set_error(BCOSK_EUNSUPPORTED, "avgpool_fwd: c/8 must be a power of two or a multiple of 32");
+  if (!x || !y || lpp == 0) return set_error(BCOSK_EUNSUPPORTED, "avgpool_fwd: c must be a positive multiple of 8");
   if (nb > 65535) return set_error(BCOSK_EUNSUPPORTED, "avgpool_fwd: batch too large for the grid");
   {
     // row-staged kernel: <= 32 lanes per pixel, k full input rows (all planes) fit shared memory

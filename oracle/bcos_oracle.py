@@ -369,7 +369,8 @@ class OracleResNet:
 # B-cosified DenseNet (torchvision skeleton; bcos/models/standard_models.py:56-63 DenseNetBcos: classifier (1x1 B-cos
 # conv) before global average pooling; features[3] (pool0) -> AvgPool2d(3,2,1), experiment_parameters.py:108-129)
 # ----------------------------------------------------------------------------------------------
-DENSENET_ARCH = {"densenet121": (32, (6, 12, 24, 16), 64)}
+DENSENET_ARCH = {"densenet121": (32, (6, 12, 24, 16), 64), "densenet169": (32, (6, 12, 32, 32), 64),
+                 "densenet201": (32, (6, 12, 48, 32), 64)}     # torchvision densenet.py: growth rate, block config, initial features
 
 
 def _dn_names(nblocks: int):

@@ -614,6 +614,25 @@ def test_gain_recomputed_from_relu_output(bcosk_lib, case):
     assert (a - b).abs().max() <= 2e-2 * b.abs().max()
 
 
+@pytest.mark.parametrize("c,planes,k,st,pad", [(320, 2, 2, 2, 0), (448, 1, 2, 2, 0), (40, 2, 3, 2, 1), (8, 1, 2, 2, 0), (1056, 2, 2, 2, 0)])
+def test_avgpool_any_channel_count(bcosk_lib, c, planes, k, st, pad):
+    """pooling kernels for channel counts that are neither a power of two x 8 nor a multiple of 256 (DenseNet-169 / -201 transitions:
+    320, 448, 896 channels)"""
+    g = torch.Generator().manual_seed(c)
+    nb, H = 2, 10
+    dt = torch.bfloat16
+    a = _rand_act(g, nb, H, H, c, planes)
+    oh = (H + 2 * pad - k) // st + 1
+    py = torch.zeros(nb, oh, oh, planes * c, dtype=dt)
+    psq = torch.zeros(1, nb * oh * oh)
+    ops = [O.AvgPoolFwdOp("pool", a.t, c, planes, k, st, pad, py, 1, psq)]
+    gy = _rand_act(g, nb, oh, oh, c, planes).t
+    gain = torch.rand(nb * H * H, c, generator=g).to(dt if planes == 1 else torch.float32)
+    gx = torch.zeros(nb, H, H, planes * c, dtype=dt)
+    ops.append(O.AvgPoolBwdMulOp("poolbwd", gy, c, planes, k, st, pad, gain, gx, 1))
+    print(_run_and_compare(ops, tol16=BF16_TOL if planes == 1 else 2e-4))
+
+
 def test_elementwise_kernels(bcosk_lib):
     g = torch.Generator().manual_seed(5)
     nb, S = 3, 32
