@@ -617,6 +617,120 @@ vit_attention_bwd_full_kernel(const T* __restrict__ qkv, int planes, const float
   }
 }
 
+// The same gradients for longer sequences (113..208 tokens: CLIP ViT-B/16 has 197), where two n x n fp32 blocks no longer fit shared memory:
+// nothing n x n is kept.  Pass 1 (a warp per query row) leaves the softmax statistics m_i, l_i and D_i = sum_j P_ij dP_ij; pass 2 (per
+// query row) and pass 3 (per key column) recompute s_ij, P_ij, dP_ij and dz_ij = P_ij (dP_ij - D_i) scale from q, k, v, g in shared
+// memory and reduce them through one per-warp row buffer.  3x the dot products of the block form, same formulas.
+template <typename T>
+__global__ void __launch_bounds__(256, 1)
+vit_attention_bwd_full_long_kernel(const T* __restrict__ qkv, int planes, const float* __restrict__ g, int n, int heads, float scale, T* __restrict__ out) {
+  extern __shared__ float sm[];
+  constexpr int LDB = VAT_D + 1;
+  float* sq_ = sm;                                  // [n][LDB] q
+  float* sk = sq_ + (size_t)n * LDB;                // k
+  float* sv = sk + (size_t)n * LDB;                 // v
+  float* sg = sv + (size_t)n * LDB;                 // g
+  float* sm_ = sg + (size_t)n * LDB;                // [n] row maximum of z
+  float* sl = sm_ + n;                              // [n] 1 / sum exp
+  float* sD = sl + n;                               // [n] sum_j P dP
+  const int nw = blockDim.x >> 5;
+  float* rowA = sD + n;                             // [nw][n] per-warp row buffers
+  float* rowB = rowA + (size_t)nw * n;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int hd = heads * VAT_D, pst = 3 * hd, ld = planes * pst;
+  const T* base = qkv + (size_t)b * n * ld + h * VAT_D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < n * (VAT_D / 8); i += blockDim.x) {
+    const int r = i / (VAT_D / 8), c8 = (i % (VAT_D / 8)) * 8;
+    float f[8];
+    load8_row<T>(base + (size_t)r * ld, planes, pst, c8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sq_[r * LDB + c8 + k] = f[k];
+    load8_row<T>(base + (size_t)r * ld + hd, planes, pst, c8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sk[r * LDB + c8 + k] = f[k];
+    load8_row<T>(base + (size_t)r * ld + 2 * hd, planes, pst, c8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sv[r * LDB + c8 + k] = f[k];
+  }
+  const float* gh = g + (size_t)b * n * hd + h * VAT_D;
+  for (int i = threadIdx.x; i < n * VAT_D; i += blockDim.x) sg[(i / VAT_D) * LDB + (i % VAT_D)] = __ldg(gh + (size_t)(i / VAT_D) * hd + (i % VAT_D));
+  __syncthreads();
+  auto dot = [&](const float* a, const float* c) {
+    float s = 0.f;
+#pragma unroll 16
+    for (int dd = 0; dd < VAT_D; ++dd) s = fmaf(a[dd], c[dd], s);
+    return s;
+  };
+  float* ra = rowA + (size_t)warp * n;
+  float* rb = rowB + (size_t)warp * n;
+  T* obase = out + (size_t)b * n * pst + h * VAT_D;
+  // ---- pass 1 + 2: a warp per query row i: statistics, then dz_i[.] -> dQ_i
+  for (int i = warp; i < n; i += nw) {
+    float mx = -INFINITY;
+    for (int j = lane; j < n; j += 32) {
+      const float s = dot(sq_ + i * LDB, sk + j * LDB) * scale;
+      ra[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < n; j += 32) {
+      const float e = expf(ra[j] - mx);
+      ra[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    float acc = 0.f;
+    for (int j = lane; j < n; j += 32) {
+      const float pj = ra[j] * inv;
+      const float dp = dot(sg + i * LDB, sv + j * LDB);
+      ra[j] = pj;
+      rb[j] = dp;
+      acc = fmaf(pj, dp, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) { sm_[i] = mx; sl[i] = inv; sD[i] = acc; }
+    for (int j = lane; j < n; j += 32) rb[j] = ra[j] * (rb[j] - acc) * scale;      // dz_i[j]
+    __syncwarp();
+    float q0 = 0.f, q1 = 0.f;
+    for (int t = 0; t < n; ++t) {
+      const float a = rb[t];
+      q0 = fmaf(a, sk[t * LDB + lane], q0);
+      q1 = fmaf(a, sk[t * LDB + lane + 32], q1);
+    }
+    obase[(size_t)i * pst + lane] = T(q0);
+    obase[(size_t)i * pst + lane + 32] = T(q1);
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- pass 3: a warp per key column j: P_.j and dz_.j recomputed -> dV_j, dK_j
+  for (int j = warp; j < n; j += nw) {
+    for (int i = lane; i < n; i += 32) {
+      const float s = dot(sq_ + i * LDB, sk + j * LDB) * scale;
+      const float pj = expf(s - sm_[i]) * sl[i];
+      const float dp = dot(sg + i * LDB, sv + j * LDB);
+      ra[i] = pj;
+      rb[i] = pj * (dp - sD[i]) * scale;
+    }
+    __syncwarp();
+    float v0 = 0.f, v1 = 0.f, k0 = 0.f, k1 = 0.f;
+    for (int t = 0; t < n; ++t) {
+      const float pw = ra[t], dz = rb[t];
+      v0 = fmaf(pw, sg[t * LDB + lane], v0);
+      v1 = fmaf(pw, sg[t * LDB + lane + 32], v1);
+      k0 = fmaf(dz, sq_[t * LDB + lane], k0);
+      k1 = fmaf(dz, sq_[t * LDB + lane + 32], k1);
+    }
+    obase[(size_t)j * pst + 2 * hd + lane] = T(v0);
+    obase[(size_t)j * pst + 2 * hd + lane + 32] = T(v1);
+    obase[(size_t)j * pst + hd + lane] = T(k0);
+    obase[(size_t)j * pst + hd + lane + 32] = T(k1);
+    __syncwarp();
+  }
+}
+
 }  // namespace bcosk
 
 using namespace bcosk;
@@ -772,8 +886,25 @@ extern "C" int bcosk_vit_attention_bwd_full(const void* qkv, int32_t planes, con
                                             float scale, void* out, int32_t dtype, void* stream) {
   if (!qkv || !g || !out || planes < 1 || planes > 3 || batch < 1) return set_error(BCOSK_EINVAL, "vit_attention_bwd_full: bad argument");
   if (dim_head != VAT_D) return set_error(BCOSK_EUNSUPPORTED, "vit_attention_bwd_full: dim_head must be 64");
-  const size_t smem = (2 * (size_t)n * n + 4 * (size_t)n * (VAT_D + 1)) * sizeof(float);
-  if (smem > 227 * 1024) return set_error(BCOSK_EUNSUPPORTED, "vit_attention_bwd_full: sequence too long for the shared-memory kernel");
+  size_t smem = (2 * (size_t)n * n + 4 * (size_t)n * (VAT_D + 1)) * sizeof(float);
+  if (smem > 227 * 1024) {
+    // longer sequences (CLIP ViT-B/16: 197 tokens): the recomputing form, nothing n x n in shared memory
+    smem = (4 * (size_t)n * (VAT_D + 1) + 3 * (size_t)n + 2 * 8 * (size_t)n) * sizeof(float);
+    if (smem > 227 * 1024) return set_error(BCOSK_EUNSUPPORTED, "vit_attention_bwd_full: sequence too long for the shared-memory kernels (n <= 208)");
+    if (dtype == BCOSK_DTYPE_BF16) {
+      BCOSK_CUDA_CHECK(cudaFuncSetAttribute(vit_attention_bwd_full_long_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      vit_attention_bwd_full_long_kernel<__nv_bfloat16><<<batch * heads, 256, smem, SV(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), planes, g, n, heads,
+                                                                                                 scale, reinterpret_cast<__nv_bfloat16*>(out));
+    } else if (dtype == BCOSK_DTYPE_F16) {
+      BCOSK_CUDA_CHECK(cudaFuncSetAttribute(vit_attention_bwd_full_long_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      vit_attention_bwd_full_long_kernel<__half><<<batch * heads, 256, smem, SV(stream)>>>(reinterpret_cast<const __half*>(qkv), planes, g, n, heads, scale,
+                                                                                          reinterpret_cast<__half*>(out));
+    } else {
+      return set_error(BCOSK_EINVAL, "vit_attention_bwd_full: dtype");
+    }
+    BCOSK_CUDA_CHECK(cudaGetLastError());
+    return BCOSK_OK;
+  }
   if (dtype == BCOSK_DTYPE_BF16) {
     BCOSK_CUDA_CHECK(cudaFuncSetAttribute(vit_attention_bwd_full_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     vit_attention_bwd_full_kernel<__nv_bfloat16><<<batch * heads, 256, smem, SV(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), planes, g, n, heads, scale,

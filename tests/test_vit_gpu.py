@@ -187,3 +187,51 @@ def test_clip_vit_fused_plan_matches_golden(bcosk_lib, golden_dir):
             assert cos >= 0.9
         assert torch.allclose(plan.embed(x6), out["embedding"], rtol=1e-5, atol=1e-6)
         del plan
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [113, 197, 208])
+def test_clip_vit_true_attention_backward_long_sequences(bcosk_lib, T):
+    """bcosk_vit_attention_bwd_full beyond 112 tokens (the recomputing kernel: no n x n block in shared memory) vs the emulator"""
+    g = torch.Generator().manual_seed(T)
+    dt, planes, nb, heads = torch.float16, 1, 2, 2
+    code = L.DTYPE_CODE["fp16"]
+    hd = heads * 64
+    qkv = _planes(g, (nb, T, 1, 3 * hd), planes, dt)
+    op = O.VitAttentionOp("attn.bwd_full.long", qkv, planes, torch.randn(nb, T, 1, hd, generator=g), nb, T, heads, 64, 64 ** -0.5, True,
+                          torch.zeros(nb, T, 1, 3 * hd, dtype=dt), code, True, True)
+    print("attention_bwd_full", T, _check(op, 2e-3, 2e-5))
+
+
+@pytest.mark.gpu
+def test_clip_vit_b16_geometry_197_tokens(bcosk_lib):
+    """CLIP ViT-B/16 geometry (196 patches + class token = 197 tokens: both query tiles of the attention kernels, the true attention
+    backward with 197 x 197 score blocks), two residual blocks, against the oracle in fp32 and fp64."""
+    from bcos_b200.engine import CLIPViTPlan
+    res, patch, width, layers, heads, out_dim = 224, 16, 768, 2, 12, 512
+    sd = synth.synth_state_dict(OR.clip_vit_state_shapes(res, patch, width, layers, out_dim), 1)
+    u8 = synth.synth_images_u8(2, res, 6)
+    x6 = synth.to_bcos_input(u8)
+    t = OR.clip_seed_direction(out_dim, 1)
+
+    def oracle(dtype):
+        o = OR.OracleCLIPViT({k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}, heads=heads)
+        xb = x6.to(dtype).clone().requires_grad_(True)
+        with torch.enable_grad():
+            emb = o.forward(xb, detach=True)
+            torch.nn.functional.cosine_similarity(emb, t.to(dtype)[None], dim=1).sum().backward(inputs=[xb])
+        return emb.detach().float(), (xb * xb.grad).sum(1).detach().float()
+
+    e32, c32 = oracle(torch.float32)
+    e64, c64 = oracle(torch.float64)
+    plan = CLIPViTPlan(sd, 2, heads=heads, device="cuda", input_u8=True)
+    assert plan.ntok == 197
+    out = plan.explain_direction(torch.from_numpy(u8), t)
+    torch.cuda.synchronize()
+    emb, cmap = out["embedding"].float().cpu(), out["contribution_map"].float().cpu()
+    rng = c32.flatten(1).max(1).values - c32.flatten(1).min(1).values
+    e_rel = ((emb - e32).abs().max() / e32.abs().max()).item()
+    mar = min(((cmap - c).abs().flatten(1).max(1).values / rng).max().item() for c in (c32, c64))
+    cos = torch.nn.functional.cosine_similarity(cmap.flatten(1).double(), c32.flatten(1).double()).min().item()
+    print(f"CLIP ViT-B/16 geometry, 2 blocks: embedding rel err {e_rel:.2e}, map cosine {cos:.8f}, max-abs/range {mar:.2e}")
+    assert e_rel <= 2e-3 and cos >= 0.999 and mar <= 1e-3
