@@ -218,6 +218,40 @@ def test_resnet18_train_step_matches_oracle(bcosk_lib, dtype, loss_scale, min_co
     assert math.isfinite(loss2)
 
 
+@pytest.mark.parametrize("arch,nb,min_cos,fc_cos", [("resnet50", 8, 0.85, 0.99), ("resnet34", 4, 0.98, 0.9999)])
+def test_other_resnets_train_step_matches_oracle(bcosk_lib, arch, nb, min_cos, fc_cos):
+    """bottleneck blocks (1x1 / strided 3x3 / 1x1, strided 1x1 shortcuts - the benchmarked ResNet-50) and the deeper basic-block net:
+    loss, every weight gradient and the updated running variances of one fine-tuning step against the oracle's autograd.
+    The random-init ResNet-50 with batch-statistics BN is ill conditioned: the reference arithmetic's own gradients differ by
+    1.5e-3 .. 4e-3 (relative) between fp32 and fp64 (ResNet-18: 7e-6), i.e. ~500x the sensitivity to rounding - one fp16 plane
+    (2^-11) leaves cosines of 0.87 (a BN weight) .. 0.97 there (independent of the loss scale: not a range effect) where ResNet-18 / -34 reach 0.998."""
+    S = 64
+    sd = synth.synth_state_dict(OR.resnet_state_shapes(arch), 0)
+    imgs = synth.synth_images_u8(nb, S, 2)
+    x6 = synth.to_bcos_input(imgs)
+    labels = torch.arange(nb) * 53 % 1000
+    om = OR.OracleResNet(arch, sd)
+    om.calibrate_bn(x6)
+    ref = OR.train_step_reference(om, x6, labels)
+    plan = ResNetTrainPlan(arch, sd, nb, dtype="fp16", device="cuda", image_size=S, loss_scale=65536.0)
+    loss = plan.train_step(torch.from_numpy(imgs), labels)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref["loss"])) <= 1e-3 * float(ref["loss"])
+    g = plan.gradients()
+    assert set(g) == set(ref["grads"])
+    cos = {}
+    for k, gr in ref["grads"].items():
+        a, b = g[k].cpu().double().flatten(), gr.double().flatten()
+        cos[k] = float(torch.dot(a, b) / (a.norm() * b.norm()))
+    worst = min(cos, key=cos.get)
+    print(f"REPORT train step {arch} fp16: min cos {cos[worst]:.5f} ({worst}) median {sorted(cos.values())[len(cos) // 2]:.5f} "
+          f"fc {cos['model.fc.linear.weight']:.6f}")
+    assert min(cos.values()) >= min_cos and cos["model.fc.linear.weight"] >= fc_cos
+    new = plan.state_dict()
+    for k, v in ref["running_var"].items():
+        assert _rel(new[k].cpu(), v) < 2e-3, k
+
+
 def test_captured_train_step_equals_eager(bcosk_lib):
     """ResNetTrainPlan.capture(): the whole step as one CUDA graph (whole-model AGC + AdamW launch, device-side Adam step counter,
     one operand-refresh launch) gives the same weights as the eager step; capturing does not advance the training state."""
