@@ -55,8 +55,9 @@ def test_densenet_variants(bcosk_lib, arch):
     _check(plan.explain(torch.from_numpy(u8)), om, OR.OracleDenseNet(arch, _d(sd)), x6, arch)
 
 
-def test_vit_small(bcosk_lib):
-    arch, nb, size = "simple_vit_s_patch16_224", 2, 96
+@pytest.mark.parametrize("arch,nb,size", [("simple_vit_s_patch16_224", 2, 96), ("simple_vit_ti_patch16_224", 1, 256)])
+def test_vit_small(bcosk_lib, arch, nb, size):
+    """SimpleViT-S, and ViT-Ti on a 256^2 input (256 tokens: three query tiles / more than 208 keys in the attention kernels)"""
     sd = synth.synth_state_dict(OR.vit_state_shapes(arch), 0)
     u8 = synth.synth_images_u8(nb, size, 4)
     x6 = synth.to_bcos_input(u8)

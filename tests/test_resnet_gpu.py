@@ -307,11 +307,12 @@ def test_plan_from_released_checkpoint_matches_golden(bcosk_lib, golden_dir, tmp
     assert not torch.allclose(out_ema["logits"], out["logits"])
 
 
-def test_grid_images_448_default_mode(bcosk_lib):
+@pytest.mark.parametrize("arch", ["resnet18", "resnet50"])
+def test_grid_images_448_default_mode(bcosk_lib, arch):
     """The localisation metric's inputs (interpretability/analyses/localisation.py:313-398: 2x2 grids of 224^2 images = 448^2, one
     explanation per grid cell's class): the default (contract) plan at 448^2 with uint8 input, several targets from one forward,
     against the oracle - larger feature maps than any golden (M = 100 352 stem rows per image, ragged last tiles in layer4)."""
-    arch, S, nb = "resnet18", 448, 2
+    S, nb = 448, 2
     sd = synth.synth_state_dict(OR.resnet_state_shapes(arch), 0)
     u8 = synth.synth_images_u8(nb, S, 3)
     x6 = synth.to_bcos_input(u8)
