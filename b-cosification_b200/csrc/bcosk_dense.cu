@@ -252,6 +252,82 @@ stem_im2col_u8_kernel(const uint8_t* __restrict__ x, int H, int W, int k, int st
   }
 }
 
+// fp16 patch matrix with a_scale = 2^-6 (what the plans use): no conversion instructions at all.  The k input rows are staged as one
+// word per pixel (R | G << 8 | B << 16 | 64 << 24; zero outside the image, zero columns for the padding), PRMT interleaves two of its
+// bytes with 0x64 into a half2 whose lanes are 1024 + byte, and one HFMA2 (x 2^-6, - 16) turns that into byte / 64 exactly - the
+// indicator byte 64 becomes 1.0.  (The generic kernel below spends ~220 instructions per 16-byte vector, 85 % issue-active, on
+// I2F / F2F conversions: profiles/r02_parity_mode.md.)
+__global__ void __launch_bounds__(256)
+stem_im2col_u8_h64_kernel(const uint8_t* __restrict__ x, int H, int W, int k, int stride, int pad, int op, int oq, SF6 mean, SF6 istd,
+                          __half* __restrict__ out, int kp, float* __restrict__ inv_norm) {
+  extern __shared__ uint8_t sm_raw[];
+  const int img = blockIdx.y, p = blockIdx.x;
+  const int WP = W + 2 * pad;
+  uint32_t* sw = reinterpret_cast<uint32_t*>(sm_raw);                 // [k][WP] packed pixels
+  float* sq = reinterpret_cast<float*>(sw + k * WP);                  // [k][W] sum_c xn^2 (0 for rows outside the image)
+  const uint8_t* xi = x + (size_t)img * 3 * H * W;
+  const int iy0 = p * stride - pad;
+  for (int e = threadIdx.x; e < k * WP; e += blockDim.x) {
+    const int dy = e / WP, xx = e - dy * WP;
+    const int iy = iy0 + dy, ix = xx - pad;
+    uint32_t wv = 0u;
+    float acc = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const uint32_t r = xi[((size_t)0 * H + iy) * W + ix], g = xi[((size_t)1 * H + iy) * W + ix], b = xi[((size_t)2 * H + iy) * W + ix];
+      wv = r | (g << 8) | (b << 16) | (64u << 24);
+      const uint32_t cv[3] = {r, g, b};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float xv = (float)cv[c] * (1.0f / 255.0f);
+        const float a = (xv - mean.v[c]) * istd.v[c], bb = ((1.0f - xv) - mean.v[c + 3]) * istd.v[c + 3];
+        acc = fmaf(a, a, acc);
+        acc = fmaf(bb, bb, acc);
+      }
+    }
+    sw[e] = wv;
+    if (ix >= 0 && ix < W) sq[dy * W + ix] = acc;
+  }
+  __syncthreads();
+  const int nvec = kp >> 3, ntap = k * k;
+  const long long row0 = ((long long)img * op + p) * oq;
+  {
+    const int v0 = threadIdx.x % nvec, qstep = blockDim.x / nvec;
+    int base[2];
+    bool live[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int t = v0 * 2 + h;
+      const int dy = t / k, dx = t - dy * k;
+      live[h] = t < ntap;
+      base[h] = live[h] ? dy * WP + dx : 0;
+    }
+    const __half2 sc = __floats2half2_rn(0.015625f, 0.015625f), off = __floats2half2_rn(-16.f, -16.f);
+    for (int q = threadIdx.x / nvec; q < oq; q += qstep) {
+      uint32_t w[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t px = live[h] ? sw[base[h] + q * stride] : 0u;
+        uint32_t lo = __byte_perm(px, 0x64646464u, 0x4140), hi = __byte_perm(px, 0x64646464u, 0x4342);
+        __half2 a = __hfma2(*reinterpret_cast<__half2*>(&lo), sc, off), b = __hfma2(*reinterpret_cast<__half2*>(&hi), sc, off);
+        w[2 * h] = *reinterpret_cast<uint32_t*>(&a);
+        w[2 * h + 1] = *reinterpret_cast<uint32_t*>(&b);
+      }
+      *reinterpret_cast<uint4*>(out + (row0 + q) * (long long)kp + v0 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  if (inv_norm != nullptr) {
+    for (int q = threadIdx.x; q < oq; q += blockDim.x) {
+      float acc = 0.f;
+      for (int dy = 0; dy < k; ++dy)
+        for (int dx = 0; dx < k; ++dx) {
+          const int ix = q * stride - pad + dx;
+          if (ix >= 0 && ix < W) acc += sq[dy * W + ix];
+        }
+      inv_norm[row0 + q] = 1.0f / sqrtf(acc + 1e-6f);
+    }
+  }
+}
+
 }  // namespace bcosk
 
 using namespace bcosk;
@@ -267,6 +343,13 @@ extern "C" int bcosk_stem_im2col_u8(const uint8_t* x, int32_t nb, int32_t h, int
   const size_t smem = (size_t)((k * 3 * w + 15) / 16) * 16 + (size_t)k * w * sizeof(float);
   if (smem > 48 * 1024) return set_error(BCOSK_EUNSUPPORTED, "stem_im2col_u8: image too wide for the shared-memory rows");
   dim3 grid(op, nb);
+  if (dtype == BCOSK_DTYPE_F16 && a_scale == 0.015625f) {
+    const size_t smem_h = (size_t)k * (w + 2 * pad) * 4 + (size_t)k * w * sizeof(float);
+    if (smem_h > 48 * 1024) return set_error(BCOSK_EUNSUPPORTED, "stem_im2col_u8: image too wide for the shared-memory rows");
+    stem_im2col_u8_h64_kernel<<<grid, 256, smem_h, SD(stream)>>>(x, h, w, k, stride, pad, op, oq, m, s, reinterpret_cast<__half*>(out), kp, inv_norm);
+    BCOSK_CUDA_CHECK(cudaGetLastError());
+    return BCOSK_OK;
+  }
   if (dtype == BCOSK_DTYPE_BF16)
     stem_im2col_u8_kernel<__nv_bfloat16><<<grid, 256, smem, SD(stream)>>>(x, h, w, k, stride, pad, op, oq, m, s, a_scale, reinterpret_cast<__nv_bfloat16*>(out), kp, inv_norm);
   else if (dtype == BCOSK_DTYPE_F16)
