@@ -340,12 +340,15 @@ __global__ void avgpool_bwd_mul_kernel(const T* __restrict__ gy, int nb, int h, 
 template <typename T>
 __global__ void __launch_bounds__(256)
 avgpool_fwd_rows_kernel(const T* __restrict__ x, int h, int w, int c, int planes, int k, int stride, int pad, T* __restrict__ y,
-                        int op, int oq, float* __restrict__ sq) {
+                        int op, int oq, float* __restrict__ sq, int split) {
   extern __shared__ __align__(128) uint8_t pool_smem[];
   __shared__ __align__(8) uint64_t bar;
-  const int img = blockIdx.y, p = blockIdx.x;
+  // `split` CTAs share an output row (each stages only the input pixels its outputs read: more CTAs per SM, more loads in flight)
+  const int img = blockIdx.y, p = blockIdx.x / split, part = blockIdx.x - p * split;
   const int ld = planes * c;                               // precision planes side by side in every pixel
-  const uint32_t row_bytes = (uint32_t)w * ld * sizeof(T);
+  const int q_lo = (int)((long long)oq * part / split), q_hi = (int)((long long)oq * (part + 1) / split);
+  const int x_lo = max(0, q_lo * stride - pad), x_hi = min(w, (q_hi - 1) * stride - pad + k);
+  const uint32_t row_bytes = (uint32_t)(x_hi - x_lo) * ld * sizeof(T);
   const int y0 = p * stride - pad;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
@@ -356,18 +359,18 @@ avgpool_fwd_rows_kernel(const T* __restrict__ x, int h, int w, int c, int planes
     mbar_arrive_expect_tx(&bar, total);
     for (int dy = 0; dy < k; ++dy) {
       const int yy = y0 + dy;
-      if (yy >= 0 && yy < h) bulk_load_1d(pool_smem + dy * row_bytes, x + ((size_t)img * h + yy) * w * ld, row_bytes, &bar);
+      if (yy >= 0 && yy < h) bulk_load_1d(pool_smem + dy * row_bytes, x + (((size_t)img * h + yy) * w + x_lo) * ld, row_bytes, &bar);
     }
   }
   __syncthreads();
   mbar_wait(&bar, 0);
   const int cg = c / 8;
   const float inv = 1.0f / (float)(k * k);
-  const int items = oq * cg;
+  const int items = (q_hi - q_lo) * cg;
   const int items_pad = (items + 31) & ~31;
   for (int it = threadIdx.x; it < items_pad; it += blockDim.x) {
     const bool valid = it < items;
-    const int q = it / cg, g = it - q * cg;
+    const int q = q_lo + it / cg, g = it % cg;
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -380,10 +383,10 @@ avgpool_fwd_rows_kernel(const T* __restrict__ x, int h, int w, int c, int planes
           if (xx < 0 || xx >= w) continue;
           // the tap's fp32 value first (sum of its planes: exact), then the running sum - the order F.avg_pool2d adds in
           float f[8];
-          unpack8<T>(*reinterpret_cast<const uint4*>(pool_smem + dy * row_bytes + ((size_t)xx * ld + g * 8) * sizeof(T)), f);
+          unpack8<T>(*reinterpret_cast<const uint4*>(pool_smem + dy * row_bytes + ((size_t)(xx - x_lo) * ld + g * 8) * sizeof(T)), f);
           for (int pl = 1; pl < planes; ++pl) {
             float f2[8];
-            unpack8<T>(*reinterpret_cast<const uint4*>(pool_smem + dy * row_bytes + ((size_t)xx * ld + pl * c + g * 8) * sizeof(T)), f2);
+            unpack8<T>(*reinterpret_cast<const uint4*>(pool_smem + dy * row_bytes + ((size_t)(xx - x_lo) * ld + pl * c + g * 8) * sizeof(T)), f2);
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] += f2[i];
           }
@@ -723,14 +726,18 @@ extern "C" int bcosk_avgpool_fwd(const void* x, int32_t nb, int32_t h, int32_t w
   if (nb > 65535) return set_error(BCOSK_EUNSUPPORTED, "avgpool_fwd: batch too large for the grid");
   {
     // row-staged kernel: <= 32 lanes per pixel, k full input rows (all planes) fit shared memory
-    const size_t smem = (size_t)k * w * planes * c * 2;
-    if (c / 8 <= 32 && (c / 8 & (c / 8 - 1)) == 0 && c % 8 == 0 && smem <= 100 * 1024 && op <= 65535) {
+    const size_t smem_row = (size_t)k * w * planes * c * 2;
+    if (c / 8 <= 32 && (c / 8 & (c / 8 - 1)) == 0 && c % 8 == 0 && smem_row <= 100 * 1024 && op <= 32767) {
+      // long rows: two or three CTAs per output row (<= ~44 KB each: five CTAs per SM instead of two)
+      const int split = smem_row > 88 * 1024 ? 3 : (smem_row > 44 * 1024 ? 2 : 1);
+      const int span = ((oq + split - 1) / split - 1) * stride + k + stride;          // input pixels one part reads (upper bound)
+      size_t smem = (size_t)k * (span < w ? span : w) * planes * c * 2;
       if (smem > 48 * 1024) {
         BCOSK_DTYPE_SWITCH(dtype, BCOSK_CUDA_CHECK(cudaFuncSetAttribute(avgpool_fwd_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                                          100 * 1024));)
       }
-      BCOSK_DTYPE_SWITCH(dtype, avgpool_fwd_rows_kernel<T><<<dim3(op, nb), 256, smem, S(stream)>>>(
-          reinterpret_cast<const T*>(x), h, w, c, planes, k, stride, pad, reinterpret_cast<T*>(y), op, oq, sq);)
+      BCOSK_DTYPE_SWITCH(dtype, avgpool_fwd_rows_kernel<T><<<dim3(op * split, nb), 256, smem, S(stream)>>>(
+          reinterpret_cast<const T*>(x), h, w, c, planes, k, stride, pad, reinterpret_cast<T*>(y), op, oq, sq, split);)
       BCOSK_CUDA_CHECK(cudaGetLastError());
       return BCOSK_OK;
     }

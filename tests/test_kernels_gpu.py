@@ -633,6 +633,18 @@ def test_avgpool_any_channel_count(bcosk_lib, c, planes, k, st, pad):
     print(_run_and_compare(ops, tol16=BF16_TOL if planes == 1 else 2e-4))
 
 
+@pytest.mark.parametrize("c,planes,W,k,st,pad", [(64, 2, 112, 3, 2, 1), (64, 3, 112, 3, 2, 1), (128, 2, 56, 2, 2, 0), (64, 1, 224, 3, 2, 1)])
+def test_avgpool_long_rows_split_across_ctas(bcosk_lib, c, planes, W, k, st, pad):
+    """row-staged pooling: rows whose k input rows exceed ~44 KB of shared memory are shared by two or three CTAs"""
+    g = torch.Generator().manual_seed(W + c)
+    nb, H = 1, 10
+    a = _rand_act(g, nb, H, W, c, planes)
+    oh, ow = (H + 2 * pad - k) // st + 1, (W + 2 * pad - k) // st + 1
+    py = torch.zeros(nb, oh, ow, planes * c, dtype=torch.bfloat16)
+    psq = torch.zeros(1, nb * oh * ow)
+    print(_run_and_compare([O.AvgPoolFwdOp("pool", a.t, c, planes, k, st, pad, py, 1, psq)], tol16=BF16_TOL if planes == 1 else 2e-4))
+
+
 def test_elementwise_kernels(bcosk_lib):
     g = torch.Generator().manual_seed(5)
     nb, S = 3, 32
